@@ -1,0 +1,65 @@
+"""Seeded synthetic cases shared by tests/golden/make_golden.py (which runs the reference on them)
+and the tests (which run the oracle and the CUDA path on them).  numpy Generators only, so the
+values are identical on every machine; nothing here depends on torch's RNG."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "bayesian-neural-nets_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import lbbnn_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MNIST_SIZES = [(784, 400), (400, 600), (600, 10)]
+NUM_BATCHES = 600
+
+
+def t(a, dtype=torch.float32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dtype)
+
+
+def lrt_layer_case(seed, batch, in_features, out_features, mu_range=0.2, spread_lambda=False):
+    """One layer: params by the reference's init ranges, x~U[0,1), eps~N(0,1), random upstream grad."""
+    rng = np.random.default_rng(seed)
+    p = O.init_lrt_params(rng, in_features, out_features, mu_range)
+    if spread_lambda:  # trained-like inclusion probabilities spanning (0,1)
+        p["lambdal"] = t(rng.normal(0.0, 2.0, size=(out_features, in_features)))
+    x = t(rng.uniform(0.0, 1.0, size=(batch, in_features)))
+    eps = t(rng.standard_normal(size=(batch, out_features)))
+    gout = t(rng.standard_normal(size=(batch, out_features)))
+    return {"p": p, "x": x, "eps": eps, "gout": gout}
+
+
+def lrt_net_case(seed, batch, sizes=MNIST_SIZES, classes=10):
+    rng = np.random.default_rng(seed)
+    layers = [O.init_lrt_params(rng, i, o) for i, o in sizes]
+    x = t(rng.uniform(0.0, 1.0, size=(batch, sizes[0][0])))
+    y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
+    eps = [t(rng.standard_normal(size=(batch, o))) for _, o in sizes]
+    return {"layers": layers, "x": x, "y": y, "eps": eps}
+
+
+def grad_digest(g, stride=97):
+    """Small, position-sensitive summary of a big gradient tensor: strided sample + moments."""
+    flat = g.detach().reshape(-1).double()
+    return {
+        "sample": flat[::stride].float().numpy(),
+        "sum": np.float64(flat.sum().item()),
+        "abs": np.float64(flat.abs().sum().item()),
+        "l2": np.float64(flat.pow(2).sum().sqrt().item()),
+    }
+
+
+def rel_err(a, b):
+    """max|a-b| / max|b|  -- the tolerance definition of SURVEY.md §4."""
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    den = b.abs().max().item()
+    if den == 0.0:
+        den = 1.0
+    return (a - b).abs().max().item() / den

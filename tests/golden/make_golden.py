@@ -1,0 +1,119 @@
+"""Generate tests/golden/*.npz by RUNNING THE REFERENCE'S OWN CLASSES on the seeded cases of
+tests/cases.py.  Needs /root/reference (build container only); the resulting fixtures travel.
+
+    python tests/golden/make_golden.py [lrt|mnf|mf|all]
+
+Every stored value is an output of reference code (AST-sliced, see ref_harness.py) under replayed
+noise; inputs are regenerated from the seeds by tests/cases.py, so the big MNIST-shape cases keep
+only outputs plus gradient digests.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+
+import cases as C  # noqa: E402
+import ref_harness as H  # noqa: E402
+
+
+def _load_params(layer, p):
+    with torch.no_grad():
+        for k, v in p.items():
+            getattr(layer, k).copy_(v)
+
+
+def _grads(layer, names):
+    return {k: getattr(layer, k).grad.detach().clone() for k in names}
+
+
+LRT_NAMES = ["weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"]
+
+
+def golden_lrt():
+    ns = H.load_reference_classes("LBBNN-GP-MF-LRT.py")
+    Layer, Net = ns["BayesianLinear"], ns["BayesianNetwork"]
+
+    # ---- single layer, odd sizes, full tensors ----------------------------------------------
+    out = {}
+    for tag, (seed, b, i, o, spread) in {
+        "a": (11, 9, 37, 23, False),
+        "b": (12, 5, 20, 1, True),      # sim-study shape (20 -> 1)
+        "c": (13, 33, 130, 10, True),
+    }.items():
+        case = C.lrt_layer_case(seed, b, i, o, spread_lambda=spread)
+        layer = Layer(i, o)
+        _load_params(layer, case["p"])
+        x = case["x"].clone().requires_grad_(True)
+        layer.train()
+        with H.replay(H.NoiseQueue([("normal", case["eps"])])):
+            act = layer(x, sample=True)
+        kl = layer.kl
+        loss = (act * case["gout"]).sum() + kl / C.NUM_BATCHES
+        loss.backward()
+        out[f"{tag}_meta"] = np.array([seed, b, i, o, int(spread)])
+        out[f"{tag}_act"] = act.detach().numpy()
+        out[f"{tag}_kl"] = np.float64(kl.item())
+        out[f"{tag}_dx"] = x.grad.numpy()
+        for k, g in _grads(layer, LRT_NAMES).items():
+            out[f"{tag}_d_{k}"] = g.numpy()
+        layer.eval()
+        with torch.no_grad():
+            mean_act = layer(case["x"], sample=False)
+            assert layer.kl == 0
+            with H.replay(H.NoiseQueue([("normal", case["eps"])])):
+                act_eval = layer(case["x"], sample=True, calculate_log_probs=True)
+        out[f"{tag}_act_mean"] = mean_act.numpy()
+        out[f"{tag}_act_eval_sample"] = act_eval.numpy()
+        out[f"{tag}_kl_eval"] = np.float64(layer.kl.item())
+    np.savez_compressed(os.path.join(HERE, "lrt_layer.npz"), **out)
+
+    # ---- MNIST-shape network, one training objective + grads -----------------------------------
+    out = {}
+    case = C.lrt_net_case(seed=0, batch=100)
+    net = Net()
+    for lay, p in zip((net.l1, net.l2, net.l3), case["layers"]):
+        _load_params(lay, p)
+    net.train()
+    with H.replay(H.NoiseQueue([("normal", e) for e in case["eps"]])):
+        logp = net(case["x"].view(100, 1, 28, 28), sample=True)
+    nll = torch.nn.functional.nll_loss(logp, case["y"], reduction="sum")
+    kl = net.kl()
+    loss = nll + kl / C.NUM_BATCHES
+    loss.backward()
+    out["logp"] = logp.detach().numpy()
+    out["nll"] = np.float64(nll.item())
+    out["kl"] = np.float64(kl.item())
+    out["loss"] = np.float64(loss.item())
+    for li, lay in enumerate((net.l1, net.l2, net.l3)):
+        for k, g in _grads(lay, LRT_NAMES).items():
+            d = C.grad_digest(g)
+            for dk, dv in d.items():
+                out[f"l{li}_{k}_{dk}"] = dv
+            if g.numel() <= 6000:
+                out[f"l{li}_{k}_full"] = g.numpy()
+    net.eval()
+    with torch.no_grad():
+        mean_logp = net(case["x"], sample=False)
+        with H.replay(H.NoiseQueue([("normal", e) for e in case["eps"]])):
+            samp_logp = net(case["x"], sample=True)
+    out["mean_logp"] = mean_logp.numpy()
+    out["mean_argmax"] = mean_logp.argmax(1).numpy()
+    out["eval_sample_logp"] = samp_logp.numpy()
+    out["eval_sample_argmax"] = samp_logp.argmax(1).numpy()
+    np.savez_compressed(os.path.join(HERE, "lrt_net_mnist.npz"), **out)
+    print("lrt golden written; loss", loss.item(), "kl", kl.item())
+
+
+if __name__ == "__main__":
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("lrt", "all"):
+        golden_lrt()
+    if what in ("mnf", "all") and "golden_mnf" in globals():
+        globals()["golden_mnf"]()
+    if what in ("mf", "all") and "golden_mf" in globals():
+        globals()["golden_mf"]()
