@@ -1,0 +1,10 @@
+"""lbbnn -- B200-native (sm_100a) implementation of the variational-layer hot path of
+LarsELund/Bayesian-Neural-Nets.  Python host code over the C-ABI of liblbbnn.so (include/lbbnn.h).
+CUDA only: importing this package without the built library raises."""
+from . import _capi
+from ._capi import LbbnnError, philox_normal, philox_uniform
+from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
+from .engine import LRTTrainer
+
+__all__ = ["BayesianLinear", "BayesianNetwork", "LayerConfig", "LRTTrainer", "LbbnnError", "lrt_linear",
+           "manual_seed", "philox_normal", "philox_uniform"]

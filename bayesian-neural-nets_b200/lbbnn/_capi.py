@@ -1,0 +1,159 @@
+"""ctypes binding of liblbbnn.so (include/lbbnn.h).  No torch types cross this boundary: tensors are
+passed as raw device pointers + sizes, the stream as the raw cudaStream_t handle.
+
+There is NO CPU fallback: if the library is missing this module raises at import, and every wrapper
+rejects non-CUDA tensors.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblbbnn.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: the CUDA extension has not been built "
+        "(run `python bayesian-neural-nets_b200/build.py` or __graft_entry__.build()). "
+        "lbbnn has no CPU or eager-PyTorch fallback.")
+
+lib = C.CDLL(LIB_PATH)
+
+VAR_REFERENCE, VAR_EXACT = 0, 1
+FLAG_SAMPLE, FLAG_RELU, FLAG_KL, FLAG_ACCUMULATE, FLAG_MASK_DX = 1, 2, 4, 8, 16
+
+
+class Priors(C.Structure):
+    _fields_ = [("mu", C.c_float), ("sigma", C.c_float), ("alpha", C.c_float),
+                ("bias_mu", C.c_float), ("bias_sigma", C.c_float)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("weight_mu", C.c_void_p), ("weight_rho", C.c_void_p), ("lambdal", C.c_void_p),
+                ("bias_mu", C.c_void_p), ("bias_rho", C.c_void_p), ("z", C.c_void_p),
+                ("in_features", C.c_int64), ("out_features", C.c_int64)]
+
+
+class LayerGrads(C.Structure):
+    _fields_ = [("weight_mu", C.c_void_p), ("weight_rho", C.c_void_p), ("lambdal", C.c_void_p),
+                ("bias_mu", C.c_void_p), ("bias_rho", C.c_void_p), ("z", C.c_void_p)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("eps", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_uint64),
+                ("step_dev", C.c_void_p), ("step_stride", C.c_uint64)]
+
+
+_P, _I64, _U64, _INT, _F, _SZ = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); kept in one table so tests can check every header symbol is bound
+SIGNATURES = {
+    "lbbnn_last_error": (C.c_char_p, []),
+    "lbbnn_abi_version": (_INT, []),
+    "lbbnn_device_ok": (_INT, []),
+    "lbbnn_philox_normal": (_INT, [_P, _I64, _U64, _U64, _P]),
+    "lbbnn_philox_uniform": (_INT, [_P, _I64, _U64, _U64, _P]),
+    "lbbnn_lrt_f32_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "lbbnn_lrt_f32_fwd": (_INT, [C.POINTER(Layer), _P, _I64, C.POINTER(Noise), C.POINTER(Priors), _INT, _INT,
+                                 _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_lrt_f32_bwd_params": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Noise), C.POINTER(Priors),
+                                        _INT, _INT, _P, _F, C.POINTER(LayerGrads), _P, _SZ, _P]),
+    "lbbnn_lrt_f32_bwd_input": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Noise), _INT, _INT, _P,
+                                       _P, _SZ, _P]),
+    "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P]),
+    "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P]),
+    "lbbnn_counter_inc": (_INT, [_P, _P]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)   # AttributeError here = header/library mismatch: fail loudly
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+class LbbnnError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise LbbnnError(f"liblbbnn error {rc}: {lib.lbbnn_last_error().decode()}")
+
+
+def ptr(t, dtype=torch.float32, allow_none=False):
+    """Raw device pointer of a contiguous CUDA tensor (the only kind the library accepts)."""
+    if t is None:
+        if allow_none:
+            return None
+        raise LbbnnError("required tensor is None")
+    if not t.is_cuda:
+        raise LbbnnError("lbbnn kernels take CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if t.dtype != dtype:
+        raise LbbnnError(f"expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise LbbnnError("tensor must be contiguous")
+    return t.data_ptr()
+
+
+def current_stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+_device_checked = False
+
+
+def require_device():
+    global _device_checked
+    if _device_checked:
+        return
+    if not torch.cuda.is_available():
+        raise LbbnnError("no CUDA device: lbbnn runs on B200 (sm_100a) only and has no CPU fallback")
+    if not lib.lbbnn_device_ok():
+        raise LbbnnError("the current CUDA device is not compute capability 10.x; liblbbnn is sm_100a-only")
+    _device_checked = True
+
+
+# ---- workspace: one growable buffer per (device, stream) -------------------------------------------
+_workspaces = {}
+
+
+def workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device(), current_stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            raise LbbnnError("workspace would have to grow during CUDA-graph capture; run one eager step first")
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def lrt_workspace_bytes(batch, in_features, out_features):
+    return int(lib.lbbnn_lrt_f32_workspace_bytes(batch, in_features, out_features))
+
+
+def make_layer(weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z=None):
+    out_f, in_f = weight_mu.shape
+    return Layer(ptr(weight_mu), ptr(weight_rho), ptr(lambdal), ptr(bias_mu), ptr(bias_rho),
+                 ptr(z, allow_none=True), in_f, out_f)
+
+
+def make_noise(eps=None, seed=0, stream_id=0, step_dev=None, step_stride=0):
+    return Noise(ptr(eps, allow_none=True), seed & (2 ** 64 - 1), stream_id & (2 ** 64 - 1),
+                 ptr(step_dev, torch.int64, allow_none=True), step_stride)
+
+
+def philox_normal(shape, seed, stream_id, device="cuda"):
+    """Materialise the native N(0,1) noise of stream (seed, stream_id) -- what a fused kernel draws."""
+    require_device()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    check(lib.lbbnn_philox_normal(ptr(out), out.numel(), seed, stream_id, current_stream()))
+    return out
+
+
+def philox_uniform(shape, seed, stream_id, device="cuda"):
+    require_device()
+    out = torch.empty(shape, dtype=torch.float32, device=device)
+    check(lib.lbbnn_philox_uniform(ptr(out), out.numel(), seed, stream_id, current_stream()))
+    return out

@@ -1,0 +1,175 @@
+"""Whole-step runner for the LRT network: forward, loss, backward and Adam as one CUDA-graph replay.
+
+Reference: the body of `train` (LBBNN-GP-MF-LRT.py:217-229) for one minibatch --
+net(data, sample=True), nll_loss(sum) + kl/NUM_BATCHES, backward, optimizer.step().
+The eager drop-in modules (lrt.py) launch the same kernels one Python call at a time; at MNIST shape
+the step is a few tens of microseconds of GPU work, so the Python/launch overhead dominates unless the
+sequence is captured once and replayed.  Parameters, gradients and Adam state live in flat buffers
+(one Adam launch); the nn.Parameters of the network are re-pointed at views of the flat buffer, so the
+module keeps working (state_dict, eager forward) while the trainer owns the storage.
+"""
+import torch
+
+from . import _capi as K
+from . import lrt as _lrt
+
+_PARAM_NAMES = ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho")
+
+
+def _pad4(n):
+    return (n + 3) // 4 * 4
+
+
+class LRTTrainer:
+    def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
+                 use_graph=True, inject_noise=False, process_group=None):
+        K.require_device()
+        self.net = net
+        self.layers = list(net.layers)
+        self.B = int(batch_size)
+        self.num_batches = int(num_batches)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.seed = _lrt.current_seed() if seed is None else int(seed)
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.rank = 0 if process_group is None else torch.distributed.get_rank(process_group)
+        dev = self.layers[0].weight_mu.device
+        if dev.type != "cuda":
+            raise K.LbbnnError("LRTTrainer needs the network on a CUDA device (no CPU fallback)")
+        self.device = dev
+
+        # ---- flat parameter / gradient / Adam-state storage ------------------------------------
+        offs, total = [], 0
+        for l in self.layers:
+            for name in _PARAM_NAMES:
+                p = getattr(l, name)
+                offs.append((l, name, total, p.numel(), p.shape))
+                total += _pad4(p.numel())
+        self.n_flat = total
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.no_grad():
+            for l, name, off, n, shape in offs:
+                p = getattr(l, name)
+                view = self.flat[off:off + n].view(shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.gflat[off:off + n].view(shape)
+
+        # ---- static activations / scratch --------------------------------------------------------
+        sizes = [(l.in_features, l.out_features) for l in self.layers]
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.x = torch.zeros(self.B, sizes[0][0], **f32)
+        self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.acts = [torch.zeros(self.B, o, **f32) for _, o in sizes]
+        self.stds = [torch.zeros(self.B, o, **f32) for _, o in sizes]
+        self.gbuf = [torch.zeros(self.B, o, **f32) for _, o in sizes]   # dL/d(pre-activation) per layer
+        self.eps_in = [torch.zeros(self.B, o, **f32) for _, o in sizes] if inject_noise else None
+        self.stats = torch.zeros(1 + len(sizes), **f32)                  # [nll, kl_1 .. kl_L]
+        nbytes = max(K.lrt_workspace_bytes(self.B, i, o) for i, o in sizes)
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.x_host = torch.zeros(self.B, sizes[0][0], dtype=torch.float32).pin_memory()
+        self.y_host = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        self.stats_host = torch.zeros(1 + len(sizes), dtype=torch.float32).pin_memory()
+        self.kernels_per_step = 0
+        self.graph = None
+        if use_graph:
+            self._capture()
+
+    # ---- the launch sequence ------------------------------------------------------------------------
+    def _noise(self, i):
+        if self.eps_in is not None:
+            return K.make_noise(self.eps_in[i])
+        # stream = layer index + step * n_layers (+ rank offset in the seed so ranks draw disjoint noise)
+        return K.make_noise(None, self.seed + 0x9E3779B97F4A7C15 * self.rank, i, self.step_dev, len(self.layers))
+
+    def _enqueue(self):
+        st = K.current_stream()
+        L = len(self.layers)
+        n_launch = 0
+        descs = [K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+                 for l in self.layers]
+        ws, wsn = self.ws.data_ptr(), self.ws.numel()
+        h = self.x
+        for i, l in enumerate(self.layers):
+            flags = K.FLAG_SAMPLE | K.FLAG_KL | (K.FLAG_RELU if i < L - 1 else 0)
+            K.check(K.lib.lbbnn_lrt_f32_fwd(descs[i], K.ptr(h), self.B, self._noise(i), l.cfg.priors, l.cfg.var_mode,
+                                            flags, K.ptr(self.acts[i]), K.ptr(self.stds[i]),
+                                            self.stats[1 + i:].data_ptr(), ws, wsn, st))
+            n_launch += 2
+            h = self.acts[i]
+        C = self.layers[-1].out_features
+        K.check(K.lib.lbbnn_logsoftmax_nll_f32(K.ptr(self.acts[-1]), K.ptr(self.y, torch.int64), self.B, C, None,
+                                               self.stats.data_ptr(), K.ptr(self.gbuf[-1]), 1.0, st))
+        n_launch += 1
+        klg = 1.0 / (self.num_batches * self.world)   # KL is replicated on every rank: its grad is added once
+        for i in reversed(range(L)):
+            l = self.layers[i]
+            xin = self.x if i == 0 else self.acts[i - 1]
+            g = l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad, l.bias_mu.grad, l.bias_rho.grad
+            K.check(K.lib.lbbnn_lrt_f32_bwd_params(
+                descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.stds[i]), self._noise(i), l.cfg.priors,
+                l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, K.LayerGrads(*[t.data_ptr() for t in g], None), ws, wsn, st))
+            n_launch += 1
+            if i > 0:
+                K.check(K.lib.lbbnn_lrt_f32_bwd_input(
+                    descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.stds[i]), self._noise(i),
+                    l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(self.gbuf[i - 1]), ws, wsn, st))
+                n_launch += 2
+        if self.pg is not None:
+            torch.distributed.all_reduce(self.gflat, group=self.pg)
+        K.check(K.lib.lbbnn_adam_f32(K.ptr(self.flat), K.ptr(self.gflat), K.ptr(self.exp_avg), K.ptr(self.exp_avg_sq),
+                                     self.n_flat, self.lr, self.betas[0], self.betas[1], self.eps,
+                                     K.ptr(self.step_dev, torch.int64), st))
+        K.check(K.lib.lbbnn_counter_inc(K.ptr(self.step_dev, torch.int64), st))
+        n_launch += 2
+        self.kernels_per_step = n_launch
+
+    def _capture(self):
+        # side stream warm-up (also sizes nothing: all buffers are preallocated), then capture
+        state = [t.clone() for t in (self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev)]
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for t, saved in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev), state):
+            t.copy_(saved)   # the warm-up step must not count as training
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._enqueue()
+
+    # ---- public API -----------------------------------------------------------------------------------
+    def step_device(self):
+        """One training step on the data already in self.x / self.y (device resident)."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue()
+
+    def step(self, x_host, y_host, read_loss=True):
+        """One training step from HOST tensors: pinned staging -> H2D -> step -> D2H of [nll, kl...]."""
+        self.x_host.copy_(x_host.reshape(self.x_host.shape))
+        self.y_host.copy_(y_host)
+        self.x.copy_(self.x_host, non_blocking=True)
+        self.y.copy_(self.y_host, non_blocking=True)
+        self.step_device()
+        if not read_loss:
+            return None
+        self.stats_host.copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        nll = float(self.stats_host[0])
+        kl = float(self.stats_host[1:].sum())
+        return {"nll": nll, "kl": kl, "loss": nll + kl / self.num_batches}
+
+    @property
+    def h2d_bytes_per_step(self):
+        return self.x_host.numel() * 4 + self.y_host.numel() * 8
+
+    @property
+    def d2h_bytes_per_step(self):
+        return self.stats_host.numel() * 4

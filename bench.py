@@ -1,0 +1,352 @@
+#!/usr/bin/env python3
+"""Benchmark of the variational-layer hot path (BASELINE.json metric: train samples/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Default workload = BASELINE.json configs[1]: LRT MNIST-shape MLP 784-400-600-10, batch 100 per GPU,
+one step = forward + loss + backward + Adam on one synthetic minibatch (LBBNN-GP-MF-LRT.py:217-229).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "bayesian-neural-nets_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np
+import torch
+
+SIZES = {"lrt_mnist": (784, 400, 600, 10)}
+BATCH = {"lrt_mnist": 100}
+NUM_BATCHES = 600
+POOL = 512          # distinct input batches: 512 x 313.6 KB = 160 MB > 126 MB L2
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            d = json.load(fh)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (NVML, polled from a thread during the timed region)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.002):
+        self.samples, self.period, self.stop_flag, self.ok = [], period, False, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:  # noqa: BLE001
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((time.perf_counter(), mhz, rs))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def start(self):
+        if self.ok:
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.ok:
+            self.th.join(timeout=1.0)
+
+    def summary(self, t0, t1):
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvml unavailable: " + self.err}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        mask = 0
+        for _, _, r in inside:
+            mask |= r
+        reasons = [n for b, n in self.REASONS.items() if mask & b and n != "gpu_idle"]
+        return {"sm_mhz": statistics.median([s[1] for s in inside]) if inside else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(inside)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic data: x ~ U[0,1) (MNIST ToTensor range), y ~ randint(10)
+# ------------------------------------------------------------------------------------------------
+def make_pool(batch, in_features, classes, seed):
+    rng = np.random.default_rng(seed)
+    x = torch.from_numpy(rng.random((POOL, batch, in_features), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, classes, size=(POOL, batch))).long()
+    return x, y
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference step, timed on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(workload, steps, warmup, budget_s=20.0):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lbbnn_oracle as O
+    sizes, B = SIZES[workload], BATCH[workload]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    rng = np.random.default_rng(0)
+    layers = [{k: v.clone().requires_grad_(True) for k, v in O.init_lrt_params(rng, i, o).items()}
+              for i, o in zip(sizes[:-1], sizes[1:])]
+    opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
+    x = torch.from_numpy(rng.random((8, B, sizes[0]), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, sizes[-1], size=(8, B))).long()
+
+    def one(i):
+        eps = [torch.randn(B, o) for o in sizes[1:]]            # LRT:174
+        opt.zero_grad(set_to_none=True)
+        loss, _, _, _ = O.lrt_net_loss(x[i % 8], y[i % 8], layers, eps, NUM_BATCHES)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        one(i)
+    t0 = time.perf_counter()
+    done = 0
+    for i in range(steps):
+        one(i)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "sample": f"{done} training steps (fwd+loss+bwd+Adam) of {workload} batch {B}, oracle port "
+                      f"(oracle/lbbnn_oracle.py) on torch-CPU fp32, {cores} threads",
+            "ms_per_step": dt / done * 1e3, "steps": done}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_steps(args.workload, args.steps, args.warmup, budget_s=120.0)
+    B = BATCH[args.workload]
+    line = {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.workload, 1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(workload, n_gpus):
+    sizes, B = SIZES[workload], BATCH[workload]
+    return {"workload": f"{workload}: LRT MLP {'-'.join(map(str, sizes))}, batch {B} per GPU, "
+                        f"fwd+loss+bwd+Adam, NUM_BATCHES={NUM_BATCHES}",
+            "batch_per_gpu": B, "global_batch": B * n_gpus,
+            "parallelism": "single GPU" if n_gpus == 1 else f"dp{n_gpus} (NCCL all-reduce of the flat gradient)",
+            "l2": f"inputs rotate through a pool of {POOL} distinct batches "
+                  f"({POOL * B * sizes[0] * 4 / 1e6:.0f} MB > 126 MB L2); parameters are the step's own working set"}
+
+
+# ------------------------------------------------------------------------------------------------
+# per-call timing of the step's C-ABI calls (cold L2), for the roofline of the dominant kernel
+# ------------------------------------------------------------------------------------------------
+def profile_calls(tr, reps=20):
+    """Time every C-ABI call of one training step on its own: CUDA events on the launching stream around
+    each call, L2 flushed (a 256 MB memset) before each, `reps` repetitions.  Returns a list of
+    {name, us, bytes} with the ALGORITHMIC bytes of DESIGN.md §Kernels."""
+    from lbbnn import _capi as K
+    B, L = tr.B, len(tr.layers)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device)
+    st = K.current_stream()
+    ws, wsn = tr.ws.data_ptr(), tr.ws.numel()
+    descs = [K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+             for l in tr.layers]
+    calls = []
+    for i, l in enumerate(tr.layers):
+        K_, N_ = l.in_features, l.out_features
+        xin = tr.x if i == 0 else tr.acts[i - 1]
+        flags = K.FLAG_SAMPLE | K.FLAG_KL | (K.FLAG_RELU if i < L - 1 else 0)
+        calls.append((f"lrt_f32_fwd[l{i + 1}] (partial+epilogue)", 12 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
+                      lambda i=i, l=l, xin=xin, flags=flags: K.lib.lbbnn_lrt_f32_fwd(
+                          descs[i], K.ptr(xin), B, tr._noise(i), l.cfg.priors, l.cfg.var_mode, flags,
+                          K.ptr(tr.acts[i]), K.ptr(tr.stds[i]), tr.stats[1 + i:].data_ptr(), ws, wsn, st)))
+        g = l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad, l.bias_mu.grad, l.bias_rho.grad
+        calls.append((f"lrt_f32_bwd_params[l{i + 1}]", 24 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
+                      lambda i=i, l=l, xin=xin, g=g: K.lib.lbbnn_lrt_f32_bwd_params(
+                          descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.stds[i]), tr._noise(i), l.cfg.priors,
+                          l.cfg.var_mode, K.FLAG_SAMPLE, None, 1.0 / NUM_BATCHES,
+                          K.LayerGrads(*[t.data_ptr() for t in g], None), ws, wsn, st)))
+        if i > 0:
+            calls.append((f"lrt_f32_bwd_input[l{i + 1}] (partial+epilogue)", 12 * K_ * N_ + 8 * B * N_ + 8 * B * K_,
+                          lambda i=i, l=l, xin=xin: K.lib.lbbnn_lrt_f32_bwd_input(
+                              descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.stds[i]), tr._noise(i),
+                              l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(tr.gbuf[i - 1]), ws, wsn, st)))
+    calls.append(("adam_f32 (flat)", 28 * tr.n_flat,
+                  lambda: K.lib.lbbnn_adam_f32(K.ptr(tr.flat), K.ptr(tr.gflat), K.ptr(tr.exp_avg),
+                                               K.ptr(tr.exp_avg_sq), tr.n_flat, 0.0, 0.9, 0.999, 1e-8,
+                                               K.ptr(tr.step_dev, torch.int64), st)))
+    out = []
+    for name, nbytes, fn in calls:
+        times = []
+        for _ in range(reps + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            K.check(fn())
+            e1.record()
+            e1.synchronize()
+            times.append(e0.elapsed_time(e1) * 1e3)
+        out.append({"name": name, "us": statistics.mean(times[2:]), "bytes": nbytes})
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import lbbnn
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    workload = args.workload
+    sizes, B = SIZES[workload], BATCH[workload]
+    torch.manual_seed(0)                       # identical initial parameters on every rank
+    lbbnn.manual_seed(1234)
+    net = lbbnn.BayesianNetwork(sizes).to(dev)
+    tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+
+    pool_x_host, pool_y_host = make_pool(B, sizes[0], sizes[-1], seed=1000 + rank)
+    pool_x_host, pool_y_host = pool_x_host.pin_memory(), pool_y_host.pin_memory()
+    pool_x, pool_y = pool_x_host.to(dev), pool_y_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") ---------------------------------------------------------
+    def dev_step(i):
+        tr.x.copy_(pool_x[i % POOL], non_blocking=True)
+        tr.y.copy_(pool_y[i % POOL], non_blocking=True)
+        tr.step_device()
+
+    for i in range(args.warmup):
+        dev_step(i)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        dev_step(args.warmup + i)
+    e1.record()
+    barrier()
+    t1 = time.perf_counter()
+    ms = e0.elapsed_time(e1)
+
+    # ---- end to end through the public API with host buffers ("e2e") ----------------------------------
+    for i in range(min(args.warmup, 5)):
+        tr.step(pool_x_host[i % POOL], pool_y_host[i % POOL])
+    barrier()
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        out = tr.step(pool_x_host[(i + 7) % POOL], pool_y_host[(i + 7) % POOL])
+    barrier()
+    te1 = time.perf_counter()
+    e2e_ms = (te1 - te0) * 1e3
+    sampler.stop()
+    clocks = sampler.summary(t0, te1)
+
+    if world > 1:
+        tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+        ms, e2e_ms = tms.tolist()
+    assert out["loss"] == out["loss"], "loss is NaN"
+
+    if rank == 0:
+        peaks = load_peaks()
+        prof = profile_calls(tr)
+        top = max(prof, key=lambda r: r["us"])
+        achieved = top["bytes"] / (top["us"] * 1e-6) / 1e9
+        step_bytes = sum(r["bytes"] for r in prof)
+        cpu = cpu_reference_steps(workload, steps=60, warmup=3, budget_s=15.0) if world == 1 else None
+        line = {
+            "metric": "train_samples_per_sec", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(workload, world),
+            "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
+                    "h2d_bytes_per_step": tr.h2d_bytes_per_step, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": tr.kernels_per_step * args.steps,
+            "kernels_per_step": tr.kernels_per_step,
+            "roofline": {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                         "peak_source": peaks["source"], "us_per_launch": top["us"], "bytes_per_launch": top["bytes"],
+                         "timing": "cold L2 (256 MB memset before each launch), CUDA events, mean of 20"},
+            "step_roofline": {"bytes_per_step": step_bytes, "hbm_floor_us": step_bytes / peaks["hbm_gbs"] / 1e3,
+                              "sum_of_calls_us_cold": sum(r["us"] for r in prof),
+                              "frac_of_hbm_floor": (step_bytes / peaks["hbm_gbs"] / 1e3) / (ms / args.steps * 1e3)},
+            "kernels": [{"name": r["name"], "us": round(r["us"], 2), "bytes": r["bytes"],
+                         "gbps": round(r["bytes"] / r["us"] / 1e3, 1)} for r in prof],
+            "clocks": clocks,
+            "last_loss": out["loss"],
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES))
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,146 @@
+/* liblbbnn -- C-ABI of the B200 (sm_100a) kernels behind the drop-in BayesianLinear layers.
+ *
+ * The reference (LarsELund/Bayesian-Neural-Nets) has no FFI: its boundary is the Python nn.Module
+ * surface of `BayesianLinear`.  The entry points below are what that surface binds
+ * to in this repo: each one replaces a block of eager ATen calls inside a reference method, cited
+ * as file:line (LRT = LBBNN-GP-MF-LRT.py, MNF = LBBNN-GP-MF-MNF.py, MF = LBBNN-GP-MF.py,
+ * flows2 = flows2.py).  INTEGRATION.md shows the ctypes binding a maintainer adds on the
+ * reference side.
+ *
+ * Conventions: plain device pointers, int64 sizes, row-major contiguous tensors, fp32 unless a
+ * name says bf16; no allocation and no host synchronisation inside any call (the caller passes
+ * outputs and workspace; *_workspace_bytes tells how much); every call enqueues on the given
+ * cudaStream_t (pass the raw handle; 0 = legacy default stream) and is safe to capture in a CUDA
+ * graph.  Return value 0 = ok, negative = error, message from lbbnn_last_error() (thread-local).
+ * Host (CPU) pointers are rejected: there is no CPU fallback.
+ */
+#ifndef LBBNN_H
+#define LBBNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBBNN_ABI_VERSION 1
+
+enum { LBBNN_OK = 0, LBBNN_ERR_INVALID = -1, LBBNN_ERR_CUDA = -2, LBBNN_ERR_UNSUPPORTED = -3 };
+
+/* variance of the masked weight: sigma^2 alpha^2 as the reference computes it (LRT:171, MNF:196)
+ * or the spike-and-slab variance alpha(sigma^2+(1-alpha)mu^2) of BASELINE.json's north_star */
+enum { LBBNN_VAR_REFERENCE = 0, LBBNN_VAR_EXACT = 1 };
+
+enum {
+  LBBNN_FLAG_SAMPLE = 1,      /* LRT sample branch (LRT:169-175); absent = mean branch (LRT:177-180) */
+  LBBNN_FLAG_RELU = 2,        /* fwd: write relu(act) (the F.relu of LRT:208-209 fused in) */
+  LBBNN_FLAG_KL = 4,          /* fwd: also reduce the layer's KL (LRT:182-194) into kl_out */
+  LBBNN_FLAG_ACCUMULATE = 8,  /* bwd: grads += instead of = */
+  LBBNN_FLAG_MASK_DX = 16     /* bwd: dx *= (x > 0), i.e. back through the relu that produced x */
+};
+
+typedef void* lbbnn_stream; /* cudaStream_t */
+
+#if defined(__GNUC__)
+#define LBBNN_API __attribute__((visibility("default")))
+#else
+#define LBBNN_API
+#endif
+
+/* fixed priors of the LRT/MNF layers (LRT:141-158; MNFsim:157-174 for the sim-study values) */
+typedef struct lbbnn_priors {
+  float mu, sigma, alpha, bias_mu, bias_sigma;
+} lbbnn_priors;
+
+/* variational parameters of one layer, the nn.Parameters of BayesianLinear (LRT:137-151):
+ * weight_mu, weight_rho, lambdal are (out,in); bias_mu, bias_rho are (out,).  z is MNF's
+ * multiplicative noise vector (in,) or NULL (MNF:197: mm(x*z, M^T) == mm(x, (M*z)^T)). */
+typedef struct lbbnn_layer {
+  const float* weight_mu;
+  const float* weight_rho;
+  const float* lambdal;
+  const float* bias_mu;
+  const float* bias_rho;
+  const float* z;
+  int64_t in_features, out_features;
+} lbbnn_layer;
+
+typedef struct lbbnn_layer_grads {
+  float* weight_mu;
+  float* weight_rho;
+  float* lambdal;
+  float* bias_mu;
+  float* bias_rho;
+  float* z; /* (in,) or NULL */
+} lbbnn_layer_grads;
+
+/* Noise source of one call.  eps != NULL: injected tensor, indexed like the output it perturbs
+ * (the parity tests feed the oracle's noise through this).  eps == NULL: native Philox4x32-10 with
+ * key `seed` and stream  stream_id + (step_dev ? *step_dev * step_stride : 0); step_dev is a device
+ * int64 so that a captured CUDA graph draws fresh noise on every replay. */
+typedef struct lbbnn_noise {
+  const float* eps;
+  uint64_t seed;
+  uint64_t stream_id;
+  const int64_t* step_dev;
+  uint64_t step_stride;
+} lbbnn_noise;
+
+LBBNN_API const char* lbbnn_last_error(void);
+LBBNN_API int lbbnn_abi_version(void);
+/* 1 if the current device is compute capability 10.x */
+LBBNN_API int lbbnn_device_ok(void);
+
+/* ---- noise --------------------------------------------------------------------------------
+ * Native noise is Philox4x32-10 keyed by (seed, stream_id, element); these two calls materialise
+ * exactly the values the fused kernels draw, so the CPU oracle can consume identical noise
+ * (replaces torch.randn LRT:174 / torch.bernoulli's uniform, flows2:209). */
+LBBNN_API int lbbnn_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t stream_id, lbbnn_stream s);
+LBBNN_API int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id, lbbnn_stream s);
+
+/* ---- LRT layer, fp32 SIMT path (parity mode) ---------------------------------------------------
+ * fwd replaces BayesianLinear.forward LRT:166-196 (alpha, sigma, M, V prologue; both mm's; eps;
+ * sqrt/FMA epilogue; closed-form KL).  noise: see lbbnn_noise (shape (batch,out)).  Outputs: act (batch,out); std_out (batch,out) = sqrt(var_b), kept for
+ * the backward (may be NULL when no backward follows); kl_out: one float (FLAG_KL).
+ * bwd_params / bwd_input replace autograd through the same lines (formulas: SURVEY.md §3.5).
+ *   gact   = dL/d(act before relu) (batch,out)
+ *   kl_grad_dev (device float or NULL) * kl_grad_host = dL/d(kl)
+ */
+LBBNN_API size_t lbbnn_lrt_f32_workspace_bytes(int64_t batch, int64_t in_features, int64_t out_features);
+
+LBBNN_API int lbbnn_lrt_f32_fwd(const lbbnn_layer* layer, const float* x, int64_t batch,
+                      const lbbnn_noise* noise,
+                      const lbbnn_priors* priors, int var_mode, int flags,
+                      float* act, float* std_out, float* kl_out,
+                      void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+LBBNN_API int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* layer, const float* x, int64_t batch,
+                             const float* gact, const float* std_saved,
+                             const lbbnn_noise* noise,
+                             const lbbnn_priors* priors, int var_mode, int flags,
+                             const float* kl_grad_dev, float kl_grad_host,
+                             const lbbnn_layer_grads* grads,
+                             void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+LBBNN_API int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* layer, const float* x, int64_t batch,
+                            const float* gact, const float* std_saved,
+                            const lbbnn_noise* noise,
+                            int var_mode, int flags, float* dx,
+                            void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+/* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
+ * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL. */
+LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
+                             float* logp, float* nll_sum, float* dlogits, float grad_scale, lbbnn_stream s);
+
+/* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
+ * step_dev: device int64 holding the number of steps ALREADY taken (t-1); lbbnn_counter_inc bumps it. */
+LBBNN_API int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                   float lr, float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s);
+LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBBNN_H */

@@ -1,0 +1,224 @@
+"""GPU parity tests of the LRT path: CUDA kernels (through the C-ABI) vs the CPU oracle on the same
+seeded inputs and the same injected noise, and vs the golden outputs of the reference itself.
+
+Tolerance (BASELINE.json north_star): max|a-b|/max|b| <= 1e-5 per tensor in fp32;
+masks / argmax predictions bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases as C
+import lbbnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+NAMES = ["weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"]
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import lbbnn
+    return lbbnn
+
+
+def _cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+def _oracle_layer(case, var_mode="reference", sample=True, dtype=torch.float32):
+    p = {k: v.to(dtype).clone().requires_grad_(True) for k, v in case["p"].items()}
+    x = case["x"].to(dtype).clone().requires_grad_(True)
+    act = O.lrt_forward(x, p, case["eps"].to(dtype), sample=sample, var_mode=var_mode)
+    kl = O.lrt_kl(p)
+    ((act * case["gout"].to(dtype)).sum() + kl / C.NUM_BATCHES).backward()
+    return act.detach(), kl.detach(), x.grad, {k: v.grad for k, v in p.items()}
+
+
+def _cuda_layer(lb, case, var_mode="reference", sample=True):
+    p = {k: v.cuda().requires_grad_(True) for k, v in case["p"].items()}
+    x = case["x"].cuda().requires_grad_(True)
+    cfg = lb.LayerConfig(var_mode=var_mode)
+    act, kl = lb.lrt_linear(x, p["weight_mu"], p["weight_rho"], p["lambdal"], p["bias_mu"], p["bias_rho"],
+                            eps=case["eps"].cuda(), cfg=cfg, sample=sample, want_kl=True)
+    ((act * case["gout"].cuda()).sum() + kl / C.NUM_BATCHES).backward()
+    return act.detach(), kl.detach(), x.grad, {k: v.grad for k, v in p.items()}
+
+
+SHAPES = [(11, 9, 37, 23, False), (12, 5, 20, 1, True), (13, 33, 130, 10, True),
+          (21, 100, 784, 400, False), (22, 1000, 400, 600, True), (23, 257, 600, 10, True), (24, 1, 64, 64, False)]
+
+
+@pytest.mark.parametrize("seed,b,i,o,spread", SHAPES)
+@pytest.mark.parametrize("var_mode", ["reference", "exact"])
+def test_layer_fwd_bwd_matches_oracle(lb, seed, b, i, o, spread, var_mode):
+    case = C.lrt_layer_case(seed, b, i, o, spread_lambda=spread)
+    ref = _oracle_layer(case, var_mode, dtype=torch.float64)      # fp64 truth
+    ref32 = _oracle_layer(case, var_mode)
+    got = _cuda_layer(lb, case, var_mode)
+    assert C.rel_err(got[0], ref[0]) < TOL, "activations"
+    assert abs(got[1].item() - ref[1].item()) / abs(ref[1].item()) < TOL, "kl"
+    assert C.rel_err(got[2], ref[2]) < TOL, "dx"
+    for k in NAMES:
+        assert C.rel_err(got[3][k], ref[3][k]) < TOL, k
+    # and no worse than ~the fp32 oracle itself is
+    assert C.rel_err(got[0], ref32[0]) < TOL
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_layer_matches_reference_golden(lb, tag):
+    g = np.load(os.path.join(C.GOLDEN, "lrt_layer.npz"))
+    seed, b, i, o, spread = (int(v) for v in g[f"{tag}_meta"])
+    case = C.lrt_layer_case(seed, b, i, o, spread_lambda=bool(spread))
+    act, kl, dx, grads = _cuda_layer(lb, case)
+    assert C.rel_err(act, g[f"{tag}_act"]) < TOL
+    assert abs(kl.item() - float(g[f"{tag}_kl"])) / abs(float(g[f"{tag}_kl"])) < TOL
+    assert C.rel_err(dx, g[f"{tag}_dx"]) < TOL
+    for k in NAMES:
+        assert C.rel_err(grads[k], g[f"{tag}_d_{k}"]) < TOL, k
+
+
+def test_mean_branch_and_eval_kl(lb):
+    case = C.lrt_layer_case(13, 33, 130, 10, spread_lambda=True)
+    g = np.load(os.path.join(C.GOLDEN, "lrt_layer.npz"))
+    layer = lb.BayesianLinear(130, 10).cuda()
+    with torch.no_grad():
+        for k, v in case["p"].items():
+            getattr(layer, k).copy_(v)
+    layer.eval()
+    with torch.no_grad():
+        mean = layer(case["x"].cuda(), sample=False)
+        assert layer.kl == 0
+        samp = layer(case["x"].cuda(), sample=True, calculate_log_probs=True, eps=case["eps"].cuda())
+    assert C.rel_err(mean, g["c_act_mean"]) < TOL
+    assert C.rel_err(samp, g["c_act_eval_sample"]) < TOL
+    assert abs(layer.kl.item() - float(g["c_kl_eval"])) / float(g["c_kl_eval"]) < TOL
+
+
+def _load_net(lb, case):
+    net = lb.BayesianNetwork().cuda()
+    with torch.no_grad():
+        for l, p in zip(net.layers, case["layers"]):
+            for k, v in p.items():
+                getattr(l, k).copy_(v)
+    return net
+
+
+def test_mnist_net_training_objective_matches_reference(lb):
+    g = np.load(os.path.join(C.GOLDEN, "lrt_net_mnist.npz"))
+    case = C.lrt_net_case(seed=0, batch=100)
+    net = _load_net(lb, case)
+    net.train()
+    logp = net(case["x"].cuda().view(100, 1, 28, 28), sample=True, eps=[e.cuda() for e in case["eps"]])
+    nll = F.nll_loss(logp, case["y"].cuda(), reduction="sum")
+    kl = net.kl()
+    loss = nll + kl / C.NUM_BATCHES
+    loss.backward()
+    assert C.rel_err(logp, g["logp"]) < TOL
+    for name, val in (("nll", nll), ("kl", kl), ("loss", loss)):
+        assert abs(val.item() - float(g[name])) / abs(float(g[name])) < TOL, name
+    for li, l in enumerate(net.layers):
+        for k in NAMES:
+            grad = getattr(l, k).grad
+            d = C.grad_digest(grad.cpu())
+            assert C.rel_err(d["sample"], g[f"l{li}_{k}_sample"]) < TOL, (li, k)
+            assert abs(d["l2"] - float(g[f"l{li}_{k}_l2"])) / float(g[f"l{li}_{k}_l2"]) < TOL, (li, k)
+            if f"l{li}_{k}_full" in g:
+                assert C.rel_err(grad, g[f"l{li}_{k}_full"]) < TOL, (li, k)
+
+
+def test_mnist_net_predictions_bit_exact(lb):
+    g = np.load(os.path.join(C.GOLDEN, "lrt_net_mnist.npz"))
+    case = C.lrt_net_case(seed=0, batch=100)
+    net = _load_net(lb, case)
+    net.eval()
+    with torch.no_grad():
+        mean_logp = net(case["x"].cuda(), sample=False)
+        samp = net(case["x"].cuda(), sample=True, eps=[e.cuda() for e in case["eps"]])
+    assert C.rel_err(mean_logp, g["mean_logp"]) < TOL
+    assert np.array_equal(mean_logp.argmax(1).cpu().numpy(), g["mean_argmax"])
+    assert np.array_equal(samp.argmax(1).cpu().numpy(), g["eval_sample_argmax"])
+
+
+def test_native_philox_noise_is_reproducible_and_normal(lb):
+    a = lb.philox_normal((1000, 400), seed=7, stream_id=3)
+    b = lb.philox_normal((1000, 400), seed=7, stream_id=3)
+    c = lb.philox_normal((1000, 400), seed=7, stream_id=4)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert abs(a.mean().item()) < 5e-3 and abs(a.std().item() - 1) < 5e-3
+    assert abs((a ** 4).mean().item() - 3) < 0.1          # kurtosis of N(0,1)
+    u = lb.philox_uniform((100000,), seed=1, stream_id=0)
+    assert 0 < u.min().item() and u.max().item() < 1 and abs(u.mean().item() - 0.5) < 5e-3
+    # odd length: the tail elements come from the same quads
+    assert torch.equal(lb.philox_normal((10,), 7, 3), a.flatten()[:10])
+
+
+@pytest.mark.parametrize("b,i,o", [(100, 784, 400), (33, 130, 10), (7, 37, 23)])
+def test_native_noise_matches_oracle_on_exported_eps(lb, b, i, o):
+    """The layer draws eps inside the kernel; exporting the same Philox stream and feeding it to the
+    oracle must give the same activations and gradients (fwd and bwd regenerate identical noise)."""
+    case = C.lrt_layer_case(31, b, i, o)
+    layer = lb.BayesianLinear(i, o).cuda()
+    with torch.no_grad():
+        for k, v in case["p"].items():
+            getattr(layer, k).copy_(v)
+    layer.train()
+    x = case["x"].cuda().requires_grad_(True)
+    act = layer(x, sample=True)
+    ((act * case["gout"].cuda()).sum() + layer.kl / C.NUM_BATCHES).backward()
+    seed, stream = layer.last_noise_key
+    case["eps"] = lb.philox_normal((b, o), seed, stream).cpu()
+    ref = _oracle_layer(case, dtype=torch.float64)
+    assert C.rel_err(act, ref[0]) < TOL
+    assert C.rel_err(x.grad, ref[2]) < TOL
+    for k in NAMES:
+        assert C.rel_err(getattr(layer, k).grad, ref[3][k]) < TOL, k
+
+
+def test_cpu_tensors_are_rejected(lb):
+    layer = lb.BayesianLinear(8, 4)
+    with pytest.raises(lb.LbbnnError):
+        layer(torch.zeros(2, 8), sample=True)
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph):
+    """Whole captured step (fwd, loss, bwd, Adam) vs oracle autograd + torch.optim.Adam, 3 steps."""
+    case = C.lrt_net_case(seed=5, batch=100)
+    net = _load_net(lb, case)
+    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph, inject_noise=True)
+    layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+    opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
+    rng = np.random.default_rng(99)
+    for step in range(3):
+        eps = [C.t(rng.standard_normal(size=tuple(e.shape))) for e in case["eps"]]
+        for buf, e in zip(tr.eps_in, eps):
+            buf.copy_(e)
+        out = tr.step(case["x"], case["y"])
+        opt.zero_grad()
+        loss, nll, kl, _ = O.lrt_net_loss(case["x"], case["y"], layers, eps, C.NUM_BATCHES)
+        loss.backward()
+        assert abs(out["nll"] - nll.item()) / abs(nll.item()) < 1e-4, step
+        assert abs(out["kl"] - kl.item()) / abs(kl.item()) < TOL, step
+        for li, (l, p) in enumerate(zip(net.layers, layers)):
+            for k in NAMES:
+                assert C.rel_err(getattr(l, k).grad, p[k].grad) < 5e-5, (step, li, k, "grad")
+                # Adam's first steps are ~lr*sign(g): drive torch's Adam with the trainer's own gradient so
+                # the optimizer kernel is compared exactly instead of amplifying 1e-6 gradient differences
+                p[k].grad = getattr(l, k).grad.detach().cpu().clone()
+        opt.step()
+        for li, (l, p) in enumerate(zip(net.layers, layers)):
+            for k in NAMES:
+                assert C.rel_err(getattr(l, k).data, p[k].data) < 2e-6, (step, li, k, "param")
+
+
+def test_trainer_native_noise_changes_every_replay(lb):
+    case = C.lrt_net_case(seed=6, batch=100)
+    net = _load_net(lb, case)
+    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=0.0, use_graph=True)
+    a = tr.step(case["x"], case["y"])["nll"]
+    b = tr.step(case["x"], case["y"])["nll"]
+    assert a != b          # lr = 0: only the Philox stream (keyed by the device step counter) changed
+    assert tr.step_dev.item() == 2
