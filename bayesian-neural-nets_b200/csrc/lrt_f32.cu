@@ -3,14 +3,15 @@
 // Replaces BayesianLinear.forward of LBBNN-GP-MF-LRT.py:166-196 (and the GEMM part of
 // LBBNN-GP-MF-MNF.py:190-206) and autograd through it.
 //
-// Forward  = split-K dual GEMM with the parameter prologue and the KL reduction fused into the
-//            weight-tile loader (each mu/rho/lambda element is read from HBM exactly once per
-//            m-tile and never materialised as M,V), followed by a distributed epilogue that
-//            sums the split partials in a fixed order (deterministic), adds the biases and applies
-//            sqrt / eps / FMA (/ relu).
-// Backward = dW kernel (dM = dE^T x, dV = dS^T x^2, contraction over the batch) whose epilogue
-//            applies the chain rule to (mu, rho, lambda) and adds the closed-form KL gradient, and
-//            a split-N dX kernel (dx = dE M + 2 x (dS V)) + epilogue (relu mask of the producer).
+// Structure (r01 ncu finding: transcendental chains fused into GEMM loaders/epilogues serialise at
+// 8 warps/SM; as separate elementwise passes they run at full occupancy on all SMs):
+//   prologue  elementwise over (mu,rho,lambda): M = alpha mu [z], V = sigma^2 alpha^2, KL partials
+//   fwd GEMM  split-K dual GEMM  E += x M^T, S += x^2 V^T  -> partials
+//   fwd epi   fixed-order sum of partials, + biases, sqrt / eps / FMA (/ relu); saves
+//             ds_factor = eps / (2 sqrt(var_b)) = d act / d var_b for the backward; finalises KL
+//   dW GEMM   dM = dE^T x, dV = dS^T x^2 (contraction over the batch), bias column sums
+//   finalize  elementwise chain rule (dM,dV) -> (dmu,drho,dlambda) + closed-form KL gradient
+//   dX GEMM   split-N  dx = dE M + 2 x (dS V) -> partials; epilogue sums (+ relu mask)
 #include "common.cuh"
 
 namespace lbbnn {
@@ -38,85 +39,125 @@ __device__ __forceinline__ float4 load4(const float* __restrict__ base, int64_t 
 }
 
 __device__ __forceinline__ void store4(float* __restrict__ base, int64_t row, int64_t col, int64_t nrows,
-                                       int64_t ncols, int64_t ld, bool vec, float4 v, bool accumulate) {
+                                       int64_t ncols, int64_t ld, bool vec, float4 v) {
   if (row >= nrows) return;
   float* p = base + row * ld + col;
   if (vec && col + 3 < ncols) {
-    if (accumulate) {
-      float4 o = *reinterpret_cast<float4*>(p);
-      v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-    }
     *reinterpret_cast<float4*>(p) = v;
   } else {
     const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (col + j < ncols) p[j] = accumulate ? p[j] + e[j] : e[j];
+      if (col + j < ncols) p[j] = e[j];
   }
 }
 
-// eps for elements (row, col..col+3) of a (rows, ld) tensor: injected or native Philox.
-__device__ __forceinline__ float4 eps4(const Noise& nz, int64_t row, int64_t col, int64_t nrows, int64_t ld,
-                                       bool vec) {
-  if (nz.ptr) return load4(nz.ptr, row, col, nrows, ld, ld, vec);
-  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (row >= nrows) return r;
-  const uint64_t e = (uint64_t)row * (uint64_t)ld + (uint64_t)col;
-  if ((e & 3u) == 0 && col + 3 < ld) {
-    float n[4];
-    philox_normal4(nz.seed, nz.stream, e >> 2, n);
-    r = make_float4(n[0], n[1], n[2], n[3]);
+// flat 4-wide access with a ragged tail
+__device__ __forceinline__ void loadq(const float* __restrict__ p, int64_t e0, int64_t n, bool vec, float out[4]) {
+  if (vec && e0 + 3 < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + e0));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
   } else {
-    if (col + 0 < ld) r.x = philox_normal1(nz.seed, nz.stream, e + 0);
-    if (col + 1 < ld) r.y = philox_normal1(nz.seed, nz.stream, e + 1);
-    if (col + 2 < ld) r.z = philox_normal1(nz.seed, nz.stream, e + 2);
-    if (col + 3 < ld) r.w = philox_normal1(nz.seed, nz.stream, e + 3);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (e0 + j < n) ? __ldg(p + e0 + j) : 0.f;
   }
-  return r;
 }
-
-// dS = G * eps / (2 std)  (SURVEY.md §3.5), zero where std is not positive (padding)
-__device__ __forceinline__ float ds_of(float g, float e, float sd) { return sd > 0.f ? g * e / (2.0f * sd) : 0.f; }
+// same, for buffers written earlier in the same launch sequence is fine too (ld.global.nc is only
+// unsafe within one kernel); partial buffers are read in a later kernel than the one writing them.
+__device__ __forceinline__ void storeq(float* __restrict__ p, int64_t e0, int64_t n, bool vec, const float v[4],
+                                       bool accumulate) {
+  if (vec && e0 + 3 < n) {
+    float4 o = make_float4(v[0], v[1], v[2], v[3]);
+    if (accumulate) {
+      const float4 c = *reinterpret_cast<const float4*>(p + e0);
+      o.x += c.x; o.y += c.y; o.z += c.z; o.w += c.w;
+    }
+    *reinterpret_cast<float4*>(p + e0) = o;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e0 + j < n) p[e0 + j] = accumulate ? p[e0 + j] + v[j] : v[j];
+  }
+}
 
 // ================================================================================================
-// forward: split-K partial dual GEMM with fused prologue + KL
+// prologue: M, V and the KL partial sums, elementwise over the (out,in) parameters
+// ================================================================================================
+struct PrologueArgs {
+  const float *mu, *rho, *lam, *z;
+  int64_t n, K;
+  float *M, *V;     // V may be NULL (mean branch)
+  double* kl_part;  // [gridDim.x] or NULL
+  int var_mode;
+  lbbnn_priors pri;
+};
+
+__global__ void __launch_bounds__(kThreads) lrt_f32_prologue(const PrologueArgs a) {
+  __shared__ float red[32];
+  const bool vec = (a.n % 4 == 0) && (a.K % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
+                   aligned16(a.M) && (a.V == nullptr || aligned16(a.V));
+  const int64_t nq = ceil_div(a.n, 4);
+  float kl = 0.f;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float mu[4], rho[4], lam[4], m[4], v[4];
+    loadq(a.mu, e0, a.n, vec, mu);
+    loadq(a.rho, e0, a.n, vec, rho);
+    loadq(a.lam, e0, a.n, vec, lam);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      m[j] = v[j] = 0.f;
+      if (e0 + j < a.n) {
+        const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
+        const float zk = a.z ? __ldg(a.z + (e0 + j) % a.K) : 1.0f;
+        const Moments mo = weight_moments(mu[j], sg, al, a.var_mode);
+        m[j] = mo.m * zk;
+        v[j] = mo.v;
+        if (a.kl_part) kl += kl_weight_elem(mu[j] * zk, sg, al, a.pri);
+      }
+    }
+    storeq(a.M, e0, a.n, vec, m, false);
+    if (a.V) storeq(a.V, e0, a.n, vec, v, false);
+  }
+  if (a.kl_part) {
+    const float s = block_sum(kl, red);
+    if (threadIdx.x == 0) a.kl_part[blockIdx.x] = (double)s;
+  }
+}
+
+// ================================================================================================
+// forward: split-K partial dual GEMM  E = x M^T,  S = x^2 V^T
 // ================================================================================================
 constexpr int F_BM = 128, F_BN = 64, F_BK = 16;
 
 struct FwdArgs {
-  const float *x, *mu, *rho, *lam, *z;
+  const float *x, *M, *V;
   int64_t B, K, N;
-  int chunks_per_split, splits;
-  float* part;      // [splits][2][B][N]
-  double* kl_part;  // [splits * gridDim.x]
-  int var_mode, want_kl, sample;
-  lbbnn_priors pri;
+  int chunks_per_split, splits, sample;
+  float* part;  // [splits][2][B][N]
 };
 
-__global__ void __launch_bounds__(kThreads) lrt_f32_fwd_partial(const FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) lrt_f32_fwd_partial(const FwdArgs a) {
   __shared__ __align__(16) float xs[F_BK][F_BM];
   __shared__ __align__(16) float xq[F_BK][F_BM];
   __shared__ __align__(16) float ms[F_BK][F_BN];
   __shared__ __align__(16) float vs[F_BK][F_BN];
-  __shared__ float red[32];
 
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;  // tx: 4 output features, ty: 8 batch rows
   const int64_t n0 = (int64_t)blockIdx.x * F_BN, m0 = (int64_t)blockIdx.y * F_BM;
   const int64_t kbeg = (int64_t)blockIdx.z * a.chunks_per_split * F_BK;
   const int64_t kend = min(a.K, kbeg + (int64_t)a.chunks_per_split * F_BK);
-  const bool vec = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam);
-  const bool do_kl = a.want_kl && blockIdx.y == 0;
+  const bool vec = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.M) && (a.V == nullptr || aligned16(a.V));
 
   float accE[8][4], accS[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) accE[i][j] = accS[i][j] = 0.f;
-  float kl = 0.f;
 
-  float4 xr[2], pm, pr, pl;
-  const int prow = tid >> 2, pkq = tid & 3;  // loader coordinates for the parameter tile
+  float4 xr[2], pm, pv;
+  const int prow = tid >> 2, pkq = (tid & 3) * 4;  // loader coordinates for the weight tiles
 
   auto gload = [&](int64_t k0) {
 #pragma unroll
@@ -124,11 +165,10 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_fwd_partial(const FwdArgs a)
       const int id = tid + i * kThreads;
       xr[i] = load4(a.x, m0 + (id >> 2), k0 + (id & 3) * 4, a.B, kend, a.K, vec);
     }
-    pm = load4(a.mu, n0 + prow, k0 + pkq * 4, a.N, kend, a.K, vec);
-    pr = load4(a.rho, n0 + prow, k0 + pkq * 4, a.N, kend, a.K, vec);
-    pl = load4(a.lam, n0 + prow, k0 + pkq * 4, a.N, kend, a.K, vec);
+    pm = load4(a.M, n0 + prow, k0 + pkq, a.N, kend, a.K, vec);
+    pv = a.sample ? load4(a.V, n0 + prow, k0 + pkq, a.N, kend, a.K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto sstore = [&](int64_t k0) {
+  auto sstore = [&]() {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int id = tid + i * kThreads;
@@ -140,22 +180,11 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_fwd_partial(const FwdArgs a)
         xq[kq + j][r] = e[j] * e[j];
       }
     }
-    const float mu[4] = {pm.x, pm.y, pm.z, pm.w}, rho[4] = {pr.x, pr.y, pr.z, pr.w}, lam[4] = {pl.x, pl.y, pl.z, pl.w};
-    const bool rowok = n0 + prow < a.N;
+    const float m[4] = {pm.x, pm.y, pm.z, pm.w}, v[4] = {pv.x, pv.y, pv.z, pv.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int64_t gk = k0 + pkq * 4 + j;
-      float m = 0.f, v = 0.f;
-      if (rowok && gk < kend) {
-        const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
-        const float zk = a.z ? __ldg(a.z + gk) : 1.0f;
-        const Moments mo = weight_moments(mu[j], sg, al, a.var_mode);
-        m = mo.m * zk;
-        v = a.sample ? mo.v : 0.f;
-        if (do_kl) kl += kl_weight_elem(mu[j] * zk, sg, al, a.pri);
-      }
-      ms[pkq * 4 + j][prow] = m;
-      vs[pkq * 4 + j][prow] = v;
+      ms[pkq + j][prow] = m[j];
+      vs[pkq + j][prow] = v[j];
     }
   };
 
@@ -163,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_fwd_partial(const FwdArgs a)
     gload(kbeg);
     for (int64_t k0 = kbeg; k0 < kend; k0 += F_BK) {
       __syncthreads();  // previous tile fully consumed
-      sstore(k0);
+      sstore();
       __syncthreads();
       if (k0 + F_BK < kend) gload(k0 + F_BK);  // prefetch next tile into registers
 #pragma unroll
@@ -194,13 +223,8 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_fwd_partial(const FwdArgs a)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int64_t gm = m0 + ty * 8 + i, gn = n0 + tx * 4;
-    store4(pe, gm, gn, a.B, a.N, a.N, vst, make_float4(accE[i][0], accE[i][1], accE[i][2], accE[i][3]), false);
-    if (a.sample)
-      store4(ps, gm, gn, a.B, a.N, a.N, vst, make_float4(accS[i][0], accS[i][1], accS[i][2], accS[i][3]), false);
-  }
-  if (do_kl) {
-    const float s = block_sum(kl, red);
-    if (tid == 0) a.kl_part[(int64_t)blockIdx.z * gridDim.x + blockIdx.x] = (double)s;
+    store4(pe, gm, gn, a.B, a.N, a.N, vst, make_float4(accE[i][0], accE[i][1], accE[i][2], accE[i][3]));
+    if (a.sample) store4(ps, gm, gn, a.B, a.N, a.N, vst, make_float4(accS[i][0], accS[i][1], accS[i][2], accS[i][3]));
   }
 }
 
@@ -211,80 +235,71 @@ struct FwdEpiArgs {
   const float *bias_mu, *bias_rho;
   Noise noise;
   int flags;
-  float *act, *std_out, *kl_out;
+  float *act, *dsf, *kl_out;
   const double* kl_part;
   int n_kl_part;
   lbbnn_priors pri;
 };
 
-__global__ void __launch_bounds__(kThreads) lrt_f32_fwd_epilogue(const FwdEpiArgs a) {
+constexpr int kEpiThreads = 128;
+
+__global__ void __launch_bounds__(kEpiThreads) lrt_f32_fwd_epilogue(const FwdEpiArgs a) {
   __shared__ double dred[32];
   Noise nz = a.noise;
   nz.resolve();
   const bool sample = a.flags & LBBNN_FLAG_SAMPLE;
   const int64_t total = a.B * a.N;
-  const bool vec = (a.N % 4 == 0) && aligned16(a.part) && aligned16(a.act) &&
-                   (a.std_out == nullptr || aligned16(a.std_out)) && (a.noise.ptr == nullptr || aligned16(a.noise.ptr));
+  const bool vec = (total % 4 == 0) && aligned16(a.part) && aligned16(a.act) && (a.dsf == nullptr || aligned16(a.dsf)) &&
+                   (nz.ptr == nullptr || aligned16(nz.ptr));
   const int64_t nquads = ceil_div(total, 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
     float E[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f};
-    const bool full = vec && e0 + 3 < total;
-    if (full) {
-      for (int s = 0; s < a.splits; ++s) {
-        const float4 pe = *reinterpret_cast<const float4*>(a.part + ((int64_t)s * 2 + 0) * total + e0);
-        E[0] += pe.x; E[1] += pe.y; E[2] += pe.z; E[3] += pe.w;
-        if (sample) {
-          const float4 ps = *reinterpret_cast<const float4*>(a.part + ((int64_t)s * 2 + 1) * total + e0);
-          S[0] += ps.x; S[1] += ps.y; S[2] += ps.z; S[3] += ps.w;
+    // fixed summation order over the splits; loads issued four splits at a time for memory parallelism
+    for (int s0 = 0; s0 < a.splits; s0 += 4) {
+      float pe[4][4], ps[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < a.splits) {
+          loadq(a.part + ((int64_t)(s0 + u) * 2 + 0) * total, e0, total, vec, pe[u]);
+          if (sample) loadq(a.part + ((int64_t)(s0 + u) * 2 + 1) * total, e0, total, vec, ps[u]);
         }
       }
-    } else {
-      for (int s = 0; s < a.splits; ++s)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (e0 + j < total) {
-            E[j] += a.part[((int64_t)s * 2 + 0) * total + e0 + j];
-            if (sample) S[j] += a.part[((int64_t)s * 2 + 1) * total + e0 + j];
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u < a.splits) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            E[j] += pe[u][j];
+            if (sample) S[j] += ps[u][j];
           }
-    }
-    if (sample) {
-      if (nz.ptr) {
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (e0 + j < total) ep[j] = nz.ptr[e0 + j];
-      } else {
-        philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+        }
       }
     }
-    float out[4], sd[4];
+    if (sample) {
+      if (nz.ptr) loadq(nz.ptr, e0, total, vec, ep);
+      else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+    }
+    float out[4], df[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      out[j] = sd[j] = 0.f;
+      out[j] = df[j] = 0.f;
       if (e0 + j < total) {
         const int64_t n = (e0 + j) % a.N;
         float v = E[j] + __ldg(a.bias_mu + n);
         if (sample) {
           const float sb = sigma_of(__ldg(a.bias_rho + n));
-          sd[j] = sqrtf(S[j] + sb * sb);
-          v = fmaf(sd[j], ep[j], v);
+          const float sd = sqrtf(S[j] + sb * sb);
+          v = fmaf(sd, ep[j], v);
+          df[j] = ep[j] / (2.0f * sd);  // d act / d var_b  (dS = G eps / (2 sqrt S))
         }
         out[j] = (a.flags & LBBNN_FLAG_RELU) ? fmaxf(v, 0.f) : v;
       }
     }
-    if (full) {
-      *reinterpret_cast<float4*>(a.act + e0) = make_float4(out[0], out[1], out[2], out[3]);
-      if (a.std_out && sample) *reinterpret_cast<float4*>(a.std_out + e0) = make_float4(sd[0], sd[1], sd[2], sd[3]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        if (e0 + j < total) {
-          a.act[e0 + j] = out[j];
-          if (a.std_out && sample) a.std_out[e0 + j] = sd[j];
-        }
-    }
+    storeq(a.act, e0, total, vec, out, false);
+    if (a.dsf && sample) storeq(a.dsf, e0, total, vec, df, false);
   }
-  // KL finalisation: fixed-order sum of the per-CTA partials in double + the bias term (LRT:185-186)
+  // KL finalisation: fixed-order sum of the prologue's per-block partials in double + the bias term
   if ((a.flags & LBBNN_FLAG_KL) && blockIdx.x == 0) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < a.n_kl_part; i += blockDim.x) acc += a.kl_part[i];
@@ -296,81 +311,76 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_fwd_epilogue(const FwdEpiArg
 }
 
 // ================================================================================================
-// backward wrt parameters: dM = dE^T x, dV = dS^T x^2 with fused chain rule + KL gradient
+// backward wrt parameters, GEMM part: dM = dE^T x, dV = dS^T x^2, bias column sums
 // ================================================================================================
-constexpr int W_BN = 64, W_BK = 64, W_BB = 16;
+constexpr int W_BN = 32, W_BK = 64, W_BB = 16;
 
 struct BwdWArgs {
-  const float *x, *g, *sd, *mu, *rho, *lam, *z, *bias_mu, *bias_rho;
-  Noise noise;
+  const float *x, *g, *dsf;
   int64_t B, K, N;
-  int var_mode, sample, accumulate;
-  const float* klg_dev;
-  float klg_host;
-  lbbnn_priors pri;
-  float *dmu, *drho, *dlam, *dbmu, *dbrho, *dz;
+  int sample;
+  float *dM, *dV;   // (N,K) each
+  float* colsum;    // [2][N]: sum_b dE, sum_b dS
 };
 
-__global__ void __launch_bounds__(kThreads) lrt_f32_bwd_params(const BwdWArgs a) {
+__global__ void __launch_bounds__(kThreads) lrt_f32_bwd_w_gemm(const BwdWArgs a) {
   __shared__ __align__(16) float ge[W_BB][W_BN];
   __shared__ __align__(16) float gs[W_BB][W_BN];
   __shared__ __align__(16) float xs[W_BB][W_BK];
   __shared__ __align__(16) float xq[W_BB][W_BK];
 
   const int tid = threadIdx.x;
-  const int tk = tid & 15, tn = tid >> 4;  // thread tile: 4 n x 4 k, lanes run along k (coalesced epilogue)
+  const int tk = tid & 15, tn = tid >> 4;  // thread tile: 2 n x 4 k, lanes run along k
   const int64_t n0 = (int64_t)blockIdx.x * W_BN, k0 = (int64_t)blockIdx.y * W_BK;
-  const bool vecn = (a.N % 4 == 0) && aligned16(a.g) && aligned16(a.sd) && (a.noise.ptr == nullptr || aligned16(a.noise.ptr));
-  const bool veck = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
-                    aligned16(a.dmu) && aligned16(a.drho) && aligned16(a.dlam);
-  const float klg = (a.klg_dev ? __ldg(a.klg_dev) : 1.0f) * a.klg_host;
-  Noise nz = a.noise;
-  nz.resolve();
+  const bool vecn = (a.N % 4 == 0) && aligned16(a.g) && (a.dsf == nullptr || aligned16(a.dsf));
+  const bool veck = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.dM) && aligned16(a.dV);
 
-  float accM[4][4], accV[4][4];
+  float accM[2][4], accV[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) accM[i][j] = accV[i][j] = 0.f;
-  float be[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};  // bias column sums (k-tile 0 only)
+  float be[4] = {0.f, 0.f, 0.f, 0.f}, bs[4] = {0.f, 0.f, 0.f, 0.f};
 
-  const int lb = tid >> 4, lq = (tid & 15) * 4;  // loader: row b, 4 columns
-  float4 rg, rs, rx;
+  const int gb = tid >> 3, gq = (tid & 7) * 4;   // G loader (threads 0..127): row b, 4 columns of the n-tile
+  const int xb = tid >> 4, xk = (tid & 15) * 4;  // x loader (all threads)
+  float4 rg = make_float4(0.f, 0.f, 0.f, 0.f), rs = rg, rx;
 
   auto gload = [&](int64_t b0) {
-    const int64_t b = b0 + lb;
-    const float4 g = load4(a.g, b, n0 + lq, a.B, a.N, a.N, vecn);
-    rg = g;
-    rs = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (a.sample) {
-      const float4 sd = load4(a.sd, b, n0 + lq, a.B, a.N, a.N, vecn);
-      const float4 ep = eps4(nz, b, n0 + lq, a.B, a.N, vecn);
-      rs = make_float4(ds_of(g.x, ep.x, sd.x), ds_of(g.y, ep.y, sd.y), ds_of(g.z, ep.z, sd.z), ds_of(g.w, ep.w, sd.w));
+    if (tid < 128) {
+      rg = load4(a.g, b0 + gb, n0 + gq, a.B, a.N, a.N, vecn);
+      rs = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.sample) {
+        const float4 f = load4(a.dsf, b0 + gb, n0 + gq, a.B, a.N, a.N, vecn);
+        rs = make_float4(rg.x * f.x, rg.y * f.y, rg.z * f.z, rg.w * f.w);
+      }
     }
-    rx = load4(a.x, b, k0 + lq, a.B, a.K, a.K, veck);
+    rx = load4(a.x, b0 + xb, k0 + xk, a.B, a.K, a.K, veck);
   };
 
   gload(0);
   for (int64_t b0 = 0; b0 < a.B; b0 += W_BB) {
     __syncthreads();
-    *reinterpret_cast<float4*>(&ge[lb][lq]) = rg;
-    *reinterpret_cast<float4*>(&gs[lb][lq]) = rs;
-    *reinterpret_cast<float4*>(&xs[lb][lq]) = rx;
-    *reinterpret_cast<float4*>(&xq[lb][lq]) = make_float4(rx.x * rx.x, rx.y * rx.y, rx.z * rx.z, rx.w * rx.w);
-    be[0] += rg.x; be[1] += rg.y; be[2] += rg.z; be[3] += rg.w;
-    bs[0] += rs.x; bs[1] += rs.y; bs[2] += rs.z; bs[3] += rs.w;
+    if (tid < 128) {
+      *reinterpret_cast<float4*>(&ge[gb][gq]) = rg;
+      *reinterpret_cast<float4*>(&gs[gb][gq]) = rs;
+      be[0] += rg.x; be[1] += rg.y; be[2] += rg.z; be[3] += rg.w;
+      bs[0] += rs.x; bs[1] += rs.y; bs[2] += rs.z; bs[3] += rs.w;
+    }
+    *reinterpret_cast<float4*>(&xs[xb][xk]) = rx;
+    *reinterpret_cast<float4*>(&xq[xb][xk]) = make_float4(rx.x * rx.x, rx.y * rx.y, rx.z * rx.z, rx.w * rx.w);
     __syncthreads();
     if (b0 + W_BB < a.B) gload(b0 + W_BB);
 #pragma unroll
     for (int b = 0; b < W_BB; ++b) {
-      const float4 e4 = *reinterpret_cast<const float4*>(&ge[b][tn * 4]);
-      const float4 s4 = *reinterpret_cast<const float4*>(&gs[b][tn * 4]);
+      const float2 e2 = *reinterpret_cast<const float2*>(&ge[b][tn * 2]);
+      const float2 s2 = *reinterpret_cast<const float2*>(&gs[b][tn * 2]);
       const float4 x4 = *reinterpret_cast<const float4*>(&xs[b][tk * 4]);
       const float4 q4 = *reinterpret_cast<const float4*>(&xq[b][tk * 4]);
-      const float ev[4] = {e4.x, e4.y, e4.z, e4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+      const float ev[2] = {e2.x, e2.y}, sv[2] = {s2.x, s2.y};
       const float xv[4] = {x4.x, x4.y, x4.z, x4.w}, qv[4] = {q4.x, q4.y, q4.z, q4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           accM[i][j] = fmaf(ev[i], xv[j], accM[i][j]);
@@ -378,35 +388,76 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_params(const BwdWArgs a)
         }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int64_t n = n0 + tn * 2 + i, kc = k0 + tk * 4;
+    store4(a.dM, n, kc, a.N, a.K, a.K, veck, make_float4(accM[i][0], accM[i][1], accM[i][2], accM[i][3]));
+    if (a.sample) store4(a.dV, n, kc, a.N, a.K, a.K, veck, make_float4(accV[i][0], accV[i][1], accV[i][2], accV[i][3]));
+  }
+  // bias column sums over the batch (k-tile 0 CTAs only)
+  if (blockIdx.y == 0) {
+    __syncthreads();
+    if (tid < 128) {
+      *reinterpret_cast<float4*>(&ge[gb][gq]) = make_float4(be[0], be[1], be[2], be[3]);
+      *reinterpret_cast<float4*>(&gs[gb][gq]) = make_float4(bs[0], bs[1], bs[2], bs[3]);
+    }
+    __syncthreads();
+    if (tid < W_BN && n0 + tid < a.N) {
+      float se = 0.f, ss = 0.f;
+#pragma unroll
+      for (int b = 0; b < W_BB; ++b) { se += ge[b][tid]; ss += gs[b][tid]; }
+      a.colsum[n0 + tid] = se;
+      a.colsum[a.N + n0 + tid] = ss;
+    }
+  }
+}
 
-  // ---- epilogue: chain rule through M = alpha mu z, V(sigma, alpha[, mu]) + KL gradient ------------
+// ================================================================================================
+// finalize: chain rule through M = alpha mu z, V(sigma, alpha[, mu]) + closed-form KL gradient
+// ================================================================================================
+struct FinalizeArgs {
+  const float *mu, *rho, *lam, *z, *bias_mu, *bias_rho;
+  const float *dM, *dV, *colsum;
+  int64_t N, K;
+  int var_mode, sample, accumulate;
+  const float* klg_dev;
+  float klg_host;
+  lbbnn_priors pri;
+  float *dmu, *drho, *dlam, *dbmu, *dbrho, *dz;
+};
+
+__global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs a) {
+  const int64_t n = a.N * a.K;
+  const bool vec = (n % 4 == 0) && (a.K % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
+                   aligned16(a.dM) && aligned16(a.dV) && aligned16(a.dmu) && aligned16(a.drho) && aligned16(a.dlam);
+  const float klg = (a.klg_dev ? __ldg(a.klg_dev) : 1.0f) * a.klg_host;
   const lbbnn_priors P = a.pri;
   const float inv_sp2 = 1.0f / (P.sigma * P.sigma);
-  float dzv[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t n = n0 + tn * 4 + i, kc = k0 + tk * 4;
-    if (n >= a.N || kc >= a.K) continue;
-    const float4 m4 = load4(a.mu, n, kc, a.N, a.K, a.K, veck);
-    const float4 r4 = load4(a.rho, n, kc, a.N, a.K, a.K, veck);
-    const float4 l4 = load4(a.lam, n, kc, a.N, a.K, a.K, veck);
-    const float mu[4] = {m4.x, m4.y, m4.z, m4.w}, rho[4] = {r4.x, r4.y, r4.z, r4.w}, lam[4] = {l4.x, l4.y, l4.z, l4.w};
-    float gm[4], gr[4], gl[4];
+  const int64_t nq = ceil_div(n, 4);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float mu[4], rho[4], lam[4], dM[4], dV[4] = {0.f, 0.f, 0.f, 0.f}, gm[4], gr[4], gl[4];
+    loadq(a.mu, e0, n, vec, mu);
+    loadq(a.rho, e0, n, vec, rho);
+    loadq(a.lam, e0, n, vec, lam);
+    loadq(a.dM, e0, n, vec, dM);
+    if (a.sample) loadq(a.dV, e0, n, vec, dV);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       gm[j] = gr[j] = gl[j] = 0.f;
-      if (kc + j >= a.K) continue;
+      if (e0 + j >= n) continue;
       const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
-      const float zk = a.z ? __ldg(a.z + kc + j) : 1.0f;
-      const float dM = accM[i][j] * zk, dV = accV[i][j];
-      float dmu = al * dM, dsg, dal;
+      const int64_t k = (e0 + j) % a.K;
+      const float zk = a.z ? __ldg(a.z + k) : 1.0f;
+      const float dMz = dM[j] * zk;
+      float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j];
       if (a.var_mode == LBBNN_VAR_REFERENCE) {
-        dsg = 2.0f * al * al * sg * dV;
-        dal = mu[j] * dM + 2.0f * al * sg * sg * dV;
+        dsg = 2.0f * al * al * sg * dV[j];
+        dal = mu[j] * dMz + 2.0f * al * sg * sg * dV[j];
       } else {
-        dmu += 2.0f * al * (1.0f - al) * mu[j] * dV;
-        dsg = 2.0f * al * sg * dV;
-        dal = mu[j] * dM + (sg * sg + (1.0f - 2.0f * al) * mu[j] * mu[j]) * dV;
+        dmu += 2.0f * al * (1.0f - al) * mu[j] * dV[j];
+        dsg = 2.0f * al * sg * dV[j];
+        dal = mu[j] * dMz + (sg * sg + (1.0f - 2.0f * al) * mu[j] * mu[j]) * dV[j];
       }
       if (klg != 0.f) {
         const float d = mu[j] * zk - P.mu;
@@ -414,44 +465,30 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_params(const BwdWArgs a)
         dsg += klg * al * (sg * inv_sp2 - 1.0f / sg);
         dal += klg * (logf(P.sigma / sg) - 0.5f + logf(al / P.alpha) + (sg * sg + d * d) * 0.5f * inv_sp2 -
                       logf((1.0f - al) / (1.0f - P.alpha)));
-        dzv[j] += klg * al * d * inv_sp2 * mu[j];
+        dzk += klg * al * d * inv_sp2 * mu[j];
       }
-      dzv[j] += al * mu[j] * accM[i][j];
       gm[j] = dmu;
       gr[j] = dsg * dsigma_drho(rho[j]);
       gl[j] = dal * al * (1.0f - al);
+      if (a.dz) atomicAdd(a.dz + k, dzk);  // MNF only; caller zeroes dz first
     }
-    store4(a.dmu, n, kc, a.N, a.K, a.K, veck, make_float4(gm[0], gm[1], gm[2], gm[3]), a.accumulate);
-    store4(a.drho, n, kc, a.N, a.K, a.K, veck, make_float4(gr[0], gr[1], gr[2], gr[3]), a.accumulate);
-    store4(a.dlam, n, kc, a.N, a.K, a.K, veck, make_float4(gl[0], gl[1], gl[2], gl[3]), a.accumulate);
+    storeq(a.dmu, e0, n, vec, gm, a.accumulate);
+    storeq(a.drho, e0, n, vec, gr, a.accumulate);
+    storeq(a.dlam, e0, n, vec, gl, a.accumulate);
   }
-  if (a.dz) {  // MNF: dz_k = sum_n (alpha mu dM' + KL term); caller zeroes dz first
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (k0 + tk * 4 + j < a.K) atomicAdd(a.dz + k0 + tk * 4 + j, dzv[j]);
-  }
-
-  // ---- bias gradients (k-tile 0 CTAs): column sums over the batch -----------------------------------
-  if (blockIdx.y == 0) {
-    __syncthreads();
-    *reinterpret_cast<float4*>(&ge[lb][lq]) = make_float4(be[0], be[1], be[2], be[3]);
-    *reinterpret_cast<float4*>(&gs[lb][lq]) = make_float4(bs[0], bs[1], bs[2], bs[3]);
-    __syncthreads();
-    if (tid < W_BN && n0 + tid < a.N) {
-      float se = 0.f, ss = 0.f;
-#pragma unroll
-      for (int b = 0; b < W_BB; ++b) { se += ge[b][tid]; ss += gs[b][tid]; }
-      const int64_t n = n0 + tid;
-      const float bm = __ldg(a.bias_mu + n), br = __ldg(a.bias_rho + n), sb = sigma_of(br);
-      float dbm = se, dsb = 2.0f * sb * ss;
+  // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186)
+  if (blockIdx.x == 0) {
+    for (int64_t i = threadIdx.x; i < a.N; i += blockDim.x) {
+      const float bm = __ldg(a.bias_mu + i), br = __ldg(a.bias_rho + i), sb = sigma_of(br);
+      float dbm = a.colsum[i], dsb = a.sample ? 2.0f * sb * a.colsum[a.N + i] : 0.f;
       if (klg != 0.f) {
         const float inv = 1.0f / (P.bias_sigma * P.bias_sigma);
         dbm += klg * (bm - P.bias_mu) * inv;
         dsb += klg * (sb * inv - 1.0f / sb);
       }
       const float dbr = dsb * dsigma_drho(br);
-      a.dbmu[n] = a.accumulate ? a.dbmu[n] + dbm : dbm;
-      a.dbrho[n] = a.accumulate ? a.dbrho[n] + dbr : dbr;
+      a.dbmu[i] = a.accumulate ? a.dbmu[i] + dbm : dbm;
+      a.dbrho[i] = a.accumulate ? a.dbrho[i] + dbr : dbr;
     }
   }
 }
@@ -462,14 +499,13 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_params(const BwdWArgs a)
 constexpr int X_BM = 128, X_BK = 64, X_BN = 16;
 
 struct BwdXArgs {
-  const float *x, *g, *sd, *mu, *rho, *lam, *z;
-  Noise noise;
+  const float *x, *g, *dsf, *M, *V;
   int64_t B, K, N;
-  int chunks_per_split, splits, var_mode, sample;
+  int chunks_per_split, splits, sample;
   float* part;  // [splits][B][K]
 };
 
-__global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_partial(const BwdXArgs a) {
+__global__ void __launch_bounds__(kThreads, 2) lrt_f32_bwd_x_partial(const BwdXArgs a) {
   __shared__ __align__(16) float ge[X_BN][X_BM];
   __shared__ __align__(16) float gs[X_BN][X_BM];
   __shared__ __align__(16) float ms[X_BN][X_BK];
@@ -480,8 +516,8 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_partial(const BwdX
   const int64_t k0 = (int64_t)blockIdx.x * X_BK, m0 = (int64_t)blockIdx.y * X_BM;
   const int64_t nbeg = (int64_t)blockIdx.z * a.chunks_per_split * X_BN;
   const int64_t nend = min(a.N, nbeg + (int64_t)a.chunks_per_split * X_BN);
-  const bool vecn = (a.N % 4 == 0) && aligned16(a.g) && aligned16(a.sd) && (a.noise.ptr == nullptr || aligned16(a.noise.ptr));
-  const bool veck = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.part);
+  const bool vecn = (a.N % 4 == 0) && aligned16(a.g) && (a.dsf == nullptr || aligned16(a.dsf));
+  const bool veck = (a.K % 4 == 0) && aligned16(a.x) && aligned16(a.M) && (a.V == nullptr || aligned16(a.V)) && aligned16(a.part);
 
   float accE[8][4], accS[8][4];
 #pragma unroll
@@ -489,30 +525,25 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_partial(const BwdX
 #pragma unroll
     for (int j = 0; j < 4; ++j) accE[i][j] = accS[i][j] = 0.f;
 
-  float4 rg[2], rs[2], pm, pr, pl;
+  float4 rg[2], rs[2], pm, pv;
   const int prow = tid >> 4, pkq = (tid & 15) * 4;
-  Noise nz = a.noise;
-  nz.resolve();
 
   auto gload = [&](int64_t nb) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int id = tid + i * kThreads;
       const int64_t b = m0 + (id >> 2), n = nb + (id & 3) * 4;
-      const float4 g = load4(a.g, b, n, a.B, nend, a.N, vecn);
-      rg[i] = g;
+      rg[i] = load4(a.g, b, n, a.B, nend, a.N, vecn);
       rs[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (a.sample) {
-        const float4 sd = load4(a.sd, b, n, a.B, nend, a.N, vecn);
-        const float4 ep = eps4(nz, b, n, a.B, a.N, vecn);
-        rs[i] = make_float4(ds_of(g.x, ep.x, sd.x), ds_of(g.y, ep.y, sd.y), ds_of(g.z, ep.z, sd.z), ds_of(g.w, ep.w, sd.w));
+        const float4 f = load4(a.dsf, b, n, a.B, nend, a.N, vecn);
+        rs[i] = make_float4(rg[i].x * f.x, rg[i].y * f.y, rg[i].z * f.z, rg[i].w * f.w);
       }
     }
-    pm = load4(a.mu, nb + prow, k0 + pkq, nend, a.K, a.K, veck);
-    pr = load4(a.rho, nb + prow, k0 + pkq, nend, a.K, a.K, veck);
-    pl = load4(a.lam, nb + prow, k0 + pkq, nend, a.K, a.K, veck);
+    pm = load4(a.M, nb + prow, k0 + pkq, nend, a.K, a.K, veck);
+    pv = a.sample ? load4(a.V, nb + prow, k0 + pkq, nend, a.K, a.K, veck) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  auto sstore = [&](int64_t nb) {
+  auto sstore = [&]() {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int id = tid + i * kThreads;
@@ -524,29 +555,15 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_partial(const BwdX
         gs[nq + j][r] = s[j];
       }
     }
-    const float mu[4] = {pm.x, pm.y, pm.z, pm.w}, rho[4] = {pr.x, pr.y, pr.z, pr.w}, lam[4] = {pl.x, pl.y, pl.z, pl.w};
-    float m[4], v[4];
-    const bool rowok = nb + prow < nend;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      m[j] = v[j] = 0.f;
-      const int64_t gk = k0 + pkq + j;
-      if (rowok && gk < a.K) {
-        const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
-        const Moments mo = weight_moments(mu[j], sg, al, a.var_mode);
-        m[j] = mo.m * (a.z ? __ldg(a.z + gk) : 1.0f);
-        v[j] = mo.v;
-      }
-    }
-    *reinterpret_cast<float4*>(&ms[prow][pkq]) = make_float4(m[0], m[1], m[2], m[3]);
-    *reinterpret_cast<float4*>(&vs[prow][pkq]) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(&ms[prow][pkq]) = pm;
+    *reinterpret_cast<float4*>(&vs[prow][pkq]) = pv;
   };
 
   if (nbeg < nend) {
     gload(nbeg);
     for (int64_t nb = nbeg; nb < nend; nb += X_BN) {
       __syncthreads();
-      sstore(nb);
+      sstore();
       __syncthreads();
       if (nb + X_BN < nend) gload(nb + X_BN);
 #pragma unroll
@@ -578,18 +595,37 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_partial(const BwdX
     const float4 x4 = load4(a.x, b, kc, a.B, a.K, a.K, veck);
     const float4 o = make_float4(fmaf(2.0f * x4.x, accS[i][0], accE[i][0]), fmaf(2.0f * x4.y, accS[i][1], accE[i][1]),
                                  fmaf(2.0f * x4.z, accS[i][2], accE[i][2]), fmaf(2.0f * x4.w, accS[i][3], accE[i][3]));
-    store4(part, b, kc, a.B, a.K, a.K, veck, o, false);
+    store4(part, b, kc, a.B, a.K, a.K, veck, o);
   }
 }
 
-__global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_epilogue(const float* __restrict__ part, int splits,
-                                                                       int64_t total, const float* __restrict__ x,
-                                                                       int mask, int accumulate, float* __restrict__ dx) {
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
-    float s = 0.f;
-    for (int i = 0; i < splits; ++i) s += part[(int64_t)i * total + e];
-    if (mask && !(x[e] > 0.f)) s = 0.f;
-    dx[e] = accumulate ? dx[e] + s : s;
+__global__ void __launch_bounds__(kEpiThreads) lrt_f32_bwd_x_epilogue(const float* __restrict__ part, int splits,
+                                                                      int64_t total, const float* __restrict__ x,
+                                                                      int mask, int accumulate, float* __restrict__ dx) {
+  const bool vec = (total % 4 == 0) && aligned16(part) && aligned16(x) && aligned16(dx);
+  const int64_t nq = ceil_div(total, 4);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, xv[4];
+    for (int s0 = 0; s0 < splits; s0 += 4) {
+      float p[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (s0 + u < splits) loadq(part + (int64_t)(s0 + u) * total, e0, total, vec, p[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (s0 + u < splits) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) s[j] += p[u][j];
+        }
+    }
+    if (mask) {
+      loadq(x, e0, total, vec, xv);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!(xv[j] > 0.f)) s[j] = 0.f;
+    }
+    storeq(dx, e0, total, vec, s, accumulate);
   }
 }
 
@@ -597,9 +633,9 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_input_epilogue(const flo
 struct Split { int chunks_per_split, splits; };
 
 Split pick_split(int64_t tiles, int64_t chunks) {
-  int64_t target = 2LL * sm_count();
+  const int64_t target = sm_count();
   int64_t want = tiles >= target ? 1 : ceil_div(target, tiles);
-  if (want > chunks) want = chunks;
+  if (want > chunks / 2) want = chunks / 2;  // at least two chunks per split: keep the prefetch pipeline busy
   if (want < 1) want = 1;
   Split s;
   s.chunks_per_split = (int)ceil_div(chunks, want);
@@ -614,10 +650,33 @@ Split dx_split(int64_t B, int64_t K, int64_t N) {
   return pick_split(ceil_div(B, X_BM) * ceil_div(K, X_BK), ceil_div(N, X_BN));
 }
 
+int64_t elementwise_blocks(int64_t n) {
+  int64_t b = ceil_div(ceil_div(n, 4), kThreads);
+  const int64_t cap = 16LL * sm_count();
+  return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
 size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
-size_t fwd_part_bytes(int64_t B, int64_t K, int64_t N) { return align_up((size_t)fwd_split(B, K, N).splits * 2 * B * N * sizeof(float)); }
-size_t kl_part_bytes(int64_t B, int64_t K, int64_t N) { return align_up((size_t)fwd_split(B, K, N).splits * ceil_div(N, F_BN) * sizeof(double)); }
-size_t dx_part_bytes(int64_t B, int64_t K, int64_t N) { return align_up((size_t)dx_split(B, K, N).splits * B * K * sizeof(float)); }
+
+// workspace layout: [ M | V | kl partials | GEMM scratch (fwd partials / dM,dV,colsum / dx partials) ]
+struct WsLayout {
+  size_t off_m, off_v, off_kl, off_scratch, total;
+};
+WsLayout ws_layout(int64_t B, int64_t K, int64_t N) {
+  WsLayout w;
+  const size_t nk = align_up((size_t)N * K * sizeof(float));
+  w.off_m = 0;
+  w.off_v = nk;
+  w.off_kl = 2 * nk;
+  w.off_scratch = w.off_kl + align_up((size_t)elementwise_blocks(N * K) * sizeof(double));
+  const size_t fwd = (size_t)fwd_split(B, K, N).splits * 2 * B * N * sizeof(float);
+  const size_t dw = 2 * nk + align_up((size_t)2 * N * sizeof(float));
+  const size_t dx = (size_t)dx_split(B, K, N).splits * B * K * sizeof(float);
+  size_t scratch = fwd > dw ? fwd : dw;
+  if (dx > scratch) scratch = dx;
+  w.total = w.off_scratch + align_up(scratch) + 256;
+  return w;
+}
 
 int check_layer(const lbbnn_layer* L) {
   LBBNN_REQUIRE(L != nullptr, "layer is NULL");
@@ -627,6 +686,17 @@ int check_layer(const lbbnn_layer* L) {
   return LBBNN_OK;
 }
 
+int launch_prologue(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, bool want_v, bool want_kl, float* M,
+                    float* V, double* kl_part, cudaStream_t st) {
+  PrologueArgs pa;
+  pa.mu = L->weight_mu; pa.rho = L->weight_rho; pa.lam = L->lambdal; pa.z = L->z;
+  pa.n = L->in_features * L->out_features; pa.K = L->in_features;
+  pa.M = M; pa.V = want_v ? V : nullptr; pa.kl_part = want_kl ? kl_part : nullptr;
+  pa.var_mode = var_mode; pa.pri = *pri;
+  lrt_f32_prologue<<<(unsigned)elementwise_blocks(pa.n), kThreads, 0, st>>>(pa);
+  return check_launch("lrt_f32_prologue");
+}
+
 }  // namespace
 }  // namespace lbbnn
 
@@ -634,33 +704,39 @@ using namespace lbbnn;
 
 extern "C" size_t lbbnn_lrt_f32_workspace_bytes(int64_t B, int64_t K, int64_t N) {
   if (B <= 0 || K <= 0 || N <= 0) return 0;
-  size_t fwd = fwd_part_bytes(B, K, N) + kl_part_bytes(B, K, N);
-  size_t bwd = dx_part_bytes(B, K, N);
-  return (fwd > bwd ? fwd : bwd) + 256;
+  return ws_layout(B, K, N).total;
+}
+
+extern "C" size_t lbbnn_lrt_f32_mv_bytes(int64_t K, int64_t N) {
+  if (K <= 0 || N <= 0) return 0;
+  return 2 * align_up((size_t)N * K * sizeof(float));
 }
 
 extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B, const lbbnn_noise* nz,
-                                 const lbbnn_priors* pri, int var_mode, int flags, float* act,
-                                 float* std_out, float* kl_out, void* ws, size_t ws_bytes, lbbnn_stream s) {
+                                 const lbbnn_priors* pri, int var_mode, int flags, float* act, float* ds_factor,
+                                 float* kl_out, float* mv_cache, void* ws, size_t ws_bytes, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;
   LBBNN_REQUIRE(x && act && B > 0, "x/act NULL or empty batch");
   LBBNN_REQUIRE(pri != nullptr, "priors NULL");
   LBBNN_REQUIRE(var_mode == LBBNN_VAR_REFERENCE || var_mode == LBBNN_VAR_EXACT, "bad var_mode %d", var_mode);
   LBBNN_REQUIRE(!(flags & LBBNN_FLAG_KL) || kl_out, "FLAG_KL needs kl_out");
   const int64_t K = L->in_features, N = L->out_features;
-  LBBNN_REQUIRE(ws && ws_bytes >= lbbnn_lrt_f32_workspace_bytes(B, K, N), "workspace too small (%zu < %zu)", ws_bytes,
-                lbbnn_lrt_f32_workspace_bytes(B, K, N));
-  const Split sp = fwd_split(B, K, N);
+  const WsLayout w = ws_layout(B, K, N);
+  LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small (%zu < %zu)", ws_bytes, w.total);
+  const bool sample = flags & LBBNN_FLAG_SAMPLE, want_kl = flags & LBBNN_FLAG_KL;
   cudaStream_t st = (cudaStream_t)s;
+  char* base = (char*)ws;
+  float* M = mv_cache ? mv_cache : (float*)(base + w.off_m);
+  float* V = mv_cache ? (float*)((char*)mv_cache + align_up((size_t)N * K * sizeof(float))) : (float*)(base + w.off_v);
+  double* kl_part = (double*)(base + w.off_kl);
+  if (int rc = launch_prologue(L, pri, var_mode, sample, want_kl, M, V, kl_part, st)) return rc;
 
+  const Split sp = fwd_split(B, K, N);
   FwdArgs fa;
-  fa.x = x; fa.mu = L->weight_mu; fa.rho = L->weight_rho; fa.lam = L->lambdal; fa.z = L->z;
+  fa.x = x; fa.M = M; fa.V = sample ? V : nullptr;
   fa.B = B; fa.K = K; fa.N = N;
-  fa.chunks_per_split = sp.chunks_per_split; fa.splits = sp.splits;
-  fa.part = (float*)ws;
-  fa.kl_part = (double*)((char*)ws + fwd_part_bytes(B, K, N));
-  fa.var_mode = var_mode; fa.want_kl = (flags & LBBNN_FLAG_KL) ? 1 : 0; fa.sample = (flags & LBBNN_FLAG_SAMPLE) ? 1 : 0;
-  fa.pri = *pri;
+  fa.chunks_per_split = sp.chunks_per_split; fa.splits = sp.splits; fa.sample = sample ? 1 : 0;
+  fa.part = (float*)(base + w.off_scratch);
   dim3 grid((unsigned)ceil_div(N, F_BN), (unsigned)ceil_div(B, F_BM), (unsigned)sp.splits);
   lrt_f32_fwd_partial<<<grid, kThreads, 0, st>>>(fa);
   if (int rc = check_launch("lrt_f32_fwd_partial")) return rc;
@@ -669,61 +745,83 @@ extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B
   ea.part = fa.part; ea.splits = sp.splits; ea.B = B; ea.N = N;
   ea.bias_mu = L->bias_mu; ea.bias_rho = L->bias_rho;
   ea.noise = make_noise(nz);
-  ea.flags = flags; ea.act = act; ea.std_out = std_out; ea.kl_out = kl_out;
-  ea.kl_part = fa.kl_part; ea.n_kl_part = sp.splits * (int)grid.x; ea.pri = *pri;
-  int64_t blocks = ceil_div(ceil_div(B * N, 4), kThreads);
-  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-  lrt_f32_fwd_epilogue<<<(unsigned)blocks, kThreads, 0, st>>>(ea);
+  ea.flags = flags; ea.act = act; ea.dsf = ds_factor; ea.kl_out = kl_out;
+  ea.kl_part = kl_part; ea.n_kl_part = (int)elementwise_blocks(N * K); ea.pri = *pri;
+  int64_t blocks = ceil_div(ceil_div(B * N, 4), kEpiThreads);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  lrt_f32_fwd_epilogue<<<(unsigned)blocks, kEpiThreads, 0, st>>>(ea);
   return check_launch("lrt_f32_fwd_epilogue");
 }
 
 extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, int64_t B, const float* gact,
-                                        const float* std_saved, const lbbnn_noise* nz,
-                                        const lbbnn_priors* pri, int var_mode, int flags, const float* kl_grad_dev,
-                                        float kl_grad_host, const lbbnn_layer_grads* G, void* ws, size_t ws_bytes,
-                                        lbbnn_stream s) {
-  (void)ws; (void)ws_bytes;
+                                        const float* ds_factor, const lbbnn_priors* pri, int var_mode, int flags,
+                                        const float* kl_grad_dev, float kl_grad_host, const lbbnn_layer_grads* G,
+                                        void* ws, size_t ws_bytes, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;
   LBBNN_REQUIRE(x && gact && B > 0 && pri && G, "NULL argument");
   LBBNN_REQUIRE(G->weight_mu && G->weight_rho && G->lambdal && G->bias_mu && G->bias_rho, "NULL gradient buffer");
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
-  LBBNN_REQUIRE(!sample || std_saved, "sample-branch backward needs the saved std");
+  LBBNN_REQUIRE(!sample || ds_factor, "sample-branch backward needs the saved ds_factor");
   LBBNN_REQUIRE(G->z == nullptr || L->z != nullptr, "dz requested but the layer has no z");
+  const int64_t K = L->in_features, N = L->out_features;
+  const WsLayout w = ws_layout(B, K, N);
+  LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small (%zu < %zu)", ws_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)s;
+  char* scratch = (char*)ws + w.off_scratch;
+  const size_t nk = align_up((size_t)N * K * sizeof(float));
   BwdWArgs a;
-  a.x = x; a.g = gact; a.sd = std_saved; a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.z = L->z;
-  a.bias_mu = L->bias_mu; a.bias_rho = L->bias_rho;
-  a.noise = make_noise(nz);
-  a.B = B; a.K = L->in_features; a.N = L->out_features;
-  a.var_mode = var_mode; a.sample = sample ? 1 : 0; a.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
-  a.klg_dev = kl_grad_dev; a.klg_host = kl_grad_host; a.pri = *pri;
-  a.dmu = G->weight_mu; a.drho = G->weight_rho; a.dlam = G->lambdal; a.dbmu = G->bias_mu; a.dbrho = G->bias_rho; a.dz = G->z;
-  dim3 grid((unsigned)ceil_div(a.N, W_BN), (unsigned)ceil_div(a.K, W_BK));
-  lrt_f32_bwd_params<<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
-  return check_launch("lrt_f32_bwd_params");
+  a.x = x; a.g = gact; a.dsf = ds_factor; a.B = B; a.K = K; a.N = N; a.sample = sample ? 1 : 0;
+  a.dM = (float*)scratch; a.dV = (float*)(scratch + nk); a.colsum = (float*)(scratch + 2 * nk);
+  dim3 grid((unsigned)ceil_div(N, W_BN), (unsigned)ceil_div(K, W_BK));
+  lrt_f32_bwd_w_gemm<<<grid, kThreads, 0, st>>>(a);
+  if (int rc = check_launch("lrt_f32_bwd_w_gemm")) return rc;
+
+  FinalizeArgs f;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.dM = a.dM; f.dV = a.dV; f.colsum = a.colsum; f.N = N; f.K = K;
+  f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
+  f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
+  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z;
+  lrt_f32_finalize<<<(unsigned)elementwise_blocks(N * K), kThreads, 0, st>>>(f);
+  return check_launch("lrt_f32_finalize");
 }
 
 extern "C" int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* L, const float* x, int64_t B, const float* gact,
-                                       const float* std_saved, const lbbnn_noise* nz,
-                                       int var_mode, int flags, float* dx, void* ws, size_t ws_bytes, lbbnn_stream s) {
+                                       const float* ds_factor, const lbbnn_priors* pri, int var_mode, int flags,
+                                       const float* mv_cache, float* dx, void* ws, size_t ws_bytes, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;
-  LBBNN_REQUIRE(x && gact && dx && B > 0, "NULL argument");
+  LBBNN_REQUIRE(x && gact && dx && B > 0 && pri, "NULL argument");
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
-  LBBNN_REQUIRE(!sample || std_saved, "sample-branch backward needs the saved std");
+  LBBNN_REQUIRE(!sample || ds_factor, "sample-branch backward needs the saved ds_factor");
   const int64_t K = L->in_features, N = L->out_features;
-  LBBNN_REQUIRE(ws && ws_bytes >= lbbnn_lrt_f32_workspace_bytes(B, K, N), "workspace too small");
+  const WsLayout w = ws_layout(B, K, N);
+  LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small (%zu < %zu)", ws_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)s;
+  char* base = (char*)ws;
+  const float *M, *V;
+  if (mv_cache) {  // M,V kept from the forward of this step
+    M = mv_cache;
+    V = (const float*)((const char*)mv_cache + align_up((size_t)N * K * sizeof(float)));
+  } else {         // recompute them (parameters unchanged since the forward)
+    if (int rc = launch_prologue(L, pri, var_mode, sample, false, (float*)(base + w.off_m), (float*)(base + w.off_v),
+                                 nullptr, st))
+      return rc;
+    M = (const float*)(base + w.off_m);
+    V = (const float*)(base + w.off_v);
+  }
   const Split sp = dx_split(B, K, N);
   BwdXArgs a;
-  a.x = x; a.g = gact; a.sd = std_saved; a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.z = L->z;
-  a.noise = make_noise(nz);
+  a.x = x; a.g = gact; a.dsf = ds_factor; a.M = M; a.V = sample ? V : nullptr;
   a.B = B; a.K = K; a.N = N;
-  a.chunks_per_split = sp.chunks_per_split; a.splits = sp.splits; a.var_mode = var_mode; a.sample = sample ? 1 : 0;
-  a.part = (float*)ws;
+  a.chunks_per_split = sp.chunks_per_split; a.splits = sp.splits; a.sample = sample ? 1 : 0;
+  a.part = (float*)(base + w.off_scratch);
   dim3 grid((unsigned)ceil_div(K, X_BK), (unsigned)ceil_div(B, X_BM), (unsigned)sp.splits);
-  lrt_f32_bwd_input_partial<<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
-  if (int rc = check_launch("lrt_f32_bwd_input_partial")) return rc;
-  int64_t blocks = ceil_div(B * K, kThreads);
-  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
-  lrt_f32_bwd_input_epilogue<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)s>>>(
-      a.part, sp.splits, B * K, x, (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0, (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0, dx);
-  return check_launch("lrt_f32_bwd_input_epilogue");
+  lrt_f32_bwd_x_partial<<<grid, kThreads, 0, st>>>(a);
+  if (int rc = check_launch("lrt_f32_bwd_x_partial")) return rc;
+  int64_t blocks = ceil_div(ceil_div(B * K, 4), kEpiThreads);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  lrt_f32_bwd_x_epilogue<<<(unsigned)blocks, kEpiThreads, 0, st>>>(a.part, sp.splits, B * K, x,
+                                                                  (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0,
+                                                                  (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0, dx);
+  return check_launch("lrt_f32_bwd_x_epilogue");
 }

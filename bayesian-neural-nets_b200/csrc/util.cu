@@ -62,14 +62,15 @@ int philox_export(float* out, int64_t n, uint64_t seed, uint64_t stream_id, int 
   return check_launch("philox_export");
 }
 
-// one warp per row: log_softmax(dim=1), nll(sum) and its gradient (LRT:210,223)
+// one warp per row: log_softmax(dim=1), nll(sum) and its gradient (LRT:210,223); single block so the
+// nll sum has a fixed order
 __global__ void logsoftmax_nll_kernel(const float* __restrict__ logits, const int64_t* __restrict__ target, int64_t B,
                                       int64_t C, float* __restrict__ logp, float* __restrict__ nll_sum,
-                                      float* __restrict__ dlogits, float gscale) {
+                                      float* __restrict__ dlogits, float gscale, int64_t* step_inc) {
   __shared__ float red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   float local = 0.f;
-  for (int64_t b = warp; b < B; b += nw) {  // single block: fixed summation order
+  for (int64_t b = warp; b < B; b += nw) {
     const float* row = logits + b * C;
     float mx = -INFINITY;
     for (int64_t c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
@@ -88,24 +89,58 @@ __global__ void logsoftmax_nll_kernel(const float* __restrict__ logits, const in
     }
   }
   const float tot = block_sum(local, red);
-  if (threadIdx.x == 0 && nll_sum) *nll_sum = tot;
+  if (threadIdx.x == 0) {
+    if (nll_sum) *nll_sum = tot;
+    if (step_inc) *step_inc += 1;
+  }
 }
 
-__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
-                            const int64_t* __restrict__ step_dev) {
-  const double t = (double)(*step_dev + 1);
-  const float bc1 = (float)(1.0 - pow((double)b1, t));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)b2, t));
-  const float step_size = lr / bc1;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float gi = g[i];
-    const float mi = m[i] + (gi - m[i]) * (1.0f - b1);   // lerp form, as torch's _single_tensor_adam
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= step_size * (mi / denom);
+// torch.optim.Adam (single-tensor, non-amsgrad) on one flat fp32 buffer, 4 elements per thread
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
+                                                   float b1, float b2, float eps, const int64_t* __restrict__ step_dev) {
+  __shared__ float sh[2];
+  if (threadIdx.x == 0) {
+    const double t = (double)(*step_dev);
+    sh[0] = lr / (float)(1.0 - pow((double)b1, t));        // step_size = lr / bias_correction1
+    sh[1] = (float)sqrt(1.0 - pow((double)b2, t));         // sqrt(bias_correction2)
+  }
+  __syncthreads();
+  const float step_size = sh[0], bc2_sqrt = sh[1];
+  const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  const int64_t nq = ceil_div(n, 4);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float pv[4], gv[4], mv[4], vv[4];
+    if (vec) {
+      const float4 a = *reinterpret_cast<const float4*>(p + e0), b = *reinterpret_cast<const float4*>(g + e0);
+      const float4 c = *reinterpret_cast<const float4*>(m + e0), d = *reinterpret_cast<const float4*>(v + e0);
+      pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+      mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w; vv[0] = d.x; vv[1] = d.y; vv[2] = d.z; vv[3] = d.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = e0 + j < n;
+        pv[j] = ok ? p[e0 + j] : 0.f; gv[j] = ok ? g[e0 + j] : 0.f;
+        mv[j] = ok ? m[e0 + j] : 0.f; vv[j] = ok ? v[e0 + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      mv[j] = mv[j] + (gv[j] - mv[j]) * (1.0f - b1);   // lerp form, as torch's _single_tensor_adam
+      vv[j] = b2 * vv[j] + (1.0f - b2) * gv[j] * gv[j];
+      const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+      pv[j] -= step_size * (mv[j] / denom);
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(p + e0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+      *reinterpret_cast<float4*>(m + e0) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(v + e0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < n) { p[e0 + j] = pv[j]; m[e0 + j] = mv[j]; v[e0 + j] = vv[j]; }
+    }
   }
 }
 
@@ -137,17 +172,19 @@ extern "C" int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64
 }
 
 extern "C" int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t B, int64_t C, float* logp,
-                                        float* nll_sum, float* dlogits, float grad_scale, lbbnn_stream s) {
+                                        float* nll_sum, float* dlogits, float grad_scale, int64_t* step_inc,
+                                        lbbnn_stream s) {
   LBBNN_REQUIRE(logits && target && B > 0 && C > 0, "bad logits/target");
-  logsoftmax_nll_kernel<<<1, 1024, 0, (cudaStream_t)s>>>(logits, target, B, C, logp, nll_sum, dlogits, grad_scale);
+  logsoftmax_nll_kernel<<<1, 1024, 0, (cudaStream_t)s>>>(logits, target, B, C, logp, nll_sum, dlogits, grad_scale,
+                                                         step_inc);
   return check_launch("logsoftmax_nll");
 }
 
 extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                               float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s) {
   LBBNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "NULL argument");
-  int64_t blocks = ceil_div(n, 256 * 4);
-  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+  int64_t blocks = ceil_div(ceil_div(n, 4), 256);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                              step_dev);
   return check_launch("adam");

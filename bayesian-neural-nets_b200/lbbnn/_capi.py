@@ -55,13 +55,14 @@ SIGNATURES = {
     "lbbnn_philox_normal": (_INT, [_P, _I64, _U64, _U64, _P]),
     "lbbnn_philox_uniform": (_INT, [_P, _I64, _U64, _U64, _P]),
     "lbbnn_lrt_f32_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "lbbnn_lrt_f32_mv_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_lrt_f32_fwd": (_INT, [C.POINTER(Layer), _P, _I64, C.POINTER(Noise), C.POINTER(Priors), _INT, _INT,
-                                 _P, _P, _P, _P, _SZ, _P]),
-    "lbbnn_lrt_f32_bwd_params": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Noise), C.POINTER(Priors),
-                                        _INT, _INT, _P, _F, C.POINTER(LayerGrads), _P, _SZ, _P]),
-    "lbbnn_lrt_f32_bwd_input": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Noise), _INT, _INT, _P,
+                                 _P, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_lrt_f32_bwd_params": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _F,
+                                        C.POINTER(LayerGrads), _P, _SZ, _P]),
+    "lbbnn_lrt_f32_bwd_input": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _P,
                                        _P, _SZ, _P]),
-    "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P]),
+    "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
 }
@@ -131,6 +132,10 @@ def workspace(nbytes, device):
 
 def lrt_workspace_bytes(batch, in_features, out_features):
     return int(lib.lbbnn_lrt_f32_workspace_bytes(batch, in_features, out_features))
+
+
+def lrt_mv_bytes(in_features, out_features):
+    return int(lib.lbbnn_lrt_f32_mv_bytes(in_features, out_features))
 
 
 def make_layer(weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z=None):

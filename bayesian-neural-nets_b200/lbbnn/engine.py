@@ -65,7 +65,8 @@ class LRTTrainer:
         self.x = torch.zeros(self.B, sizes[0][0], **f32)
         self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.acts = [torch.zeros(self.B, o, **f32) for _, o in sizes]
-        self.stds = [torch.zeros(self.B, o, **f32) for _, o in sizes]
+        self.dsf = [torch.zeros(self.B, o, **f32) for _, o in sizes]     # eps/(2 sqrt(var_b)) per layer
+        self.mv = [None] + [torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) for i, o in sizes[1:]]  # M,V kept for dX
         self.gbuf = [torch.zeros(self.B, o, **f32) for _, o in sizes]   # dL/d(pre-activation) per layer
         self.eps_in = [torch.zeros(self.B, o, **f32) for _, o in sizes] if inject_noise else None
         self.stats = torch.zeros(1 + len(sizes), **f32)                  # [nll, kl_1 .. kl_L]
@@ -97,13 +98,16 @@ class LRTTrainer:
         for i, l in enumerate(self.layers):
             flags = K.FLAG_SAMPLE | K.FLAG_KL | (K.FLAG_RELU if i < L - 1 else 0)
             K.check(K.lib.lbbnn_lrt_f32_fwd(descs[i], K.ptr(h), self.B, self._noise(i), l.cfg.priors, l.cfg.var_mode,
-                                            flags, K.ptr(self.acts[i]), K.ptr(self.stds[i]),
-                                            self.stats[1 + i:].data_ptr(), ws, wsn, st))
-            n_launch += 2
+                                            flags, K.ptr(self.acts[i]), K.ptr(self.dsf[i]),
+                                            self.stats[1 + i:].data_ptr(), K.ptr(self.mv[i], allow_none=True),
+                                            ws, wsn, st))
+            n_launch += 3
             h = self.acts[i]
         C = self.layers[-1].out_features
+        # loss head; also bumps the step counter: noise above used step t-1, Adam below uses t
         K.check(K.lib.lbbnn_logsoftmax_nll_f32(K.ptr(self.acts[-1]), K.ptr(self.y, torch.int64), self.B, C, None,
-                                               self.stats.data_ptr(), K.ptr(self.gbuf[-1]), 1.0, st))
+                                               self.stats.data_ptr(), K.ptr(self.gbuf[-1]), 1.0,
+                                               K.ptr(self.step_dev, torch.int64), st))
         n_launch += 1
         klg = 1.0 / (self.num_batches * self.world)   # KL is replicated on every rank: its grad is added once
         for i in reversed(range(L)):
@@ -111,21 +115,21 @@ class LRTTrainer:
             xin = self.x if i == 0 else self.acts[i - 1]
             g = l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad, l.bias_mu.grad, l.bias_rho.grad
             K.check(K.lib.lbbnn_lrt_f32_bwd_params(
-                descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.stds[i]), self._noise(i), l.cfg.priors,
+                descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.dsf[i]), l.cfg.priors,
                 l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, K.LayerGrads(*[t.data_ptr() for t in g], None), ws, wsn, st))
-            n_launch += 1
+            n_launch += 2
             if i > 0:
                 K.check(K.lib.lbbnn_lrt_f32_bwd_input(
-                    descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.stds[i]), self._noise(i),
-                    l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(self.gbuf[i - 1]), ws, wsn, st))
+                    descs[i], K.ptr(xin), self.B, K.ptr(self.gbuf[i]), K.ptr(self.dsf[i]), l.cfg.priors,
+                    l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(self.mv[i]), K.ptr(self.gbuf[i - 1]),
+                    ws, wsn, st))
                 n_launch += 2
         if self.pg is not None:
             torch.distributed.all_reduce(self.gflat, group=self.pg)
         K.check(K.lib.lbbnn_adam_f32(K.ptr(self.flat), K.ptr(self.gflat), K.ptr(self.exp_avg), K.ptr(self.exp_avg_sq),
                                      self.n_flat, self.lr, self.betas[0], self.betas[1], self.eps,
                                      K.ptr(self.step_dev, torch.int64), st))
-        K.check(K.lib.lbbnn_counter_inc(K.ptr(self.step_dev, torch.int64), st))
-        n_launch += 2
+        n_launch += 1
         self.kernels_per_step = n_launch
 
     def _capture(self):

@@ -58,27 +58,28 @@ class _LRTFunction(torch.autograd.Function):
         noise = K.make_noise(eps, noise_key[0], noise_key[1])
         flags = (K.FLAG_SAMPLE if sample else 0) | (K.FLAG_KL if want_kl else 0)
         act = torch.empty(B, out_f, dtype=torch.float32, device=x.device)
-        std = torch.empty(B, out_f, dtype=torch.float32, device=x.device) if sample else None
+        dsf = torch.empty(B, out_f, dtype=torch.float32, device=x.device) if sample else None
         kl = torch.zeros((), dtype=torch.float32, device=x.device)
-        nbytes = K.lrt_workspace_bytes(B, in_f, out_f)
-        ws = K.workspace(nbytes, x.device)
+        # keep M,V for the input-gradient GEMM of the backward (else it recomputes them)
+        mv = (torch.empty(K.lrt_mv_bytes(in_f, out_f) // 4, dtype=torch.float32, device=x.device)
+              if ctx.needs_input_grad[0] else None)
+        ws = K.workspace(K.lrt_workspace_bytes(B, in_f, out_f), x.device)
         K.check(K.lib.lbbnn_lrt_f32_fwd(layer, K.ptr(x), B, noise, cfg.priors, cfg.var_mode, flags, K.ptr(act),
-                                        K.ptr(std, allow_none=True), K.ptr(kl), ws.data_ptr(), ws.numel(),
-                                        K.current_stream()))
-        ctx.save_for_backward(x, *params, zc, std, eps)
-        ctx.cfg, ctx.sample, ctx.want_kl, ctx.noise_key = cfg, sample, want_kl, noise_key
+                                        K.ptr(dsf, allow_none=True), K.ptr(kl), K.ptr(mv, allow_none=True),
+                                        ws.data_ptr(), ws.numel(), K.current_stream()))
+        ctx.save_for_backward(x, *params, zc, dsf, mv)
+        ctx.cfg, ctx.sample, ctx.want_kl = cfg, sample, want_kl
         return act, kl
 
     @staticmethod
     def backward(ctx, g_act, g_kl):
-        x, wmu, wrho, lam, bmu, brho, z, std, eps = ctx.saved_tensors
+        x, wmu, wrho, lam, bmu, brho, z, dsf, mv = ctx.saved_tensors
         cfg = ctx.cfg
         B, in_f = x.shape
         out_f = wmu.shape[0]
         dev = x.device
         g_act = torch.zeros(B, out_f, dtype=torch.float32, device=dev) if g_act is None else g_act.contiguous()
         layer = K.make_layer(wmu, wrho, lam, bmu, brho, z)
-        noise = K.make_noise(eps, ctx.noise_key[0], ctx.noise_key[1])
         flags = K.FLAG_SAMPLE if ctx.sample else 0
         ws = K.workspace(K.lrt_workspace_bytes(B, in_f, out_f), dev)
         grads = [torch.empty_like(t) for t in (wmu, wrho, lam, bmu, brho)]
@@ -86,16 +87,16 @@ class _LRTFunction(torch.autograd.Function):
         use_kl = ctx.want_kl and g_kl is not None
         g_kl_c = g_kl.contiguous().float() if use_kl else None
         K.check(K.lib.lbbnn_lrt_f32_bwd_params(
-            layer, K.ptr(x), B, K.ptr(g_act), K.ptr(std, allow_none=True), noise, cfg.priors, cfg.var_mode, flags,
+            layer, K.ptr(x), B, K.ptr(g_act), K.ptr(dsf, allow_none=True), cfg.priors, cfg.var_mode, flags,
             K.ptr(g_kl_c, allow_none=True), 1.0 if use_kl else 0.0,
             K.LayerGrads(*[K.ptr(g) for g in grads], K.ptr(dz, allow_none=True)),
             ws.data_ptr(), ws.numel(), K.current_stream()))
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            K.check(K.lib.lbbnn_lrt_f32_bwd_input(layer, K.ptr(x), B, K.ptr(g_act), K.ptr(std, allow_none=True), noise,
-                                                  cfg.var_mode, flags, K.ptr(dx), ws.data_ptr(), ws.numel(),
-                                                  K.current_stream()))
+            K.check(K.lib.lbbnn_lrt_f32_bwd_input(layer, K.ptr(x), B, K.ptr(g_act), K.ptr(dsf, allow_none=True),
+                                                  cfg.priors, cfg.var_mode, flags, K.ptr(mv, allow_none=True),
+                                                  K.ptr(dx), ws.data_ptr(), ws.numel(), K.current_stream()))
         return (dx, *grads, dz, None, None, None, None, None)
 
 

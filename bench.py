@@ -190,21 +190,23 @@ def profile_calls(tr, reps=20):
         K_, N_ = l.in_features, l.out_features
         xin = tr.x if i == 0 else tr.acts[i - 1]
         flags = K.FLAG_SAMPLE | K.FLAG_KL | (K.FLAG_RELU if i < L - 1 else 0)
-        calls.append((f"lrt_f32_fwd[l{i + 1}] (partial+epilogue)", 12 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
+        calls.append((f"lrt_f32_fwd[l{i + 1}] (prologue+gemm+epilogue)", 12 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
                       lambda i=i, l=l, xin=xin, flags=flags: K.lib.lbbnn_lrt_f32_fwd(
                           descs[i], K.ptr(xin), B, tr._noise(i), l.cfg.priors, l.cfg.var_mode, flags,
-                          K.ptr(tr.acts[i]), K.ptr(tr.stds[i]), tr.stats[1 + i:].data_ptr(), ws, wsn, st)))
+                          K.ptr(tr.acts[i]), K.ptr(tr.dsf[i]), tr.stats[1 + i:].data_ptr(),
+                          K.ptr(tr.mv[i], allow_none=True), ws, wsn, st)))
         g = l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad, l.bias_mu.grad, l.bias_rho.grad
-        calls.append((f"lrt_f32_bwd_params[l{i + 1}]", 24 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
+        calls.append((f"lrt_f32_bwd_params[l{i + 1}] (gemm+finalize)", 24 * K_ * N_ + 4 * B * K_ + 8 * B * N_,
                       lambda i=i, l=l, xin=xin, g=g: K.lib.lbbnn_lrt_f32_bwd_params(
-                          descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.stds[i]), tr._noise(i), l.cfg.priors,
+                          descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.dsf[i]), l.cfg.priors,
                           l.cfg.var_mode, K.FLAG_SAMPLE, None, 1.0 / NUM_BATCHES,
                           K.LayerGrads(*[t.data_ptr() for t in g], None), ws, wsn, st)))
         if i > 0:
-            calls.append((f"lrt_f32_bwd_input[l{i + 1}] (partial+epilogue)", 12 * K_ * N_ + 8 * B * N_ + 8 * B * K_,
+            calls.append((f"lrt_f32_bwd_input[l{i + 1}] (gemm+epilogue)", 8 * K_ * N_ + 8 * B * N_ + 8 * B * K_,
                           lambda i=i, l=l, xin=xin: K.lib.lbbnn_lrt_f32_bwd_input(
-                              descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.stds[i]), tr._noise(i),
-                              l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(tr.gbuf[i - 1]), ws, wsn, st)))
+                              descs[i], K.ptr(xin), B, K.ptr(tr.gbuf[i]), K.ptr(tr.dsf[i]), l.cfg.priors,
+                              l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(tr.mv[i]),
+                              K.ptr(tr.gbuf[i - 1]), ws, wsn, st)))
     calls.append(("adam_f32 (flat)", 28 * tr.n_flat,
                   lambda: K.lib.lbbnn_adam_f32(K.ptr(tr.flat), K.ptr(tr.gflat), K.ptr(tr.exp_avg),
                                                K.ptr(tr.exp_avg_sq), tr.n_flat, 0.0, 0.9, 0.999, 1e-8,

@@ -100,44 +100,50 @@ LBBNN_API int lbbnn_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t
 LBBNN_API int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id, lbbnn_stream s);
 
 /* ---- LRT layer, fp32 SIMT path (parity mode) ---------------------------------------------------
- * fwd replaces BayesianLinear.forward LRT:166-196 (alpha, sigma, M, V prologue; both mm's; eps;
- * sqrt/FMA epilogue; closed-form KL).  noise: see lbbnn_noise (shape (batch,out)).  Outputs: act (batch,out); std_out (batch,out) = sqrt(var_b), kept for
- * the backward (may be NULL when no backward follows); kl_out: one float (FLAG_KL).
+ * fwd replaces BayesianLinear.forward LRT:166-196: an elementwise prologue (alpha, sigma, M, V, KL
+ * terms), the two mm's as one split-K dual GEMM, and an epilogue (biases, eps, sqrt/FMA, optional
+ * relu, KL total).  noise: see lbbnn_noise (shape (batch,out)).
+ * Outputs: act (batch,out); ds_factor (batch,out) = eps/(2 sqrt(var_b)) = d act/d var_b, kept for the
+ * backward (may be NULL when no backward follows); kl_out: one float (FLAG_KL); mv_cache (optional,
+ * lbbnn_lrt_f32_mv_bytes) receives M,V so that bwd_input of the same step need not recompute them.
  * bwd_params / bwd_input replace autograd through the same lines (formulas: SURVEY.md §3.5).
  *   gact   = dL/d(act before relu) (batch,out)
  *   kl_grad_dev (device float or NULL) * kl_grad_host = dL/d(kl)
+ * One workspace of lbbnn_lrt_f32_workspace_bytes serves all three calls (stream-ordered reuse).
  */
 LBBNN_API size_t lbbnn_lrt_f32_workspace_bytes(int64_t batch, int64_t in_features, int64_t out_features);
+LBBNN_API size_t lbbnn_lrt_f32_mv_bytes(int64_t in_features, int64_t out_features);
 
 LBBNN_API int lbbnn_lrt_f32_fwd(const lbbnn_layer* layer, const float* x, int64_t batch,
-                      const lbbnn_noise* noise,
-                      const lbbnn_priors* priors, int var_mode, int flags,
-                      float* act, float* std_out, float* kl_out,
-                      void* workspace, size_t workspace_bytes, lbbnn_stream s);
+                                const lbbnn_noise* noise, const lbbnn_priors* priors, int var_mode, int flags,
+                                float* act, float* ds_factor, float* kl_out, float* mv_cache,
+                                void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 LBBNN_API int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* layer, const float* x, int64_t batch,
-                             const float* gact, const float* std_saved,
-                             const lbbnn_noise* noise,
-                             const lbbnn_priors* priors, int var_mode, int flags,
-                             const float* kl_grad_dev, float kl_grad_host,
-                             const lbbnn_layer_grads* grads,
-                             void* workspace, size_t workspace_bytes, lbbnn_stream s);
+                                       const float* gact, const float* ds_factor,
+                                       const lbbnn_priors* priors, int var_mode, int flags,
+                                       const float* kl_grad_dev, float kl_grad_host,
+                                       const lbbnn_layer_grads* grads,
+                                       void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 LBBNN_API int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* layer, const float* x, int64_t batch,
-                            const float* gact, const float* std_saved,
-                            const lbbnn_noise* noise,
-                            int var_mode, int flags, float* dx,
-                            void* workspace, size_t workspace_bytes, lbbnn_stream s);
+                                      const float* gact, const float* ds_factor,
+                                      const lbbnn_priors* priors, int var_mode, int flags,
+                                      const float* mv_cache, float* dx,
+                                      void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
- * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL. */
+ * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.
+ * step_inc (device int64 or NULL) is incremented by one: the trainer's step counter, bumped between
+ * the forward (noise of step t) and the optimizer (bias correction t+1) without an extra launch. */
 LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
-                             float* logp, float* nll_sum, float* dlogits, float grad_scale, lbbnn_stream s);
+                                       float* logp, float* nll_sum, float* dlogits, float grad_scale,
+                                       int64_t* step_inc, lbbnn_stream s);
 
 /* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
- * step_dev: device int64 holding the number of steps ALREADY taken (t-1); lbbnn_counter_inc bumps it. */
+ * step_dev: device int64 holding t, the 1-based index of THIS update. */
 LBBNN_API int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                   float lr, float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s);
+                             float lr, float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s);
 LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
 
 #ifdef __cplusplus
