@@ -227,8 +227,16 @@ def profile_calls(tr, reps=20):
 
 
 # ------------------------------------------------------------------------------------------------
+def _mark(msg):
+    if os.environ.get("LBBNN_BENCH_VERBOSE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import lbbnn
+    if os.environ.get("LBBNN_HANG_DUMP"):
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["LBBNN_HANG_DUMP"]), exit=True)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,7 +256,9 @@ def run_ours(args):
     torch.manual_seed(0)                       # identical initial parameters on every rank
     lbbnn.manual_seed(1234)
     net = lbbnn.BayesianNetwork(sizes).to(dev)
+    _mark("process group up, building trainer")
     tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+    _mark("trainer captured")
 
     pool_x_host, pool_y_host = make_pool(B, sizes[0], sizes[-1], seed=1000 + rank)
     pool_x_host, pool_y_host = pool_x_host.pin_memory(), pool_y_host.pin_memory()
@@ -267,6 +277,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         dev_step(i)
+    _mark("warmup done")
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -279,6 +290,7 @@ def run_ours(args):
     barrier()
     t1 = time.perf_counter()
     ms = e0.elapsed_time(e1)
+    _mark(f"timed region done: {ms / args.steps * 1e3:.1f} us/step")
 
     # ---- end to end through the public API with host buffers ("e2e") ----------------------------------
     for i in range(min(args.warmup, 5)):
@@ -290,6 +302,7 @@ def run_ours(args):
     barrier()
     te1 = time.perf_counter()
     e2e_ms = (te1 - te0) * 1e3
+    _mark("e2e done")
     sampler.stop()
     clocks = sampler.summary(t0, te1)
 
@@ -332,8 +345,14 @@ def run_ours(args):
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
     if world > 1:
+        # destroy_process_group() hangs while a CUDA graph still holds captured NCCL kernels (seen on the box:
+        # both ranks stuck there until the 600 s collective timeout): drop the graph, sync, and leave without it.
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        tr.graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
