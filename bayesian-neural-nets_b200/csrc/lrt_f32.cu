@@ -629,6 +629,20 @@ __global__ void __launch_bounds__(kEpiThreads) lrt_f32_bwd_x_epilogue(const floa
   }
 }
 
+// sum of the prologue's KL partials + the bias term -> kl_out (single block, fixed order)
+__global__ void __launch_bounds__(kThreads) lrt_kl_finalize(const double* __restrict__ kl_part, int n_part,
+                                                            const float* __restrict__ bias_mu,
+                                                            const float* __restrict__ bias_rho, int64_t N,
+                                                            const lbbnn_priors pri, float* __restrict__ kl_out) {
+  __shared__ double dred[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n_part; i += blockDim.x) acc += kl_part[i];
+  for (int64_t n = threadIdx.x; n < N; n += blockDim.x)
+    acc += (double)kl_bias_elem(__ldg(bias_mu + n), sigma_of(__ldg(bias_rho + n)), pri);
+  const double tot = block_sum(acc, dred);
+  if (threadIdx.x == 0) *kl_out = (float)tot;
+}
+
 // ---- split heuristics (shared by the workspace query and the launchers) ----------------------------
 struct Split { int chunks_per_split, splits; };
 
@@ -824,4 +838,41 @@ extern "C" int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* L, const float* x, int
                                                                   (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0,
                                                                   (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0, dx);
   return check_launch("lrt_f32_bwd_x_epilogue");
+}
+
+extern "C" int lbbnn_lrt_f32_prologue(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, int flags, float* M,
+                                      float* V, float* kl_out, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(pri && M, "NULL argument");
+  const bool sample = flags & LBBNN_FLAG_SAMPLE;
+  LBBNN_REQUIRE(!sample || V, "sample branch needs V");
+  const int64_t n = L->in_features * L->out_features;
+  const size_t need = align_up((size_t)elementwise_blocks(n) * sizeof(double));
+  LBBNN_REQUIRE(kl_out == nullptr || (ws && ws_bytes >= need), "workspace too small for the KL partials");
+  cudaStream_t st = (cudaStream_t)s;
+  if (int rc = launch_prologue(L, pri, var_mode, sample, kl_out != nullptr, M, V, (double*)ws, st)) return rc;
+  if (kl_out) {
+    lrt_kl_finalize<<<1, kThreads, 0, st>>>((const double*)ws, (int)elementwise_blocks(n), L->bias_mu, L->bias_rho,
+                                            L->out_features, *pri, kl_out);
+    return check_launch("lrt_kl_finalize");
+  }
+  return LBBNN_OK;
+}
+
+extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, const float* dV, const float* colsum,
+                                      const lbbnn_priors* pri, int var_mode, int flags, const float* kl_grad_dev,
+                                      float kl_grad_host, const lbbnn_layer_grads* G, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(dM && colsum && pri && G, "NULL argument");
+  LBBNN_REQUIRE(G->weight_mu && G->weight_rho && G->lambdal && G->bias_mu && G->bias_rho, "NULL gradient buffer");
+  const bool sample = flags & LBBNN_FLAG_SAMPLE;
+  LBBNN_REQUIRE(!sample || dV, "sample branch needs dV");
+  FinalizeArgs f;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.dM = dM; f.dV = dV ? dV : dM; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
+  f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
+  f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
+  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z;
+  lrt_f32_finalize<<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
+  return check_launch("lrt_f32_finalize");
 }

@@ -22,6 +22,7 @@ lib = C.CDLL(LIB_PATH)
 
 VAR_REFERENCE, VAR_EXACT = 0, 1
 FLAG_SAMPLE, FLAG_RELU, FLAG_KL, FLAG_ACCUMULATE, FLAG_MASK_DX = 1, 2, 4, 8, 16
+PACK_PAIR, PACK_SQUARE, PACK_SCALE = 0, 1, 2
 
 
 class Priors(C.Structure):
@@ -62,6 +63,15 @@ SIGNATURES = {
                                         C.POINTER(LayerGrads), _P, _SZ, _P]),
     "lbbnn_lrt_f32_bwd_input": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _P,
                                        _P, _SZ, _P]),
+    "lbbnn_lrt_f32_prologue": (_INT, [C.POINTER(Layer), C.POINTER(Priors), _INT, _INT, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_lrt_f32_finalize": (_INT, [C.POINTER(Layer), _P, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _F,
+                                      C.POINTER(LayerGrads), _P]),
+    "lbbnn_tc_dual_gemm_raw": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "lbbnn_tc_lrt_fwd": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, C.POINTER(Noise), _INT,
+                                _P, _P, _P, _P, _P, _P, _P]),
+    "lbbnn_tc_lrt_bwd_input": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P, _P]),
+    "lbbnn_bf16_pack": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _P, _P, _P]),
+    "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
@@ -162,3 +172,32 @@ def philox_uniform(shape, seed, stream_id, device="cuda"):
     out = torch.empty(shape, dtype=torch.float32, device=device)
     check(lib.lbbnn_philox_uniform(ptr(out), out.numel(), seed, stream_id, current_stream()))
     return out
+
+
+# ---- bf16 tensor-core path ----------------------------------------------------------------------------
+BF16 = torch.bfloat16
+
+
+def bf16_pack(a, b, op, transposed=True):
+    """fp32 (rows, cols) -> (bf16 a, bf16 f(a,b)) and, if asked, their (cols, rows) transposes."""
+    require_device()
+    rows, cols = a.shape
+    o1 = torch.empty(rows, cols, dtype=BF16, device=a.device)
+    o2 = torch.empty(rows, cols, dtype=BF16, device=a.device)
+    o1t = torch.empty(cols, rows, dtype=BF16, device=a.device) if transposed else None
+    o2t = torch.empty(cols, rows, dtype=BF16, device=a.device) if transposed else None
+    check(lib.lbbnn_bf16_pack(ptr(a), ptr(b, allow_none=True), op, rows, cols, ptr(o1, BF16), ptr(o2, BF16),
+                              ptr(o1t, BF16, allow_none=True), ptr(o2t, BF16, allow_none=True), current_stream()))
+    return o1, o2, o1t, o2t
+
+
+def tc_dual_gemm_raw(a1, a2, b1, b2):
+    """D1 = a1 @ b1.T, D2 = a2 @ b2.T (bf16 in, fp32 out) on tcgen05."""
+    require_device()
+    m, k = a1.shape
+    n = b1.shape[0]
+    d1 = torch.empty(m, n, dtype=torch.float32, device=a1.device)
+    d2 = torch.empty(m, n, dtype=torch.float32, device=a1.device)
+    check(lib.lbbnn_tc_dual_gemm_raw(ptr(a1, BF16), ptr(a2, BF16), ptr(b1, BF16), ptr(b2, BF16), m, n, k,
+                                     ptr(d1), ptr(d2), current_stream()))
+    return d1, d2

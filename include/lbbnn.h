@@ -132,6 +132,52 @@ LBBNN_API int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* layer, const float* x, 
                                       const float* mv_cache, float* dx,
                                       void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
+/* The elementwise halves of the LRT layer on their own (the tensor-core path composes them with the
+ * bf16 GEMMs below).  prologue: M = alpha mu [z], V (LRT:170-171) as fp32 (out,in) + the layer KL
+ * (LRT:182-194) into kl_out (NULL = skip).  finalize: chain rule from (dM, dV, colsum = [sum_b dE;
+ * sum_b dS]) to the parameter gradients + closed-form KL gradient. */
+LBBNN_API int lbbnn_lrt_f32_prologue(const lbbnn_layer* layer, const lbbnn_priors* priors, int var_mode, int flags,
+                                     float* M, float* V, float* kl_out,
+                                     void* workspace, size_t workspace_bytes, lbbnn_stream s);
+LBBNN_API int lbbnn_lrt_f32_finalize(const lbbnn_layer* layer, const float* dM, const float* dV, const float* colsum,
+                                     const lbbnn_priors* priors, int var_mode, int flags,
+                                     const float* kl_grad_dev, float kl_grad_host,
+                                     const lbbnn_layer_grads* grads, lbbnn_stream s);
+
+/* ---- bf16 tensor-core path (tcgen05 / TMEM / TMA) ----------------------------------------------
+ * One persistent warp-specialised kernel computes D1 = A1 B1^T and D2 = A2 B2^T (all operands K-major
+ * bf16, fp32 accumulation in TMEM) and applies a fused epilogue.  Operands must be 16-byte aligned
+ * with K % 8 == 0 (TMA pitch); ragged M/N/K tiles are zero-filled by TMA and masked in the epilogue.
+ *   raw        D1, D2 as fp32 (M,N): the dW GEMM pair (dM = dE^T x, dV = dS^T x^2) and tests
+ *   lrt_fwd    act = D1 + b_mu + sqrt(D2 + sigma_b^2) eps (LRT:172-175) [relu]; writes act and act^2
+ *              in bf16 (batch,out), optionally their transposes (out,batch) for the next dW GEMM, the
+ *              fp32 ds_factor and an fp32 copy of act.  bf16(act^2) is rounded from the fp32 act.
+ *   lrt_bwd_input  dx = dE M + 2 x (dS V) [relu mask] = previous layer's dE; dS_prev = dE_prev *
+ *              ds_factor_prev; both in bf16 (batch,in) and optionally transposed (in,batch). */
+enum { LBBNN_TC_EPI_RAW = 0, LBBNN_TC_EPI_FWD = 1, LBBNN_TC_EPI_DX = 2 };
+enum { LBBNN_PACK_PAIR = 0, LBBNN_PACK_SQUARE = 1, LBBNN_PACK_SCALE = 2 };
+
+LBBNN_API int lbbnn_tc_dual_gemm_raw(const void* A1, const void* A2, const void* B1, const void* B2,
+                                     int64_t M, int64_t N, int64_t K, float* D1, float* D2, lbbnn_stream s);
+LBBNN_API int lbbnn_tc_lrt_fwd(const void* x_bf, const void* x2_bf, const void* M_bf, const void* V_bf,
+                               int64_t batch, int64_t in_features, int64_t out_features,
+                               const float* bias_mu, const float* bias_rho, const lbbnn_noise* noise, int flags,
+                               void* act_bf, void* act2_bf, void* actT_bf, void* act2T_bf,
+                               float* ds_factor, float* act_f32, lbbnn_stream s);
+LBBNN_API int lbbnn_tc_lrt_bwd_input(const void* dE_bf, const void* dS_bf, const void* MT_bf, const void* VT_bf,
+                                     int64_t batch, int64_t in_features, int64_t out_features,
+                                     const void* x_bf, const float* ds_factor_prev, int flags,
+                                     void* dE_prev_bf, void* dS_prev_bf, void* dE_prevT_bf, void* dS_prevT_bf,
+                                     lbbnn_stream s);
+/* fp32 (rows,cols) -> bf16 operand pairs, optionally also transposed (cols,rows):
+ *   PAIR: (a, b)   SQUARE: (a, a*a)   SCALE: (a, a*b).   outT/out2T may be NULL. */
+LBBNN_API int lbbnn_bf16_pack(const float* a, const float* b, int op, int64_t rows, int64_t cols,
+                              void* out1, void* out2, void* out1T, void* out2T, lbbnn_stream s);
+/* column sums over the batch: out[0..cols) = sum_r a, out[cols..2cols) = sum_r a*b (fixed order).
+ * a_is_bf16: a and b(=second operand, already the product) are bf16 tensors dE, dS instead. */
+LBBNN_API int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols,
+                            float* out, lbbnn_stream s);
+
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
  * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.
  * step_inc (device int64 or NULL) is incremented by one: the trainer's step counter, bumped between

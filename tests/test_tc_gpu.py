@@ -1,0 +1,105 @@
+"""GPU tests of the bf16 tcgen05 dual GEMM and its fused epilogues.
+
+bf16 tolerance (stated here): the kernel is compared with a torch reference whose GEMM
+operands are the SAME bf16-rounded tensors with fp32 accumulation -- remaining differences are
+summation order only, so the bound is 1e-4 (max|a-b|/max|b|).  The distance of the bf16 mode from the
+plain fp32 oracle is checked separately at 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    from lbbnn import _capi
+    return _capi
+
+
+def _rand_bf16(rng, *shape, scale=1.0):
+    return (torch.from_numpy(rng.standard_normal(size=shape).astype(np.float32)) * scale).cuda().to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (100, 72, 200), (1000, 136, 1096),
+                                   (4096, 512, 1024)])
+def test_raw_dual_gemm_matches_torch(K, m, n, k):
+    rng = np.random.default_rng(m * 7 + n * 3 + k)
+    a1, a2 = _rand_bf16(rng, m, k), _rand_bf16(rng, m, k)
+    b1, b2 = _rand_bf16(rng, n, k), _rand_bf16(rng, n, k)
+    d1, d2 = K.tc_dual_gemm_raw(a1, a2, b1, b2)
+    torch.cuda.synchronize()
+    r1 = a1.float() @ b1.float().T
+    r2 = a2.float() @ b2.float().T
+    assert C.rel_err(d1, r1) < 1e-4
+    assert C.rel_err(d2, r2) < 1e-4
+
+
+def test_pack_and_colsum(K):
+    rng = np.random.default_rng(3)
+    a = torch.from_numpy(rng.standard_normal(size=(70, 45)).astype(np.float32)).cuda()
+    b = torch.from_numpy(rng.standard_normal(size=(70, 45)).astype(np.float32)).cuda()
+    for op, second in ((K.PACK_PAIR, b), (K.PACK_SQUARE, a * a), (K.PACK_SCALE, a * b)):
+        o1, o2, o1t, o2t = K.bf16_pack(a, b, op)
+        assert torch.equal(o1, a.to(torch.bfloat16)) and torch.equal(o2, second.to(torch.bfloat16))
+        assert torch.equal(o1t, o1.T.contiguous()) and torch.equal(o2t, o2.T.contiguous())
+    out = torch.empty(2 * 45, device="cuda")
+    K.check(K.lib.lbbnn_colsum2(K.ptr(a), K.ptr(b), 0, 70, 45, K.ptr(out), K.current_stream()))
+    assert C.rel_err(out[:45], a.sum(0)) < 1e-5 and C.rel_err(out[45:], (a * b).sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("b,i,o,relu", [(256, 128, 256, True), (200, 136, 72, False)])
+def test_tc_lrt_fwd_epilogue(K, b, i, o, relu):
+    rng = np.random.default_rng(b + i + o)
+    x = torch.from_numpy(rng.random((b, i), dtype=np.float32)).cuda()
+    m = torch.from_numpy((rng.standard_normal((o, i)) * 0.1).astype(np.float32)).cuda()
+    v = torch.from_numpy((rng.random((o, i)) * 1e-3).astype(np.float32)).cuda()
+    bmu = torch.from_numpy(rng.uniform(-0.2, 0.2, o).astype(np.float32)).cuda()
+    brho = torch.from_numpy(rng.uniform(-5, -4, o).astype(np.float32)).cuda()
+    eps = torch.from_numpy(rng.standard_normal((b, o)).astype(np.float32)).cuda()
+    xb, x2b, _, _ = K.bf16_pack(x, None, K.PACK_SQUARE, transposed=False)
+    mb, vb, _, _ = K.bf16_pack(m, v, K.PACK_PAIR, transposed=False)
+    bf = torch.bfloat16
+    act, act2 = torch.empty(b, o, dtype=bf, device="cuda"), torch.empty(b, o, dtype=bf, device="cuda")
+    actT, act2T = torch.empty(o, b, dtype=bf, device="cuda"), torch.empty(o, b, dtype=bf, device="cuda")
+    dsf, actf = torch.empty(b, o, device="cuda"), torch.empty(b, o, device="cuda")
+    flags = K.FLAG_SAMPLE | (K.FLAG_RELU if relu else 0)
+    K.check(K.lib.lbbnn_tc_lrt_fwd(K.ptr(xb, bf), K.ptr(x2b, bf), K.ptr(mb, bf), K.ptr(vb, bf), b, i, o, K.ptr(bmu),
+                                   K.ptr(brho), K.make_noise(eps), flags, K.ptr(act, bf), K.ptr(act2, bf),
+                                   K.ptr(actT, bf), K.ptr(act2T, bf), K.ptr(dsf), K.ptr(actf), K.current_stream()))
+    torch.cuda.synchronize()
+    e = xb.float() @ mb.float().T + bmu
+    sd = torch.sqrt(x2b.float() @ vb.float().T + torch.log1p(torch.exp(brho)) ** 2)
+    ref = e + sd * eps
+    if relu:
+        ref = torch.relu(ref)
+    assert C.rel_err(actf, ref) < 1e-4
+    assert C.rel_err(dsf, eps / (2 * sd)) < 1e-4
+    assert torch.equal(act, actf.to(bf)) and torch.equal(act2, (actf * actf).to(bf))
+    assert torch.equal(actT, act.T.contiguous()) and torch.equal(act2T, act2.T.contiguous())
+    # distance of the bf16 mode from the fp32 math on unrounded operands
+    full = x @ m.T + bmu + torch.sqrt((x * x) @ v.T + torch.log1p(torch.exp(brho)) ** 2) * eps
+    full = torch.relu(full) if relu else full
+    assert (actf - full).norm() / full.norm() < 2e-2
+
+
+def test_tc_lrt_bwd_input_epilogue(K):
+    b, i, o = 256, 192, 128
+    rng = np.random.default_rng(9)
+    bf = torch.bfloat16
+    de, ds = _rand_bf16(rng, b, o), _rand_bf16(rng, b, o, scale=0.1)
+    mt, vt = _rand_bf16(rng, i, o, scale=0.1), _rand_bf16(rng, i, o, scale=0.01)
+    x = torch.relu(_rand_bf16(rng, b, i).float()).to(bf)
+    dsf_prev = torch.from_numpy(rng.standard_normal((b, i)).astype(np.float32)).cuda()
+    outs = [torch.empty(b, i, dtype=bf, device="cuda") for _ in range(2)] + [torch.empty(i, b, dtype=bf, device="cuda") for _ in range(2)]
+    K.check(K.lib.lbbnn_tc_lrt_bwd_input(K.ptr(de, bf), K.ptr(ds, bf), K.ptr(mt, bf), K.ptr(vt, bf), b, i, o, K.ptr(x, bf),
+                                         K.ptr(dsf_prev), K.FLAG_SAMPLE | K.FLAG_MASK_DX, *[K.ptr(t, bf) for t in outs],
+                                         K.current_stream()))
+    torch.cuda.synchronize()
+    g = de.float() @ mt.float().T + 2 * x.float() * (ds.float() @ vt.float().T)
+    g = g * (x.float() > 0)
+    assert C.rel_err(outs[0].float(), g) < 1e-2           # bf16 output rounding
+    assert C.rel_err(outs[1].float(), g * dsf_prev) < 1e-2
+    assert torch.equal(outs[2], outs[0].T.contiguous()) and torch.equal(outs[3], outs[1].T.contiguous())
