@@ -39,24 +39,27 @@ __global__ void __launch_bounds__(256) bf16_pack_kernel(const float* __restrict_
   }
 }
 
-// one block per 32 columns; 8 row-lanes per column accumulate strided rows, then a fixed-order
-// smem reduction: deterministic.
+// column sums in two deterministic stages: stage 1 = grid (cols/32, S row slices), each block sums its
+// slice with 8 row-lanes per column and a fixed-order smem reduction -> partial[s][2][cols];
+// stage 2 sums the S partials in order.
 template <bool BF16>
-__global__ void __launch_bounds__(256) colsum2_kernel(const void* __restrict__ a_, const void* __restrict__ b_, int64_t rows,
-                                                      int64_t cols, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) colsum2_stage1(const void* __restrict__ a_, const void* __restrict__ b_, int64_t rows,
+                                                      int64_t cols, int64_t rows_per_slice, float* __restrict__ partial) {
   __shared__ float s1[8][33], s2[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t rbeg = (int64_t)blockIdx.y * rows_per_slice, rend = min(rows, rbeg + rows_per_slice);
   float acc1 = 0.f, acc2 = 0.f;
   if (c < cols) {
-    for (int64_t r = ty; r < rows; r += 8) {
+#pragma unroll 4
+    for (int64_t r = rbeg + ty; r < rend; r += 8) {
       if (BF16) {
         acc1 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(a_)[r * cols + c]);
         acc2 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(b_)[r * cols + c]);
       } else {
-        const float v = reinterpret_cast<const float*>(a_)[r * cols + c];
+        const float v = __ldg(reinterpret_cast<const float*>(a_) + r * cols + c);
         acc1 += v;
-        acc2 += b_ ? v * reinterpret_cast<const float*>(b_)[r * cols + c] : 0.f;
+        acc2 += b_ ? v * __ldg(reinterpret_cast<const float*>(b_) + r * cols + c) : 0.f;
       }
     }
   }
@@ -67,9 +70,24 @@ __global__ void __launch_bounds__(256) colsum2_kernel(const void* __restrict__ a
     float r1 = 0.f, r2 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) { r1 += s1[i][tx]; r2 += s2[i][tx]; }
-    out[c] = r1;
-    out[cols + c] = r2;
+    partial[((int64_t)blockIdx.y * 2 + 0) * cols + c] = r1;
+    partial[((int64_t)blockIdx.y * 2 + 1) * cols + c] = r2;
   }
+}
+
+__global__ void __launch_bounds__(256) colsum2_stage2(const float* __restrict__ partial, int slices, int64_t cols,
+                                                      float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // over 2*cols
+  if (i >= 2 * cols) return;
+  const int64_t which = i / cols, c = i % cols;
+  float acc = 0.f;
+  for (int s = 0; s < slices; ++s) acc += partial[((int64_t)s * 2 + which) * cols + c];
+  out[i] = acc;
+}
+
+int colsum_slices(int64_t rows) {
+  int64_t s = rows / 128;
+  return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
 }
 
 }  // namespace
@@ -89,12 +107,22 @@ extern "C" int lbbnn_bf16_pack(const float* a, const float* b, int op, int64_t r
   return check_launch("bf16_pack");
 }
 
+extern "C" size_t lbbnn_colsum2_workspace_bytes(int64_t rows, int64_t cols) {
+  if (rows <= 0 || cols <= 0) return 0;
+  return (size_t)colsum_slices(rows) * 2 * cols * sizeof(float);
+}
+
 extern "C" int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols, float* out,
-                             lbbnn_stream s) {
+                             void* ws, size_t ws_bytes, lbbnn_stream s) {
   LBBNN_REQUIRE(a && out && rows > 0 && cols > 0, "bad input");
   LBBNN_REQUIRE(!a_is_bf16 || b, "bf16 mode needs both tensors");
-  const unsigned grid = (unsigned)ceil_div(cols, 32);
-  if (a_is_bf16) colsum2_kernel<true><<<grid, 256, 0, (cudaStream_t)s>>>(a, b, rows, cols, out);
-  else colsum2_kernel<false><<<grid, 256, 0, (cudaStream_t)s>>>(a, b, rows, cols, out);
-  return check_launch("colsum2");
+  LBBNN_REQUIRE(ws && ws_bytes >= lbbnn_colsum2_workspace_bytes(rows, cols), "colsum2 workspace too small");
+  const int slices = colsum_slices(rows);
+  const int64_t rps = ceil_div(rows, slices);
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)slices);
+  if (a_is_bf16) colsum2_stage1<true><<<grid, 256, 0, (cudaStream_t)s>>>(a, b, rows, cols, rps, (float*)ws);
+  else colsum2_stage1<false><<<grid, 256, 0, (cudaStream_t)s>>>(a, b, rows, cols, rps, (float*)ws);
+  if (int rc = check_launch("colsum2_stage1")) return rc;
+  colsum2_stage2<<<(unsigned)ceil_div(2 * cols, 256), 256, 0, (cudaStream_t)s>>>((const float*)ws, slices, cols, out);
+  return check_launch("colsum2_stage2");
 }

@@ -95,6 +95,48 @@ __global__ void logsoftmax_nll_kernel(const float* __restrict__ logits, const in
   }
 }
 
+// large batches: one warp per row over many blocks, per-block partial sums, then a fixed-order final sum
+__global__ void __launch_bounds__(256) logsoftmax_nll_rows(const float* __restrict__ logits, const int64_t* __restrict__ target,
+                                                           int64_t B, int64_t C, float* __restrict__ logp,
+                                                           float* __restrict__ partial, float* __restrict__ dlogits,
+                                                           float gscale) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t b = (int64_t)blockIdx.x * 8 + warp;
+  float local = 0.f;
+  if (b < B) {
+    const float* row = logits + b * C;
+    float mx = -INFINITY;
+    for (int64_t c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int64_t c = lane; c < C; c += 32) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    const int64_t t = target[b];
+    for (int64_t c = lane; c < C; c += 32) {
+      const float lp = row[c] - lse;
+      if (logp) logp[b * C + c] = lp;
+      if (dlogits) dlogits[b * C + c] = gscale * (expf(lp) - (c == t ? 1.0f : 0.0f));
+      if (c == t) local -= lp;
+    }
+  }
+  const float tot = block_sum(local, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(256) nll_final_sum(const float* __restrict__ partial, int n, float* __restrict__ nll_sum,
+                                                     int64_t* step_inc) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += (double)partial[i];
+  const double tot = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    if (nll_sum) *nll_sum = (float)tot;
+    if (step_inc) *step_inc += 1;
+  }
+}
+
 // torch.optim.Adam (single-tensor, non-amsgrad) on one flat fp32 buffer, 4 elements per thread
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
@@ -112,7 +154,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
     float pv[4], gv[4], mv[4], vv[4];
-    if (vec) {
+    if (vec && e0 + 3 < n) {
       const float4 a = *reinterpret_cast<const float4*>(p + e0), b = *reinterpret_cast<const float4*>(g + e0);
       const float4 c = *reinterpret_cast<const float4*>(m + e0), d = *reinterpret_cast<const float4*>(v + e0);
       pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
@@ -132,7 +174,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
       const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
       pv[j] -= step_size * (mv[j] / denom);
     }
-    if (vec) {
+    if (vec && e0 + 3 < n) {
       *reinterpret_cast<float4*>(p + e0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
       *reinterpret_cast<float4*>(m + e0) = make_float4(mv[0], mv[1], mv[2], mv[3]);
       *reinterpret_cast<float4*>(v + e0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
@@ -173,18 +215,28 @@ extern "C" int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64
 
 extern "C" int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t B, int64_t C, float* logp,
                                         float* nll_sum, float* dlogits, float grad_scale, int64_t* step_inc,
-                                        lbbnn_stream s) {
+                                        void* ws, size_t ws_bytes, lbbnn_stream s) {
   LBBNN_REQUIRE(logits && target && B > 0 && C > 0, "bad logits/target");
-  logsoftmax_nll_kernel<<<1, 1024, 0, (cudaStream_t)s>>>(logits, target, B, C, logp, nll_sum, dlogits, grad_scale,
-                                                         step_inc);
-  return check_launch("logsoftmax_nll");
+  if (B <= 512) {   // one block: no scratch needed
+    logsoftmax_nll_kernel<<<1, 1024, 0, (cudaStream_t)s>>>(logits, target, B, C, logp, nll_sum, dlogits, grad_scale,
+                                                           step_inc);
+    return check_launch("logsoftmax_nll");
+  }
+  const int64_t blocks = ceil_div(B, 8);
+  LBBNN_REQUIRE(ws && ws_bytes >= (size_t)blocks * sizeof(float), "loss workspace too small (need %lld bytes)",
+                (long long)(blocks * sizeof(float)));
+  logsoftmax_nll_rows<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(logits, target, B, C, logp, (float*)ws, dlogits,
+                                                                     grad_scale);
+  if (int rc = check_launch("logsoftmax_nll_rows")) return rc;
+  nll_final_sum<<<1, 256, 0, (cudaStream_t)s>>>((const float*)ws, (int)blocks, nll_sum, step_inc);
+  return check_launch("nll_final_sum");
 }
 
 extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                               float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s) {
   LBBNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "NULL argument");
-  int64_t blocks = ceil_div(ceil_div(n, 4), 256);
-  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  const int64_t blocks = ceil_div(ceil_div(n, 4), 256);   // one quad per thread: no grid-stride loop
+  LBBNN_REQUIRE(blocks < (1LL << 31), "flat buffer too large");
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
                                                              step_dev);
   return check_launch("adam");

@@ -71,8 +71,9 @@ SIGNATURES = {
                                 _P, _P, _P, _P, _P, _P, _P]),
     "lbbnn_tc_lrt_bwd_input": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P, _P]),
     "lbbnn_bf16_pack": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _P, _P, _P]),
-    "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P]),
-    "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P]),
+    "lbbnn_colsum2_workspace_bytes": (_SZ, [_I64, _I64]),
+    "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _SZ, _P]),
+    "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
 }
@@ -93,6 +94,8 @@ def check(rc):
 
 
 def ptr(t, dtype=torch.float32, allow_none=False):
+    if isinstance(dtype, bool):          # ptr(t, True) shorthand: fp32, None allowed
+        dtype, allow_none = torch.float32, dtype
     """Raw device pointer of a contiguous CUDA tensor (the only kind the library accepts)."""
     if t is None:
         if allow_none:

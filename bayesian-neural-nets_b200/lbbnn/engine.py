@@ -107,7 +107,7 @@ class LRTTrainer:
         # loss head; also bumps the step counter: noise above used step t-1, Adam below uses t
         K.check(K.lib.lbbnn_logsoftmax_nll_f32(K.ptr(self.acts[-1]), K.ptr(self.y, torch.int64), self.B, C, None,
                                                self.stats.data_ptr(), K.ptr(self.gbuf[-1]), 1.0,
-                                               K.ptr(self.step_dev, torch.int64), st))
+                                               K.ptr(self.step_dev, torch.int64), ws, wsn, st))
         n_launch += 1
         klg = 1.0 / (self.num_batches * self.world)   # KL is replicated on every rank: its grad is added once
         for i in reversed(range(L)):
@@ -177,3 +177,186 @@ class LRTTrainer:
     @property
     def d2h_bytes_per_step(self):
         return self.stats_host.numel() * 4
+
+
+class LRTTensorCoreTrainer:
+    """Whole-step runner for WIDE LRT stacks in bf16 on the tensor cores (BASELINE.json configs[4]:
+    4096-4096-4096-10, batch 8192).  Master parameters, KL, chain rule and Adam stay fp32; the GEMM
+    operands (x, x^2, M, V and the backward's dE, dS) are bf16 with fp32 accumulation in TMEM.
+
+    Forward and dW GEMM pairs of EVERY layer run on the tcgen05 dual-GEMM kernel (ragged shapes such as
+    the 10-class output are zero-filled by TMA).  The input-gradient GEMM of a layer whose out_features
+    is not a multiple of 8 (the classifier: its contraction dim would break the TMA pitch) runs on the
+    fp32 SIMT kernel instead.  Same reference step as LRTTrainer (LBBNN-GP-MF-LRT.py:217-229).
+    """
+
+    def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
+                 use_graph=True, inject_noise=False, process_group=None):
+        K.require_device()
+        self.net = net
+        self.layers = list(net.layers)
+        L = len(self.layers)
+        for l in self.layers:
+            if l.in_features % 8:
+                raise K.LbbnnError("tensor-core layers need in_features divisible by 8 (TMA pitch)")
+        self.B = int(batch_size)
+        if self.B % 8:
+            raise K.LbbnnError("batch must be divisible by 8 (the dW GEMM contracts over it)")
+        self.num_batches = int(num_batches)
+        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.seed = _lrt.current_seed() if seed is None else int(seed)
+        self.pg = process_group
+        self.world = 1 if process_group is None else torch.distributed.get_world_size(process_group)
+        self.rank = 0 if process_group is None else torch.distributed.get_rank(process_group)
+        dev = self.layers[0].weight_mu.device
+        self.device = dev
+
+        offs, total = [], 0
+        for l in self.layers:
+            for name in _PARAM_NAMES:
+                p = getattr(l, name)
+                offs.append((l, name, total, p.numel(), p.shape))
+                total += _pad4(p.numel())
+        self.n_flat = total
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        self.flat, self.gflat = torch.zeros(total, **f32), torch.zeros(total, **f32)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(total, **f32), torch.zeros(total, **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.no_grad():
+            for l, name, off, n, shape in offs:
+                p = getattr(l, name)
+                view = self.flat[off:off + n].view(shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.gflat[off:off + n].view(shape)
+
+        B = self.B
+        sizes = [(l.in_features, l.out_features) for l in self.layers]
+        self.sizes = sizes
+        self.simt_dx = [o % 8 != 0 for _, o in sizes]       # input-gradient GEMM on the fp32 SIMT kernel
+        self.x = torch.zeros(B, sizes[0][0], **f32)
+        self.y = torch.zeros(B, dtype=torch.int64, device=dev)
+        self.x_bf, self.x2_bf = torch.zeros(B, sizes[0][0], **bf), torch.zeros(B, sizes[0][0], **bf)
+        self.xT_bf, self.x2T_bf = torch.zeros(sizes[0][0], B, **bf), torch.zeros(sizes[0][0], B, **bf)
+        maxnk = max(i * o for i, o in sizes)
+        self.M32, self.V32 = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)     # prologue out, reused
+        self.dM, self.dV = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)       # dW GEMM out, reused
+        self.tc = []
+        for li, (i, o) in enumerate(sizes):
+            last = li == L - 1
+            need_g32 = last or self.simt_dx[li + 1]        # dL/d(pre-activation) arrives in fp32
+            need_act32 = last or self.simt_dx[li + 1]      # fp32 activations: logits / input of a SIMT dX
+            tc_dx = li > 0 and not self.simt_dx[li]
+            d = dict(
+                M=torch.zeros(o, i, **bf), V=torch.zeros(o, i, **bf),
+                MT=torch.zeros(i, o, **bf) if tc_dx else None, VT=torch.zeros(i, o, **bf) if tc_dx else None,
+                mv32=torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) if (li > 0 and self.simt_dx[li]) else None,
+                act=None if last else torch.zeros(B, o, **bf), act2=None if last else torch.zeros(B, o, **bf),
+                actT=None if last else torch.zeros(o, B, **bf), act2T=None if last else torch.zeros(o, B, **bf),
+                dsf=torch.zeros(B, o, **f32), act32=torch.zeros(B, o, **f32) if need_act32 else None,
+                g32=torch.zeros(B, o, **f32) if need_g32 else None,
+                dE=torch.zeros(B, o, **bf), dS=torch.zeros(B, o, **bf),
+                dET=torch.zeros(o, B, **bf), dST=torch.zeros(o, B, **bf),
+                colsum=torch.zeros(2 * o, **f32),
+                eps=torch.zeros(B, o, **f32) if inject_noise else None)
+            self.tc.append(d)
+        self.inject = inject_noise
+        self.stats = torch.zeros(1 + L, **f32)
+        nbytes = max([1 << 20, B // 8 * 4 + 1024] +
+                     [int(K.lib.lbbnn_colsum2_workspace_bytes(B, o)) for _, o in sizes] +
+                     [K.lrt_workspace_bytes(B, i, o) for (i, o), sd in zip(sizes, self.simt_dx) if sd])
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.x_host = torch.zeros(B, sizes[0][0], dtype=torch.float32).pin_memory()
+        self.y_host = torch.zeros(B, dtype=torch.int64).pin_memory()
+        self.stats_host = torch.zeros(1 + L, dtype=torch.float32).pin_memory()
+        self.kernels_per_step = 0
+        self.graph = None
+        if use_graph:
+            self._capture()
+
+    def _noise(self, i):
+        if self.inject:
+            return K.make_noise(self.tc[i]["eps"])
+        return K.make_noise(None, self.seed + 0x9E3779B97F4A7C15 * self.rank, i, self.step_dev, len(self.layers))
+
+    def _enqueue(self):
+        st = K.current_stream()
+        L, B, bf = len(self.layers), self.B, torch.bfloat16
+        ws, wsn = self.ws.data_ptr(), self.ws.numel()
+        lib, P = K.lib, K.ptr
+        n = 0
+        descs = [K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+                 for l in self.layers]
+        # input staging: x, x^2 and their transposes in bf16
+        K.check(lib.lbbnn_bf16_pack(P(self.x), None, K.PACK_SQUARE, B, self.sizes[0][0], P(self.x_bf, bf),
+                                    P(self.x2_bf, bf), P(self.xT_bf, bf), P(self.x2T_bf, bf), st)); n += 1
+        a, a2 = self.x_bf, self.x2_bf
+        for i in range(L):
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            last = i == L - 1
+            if d["mv32"] is not None:      # keep the fp32 M,V of this layer for its SIMT input-gradient GEMM
+                M32 = d["mv32"]
+                V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
+            else:
+                M32, V32 = self.M32, self.V32
+            K.check(lib.lbbnn_lrt_f32_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, K.FLAG_SAMPLE, P(M32), P(V32),
+                                               self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
+            K.check(lib.lbbnn_bf16_pack(P(M32), P(V32), K.PACK_PAIR, fo, fi, P(d["M"], bf), P(d["V"], bf),
+                                        P(d["MT"], bf, True), P(d["VT"], bf, True), st)); n += 1
+            K.check(lib.lbbnn_tc_lrt_fwd(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data),
+                                         P(l.bias_rho.data), self._noise(i),
+                                         K.FLAG_SAMPLE | (0 if last else K.FLAG_RELU),
+                                         P(d["act"], bf, True), P(d["act2"], bf, True), P(d["actT"], bf, True),
+                                         P(d["act2T"], bf, True), P(d["dsf"]), P(d["act32"], allow_none=True), st)); n += 1
+            a, a2 = d["act"], d["act2"]
+        dl = self.tc[-1]
+        K.check(lib.lbbnn_logsoftmax_nll_f32(P(dl["act32"]), P(self.y, torch.int64), B, self.sizes[-1][1], None,
+                                             self.stats.data_ptr(), P(dl["g32"]), 1.0,
+                                             P(self.step_dev, torch.int64), ws, wsn, st)); n += 2 if B > 512 else 1
+        klg = 1.0 / (self.num_batches * self.world)
+
+        def grads_of(l):
+            return K.LayerGrads(*[t.data_ptr() for t in (l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad,
+                                                         l.bias_mu.grad, l.bias_rho.grad)], None)
+
+        for i in reversed(range(L)):
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            if d["g32"] is not None:       # fp32 upstream gradient: stage dE, dS (+ transposes) and the bias sums
+                K.check(lib.lbbnn_bf16_pack(P(d["g32"]), P(d["dsf"]), K.PACK_SCALE, B, fo, P(d["dE"], bf), P(d["dS"], bf),
+                                            P(d["dET"], bf), P(d["dST"], bf), st)); n += 1
+                K.check(lib.lbbnn_colsum2(P(d["g32"]), P(d["dsf"]), 0, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
+            else:
+                K.check(lib.lbbnn_colsum2(P(d["dE"], bf), P(d["dS"], bf), 1, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
+            xT, x2T = (self.xT_bf, self.x2T_bf) if i == 0 else (self.tc[i - 1]["actT"], self.tc[i - 1]["act2T"])
+            # dM = dE^T x, dV = dS^T x^2: (out, B) x (in, B)^T
+            K.check(lib.lbbnn_tc_dual_gemm_raw(P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B,
+                                               P(self.dM), P(self.dV), st)); n += 1
+            K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(self.dM), P(self.dV), P(d["colsum"]), l.cfg.priors,
+                                               l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, grads_of(l), st)); n += 1
+            if i == 0:
+                continue
+            p = self.tc[i - 1]
+            if self.simt_dx[i]:
+                K.check(lib.lbbnn_lrt_f32_bwd_input(descs[i], P(p["act32"]), B, P(d["g32"]), P(d["dsf"]), l.cfg.priors,
+                                                    l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(d["mv32"]),
+                                                    P(p["g32"]), ws, wsn, st)); n += 2
+            else:
+                K.check(lib.lbbnn_tc_lrt_bwd_input(P(d["dE"], bf), P(d["dS"], bf), P(d["MT"], bf), P(d["VT"], bf), B, fi,
+                                                   fo, P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
+                                                   P(p["dE"], bf), P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf),
+                                                   st)); n += 1
+        if self.pg is not None:
+            torch.distributed.all_reduce(self.gflat, group=self.pg)
+        K.check(lib.lbbnn_adam_f32(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
+                                   self.lr, self.betas[0], self.betas[1], self.eps, P(self.step_dev, torch.int64),
+                                   st)); n += 1
+        self.kernels_per_step = n
+
+    _capture = LRTTrainer._capture
+    step_device = LRTTrainer.step_device
+    step = LRTTrainer.step
+    h2d_bytes_per_step = LRTTrainer.h2d_bytes_per_step
+    d2h_bytes_per_step = LRTTrainer.d2h_bytes_per_step

@@ -23,10 +23,12 @@ for p in (os.path.join(ROOT, "bayesian-neural-nets_b200"), os.path.join(ROOT, "t
 import numpy as np
 import torch
 
-SIZES = {"lrt_mnist": (784, 400, 600, 10)}
-BATCH = {"lrt_mnist": 100}
+SIZES = {"lrt_mnist": (784, 400, 600, 10), "lrt_wide": (4096, 4096, 4096, 10)}
+BATCH = {"lrt_mnist": 100, "lrt_wide": 8192}
+DTYPE = {"lrt_mnist": "f32", "lrt_wide": "bf16"}
+POOLS = {"lrt_mnist": 512, "lrt_wide": 4}      # lrt_wide: one 134 MB batch already exceeds L2
 NUM_BATCHES = 600
-POOL = 512          # distinct input batches: 512 x 313.6 KB = 160 MB > 126 MB L2
+POOL = 512          # default number of distinct input batches (lrt_mnist: 512 x 313.6 KB = 160 MB > 126 MB L2)
 
 
 def load_peaks():
@@ -98,10 +100,10 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # synthetic data: x ~ U[0,1) (MNIST ToTensor range), y ~ randint(10)
 # ------------------------------------------------------------------------------------------------
-def make_pool(batch, in_features, classes, seed):
+def make_pool(pool, batch, in_features, classes, seed):
     rng = np.random.default_rng(seed)
-    x = torch.from_numpy(rng.random((POOL, batch, in_features), dtype=np.float32))
-    y = torch.from_numpy(rng.integers(0, classes, size=(POOL, batch))).long()
+    x = torch.from_numpy(rng.random((pool, batch, in_features), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, classes, size=(pool, batch))).long()
     return x, y
 
 
@@ -118,13 +120,14 @@ def cpu_reference_steps(workload, steps, warmup, budget_s=20.0):
     layers = [{k: v.clone().requires_grad_(True) for k, v in O.init_lrt_params(rng, i, o).items()}
               for i, o in zip(sizes[:-1], sizes[1:])]
     opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
-    x = torch.from_numpy(rng.random((8, B, sizes[0]), dtype=np.float32))
-    y = torch.from_numpy(rng.integers(0, sizes[-1], size=(8, B))).long()
+    nb = 8 if B <= 1000 else 1
+    x = torch.from_numpy(rng.random((nb, B, sizes[0]), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, sizes[-1], size=(nb, B))).long()
 
     def one(i):
         eps = [torch.randn(B, o) for o in sizes[1:]]            # LRT:174
         opt.zero_grad(set_to_none=True)
-        loss, _, _, _ = O.lrt_net_loss(x[i % 8], y[i % 8], layers, eps, NUM_BATCHES)
+        loss, _, _, _ = O.lrt_net_loss(x[i % nb], y[i % nb], layers, eps, NUM_BATCHES)
         loss.backward()
         opt.step()
         return loss
@@ -154,7 +157,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s",
             "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, 1),
+            "config": workload_config(args.workload, 1),  # the CPU reference computes in fp32
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -163,6 +166,7 @@ def run_reference(args):
 
 def workload_config(workload, n_gpus):
     sizes, B = SIZES[workload], BATCH[workload]
+    POOL = POOLS[workload]
     return {"workload": f"{workload}: LRT MLP {'-'.join(map(str, sizes))}, batch {B} per GPU, "
                         f"fwd+loss+bwd+Adam, NUM_BATCHES={NUM_BATCHES}",
             "batch_per_gpu": B, "global_batch": B * n_gpus,
@@ -226,6 +230,43 @@ def profile_calls(tr, reps=20):
     return out
 
 
+def profile_calls_wide(tr, reps=5):
+    """Tensor-core GEMM calls of one wide step timed on their own (CUDA events, operands > L2): FLOPs are the
+    ALGORITHMIC 2 GEMMs x 2 B in out per call."""
+    from lbbnn import _capi as K
+    bf, st, B = torch.bfloat16, K.current_stream(), tr.B
+    P = K.ptr
+    out = []
+    i = 1 if len(tr.layers) > 2 else 0
+    l, d = tr.layers[i], tr.tc[i]
+    fi, fo = tr.sizes[i]
+    a, a2 = (tr.x_bf, tr.x2_bf) if i == 0 else (tr.tc[i - 1]["act"], tr.tc[i - 1]["act2"])
+    xT, x2T = (tr.xT_bf, tr.x2T_bf) if i == 0 else (tr.tc[i - 1]["actT"], tr.tc[i - 1]["act2T"])
+    calls = [(f"tc_lrt_fwd[l{i + 1}] (tcgen05 dual GEMM + eps/sqrt/relu epilogue)", lambda: K.lib.lbbnn_tc_lrt_fwd(
+        P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data), P(l.bias_rho.data), tr._noise(i),
+        K.FLAG_SAMPLE | K.FLAG_RELU, P(d["act"], bf), P(d["act2"], bf), P(d["actT"], bf), P(d["act2T"], bf), P(d["dsf"]),
+        P(d["act32"], allow_none=True), st)),
+        (f"tc_dual_gemm_raw[l{i + 1}] (dM, dV)", lambda: K.lib.lbbnn_tc_dual_gemm_raw(
+            P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B, P(tr.dM), P(tr.dV), st))]
+    if i > 0:
+        p = tr.tc[i - 1]
+        calls.append((f"tc_lrt_bwd_input[l{i + 1}] (dx + relu mask + next dE/dS epilogue)", lambda: K.lib.lbbnn_tc_lrt_bwd_input(
+            P(d["dE"], bf), P(d["dS"], bf), P(d["MT"], bf), P(d["VT"], bf), B, fi, fo, P(p["act"], bf), P(p["dsf"]),
+            K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf), P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf), st)))
+    flops = 2 * 2.0 * B * fi * fo
+    for name, fn in calls:
+        for _ in range(2):
+            K.check(fn())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            K.check(fn())
+        e1.record()
+        e1.synchronize()
+        out.append({"name": name, "us": e0.elapsed_time(e1) / reps * 1e3, "flops": flops})
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def _mark(msg):
     if os.environ.get("LBBNN_BENCH_VERBOSE"):
@@ -252,15 +293,17 @@ def run_ours(args):
         pg = dist.group.WORLD
 
     workload = args.workload
-    sizes, B = SIZES[workload], BATCH[workload]
+    sizes, B, POOL = SIZES[workload], BATCH[workload], POOLS[workload]
+    wide = workload == "lrt_wide"
     torch.manual_seed(0)                       # identical initial parameters on every rank
     lbbnn.manual_seed(1234)
     net = lbbnn.BayesianNetwork(sizes).to(dev)
     _mark("process group up, building trainer")
-    tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+    Trainer = lbbnn.LRTTensorCoreTrainer if wide else lbbnn.LRTTrainer
+    tr = Trainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
     _mark("trainer captured")
 
-    pool_x_host, pool_y_host = make_pool(B, sizes[0], sizes[-1], seed=1000 + rank)
+    pool_x_host, pool_y_host = make_pool(POOL, B, sizes[0], sizes[-1], seed=1000 + rank)
     pool_x_host, pool_y_host = pool_x_host.pin_memory(), pool_y_host.pin_memory()
     pool_x, pool_y = pool_x_host.to(dev), pool_y_host.to(dev)
 
@@ -314,30 +357,46 @@ def run_ours(args):
 
     if rank == 0:
         peaks = load_peaks()
-        prof = profile_calls(tr)
-        top = max(prof, key=lambda r: r["us"])
-        achieved = top["bytes"] / (top["us"] * 1e-6) / 1e9
-        step_bytes = sum(r["bytes"] for r in prof)
-        cpu = cpu_reference_steps(workload, steps=60, warmup=3, budget_s=15.0) if world == 1 else None
+        if wide:
+            prof = profile_calls_wide(tr)
+            top = max(prof, key=lambda r: r["us"])
+            ach = top["flops"] / (top["us"] * 1e-6) / 1e12
+            step_flops = sum(2 * 2.0 * B * i * o * (3 if li > 0 else 2) for li, (i, o) in enumerate(zip(sizes[:-1], sizes[1:])))
+            roof = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "us_per_launch": top["us"], "flops_per_launch": top["flops"],
+                    "timing": "kernel alone, operands larger than L2, CUDA events, mean of 5; burst peak"}
+            step_roof = {"flops_per_step": step_flops, "achieved_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12,
+                         "frac_of_sustained_peak": step_flops / (ms / args.steps * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
+            kern = [{"name": r["name"], "us": round(r["us"], 1), "tflops": round(r["flops"] / r["us"] / 1e6, 1)} for r in prof]
+        else:
+            prof = profile_calls(tr)
+            top = max(prof, key=lambda r: r["us"])
+            achieved = top["bytes"] / (top["us"] * 1e-6) / 1e9
+            step_bytes = sum(r["bytes"] for r in prof)
+            roof = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peaks["hbm_gbs"],
+                    "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
+                    "peak_source": peaks["source"], "us_per_launch": top["us"], "bytes_per_launch": top["bytes"],
+                    "timing": "cold L2 (256 MB memset before each launch), CUDA events, mean of 20"}
+            step_roof = {"bytes_per_step": step_bytes, "hbm_floor_us": step_bytes / peaks["hbm_gbs"] / 1e3,
+                         "sum_of_calls_us_cold": sum(r["us"] for r in prof),
+                         "frac_of_hbm_floor": (step_bytes / peaks["hbm_gbs"] / 1e3) / (ms / args.steps * 1e3)}
+            kern = [{"name": r["name"], "us": round(r["us"], 2), "bytes": r["bytes"],
+                     "gbps": round(r["bytes"] / r["us"] / 1e3, 1)} for r in prof]
+        cpu = None
+        if world == 1:
+            cpu = cpu_reference_steps(workload, steps=2 if wide else 60, warmup=1 if wide else 3, budget_s=15.0)
         line = {
             "metric": "train_samples_per_sec", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE[workload], "data": "synthetic",
             "config": workload_config(workload, world),
             "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s",
                     "h2d_bytes_per_step": tr.h2d_bytes_per_step, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
                     "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": tr.kernels_per_step * args.steps,
             "kernels_per_step": tr.kernels_per_step,
-            "roofline": {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peaks["hbm_gbs"],
-                         "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"], "traffic": None,
-                         "peak_source": peaks["source"], "us_per_launch": top["us"], "bytes_per_launch": top["bytes"],
-                         "timing": "cold L2 (256 MB memset before each launch), CUDA events, mean of 20"},
-            "step_roofline": {"bytes_per_step": step_bytes, "hbm_floor_us": step_bytes / peaks["hbm_gbs"] / 1e3,
-                              "sum_of_calls_us_cold": sum(r["us"] for r in prof),
-                              "frac_of_hbm_floor": (step_bytes / peaks["hbm_gbs"] / 1e3) / (ms / args.steps * 1e3)},
-            "kernels": [{"name": r["name"], "us": round(r["us"], 2), "bytes": r["bytes"],
-                         "gbps": round(r["bytes"] / r["us"] / 1e3, 1)} for r in prof],
+            "roofline": roof, "step_roofline": step_roof, "kernels": kern,
             "clocks": clocks,
             "last_loss": out["loss"],
         }

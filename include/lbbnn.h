@@ -175,16 +175,18 @@ LBBNN_API int lbbnn_bf16_pack(const float* a, const float* b, int op, int64_t ro
                               void* out1, void* out2, void* out1T, void* out2T, lbbnn_stream s);
 /* column sums over the batch: out[0..cols) = sum_r a, out[cols..2cols) = sum_r a*b (fixed order).
  * a_is_bf16: a and b(=second operand, already the product) are bf16 tensors dE, dS instead. */
+LBBNN_API size_t lbbnn_colsum2_workspace_bytes(int64_t rows, int64_t cols);
 LBBNN_API int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols,
-                            float* out, lbbnn_stream s);
+                            float* out, void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
  * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.
  * step_inc (device int64 or NULL) is incremented by one: the trainer's step counter, bumped between
- * the forward (noise of step t) and the optimizer (bias correction t+1) without an extra launch. */
+ * the forward (noise of step t) and the optimizer (bias correction t+1) without an extra launch.
+ * batch > 512 runs multi-block and needs a workspace of ceil(batch/8) floats (NULL is fine below that). */
 LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
                                        float* logp, float* nll_sum, float* dlogits, float grad_scale,
-                                       int64_t* step_inc, lbbnn_stream s);
+                                       int64_t* step_inc, void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 /* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
  * step_dev: device int64 holding t, the 1-based index of THIS update. */
