@@ -9,10 +9,12 @@
 //   dX        A = (dE, dS)        B = (M^T, V^T)      epilogue: dx = D1 + 2 x D2, relu mask, next dE/dS
 //   dW        A = (dE^T, dS^T)    B = (x^T, x^2^T)    epilogue: dM = D1, dV = D2 (fp32, for finalize)
 //
-// Kernel shape: persistent, one CTA per SM, 192 threads =
+// Kernel shape: persistent, one CTA per SM, 320 threads =
 //   warp 0      TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4 boxes of 128x64 bf16 per stage)
 //   warp 1      MMA issuer     (one elected lane: tcgen05.mma.cta_group::1.kind::f16, M=128 N=128 K=16)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b.x32 -> registers -> math -> global)
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b.x16 -> registers -> math -> global; two warps per TMEM
+//                               lane quarter, one per 64-column half; r01: with 4 warps the fwd epilogue
+//                               took ~2x the MMA time of a tile)
 // smem: 3 stages x 64 KB ring (full/empty mbarriers); TMEM: 512 columns = 2 accumulator stages x
 // (D1: 128 cols, D2: 128 cols), so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
@@ -27,9 +29,12 @@ constexpr int UMMA_K = 16;
 constexpr int kStages = 3;
 constexpr int kTileBytes = BM * BK * 2;         // 16 KB per operand tile
 constexpr int kStageBytes = 4 * kTileBytes;     // A1, A2, B1, B2
-constexpr int kTcThreads = 192;
+constexpr int kEpiWarps = 8;                    // 2 per TMEM lane quarter: each takes one 64-column half of the tile
+constexpr int kTcThreads = 64 + kEpiWarps * 32; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EW = 16;                          // epilogue chunk: columns per tcgen05.ld
+constexpr int kBiasBytes = 2 * 2 * BN * 4;      // [accumulator stage][b_mu | sigma_b^2][BN]
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -124,6 +129,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -146,49 +163,49 @@ struct TcEpi {
   __nv_bfloat16 *de, *ds, *deT, *dsT;                    // next (previous-layer) dE, dS and transposes
 };
 
-// one thread = one output row (TMEM lane), 32 consecutive columns
+// one thread = one output row (TMEM lane), EW consecutive columns; sbias = this tile's b_mu[BN] | sigma_b^2[BN]
 __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, int64_t M, int64_t N, int64_t row, int64_t col0,
-                                               const float d1[32], const float d2[32]) {
+                                               const float* __restrict__ sbias, int cl, const float d1[EW],
+                                               const float d2[EW]) {
   if (row >= M) return;
-  const bool fullc = col0 + 31 < N;
+  const bool fullc = col0 + EW - 1 < N;
   if (e.mode == LBBNN_TC_EPI_RAW) {
     float* p1 = e.d1 + row * N + col0;
     float* p2 = e.d2 + row * N + col0;
     if (fullc && (N % 4 == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
+      for (int j = 0; j < EW; j += 4) {
         *reinterpret_cast<float4*>(p1 + j) = make_float4(d1[j], d1[j + 1], d1[j + 2], d1[j + 3]);
         *reinterpret_cast<float4*>(p2 + j) = make_float4(d2[j], d2[j + 1], d2[j + 2], d2[j + 3]);
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < EW; ++j)
         if (col0 + j < N) { p1[j] = d1[j]; p2[j] = d2[j]; }
     }
     return;
   }
-  float o[32], o2[32];
+  float o[EW], o2[EW];
   if (e.mode == LBBNN_TC_EPI_FWD) {
     // act = D1 + b_mu + sqrt(D2 + sigma_b^2) eps  (LRT:172-175); ds factor = eps / (2 sd)
-    float ep[32];
+    float ep[EW];
     if (nz.ptr) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ep[j] = (col0 + j < N) ? __ldg(nz.ptr + row * N + col0 + j) : 0.f;
+      for (int j = 0; j < EW; ++j) ep[j] = (col0 + j < N) ? __ldg(nz.ptr + row * N + col0 + j) : 0.f;
     } else if (N % 4 == 0) {   // quads of the flat (M,N) index are aligned with this row's columns
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) philox_normal4(nz.seed, nz.stream, ((uint64_t)row * (uint64_t)N + (uint64_t)(col0 + j)) >> 2, ep + j);
+      for (int j = 0; j < EW; j += 4) philox_normal4(nz.seed, nz.stream, ((uint64_t)row * (uint64_t)N + (uint64_t)(col0 + j)) >> 2, ep + j);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) ep[j] = philox_normal1(nz.seed, nz.stream, (uint64_t)row * (uint64_t)N + (uint64_t)(col0 + j));
+      for (int j = 0; j < EW; ++j) ep[j] = philox_normal1(nz.seed, nz.stream, (uint64_t)row * (uint64_t)N + (uint64_t)(col0 + j));
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < EW; ++j) {
       const int64_t n = col0 + j;
       float v = 0.f, f = 0.f;
       if (n < N) {
-        const float sb = sigma_of(__ldg(e.bias_rho + n));
-        const float sd = sqrtf(fmaxf(d2[j], 0.f) + sb * sb);
-        v = d1[j] + __ldg(e.bias_mu + n) + sd * ep[j];
+        const float sd = sqrtf(fmaxf(d2[j], 0.f) + sbias[BN + cl + j]);
+        v = d1[j] + sbias[cl + j] + sd * ep[j];
         f = ep[j] / (2.0f * sd);
         if (e.flags & LBBNN_FLAG_RELU) v = fmaxf(v, 0.f);
       }
@@ -199,13 +216,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     if (e.o_f32 || e.dsf) {
       if (v4) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
+        for (int j = 0; j < EW; j += 4) {
           if (e.o_f32) *reinterpret_cast<float4*>(e.o_f32 + row * N + col0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           if (e.dsf) *reinterpret_cast<float4*>(e.dsf + row * N + col0 + j) = make_float4(o2[j], o2[j + 1], o2[j + 2], o2[j + 3]);
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < EW; ++j)
           if (col0 + j < N) {
             if (e.o_f32) e.o_f32[row * N + col0 + j] = o[j];
             if (e.dsf) e.dsf[row * N + col0 + j] = o2[j];
@@ -215,7 +232,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     // row-major bf16: act, act^2
     if (fullc && (N % 8 == 0)) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 8) {
+      for (int j = 0; j < EW; j += 8) {
         uint4 a, b;
         a.x = pack_bf16(o[j], o[j + 1]); a.y = pack_bf16(o[j + 2], o[j + 3]); a.z = pack_bf16(o[j + 4], o[j + 5]); a.w = pack_bf16(o[j + 6], o[j + 7]);
         b.x = pack_bf16(o[j] * o[j], o[j + 1] * o[j + 1]); b.y = pack_bf16(o[j + 2] * o[j + 2], o[j + 3] * o[j + 3]);
@@ -225,7 +242,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < EW; ++j)
         if (col0 + j < N) {
           if (e.o_bf) e.o_bf[row * N + col0 + j] = __float2bfloat16_rn(o[j]);
           if (e.o2_bf) e.o2_bf[row * N + col0 + j] = __float2bfloat16_rn(o[j] * o[j]);
@@ -234,7 +251,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     // transposed bf16 (N,M): lanes of a warp are consecutive rows -> coalesced 64 B per column
     if (e.oT_bf) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < EW; ++j)
         if (col0 + j < N) {
           e.oT_bf[(col0 + j) * M + row] = __float2bfloat16_rn(o[j]);
           e.o2T_bf[(col0 + j) * M + row] = __float2bfloat16_rn(o[j] * o[j]);
@@ -243,10 +260,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     return;
   }
   // LBBNN_TC_EPI_DX: dx = D1 + 2 x D2; through the relu that produced x; dS_prev = dx * dsf_prev
-  float xv[32], fv[32];
+  float xv[EW], fv[EW];
   if (fullc && (N % 8 == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < EW; j += 8) {
       const uint4 u = *reinterpret_cast<const uint4*>(e.x_bf + row * N + col0 + j);
       const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
@@ -256,20 +273,20 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
       }
     }
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < EW; j += 4) {
       const float4 f4 = e.dsf_prev ? *reinterpret_cast<const float4*>(e.dsf_prev + row * N + col0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
       fv[j] = f4.x; fv[j + 1] = f4.y; fv[j + 2] = f4.z; fv[j + 3] = f4.w;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
+    for (int j = 0; j < EW; ++j) {
       const bool ok = col0 + j < N;
       xv[j] = ok ? __bfloat162float(e.x_bf[row * N + col0 + j]) : 0.f;
       fv[j] = (ok && e.dsf_prev) ? e.dsf_prev[row * N + col0 + j] : 0.f;
     }
   }
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < EW; ++j) {
     float g = fmaf(2.0f * xv[j], d2[j], d1[j]);
     if ((e.flags & LBBNN_FLAG_MASK_DX) && !(xv[j] > 0.f)) g = 0.f;
     o[j] = g;
@@ -277,7 +294,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
   }
   if (fullc && (N % 8 == 0)) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 8) {
+    for (int j = 0; j < EW; j += 8) {
       uint4 a, b;
       a.x = pack_bf16(o[j], o[j + 1]); a.y = pack_bf16(o[j + 2], o[j + 3]); a.z = pack_bf16(o[j + 4], o[j + 5]); a.w = pack_bf16(o[j + 6], o[j + 7]);
       b.x = pack_bf16(o2[j], o2[j + 1]); b.y = pack_bf16(o2[j + 2], o2[j + 3]); b.z = pack_bf16(o2[j + 4], o2[j + 5]); b.w = pack_bf16(o2[j + 6], o2[j + 7]);
@@ -286,7 +303,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < EW; ++j)
       if (col0 + j < N) {
         e.de[row * N + col0 + j] = __float2bfloat16_rn(o[j]);
         e.ds[row * N + col0 + j] = __float2bfloat16_rn(o2[j]);
@@ -294,7 +311,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
   }
   if (e.deT) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < EW; ++j)
       if (col0 + j < N) {
         e.deT[(col0 + j) * M + row] = __float2bfloat16_rn(o[j]);
         e.dsT[(col0 + j) * M + row] = __float2bfloat16_rn(o2[j]);
@@ -315,6 +332,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]        MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]      epilogue -> MMA
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* sbias_all = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_m = (M + BM - 1) / BM, num_n = (N + BN - 1) / BN;
@@ -323,7 +341,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], kEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_holder, kTmemCols);
@@ -379,24 +397,38 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue warps (2..5): TMEM lane quarter = warp % 4 =====
+    // ===== epilogue warps (2..9): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     Noise nz = epi.noise;
     nz.resolve();
-    const int q = warp & 3;
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
       const int m0 = (t % num_m) * BM, n0 = (t / num_m) * BN;
+      float* sbias = sbias_all + as * 2 * BN;
+      if (epi.mode == LBBNN_TC_EPI_FWD) {                 // this tile's bias terms, once per column
+        const int c = et & (BN - 1);
+        const int64_t n = n0 + c;
+        float v = 0.f;
+        if (n < N) {
+          if (et < BN) v = __ldg(epi.bias_mu + n);
+          else { const float sb = sigma_of(__ldg(epi.bias_rho + n)); v = sb * sb; }
+        }
+        sbias[(et < BN ? 0 : BN) + c] = v;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        float v1[32], v2[32];
-        tmem_ld32(tbase + c * 32, v1);
-        tmem_ld32(tbase + 128 + c * 32, v2);
-        epilogue_chunk(epi, nz, M, N, row, n0 + c * 32, v1, v2);
+      for (int c = 0; c < 64 / EW; ++c) {
+        float v1[EW], v2[EW];
+        tmem_ld16(tbase + c * EW, v1);
+        tmem_ld16(tbase + 128 + c * EW, v2);
+        const int cl = half * 64 + c * EW;
+        epilogue_chunk(epi, nz, M, N, row, n0 + cl, sbias, cl, v1, v2);
       }
       tc_fence_before();
       __syncwarp();

@@ -138,17 +138,17 @@ __global__ void __launch_bounds__(256) nll_final_sum(const float* __restrict__ p
 }
 
 // torch.optim.Adam (single-tensor, non-amsgrad) on one flat fp32 buffer, 4 elements per thread
+// bias corrections of step t, computed once (double pow) instead of in every block
+__global__ void adam_prepare(const int64_t* __restrict__ step_dev, float lr, float b1, float b2, float* __restrict__ coef) {
+  const double t = (double)(*step_dev);
+  coef[0] = lr / (float)(1.0 - pow((double)b1, t));        // step_size = lr / bias_correction1
+  coef[1] = (float)sqrt(1.0 - pow((double)b2, t));         // sqrt(bias_correction2)
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                   float* __restrict__ m, float* __restrict__ v, int64_t n, float lr,
-                                                   float b1, float b2, float eps, const int64_t* __restrict__ step_dev) {
-  __shared__ float sh[2];
-  if (threadIdx.x == 0) {
-    const double t = (double)(*step_dev);
-    sh[0] = lr / (float)(1.0 - pow((double)b1, t));        // step_size = lr / bias_correction1
-    sh[1] = (float)sqrt(1.0 - pow((double)b2, t));         // sqrt(bias_correction2)
-  }
-  __syncthreads();
-  const float step_size = sh[0], bc2_sqrt = sh[1];
+                                                   float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                                   float b1, float b2, float eps, const float* __restrict__ coef) {
+  const float step_size = __ldg(coef), bc2_sqrt = __ldg(coef + 1);
   const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
   const int64_t nq = ceil_div(n, 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
@@ -233,12 +233,15 @@ extern "C" int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* targ
 }
 
 extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                              float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s) {
-  LBBNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && n > 0, "NULL argument");
+                              float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
+                              lbbnn_stream s) {
+  LBBNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && coef_scratch && n > 0, "NULL argument");
+  adam_prepare<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef_scratch);
+  if (int rc = check_launch("adam_prepare")) return rc;
   const int64_t blocks = ceil_div(ceil_div(n, 4), 256);   // one quad per thread: no grid-stride loop
   LBBNN_REQUIRE(blocks < (1LL << 31), "flat buffer too large");
-  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps,
-                                                             step_dev);
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                             coef_scratch);
   return check_launch("adam");
 }
 

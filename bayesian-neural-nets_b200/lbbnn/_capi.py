@@ -74,7 +74,7 @@ SIGNATURES = {
     "lbbnn_colsum2_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _SZ, _P]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
-    "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P]),
+    "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
 }
 

@@ -51,6 +51,7 @@ class LRTTrainer:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.adam_coef = torch.zeros(2, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for l, name, off, n, shape in offs:
                 p = getattr(l, name)
@@ -128,8 +129,8 @@ class LRTTrainer:
             torch.distributed.all_reduce(self.gflat, group=self.pg)
         K.check(K.lib.lbbnn_adam_f32(K.ptr(self.flat), K.ptr(self.gflat), K.ptr(self.exp_avg), K.ptr(self.exp_avg_sq),
                                      self.n_flat, self.lr, self.betas[0], self.betas[1], self.eps,
-                                     K.ptr(self.step_dev, torch.int64), st))
-        n_launch += 1
+                                     K.ptr(self.step_dev, torch.int64), K.ptr(self.adam_coef), st))
+        n_launch += 2
         self.kernels_per_step = n_launch
 
     def _capture(self):
@@ -223,6 +224,7 @@ class LRTTensorCoreTrainer:
         self.flat, self.gflat = torch.zeros(total, **f32), torch.zeros(total, **f32)
         self.exp_avg, self.exp_avg_sq = torch.zeros(total, **f32), torch.zeros(total, **f32)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.adam_coef = torch.zeros(2, dtype=torch.float32, device=dev)
         with torch.no_grad():
             for l, name, off, n, shape in offs:
                 p = getattr(l, name)
@@ -352,7 +354,7 @@ class LRTTensorCoreTrainer:
             torch.distributed.all_reduce(self.gflat, group=self.pg)
         K.check(lib.lbbnn_adam_f32(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
                                    self.lr, self.betas[0], self.betas[1], self.eps, P(self.step_dev, torch.int64),
-                                   st)); n += 1
+                                   P(self.adam_coef), st)); n += 2
         self.kernels_per_step = n
 
     _capture = LRTTrainer._capture

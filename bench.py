@@ -214,7 +214,7 @@ def profile_calls(tr, reps=20):
     calls.append(("adam_f32 (flat)", 28 * tr.n_flat,
                   lambda: K.lib.lbbnn_adam_f32(K.ptr(tr.flat), K.ptr(tr.gflat), K.ptr(tr.exp_avg),
                                                K.ptr(tr.exp_avg_sq), tr.n_flat, 0.0, 0.9, 0.999, 1e-8,
-                                               K.ptr(tr.step_dev, torch.int64), st)))
+                                               K.ptr(tr.step_dev, torch.int64), K.ptr(tr.adam_coef), st)))
     out = []
     for name, nbytes, fn in calls:
         times = []

@@ -189,9 +189,11 @@ LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* targe
                                        int64_t* step_inc, void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
 /* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
- * step_dev: device int64 holding t, the 1-based index of THIS update. */
+ * step_dev: device int64 holding t, the 1-based index of THIS update; coef_scratch: 2 device floats
+ * (the bias-corrected step size is computed once on the device, so a graph replay needs no host input). */
 LBBNN_API int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                             float lr, float beta1, float beta2, float eps, const int64_t* step_dev, lbbnn_stream s);
+                             float lr, float beta1, float beta2, float eps, const int64_t* step_dev,
+                             float* coef_scratch, lbbnn_stream s);
 LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
 
 #ifdef __cplusplus
