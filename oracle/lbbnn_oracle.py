@@ -153,3 +153,144 @@ def init_lrt_params(rng, in_features, out_features, mu_range=0.2, dtype=torch.fl
         "bias_mu": u(-0.2, 0.2, out_features),
         "bias_rho": u(-5.0, -4.0, out_features),
     }
+
+
+# --------------------------------------------------------------------------------------
+# MF (full weight sampling) layer  (LBBNN-GP-MF.py:74-319; sim-study variant MFsim:173-300)
+# --------------------------------------------------------------------------------------
+LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
+
+
+class _StdGammaReparam(torch.autograd.Function):
+    """A given standard-gamma draw g0 ~ Gamma(a, 1) with torch's implicit reparameterisation gradient
+    dg0/da (torch/distributions/gamma.py:79-87 -> torch._standard_gamma / _standard_gamma_grad)."""
+
+    @staticmethod
+    def forward(ctx, a, g0):
+        ctx.save_for_backward(a.detach(), g0)
+        return g0.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, g0 = ctx.saved_tensors
+        return grad * torch._standard_gamma_grad(a, g0), None
+
+
+def gamma_rsample(a, b, g0):
+    """tau = Gamma(a, b).rsample() for the injected standard-gamma draw g0 (MF:141)."""
+    return _StdGammaReparam.apply(a, g0) / b
+
+
+def relaxed_bernoulli_rsample(alpha, u, temperature=0.001):
+    """RelaxedBernoulli(probs=alpha, T).rsample() for the injected uniform u (MF:115;
+    torch relaxed_bernoulli.py:104-112 + SigmoidTransform's clipped sigmoid)."""
+    fi = torch.finfo(alpha.dtype)
+    p = alpha.clamp(min=fi.eps, max=1 - fi.eps)
+    uu = u.clamp(min=fi.eps, max=1 - fi.eps)
+    logits = (uu.log() - (-uu).log1p() + p.log() - (-p).log1p()) / temperature
+    return torch.clamp(torch.sigmoid(logits), min=fi.tiny, max=1.0 - fi.eps)
+
+
+def exact_bernoulli_sample(alpha, u):
+    """Bernoulli(alpha).sample() as a mask of the injected uniform: gamma = [u < alpha] (MF:113)."""
+    return (u < alpha).to(alpha.dtype)
+
+
+def gaussian_log_prob_iid(w, mu, sigma):
+    """MF:93-96."""
+    return -LOG_SQRT_2PI - torch.log(sigma) - ((w - mu) ** 2) / (2 * sigma ** 2)
+
+
+def gaussian_full_log_prob(w, gamma, mu, sigma):
+    """MF:99-101: sum log(gamma * N(w; mu, sigma) + (1-gamma) + 1e-8)."""
+    return torch.log(gamma * torch.exp(gaussian_log_prob_iid(w, mu, sigma)) + (1 - gamma) + 1e-8).sum()
+
+
+def bernoulli_log_prob(gamma, alpha, exact):
+    """MF:122-128."""
+    g = torch.round(gamma.detach()) if exact else gamma
+    return (g * torch.log(alpha + 1e-8) + (1 - g) * torch.log(1 - alpha + 1e-8)).sum()
+
+
+def gauss_gamma_log_prob(w, gamma, a, b, tau, exact):
+    """MF:140-151 with tau already drawn."""
+    g = torch.round(gamma.detach()) if exact else gamma
+    const = a * torch.log(b) + (a - 0.5) * tau - b * tau - torch.lgamma(a) - 0.5 * math.log(2 * math.pi)
+    return (g * const - tau * w ** 2 + (1 - g) + 1e-8).sum()
+
+
+def beta_binomial_log_prob(gamma, pa, pb, exact):
+    """MF:162-173 (nine lgamma terms, two of which cancel)."""
+    g = torch.round(gamma.detach()) if exact else gamma
+    one = torch.ones_like(gamma)
+    lg = torch.lgamma
+    return (lg(one) + lg(g + one * pa) + lg(one * (1 + pb) - g) + lg(one * (pa + pb)) - lg(one * pa + g)
+            - lg(one * 2 - g) - lg(one * (1 + pa + pb)) - lg(one * pa) - lg(one * pb)).sum()
+
+
+def mf_forward(x, p, cgamma, noise, sample=True, medimean=False, alpha_stale=None, calc_log_probs=True,
+               exact=(False, False, False, False), logprob_on_ws=False):
+    """MF BayesianLinear.forward, MF:228-255.
+
+    p: weight_mu, weight_rho, lambdal, bias_mu, bias_rho, weight_a, weight_b, bias_a, bias_b, pa, pb.
+    noise: eps_w (out,in), eps_b (out,), g0_w (1,), g0_b (out,) -- the normal draws of MF:85-87 and the
+    standard-gamma draws behind MF:141.  exact = (.exact of gamma, weight_prior, bias_prior, gamma_prior).
+    logprob_on_ws: the sim-study variant evaluates the weight log-probs at the unmasked ws (MFsim:233,237).
+    Returns (F.linear output, log_prior, log_variational_posterior).
+    """
+    sw, sb = sigma_of(p["weight_rho"]), sigma_of(p["bias_rho"])
+    ws = None
+    if sample:
+        ws = p["weight_mu"] + sw * noise["eps_w"]
+        weight = cgamma * ws
+        bias = p["bias_mu"] + sb * noise["eps_b"]
+    elif medimean:
+        weight = cgamma * p["weight_mu"]
+        bias = p["bias_mu"]
+    else:
+        weight = alpha_stale * p["weight_mu"]
+        bias = p["bias_mu"]
+    log_prior = log_q = 0
+    if calc_log_probs:
+        alpha = alpha_of(p["lambdal"])
+        wlp = ws if (logprob_on_ws and ws is not None) else weight
+        tau_w = gamma_rsample(p["weight_a"], p["weight_b"], noise["g0_w"])
+        tau_b = gamma_rsample(p["bias_a"], p["bias_b"], noise["g0_b"])
+        log_prior = (gauss_gamma_log_prob(wlp, cgamma, p["weight_a"], p["weight_b"], tau_w, exact[1])
+                     + gauss_gamma_log_prob(bias, torch.ones_like(bias), p["bias_a"], p["bias_b"], tau_b, exact[2])
+                     + beta_binomial_log_prob(cgamma, p["pa"], p["pb"], exact[3]))
+        log_q = (gaussian_full_log_prob(wlp, cgamma, p["weight_mu"], sw)
+                 + bernoulli_log_prob(cgamma, alpha, exact[0])
+                 + gaussian_log_prob_iid(bias, p["bias_mu"], sb).sum())
+    return F.linear(x, weight, bias), log_prior, log_q
+
+
+def mf_net_elbo(x, y, layers, noises, us, num_batches, temperature=0.001, gamma_exact=False):
+    """sample_elbo with SAMPLES=1, MF:285-319: gamma_k = rsample(alpha_k) per layer (relaxed unless
+    gamma_exact), forward, loss = nll + (log_q - log_p)/NUM_BATCHES."""
+    h = x.reshape(-1, layers[0]["weight_mu"].shape[1])
+    log_p = log_q = 0
+    gammas = []
+    for i, (p, nz, u) in enumerate(zip(layers, noises, us)):
+        alpha = alpha_of(p["lambdal"])
+        g = exact_bernoulli_sample(alpha, u) if gamma_exact else relaxed_bernoulli_rsample(alpha, u, temperature)
+        gammas.append(g)
+        h, lp, lq = mf_forward(h, p, g, nz, exact=(gamma_exact, False, False, False))
+        log_p, log_q = log_p + lp, log_q + lq
+        h = F.relu(h) if i < len(layers) - 1 else F.log_softmax(h, dim=1)
+    nll = F.nll_loss(h, y, reduction="sum")
+    return nll + (log_q - log_p) / num_batches, nll, log_p, log_q, h, gammas
+
+
+def init_mf_params(rng, in_features, out_features, dtype=torch.float32, sim=False):
+    """MF:192-220 ranges (sim study MFsim:182-191: mu~U(-.01,.01), lambda~U(-.5,.5))."""
+    def u(lo, hi, *shape):
+        return torch.from_numpy(rng.uniform(lo, hi, size=shape)).to(dtype)
+    mr, lr = (0.01, (-0.5, 0.5)) if sim else (0.2, (0.0, 1.0))
+    return {
+        "weight_mu": u(-mr, mr, out_features, in_features), "weight_rho": u(-5, -4, out_features, in_features),
+        "lambdal": u(lr[0], lr[1], out_features, in_features),
+        "bias_mu": u(-0.2, 0.2, out_features), "bias_rho": u(-5, -4, out_features),
+        "weight_a": u(1, 1.1, 1), "weight_b": u(1, 1.1, 1), "bias_a": u(1, 1.1, out_features),
+        "bias_b": u(1, 1.1, out_features), "pa": u(1, 1.1, 1), "pb": u(1, 1.1, 1),
+    }

@@ -63,3 +63,31 @@ def rel_err(a, b):
     if den == 0.0:
         den = 1.0
     return (a - b).abs().max().item() / den
+
+
+def mf_layer_case(seed, batch, in_features, out_features, sim=False, spread_lambda=True):
+    """MF layer: params (reference ranges), x, the layer's noise draws and a uniform for gamma."""
+    rng = np.random.default_rng(seed)
+    p = O.init_mf_params(rng, in_features, out_features, sim=sim)
+    if spread_lambda:
+        p["lambdal"] = t(rng.normal(0.0, 2.0, size=(out_features, in_features)))
+    x = t(rng.uniform(0.0, 1.0, size=(batch, in_features)))
+    noise = {"eps_w": t(rng.standard_normal(size=(out_features, in_features))),
+             "eps_b": t(rng.standard_normal(size=(out_features,))),
+             "g0_w": t(rng.gamma(1.05, size=(1,))), "g0_b": t(rng.gamma(1.05, size=(out_features,)))}
+    u = t(rng.uniform(0.0, 1.0, size=(out_features, in_features)))
+    gout = t(rng.standard_normal(size=(batch, out_features)))
+    return {"p": p, "x": x, "noise": noise, "u": u, "gout": gout}
+
+
+def mf_net_case(seed, batch, sizes=MNIST_SIZES, classes=10):
+    rng = np.random.default_rng(seed)
+    layers, noises, us = [], [], []
+    for i, o in sizes:
+        layers.append(O.init_mf_params(rng, i, o))
+        noises.append({"eps_w": t(rng.standard_normal(size=(o, i))), "eps_b": t(rng.standard_normal(size=(o,))),
+                       "g0_w": t(rng.gamma(1.05, size=(1,))), "g0_b": t(rng.gamma(1.05, size=(o,)))})
+        us.append(t(rng.uniform(0.0, 1.0, size=(o, i))))
+    x = t(rng.uniform(0.0, 1.0, size=(batch, sizes[0][0])))
+    y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
+    return {"layers": layers, "noises": noises, "us": us, "x": x, "y": y}

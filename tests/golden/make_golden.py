@@ -109,6 +109,87 @@ def golden_lrt():
     print("lrt golden written; loss", loss.item(), "kl", kl.item())
 
 
+MF_NAMES = ["weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho", "weight_a", "weight_b", "bias_a", "bias_b",
+            "pa", "pb"]
+
+
+def _mf_queue(nz, u=None):
+    """Draw order inside MF BayesianLinear.forward (MF:232-249): eps_w, eps_b, then the two Gamma.rsample."""
+    q = []
+    if u is not None:
+        q.append(("uniform", u))
+    q += [("normal", nz["eps_w"]), ("normal", nz["eps_b"]), ("gamma", nz["g0_w"]), ("gamma", nz["g0_b"])]
+    return q
+
+
+def golden_mf():
+    out = {}
+    for script, tagp, sim in (("LBBNN-GP-MF.py", "m", False), ("LBBNN-GP-MFsim_study.py", "s", True)):
+        ns = H.load_reference_classes(script)
+        Layer = ns["BayesianLinear"]
+        shapes = {"a": (41, 7, 37, 23), "b": (42, 33, 130, 10)} if not sim else {"a": (43, 9, 20, 1)}
+        for tag, (seed, b, i, o) in shapes.items():
+            key = tagp + tag
+            case = C.mf_layer_case(seed, b, i, o, sim=sim)
+            for relaxed in (True, False):
+                layer = Layer(i, o) if sim else Layer(i, o, 1)
+                _load_params(layer, case["p"])
+                layer.train()
+                x = case["x"].clone().requires_grad_(True)
+                layer.alpha = 1 / (1 + torch.exp(-layer.lambdal))
+                layer.gamma.alpha = layer.alpha
+                layer.gamma.exact = not relaxed
+                with H.replay(H.NoiseQueue([("uniform", case["u"])])):
+                    cg = layer.gamma.rsample()
+                with H.replay(H.NoiseQueue(_mf_queue(case["noise"]))):
+                    act = layer(x, cg, sample=True)
+                loss = (act * case["gout"]).sum() + (layer.log_variational_posterior - layer.log_prior) / C.NUM_BATCHES
+                loss.backward()
+                k2 = key + ("_rel" if relaxed else "_ex")
+                out[k2 + "_meta"] = np.array([seed, b, i, o, int(sim)])
+                out[k2 + "_gamma"] = cg.detach().numpy()
+                out[k2 + "_act"] = act.detach().numpy()
+                out[k2 + "_log_prior"] = np.float64(layer.log_prior.item())
+                out[k2 + "_log_q"] = np.float64(layer.log_variational_posterior.item())
+                out[k2 + "_dx"] = x.grad.numpy()
+                for name, g in _grads(layer, MF_NAMES).items():
+                    out[k2 + "_d_" + name] = g.numpy()
+            # eval-mode means (medimean / joint mean with the stale alpha)
+            layer.eval()
+            with torch.no_grad():
+                layer.alpha = 1 / (1 + torch.exp(-layer.lambdal))
+                med = layer(case["x"], (layer.alpha > 0.5).float(), sample=False, medimean=True)
+                jm = layer(case["x"], cg, sample=False, medimean=False)
+            out[key + "_medimean"] = med.numpy()
+            out[key + "_jointmean"] = jm.numpy()
+    np.savez_compressed(os.path.join(HERE, "mf_layer.npz"), **out)
+
+    # MNIST-shape sample_elbo (SAMPLES=1) + grads
+    ns = H.load_reference_classes("LBBNN-GP-MF.py")
+    Net = ns["BayesianNetwork"]
+    case = C.mf_net_case(seed=50, batch=100)
+    net = Net()
+    for lay, p in zip((net.l1, net.l2, net.l3), case["layers"]):
+        _load_params(lay, p)
+    net.train()
+    q = [("uniform", u) for u in case["us"]]
+    for nz in case["noises"]:
+        q += _mf_queue(nz)
+    with H.replay(H.NoiseQueue(q)):
+        loss, log_prior, log_q, nll = net.sample_elbo(case["x"].view(100, 1, 28, 28), case["y"])
+    loss.backward()
+    out = {"loss": np.float64(loss.item()), "log_prior": np.float64(log_prior.item()), "log_q": np.float64(log_q.item()),
+           "nll": np.float64(nll.item())}
+    for li, lay in enumerate((net.l1, net.l2, net.l3)):
+        for k, g in _grads(lay, MF_NAMES).items():
+            for dk, dv in C.grad_digest(g).items():
+                out[f"l{li}_{k}_{dk}"] = dv
+            if g.numel() <= 6000:
+                out[f"l{li}_{k}_full"] = g.numpy()
+    np.savez_compressed(os.path.join(HERE, "mf_net_mnist.npz"), **out)
+    print("mf golden written; loss", loss.item(), "log_prior", log_prior.item(), "log_q", log_q.item())
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("lrt", "all"):

@@ -69,3 +69,57 @@ def test_fp64_oracle_brackets_fp32():
     a32 = O.lrt_forward(case["x"], case["p"], case["eps"])
     a64 = O.lrt_forward(case["x"].double(), {k: v.double() for k, v in case["p"].items()}, case["eps"].double())
     assert C.rel_err(a32, a64) < 1e-6
+
+
+MF_NAMES = ["weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho", "weight_a", "weight_b", "bias_a", "bias_b",
+            "pa", "pb"]
+
+
+@pytest.mark.parametrize("key", ["ma_rel", "ma_ex", "mb_rel", "mb_ex", "sa_rel", "sa_ex"])
+def test_mf_layer_matches_reference(key):
+    g = _npz("mf_layer.npz")
+    seed, b, i, o, sim = (int(v) for v in g[f"{key}_meta"])
+    relaxed = key.endswith("_rel")
+    case = C.mf_layer_case(seed, b, i, o, sim=bool(sim))
+    p = {k: v.clone().requires_grad_(True) for k, v in case["p"].items()}
+    x = case["x"].clone().requires_grad_(True)
+    alpha = O.alpha_of(p["lambdal"])
+    cg = O.relaxed_bernoulli_rsample(alpha, case["u"]) if relaxed else O.exact_bernoulli_sample(alpha, case["u"])
+    assert np.array_equal(cg.detach().numpy(), g[f"{key}_gamma"])           # inclusion masks bit-exact
+    act, lp, lq = O.mf_forward(x, p, cg, case["noise"], exact=(not relaxed, False, False, False),
+                               logprob_on_ws=bool(sim))
+    ((act * case["gout"]).sum() + (lq - lp) / C.NUM_BATCHES).backward()
+    assert C.rel_err(act, g[f"{key}_act"]) < TOL
+    assert abs(lp.item() - float(g[f"{key}_log_prior"])) / abs(float(g[f"{key}_log_prior"])) < 5e-6
+    assert abs(lq.item() - float(g[f"{key}_log_q"])) / abs(float(g[f"{key}_log_q"])) < 5e-6
+    assert C.rel_err(x.grad, g[f"{key}_dx"]) < TOL
+    for k in MF_NAMES:
+        assert C.rel_err(p[k].grad, g[f"{key}_d_{k}"]) < 2e-5, k
+
+
+def test_mf_means_match_reference():
+    g = _npz("mf_layer.npz")
+    for key, (seed, b, i, o, sim) in {"ma": (41, 7, 37, 23, False), "mb": (42, 33, 130, 10, False), "sa": (43, 9, 20, 1, True)}.items():
+        case = C.mf_layer_case(seed, b, i, o, sim=sim)
+        alpha = O.alpha_of(case["p"]["lambdal"])
+        med, _, _ = O.mf_forward(case["x"], case["p"], (alpha > 0.5).float(), None, sample=False, medimean=True,
+                                 calc_log_probs=False)
+        jm, _, _ = O.mf_forward(case["x"], case["p"], None, None, sample=False, medimean=False, alpha_stale=alpha,
+                                calc_log_probs=False)
+        assert C.rel_err(med, g[f"{key}_medimean"]) < TOL and C.rel_err(jm, g[f"{key}_jointmean"]) < TOL
+
+
+def test_mf_mnist_elbo_matches_reference():
+    g = _npz("mf_net_mnist.npz")
+    case = C.mf_net_case(seed=50, batch=100)
+    layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+    loss, nll, lp, lq, _, _ = O.mf_net_elbo(case["x"], case["y"], layers, case["noises"], case["us"], C.NUM_BATCHES)
+    loss.backward()
+    for name, val in (("loss", loss), ("nll", nll), ("log_prior", lp), ("log_q", lq)):
+        assert abs(val.item() - float(g[name])) / abs(float(g[name])) < 5e-6, name
+    for li, p in enumerate(layers):
+        for k, v in p.items():
+            d = C.grad_digest(v.grad)
+            assert C.rel_err(d["sample"], g[f"l{li}_{k}_sample"]) < 2e-5, (li, k)
+            if f"l{li}_{k}_full" in g:
+                assert C.rel_err(v.grad, g[f"l{li}_{k}_full"]) < 2e-5, (li, k)
