@@ -876,3 +876,62 @@ extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, con
   lrt_f32_finalize<<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize");
 }
+
+// ---- plain linear layer on the same kernels (mean-branch GEMM: E only) ---------------------------------
+extern "C" int lbbnn_linear_f32_fwd(const float* x, const float* W, const float* bias, int64_t B, int64_t K, int64_t N,
+                                    int flags, float* out, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(x && W && bias && out && B > 0 && K > 0 && N > 0, "NULL argument");
+  const WsLayout w = ws_layout(B, K, N);
+  LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small (%zu < %zu)", ws_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)s;
+  const Split sp = fwd_split(B, K, N);
+  FwdArgs fa;
+  fa.x = x; fa.M = W; fa.V = nullptr; fa.B = B; fa.K = K; fa.N = N;
+  fa.chunks_per_split = sp.chunks_per_split; fa.splits = sp.splits; fa.sample = 0;
+  fa.part = (float*)((char*)ws + w.off_scratch);
+  dim3 grid((unsigned)ceil_div(N, F_BN), (unsigned)ceil_div(B, F_BM), (unsigned)sp.splits);
+  lrt_f32_fwd_partial<<<grid, kThreads, 0, st>>>(fa);
+  if (int rc = check_launch("lrt_f32_fwd_partial")) return rc;
+  FwdEpiArgs ea;
+  ea.part = fa.part; ea.splits = sp.splits; ea.B = B; ea.N = N; ea.bias_mu = bias; ea.bias_rho = bias;
+  ea.noise = make_noise(nullptr); ea.flags = flags & LBBNN_FLAG_RELU; ea.act = out; ea.dsf = nullptr; ea.kl_out = nullptr;
+  ea.kl_part = nullptr; ea.n_kl_part = 0; ea.pri = lbbnn_priors{0.f, 1.f, 0.5f, 0.f, 1.f};
+  int64_t blocks = ceil_div(ceil_div(B * N, 4), kEpiThreads);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  lrt_f32_fwd_epilogue<<<(unsigned)blocks, kEpiThreads, 0, st>>>(ea);
+  return check_launch("lrt_f32_fwd_epilogue");
+}
+
+extern "C" int lbbnn_linear_f32_bwd_params(const float* x, const float* gout, int64_t B, int64_t K, int64_t N, float* dW,
+                                           float* dbias, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(x && gout && dW && dbias && B > 0 && K > 0 && N > 0, "NULL argument");
+  LBBNN_REQUIRE(ws && ws_bytes >= (size_t)2 * N * sizeof(float), "workspace too small");
+  BwdWArgs a;
+  a.x = x; a.g = gout; a.dsf = nullptr; a.B = B; a.K = K; a.N = N; a.sample = 0;
+  a.dM = dW; a.dV = dW; a.colsum = (float*)ws;
+  dim3 grid((unsigned)ceil_div(N, W_BN), (unsigned)ceil_div(K, W_BK));
+  lrt_f32_bwd_w_gemm<<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
+  if (int rc = check_launch("lrt_f32_bwd_w_gemm")) return rc;
+  LBBNN_CUDA(cudaMemcpyAsync(dbias, ws, (size_t)N * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)s));
+  return LBBNN_OK;
+}
+
+extern "C" int lbbnn_linear_f32_bwd_input(const float* x, const float* W, const float* gout, int64_t B, int64_t K,
+                                          int64_t N, int flags, float* dx, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(x && W && gout && dx && B > 0 && K > 0 && N > 0, "NULL argument");
+  const WsLayout w = ws_layout(B, K, N);
+  LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small");
+  const Split sp = dx_split(B, K, N);
+  BwdXArgs a;
+  a.x = x; a.g = gout; a.dsf = nullptr; a.M = W; a.V = nullptr; a.B = B; a.K = K; a.N = N;
+  a.chunks_per_split = sp.chunks_per_split; a.splits = sp.splits; a.sample = 0;
+  a.part = (float*)((char*)ws + w.off_scratch);
+  dim3 grid((unsigned)ceil_div(K, X_BK), (unsigned)ceil_div(B, X_BM), (unsigned)sp.splits);
+  lrt_f32_bwd_x_partial<<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
+  if (int rc = check_launch("lrt_f32_bwd_x_partial")) return rc;
+  int64_t blocks = ceil_div(ceil_div(B * K, 4), kEpiThreads);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  lrt_f32_bwd_x_epilogue<<<(unsigned)blocks, kEpiThreads, 0, (cudaStream_t)s>>>(a.part, sp.splits, B * K, x,
+                                                                  (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0, 0, dx);
+  return check_launch("lrt_f32_bwd_x_epilogue");
+}

@@ -1,0 +1,346 @@
+// Mean-field (full weight sampling) path: LBBNN-GP-MF.py:74-255 (sim-study variant MFsim:173-244).
+//
+//   mf_gamma      gamma.rsample(): hard Bernoulli mask [u < alpha] (MF:113) or the relaxed-Bernoulli
+//                 reparameterisation at temperature T (MF:115), and its backward to lambda
+//   mf_sample     w = gamma (mu + sigma eps)  (MF:232-233; medimean / joint-mean variants MF:237-242) and,
+//                 in the same pass over the weights, the five element sums that the log-prior and
+//                 log-variational-posterior are built from (MF:247-251):
+//                   s0 = sum g            (GaussGamma: multiplies the (a,b,tau) constant, MF:148)
+//                   s1 = sum w^2          (GaussGamma: -tau w^2)
+//                   s2 = sum lgamma(1+pb-g) - lgamma(2-g)      (BetaBinomial, MF:167-173; the other seven
+//                                          lgamma terms do not depend on the element or cancel)
+//                   s3 = sum log(gamma N(w; mu, sigma) + (1-gamma) + 1e-8)     (full_log_prob, MF:99-101)
+//                   s4 = sum g log(alpha+1e-8) + (1-g) log(1-alpha+1e-8)      (Bernoulli.log_prob, MF:122-128)
+//   mf_sample_bwd autograd of the above: (dL/dw, dL/ds0..4) -> dmu, drho, dlambda, dgamma, dpb
+// All vectorised (float4) and coalesced; reductions are two-stage with a fixed order (deterministic).
+#include "common.cuh"
+
+namespace lbbnn {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
+
+__device__ __forceinline__ void ldq(const float* __restrict__ p, int64_t e0, int64_t n, bool vec, float out[4]) {
+  if (vec && e0 + 3 < n) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p + e0));
+    out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = (e0 + j < n) ? __ldg(p + e0 + j) : 0.f;
+  }
+}
+__device__ __forceinline__ void stq(float* __restrict__ p, int64_t e0, int64_t n, bool vec, const float v[4]) {
+  if (vec && e0 + 3 < n) {
+    *reinterpret_cast<float4*>(p + e0) = make_float4(v[0], v[1], v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e0 + j < n) p[e0 + j] = v[j];
+  }
+}
+
+// digamma for x > 0: recurrence up to x >= 6, then the asymptotic series
+__device__ __forceinline__ float digammaf(float x) {
+  float r = 0.f;
+  while (x < 6.0f) { r -= 1.0f / x; x += 1.0f; }
+  const float f = 1.0f / (x * x);
+  return r + logf(x) - 0.5f / x - f * (1.0f / 12.0f - f * (1.0f / 120.0f - f * (1.0f / 252.0f - f * (1.0f / 240.0f - f / 132.0f))));
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+constexpr float kEps = 1.1920928955078125e-07f;   // torch.finfo(float32).eps
+constexpr float kTiny = 1.1754943508222875e-38f;  // torch.finfo(float32).tiny
+
+// ---- gamma.rsample ----------------------------------------------------------------------------------
+struct GammaArgs {
+  const float *lam, *alpha_in;  // one of them: alpha = sigmoid(lam) or the given tensor
+  Noise u;
+  int64_t n;
+  int exact;
+  float inv_t;
+  float* gamma;
+};
+
+__global__ void __launch_bounds__(kThreads) mf_gamma_kernel(const GammaArgs a) {
+  Noise nz = a.u;
+  nz.resolve();
+  const float* src = a.lam ? a.lam : a.alpha_in;
+  const bool vec = (a.n % 4 == 0) && aligned16(src) && aligned16(a.gamma) && (nz.ptr == nullptr || aligned16(nz.ptr));
+  const int64_t nq = ceil_div(a.n, 4);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float s[4], u[4], g[4];
+    ldq(src, e0, a.n, vec, s);
+    if (nz.ptr) ldq(nz.ptr, e0, a.n, vec, u);
+    else philox_uniform4(nz.seed, nz.stream, (uint64_t)q, u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float al = a.lam ? alpha_of(s[j]) : s[j];
+      if (a.exact) {
+        g[j] = u[j] < al ? 1.0f : 0.0f;
+      } else {  // torch RelaxedBernoulli.rsample: clamp_probs, logistic noise, /T, clipped sigmoid
+        const float p = clampf(al, kEps, 1.0f - kEps), uu = clampf(u[j], kEps, 1.0f - kEps);
+        const float logits = (logf(uu) - log1pf(-uu) + logf(p) - log1pf(-p)) * a.inv_t;
+        g[j] = clampf(1.0f / (1.0f + expf(-logits)), kTiny, 1.0f - kEps);
+      }
+    }
+    stq(a.gamma, e0, a.n, vec, g);
+  }
+}
+
+// d gamma / d lambda for the relaxed draw: gamma(1-gamma)/T * (1/p + 1/(1-p)) * alpha(1-alpha), zero where clipped
+__global__ void __launch_bounds__(kThreads) mf_gamma_bwd_kernel(const float* __restrict__ lam, const float* __restrict__ alpha_in,
+                                                                const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                                                int64_t n, float inv_t, float* __restrict__ dout) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float al = lam ? alpha_of(lam[i]) : alpha_in[i];
+    const float g = gamma[i];
+    float d = 0.f;
+    if (g > kTiny && g < 1.0f - kEps && al > kEps && al < 1.0f - kEps) {
+      d = dgamma[i] * g * (1.0f - g) * inv_t * (1.0f / al + 1.0f / (1.0f - al));
+      if (lam) d *= al * (1.0f - al);
+    }
+    dout[i] = d;
+  }
+}
+
+// ---- weight sampling + log-prob sums ------------------------------------------------------------------
+struct SampleArgs {
+  const float *mu, *rho, *lam, *gamma, *alpha_stale, *pb;
+  Noise eps;
+  int64_t n;
+  int mode;        // LBBNN_MF_SAMPLE / MEDIMEAN / JOINTMEAN
+  int want_lp;     // compute the five sums
+  int lp_on_ws;    // sim-study: log-probs at the unmasked ws
+  int exact_b, exact_wp, exact_gp;   // round(gamma.detach()) inside Bernoulli / GaussGamma / BetaBinomial log_prob
+  float* w;
+  double* part;    // [gridDim.x][5]
+};
+
+__global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a) {
+  __shared__ double red[32];
+  Noise nz = a.eps;
+  nz.resolve();
+  const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w) &&
+                   (a.gamma == nullptr || aligned16(a.gamma)) && (a.alpha_stale == nullptr || aligned16(a.alpha_stale)) &&
+                   (nz.ptr == nullptr || aligned16(nz.ptr));
+  const float pb = a.want_lp ? __ldg(a.pb) : 1.0f;
+  const int64_t nq = ceil_div(a.n, 4);
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float mu[4], rho[4], lam[4], ga[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f}, w[4];
+    ldq(a.mu, e0, a.n, vec, mu);
+    if (a.mode == LBBNN_MF_SAMPLE || a.want_lp) ldq(a.rho, e0, a.n, vec, rho);
+    if (a.want_lp || (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr)) ldq(a.lam, e0, a.n, vec, lam);
+    if (a.mode == LBBNN_MF_JOINTMEAN) {
+      if (a.alpha_stale) ldq(a.alpha_stale, e0, a.n, vec, ga);
+    } else {
+      ldq(a.gamma, e0, a.n, vec, ga);
+    }
+    if (a.mode == LBBNN_MF_SAMPLE) {
+      if (nz.ptr) ldq(nz.ptr, e0, a.n, vec, ep);
+      else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      w[j] = 0.f;
+      if (e0 + j >= a.n) continue;
+      float ws = mu[j];
+      float sg = 0.f;
+      if (a.mode == LBBNN_MF_SAMPLE) { sg = sigma_of(rho[j]); ws = fmaf(sg, ep[j], mu[j]); }
+      float g = ga[j];
+      if (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr) g = alpha_of(lam[j]);
+      w[j] = g * ws;
+      if (a.want_lp) {
+        if (a.mode != LBBNN_MF_SAMPLE) sg = sigma_of(rho[j]);
+        const float al = alpha_of(lam[j]);
+        const float wl = a.lp_on_ws ? ws : w[j];
+        const float gr = rintf(g);
+        const float g_wp = a.exact_wp ? gr : g, g_gp = a.exact_gp ? gr : g, g_b = a.exact_b ? gr : g;
+        s[0] += g_wp;
+        s[1] += wl * wl;
+        s[2] += lgammaf(1.0f + pb - g_gp) - lgammaf(2.0f - g_gp);
+        const float dlt = wl - mu[j];
+        const float logn = -kLogSqrt2Pi - logf(sg) - (dlt * dlt) / (2.0f * sg * sg);
+        s[3] += logf(g * expf(logn) + (1.0f - g) + 1e-8f);
+        s[4] += g_b * logf(al + 1e-8f) + (1.0f - g_b) * logf(1.0f - al + 1e-8f);
+      }
+    }
+    stq(a.w, e0, a.n, vec, w);
+  }
+  if (a.want_lp) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const double t = block_sum((double)s[k], red);
+      if (threadIdx.x == 0) a.part[(int64_t)blockIdx.x * 5 + k] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) sum_partials_kernel(const double* __restrict__ part, int nblocks, int width,
+                                                                float* __restrict__ out) {
+  __shared__ double red[32];
+  for (int k = 0; k < width; ++k) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += part[(int64_t)i * width + k];
+    const double t = block_sum(acc, red);
+    if (threadIdx.x == 0) out[k] = (float)t;
+  }
+}
+
+struct SampleBwdArgs {
+  const float *mu, *rho, *lam, *gamma, *pb, *dw, *c;   // c: dL/ds0..4 (device, 5 floats)
+  Noise eps;
+  int64_t n;
+  int lp_on_ws, exact_b, exact_wp, exact_gp, want_dgamma;
+  float *dmu, *drho, *dlam, *dgamma;
+  double* part;   // [gridDim.x][1]: sum psi(1+pb-g) (for dpb)
+};
+
+__global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwdArgs a) {
+  __shared__ double red[32];
+  Noise nz = a.eps;
+  nz.resolve();
+  const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.gamma) &&
+                   (a.dw == nullptr || aligned16(a.dw)) && aligned16(a.dmu) && aligned16(a.drho) && aligned16(a.dlam) &&
+                   (a.dgamma == nullptr || aligned16(a.dgamma)) && (nz.ptr == nullptr || aligned16(nz.ptr));
+  float c[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.c) {
+#pragma unroll
+    for (int k = 0; k < 5; ++k) c[k] = __ldg(a.c + k);
+  }
+  const float pb = __ldg(a.pb);
+  const int64_t nq = ceil_div(a.n, 4);
+  float psisum = 0.f;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float mu[4], rho[4], lam[4], ga[4], ep[4], dw[4] = {0.f, 0.f, 0.f, 0.f}, gm[4], gr[4], gl[4], gg[4];
+    ldq(a.mu, e0, a.n, vec, mu);
+    ldq(a.rho, e0, a.n, vec, rho);
+    ldq(a.lam, e0, a.n, vec, lam);
+    ldq(a.gamma, e0, a.n, vec, ga);
+    if (a.dw) ldq(a.dw, e0, a.n, vec, dw);
+    if (nz.ptr) ldq(nz.ptr, e0, a.n, vec, ep);
+    else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gm[j] = gr[j] = gl[j] = gg[j] = 0.f;
+      if (e0 + j >= a.n) continue;
+      const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]), g = ga[j];
+      const float ws = fmaf(sg, ep[j], mu[j]), w = g * ws, wl = a.lp_on_ws ? ws : w;
+      const float grd = rintf(g);
+      const float g_gp = a.exact_gp ? grd : g, g_b = a.exact_b ? grd : g;
+      const float dlt = wl - mu[j], inv_s2 = 1.0f / (sg * sg);
+      const float logn = -kLogSqrt2Pi - logf(sg) - (dlt * dlt) * 0.5f * inv_s2;
+      const float p = expf(logn), D = g * p + (1.0f - g) + 1e-8f, r = g * p / D;
+      const float dwl = c[1] * 2.0f * wl - c[3] * r * dlt * inv_s2;          // direct dL/d(wl)
+      const float dmu_dir = c[3] * r * dlt * inv_s2;
+      const float dsg_dir = c[3] * r * (dlt * dlt * inv_s2 / sg - 1.0f / sg);
+      const float psi = digammaf(1.0f + pb - g_gp);
+      psisum += psi;
+      float dg_dir = c[3] * (p - 1.0f) / D;
+      if (!a.exact_wp) dg_dir += c[0];
+      if (!a.exact_gp) dg_dir += c[2] * (digammaf(2.0f - g_gp) - psi);
+      if (!a.exact_b) dg_dir += c[4] * (logf(al + 1e-8f) - logf(1.0f - al + 1e-8f));
+      const float dal = c[4] * (g_b / (al + 1e-8f) - (1.0f - g_b) / (1.0f - al + 1e-8f));
+      const float dw_tot = dw[j] + (a.lp_on_ws ? 0.f : dwl);
+      const float dws = g * dw_tot + (a.lp_on_ws ? dwl : 0.f);
+      gm[j] = dws + dmu_dir;
+      gr[j] = (ep[j] * dws + dsg_dir) * dsigma_drho(rho[j]);
+      gl[j] = dal * al * (1.0f - al);
+      gg[j] = ws * dw_tot + dg_dir;
+    }
+    stq(a.dmu, e0, a.n, vec, gm);
+    stq(a.drho, e0, a.n, vec, gr);
+    stq(a.dlam, e0, a.n, vec, gl);
+    if (a.want_dgamma) stq(a.dgamma, e0, a.n, vec, gg);
+  }
+  const double t = block_sum((double)psisum, red);
+  if (threadIdx.x == 0) a.part[blockIdx.x] = t;
+}
+
+__global__ void scale_scalar_kernel(float* v, const float* c, int k) { *v *= c ? c[k] : 0.f; }
+
+int64_t ew_blocks(int64_t n) {
+  int64_t b = ceil_div(ceil_div(n, 4), kThreads);
+  const int64_t cap = 8LL * sm_count();
+  return b < 1 ? 1 : (b > cap ? cap : b);
+}
+
+}  // namespace
+}  // namespace lbbnn
+
+using namespace lbbnn;
+
+extern "C" size_t lbbnn_mf_workspace_bytes(int64_t n) { return n > 0 ? (size_t)ew_blocks(n) * 5 * sizeof(double) + 256 : 0; }
+
+extern "C" int lbbnn_mf_gamma_sample(const float* lambdal, const float* alpha, int64_t n, const lbbnn_noise* u, int exact,
+                                     float temperature, float* gamma, lbbnn_stream s) {
+  LBBNN_REQUIRE((lambdal != nullptr) != (alpha != nullptr), "give exactly one of lambdal / alpha");
+  LBBNN_REQUIRE(gamma && n > 0 && temperature > 0.f, "bad argument");
+  GammaArgs a;
+  a.lam = lambdal; a.alpha_in = alpha; a.u = make_noise(u); a.n = n; a.exact = exact; a.inv_t = 1.0f / temperature; a.gamma = gamma;
+  mf_gamma_kernel<<<(unsigned)ew_blocks(n), kThreads, 0, (cudaStream_t)s>>>(a);
+  return check_launch("mf_gamma");
+}
+
+extern "C" int lbbnn_mf_gamma_sample_bwd(const float* lambdal, const float* alpha, const float* gamma, const float* dgamma,
+                                         int64_t n, float temperature, float* dout, lbbnn_stream s) {
+  LBBNN_REQUIRE((lambdal != nullptr) != (alpha != nullptr), "give exactly one of lambdal / alpha");
+  LBBNN_REQUIRE(gamma && dgamma && dout && n > 0, "bad argument");
+  int64_t blocks = ceil_div(n, kThreads);
+  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+  mf_gamma_bwd_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)s>>>(lambdal, alpha, gamma, dgamma, n, 1.0f / temperature, dout);
+  return check_launch("mf_gamma_bwd");
+}
+
+extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                   const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode,
+                                   int flags, float* w, float* sums, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(mu && rho && lambdal && w && n > 0, "NULL argument");
+  LBBNN_REQUIRE(mode == LBBNN_MF_JOINTMEAN || gamma, "gamma required");
+  const bool lp = flags & LBBNN_MF_FLAG_LOGPROBS;
+  LBBNN_REQUIRE(!lp || (sums && pb && ws && ws_bytes >= lbbnn_mf_workspace_bytes(n)), "log-probs need sums, pb and workspace");
+  SampleArgs a;
+  a.mu = mu; a.rho = rho; a.lam = lambdal; a.gamma = gamma; a.alpha_stale = alpha_stale; a.pb = pb;
+  a.eps = make_noise(eps); a.n = n; a.mode = mode; a.want_lp = lp ? 1 : 0;
+  a.lp_on_ws = (flags & LBBNN_MF_FLAG_LP_ON_WS) ? 1 : 0;
+  a.exact_b = (flags & LBBNN_MF_FLAG_EXACT_GAMMA) ? 1 : 0;
+  a.exact_wp = (flags & LBBNN_MF_FLAG_EXACT_WPRIOR) ? 1 : 0;
+  a.exact_gp = (flags & LBBNN_MF_FLAG_EXACT_GPRIOR) ? 1 : 0;
+  a.w = w; a.part = (double*)ws;
+  const unsigned blocks = (unsigned)ew_blocks(n);
+  mf_sample_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  if (int rc = check_launch("mf_sample")) return rc;
+  if (lp) {
+    sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 5, sums);
+    return check_launch("mf_sum_partials");
+  }
+  return LBBNN_OK;
+}
+
+extern "C" int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma, const float* pb,
+                                   int64_t n, const lbbnn_noise* eps, int flags, const float* dw, const float* dsums,
+                                   float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb, void* ws,
+                                   size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(mu && rho && lambdal && gamma && pb && dmu && drho && dlambdal && dpb && n > 0, "NULL argument");
+  LBBNN_REQUIRE(ws && ws_bytes >= lbbnn_mf_workspace_bytes(n), "workspace too small");
+  SampleBwdArgs a;
+  a.mu = mu; a.rho = rho; a.lam = lambdal; a.gamma = gamma; a.pb = pb; a.dw = dw; a.c = dsums;
+  a.eps = make_noise(eps); a.n = n;
+  a.lp_on_ws = (flags & LBBNN_MF_FLAG_LP_ON_WS) ? 1 : 0;
+  a.exact_b = (flags & LBBNN_MF_FLAG_EXACT_GAMMA) ? 1 : 0;
+  a.exact_wp = (flags & LBBNN_MF_FLAG_EXACT_WPRIOR) ? 1 : 0;
+  a.exact_gp = (flags & LBBNN_MF_FLAG_EXACT_GPRIOR) ? 1 : 0;
+  a.want_dgamma = dgamma ? 1 : 0;
+  a.dmu = dmu; a.drho = drho; a.dlam = dlambdal; a.dgamma = dgamma; a.part = (double*)ws;
+  const unsigned blocks = (unsigned)ew_blocks(n);
+  mf_sample_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  if (int rc = check_launch("mf_sample_bwd")) return rc;
+  sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 1, dpb);
+  if (int rc = check_launch("mf_sum_partials")) return rc;
+  scale_scalar_kernel<<<1, 1, 0, (cudaStream_t)s>>>(dpb, dsums, 2);   // dpb = dL/ds2 * sum psi(1+pb-g)
+  return check_launch("mf_scale");
+}

@@ -23,6 +23,8 @@ lib = C.CDLL(LIB_PATH)
 VAR_REFERENCE, VAR_EXACT = 0, 1
 FLAG_SAMPLE, FLAG_RELU, FLAG_KL, FLAG_ACCUMULATE, FLAG_MASK_DX = 1, 2, 4, 8, 16
 PACK_PAIR, PACK_SQUARE, PACK_SCALE = 0, 1, 2
+MF_SAMPLE, MF_MEDIMEAN, MF_JOINTMEAN = 0, 1, 2
+MF_FLAG_LOGPROBS, MF_FLAG_LP_ON_WS, MF_FLAG_EXACT_GAMMA, MF_FLAG_EXACT_WPRIOR, MF_FLAG_EXACT_GPRIOR = 1, 2, 4, 8, 16
 
 
 class Priors(C.Structure):
@@ -73,6 +75,15 @@ SIGNATURES = {
     "lbbnn_bf16_pack": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _P, _P, _P]),
     "lbbnn_colsum2_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _SZ, _P]),
+    "lbbnn_linear_f32_fwd": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _SZ, _P]),
+    "lbbnn_linear_f32_bwd_params": (_INT, [_P, _P, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
+    "lbbnn_linear_f32_bwd_input": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _SZ, _P]),
+    "lbbnn_mf_workspace_bytes": (_SZ, [_I64]),
+    "lbbnn_mf_gamma_sample": (_INT, [_P, _P, _I64, C.POINTER(Noise), _INT, _F, _P, _P]),
+    "lbbnn_mf_gamma_sample_bwd": (_INT, [_P, _P, _P, _P, _I64, _F, _P, _P]),
+    "lbbnn_mf_sample_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _INT, _P, _P, _P, _SZ, _P]),
+    "lbbnn_mf_sample_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _P, _P, _P,
+                                   _P, _SZ, _P]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),

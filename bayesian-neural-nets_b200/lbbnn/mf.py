@@ -1,0 +1,303 @@
+"""Drop-in mean-field (full weight sampling) layer and network, reference LBBNN-GP-MF.py:74-319
+(and the sim-study variant LBBNN-GP-MFsim_study.py:173-300 via `logprob_on_ws=True`).
+
+The O(out*in) work -- gamma.rsample(), w = gamma (mu + sigma eps), the five element sums behind
+log_prior / log_variational_posterior, F.linear and all their gradients -- runs in liblbbnn kernels.
+The O(1)/O(out) hyper-prior glue (Gamma(a,b).rsample(), the (a,b,tau) and (pa,pb) constants, the bias
+terms) stays in torch on the device, exactly where the reference has it, so autograd reaches
+weight_a/weight_b/bias_a/bias_b/pa/pb unchanged.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi as K
+from .lrt import GaussianView, current_seed, _layer_ids
+
+_LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
+
+
+class _GammaSample(torch.autograd.Function):
+    """gamma.rsample() for a given alpha tensor (MF:110-117)."""
+
+    @staticmethod
+    def forward(ctx, alpha, u, exact, temperature, key):
+        K.require_device()
+        alpha_c = alpha.contiguous()
+        gamma = torch.empty_like(alpha_c)
+        noise = K.make_noise(u.contiguous() if u is not None else None, key[0], key[1])
+        K.check(K.lib.lbbnn_mf_gamma_sample(None, K.ptr(alpha_c), alpha_c.numel(), noise, int(exact), temperature,
+                                            K.ptr(gamma), K.current_stream()))
+        ctx.save_for_backward(alpha_c, gamma)
+        ctx.exact, ctx.t = exact, temperature
+        if exact:
+            ctx.mark_non_differentiable(gamma)
+        return gamma
+
+    @staticmethod
+    def backward(ctx, dgamma):
+        if ctx.exact:
+            return None, None, None, None, None
+        alpha, gamma = ctx.saved_tensors
+        dalpha = torch.empty_like(alpha)
+        K.check(K.lib.lbbnn_mf_gamma_sample_bwd(None, K.ptr(alpha), K.ptr(gamma), K.ptr(dgamma.contiguous()),
+                                                alpha.numel(), ctx.t, K.ptr(dalpha), K.current_stream()))
+        return dalpha, None, None, None, None
+
+
+class _MFSample(torch.autograd.Function):
+    """(w, sums[5]) = f(mu, rho, lambda, gamma, pb): weight sampling + log-prob element sums (csrc/mf.cu)."""
+
+    @staticmethod
+    def forward(ctx, mu, rho, lam, gamma, pb, alpha_stale, eps, mode, flags, key):
+        K.require_device()
+        mu, rho, lam = mu.contiguous(), rho.contiguous(), lam.contiguous()
+        gamma = gamma.contiguous() if gamma is not None else None
+        n = mu.numel()
+        w = torch.empty_like(mu)
+        sums = torch.zeros(5, dtype=torch.float32, device=mu.device)
+        ws = K.workspace(K.lib.lbbnn_mf_workspace_bytes(n), mu.device)
+        eps = eps.contiguous() if eps is not None else None
+        noise = K.make_noise(eps, key[0], key[1])
+        K.check(K.lib.lbbnn_mf_sample_fwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma, allow_none=True),
+                                          K.ptr(alpha_stale, allow_none=True), K.ptr(pb), n, noise, mode, flags,
+                                          K.ptr(w), K.ptr(sums), ws.data_ptr(), ws.numel(), K.current_stream()))
+        ctx.save_for_backward(mu, rho, lam, gamma, pb, eps)
+        ctx.mode, ctx.flags, ctx.key = mode, flags, key
+        return w, sums
+
+    @staticmethod
+    def backward(ctx, dw, dsums):
+        if ctx.mode != K.MF_SAMPLE:
+            raise K.LbbnnError("gradients through the medimean / joint-mean forward are not implemented "
+                               "(the reference only uses them under no_grad)")
+        mu, rho, lam, gamma, pb, eps = ctx.saved_tensors
+        n = mu.numel()
+        dmu, drho, dlam = torch.empty_like(mu), torch.empty_like(mu), torch.empty_like(mu)
+        want_dg = ctx.needs_input_grad[3]
+        dgamma = torch.empty_like(mu) if want_dg else None
+        dpb = torch.zeros_like(pb)
+        ws = K.workspace(K.lib.lbbnn_mf_workspace_bytes(n), mu.device)
+        noise = K.make_noise(eps, ctx.key[0], ctx.key[1])
+        dw_c = dw.contiguous() if dw is not None else None
+        ds_c = dsums.contiguous() if dsums is not None else None
+        K.check(K.lib.lbbnn_mf_sample_bwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma), K.ptr(pb), n, noise, ctx.flags,
+                                          K.ptr(dw_c, allow_none=True), K.ptr(ds_c, allow_none=True), K.ptr(dmu),
+                                          K.ptr(drho), K.ptr(dlam), K.ptr(dgamma, allow_none=True), K.ptr(dpb),
+                                          ws.data_ptr(), ws.numel(), K.current_stream()))
+        return dmu, drho, dlam, dgamma, dpb, None, None, None, None, None
+
+
+class _Linear(torch.autograd.Function):
+    """F.linear(x, W, b) on the fp32 SIMT GEMM kernels (MF:255)."""
+
+    @staticmethod
+    def forward(ctx, x, W, b):
+        K.require_device()
+        x, W, b = x.contiguous(), W.contiguous(), b.contiguous()
+        B, kf = x.shape
+        nf = W.shape[0]
+        out = torch.empty(B, nf, dtype=torch.float32, device=x.device)
+        ws = K.workspace(K.lrt_workspace_bytes(B, kf, nf), x.device)
+        K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(x), K.ptr(W), K.ptr(b), B, kf, nf, 0, K.ptr(out), ws.data_ptr(), ws.numel(),
+                                           K.current_stream()))
+        ctx.save_for_backward(x, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, W = ctx.saved_tensors
+        g = g.contiguous()
+        B, kf = x.shape
+        nf = W.shape[0]
+        ws = K.workspace(K.lrt_workspace_bytes(B, kf, nf), x.device)
+        dW, db = torch.empty_like(W), torch.empty(nf, dtype=torch.float32, device=x.device)
+        K.check(K.lib.lbbnn_linear_f32_bwd_params(K.ptr(x), K.ptr(g), B, kf, nf, K.ptr(dW), K.ptr(db), ws.data_ptr(),
+                                                  ws.numel(), K.current_stream()))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x)
+            K.check(K.lib.lbbnn_linear_f32_bwd_input(K.ptr(x), K.ptr(W), K.ptr(g), B, kf, nf, 0, K.ptr(dx), ws.data_ptr(),
+                                                     ws.numel(), K.current_stream()))
+        return dx, dW, db
+
+
+class _StdGammaReparam(torch.autograd.Function):
+    """Injected standard-gamma draw with torch's implicit reparameterisation gradient (gamma.py:79-87)."""
+
+    @staticmethod
+    def forward(ctx, a, g0):
+        ctx.save_for_backward(a.detach(), g0)
+        return g0.clone()
+
+    @staticmethod
+    def backward(ctx, grad):
+        a, g0 = ctx.saved_tensors
+        return grad * torch._standard_gamma_grad(a, g0), None
+
+
+class MFBernoulliView:
+    """Stand-in for the reference's `Bernoulli` helper (MF:105-128): `.alpha` is a plain tensor attribute the
+    caller refreshes (MF:292-297, 369-374); `.exact` False = relaxed at `temperature` (TEMPER_PRIOR, MF:44)."""
+
+    def __init__(self, alpha, temperature=0.001):
+        self.alpha = alpha
+        self.exact = False
+        self.temperature = temperature
+        self._uid = next(_layer_ids)
+        self._calls = 0
+        self.last_noise_key = None
+
+    def rsample(self, u=None):
+        self._calls += 1
+        self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
+        return _GammaSample.apply(self.alpha, u, bool(self.exact), float(self.temperature), self.last_noise_key)
+
+
+class _ExactFlag:
+    """The `.exact` switch of GaussGamma / BetaBinomial (MF:137,160), flipped by the driver at epoch 20 (MF:559-569)."""
+
+    def __init__(self, **kw):
+        self.exact = False
+        self.__dict__.update(kw)
+
+
+class BayesianLinear(nn.Module):
+    """MF layer, drop-in for LBBNN-GP-MF.py:182-255 (ctor `(in_features, out_features, layer_id)`).
+    `noise=` on forward injects {"eps_w","eps_b","g0_w","g0_b"} (parity tests)."""
+
+    def __init__(self, in_features, out_features, layer_id=1, *, device=None, temperature=0.001, mu_init=0.2,
+                 lambda_init=(0.0, 1.0), logprob_on_ws=False):
+        super().__init__()
+        self.layer, self.in_features, self.out_features = layer_id, in_features, out_features
+        U = lambda *shape: torch.empty(*shape)  # noqa: E731  (same RNG consumption order as the reference ctor)
+        self.weight_mu = nn.Parameter(U(out_features, in_features).uniform_(-mu_init, mu_init))
+        self.weight_rho = nn.Parameter(U(out_features, in_features).uniform_(-5, -4))
+        self.weight_a = nn.Parameter(U(1).uniform_(1, 1.1))
+        self.weight_b = nn.Parameter(U(1).uniform_(1, 1.1))
+        self.lambdal = nn.Parameter(U(out_features, in_features).uniform_(*lambda_init))
+        self.gammas = U(out_features, in_features).uniform_(0.99, 1)
+        self.alpha = U(out_features, in_features).uniform_(0.999, 0.9999)
+        self.pa = nn.Parameter(U(1).uniform_(1, 1.1))
+        self.pb = nn.Parameter(U(1).uniform_(1, 1.1))
+        self.bias_mu = nn.Parameter(U(out_features).uniform_(-0.2, 0.2))
+        self.bias_rho = nn.Parameter(U(out_features).uniform_(-5, -4))
+        self.bias_a = nn.Parameter(U(out_features).uniform_(1, 1.1))
+        self.bias_b = nn.Parameter(U(out_features).uniform_(1, 1.1))
+        self.weight = GaussianView(self.weight_mu, self.weight_rho)
+        self.bias = GaussianView(self.bias_mu, self.bias_rho)
+        self.gamma = MFBernoulliView(self.alpha, temperature)
+        self.weight_prior = _ExactFlag(a=self.weight_a, b=self.weight_b)
+        self.bias_prior = _ExactFlag(a=self.bias_a, b=self.bias_b)
+        self.gamma_prior = _ExactFlag(pa=self.pa, pb=self.pb)
+        self.logprob_on_ws = logprob_on_ws
+        self.log_prior = 0
+        self.log_variational_posterior = 0
+        self.lagrangian = 0
+        self._uid = next(_layer_ids)
+        self._calls = 0
+        self.last_noise_key = None
+        if device is not None:
+            self.to(device)
+
+    def _apply(self, fn, *a, **kw):          # keep the non-parameter tensors on the module's device
+        super()._apply(fn, *a, **kw)
+        self.gammas, self.alpha = fn(self.gammas), fn(self.alpha)
+        self.gamma.alpha = self.alpha
+        return self
+
+    def _tau(self, a, b, g0):
+        if g0 is None:
+            return torch.distributions.Gamma(a, b).rsample()
+        return _StdGammaReparam.apply(a, g0) / b
+
+    def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):
+        noise = noise or {}
+        sample_branch = self.training or sample
+        want_lp = self.training or calculate_log_probs
+        sb = self.bias.sigma
+        alpha_stale = None
+        if sample_branch:
+            self.gammas = cgamma
+            mode = K.MF_SAMPLE
+            eb = noise.get("eps_b")
+            bias = self.bias_mu + sb * (eb if eb is not None else torch.randn_like(sb))
+        elif medimean:
+            mode, bias = K.MF_MEDIMEAN, self.bias_mu
+        else:
+            mode, bias = K.MF_JOINTMEAN, self.bias_mu
+            alpha_stale = self.alpha.detach().contiguous()
+        flags = (K.MF_FLAG_LOGPROBS if want_lp else 0) | (K.MF_FLAG_LP_ON_WS if self.logprob_on_ws else 0) \
+            | (K.MF_FLAG_EXACT_GAMMA if self.gamma.exact else 0) | (K.MF_FLAG_EXACT_WPRIOR if self.weight_prior.exact else 0) \
+            | (K.MF_FLAG_EXACT_GPRIOR if self.gamma_prior.exact else 0)
+        self._calls += 1
+        self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
+        w, s = _MFSample.apply(self.weight_mu, self.weight_rho, self.lambdal, cgamma, self.pb, alpha_stale,
+                               noise.get("eps_w"), mode, flags, self.last_noise_key)
+        if want_lp:
+            self.alpha = 1 / (1 + torch.exp(-self.lambdal))                                   # MF:246
+            n = float(self.weight_mu.numel())
+            a, b, ba, bb, pa, pb = self.weight_a, self.weight_b, self.bias_a, self.bias_b, self.pa, self.pb
+            tau_w = self._tau(a, b, noise.get("g0_w"))
+            tau_b = self._tau(ba, bb, noise.get("g0_b"))
+            c_w = a * torch.log(b) + (a - 0.5) * tau_w - b * tau_w - torch.lgamma(a) - 0.5 * math.log(2 * math.pi)
+            gg_w = (s[0] * c_w - tau_w * s[1] + (n - s[0]) + n * 1e-8).sum()                   # MF:148-150
+            c_b = ba * torch.log(bb) + (ba - 0.5) * tau_b - bb * tau_b - torch.lgamma(ba) - 0.5 * math.log(2 * math.pi)
+            gg_b = (c_b - tau_b * bias ** 2 + 1e-8).sum()                                      # gamma = ones (MF:248)
+            bbin = s[2] + n * (torch.lgamma(pa + pb) - torch.lgamma(1 + pa + pb) - torch.lgamma(pa) - torch.lgamma(pb)).sum()
+            self.log_prior = gg_w + gg_b + bbin
+            lq_bias = (-_LOG_SQRT_2PI - torch.log(sb) - ((bias - self.bias_mu) ** 2) / (2 * sb ** 2)).sum()
+            self.log_variational_posterior = s[3] + s[4] + lq_bias
+        else:
+            self.log_prior, self.log_variational_posterior = 0, 0
+        return _Linear.apply(input, w, bias)
+
+
+class BayesianNetwork(nn.Module):
+    """784-400-600-10 MF network, drop-in for LBBNN-GP-MF.py:259-319 (sizes configurable)."""
+
+    def __init__(self, sizes=(28 * 28, 400, 600, 10), num_batches=600, **layer_kwargs):
+        super().__init__()
+        self.sizes, self.num_batches = tuple(sizes), num_batches
+        for n, (i, o) in enumerate(zip(sizes[:-1], sizes[1:]), 1):
+            setattr(self, f"l{n}", BayesianLinear(i, o, 1, **layer_kwargs))
+        self._names = [f"l{n}" for n in range(1, len(sizes))]
+
+    @property
+    def layers(self):
+        return [getattr(self, n) for n in self._names]
+
+    def forward(self, x, *gammas, sample=False, medimean=False, noises=None, **named):
+        gs = list(gammas) + [named[f"g{i}"] for i in range(len(gammas) + 1, len(self._names) + 1) if f"g{i}" in named]
+        x = x.view(-1, self.sizes[0])
+        ls = self.layers
+        for i, l in enumerate(ls):
+            x = l.forward(x, gs[i], sample, medimean, noise=None if noises is None else noises[i])
+            x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
+        return x
+
+    def log_prior(self):
+        return sum(l.log_prior for l in self.layers)
+
+    def log_variational_posterior(self):
+        return sum(l.log_variational_posterior for l in self.layers)
+
+    def sample_elbo(self, input, target, samples=1, noises=None, us=None):
+        """MF:285-319.  noises / us: per-sample lists of per-layer injected noise (tests)."""
+        outs, lps, lqs, nlls = [], [], [], []
+        for i in range(samples):
+            gs = []
+            for li, l in enumerate(self.layers):
+                l.alpha = 1 / (1 + torch.exp(-l.lambdal))
+                l.gamma.alpha = l.alpha
+                gs.append(l.gamma.rsample(None if us is None else us[i][li]))
+            out = self.forward(input, *gs, sample=True, medimean=False, noises=None if noises is None else noises[i])
+            outs.append(out)
+            lps.append(self.log_prior())
+            lqs.append(self.log_variational_posterior())
+            nlls.append(F.nll_loss(out, target, reduction="sum"))
+        log_prior, log_q, nll = torch.stack(lps).mean(), torch.stack(lqs).mean(), torch.stack(nlls).mean()
+        loss = nll + (log_q - log_prior) / self.num_batches
+        return loss, log_prior, log_q, nll

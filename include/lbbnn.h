@@ -179,6 +179,48 @@ LBBNN_API size_t lbbnn_colsum2_workspace_bytes(int64_t rows, int64_t cols);
 LBBNN_API int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols,
                             float* out, void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
+/* ---- plain fp32 linear layer on the same SIMT GEMM kernels: out = x W^T + b  (F.linear, MF:255) ------
+ * fwd (optional relu), bwd_params: dW = G^T x, db = sum_b G;  bwd_input: dx = G W (optional relu mask). */
+LBBNN_API int lbbnn_linear_f32_fwd(const float* x, const float* W, const float* bias, int64_t batch,
+                                   int64_t in_features, int64_t out_features, int flags, float* out,
+                                   void* workspace, size_t workspace_bytes, lbbnn_stream s);
+LBBNN_API int lbbnn_linear_f32_bwd_params(const float* x, const float* gout, int64_t batch, int64_t in_features,
+                                          int64_t out_features, float* dW, float* dbias,
+                                          void* workspace, size_t workspace_bytes, lbbnn_stream s);
+LBBNN_API int lbbnn_linear_f32_bwd_input(const float* x, const float* W, const float* gout, int64_t batch,
+                                         int64_t in_features, int64_t out_features, int flags, float* dx,
+                                         void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+/* ---- mean-field (full weight sampling) path, LBBNN-GP-MF.py ---------------------------------------
+ * gamma_sample: gamma.rsample() (MF:105-117): exact -> [u < alpha]; else torch's RelaxedBernoulli
+ *   reparameterisation at `temperature` (clamped probs / uniforms, clipped sigmoid).  alpha comes from
+ *   lambdal (sigmoid) or is given; u: lbbnn_noise (injected uniform or native Philox).
+ * sample_fwd: w = gamma (mu + sigma eps) | gamma mu | alpha mu (MF:232-242) + the five element sums the
+ *   log-probs of MF:247-251 are built from (see csrc/mf.cu); sums = 5 floats.
+ * sample_bwd: (dL/dw, dL/dsums) -> dmu, drho, dlambdal, dgamma (NULL = gamma needs no grad), dpb. */
+enum { LBBNN_MF_SAMPLE = 0, LBBNN_MF_MEDIMEAN = 1, LBBNN_MF_JOINTMEAN = 2 };
+enum {
+  LBBNN_MF_FLAG_LOGPROBS = 1,
+  LBBNN_MF_FLAG_LP_ON_WS = 2,       /* sim-study variant: log-probs at the unmasked ws (MFsim:233,237) */
+  LBBNN_MF_FLAG_EXACT_GAMMA = 4,    /* gamma.exact       (MF:122-124) */
+  LBBNN_MF_FLAG_EXACT_WPRIOR = 8,   /* weight_prior.exact (MF:142-146) */
+  LBBNN_MF_FLAG_EXACT_GPRIOR = 16   /* gamma_prior.exact  (MF:163-164) */
+};
+LBBNN_API size_t lbbnn_mf_workspace_bytes(int64_t n);
+LBBNN_API int lbbnn_mf_gamma_sample(const float* lambdal, const float* alpha, int64_t n, const lbbnn_noise* u,
+                                    int exact, float temperature, float* gamma, lbbnn_stream s);
+LBBNN_API int lbbnn_mf_gamma_sample_bwd(const float* lambdal, const float* alpha, const float* gamma,
+                                        const float* dgamma, int64_t n, float temperature, float* dout, lbbnn_stream s);
+LBBNN_API int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                  const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps,
+                                  int mode, int flags, float* w, float* sums,
+                                  void* workspace, size_t workspace_bytes, lbbnn_stream s);
+LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                  const float* pb, int64_t n, const lbbnn_noise* eps, int flags,
+                                  const float* dw, const float* dsums,
+                                  float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
+                                  void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
  * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.
  * step_inc (device int64 or NULL) is incremented by one: the trainer's step counter, bumped between
