@@ -116,12 +116,29 @@ struct SampleArgs {
   int exact_b, exact_wp, exact_gp;   // round(gamma.detach()) inside Bernoulli / GaussGamma / BetaBinomial log_prob
   float* w;
   double* part;    // [gridDim.x][5]
+  // optional, for the Monte-Carlo predictive loop: draw the hard mask inside ([u < alpha], no gamma tensor)
+  int native_gamma;
+  Noise gu;
+  // optional: sample the bias vector in the same launch (block 0): bias = b_mu + sigma_b eps_b  (MF:234)
+  const float *bias_mu, *bias_rho;
+  Noise eb;
+  int64_t n_bias;
+  float* bias_out;
 };
 
 __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a) {
   __shared__ double red[32];
-  Noise nz = a.eps;
+  Noise nz = a.eps, gu = a.gu;
   nz.resolve();
+  gu.resolve();
+  if (a.bias_out && blockIdx.x == 0) {
+    Noise eb = a.eb;
+    eb.resolve();
+    for (int64_t i = threadIdx.x; i < a.n_bias; i += blockDim.x) {
+      const float e = eb.ptr ? eb.ptr[i] : philox_normal1(eb.seed, eb.stream, (uint64_t)i);
+      a.bias_out[i] = fmaf(sigma_of(__ldg(a.bias_rho + i)), e, __ldg(a.bias_mu + i));
+    }
+  }
   const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w) &&
                    (a.gamma == nullptr || aligned16(a.gamma)) && (a.alpha_stale == nullptr || aligned16(a.alpha_stale)) &&
                    (nz.ptr == nullptr || aligned16(nz.ptr));
@@ -133,9 +150,14 @@ __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a)
     float mu[4], rho[4], lam[4], ga[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f}, w[4];
     ldq(a.mu, e0, a.n, vec, mu);
     if (a.mode == LBBNN_MF_SAMPLE || a.want_lp) ldq(a.rho, e0, a.n, vec, rho);
-    if (a.want_lp || (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr)) ldq(a.lam, e0, a.n, vec, lam);
+    if (a.want_lp || a.native_gamma || (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr)) ldq(a.lam, e0, a.n, vec, lam);
     if (a.mode == LBBNN_MF_JOINTMEAN) {
       if (a.alpha_stale) ldq(a.alpha_stale, e0, a.n, vec, ga);
+    } else if (a.native_gamma) {
+      float u[4];
+      philox_uniform4(gu.seed, gu.stream, (uint64_t)q, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ga[j] = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;
     } else {
       ldq(a.gamma, e0, a.n, vec, ga);
     }
@@ -261,6 +283,36 @@ __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwd
   if (threadIdx.x == 0) a.part[blockIdx.x] = t;
 }
 
+// Monte-Carlo predictive accumulators (test_ensemble, MF:367-406): per input row add log_softmax(logits) and
+// the row-normalised expit(log_softmax) of this weight sample; fp64 so the result does not depend on how the
+// samples are split across GPUs.  One warp per row; also bumps the sample counter (Philox stream key).
+__global__ void __launch_bounds__(kThreads) mc_accumulate_kernel(const float* __restrict__ logits, int64_t B, int64_t C,
+                                                                 double* __restrict__ sum_logp, double* __restrict__ sum_prob,
+                                                                 int64_t* counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (b < B) {
+    const float* row = logits + b * C;
+    float mx = -INFINITY;
+    for (int64_t c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int64_t c = lane; c < C; c += 32) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    float ps = 0.f;
+    for (int64_t c = lane; c < C; c += 32) ps += 1.0f / (1.0f + expf(-(row[c] - lse)));
+    ps = warp_sum(ps);
+    for (int64_t c = lane; c < C; c += 32) {
+      const float lp = row[c] - lse;
+      sum_logp[b * C + c] += (double)lp;
+      sum_prob[b * C + c] += (double)((1.0f / (1.0f + expf(-lp))) / ps);
+    }
+  }
+  if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter += 1;
+}
+
 __global__ void scale_scalar_kernel(float* v, const float* c, int k) { *v *= c ? c[k] : 0.f; }
 
 int64_t ew_blocks(int64_t n) {
@@ -296,11 +348,14 @@ extern "C" int lbbnn_mf_gamma_sample_bwd(const float* lambdal, const float* alph
   return check_launch("mf_gamma_bwd");
 }
 
-extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
-                                   const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode,
-                                   int flags, float* w, float* sums, void* ws, size_t ws_bytes, lbbnn_stream s) {
+static int mf_sample_launch(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                            const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode, int flags,
+                            float* w, float* sums, void* ws, size_t ws_bytes, const lbbnn_noise* gamma_u,
+                            const float* bias_mu, const float* bias_rho, const lbbnn_noise* eps_b, int64_t n_bias,
+                            float* bias_out, lbbnn_stream s) {
   LBBNN_REQUIRE(mu && rho && lambdal && w && n > 0, "NULL argument");
-  LBBNN_REQUIRE(mode == LBBNN_MF_JOINTMEAN || gamma, "gamma required");
+  LBBNN_REQUIRE(mode == LBBNN_MF_JOINTMEAN || gamma || gamma_u, "gamma (tensor or native draw) required");
+  LBBNN_REQUIRE(!bias_out || (bias_mu && bias_rho && n_bias > 0), "bias sampling needs bias_mu/bias_rho");
   const bool lp = flags & LBBNN_MF_FLAG_LOGPROBS;
   LBBNN_REQUIRE(!lp || (sums && pb && ws && ws_bytes >= lbbnn_mf_workspace_bytes(n)), "log-probs need sums, pb and workspace");
   SampleArgs a;
@@ -311,6 +366,9 @@ extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const floa
   a.exact_wp = (flags & LBBNN_MF_FLAG_EXACT_WPRIOR) ? 1 : 0;
   a.exact_gp = (flags & LBBNN_MF_FLAG_EXACT_GPRIOR) ? 1 : 0;
   a.w = w; a.part = (double*)ws;
+  a.native_gamma = (gamma == nullptr && gamma_u != nullptr && mode != LBBNN_MF_JOINTMEAN) ? 1 : 0;
+  a.gu = make_noise(gamma_u);
+  a.bias_mu = bias_mu; a.bias_rho = bias_rho; a.eb = make_noise(eps_b); a.n_bias = n_bias; a.bias_out = bias_out;
   const unsigned blocks = (unsigned)ew_blocks(n);
   mf_sample_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
   if (int rc = check_launch("mf_sample")) return rc;
@@ -319,6 +377,30 @@ extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const floa
     return check_launch("mf_sum_partials");
   }
   return LBBNN_OK;
+}
+
+extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                   const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode,
+                                   int flags, float* w, float* sums, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  return mf_sample_launch(mu, rho, lambdal, gamma, alpha_stale, pb, n, eps, mode, flags, w, sums, ws, ws_bytes, nullptr,
+                          nullptr, nullptr, nullptr, 0, nullptr, s);
+}
+
+// one launch per layer of the Monte-Carlo predictive loop: hard mask drawn natively, weights and bias sampled
+extern "C" int lbbnn_mf_sample_predict(const lbbnn_layer* L, const lbbnn_noise* gamma_u, const lbbnn_noise* eps_w,
+                                       const lbbnn_noise* eps_b, float* w, float* bias, lbbnn_stream s) {
+  LBBNN_REQUIRE(L && gamma_u && w && bias, "NULL argument");
+  return mf_sample_launch(L->weight_mu, L->weight_rho, L->lambdal, nullptr, nullptr, nullptr, L->in_features * L->out_features,
+                          eps_w, LBBNN_MF_SAMPLE, 0, w, nullptr, nullptr, 0, gamma_u, L->bias_mu, L->bias_rho, eps_b,
+                          L->out_features, bias, s);
+}
+
+extern "C" int lbbnn_mc_accumulate(const float* logits, int64_t batch, int64_t classes, double* sum_logp, double* sum_prob,
+                                   int64_t* counter, lbbnn_stream s) {
+  LBBNN_REQUIRE(logits && sum_logp && sum_prob && batch > 0 && classes > 0, "NULL argument");
+  mc_accumulate_kernel<<<(unsigned)ceil_div(batch, kThreads / 32), kThreads, 0, (cudaStream_t)s>>>(logits, batch, classes,
+                                                                                                 sum_logp, sum_prob, counter);
+  return check_launch("mc_accumulate");
 }
 
 extern "C" int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma, const float* pb,

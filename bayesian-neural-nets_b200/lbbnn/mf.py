@@ -301,3 +301,106 @@ class BayesianNetwork(nn.Module):
         log_prior, log_q, nll = torch.stack(lps).mean(), torch.stack(lqs).mean(), torch.stack(nlls).mean()
         loss = nll + (log_q - log_prior) / self.num_batches
         return loss, log_prior, log_q, nll
+
+
+class MCPredictor:
+    """Posterior-predictive model averaging over Monte-Carlo weight samples (test_ensemble, MF:345-436):
+    for each sample, fresh hard masks gamma ~ Bernoulli(alpha) and weights per layer, a forward over the whole
+    input batch, and the two accumulators of the reference (mean log-softmax -> ensemble argmax, MF:416-417;
+    mean row-normalised expit -> predictive probabilities / OOD entropy, MF:397-408, 478-494).
+
+    One sample = one CUDA-graph replay (3 kernels per layer + 1).  Sample s draws from Philox streams keyed
+    by s itself (a device counter), so any split of [0, S) across ranks reproduces the same draws; partial
+    sums are fp64 and are combined with ONE all-reduce (process_group) -- argmax is independent of the split.
+    """
+
+    NSTREAMS = 4   # Philox streams per (sample, layer): gamma u, eps_w, eps_b, spare
+
+    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None):
+        K.require_device()
+        self.net, self.layers, self.B = net, list(net.layers), int(batch)
+        dev = self.layers[0].weight_mu.device
+        self.device = dev
+        self.seed = current_seed() if seed is None else int(seed)
+        self.pg = process_group
+        f32 = dict(dtype=torch.float32, device=dev)
+        sizes = [(l.in_features, l.out_features) for l in self.layers]
+        self.x = torch.zeros(self.B, sizes[0][0], **f32)
+        self.w = [torch.zeros(o, i, **f32) for i, o in sizes]
+        self.b = [torch.zeros(o, **f32) for _, o in sizes]
+        self.h = [torch.zeros(self.B, o, **f32) for _, o in sizes]
+        C_ = sizes[-1][1]
+        self.sum_logp = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
+        self.sum_prob = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.ws = torch.empty(max(K.lrt_workspace_bytes(self.B, i, o) for i, o in sizes), dtype=torch.uint8, device=dev)
+        self.kernels_per_sample = 0
+        self.graph = None
+        if use_graph:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                self._enqueue()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._enqueue()
+            self.reset()
+
+    def _noise(self, layer, which):
+        stride = self.NSTREAMS * len(self.layers)
+        return K.make_noise(None, self.seed, layer * self.NSTREAMS + which, self.counter, stride)
+
+    def _enqueue(self):
+        st = K.current_stream()
+        L = len(self.layers)
+        h = self.x
+        n = 0
+        for i, l in enumerate(self.layers):
+            desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+            K.check(K.lib.lbbnn_mf_sample_predict(desc, self._noise(i, 0), self._noise(i, 1), self._noise(i, 2),
+                                                  K.ptr(self.w[i]), K.ptr(self.b[i]), st))
+            K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(h), K.ptr(self.w[i]), K.ptr(self.b[i]), self.B, l.in_features,
+                                               l.out_features, K.FLAG_RELU if i < L - 1 else 0, K.ptr(self.h[i]),
+                                               self.ws.data_ptr(), self.ws.numel(), st))
+            n += 3
+            h = self.h[i]
+        K.check(K.lib.lbbnn_mc_accumulate(K.ptr(h), self.B, self.layers[-1].out_features, self.sum_logp.data_ptr(),
+                                          self.sum_prob.data_ptr(), K.ptr(self.counter, torch.int64), st))
+        self.kernels_per_sample = n + 1
+
+    def reset(self, first_sample=0):
+        self.sum_logp.zero_()
+        self.sum_prob.zero_()
+        self.counter.fill_(int(first_sample))
+
+    def run(self, x, samples, first_sample=0):
+        """Accumulate `samples` weight samples with global indices first_sample.. on this rank."""
+        self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+        self.reset(first_sample)
+        for _ in range(samples):
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._enqueue()
+
+    def result(self, total_samples):
+        """Combine ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics."""
+        if self.pg is not None:
+            both = torch.stack([self.sum_logp, self.sum_prob])
+            torch.distributed.all_reduce(both, group=self.pg)
+            sum_logp, sum_prob = both[0], both[1]
+        else:
+            sum_logp, sum_prob = self.sum_logp, self.sum_prob
+        mean_logp = sum_logp / total_samples
+        probs = sum_prob / total_samples
+        return {"mean_logp": mean_logp, "pred": mean_logp.argmax(1), "probs": probs,
+                "entropy": -(probs * torch.log(probs)).sum(1)}
+
+
+def shard_samples(total, world, rank):
+    """Contiguous split of the MC sample indices [0, total) across ranks: (first, count)."""
+    base, rem = divmod(total, world)
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)

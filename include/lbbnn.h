@@ -215,6 +215,15 @@ LBBNN_API int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const float
                                   const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps,
                                   int mode, int flags, float* w, float* sums,
                                   void* workspace, size_t workspace_bytes, lbbnn_stream s);
+/* Monte-Carlo posterior-predictive loop (test_ensemble, MF:345-436).  sample_predict: one launch per layer
+ * draws the hard mask [u < sigmoid(lambdal)] natively (no gamma tensor), w = gamma (mu + sigma eps_w) and
+ * bias = b_mu + sigma_b eps_b.  mc_accumulate: per weight sample, sum_logp += log_softmax(logits) and
+ * sum_prob += row-normalised expit(log_softmax) (MF:397-406), both fp64 (batch,classes); bumps `counter`
+ * (device int64, the sample index that keys the Philox streams of the next replay). */
+LBBNN_API int lbbnn_mf_sample_predict(const lbbnn_layer* layer, const lbbnn_noise* gamma_u, const lbbnn_noise* eps_w,
+                                      const lbbnn_noise* eps_b, float* w, float* bias, lbbnn_stream s);
+LBBNN_API int lbbnn_mc_accumulate(const float* logits, int64_t batch, int64_t classes, double* sum_logp,
+                                  double* sum_prob, int64_t* counter, lbbnn_stream s);
 LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
                                   const float* pb, int64_t n, const lbbnn_noise* eps, int flags,
                                   const float* dw, const float* dsums,

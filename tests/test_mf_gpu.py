@@ -132,3 +132,57 @@ def test_mf_mnist_sample_elbo_matches_reference(lb):
     for l in net.layers:
         for k in MF_NAMES:
             assert torch.isfinite(getattr(l, k).grad).all(), k
+
+
+def _oracle_mc(net_params, x, seed, samples, lb, first=0):
+    """Oracle predictive average fed with the kernels' exported Philox noise for sample indices first.."""
+    L = len(net_params)
+    stride = lb.mf.MCPredictor.NSTREAMS * L
+    sum_logp = torch.zeros(x.shape[0], net_params[-1]["weight_mu"].shape[0], dtype=torch.float64)
+    sum_prob = torch.zeros_like(sum_logp)
+    for s in range(first, first + samples):
+        h = x
+        for i, p in enumerate(net_params):
+            o, k = p["weight_mu"].shape
+            base = i * lb.mf.MCPredictor.NSTREAMS + s * stride
+            u = lb.philox_uniform((o, k), seed, base + 0).cpu()
+            ew = lb.philox_normal((o, k), seed, base + 1).cpu()
+            eb = lb.philox_normal((o,), seed, base + 2).cpu()
+            g = O.exact_bernoulli_sample(O.alpha_of(p["weight_mu"] * 0 + p["lambdal"]), u)
+            h, _, _ = O.mf_forward(h, p, g, {"eps_w": ew, "eps_b": eb}, calc_log_probs=False)
+            h = torch.relu(h) if i < L - 1 else torch.log_softmax(h, 1)
+        sum_logp += h.double()
+        pr = torch.sigmoid(h)
+        sum_prob += (pr / pr.sum(1, keepdim=True)).double()
+    return sum_logp, sum_prob
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph):
+    sizes = [(64, 48), (48, 40), (40, 10)]
+    case = C.mf_net_case(seed=60, batch=50, sizes=sizes)
+    rng = np.random.default_rng(1)
+    for p in case["layers"]:
+        p["lambdal"] = C.t(rng.normal(0.0, 2.0, size=tuple(p["lambdal"].shape)))
+        p["weight_mu"] = p["weight_mu"] * 5          # decisive logits: argmax margins well above fp32 noise
+    net = lb.mf.BayesianNetwork((64, 48, 40, 10)).cuda()
+    with torch.no_grad():
+        for l, p in zip(net.layers, case["layers"]):
+            for k, v in p.items():
+                getattr(l, k).copy_(v)
+    S = 12
+    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph)
+    mc.run(case["x"].cuda(), S)
+    res = mc.result(S)
+    ref_logp, ref_prob = _oracle_mc(case["layers"], case["x"], 77, S, lb)
+    assert C.rel_err(mc.sum_logp, ref_logp) < 1e-5 and C.rel_err(mc.sum_prob, ref_prob) < 1e-5
+    assert torch.equal(res["pred"].cpu(), (ref_logp / S).argmax(1))          # ensemble predictions bit-exact
+    # sharding: 3 "ranks" each take a slice of the sample indices; the fp64 partials sum to the same thing
+    tot_l, tot_p = torch.zeros_like(mc.sum_logp), torch.zeros_like(mc.sum_prob)
+    for r in range(3):
+        first, cnt = lb.mf.shard_samples(S, 3, r)
+        mc.run(case["x"].cuda(), cnt, first_sample=first)
+        tot_l += mc.sum_logp
+        tot_p += mc.sum_prob
+    assert (tot_l - res["mean_logp"] * S).abs().max().item() < 1e-9
+    assert torch.equal((tot_l / S).argmax(1), res["pred"])
