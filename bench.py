@@ -414,15 +414,195 @@ def run_ours(args):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------
+# MC posterior-predictive workload (BASELINE.json configs[3]): MF net, S = 1024 weight samples over a
+# 1000-input test batch, samples sharded across the GPUs, one all-reduce of the accumulators.
+# ------------------------------------------------------------------------------------------------
+MC_SAMPLES, MC_BATCH, MC_SIZES = 1024, 1000, (784, 400, 600, 10)
+
+
+def _mc_net_params(rng):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lbbnn_oracle as O
+    layers = [O.init_mf_params(rng, i, o) for i, o in zip(MC_SIZES[:-1], MC_SIZES[1:])]
+    for p in layers:   # trained-like inclusion probabilities spanning (0,1)
+        p["lambdal"] = torch.from_numpy(rng.normal(0.0, 2.0, size=tuple(p["lambdal"].shape)).astype(np.float32))
+    return layers, O
+
+
+def cpu_reference_mc(budget_s=15.0, max_samples=64):
+    rng = np.random.default_rng(0)
+    layers, O = _mc_net_params(rng)
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = torch.from_numpy(rng.random((MC_BATCH, MC_SIZES[0]), dtype=np.float32))
+    acc = torch.zeros(MC_BATCH, MC_SIZES[-1])
+    done, t0 = 0, time.perf_counter()
+    with torch.no_grad():
+        while done < max_samples and (done < 2 or time.perf_counter() - t0 < budget_s):
+            h = x
+            for i, p in enumerate(layers):
+                alpha = O.alpha_of(p["lambdal"])
+                g = torch.bernoulli(alpha)                                        # gamma.exact = True (MF:113)
+                nz = {"eps_w": torch.randn_like(alpha), "eps_b": torch.randn(alpha.shape[0])}
+                h, _, _ = O.mf_forward(h, p, g, nz, calc_log_probs=False)
+                h = torch.relu(h) if i < len(layers) - 1 else torch.log_softmax(h, 1)
+            acc += h
+            done += 1
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "MC weight-samples/s", "cores": cores, "kind": "port", "steps": done,
+            "ms_per_step": dt / done * 1e3,
+            "sample": f"{done} MC weight samples (masks+weights+bias sampled, forward over {MC_BATCH} inputs, accumulate) "
+                      f"of the MF 784-400-600-10 net, oracle port on torch-CPU fp32, {cores} threads"}
+
+
+def mc_config(world):
+    return {"workload": f"mf_mc_predict: MF MLP 784-400-600-10 posterior-predictive averaging, {MC_SAMPLES} MC weight samples "
+                        f"x {MC_BATCH}-input batch per step, gamma.exact=True",
+            "mc_samples": MC_SAMPLES, "test_batch": MC_BATCH,
+            "parallelism": "single GPU" if world == 1 else f"MC samples sharded over {world} GPUs, one fp64 all-reduce per batch",
+            "l2": "each step re-samples all 559,600 weights 1024 times from Philox; inputs rotate through 8 test batches; "
+                  "the 6.7 MB of parameters are the step's own working set"}
+
+
+def run_mc(args):
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = cpu_reference_mc(budget_s=60.0, max_samples=max(8, args.steps))
+        print(json.dumps({"impl": "reference", "metric": "mc_predictive_samples_per_sec", "value": r["value"],
+                          "unit": r["unit"], "n_gpus": args.gpus, "steps": r["steps"], "warmup": 0,
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mc_config(1),
+                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    import lbbnn
+    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    rng = np.random.default_rng(0)
+    layers, _ = _mc_net_params(rng)
+    net = lbbnn.mf.BayesianNetwork(MC_SIZES).to(dev)
+    with torch.no_grad():
+        for l, p in zip(net.layers, layers):
+            for k, v in p.items():
+                getattr(l, k).copy_(v)
+    mc = lbbnn.mf.MCPredictor(net, batch=MC_BATCH, seed=4321, process_group=pg)
+    first, count = lbbnn.mf.shard_samples(MC_SAMPLES, world, rank)
+    xs_host = torch.from_numpy(rng.random((8, MC_BATCH, MC_SIZES[0]), dtype=np.float32)).pin_memory()
+    xs = xs_host.to(dev)
+    pred_host = torch.zeros(MC_BATCH, dtype=torch.int64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def step(i, host):
+        mc.run((xs_host if host else xs)[i % 8], count, first_sample=first)
+        res = mc.result(MC_SAMPLES)
+        if host:
+            pred_host.copy_(res["pred"], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return res
+
+    for i in range(args.warmup):
+        step(i, False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step(i, False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i, True)
+    barrier()
+    te1 = time.perf_counter()
+    e2e_ms = (te1 - te0) * 1e3
+    sampler.stop()
+    clocks = sampler.summary(t0, te1)
+    if world > 1:
+        tms = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
+        torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
+        ms, e2e_ms = tms.tolist()
+    if rank == 0:
+        from lbbnn import _capi as K
+        peaks = load_peaks()
+        # dominant-kernel roofline: the layer-1 sampling launch, cold L2, algorithmic 16 B per weight
+        l = net.layers[0]
+        desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        times = {"mf_sample_predict[l1]": [], "linear_f32_fwd[l1] (gemm+epilogue)": []}
+        st = K.current_stream()
+        for _ in range(12):
+            for name, fn in (("mf_sample_predict[l1]", lambda: K.lib.lbbnn_mf_sample_predict(
+                    desc, mc._noise(0, 0), mc._noise(0, 1), mc._noise(0, 2), K.ptr(mc.w[0]), K.ptr(mc.b[0]), st)),
+                    ("linear_f32_fwd[l1] (gemm+epilogue)", lambda: K.lib.lbbnn_linear_f32_fwd(
+                        K.ptr(mc.x), K.ptr(mc.w[0]), K.ptr(mc.b[0]), MC_BATCH, 784, 400, K.FLAG_RELU, K.ptr(mc.h[0]),
+                        mc.ws.data_ptr(), mc.ws.numel(), st))):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); K.check(fn()); b.record(); b.synchronize()
+                times[name].append(a.elapsed_time(b) * 1e3)
+        us_s = statistics.mean(times["mf_sample_predict[l1]"][2:])
+        us_g = statistics.mean(times["linear_f32_fwd[l1] (gemm+epilogue)"][2:])
+        nbytes = 16 * 784 * 400
+        cpu = cpu_reference_mc() if world == 1 else None
+        line = {"metric": "mc_predictive_samples_per_sec", "value": MC_SAMPLES * args.steps / (ms * 1e-3),
+                "unit": "MC weight-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": mc_config(world),
+                "e2e": {"value": MC_SAMPLES * args.steps / (e2e_ms * 1e-3), "unit": "MC weight-samples/s",
+                        "h2d_bytes_per_step": MC_BATCH * MC_SIZES[0] * 4, "d2h_bytes_per_step": MC_BATCH * 8,
+                        "ms_per_step": e2e_ms / args.steps},
+                "gpu_launches": mc.kernels_per_sample * count * args.steps, "kernels_per_sample": mc.kernels_per_sample,
+                "input_samples_per_sec": MC_SAMPLES * MC_BATCH * args.steps / (ms * 1e-3),
+                "roofline": {"bound": "hbm", "kernel": "mf_sample_predict[l1] (mask + weight + bias sampling)",
+                             "achieved": nbytes / (us_s * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                             "frac": nbytes / (us_s * 1e-6) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                             "peak_source": peaks["source"], "us_per_launch": us_s, "bytes_per_launch": nbytes,
+                             "timing": "cold L2 (256 MB memset before each launch), CUDA events, mean of 10"},
+                "kernels": [{"name": "mf_sample_predict[l1]", "us": round(us_s, 2)},
+                            {"name": "linear_f32_fwd[l1] (gemm+epilogue)", "us": round(us_g, 2),
+                             "gflops": round(2 * MC_BATCH * 784 * 400 / us_g / 1e3, 1)}],
+                "clocks": clocks}
+        if cpu is not None:
+            line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.barrier()
+        mc.graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES))
+    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict"])
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.workload == "mf_mc_predict":
+        run_mc(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
