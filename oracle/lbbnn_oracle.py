@@ -294,3 +294,116 @@ def init_mf_params(rng, in_features, out_features, dtype=torch.float32, sim=Fals
         "weight_a": u(1, 1.1, 1), "weight_b": u(1, 1.1, 1), "bias_a": u(1, 1.1, out_features),
         "bias_b": u(1, 1.1, out_features), "pa": u(1, 1.1, 1), "pb": u(1, 1.1, 1),
     }
+
+
+# --------------------------------------------------------------------------------------
+# Flows (flows2.py) and the MNF layer (LBBNN-GP-MF-MNF.py:133-239; sim variant MNFsim:145-251)
+# --------------------------------------------------------------------------------------
+def mlp_forward(h, linears, leaky=0.1):
+    """flows2.MLP (flows2:176-185): Linear -> LeakyReLU(0.1) ..., activation after the last Linear dropped."""
+    for i, (w, b) in enumerate(linears):
+        h = F.linear(h, w, b)
+        if i < len(linears) - 1:
+            h = F.leaky_relu(h, leaky)
+    return h
+
+
+def rnvp_forward(z, mask, tp):
+    """flows2.RNVP.forward/log_det (flows2:206-219).  tp: {"net": [(W,b)...], "t": (W,b), "s": (W,b)}.
+    Note (1-gate)*shift is added on ALL dims, masked ones included (flows2:215)."""
+    z1, z2 = (1 - mask) * z, mask * z
+    y = mlp_forward(z2, tp["net"])
+    shift, scale = F.linear(y, *tp["t"]), F.linear(y, *tp["s"])
+    gate = torch.sigmoid(scale)
+    x = (z1 * gate + (1 - gate) * shift) + z2
+    return x, ((1 - mask) * gate.log()).sum(-1)
+
+
+def iaf_forward(z, mask, tp):
+    """flows2.MNF (flows2:225-241): h = tanh(f(m z)); out = m z + (1-m)(z sigma + (1-sigma) mu);
+    log_det = ((1-m) log sigma).sum() over ALL dims (a scalar even for batched z, flows2:241)."""
+    h = torch.tanh(F.linear(mask * z, *tp["f"]))
+    mu, sigma = F.linear(h, *tp["g"]), torch.sigmoid(F.linear(h, *tp["k"]))
+    return mask * z + (1 - mask) * (z * sigma + (1 - sigma) * mu), ((1 - mask) * sigma.log()).sum()
+
+
+def propagate_flow(z, masks, transforms, kind="RNVP"):
+    """flows2.PropagateFlow.forward (flows2:41-46): returns the transformed TENSOR and the summed log-dets."""
+    logdet = 0
+    f = rnvp_forward if kind == "RNVP" else iaf_forward
+    for m, tp in zip(masks, transforms):
+        z, ld = f(z, m, tp)
+        logdet = logdet + ld
+    return z, logdet
+
+
+def mnf_sample_z(p, eps_z, masks, kind="RNVP"):
+    """sample_z (MNF:182-187): z0 = q0_mean + exp(q0_log_var)^0.5 * eps (B,in); z_flow; returns the LAST ROW of
+    the flowed batch, the squeezed log-dets, and z0 (what the layer stores in self.z)."""
+    q0_std = p["q0_log_var"].exp().sqrt().repeat(eps_z.shape[0], 1)
+    z0 = p["q0_mean"] + q0_std * eps_z
+    zs, logdet = propagate_flow(z0, masks, p["z_flow"], kind)
+    return zs[-1], (logdet.squeeze() if torch.is_tensor(logdet) else logdet), z0
+
+
+def mnf_forward(x, p, noise, sample=True, calc_kl=True, priors: Priors = Priors(), kind="RNVP"):
+    """MNF BayesianLinear.forward (MNF:190-239) with every draw injected:
+    noise = {eps_z (B,in), z_masks [T x (B,in)], eps (B,out),                      # activation branch
+             eps_z2 (1,in), z_masks2 [T x (1,in)], eps_r (out,), r_masks [T x (in,)]}  # KL branch
+    Returns (activations, kl)."""
+    z_k, _, _ = mnf_sample_z(p, noise["eps_z"], noise["z_masks"], kind)
+    act = lrt_forward(x, p, noise.get("eps"), sample=sample, z=z_k)        # MNF:195-200 / 203-206
+    if not calc_kl:
+        return act, 0
+    z2, log_det_q, z0 = mnf_sample_z(p, noise["eps_z2"], noise["z_masks2"], kind)   # MNF:210, self.z := (1,in)
+    a, s = alpha_of(p["lambdal"]), sigma_of(p["weight_rho"])
+    w_mean, w_var = z2 * p["weight_mu"] * a, s ** 2 * a ** 2
+    log_q0 = (-0.5 * math.log(math.pi) - 0.5 * p["q0_log_var"]
+              - 0.5 * ((z0 - p["q0_mean"]) ** 2 / p["q0_log_var"].exp())).sum()           # log pi, not log 2 pi
+    log_q = -log_det_q + log_q0
+    act_mu, act_var = p["r0_c"] @ w_mean.T, p["r0_c"] ** 2 @ w_var.T
+    a_r = torch.tanh(act_mu + act_var.sqrt() * noise["eps_r"])
+    mean_r = p["r0_b1"].outer(a_r).mean(-1)
+    log_var_r = p["r0_b2"].outer(a_r).mean(-1)
+    z_b, log_det_r = propagate_flow(z2, noise["r_masks"], p["r_flow"], kind)            # 1-D input
+    log_rb = (-0.5 * math.log(math.pi) - 0.5 * log_var_r
+              - 0.5 * ((z_b[-1] - mean_r) ** 2 / log_var_r.exp())).sum()                 # z_b[-1]: a SCALAR
+    log_r = log_det_r + log_rb
+    return act, lrt_kl(p, priors, z=z2) + log_q - log_r
+
+
+def mnf_net_loss(x, y, layers, noises, num_batches, priors: Priors = Priors(), kind="RNVP"):
+    """MNF BayesianNetwork.forward + train objective (MNF:244-275)."""
+    h = x.reshape(-1, layers[0]["weight_mu"].shape[1])
+    kl = 0
+    for i, (p, nz) in enumerate(zip(layers, noises)):
+        h, k = mnf_forward(h, p, nz, priors=priors, kind=kind)
+        kl = kl + k
+        h = F.relu(h) if i < len(layers) - 1 else F.log_softmax(h, dim=1)
+    nll = F.nll_loss(h, y, reduction="sum")
+    return nll + kl / num_batches, nll, kl, h
+
+
+def init_flow_params(rng, dim, num_transforms=2, h_sizes=(75, 75, 75, 75), kind="RNVP", hidden=100, dtype=torch.float32):
+    """nn.Linear default init ranges (U(+-1/sqrt(fan_in))) from a numpy Generator."""
+    def lin(i, o):
+        k = 1.0 / math.sqrt(i)
+        return (torch.from_numpy(rng.uniform(-k, k, size=(o, i))).to(dtype), torch.from_numpy(rng.uniform(-k, k, size=(o,))).to(dtype))
+    out = []
+    for _ in range(num_transforms):
+        if kind == "RNVP":
+            sizes = [dim] + list(h_sizes)
+            out.append({"net": [lin(a, b) for a, b in zip(sizes[:-1], sizes[1:])], "t": lin(sizes[-1], dim), "s": lin(sizes[-1], dim)})
+        else:
+            out.append({"f": lin(dim, hidden), "g": lin(hidden, dim), "k": lin(hidden, dim)})
+    return out
+
+
+def init_mnf_params(rng, in_features, out_features, num_transforms=2, h_sizes=(75, 75, 75, 75), kind="RNVP", dtype=torch.float32):
+    """MNF:140-176: LRT params with mu~U(-.01,.01) + q0/r0 vectors + the two flows."""
+    p = init_lrt_params(rng, in_features, out_features, mu_range=0.01, dtype=dtype)
+    n = lambda s=0.1, off=0.0: torch.from_numpy(off + s * rng.standard_normal(size=(in_features,))).to(dtype)  # noqa: E731
+    p.update({"q0_mean": n(), "q0_log_var": n(0.1, -9.0), "r0_c": n(), "r0_b1": n(), "r0_b2": n(),
+              "z_flow": init_flow_params(rng, in_features, num_transforms, h_sizes, kind, dtype=dtype),
+              "r_flow": init_flow_params(rng, in_features, num_transforms, h_sizes, kind, dtype=dtype)})
+    return p

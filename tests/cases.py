@@ -91,3 +91,73 @@ def mf_net_case(seed, batch, sizes=MNIST_SIZES, classes=10):
     x = t(rng.uniform(0.0, 1.0, size=(batch, sizes[0][0])))
     y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
     return {"layers": layers, "noises": noises, "us": us, "x": x, "y": y}
+
+
+def _masks(rng, T, *shape):
+    """RealNVP / IAF masks: bernoulli(0.5) as [u < 0.5] (flows2:209,234)."""
+    return [t((rng.uniform(0.0, 1.0, size=shape) < 0.5).astype(np.float32)) for _ in range(T)]
+
+
+def mnf_noise(rng, batch, in_features, out_features, T=2):
+    return {"eps_z": t(rng.standard_normal(size=(batch, in_features))), "z_masks": _masks(rng, T, batch, in_features),
+            "eps": t(rng.standard_normal(size=(batch, out_features))),
+            "eps_z2": t(rng.standard_normal(size=(1, in_features))), "z_masks2": _masks(rng, T, 1, in_features),
+            "eps_r": t(rng.standard_normal(size=(out_features,))), "r_masks": _masks(rng, T, in_features)}
+
+
+def mnf_layer_case(seed, batch, in_features, out_features, T=2, h_sizes=(75, 75, 75, 75), kind="RNVP"):
+    rng = np.random.default_rng(seed)
+    p = O.init_mnf_params(rng, in_features, out_features, T, h_sizes, kind)
+    # a wider q0 than the init (-9) so that z and the flows matter numerically
+    p["q0_log_var"] = t(-2.0 + 0.3 * rng.standard_normal(size=(in_features,)))
+    p["q0_mean"] = t(1.0 + 0.1 * rng.standard_normal(size=(in_features,)))
+    x = t(rng.uniform(0.0, 1.0, size=(batch, in_features)))
+    gout = t(rng.standard_normal(size=(batch, out_features)))
+    return {"p": p, "x": x, "gout": gout, "noise": mnf_noise(rng, batch, in_features, out_features, T)}
+
+
+def mnf_net_case(seed, batch, sizes=MNIST_SIZES, classes=10, T=2):
+    rng = np.random.default_rng(seed)
+    layers = [O.init_mnf_params(rng, i, o, T) for i, o in sizes]
+    x = t(rng.uniform(0.0, 1.0, size=(batch, sizes[0][0])))
+    y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
+    noises = [mnf_noise(rng, batch, i, o, T) for i, o in sizes]
+    return {"layers": layers, "noises": noises, "x": x, "y": y}
+
+
+def flat_named(p, prefix=""):
+    """Flatten a (possibly nested) MNF parameter dict into {name: tensor} with the reference's state_dict names."""
+    out = {}
+    for k, v in p.items():
+        if k in ("z_flow", "r_flow"):
+            for ti, tp in enumerate(v):
+                if "net" in tp:
+                    for li, (w, b) in enumerate(tp["net"]):
+                        out[f"{k}.transforms.{ti}.network.{2 * li}.weight"] = w
+                        out[f"{k}.transforms.{ti}.network.{2 * li}.bias"] = b
+                    for nm in ("t", "s"):
+                        out[f"{k}.transforms.{ti}.{nm}.weight"], out[f"{k}.transforms.{ti}.{nm}.bias"] = tp[nm]
+                else:
+                    for nm in ("f", "g", "k"):
+                        out[f"{k}.transforms.{ti}.{nm}.weight"], out[f"{k}.transforms.{ti}.{nm}.bias"] = tp[nm]
+        else:
+            out[k] = v
+    return out
+
+
+def unflatten_like(p, named):
+    """Inverse of flat_named: rebuild the nested dict `p` from {name: tensor}."""
+    out = {}
+    for k, v in p.items():
+        if k in ("z_flow", "r_flow"):
+            ts = []
+            for ti, tp in enumerate(v):
+                g = lambda nm: (named[f"{k}.transforms.{ti}.{nm}.weight"], named[f"{k}.transforms.{ti}.{nm}.bias"])  # noqa: E731
+                if "net" in tp:
+                    ts.append({"net": [g(f"network.{2 * li}") for li in range(len(tp["net"]))], "t": g("t"), "s": g("s")})
+                else:
+                    ts.append({"f": g("f"), "g": g("g"), "k": g("k")})
+            out[k] = ts
+        else:
+            out[k] = named[k]
+    return out

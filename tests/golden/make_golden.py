@@ -190,6 +190,95 @@ def golden_mf():
     print("mf golden written; loss", loss.item(), "log_prior", log_prior.item(), "log_q", log_q.item())
 
 
+def _mnf_queue(nz):
+    """Draw order of MNF BayesianLinear.forward in training (MNF:182-235)."""
+    q = [("normal", nz["eps_z"])] + [("uniform", 1.0 - m * 0.75) for m in nz["z_masks"]]      # u < .5 <=> mask = 1
+    q += [("normal", nz["eps"]), ("normal", nz["eps_z2"])] + [("uniform", 1.0 - m * 0.75) for m in nz["z_masks2"]]
+    q += [("normal", nz["eps_r"])] + [("uniform", 1.0 - m * 0.75) for m in nz["r_masks"]]
+    return q
+
+
+def _load_named(module, named):
+    sd = dict(module.named_parameters())
+    with torch.no_grad():
+        for k, v in named.items():
+            sd[k].copy_(v)
+
+
+def golden_mnf():
+    out = {}
+    for script, flows, tagp, hs in (("LBBNN-GP-MF-MNF.py", "flows2", "m", (75, 75, 75, 75)),
+                                     ("LBBNN-GP-MF-MNFsim_study.py", "flows_simstudy", "s", (50, 50, 50, 50, 50))):
+        ns = H.load_reference_classes(script, flows_module=flows)
+        Layer = ns["BayesianLinear"]
+        shapes = {"a": (71, 6, 37, 23), "b": (72, 17, 130, 10)} if tagp == "m" else {"a": (73, 9, 20, 1)}
+        for tag, (seed, b, i, o) in shapes.items():
+            key = tagp + tag
+            case = C.mnf_layer_case(seed, b, i, o, h_sizes=hs)
+            layer = Layer(i, o, 2)
+            _load_named(layer, C.flat_named(case["p"]))
+            layer.train()
+            x = case["x"].clone().requires_grad_(True)
+            with H.replay(H.NoiseQueue(_mnf_queue(case["noise"]))):
+                act = layer(x, sample=True)
+            kl = layer.kl
+            ((act * case["gout"]).sum() + kl / C.NUM_BATCHES).backward()
+            out[key + "_meta"] = np.array([seed, b, i, o, len(hs), hs[0]])
+            out[key + "_act"] = act.detach().numpy()
+            out[key + "_kl"] = np.float64(kl.item())
+            out[key + "_z"] = layer.z.detach().numpy()
+            out[key + "_dx"] = x.grad.numpy()
+            for name, prm in layer.named_parameters():
+                out[key + "_d_" + name] = prm.grad.numpy() if prm.numel() <= 4000 else C.grad_digest(prm.grad)["sample"]
+    np.savez_compressed(os.path.join(HERE, "mnf_layer.npz"), **out)
+
+    # IAF-style 'MNF' flow (flows2:225-241) through PropagateFlow, batched and 1-D
+    import flows2
+    rng = np.random.default_rng(80)
+    out = {}
+    for kind in ("RNVP", "MNF"):
+        tps = C.O.init_flow_params(rng, 24, 2, (75, 75, 75, 75), kind)
+        flow = flows2.PropagateFlow(kind, 24, 2)
+        named = C.flat_named({"z_flow": tps})
+        _load_named(flow, {k.replace("z_flow.", ""): v for k, v in named.items()})
+        for tag, shape in (("b", (5, 24)), ("v", (24,))):
+            z = C.t(rng.standard_normal(size=shape)).requires_grad_(True)
+            masks = C._masks(rng, 2, *shape)
+            with H.replay(H.NoiseQueue([("uniform", 1.0 - m * 0.75) for m in masks])):
+                zo, ld = flow(z)
+            ((zo * zo).sum() + ld.sum()).backward()
+            out[f"{kind}_{tag}_z"] = z.detach().numpy()
+            out[f"{kind}_{tag}_masks"] = np.stack([m.numpy() for m in masks])
+            out[f"{kind}_{tag}_out"] = zo.detach().numpy()
+            out[f"{kind}_{tag}_logdet"] = ld.detach().numpy()
+            out[f"{kind}_{tag}_dz"] = z.grad.numpy()
+        for k, v in named.items():
+            out[f"{kind}_p_{k}"] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, "flows.npz"), **out)
+
+    # MNIST-shape MNF network objective
+    ns = H.load_reference_classes("LBBNN-GP-MF-MNF.py", flows_module="flows2")
+    case = C.mnf_net_case(seed=90, batch=100)
+    net = ns["BayesianNetwork"]()
+    for lay, p in zip((net.l1, net.l2, net.l3), case["layers"]):
+        _load_named(lay, C.flat_named(p))
+    net.train()
+    q = []
+    for nz in case["noises"]:
+        q += _mnf_queue(nz)
+    with H.replay(H.NoiseQueue(q)):
+        logp = net(case["x"].view(100, 1, 28, 28), sample=True)
+    nll = torch.nn.functional.nll_loss(logp, case["y"], reduction="sum")
+    kl = net.kl()
+    (nll + kl / C.NUM_BATCHES).backward()
+    out = {"logp": logp.detach().numpy(), "nll": np.float64(nll.item()), "kl": np.float64(kl.item())}
+    for li, lay in enumerate((net.l1, net.l2, net.l3)):
+        for name, prm in lay.named_parameters():
+            out[f"l{li}_{name}"] = C.grad_digest(prm.grad)["sample"] if prm.numel() > 2000 else prm.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "mnf_net_mnist.npz"), **out)
+    print("mnf golden written; nll", nll.item(), "kl", kl.item())
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("lrt", "all"):

@@ -123,3 +123,61 @@ def test_mf_mnist_elbo_matches_reference():
             assert C.rel_err(d["sample"], g[f"l{li}_{k}_sample"]) < 2e-5, (li, k)
             if f"l{li}_{k}_full" in g:
                 assert C.rel_err(v.grad, g[f"l{li}_{k}_full"]) < 2e-5, (li, k)
+
+
+def _mnf_oracle(case, priors=O.Priors(), dtype=torch.float32):
+    named = {k: v.to(dtype).clone().requires_grad_(True) for k, v in C.flat_named(case["p"]).items()}
+    p = C.unflatten_like(case["p"], named)
+    x = case["x"].to(dtype).clone().requires_grad_(True)
+    nz = {k: ([m.to(dtype) for m in v] if isinstance(v, list) else v.to(dtype)) for k, v in case["noise"].items()}
+    act, kl = O.mnf_forward(x, p, nz, priors=priors)
+    ((act * case["gout"].to(dtype)).sum() + kl / C.NUM_BATCHES).backward()
+    return act, kl, x, named
+
+
+@pytest.mark.parametrize("key", ["ma", "mb", "sa"])
+def test_mnf_layer_matches_reference(key):
+    g = _npz("mnf_layer.npz")
+    seed, b, i, o, nh, hw = (int(v) for v in g[f"{key}_meta"])
+    case = C.mnf_layer_case(seed, b, i, o, h_sizes=(hw,) * nh)
+    pri = O.Priors(0.1, 1.3, 0.3, 0.0, 1.3) if key == "sa" else O.Priors()        # MNFsim:157-174
+    act, kl, x, named = _mnf_oracle(case, pri)
+    assert C.rel_err(act, g[f"{key}_act"]) < TOL
+    assert abs(kl.item() - float(g[f"{key}_kl"])) / abs(float(g[f"{key}_kl"])) < 5e-6
+    assert C.rel_err(x.grad, g[f"{key}_dx"]) < 5e-6
+    for name, v in named.items():
+        ref = g[f"{key}_d_{name}"]
+        got = v.grad if v.numel() <= 4000 else torch.from_numpy(C.grad_digest(v.grad)["sample"])
+        assert C.rel_err(got, ref) < 5e-5, name
+
+
+@pytest.mark.parametrize("kind", ["RNVP", "MNF"])
+def test_flows_match_reference(kind):
+    g = _npz("flows.npz")
+    rng = np.random.default_rng(0)
+    tmpl = O.init_flow_params(rng, 24, 2, (75, 75, 75, 75), kind)
+    named = {k: torch.from_numpy(g[f"{kind}_p_{k}"]) for k in C.flat_named({"z_flow": tmpl})}
+    tps = C.unflatten_like({"z_flow": tmpl}, named)["z_flow"]
+    for tag in ("b", "v"):
+        z = torch.from_numpy(g[f"{kind}_{tag}_z"]).requires_grad_(True)
+        masks = [torch.from_numpy(m) for m in g[f"{kind}_{tag}_masks"]]
+        zo, ld = O.propagate_flow(z, masks, tps, kind)
+        ((zo * zo).sum() + ld.sum()).backward()
+        assert C.rel_err(zo, g[f"{kind}_{tag}_out"]) < TOL
+        assert C.rel_err(ld, g[f"{kind}_{tag}_logdet"]) < TOL
+        assert C.rel_err(z.grad, g[f"{kind}_{tag}_dz"]) < 5e-6
+
+
+def test_mnf_mnist_net_matches_reference():
+    g = _npz("mnf_net_mnist.npz")
+    case = C.mnf_net_case(seed=90, batch=100)
+    named = [{k: v.clone().requires_grad_(True) for k, v in C.flat_named(p).items()} for p in case["layers"]]
+    layers = [C.unflatten_like(p, n) for p, n in zip(case["layers"], named)]
+    loss, nll, kl, logp = O.mnf_net_loss(case["x"], case["y"], layers, case["noises"], C.NUM_BATCHES)
+    loss.backward()
+    assert C.rel_err(logp, g["logp"]) < TOL
+    assert abs(nll.item() - float(g["nll"])) / float(g["nll"]) < 5e-6 and abs(kl.item() - float(g["kl"])) / float(g["kl"]) < 5e-6
+    for li, n in enumerate(named):
+        for name, v in n.items():
+            got = torch.from_numpy(C.grad_digest(v.grad)["sample"]) if v.numel() > 2000 else v.grad
+            assert C.rel_err(got, g[f"l{li}_{name}"]) < 5e-5, (li, name)
