@@ -84,7 +84,7 @@ __device__ __forceinline__ void storeq(float* __restrict__ p, int64_t e0, int64_
 // prologue: M, V and the KL partial sums, elementwise over the (out,in) parameters
 // ================================================================================================
 struct PrologueArgs {
-  const float *mu, *rho, *lam, *z;
+  const float *mu, *rho, *lam, *z, *z_kl;
   int64_t n, K;
   float *M, *V;     // V may be NULL (mean branch)
   double* kl_part;  // [gridDim.x] or NULL
@@ -110,10 +110,11 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_prologue(const PrologueArgs 
       if (e0 + j < a.n) {
         const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
         const float zk = a.z ? __ldg(a.z + (e0 + j) % a.K) : 1.0f;
+        const float zkl = a.z_kl ? __ldg(a.z_kl + (e0 + j) % a.K) : zk;
         const Moments mo = weight_moments(mu[j], sg, al, a.var_mode);
         m[j] = mo.m * zk;
         v[j] = mo.v;
-        if (a.kl_part) kl += kl_weight_elem(mu[j] * zk, sg, al, a.pri);
+        if (a.kl_part) kl += kl_weight_elem(mu[j] * zkl, sg, al, a.pri);
       }
     }
     storeq(a.M, e0, a.n, vec, m, false);
@@ -416,14 +417,14 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_bwd_w_gemm(const BwdWArgs a)
 // finalize: chain rule through M = alpha mu z, V(sigma, alpha[, mu]) + closed-form KL gradient
 // ================================================================================================
 struct FinalizeArgs {
-  const float *mu, *rho, *lam, *z, *bias_mu, *bias_rho;
+  const float *mu, *rho, *lam, *z, *z_kl, *bias_mu, *bias_rho;
   const float *dM, *dV, *colsum;
   int64_t N, K;
   int var_mode, sample, accumulate;
   const float* klg_dev;
   float klg_host;
   lbbnn_priors pri;
-  float *dmu, *drho, *dlam, *dbmu, *dbrho, *dz;
+  float *dmu, *drho, *dlam, *dbmu, *dbrho, *dz, *dz_kl;
 };
 
 __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs a) {
@@ -449,8 +450,9 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
       const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
       const int64_t k = (e0 + j) % a.K;
       const float zk = a.z ? __ldg(a.z + k) : 1.0f;
+      const float zkl = a.z_kl ? __ldg(a.z_kl + k) : zk;
       const float dMz = dM[j] * zk;
-      float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j];
+      float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j], dzkl = 0.f;
       if (a.var_mode == LBBNN_VAR_REFERENCE) {
         dsg = 2.0f * al * al * sg * dV[j];
         dal = mu[j] * dMz + 2.0f * al * sg * sg * dV[j];
@@ -460,17 +462,19 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
         dal = mu[j] * dMz + (sg * sg + (1.0f - 2.0f * al) * mu[j] * mu[j]) * dV[j];
       }
       if (klg != 0.f) {
-        const float d = mu[j] * zk - P.mu;
-        dmu += klg * al * d * inv_sp2 * zk;
+        const float d = mu[j] * zkl - P.mu;
+        dmu += klg * al * d * inv_sp2 * zkl;
         dsg += klg * al * (sg * inv_sp2 - 1.0f / sg);
         dal += klg * (logf(P.sigma / sg) - 0.5f + logf(al / P.alpha) + (sg * sg + d * d) * 0.5f * inv_sp2 -
                       logf((1.0f - al) / (1.0f - P.alpha)));
-        dzk += klg * al * d * inv_sp2 * mu[j];
+        dzkl = klg * al * d * inv_sp2 * mu[j];
       }
       gm[j] = dmu;
       gr[j] = dsg * dsigma_drho(rho[j]);
       gl[j] = dal * al * (1.0f - al);
-      if (a.dz) atomicAdd(a.dz + k, dzk);  // MNF only; caller zeroes dz first
+      // MNF only; caller zeroes dz / dz_kl first
+      if (a.dz_kl) { atomicAdd(a.dz_kl + k, dzkl); if (a.dz) atomicAdd(a.dz + k, dzk); }
+      else if (a.dz) atomicAdd(a.dz + k, dzk + dzkl);
     }
     storeq(a.dmu, e0, n, vec, gm, a.accumulate);
     storeq(a.drho, e0, n, vec, gr, a.accumulate);
@@ -703,7 +707,7 @@ int check_layer(const lbbnn_layer* L) {
 int launch_prologue(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, bool want_v, bool want_kl, float* M,
                     float* V, double* kl_part, cudaStream_t st) {
   PrologueArgs pa;
-  pa.mu = L->weight_mu; pa.rho = L->weight_rho; pa.lam = L->lambdal; pa.z = L->z;
+  pa.mu = L->weight_mu; pa.rho = L->weight_rho; pa.lam = L->lambdal; pa.z = L->z; pa.z_kl = L->z_kl;
   pa.n = L->in_features * L->out_features; pa.K = L->in_features;
   pa.M = M; pa.V = want_v ? V : nullptr; pa.kl_part = want_kl ? kl_part : nullptr;
   pa.var_mode = var_mode; pa.pri = *pri;
@@ -777,6 +781,7 @@ extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, in
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
   LBBNN_REQUIRE(!sample || ds_factor, "sample-branch backward needs the saved ds_factor");
   LBBNN_REQUIRE(G->z == nullptr || L->z != nullptr, "dz requested but the layer has no z");
+  LBBNN_REQUIRE(G->z_kl == nullptr || L->z_kl != nullptr, "dz_kl requested but the layer has no z_kl");
   const int64_t K = L->in_features, N = L->out_features;
   const WsLayout w = ws_layout(B, K, N);
   LBBNN_REQUIRE(ws && ws_bytes >= w.total, "workspace too small (%zu < %zu)", ws_bytes, w.total);
@@ -791,11 +796,11 @@ extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, in
   if (int rc = check_launch("lrt_f32_bwd_w_gemm")) return rc;
 
   FinalizeArgs f;
-  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.z_kl = L->z_kl; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
   f.dM = a.dM; f.dV = a.dV; f.colsum = a.colsum; f.N = N; f.K = K;
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
-  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z;
+  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
   lrt_f32_finalize<<<(unsigned)elementwise_blocks(N * K), kThreads, 0, st>>>(f);
   return check_launch("lrt_f32_finalize");
 }
@@ -868,11 +873,11 @@ extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, con
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
   LBBNN_REQUIRE(!sample || dV, "sample branch needs dV");
   FinalizeArgs f;
-  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.z_kl = L->z_kl; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
   f.dM = dM; f.dV = dV ? dV : dM; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
-  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z;
+  f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
   lrt_f32_finalize<<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize");
 }

@@ -4,8 +4,8 @@ CUDA only: importing this package without the built library raises."""
 from . import _capi
 from ._capi import LbbnnError, philox_normal, philox_uniform
 from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
-from . import mf
+from . import flows, mf, mnf
 from .engine import LRTTrainer, LRTTensorCoreTrainer
 
 __all__ = ["BayesianLinear", "BayesianNetwork", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "lrt_linear",
-           "manual_seed", "mf", "philox_normal", "philox_uniform"]
+           "manual_seed", "mf", "mnf", "flows", "philox_normal", "philox_uniform"]

@@ -35,17 +35,46 @@ class Priors(C.Structure):
 class Layer(C.Structure):
     _fields_ = [("weight_mu", C.c_void_p), ("weight_rho", C.c_void_p), ("lambdal", C.c_void_p),
                 ("bias_mu", C.c_void_p), ("bias_rho", C.c_void_p), ("z", C.c_void_p),
-                ("in_features", C.c_int64), ("out_features", C.c_int64)]
+                ("in_features", C.c_int64), ("out_features", C.c_int64), ("z_kl", C.c_void_p)]
 
 
 class LayerGrads(C.Structure):
     _fields_ = [("weight_mu", C.c_void_p), ("weight_rho", C.c_void_p), ("lambdal", C.c_void_p),
-                ("bias_mu", C.c_void_p), ("bias_rho", C.c_void_p), ("z", C.c_void_p)]
+                ("bias_mu", C.c_void_p), ("bias_rho", C.c_void_p), ("z", C.c_void_p), ("z_kl", C.c_void_p)]
 
 
 class Noise(C.Structure):
     _fields_ = [("eps", C.c_void_p), ("seed", C.c_uint64), ("stream_id", C.c_uint64),
                 ("step_dev", C.c_void_p), ("step_stride", C.c_uint64)]
+
+
+FLOW_MAX_T, FLOW_MAX_HIDDEN = 8, 6
+FLOW_RNVP, FLOW_IAF = 0, 1
+
+
+class FlowLinear(C.Structure):
+    _fields_ = [("W", C.c_void_p), ("b", C.c_void_p), ("in_", C.c_int), ("out", C.c_int)]
+
+
+class FlowTransform(C.Structure):
+    _fields_ = [("hidden", FlowLinear * FLOW_MAX_HIDDEN), ("shift", FlowLinear), ("scale", FlowLinear)]
+
+
+class Flow(C.Structure):
+    _fields_ = [("kind", C.c_int), ("dim", C.c_int), ("n_transforms", C.c_int), ("n_hidden", C.c_int),
+                ("t", FlowTransform * FLOW_MAX_T)]
+
+
+class FlowLinearGrad(C.Structure):
+    _fields_ = [("dW", C.c_void_p), ("db", C.c_void_p)]
+
+
+class FlowTransformGrads(C.Structure):
+    _fields_ = [("hidden", FlowLinearGrad * FLOW_MAX_HIDDEN), ("shift", FlowLinearGrad), ("scale", FlowLinearGrad)]
+
+
+class FlowGrads(C.Structure):
+    _fields_ = [("row_stride", C.c_int64), ("t", FlowTransformGrads * FLOW_MAX_T)]
 
 
 _P, _I64, _U64, _INT, _F, _SZ = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_size_t
@@ -86,6 +115,9 @@ SIGNATURES = {
     "lbbnn_mc_accumulate": (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_mf_sample_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _SZ, _P]),
+    "lbbnn_flow_save_floats": (_SZ, [C.POINTER(Flow), _I64]),
+    "lbbnn_flow_fwd": (_INT, [C.POINTER(Flow), _P, _I64, _P, C.POINTER(Noise), _P, _P, _P, _P]),
+    "lbbnn_flow_bwd": (_INT, [C.POINTER(Flow), C.POINTER(FlowGrads), _I64, _P, C.POINTER(Noise), _P, _P, _P, _P, _P]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
@@ -164,10 +196,10 @@ def lrt_mv_bytes(in_features, out_features):
     return int(lib.lbbnn_lrt_f32_mv_bytes(in_features, out_features))
 
 
-def make_layer(weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z=None):
+def make_layer(weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z=None, z_kl=None):
     out_f, in_f = weight_mu.shape
     return Layer(ptr(weight_mu), ptr(weight_rho), ptr(lambdal), ptr(bias_mu), ptr(bias_rho),
-                 ptr(z, allow_none=True), in_f, out_f)
+                 ptr(z, allow_none=True), in_f, out_f, ptr(z_kl, allow_none=True))
 
 
 def make_noise(eps=None, seed=0, stream_id=0, step_dev=None, step_stride=0):

@@ -1,0 +1,173 @@
+"""Drop-in MNF layer and network (reference LBBNN-GP-MF-MNF.py:133-260; sim-study parametrisation
+LBBNN-GP-MF-MNFsim_study.py:145-251 through the prior / init keyword arguments).
+
+What runs where: the z flows and the auxiliary r flow -> fused flow kernels (flows.py); the activation
+path mm(x*z, M^T), mm(x^2, V^T), eps/sqrt -> the fused LRT kernels with z folded into the weight prologue
+(MNF:197-198: mm(x*z, M^T) == mm(x, (M*z)^T) because z is a single (in,) vector); the KL over all weights
+with (mu*z2 - mu_p)^2 (MNF:230-233) and the W_mean/W_var moments -> prologue/finalize kernels; the two
+auxiliary GEMVs r0_c @ W^T (MNF:216-217) -> the fp32 GEMM kernels.  Only O(in)+O(out) vector glue
+(log q0, tanh, the outer-product means, log r_b) stays in torch.
+
+Reference quirks kept: one z (the last batch row's) is broadcast over the batch, so only
+that row is pushed through the flow; the KL branch draws its own z (self.z becomes (1,in)); z_b[-1] in
+log r_b is the last ELEMENT of the flowed vector; log pi (not log 2 pi) in both Gaussians.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _capi as K
+from .flows import PropagateFlow
+from .lrt import BernoulliView, GaussianView, LayerConfig, _LRTFunction, current_seed, _layer_ids
+from .mf import _Linear
+
+
+class _MomentsKL(torch.autograd.Function):
+    """(M0 = alpha mu, V = sigma^2 alpha^2, kl(weights with mu*z_kl, biases)) and their gradients."""
+
+    @staticmethod
+    def forward(ctx, wmu, wrho, lam, bmu, brho, z_kl, cfg):
+        K.require_device()
+        ps = [t.contiguous() for t in (wmu, wrho, lam, bmu, brho)]
+        zc = z_kl.contiguous()
+        layer = K.make_layer(*ps, None, zc)
+        M, V = torch.empty_like(ps[0]), torch.empty_like(ps[0])
+        kl = torch.zeros((), dtype=torch.float32, device=wmu.device)
+        ws = K.workspace(1 << 20, wmu.device)
+        K.check(K.lib.lbbnn_lrt_f32_prologue(layer, cfg.priors, cfg.var_mode, K.FLAG_SAMPLE, K.ptr(M), K.ptr(V), K.ptr(kl),
+                                             ws.data_ptr(), ws.numel(), K.current_stream()))
+        ctx.save_for_backward(*ps, zc)
+        ctx.cfg = cfg
+        return M, V, kl
+
+    @staticmethod
+    def backward(ctx, dM, dV, dkl):
+        wmu, wrho, lam, bmu, brho, z = ctx.saved_tensors
+        cfg = ctx.cfg
+        layer = K.make_layer(wmu, wrho, lam, bmu, brho, None, z)
+        dM = torch.zeros_like(wmu) if dM is None else dM.contiguous()
+        dV = torch.zeros_like(wmu) if dV is None else dV.contiguous()
+        colsum = torch.zeros(2 * wmu.shape[0], dtype=torch.float32, device=wmu.device)
+        grads = [torch.empty_like(t) for t in (wmu, wrho, lam, bmu, brho)]
+        dz = torch.zeros_like(z)
+        use_kl = dkl is not None
+        g = K.LayerGrads(*[K.ptr(t) for t in grads], None, K.ptr(dz))
+        K.check(K.lib.lbbnn_lrt_f32_finalize(layer, K.ptr(dM), K.ptr(dV), K.ptr(colsum), cfg.priors, cfg.var_mode,
+                                             K.FLAG_SAMPLE, K.ptr(dkl.contiguous().float()) if use_kl else None,
+                                             1.0 if use_kl else 0.0, g, K.current_stream()))
+        return (*grads, dz, None)
+
+
+class BayesianLinear(nn.Module):
+    """MNF layer, drop-in for LBBNN-GP-MF-MNF.py:133-239: ctor `(in_features, out_features, num_transforms)`.
+    `noise=` on forward injects the draws of SURVEY.md §3.2 (see tests/cases.py:mnf_noise)."""
+
+    def __init__(self, in_features, out_features, num_transforms=2, *, device=None, mu_prior=0.0, sigma_prior=1.0,
+                 alpha_prior=0.05, bias_mu_prior=0.0, bias_sigma_prior=1.0, mu_init=0.01, lambda_init=(0.0, 1.0),
+                 z_flow_type="RNVP", r_flow_type="RNVP", h_sizes=(75, 75, 75, 75)):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        E = torch.empty
+        self.weight_mu = nn.Parameter(E(out_features, in_features).uniform_(-mu_init, mu_init))
+        self.weight_rho = nn.Parameter(E(out_features, in_features).uniform_(-5, -4))
+        self.lambdal = nn.Parameter(E(out_features, in_features).uniform_(*lambda_init))
+        E(out_features, in_features).uniform_(0.999, 0.9999)            # the reference's alpha_q draw (MNF:149)
+        self.bias_mu = nn.Parameter(E(out_features).uniform_(-0.2, 0.2))
+        self.bias_rho = nn.Parameter(E(out_features).uniform_(-5, -4))
+        self.q0_mean = nn.Parameter(0.1 * torch.randn(in_features))
+        self.q0_log_var = nn.Parameter(-9 + 0.1 * torch.randn(in_features))
+        self.r0_c = nn.Parameter(0.1 * torch.randn(in_features))
+        self.r0_b1 = nn.Parameter(0.1 * torch.randn(in_features))
+        self.r0_b2 = nn.Parameter(0.1 * torch.randn(in_features))
+        self.z_flow = PropagateFlow(z_flow_type, in_features, num_transforms, h_sizes)
+        self.r_flow = PropagateFlow(r_flow_type, in_features, num_transforms, h_sizes)
+        self.cfg = LayerConfig(mu_prior, sigma_prior, alpha_prior, bias_mu_prior, bias_sigma_prior)
+        self.weight = GaussianView(self.weight_mu, self.weight_rho)
+        self.bias = GaussianView(self.bias_mu, self.bias_rho)
+        self.gamma = BernoulliView(self)
+        self.kl = 0
+        self.z = 0
+        self._uid = next(_layer_ids)
+        self._calls = 0
+        self.last_noise_key = None
+        if device is not None:
+            self.to(device)
+
+    @property
+    def alpha_q(self):
+        return 1 / (1 + torch.exp(-self.lambdal.detach()))
+
+    def _z0(self, eps):
+        return self.q0_mean + self.q0_log_var.exp().sqrt() * eps       # MNF:183-185
+
+    def forward(self, input, sample=False, calculate_log_probs=False, noise=None):
+        nz = noise or {}
+        dev = self.weight_mu.device
+        sample_branch = self.training or sample
+        want_kl = self.training or calculate_log_probs
+        D = self.in_features
+        inj = "eps_z" in nz
+        # every z-flow evaluation of this call as rows of ONE launch: [activation row (last batch row), KL row]
+        eps_rows = [nz["eps_z"][-1:] if inj else torch.randn(1, D, device=dev)]
+        mask_rows = [[m[-1:] for m in nz["z_masks"]]] if inj else None
+        if want_kl:
+            eps_rows.append(nz["eps_z2"] if inj else torch.randn(1, D, device=dev))
+            if inj:
+                mask_rows.append(list(nz["z_masks2"]))
+        z0 = self._z0(torch.cat(eps_rows, 0))
+        masks = [torch.cat([r[t] for r in mask_rows], 0) for t in range(len(mask_rows[0]))] if inj else None
+        zs, logdets = self.z_flow(z0, masks)
+        z_k = zs[0]
+        self._calls += 1
+        self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
+        act, _ = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z_k,
+                                    nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key)
+        if not want_kl:
+            self.kl = 0
+            return act
+        self.z = z0[1:2]                                                # sample_z() overwrites self.z with (1,in)
+        z2 = zs[1]
+        log_det_q = logdets if logdets.dim() == 0 else logdets[1]       # IAF kind: one scalar over everything
+        M0, V, kl_wb = _MomentsKL.apply(self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z2, self.cfg)
+        log_q0 = (-0.5 * math.log(math.pi) - 0.5 * self.q0_log_var
+                  - 0.5 * ((self.z - self.q0_mean) ** 2 / self.q0_log_var.exp())).sum()
+        log_q = -log_det_q + log_q0
+        zero_b = torch.zeros(self.out_features, device=dev)
+        act_mu = _Linear.apply((self.r0_c * z2)[None], M0, zero_b)[0]    # r0_c @ W_mean^T, W_mean = z2 mu alpha (MNF:211,216)
+        act_var = _Linear.apply((self.r0_c ** 2)[None], V, zero_b)[0]    # MNF:217
+        eps_r = nz["eps_r"] if "eps_r" in nz else torch.randn(self.out_features, device=dev)
+        a_r = torch.tanh(act_mu + act_var.sqrt() * eps_r)
+        mean_r = self.r0_b1 * a_r.mean()                                 # outer(b1, act).mean(-1)  (MNF:220)
+        log_var_r = self.r0_b2 * a_r.mean()
+        z_b, log_det_r = self.r_flow(z2, nz.get("r_masks"))
+        log_rb = (-0.5 * math.log(math.pi) - 0.5 * log_var_r - 0.5 * ((z_b[-1] - mean_r) ** 2 / log_var_r.exp())).sum()
+        self.kl = kl_wb + log_q - (log_det_r + log_rb)
+        return act
+
+
+class BayesianNetwork(nn.Module):
+    """784-400-600-10 MNF network, drop-in for LBBNN-GP-MF-MNF.py:244-260."""
+
+    def __init__(self, sizes=(28 * 28, 400, 600, 10), num_transforms=2, **layer_kwargs):
+        super().__init__()
+        self.sizes = tuple(sizes)
+        for n, (i, o) in enumerate(zip(sizes[:-1], sizes[1:]), 1):
+            setattr(self, f"l{n}", BayesianLinear(i, o, num_transforms=num_transforms, **layer_kwargs))
+        self._names = [f"l{n}" for n in range(1, len(sizes))]
+
+    @property
+    def layers(self):
+        return [getattr(self, n) for n in self._names]
+
+    def forward(self, x, sample=False, noises=None):
+        x = x.view(-1, self.sizes[0])
+        ls = self.layers
+        for i, l in enumerate(ls):
+            x = l.forward(x, sample, noise=None if noises is None else noises[i])
+            x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
+        return x
+
+    def kl(self):
+        return sum(l.kl for l in self.layers)

@@ -64,6 +64,7 @@ typedef struct lbbnn_layer {
   const float* bias_rho;
   const float* z;
   int64_t in_features, out_features;
+  const float* z_kl; /* MNF: the z of the KL branch (MNF:210,230-233), a different draw than `z`; NULL = use z */
 } lbbnn_layer;
 
 typedef struct lbbnn_layer_grads {
@@ -72,7 +73,8 @@ typedef struct lbbnn_layer_grads {
   float* lambdal;
   float* bias_mu;
   float* bias_rho;
-  float* z; /* (in,) or NULL */
+  float* z;    /* (in,) or NULL; accumulated with atomics, caller zeroes it */
+  float* z_kl; /* (in,) or NULL; likewise */
 } lbbnn_layer_grads;
 
 /* Noise source of one call.  eps != NULL: injected tensor, indexed like the output it perturbs
@@ -229,6 +231,44 @@ LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float
                                   const float* dw, const float* dsums,
                                   float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
                                   void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+/* ---- normalizing flows of flows2.py: PropagateFlow (flows2:14-46) over RNVP (flows2:188-219) or the
+ * IAF-style MNF transform (flows2:225-241), as fused small-MLP kernels (one CTA per row of z runs the
+ * whole stack; see csrc/flows.cu).  Weights are nn.Linear layout (out,in).
+ *   fwd:  z_out (rows,dim), logdet (rows,) [for the IAF kind the reference sums it over rows too, flows2:241:
+ *         the caller adds the rows up]; masks: injected {0,1} floats (n_transforms, rows, dim) or NULL for
+ *         native [u < 0.5] from Philox(seed, stream_id + transform); save: lbbnn_flow_save_floats floats
+ *         kept for the backward (NULL = inference only).
+ *   bwd:  dz_in (rows,dim) and the parameter gradients of EACH row into its own slice: every pointer in
+ *         lbbnn_flow_grads addresses row 0, row r lives row_stride floats further (sum the rows afterwards). */
+#define LBBNN_FLOW_MAX_T 8
+#define LBBNN_FLOW_MAX_HIDDEN 6
+enum { LBBNN_FLOW_RNVP = 0, LBBNN_FLOW_IAF = 1 };
+typedef struct lbbnn_flow_linear { const float* W; const float* b; int in, out; } lbbnn_flow_linear;
+typedef struct lbbnn_flow_transform {
+  lbbnn_flow_linear hidden[LBBNN_FLOW_MAX_HIDDEN]; /* RNVP: network.{0,2,..}; IAF: f */
+  lbbnn_flow_linear shift;                          /* RNVP: t; IAF: g */
+  lbbnn_flow_linear scale;                          /* RNVP: s; IAF: k */
+} lbbnn_flow_transform;
+typedef struct lbbnn_flow {
+  int kind, dim, n_transforms, n_hidden;
+  lbbnn_flow_transform t[LBBNN_FLOW_MAX_T];
+} lbbnn_flow;
+typedef struct lbbnn_flow_linear_grad { float* dW; float* db; } lbbnn_flow_linear_grad;
+typedef struct lbbnn_flow_transform_grads {
+  lbbnn_flow_linear_grad hidden[LBBNN_FLOW_MAX_HIDDEN];
+  lbbnn_flow_linear_grad shift, scale;
+} lbbnn_flow_transform_grads;
+typedef struct lbbnn_flow_grads {
+  int64_t row_stride;
+  lbbnn_flow_transform_grads t[LBBNN_FLOW_MAX_T];
+} lbbnn_flow_grads;
+LBBNN_API size_t lbbnn_flow_save_floats(const lbbnn_flow* flow, int64_t rows);
+LBBNN_API int lbbnn_flow_fwd(const lbbnn_flow* flow, const float* z_in, int64_t rows, const float* masks,
+                             const lbbnn_noise* mask_u, float* z_out, float* logdet, float* save, lbbnn_stream s);
+LBBNN_API int lbbnn_flow_bwd(const lbbnn_flow* flow, const lbbnn_flow_grads* grads, int64_t rows, const float* masks,
+                             const lbbnn_noise* mask_u, const float* dz_out, const float* dlogdet, const float* save,
+                             float* dz_in, lbbnn_stream s);
 
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
  * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.

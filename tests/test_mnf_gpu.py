@@ -1,0 +1,201 @@
+"""GPU parity tests of the MNF path: the fused flow kernels (flows2.py RNVP / IAF-style 'MNF' transform) and the MNF
+layer / network (LBBNN-GP-MF-MNF.py:133-260) vs the oracle and the reference's golden outputs, all noise injected.
+fp32 tolerance 1e-5 (max|a-b|/max|b|) on activations / flow outputs, 5e-5 on gradients that pass through the deep
+coupling stacks (same bound the oracle itself meets against the reference, tests/test_oracle_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import lbbnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+GTOL = 5e-5
+
+
+@pytest.fixture(scope="module")
+def lb():
+    import lbbnn
+    return lbbnn
+
+
+def _load_flow(flow, named, prefix):
+    sd = {k[len(prefix):]: v for k, v in named.items() if k.startswith(prefix)}
+    flow.load_state_dict(sd)
+    return flow
+
+
+def _flow_grads(flow, prefix):
+    return {prefix + k: v.grad for k, v in flow.named_parameters()}
+
+
+@pytest.mark.parametrize("kind", ["RNVP", "MNF"])
+def test_flow_kernels_match_reference_golden(lb, kind):
+    g = np.load(os.path.join(C.GOLDEN, "flows.npz"))
+    rng = np.random.default_rng(0)
+    tmpl = O.init_flow_params(rng, 24, 2, (75, 75, 75, 75), kind)
+    named = {k: torch.from_numpy(g[f"{kind}_p_{k}"]) for k in C.flat_named({"z_flow": tmpl})}
+    flow = _load_flow(lb.flows.PropagateFlow(kind, 24, 2), named, "z_flow.").cuda()
+    for tag in ("b", "v"):
+        z = torch.from_numpy(g[f"{kind}_{tag}_z"]).cuda().requires_grad_(True)
+        masks = [torch.from_numpy(m).cuda() for m in g[f"{kind}_{tag}_masks"]]
+        zo, ld = flow(z, masks)
+        assert zo.shape == z.shape and tuple(ld.shape) == tuple(g[f"{kind}_{tag}_logdet"].shape)
+        ((zo * zo).sum() + ld.sum()).backward()
+        assert C.rel_err(zo.detach(), g[f"{kind}_{tag}_out"]) < TOL
+        assert C.rel_err(ld.detach(), g[f"{kind}_{tag}_logdet"]) < TOL
+        assert C.rel_err(z.grad, g[f"{kind}_{tag}_dz"]) < TOL
+
+
+@pytest.mark.parametrize("kind,dim,rows,h_sizes", [("RNVP", 784, 3, (75, 75, 75, 75)), ("RNVP", 20, 1, (50,) * 5),
+                                                    ("RNVP", 400, 2, (75, 75, 75, 75)), ("MNF", 600, 2, None),
+                                                    ("RNVP", 37, 7, (33, 128))])
+def test_flow_kernels_all_gradients_match_oracle(lb, kind, dim, rows, h_sizes):
+    rng = np.random.default_rng(dim + rows)
+    tmpl = O.init_flow_params(rng, dim, 2, h_sizes or (75,) * 4, kind)
+    named = C.flat_named({"z_flow": tmpl})
+    z0 = C.t(rng.standard_normal(size=(rows, dim)))
+    masks = C._masks(rng, 2, rows, dim)
+    gz = C.t(rng.standard_normal(size=(rows, dim)))
+    gl = C.t(rng.standard_normal(size=(rows,)))
+    # fp64 truth and fp32 oracle
+    outs = {}
+    for dt in (torch.float64, torch.float32):
+        nm = {k: v.to(dt).clone().requires_grad_(True) for k, v in named.items()}
+        tps = C.unflatten_like({"z_flow": tmpl}, nm)["z_flow"]
+        z = z0.to(dt).clone().requires_grad_(True)
+        zo, ld = O.propagate_flow(z, [m.to(dt) for m in masks], tps, kind)
+        ldv = ld if ld.dim() else ld.expand(rows) / rows       # IAF kind: one scalar over everything
+        ((zo * gz.to(dt)).sum() + (ldv * gl.to(dt)).sum()).backward()
+        outs[dt] = (zo.detach(), ld.detach(), z.grad, {k: v.grad for k, v in nm.items()})
+    kw = dict(h_sizes=h_sizes) if kind == "RNVP" else {}
+    flow = _load_flow(lb.flows.PropagateFlow(kind, dim, 2, **kw), named, "z_flow.").cuda()
+    z = z0.cuda().requires_grad_(True)
+    zo, ld = flow(z, [m.cuda() for m in masks])
+    ldv = ld if ld.dim() else ld.expand(rows) / rows
+    ((zo * gz.cuda()).sum() + (ldv * gl.cuda()).sum()).backward()
+    t64, t32 = outs[torch.float64], outs[torch.float32]
+    assert C.rel_err(zo.detach(), t64[0]) < TOL and C.rel_err(ld.detach(), t64[1]) < TOL
+    assert C.rel_err(z.grad, t64[2]) < GTOL
+    got = _flow_grads(flow, "z_flow.")
+    for k, ref in t64[3].items():
+        # not worse than a few times the fp32 oracle's own distance from the fp64 truth
+        bound = max(GTOL, 4 * C.rel_err(t32[3][k], ref))
+        assert C.rel_err(got[k], ref) < bound, k
+
+
+def test_flow_native_masks_reproducible_from_philox(lb):
+    """Masks drawn inside the kernel equal [u < 0.5] of the exported Philox uniforms (bit-exact inclusion masks):
+    the oracle fed with the exported masks reproduces the native forward."""
+    rng = np.random.default_rng(5)
+    dim, rows = 400, 4
+    tmpl = O.init_flow_params(rng, dim, 2)
+    named = C.flat_named({"z_flow": tmpl})
+    lb.manual_seed(77)
+    flow = _load_flow(lb.flows.PropagateFlow("RNVP", dim, 2), named, "z_flow.").cuda()
+    z = C.t(rng.standard_normal(size=(rows, dim)))
+    with torch.no_grad():
+        zo, ld = flow(z.cuda())
+        zo2, _ = flow(z.cuda())
+    seed, stream = flow.last_noise_key
+    assert not torch.equal(zo, zo2), "every call must draw fresh masks"
+    masks = [(lb.philox_uniform(rows * dim, seed, stream + t, device="cuda") < 0.5).float().view(rows, dim) for t in range(2)]
+    frac = torch.stack(masks).mean().item()
+    assert 0.45 < frac < 0.55
+    zo_inj, ld_inj = flow(z.cuda(), masks)     # injected path with the exported masks: bit-identical
+    assert torch.equal(zo_inj.detach(), zo2) and ld_inj.shape == ld.shape
+    ref, ref_ld = O.propagate_flow(z, [m.cpu() for m in masks], tmpl, "RNVP")
+    assert C.rel_err(zo2, ref) < TOL
+
+
+def _make_mnf_layer(lb, case, i, o, h_sizes, priors=None):
+    kw = {}
+    if priors is not None:
+        kw = dict(mu_prior=priors.mu, sigma_prior=priors.sigma, alpha_prior=priors.alpha, bias_mu_prior=priors.bias_mu,
+                  bias_sigma_prior=priors.bias_sigma)
+    layer = lb.mnf.BayesianLinear(i, o, 2, h_sizes=h_sizes, **kw)
+    named = C.flat_named(case["p"] if "p" in case else case)
+    layer.load_state_dict(named)
+    return layer.cuda()
+
+
+def _cuda_noise(nz):
+    return {k: ([m.cuda() for m in v] if isinstance(v, list) else v.cuda()) for k, v in nz.items()}
+
+
+@pytest.mark.parametrize("key", ["ma", "mb", "sa"])
+def test_mnf_layer_matches_oracle_and_reference(lb, key):
+    g = np.load(os.path.join(C.GOLDEN, "mnf_layer.npz"))
+    seed, b, i, o, nh, hw = (int(v) for v in g[f"{key}_meta"])
+    case = C.mnf_layer_case(seed, b, i, o, h_sizes=(hw,) * nh)
+    pri = O.Priors(0.1, 1.3, 0.3, 0.0, 1.3) if key == "sa" else O.Priors()        # MNFsim:157-174
+    # fp64 truth
+    named64 = {k: v.double().clone().requires_grad_(True) for k, v in C.flat_named(case["p"]).items()}
+    p64 = C.unflatten_like(case["p"], named64)
+    x64 = case["x"].double().clone().requires_grad_(True)
+    nz64 = {k: ([m.double() for m in v] if isinstance(v, list) else v.double()) for k, v in case["noise"].items()}
+    act64, kl64 = O.mnf_forward(x64, p64, nz64, priors=pri)
+    ((act64 * case["gout"].double()).sum() + kl64 / C.NUM_BATCHES).backward()
+
+    layer = _make_mnf_layer(lb, case, i, o, (hw,) * nh, pri)
+    layer.train()
+    x = case["x"].cuda().requires_grad_(True)
+    act = layer(x, noise=_cuda_noise(case["noise"]))
+    ((act * case["gout"].cuda()).sum() + layer.kl / C.NUM_BATCHES).backward()
+    # vs the reference's own outputs
+    assert C.rel_err(act.detach(), g[f"{key}_act"]) < TOL
+    assert abs(layer.kl.item() - float(g[f"{key}_kl"])) / abs(float(g[f"{key}_kl"])) < TOL
+    assert C.rel_err(layer.z.detach(), g[f"{key}_z"]) < TOL
+    assert C.rel_err(x.grad, g[f"{key}_dx"]) < TOL
+    # vs the fp64 oracle, every parameter
+    assert C.rel_err(act.detach(), act64.detach()) < TOL
+    got = dict(layer.named_parameters())
+    assert set(got) == set(named64)
+    for name, v in named64.items():
+        assert got[name].grad is not None, name
+        assert C.rel_err(got[name].grad, v.grad) < GTOL, name
+        ref = g[f"{key}_d_{name}"]
+        mine = got[name].grad if v.numel() <= 4000 else torch.from_numpy(C.grad_digest(got[name].grad.cpu())["sample"])
+        assert C.rel_err(mine, ref) < GTOL, name
+
+
+def test_mnf_layer_eval_branches(lb):
+    """eval: posterior-mean branch is still stochastic in z (MNF:202-206), .kl == 0 unless calculate_log_probs."""
+    case = C.mnf_layer_case(71, 9, 50, 13)
+    layer = _make_mnf_layer(lb, case, 50, 13, (75,) * 4)
+    layer.eval()
+    nz = _cuda_noise(case["noise"])
+    with torch.no_grad():
+        act = layer(case["x"].cuda(), noise=nz)
+        assert layer.kl == 0
+        ref, _ = O.mnf_forward(case["x"], case["p"], case["noise"], sample=False, calc_kl=False)
+        assert C.rel_err(act, ref) < TOL
+        act_s = layer(case["x"].cuda(), sample=True, calculate_log_probs=True, noise=nz)
+        ref_s, ref_kl = O.mnf_forward(case["x"], case["p"], case["noise"], sample=True, calc_kl=True)
+        assert C.rel_err(act_s, ref_s) < TOL and abs(layer.kl.item() - ref_kl.item()) / abs(ref_kl.item()) < TOL
+        # native noise: runs, finite, differs call to call
+        a1, a2 = layer(case["x"].cuda(), sample=True), layer(case["x"].cuda(), sample=True)
+        assert torch.isfinite(a1).all() and not torch.equal(a1, a2)
+
+
+def test_mnf_mnist_net_matches_reference(lb):
+    g = np.load(os.path.join(C.GOLDEN, "mnf_net_mnist.npz"))
+    case = C.mnf_net_case(seed=90, batch=100)
+    net = lb.mnf.BayesianNetwork()
+    for l, p in zip(net.layers, case["layers"]):
+        l.load_state_dict(C.flat_named(p))
+    net = net.cuda().train()
+    logp = net(case["x"].cuda(), sample=True, noises=[_cuda_noise(n) for n in case["noises"]])
+    nll = torch.nn.functional.nll_loss(logp, case["y"].cuda(), reduction="sum")
+    kl = net.kl()
+    (nll + kl / C.NUM_BATCHES).backward()
+    assert C.rel_err(logp.detach(), g["logp"]) < TOL
+    assert torch.equal(logp.argmax(1).cpu(), torch.from_numpy(g["logp"]).argmax(1))
+    assert abs(nll.item() - float(g["nll"])) / float(g["nll"]) < TOL and abs(kl.item() - float(g["kl"])) / float(g["kl"]) < TOL
+    for li, l in enumerate(net.layers):
+        for name, v in l.named_parameters():
+            got = torch.from_numpy(C.grad_digest(v.grad.cpu())["sample"]) if v.numel() > 2000 else v.grad
+            assert C.rel_err(got, g[f"l{li}_{name}"]) < GTOL, (li, name)
