@@ -77,6 +77,23 @@ class FlowGrads(C.Structure):
     _fields_ = [("row_stride", C.c_int64), ("t", FlowTransformGrads * FLOW_MAX_T)]
 
 
+STEP_MAX_LAYERS = 8
+
+
+class StepLayer(C.Structure):
+    _fields_ = [("in_features", C.c_int64), ("out_features", C.c_int64), ("off_weight_mu", C.c_int64),
+                ("off_weight_rho", C.c_int64), ("off_lambdal", C.c_int64), ("off_bias_mu", C.c_int64),
+                ("off_bias_rho", C.c_int64), ("eps", C.c_void_p), ("priors", Priors), ("var_mode", C.c_int)]
+
+
+class Step(C.Structure):
+    _fields_ = [("n_layers", C.c_int), ("batch", C.c_int64), ("layer", StepLayer * STEP_MAX_LAYERS),
+                ("flat", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("grad", C.c_void_p),
+                ("x", C.c_void_p), ("y", C.c_void_p), ("step_dev", C.c_void_p), ("seed", C.c_uint64),
+                ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
+                ("kl_scale", C.c_float), ("stats", C.c_void_p)]
+
+
 _P, _I64, _U64, _INT, _F, _SZ = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_size_t
 
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is bound
@@ -118,6 +135,11 @@ SIGNATURES = {
     "lbbnn_flow_save_floats": (_SZ, [C.POINTER(Flow), _I64]),
     "lbbnn_flow_fwd": (_INT, [C.POINTER(Flow), _P, _I64, _P, C.POINTER(Noise), _P, _P, _P, _P]),
     "lbbnn_flow_bwd": (_INT, [C.POINTER(Flow), C.POINTER(FlowGrads), _I64, _P, C.POINTER(Noise), _P, _P, _P, _P, _P]),
+    "lbbnn_lrt_step_workspace_bytes": (_SZ, [C.POINTER(Step)]),
+    "lbbnn_lrt_step_raw_floats": (_SZ, [C.POINTER(Step)]),
+    "lbbnn_lrt_step_f32": (_INT, [C.POINTER(Step), _INT, _P, _SZ, _P]),
+    "lbbnn_lrt_step_profile": (_INT, [_P]),
+    "lbbnn_lrt_step_describe": (_INT, [C.POINTER(Step), C.c_char_p, _SZ]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),

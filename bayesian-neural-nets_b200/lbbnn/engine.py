@@ -8,6 +8,8 @@ sequence is captured once and replayed.  Parameters, gradients and Adam state li
 (one Adam launch); the nn.Parameters of the network are re-pointed at views of the flat buffer, so the
 module keeps working (state_dict, eager forward) while the trainer owns the storage.
 """
+from ctypes import create_string_buffer as C_create_string_buffer
+
 import torch
 
 from . import _capi as K
@@ -22,7 +24,11 @@ def _pad4(n):
 
 class LRTTrainer:
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
-                 use_graph=True, inject_noise=False, process_group=None):
+                 use_graph=True, inject_noise=False, process_group=None, fused=None, materialize_grads=True):
+        """fused: run the step as the single persistent kernel of csrc/lrt_step.cu (None = whenever it applies:
+        batch <= 128, <= 8 layers); False = one launch sequence per layer (csrc/lrt_f32.cu).
+        materialize_grads: also write the parameter gradients to `.grad` (the fused kernel otherwise consumes
+        them in registers inside the Adam update)."""
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
@@ -37,6 +43,11 @@ class LRTTrainer:
         if dev.type != "cuda":
             raise K.LbbnnError("LRTTrainer needs the network on a CUDA device (no CPU fallback)")
         self.device = dev
+        can_fuse = self.B <= 128 and len(self.layers) <= K.STEP_MAX_LAYERS
+        if fused and not can_fuse:
+            raise K.LbbnnError("the fused step kernel needs batch <= 128 and <= 8 layers")
+        self.fused = can_fuse if fused is None else bool(fused)
+        self.materialize_grads = bool(materialize_grads)
 
         # ---- flat parameter / gradient / Adam-state storage ------------------------------------
         offs, total = [], 0
@@ -59,12 +70,16 @@ class LRTTrainer:
                 view.copy_(p.data)
                 p.data = view
                 p.grad = self.gflat[off:off + n].view(shape)
+        self._offsets = {(id(l), name): off for l, name, off, n, shape in offs}
 
         # ---- static activations / scratch --------------------------------------------------------
         sizes = [(l.in_features, l.out_features) for l in self.layers]
         f32 = dict(dtype=torch.float32, device=dev)
         self.x = torch.zeros(self.B, sizes[0][0], **f32)
         self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        if self.fused:
+            self._init_fused(sizes, inject_noise, use_graph)
+            return
         self.acts = [torch.zeros(self.B, o, **f32) for _, o in sizes]
         self.dsf = [torch.zeros(self.B, o, **f32) for _, o in sizes]     # eps/(2 sqrt(var_b)) per layer
         self.mv = [None] + [torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) for i, o in sizes[1:]]  # M,V kept for dX
@@ -81,6 +96,53 @@ class LRTTrainer:
         if use_graph:
             self._capture()
 
+    # ---- fused single-kernel step (csrc/lrt_step.cu) ------------------------------------------------
+    def _init_fused(self, sizes, inject_noise, use_graph):
+        dev, f32 = self.device, dict(dtype=torch.float32, device=self.device)
+        self.eps_in = [torch.zeros(self.B, o, **f32) for _, o in sizes] if inject_noise else None
+        self.stats = torch.zeros(1 + len(sizes), **f32)
+        st = K.Step()
+        st.n_layers, st.batch = len(self.layers), self.B
+        for i, l in enumerate(self.layers):
+            sl = st.layer[i]
+            sl.in_features, sl.out_features = l.in_features, l.out_features
+            sl.off_weight_mu, sl.off_weight_rho, sl.off_lambdal, sl.off_bias_mu, sl.off_bias_rho = (
+                self._offsets[(id(l), n)] for n in _PARAM_NAMES)
+            sl.eps = K.ptr(self.eps_in[i]) if inject_noise else None
+            sl.priors, sl.var_mode = l.cfg.priors, l.cfg.var_mode
+        st.flat, st.exp_avg, st.exp_avg_sq = K.ptr(self.flat), K.ptr(self.exp_avg), K.ptr(self.exp_avg_sq)
+        st.grad = K.ptr(self.gflat) if self.materialize_grads else None
+        st.x, st.y, st.step_dev = K.ptr(self.x), K.ptr(self.y, torch.int64), K.ptr(self.step_dev, torch.int64)
+        st.seed = (self.seed + 0x9E3779B97F4A7C15 * self.rank) & (2 ** 64 - 1)
+        st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
+        st.kl_scale = 1.0 / (self.num_batches * self.world)     # KL is replicated on every rank: its grad is added once
+        st.stats = K.ptr(self.stats)
+        self._step_desc = st
+        nbytes = int(K.lib.lbbnn_lrt_step_workspace_bytes(st))
+        if nbytes == 0:
+            raise K.LbbnnError("fused step: " + K.lib.lbbnn_last_error().decode())
+        self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)     # zero-filled once (barrier ticket lives in it)
+        self.raw = self.ws[:4 * int(K.lib.lbbnn_lrt_step_raw_floats(st))].view(torch.float32)
+        buf = C_create_string_buffer(2048)
+        K.check(K.lib.lbbnn_lrt_step_describe(st, buf, 2048))
+        self.schedule = buf.value.decode()
+        self.x_host = torch.zeros(self.B, sizes[0][0], dtype=torch.float32).pin_memory()
+        self.y_host = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        self.stats_host = torch.zeros(1 + len(sizes), dtype=torch.float32).pin_memory()
+        self.kernels_per_step = 1 if self.pg is None else 2
+        self.graph = None
+        if use_graph:
+            self._capture()
+
+    def _enqueue_fused(self):
+        st, ws = K.current_stream(), self.ws
+        if self.pg is None:
+            K.check(K.lib.lbbnn_lrt_step_f32(self._step_desc, 3, ws.data_ptr(), ws.numel(), st))
+        else:   # data parallel: sum-reduce the raw (dM, dV, bias column sums), then chain rule + KL + Adam
+            K.check(K.lib.lbbnn_lrt_step_f32(self._step_desc, 1, ws.data_ptr(), ws.numel(), st))
+            torch.distributed.all_reduce(self.raw, group=self.pg)
+            K.check(K.lib.lbbnn_lrt_step_f32(self._step_desc, 2, ws.data_ptr(), ws.numel(), st))
+
     # ---- the launch sequence ------------------------------------------------------------------------
     def _noise(self, i):
         if self.eps_in is not None:
@@ -89,6 +151,8 @@ class LRTTrainer:
         return K.make_noise(None, self.seed + 0x9E3779B97F4A7C15 * self.rank, i, self.step_dev, len(self.layers))
 
     def _enqueue(self):
+        if self.fused:
+            return self._enqueue_fused()
         st = K.current_stream()
         L = len(self.layers)
         n_launch = 0

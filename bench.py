@@ -230,6 +230,54 @@ def profile_calls(tr, reps=20):
     return out
 
 
+def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20):
+    """Roofline of the persistent step kernel (the only kernel of the step).  Algorithmic bytes: per
+    weight 12 B forward read of (mu,rho,lambda) + 12 B re-read in the backward + 12 B of gradient + Adam's 28 B x 3
+    tensors (read p,g,m,v, write p,m,v), plus the activations each phase exchanges.  Duration: (a) the average launch
+    inside the timed region (= ms_per_step: one launch per step; the input copies are included, so it is an upper
+    bound), (b) the same launch alone after a 256 MB L2 flush (cold: the 27 MB of state come from HBM)."""
+    from lbbnn import _capi as K  # noqa: F401
+    pairs = list(zip(sizes[:-1], sizes[1:]))
+    nparam = sum(3 * i * o + 2 * o for i, o in pairs)
+    path = sum(36 * i * o + (4 * B * i + 8 * B * o) * 2 + (8 * B * (i + o) if li else 0) for li, (i, o) in enumerate(pairs))
+    nbytes = path + 28 * nparam
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device)
+    cold = []
+    for _ in range(reps + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.step_device()
+        e1.record()
+        e1.synchronize()
+        cold.append(e0.elapsed_time(e1) * 1e3)
+    us_cold = statistics.mean(cold[2:])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        tr.step_device()
+    e1.record()
+    e1.synchronize()
+    us_warm = e0.elapsed_time(e1) * 1e3 / 200
+    ach = nbytes / (us_per_step * 1e-6) / 1e9
+    roof = {"bound": "hbm", "kernel": "lrt_step_kernel (persistent: fwd + loss + bwd + KL + Adam of the whole stack)",
+            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+            "peak_source": peaks["source"], "us_per_launch": us_per_step, "bytes_per_launch": nbytes,
+            "us_per_launch_back_to_back": us_warm, "us_per_launch_cold_l2": us_cold,
+            "timing": "average launch over the timed region (CUDA events, one launch per step, inputs rotate through a "
+                      "pool > L2); back_to_back = 200 replays on resident inputs; cold = alone after a 256 MB L2 flush",
+            "note": "the 27 MB of parameters + Adam state are L2-resident between steps; the kernel is bound by phase "
+                    "latency (grid barriers + fp32 FFMA tiles), not by HBM"}
+    flops = sum(4.0 * B * i * o * (3 if li else 2) for li, (i, o) in enumerate(pairs))
+    step_roof = {"bytes_per_step": nbytes, "hbm_floor_us": nbytes / peaks["hbm_gbs"] / 1e3,
+                 "frac_of_hbm_floor": (nbytes / peaks["hbm_gbs"] / 1e3) / us_per_step,
+                 "flops_per_step": flops, "fp32_tflops": flops / (us_per_step * 1e-6) / 1e12,
+                 "schedule": tr.schedule}
+    kern = [{"name": "lrt_step_kernel", "us": round(us_per_step, 2), "us_back_to_back": round(us_warm, 2),
+             "us_cold_l2": round(us_cold, 2), "bytes": nbytes, "gbps": round(ach, 1)}]
+    return roof, step_roof, kern
+
+
 def profile_calls_wide(tr, reps=5):
     """Tensor-core GEMM calls of one wide step timed on their own (CUDA events, operands > L2): FLOPs are the
     ALGORITHMIC 2 GEMMs x 2 B in out per call."""
@@ -299,8 +347,11 @@ def run_ours(args):
     lbbnn.manual_seed(1234)
     net = lbbnn.BayesianNetwork(sizes).to(dev)
     _mark("process group up, building trainer")
-    Trainer = lbbnn.LRTTensorCoreTrainer if wide else lbbnn.LRTTrainer
-    tr = Trainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+    if wide:
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+    else:   # the fused persistent step kernel unless --unfused; gradients stay in registers (no .grad written)
+        tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
+                              fused=not args.unfused, materialize_grads=args.unfused)
     _mark("trainer captured")
 
     pool_x_host, pool_y_host = make_pool(POOL, B, sizes[0], sizes[-1], seed=1000 + rank)
@@ -369,6 +420,8 @@ def run_ours(args):
             step_roof = {"flops_per_step": step_flops, "achieved_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12,
                          "frac_of_sustained_peak": step_flops / (ms / args.steps * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
             kern = [{"name": r["name"], "us": round(r["us"], 1), "tflops": round(r["flops"] / r["us"] / 1e6, 1)} for r in prof]
+        elif tr.fused:
+            roof, step_roof, kern = profile_fused(tr, sizes, B, ms / args.steps * 1e3, peaks)
         else:
             prof = profile_calls(tr)
             top = max(prof, key=lambda r: r["us"])
@@ -598,6 +651,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--unfused", action="store_true", help="lrt_mnist: per-layer launch sequence instead of the step kernel")
     ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict"])
     args = ap.parse_args()
     if args.workload == "mf_mc_predict":

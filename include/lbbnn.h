@@ -270,6 +270,52 @@ LBBNN_API int lbbnn_flow_bwd(const lbbnn_flow* flow, const lbbnn_flow_grads* gra
                              const lbbnn_noise* mask_u, const float* dz_out, const float* dlogdet, const float* save,
                              float* dz_in, lbbnn_stream s);
 
+/* ---- whole LRT training step as ONE persistent cooperative kernel (small stacks, batch <= 128) --------
+ * Replaces the body of `train` for one minibatch (LRT:217-229): forward of every layer (LRT:166-211),
+ * nll_loss(sum) + kl/NUM_BATCHES (LRT:223-224), backward, optim.Adam step (LRT:358); see csrc/lrt_step.cu.
+ * Parameters, Adam state and (optionally) gradients are flat fp32 buffers; each layer names its five tensors
+ * by float offsets (weight tensors at multiples of 4).  Noise of layer i: injected `eps` (batch,out) or
+ * Philox(seed, stream = i + step * n_layers) with step = *step_dev before the call -- the same streams the
+ * per-layer entry points draw.  stats = [nll, kl_1 .. kl_L] (KL at the pre-update parameters, like LRT:213).
+ * phases: 1 = forward + loss + backward, leaving the raw (dM, dV, bias column sums) of all layers in the first
+ *             lbbnn_lrt_step_raw_floats() floats of the workspace (the buffer a data-parallel run all-reduces);
+ *         2 = chain rule + KL gradient (scaled by kl_scale = dL/dKL) + Adam on those raw gradients, writes
+ *             stats, increments *step_dev;   3 = both in one launch.
+ * The workspace must be zero-filled once before its first use and is otherwise opaque. */
+#define LBBNN_STEP_MAX_LAYERS 8
+typedef struct lbbnn_step_layer {
+  int64_t in_features, out_features;
+  int64_t off_weight_mu, off_weight_rho, off_lambdal, off_bias_mu, off_bias_rho;
+  const float* eps;
+  lbbnn_priors priors;
+  int var_mode;
+} lbbnn_step_layer;
+typedef struct lbbnn_step {
+  int n_layers;
+  int64_t batch;
+  lbbnn_step_layer layer[LBBNN_STEP_MAX_LAYERS];
+  float* flat;        /* parameters */
+  float* exp_avg;     /* Adam state, same layout */
+  float* exp_avg_sq;
+  float* grad;        /* same layout, or NULL: gradients are consumed in registers and never written */
+  const float* x;     /* (batch, in_features of layer 0) */
+  const int64_t* y;   /* (batch,) class indices */
+  int64_t* step_dev;
+  uint64_t seed;
+  float lr, beta1, beta2, eps, kl_scale;
+  float* stats;       /* 1 + n_layers floats */
+} lbbnn_step;
+LBBNN_API size_t lbbnn_lrt_step_workspace_bytes(const lbbnn_step* step);
+LBBNN_API size_t lbbnn_lrt_step_raw_floats(const lbbnn_step* step);
+LBBNN_API int lbbnn_lrt_step_f32(const lbbnn_step* step, int phases, void* workspace, size_t workspace_bytes,
+                                 lbbnn_stream s);
+/* Phase profile: while dev_stamps != NULL, CTA 0 of every following lbbnn_lrt_step_f32 launch writes its clock64()
+ * at each phase boundary (before/after every grid barrier) and inside its last work item of every phase into dev_stamps
+ * (256 int64; layout: see profiles/prof_fused_phases.py).  NULL switches it off. */
+LBBNN_API int lbbnn_lrt_step_profile(long long* dev_stamps);
+/* human-readable schedule (tile sizes / work items per phase) chosen for this step */
+LBBNN_API int lbbnn_lrt_step_describe(const lbbnn_step* step, char* buf, size_t buf_bytes);
+
 /* ---- loss head: F.log_softmax(dim=1) + F.nll_loss(reduction='sum') (LRT:210,223) ------------
  * logp (batch,classes) and dlogits (batch,classes) = grad_scale*(softmax - onehot) may be NULL.
  * step_inc (device int64 or NULL) is incremented by one: the trainer's step counter, bumped between

@@ -183,12 +183,15 @@ def test_cpu_tensors_are_rejected(lb):
         layer(torch.zeros(2, 8), sample=True)
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph):
-    """Whole captured step (fwd, loss, bwd, Adam) vs oracle autograd + torch.optim.Adam, 3 steps."""
+@pytest.mark.parametrize("use_graph,fused", [(False, False), (True, False), (False, True), (True, True)])
+def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph, fused):
+    """Whole captured step (fwd, loss, bwd, Adam) vs oracle autograd + torch.optim.Adam, 3 steps; both the
+    per-layer launch sequence and the single persistent step kernel (csrc/lrt_step.cu)."""
     case = C.lrt_net_case(seed=5, batch=100)
     net = _load_net(lb, case)
-    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph, inject_noise=True)
+    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph, inject_noise=True,
+                       fused=fused)
+    assert tr.fused == fused
     layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
     opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
     rng = np.random.default_rng(99)
@@ -214,11 +217,54 @@ def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph):
                 assert C.rel_err(getattr(l, k).data, p[k].data) < 2e-6, (step, li, k, "param")
 
 
-def test_trainer_native_noise_changes_every_replay(lb):
+@pytest.mark.parametrize("fused", [False, True])
+def test_trainer_native_noise_changes_every_replay(lb, fused):
     case = C.lrt_net_case(seed=6, batch=100)
     net = _load_net(lb, case)
-    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=0.0, use_graph=True)
+    tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=0.0, use_graph=True, fused=fused)
     a = tr.step(case["x"], case["y"])["nll"]
     b = tr.step(case["x"], case["y"])["nll"]
     assert a != b          # lr = 0: only the Philox stream (keyed by the device step counter) changed
     assert tr.step_dev.item() == 2
+
+
+@pytest.mark.parametrize("sizes,batch", [((784, 400, 600, 10), 32), ((20, 1), 128), ((37, 23, 5), 7), ((130, 64, 64, 64, 3), 100)])
+def test_fused_step_equals_per_layer_step(lb, sizes, batch):
+    """The persistent step kernel and the per-layer launch sequence draw the same Philox noise and follow the same
+    formulas: after 3 steps of native-noise training their parameters, Adam state and stats agree (odd shapes:
+    ragged tiles, K and N not multiples of 4, a single layer, five layers)."""
+    pairs = list(zip(sizes[:-1], sizes[1:]))
+    case = C.lrt_net_case(seed=11, batch=batch, sizes=pairs, classes=sizes[-1])
+    outs = []
+    for fused in (False, True):
+        torch.manual_seed(0)
+        net = lb.BayesianNetwork(sizes).cuda()
+        with torch.no_grad():
+            for l, p in zip(net.layers, case["layers"]):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        tr = lb.LRTTrainer(net, batch_size=batch, num_batches=C.NUM_BATCHES, lr=1e-3, seed=77, fused=fused,
+                           materialize_grads=fused)
+        hist = [tr.step(case["x"], case["y"]) for _ in range(3)]
+        outs.append((hist, tr.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone(), tr.gflat.clone()))
+    (h0, p0, m0, v0, g0), (h1, p1, m1, v1, g1) = outs
+    for a, b in zip(h0, h1):
+        assert abs(a["nll"] - b["nll"]) <= 2e-5 * abs(a["nll"]) and abs(a["kl"] - b["kl"]) <= 1e-5 * abs(a["kl"])
+    assert C.rel_err(g1, g0) < 5e-5
+    # Adam's first steps move every parameter by ~lr regardless of the gradient's size, so tiny gradient
+    # differences can flip a step: compare the state the gradients drive (exp_avg) and bound the parameters by lr
+    assert C.rel_err(m1, m0) < 5e-5 and C.rel_err(v1, v0) < 1e-4
+    assert (p1 - p0).abs().max().item() < 2.5e-3
+    assert (p1 - p0).abs().mean().item() < 2e-6
+
+
+def test_fused_step_without_materialized_grads_matches(lb):
+    case = C.lrt_net_case(seed=12, batch=100)
+    res = []
+    for mat in (True, False):
+        net = _load_net(lb, case)
+        tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, seed=5, fused=True, materialize_grads=mat)
+        for _ in range(2):
+            out = tr.step(case["x"], case["y"])
+        res.append((out, tr.flat.clone()))
+    assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])      # same kernel, same order: bit-identical
