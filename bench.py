@@ -170,7 +170,7 @@ def workload_config(workload, n_gpus):
     return {"workload": f"{workload}: LRT MLP {'-'.join(map(str, sizes))}, batch {B} per GPU, "
                         f"fwd+loss+bwd+Adam, NUM_BATCHES={NUM_BATCHES}",
             "batch_per_gpu": B, "global_batch": B * n_gpus,
-            "parallelism": "single GPU" if n_gpus == 1 else f"dp{n_gpus} (NCCL all-reduce of the flat gradient)",
+            "parallelism": "single GPU" if n_gpus == 1 else f"dp{n_gpus} (NCCL all-reduce of the raw weight-moment gradients dM, dV + bias sums, then chain rule + Adam)",
             "l2": f"inputs rotate through a pool of {POOL} distinct batches "
                   f"({POOL * B * sizes[0] * 4 / 1e6:.0f} MB > 126 MB L2); parameters are the step's own working set"}
 
@@ -230,7 +230,7 @@ def profile_calls(tr, reps=20):
     return out
 
 
-def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20):
+def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20, replays=True):
     """Roofline of the persistent step kernel (the only kernel of the step).  Algorithmic bytes: per
     weight 12 B forward read of (mu,rho,lambda) + 12 B re-read in the backward + 12 B of gradient + Adam's 28 B x 3
     tensors (read p,g,m,v, write p,m,v), plus the activations each phase exchanges.  Duration: (a) the average launch
@@ -241,9 +241,9 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20):
     nparam = sum(3 * i * o + 2 * o for i, o in pairs)
     path = sum(36 * i * o + (4 * B * i + 8 * B * o) * 2 + (8 * B * (i + o) if li else 0) for li, (i, o) in enumerate(pairs))
     nbytes = path + 28 * nparam
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=tr.device) if replays else None
     cold = []
-    for _ in range(reps + 2):
+    for _ in range(reps + 2 if replays else 0):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -251,14 +251,16 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20):
         e1.record()
         e1.synchronize()
         cold.append(e0.elapsed_time(e1) * 1e3)
-    us_cold = statistics.mean(cold[2:])
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(200):
-        tr.step_device()
-    e1.record()
-    e1.synchronize()
-    us_warm = e0.elapsed_time(e1) * 1e3 / 200
+    us_cold = statistics.mean(cold[2:]) if replays else None
+    us_warm = None
+    if replays:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(200):
+            tr.step_device()
+        e1.record()
+        e1.synchronize()
+        us_warm = e0.elapsed_time(e1) * 1e3 / 200
     ach = nbytes / (us_per_step * 1e-6) / 1e9
     roof = {"bound": "hbm", "kernel": "lrt_step_kernel (persistent: fwd + loss + bwd + KL + Adam of the whole stack)",
             "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
@@ -273,8 +275,8 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20):
                  "frac_of_hbm_floor": (nbytes / peaks["hbm_gbs"] / 1e3) / us_per_step,
                  "flops_per_step": flops, "fp32_tflops": flops / (us_per_step * 1e-6) / 1e12,
                  "schedule": tr.schedule}
-    kern = [{"name": "lrt_step_kernel", "us": round(us_per_step, 2), "us_back_to_back": round(us_warm, 2),
-             "us_cold_l2": round(us_cold, 2), "bytes": nbytes, "gbps": round(ach, 1)}]
+    kern = [{"name": "lrt_step_kernel", "us": round(us_per_step, 2), "us_back_to_back": us_warm and round(us_warm, 2),
+             "us_cold_l2": us_cold and round(us_cold, 2), "bytes": nbytes, "gbps": round(ach, 1)}]
     return roof, step_roof, kern
 
 
@@ -421,7 +423,8 @@ def run_ours(args):
                          "frac_of_sustained_peak": step_flops / (ms / args.steps * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}
             kern = [{"name": r["name"], "us": round(r["us"], 1), "tflops": round(r["flops"] / r["us"] / 1e6, 1)} for r in prof]
         elif tr.fused:
-            roof, step_roof, kern = profile_fused(tr, sizes, B, ms / args.steps * 1e3, peaks)
+            # extra replays are collective under data parallelism (NCCL all-reduce inside the step): single GPU only
+            roof, step_roof, kern = profile_fused(tr, sizes, B, ms / args.steps * 1e3, peaks, replays=(world == 1))
         else:
             prof = profile_calls(tr)
             top = max(prof, key=lambda r: r["us"])
