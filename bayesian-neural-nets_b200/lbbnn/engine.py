@@ -221,19 +221,82 @@ class LRTTrainer:
             self._enqueue()
 
     def step(self, x_host, y_host, read_loss=True):
-        """One training step from HOST tensors: pinned staging -> H2D -> step -> D2H of [nll, kl...]."""
-        self.x_host.copy_(x_host.reshape(self.x_host.shape))
-        self.y_host.copy_(y_host)
-        self.x.copy_(self.x_host, non_blocking=True)
-        self.y.copy_(self.y_host, non_blocking=True)
+        """One training step from HOST tensors: (pinned staging ->) H2D -> step -> D2H of [nll, kl...].
+        Pinned inputs are uploaded straight from the caller's buffer."""
+        if x_host.is_pinned() and y_host.is_pinned() and x_host.is_contiguous():
+            self.x.copy_(x_host.reshape(self.x.shape), non_blocking=True)
+            self.y.copy_(y_host, non_blocking=True)
+        else:
+            self.x_host.copy_(x_host.reshape(self.x_host.shape))
+            self.y_host.copy_(y_host)
+            self.x.copy_(self.x_host, non_blocking=True)
+            self.y.copy_(self.y_host, non_blocking=True)
         self.step_device()
         if not read_loss:
             return None
         self.stats_host.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        nll = float(self.stats_host[0])
-        kl = float(self.stats_host[1:].sum())
+        return self._stats_dict(self.stats_host)
+
+    def _stats_dict(self, st):
+        nll = float(st[0])
+        kl = float(st[1:].sum())
         return {"nll": nll, "kl": kl, "loss": nll + kl / self.num_batches}
+
+    def step_async(self, x_host, y_host):
+        """Pipelined form of step(): uploads this batch on a copy stream while the previous step is still running,
+        enqueues the step, and returns the statistics of the PREVIOUS step (None on the first call) -- every step's
+        [nll, kl...] still crosses to the host, one call late.  flush() returns the last one."""
+        if not hasattr(self, "_pipe"):
+            dev = self.device
+            self._pipe = dict(
+                copy_stream=torch.cuda.Stream(device=dev), n=0,
+                xs=[torch.empty_like(self.x) for _ in range(2)], ys=[torch.empty_like(self.y) for _ in range(2)],
+                xh=[torch.empty_like(self.x_host).pin_memory() for _ in range(2)],
+                yh=[torch.empty_like(self.y_host).pin_memory() for _ in range(2)],
+                sh=[torch.empty_like(self.stats_host).pin_memory() for _ in range(2)],
+                up=[torch.cuda.Event() for _ in range(2)], used=[torch.cuda.Event() for _ in range(2)],
+                done=[None, None])
+        P = self._pipe
+        i = P["n"] & 1
+        cur = torch.cuda.current_stream()
+        pinned = x_host.is_pinned() and y_host.is_pinned() and x_host.is_contiguous()
+        if not pinned:                                   # stage through this slot's pinned buffers
+            if P["n"] >= 2:
+                P["up"][i].synchronize()                 # the upload that last read them has finished
+            P["xh"][i].copy_(x_host.reshape(P["xh"][i].shape))
+            P["yh"][i].copy_(y_host)
+        src_x, src_y = (x_host.reshape(self.x.shape), y_host) if pinned else (P["xh"][i], P["yh"][i])
+        with torch.cuda.stream(P["copy_stream"]):
+            if P["n"] >= 2:
+                P["copy_stream"].wait_event(P["used"][i])    # the step that consumed this device slot is past its copy
+            P["xs"][i].copy_(src_x, non_blocking=True)
+            P["ys"][i].copy_(src_y, non_blocking=True)
+            P["up"][i].record(P["copy_stream"])
+        cur.wait_event(P["up"][i])
+        self.x.copy_(P["xs"][i], non_blocking=True)
+        self.y.copy_(P["ys"][i], non_blocking=True)
+        P["used"][i].record(cur)
+        self.step_device()
+        P["sh"][i].copy_(self.stats, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        P["done"][i] = ev
+        P["n"] += 1
+        prev = P["done"][i ^ 1]
+        if prev is None:
+            return None
+        prev.synchronize()
+        return self._stats_dict(P["sh"][i ^ 1])
+
+    def flush(self):
+        """Statistics of the last step enqueued by step_async()."""
+        P = getattr(self, "_pipe", None)
+        if P is None or P["n"] == 0:
+            return None
+        i = (P["n"] - 1) & 1
+        P["done"][i].synchronize()
+        return self._stats_dict(P["sh"][i])
 
     @property
     def h2d_bytes_per_step(self):
@@ -424,5 +487,8 @@ class LRTTensorCoreTrainer:
     _capture = LRTTrainer._capture
     step_device = LRTTrainer.step_device
     step = LRTTrainer.step
+    _stats_dict = LRTTrainer._stats_dict
+    step_async = LRTTrainer.step_async
+    flush = LRTTrainer.flush
     h2d_bytes_per_step = LRTTrainer.h2d_bytes_per_step
     d2h_bytes_per_step = LRTTrainer.d2h_bytes_per_step

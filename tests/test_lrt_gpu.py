@@ -268,3 +268,25 @@ def test_fused_step_without_materialized_grads_matches(lb):
             out = tr.step(case["x"], case["y"])
         res.append((out, tr.flat.clone()))
     assert res[0][0] == res[1][0] and torch.equal(res[0][1], res[1][1])      # same kernel, same order: bit-identical
+
+
+def test_step_async_returns_every_steps_stats_one_call_late(lb):
+    """The pipelined host API runs the same steps as the synchronous one: identical statistics, delivered one call late."""
+    case = C.lrt_net_case(seed=13, batch=100)
+    rng = np.random.default_rng(3)
+    xs = [C.t(rng.uniform(0, 1, size=(100, 784))) for _ in range(5)]
+    seqs = []
+    for mode in ("sync", "async", "async_pinned"):
+        net = _load_net(lb, case)
+        tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, seed=9, materialize_grads=False)
+        if mode == "sync":
+            out = [tr.step(x, case["y"]) for x in xs]
+        else:
+            pin = (lambda t_: t_.pin_memory()) if mode == "async_pinned" else (lambda t_: t_)
+            ys = pin(case["y"])
+            out = [tr.step_async(pin(x), ys) for x in xs]
+            assert out[0] is None
+            out = out[1:] + [tr.flush()]
+        seqs.append((out, tr.flat.clone()))
+    for other in seqs[1:]:
+        assert other[0] == seqs[0][0] and torch.equal(other[1], seqs[0][1])
