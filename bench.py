@@ -262,8 +262,18 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20, replays=True):
         e1.synchronize()
         us_warm = e0.elapsed_time(e1) * 1e3 / 200
     ach = nbytes / (us_per_step * 1e-6) / 1e9
+    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_lrt_step_kernel.json")) as fh:
+            nc = json.load(fh)
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        traffic = sum(float(nc[k]["value"]) * scale[nc[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:  # noqa: BLE001
+        pass
     roof = {"bound": "hbm", "kernel": "lrt_step_kernel (persistent: fwd + loss + bwd + KL + Adam of the whole stack)",
-            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+            "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
+            "traffic_note": "ncu replays flush the caches, so this is the cold-L2 DRAM traffic of one launch "
+                            "(profiles/r01_ncu_lrt_step_kernel.json); in steady state the 27 MB of state stay in L2",
             "peak_source": peaks["source"], "us_per_launch": us_per_step, "bytes_per_launch": nbytes,
             "us_per_launch_back_to_back": us_warm, "us_per_launch_cold_l2": us_cold,
             "timing": "average launch over the timed region (CUDA events, one launch per step, inputs rotate through a "
