@@ -1,0 +1,282 @@
+// Monte-Carlo posterior-predictive loop (test_ensemble, LBBNN-GP-MF.py:345-436), batched over weight samples.
+//
+// The reference runs one stochastic forward per (sample, test batch): fresh hard masks gamma ~ Bernoulli(alpha)
+// (MF:113), weights w = gamma (mu + sigma eps) and biases (MF:232-234), F.linear + relu per layer (MF:255,268-271),
+// then accumulates log_softmax outputs (MF:416) and row-normalised expit (MF:397-408) on the host.  Here SB samples
+// go through each stage in ONE launch:
+//   mc_sample    (blocks, SB)          mask + weights + bias of one layer for SB samples, vectorised and coalesced
+//   sgemm_tn     (n-tiles, m-tiles, SB) out[s] = act(x[s] W_s^T + b_s): fp32 SIMT, 128 x BN x 16 tiles, 8 x BN/16 outputs
+//                                       per thread, register-prefetched double-buffered shared memory
+//   mc_accum     (row blocks)          per input row, the SB samples IN ORDER: log_softmax, the two fp64 accumulators
+// Sample s draws from Philox streams keyed by its global index (first + s), exactly the streams of the one-sample
+// entry points (lbbnn_mf_sample_predict), so results do not depend on SB or on how samples are sharded over GPUs.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace lbbnn {
+namespace {
+
+constexpr int kThreads = 256;
+
+// ---- sampling ---------------------------------------------------------------------------------------------------
+struct McSampleArgs {
+  const float *mu, *rho, *lam, *bias_mu, *bias_rho;
+  int64_t n, n_bias;
+  uint64_t seed, stream_base, stream_stride;   // stream of (sample, which) = stream_base + which + sample * stride
+  const int64_t* first;                        // device: global index of sample 0 of this launch
+  float *w, *bias;                             // (SB, n), (SB, n_bias)
+};
+
+__global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs a) {
+  const int s = blockIdx.y;
+  const uint64_t st = a.stream_base + (uint64_t)(*a.first + s) * a.stream_stride;
+  float* w = a.w + (int64_t)s * a.n;
+  if (blockIdx.x == 0) {
+    float* bo = a.bias + (int64_t)s * a.n_bias;
+    for (int64_t i = threadIdx.x; i < a.n_bias; i += blockDim.x)
+      bo[i] = fmaf(sigma_of(__ldg(a.bias_rho + i)), philox_normal1(a.seed, st + 2, (uint64_t)i), __ldg(a.bias_mu + i));
+  }
+  const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w);
+  const int64_t nq = ceil_div(a.n, 4);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float mu[4], rho[4], lam[4], u[4], ep[4], o[4];
+    if (vec) {
+      const float4 m4 = __ldg(reinterpret_cast<const float4*>(a.mu + e0)), r4 = __ldg(reinterpret_cast<const float4*>(a.rho + e0));
+      const float4 l4 = __ldg(reinterpret_cast<const float4*>(a.lam + e0));
+      mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w; rho[0] = r4.x; rho[1] = r4.y; rho[2] = r4.z; rho[3] = r4.w;
+      lam[0] = l4.x; lam[1] = l4.y; lam[2] = l4.z; lam[3] = l4.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const bool ok = e0 + j < a.n;
+        mu[j] = ok ? __ldg(a.mu + e0 + j) : 0.f; rho[j] = ok ? __ldg(a.rho + e0 + j) : 0.f; lam[j] = ok ? __ldg(a.lam + e0 + j) : 0.f;
+      }
+    }
+    philox_uniform4(a.seed, st + 0, (uint64_t)q, u);
+    philox_normal4(a.seed, st + 1, (uint64_t)q, ep);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;      // Bernoulli(alpha).sample() (MF:113)
+      o[j] = g * fmaf(sigma_of(rho[j]), ep[j], mu[j]);            // gamma * (mu + sigma eps)   (MF:232-233)
+    }
+    if (vec) {
+      *reinterpret_cast<float4*>(w + e0) = make_float4(o[0], o[1], o[2], o[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (e0 + j < a.n) w[e0 + j] = o[j];
+    }
+  }
+}
+
+// ---- batched fp32 "TN" GEMM: out[s][m][n] = act(sum_k X[s][m][k] W[s][n][k] + bias[s][n]) ------------------------------
+constexpr int BM = 128, BK = 16;
+
+struct GemmArgs {
+  const float *X, *W, *bias;
+  float* out;
+  int64_t xs, ws, bs, os;   // per-sample strides in floats (xs = 0: every sample reads the same input)
+  int M, N, K, relu;
+};
+
+__device__ __forceinline__ float4 ld4g(const float* __restrict__ base, int row, int nrows, int col, int K, bool vec) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= nrows || col >= K) return r;
+  const float* p = base + (int64_t)row * K + col;
+  if (vec && col + 3 < K) return *reinterpret_cast<const float4*>(p);
+  r.x = p[0];
+  if (col + 1 < K) r.y = p[1];
+  if (col + 2 < K) r.z = p[2];
+  if (col + 3 < K) r.w = p[3];
+  return r;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 2) sgemm_tn_batched_kernel(const GemmArgs a) {
+  constexpr int TN = BN / 16;                  // columns per thread (8 or 4)
+  constexpr int NB4 = BN * BK / 4 / kThreads;  // float4 loads of the W tile per thread (2 or 1)
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int s = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const float* X = a.X + (int64_t)s * a.xs;
+  const float* W = a.W + (int64_t)s * a.ws;
+  const bool vec = (a.K % 4 == 0) && aligned16(X) && aligned16(W);
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[NB4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * kThreads;
+      ra[i] = ld4g(X, m0 + (idx & (BM - 1)), a.M, k0 + (idx / BM) * 4, a.K, vec);
+    }
+#pragma unroll
+    for (int i = 0; i < NB4; ++i) {
+      const int idx = tid + i * kThreads;
+      rb[i] = ld4g(W, n0 + (idx % BN), a.N, k0 + (idx / BN) * 4, a.K, vec);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int idx = tid + i * kThreads;
+      const int r = idx & (BM - 1), kq = (idx / BM) * 4;
+      As[buf][kq + 0][r] = ra[i].x; As[buf][kq + 1][r] = ra[i].y; As[buf][kq + 2][r] = ra[i].z; As[buf][kq + 3][r] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < NB4; ++i) {
+      const int idx = tid + i * kThreads;
+      const int c = idx % BN, kq = (idx / BN) * 4;
+      Bs[buf][kq + 0][c] = rb[i].x; Bs[buf][kq + 1][c] = rb[i].y; Bs[buf][kq + 2][c] = rb[i].z; Bs[buf][kq + 3][c] = rb[i].w;
+    }
+  };
+
+  const int ntile = (a.K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int t = 0; t < ntile; ++t) {
+    const int buf = t & 1;
+    if (t + 1 < ntile) gload((t + 1) * BK);   // next tile's global loads in flight during this tile's math
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      // rows ty*4..+3 and 64+ty*4..+3; columns tx*4..+3 (and BN/2 + tx*4..+3 for BN = 128): conflict-free LDS.128
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[TN];
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      if constexpr (TN == 8) {
+        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][BN / 2 + tx * 4]);
+        bv[TN - 4] = b1.x; bv[TN - 3] = b1.y; bv[TN - 2] = b1.z; bv[TN - 1] = b1.w;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < ntile) {
+      sstore(buf ^ 1);   // the other buffer was last read in iteration t-1, which ended with a barrier
+      __syncthreads();
+    }
+  }
+
+  const float* bias = a.bias + (int64_t)s * a.bs;
+  float* out = a.out + (int64_t)s * a.os;
+  const bool vst = (a.N % 4 == 0) && aligned16(out);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (r >= a.M) continue;
+#pragma unroll
+    for (int h = 0; h < TN / 4; ++h) {
+      const int c = n0 + h * (BN / 2) + tx * 4;
+      if (c >= a.N) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[j] = acc[i][h * 4 + j] + (c + j < a.N ? __ldg(bias + c + j) : 0.f);
+        if (a.relu) v[j] = fmaxf(v[j], 0.f);
+      }
+      float* p = out + (int64_t)r * a.N + c;
+      if (vst && c + 3 < a.N) {
+        *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < a.N) p[j] = v[j];
+      }
+    }
+  }
+}
+
+// ---- accumulation: per input row, the SB samples in order (deterministic fp64 sums) ---------------------------------
+__global__ void __launch_bounds__(kThreads) mc_accumulate_batched_kernel(const float* __restrict__ logits, int64_t B, int64_t C,
+                                                                         int n_samples, double* __restrict__ sum_logp,
+                                                                         double* __restrict__ sum_prob, int64_t* counter) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  if (b < B) {
+    for (int s = 0; s < n_samples; ++s) {
+      const float* row = logits + ((int64_t)s * B + b) * C;
+      float mx = -INFINITY;
+      for (int64_t c = lane; c < C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      float se = 0.f;
+      for (int64_t c = lane; c < C; c += 32) se += expf(row[c] - mx);
+      se = warp_sum(se);
+      const float lse = mx + logf(se);
+      float ps = 0.f;
+      for (int64_t c = lane; c < C; c += 32) ps += 1.0f / (1.0f + expf(-(row[c] - lse)));
+      ps = warp_sum(ps);
+      for (int64_t c = lane; c < C; c += 32) {
+        const float lp = row[c] - lse;
+        sum_logp[b * C + c] += (double)lp;
+        sum_prob[b * C + c] += (double)((1.0f / (1.0f + expf(-lp))) / ps);
+      }
+    }
+  }
+  if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter += n_samples;
+}
+
+}  // namespace
+}  // namespace lbbnn
+
+using namespace lbbnn;
+
+extern "C" int lbbnn_mc_sample(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                               uint64_t stream_base, uint64_t stream_stride, float* w, float* bias, lbbnn_stream s) {
+  LBBNN_REQUIRE(L && L->weight_mu && L->weight_rho && L->lambdal && L->bias_mu && L->bias_rho, "layer has NULL parameters");
+  LBBNN_REQUIRE(n_samples > 0 && n_samples <= 65535 && first_sample_dev && w && bias, "bad argument");
+  McSampleArgs a;
+  a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.bias_mu = L->bias_mu; a.bias_rho = L->bias_rho;
+  a.n = L->in_features * L->out_features; a.n_bias = L->out_features;
+  a.seed = seed; a.stream_base = stream_base; a.stream_stride = stream_stride; a.first = first_sample_dev;
+  a.w = w; a.bias = bias;
+  int64_t blocks = ceil_div(ceil_div(a.n, 4), kThreads);
+  const int64_t cap = std::max<int64_t>(1, 8LL * sm_count() / n_samples);
+  if (blocks > cap) blocks = cap;
+  mc_sample_kernel<<<dim3((unsigned)blocks, (unsigned)n_samples), kThreads, 0, (cudaStream_t)s>>>(a);
+  return check_launch("mc_sample");
+}
+
+extern "C" int lbbnn_linear_f32_batched(const float* x, int64_t x_stride, const float* W, const float* bias, int n_samples,
+                                        int64_t batch, int64_t in_features, int64_t out_features, int flags, float* out,
+                                        lbbnn_stream s) {
+  LBBNN_REQUIRE(x && W && bias && out && n_samples > 0 && n_samples <= 65535, "bad argument");
+  LBBNN_REQUIRE(batch > 0 && in_features > 0 && out_features > 0 && batch < (1LL << 30) && in_features < (1LL << 30) &&
+                    out_features < (1LL << 30), "bad shape");
+  GemmArgs a;
+  a.X = x; a.W = W; a.bias = bias; a.out = out;
+  a.xs = x_stride; a.ws = in_features * out_features; a.bs = out_features; a.os = batch * out_features;
+  a.M = (int)batch; a.N = (int)out_features; a.K = (int)in_features; a.relu = (flags & LBBNN_FLAG_RELU) ? 1 : 0;
+  // 128-wide column tiles unless they would be mostly padding
+  const int64_t t128 = ceil_div(out_features, 128) * 128, t64 = ceil_div(out_features, 64) * 64;
+  if (t128 * 100 <= t64 * 112) {
+    dim3 grid((unsigned)ceil_div(out_features, 128), (unsigned)ceil_div(batch, BM), (unsigned)n_samples);
+    sgemm_tn_batched_kernel<128><<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
+  } else {
+    dim3 grid((unsigned)ceil_div(out_features, 64), (unsigned)ceil_div(batch, BM), (unsigned)n_samples);
+    sgemm_tn_batched_kernel<64><<<grid, kThreads, 0, (cudaStream_t)s>>>(a);
+  }
+  return check_launch("sgemm_tn_batched");
+}
+
+extern "C" int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, int64_t batch, int64_t classes,
+                                           double* sum_logp, double* sum_prob, int64_t* counter, lbbnn_stream s) {
+  LBBNN_REQUIRE(logits && sum_logp && sum_prob && batch > 0 && classes > 0 && n_samples > 0, "bad argument");
+  mc_accumulate_batched_kernel<<<(unsigned)ceil_div(batch, kThreads / 32), kThreads, 0, (cudaStream_t)s>>>(
+      logits, batch, classes, n_samples, sum_logp, sum_prob, counter);
+  return check_launch("mc_accumulate_batched");
+}

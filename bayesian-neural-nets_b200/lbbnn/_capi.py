@@ -130,6 +130,9 @@ SIGNATURES = {
     "lbbnn_mf_sample_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _INT, _P, _P, _P, _SZ, _P]),
     "lbbnn_mf_sample_predict": (_INT, [C.POINTER(Layer), C.POINTER(Noise), C.POINTER(Noise), C.POINTER(Noise), _P, _P, _P]),
     "lbbnn_mc_accumulate": (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
+    "lbbnn_mc_sample": (_INT, [C.POINTER(Layer), _INT, _P, _U64, _U64, _U64, _P, _P, _P]),
+    "lbbnn_linear_f32_batched": (_INT, [_P, _I64, _P, _P, _INT, _I64, _I64, _I64, _INT, _P, _P]),
+    "lbbnn_mc_accumulate_batched": (_INT, [_P, _INT, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_mf_sample_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _P, _P, _P,
                                    _P, _SZ, _P]),
     "lbbnn_flow_save_floats": (_SZ, [C.POINTER(Flow), _I64]),

@@ -309,50 +309,78 @@ class MCPredictor:
     input batch, and the two accumulators of the reference (mean log-softmax -> ensemble argmax, MF:416-417;
     mean row-normalised expit -> predictive probabilities / OOD entropy, MF:397-408, 478-494).
 
-    One sample = one CUDA-graph replay (3 kernels per layer + 1).  Sample s draws from Philox streams keyed
+    samples_per_launch samples = one CUDA-graph replay (2 kernels per layer + 1).  Sample s draws from Philox streams keyed
     by s itself (a device counter), so any split of [0, S) across ranks reproduces the same draws; partial
     sums are fp64 and are combined with ONE all-reduce (process_group) -- argmax is independent of the split.
     """
 
     NSTREAMS = 4   # Philox streams per (sample, layer): gamma u, eps_w, eps_b, spare
 
-    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None):
+    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8):
+        """samples_per_launch: weight samples pushed through every kernel of the loop together (csrc/mc_predict.cu);
+        1 = the one-sample kernels.  Results do not depend on it: every sample draws from streams keyed by its index."""
         K.require_device()
         self.net, self.layers, self.B = net, list(net.layers), int(batch)
         dev = self.layers[0].weight_mu.device
         self.device = dev
         self.seed = current_seed() if seed is None else int(seed)
         self.pg = process_group
+        self.SB = SB = max(1, int(samples_per_launch))
         f32 = dict(dtype=torch.float32, device=dev)
         sizes = [(l.in_features, l.out_features) for l in self.layers]
         self.x = torch.zeros(self.B, sizes[0][0], **f32)
-        self.w = [torch.zeros(o, i, **f32) for i, o in sizes]
-        self.b = [torch.zeros(o, **f32) for _, o in sizes]
-        self.h = [torch.zeros(self.B, o, **f32) for _, o in sizes]
+        self.w = [torch.zeros(SB, o, i, **f32) for i, o in sizes]
+        self.b = [torch.zeros(SB, o, **f32) for _, o in sizes]
+        self.h = [torch.zeros(SB, self.B, o, **f32) for _, o in sizes]
         C_ = sizes[-1][1]
         self.sum_logp = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
         self.sum_prob = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
         self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
         self.ws = torch.empty(max(K.lrt_workspace_bytes(self.B, i, o) for i, o in sizes), dtype=torch.uint8, device=dev)
-        self.kernels_per_sample = 0
+        self.kernels_per_launch = 0
         self.graph = None
         if use_graph:
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(s):
-                self._enqueue()
+                self._enqueue(SB)
             torch.cuda.current_stream().wait_stream(s)
             torch.cuda.synchronize()
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._enqueue()
+                self._enqueue(SB)
             self.reset()
+
+    @property
+    def kernels_per_sample(self):
+        return self.kernels_per_launch / self.SB
 
     def _noise(self, layer, which):
         stride = self.NSTREAMS * len(self.layers)
         return K.make_noise(None, self.seed, layer * self.NSTREAMS + which, self.counter, stride)
 
-    def _enqueue(self):
+    def _enqueue(self, n):
+        """One launch sequence for the next n <= samples_per_launch samples."""
+        st = K.current_stream()
+        L = len(self.layers)
+        if self.SB == 1:
+            return self._enqueue_one()
+        stride = self.NSTREAMS * L
+        h, hs = self.x, 0
+        for i, l in enumerate(self.layers):
+            desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+            K.check(K.lib.lbbnn_mc_sample(desc, n, K.ptr(self.counter, torch.int64), self.seed & (2 ** 64 - 1),
+                                          i * self.NSTREAMS, stride, K.ptr(self.w[i]), K.ptr(self.b[i]), st))
+            K.check(K.lib.lbbnn_linear_f32_batched(K.ptr(h), hs, K.ptr(self.w[i]), K.ptr(self.b[i]), n, self.B,
+                                                   l.in_features, l.out_features, K.FLAG_RELU if i < L - 1 else 0,
+                                                   K.ptr(self.h[i]), st))
+            h, hs = self.h[i], self.B * l.out_features
+        K.check(K.lib.lbbnn_mc_accumulate_batched(K.ptr(h), n, self.B, self.layers[-1].out_features,
+                                                  self.sum_logp.data_ptr(), self.sum_prob.data_ptr(),
+                                                  K.ptr(self.counter, torch.int64), st))
+        self.kernels_per_launch = 2 * L + 1
+
+    def _enqueue_one(self):
         st = K.current_stream()
         L = len(self.layers)
         h = self.x
@@ -368,7 +396,7 @@ class MCPredictor:
             h = self.h[i]
         K.check(K.lib.lbbnn_mc_accumulate(K.ptr(h), self.B, self.layers[-1].out_features, self.sum_logp.data_ptr(),
                                           self.sum_prob.data_ptr(), K.ptr(self.counter, torch.int64), st))
-        self.kernels_per_sample = n + 1
+        self.kernels_per_launch = n + 1
 
     def reset(self, first_sample=0):
         self.sum_logp.zero_()
@@ -379,11 +407,14 @@ class MCPredictor:
         """Accumulate `samples` weight samples with global indices first_sample.. on this rank."""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
         self.reset(first_sample)
-        for _ in range(samples):
+        full, rest = divmod(int(samples), self.SB)
+        for _ in range(full):
             if self.graph is not None:
                 self.graph.replay()
             else:
-                self._enqueue()
+                self._enqueue(self.SB)
+        if rest:
+            self._enqueue(rest)      # a partial last launch runs outside the captured graph
 
     def result(self, total_samples):
         """Combine ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics."""

@@ -226,6 +226,21 @@ LBBNN_API int lbbnn_mf_sample_predict(const lbbnn_layer* layer, const lbbnn_nois
                                       const lbbnn_noise* eps_b, float* w, float* bias, lbbnn_stream s);
 LBBNN_API int lbbnn_mc_accumulate(const float* logits, int64_t batch, int64_t classes, double* sum_logp,
                                   double* sum_prob, int64_t* counter, lbbnn_stream s);
+/* The same loop batched over weight samples (csrc/mc_predict.cu): n_samples samples per launch, sample s of a launch
+ * has the global index *first_sample_dev + s and draws from Philox streams  stream_base + which + index * stream_stride
+ * (which = 0: mask uniforms, 1: weight normals, 2: bias normals) -- with stream_base = layer * 4 and stream_stride =
+ * 4 * n_layers these are exactly the draws of lbbnn_mf_sample_predict, so results do not depend on the batching.
+ *   mc_sample            w (n_samples, out, in), bias (n_samples, out) of one layer
+ *   linear_f32_batched   out[s] = x[s] W[s]^T + bias[s] (optional relu); x_stride = floats between the inputs of
+ *                        consecutive samples (0: all samples read the same input, the first layer)
+ *   mc_accumulate_batched  the two fp64 accumulators over the samples of the launch, in order; counter += n_samples */
+LBBNN_API int lbbnn_mc_sample(const lbbnn_layer* layer, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                              uint64_t stream_base, uint64_t stream_stride, float* w, float* bias, lbbnn_stream s);
+LBBNN_API int lbbnn_linear_f32_batched(const float* x, int64_t x_stride, const float* W, const float* bias, int n_samples,
+                                       int64_t batch, int64_t in_features, int64_t out_features, int flags, float* out,
+                                       lbbnn_stream s);
+LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, int64_t batch, int64_t classes,
+                                          double* sum_logp, double* sum_prob, int64_t* counter, lbbnn_stream s);
 LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
                                   const float* pb, int64_t n, const lbbnn_noise* eps, int flags,
                                   const float* dw, const float* dsums,

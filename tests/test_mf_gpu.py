@@ -157,8 +157,8 @@ def _oracle_mc(net_params, x, seed, samples, lb, first=0):
     return sum_logp, sum_prob
 
 
-@pytest.mark.parametrize("use_graph", [False, True])
-def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph):
+@pytest.mark.parametrize("use_graph,spl", [(False, 1), (True, 1), (False, 5), (True, 8), (True, 16)])
+def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl):
     sizes = [(64, 48), (48, 40), (40, 10)]
     case = C.mf_net_case(seed=60, batch=50, sizes=sizes)
     rng = np.random.default_rng(1)
@@ -171,7 +171,7 @@ def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
     S = 12
-    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph)
+    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph, samples_per_launch=spl)
     mc.run(case["x"].cuda(), S)
     res = mc.result(S)
     ref_logp, ref_prob = _oracle_mc(case["layers"], case["x"], 77, S, lb)
@@ -186,3 +186,25 @@ def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph):
         tot_p += mc.sum_prob
     assert (tot_l - res["mean_logp"] * S).abs().max().item() < 1e-9
     assert torch.equal((tot_l / S).argmax(1), res["pred"])
+
+
+def test_mc_predictor_batched_equals_one_sample_kernels(lb):
+    """Batching over samples changes neither the draws nor (beyond fp32 GEMM summation order) the statistics; the
+    batched sampler is bit-identical to the one-sample sampler; MNIST-shape layers with ragged tiles (400, 600, 10)."""
+    case = C.mf_net_case(seed=61, batch=37)
+    rng = np.random.default_rng(2)
+    for p in case["layers"]:
+        p["lambdal"] = C.t(rng.normal(0.0, 2.0, size=tuple(p["lambdal"].shape)))
+    net = lb.mf.BayesianNetwork().cuda()
+    with torch.no_grad():
+        for l, p in zip(net.layers, case["layers"]):
+            for k, v in p.items():
+                getattr(l, k).copy_(v)
+    a = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=1)
+    b = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4)
+    a.run(case["x"].cuda(), 7, first_sample=3)
+    b.run(case["x"].cuda(), 7, first_sample=3)
+    assert C.rel_err(b.sum_logp, a.sum_logp) < 1e-6 and C.rel_err(b.sum_prob, a.sum_prob) < 1e-6
+    assert torch.equal(a.result(7)["pred"], b.result(7)["pred"])
+    # last sample of the last (partial, 3-sample) launch of b == the single sample a drew last: indices 3+6
+    assert torch.equal(b.w[0][2], a.w[0][0]) and torch.equal(b.b[2][2], a.b[2][0])
