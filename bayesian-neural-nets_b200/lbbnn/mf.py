@@ -303,6 +303,50 @@ class BayesianNetwork(nn.Module):
         return loss, log_prior, log_q, nll
 
 
+class SimStudyNetwork(nn.Module):
+    """The simulation-study model: one MF layer 20 -> 1 as a logistic regression, drop-in for
+    LBBNN-GP-MFsim_study.py:250-300 (`BayesianNetwork` there).  Differences from the MNIST script that the layer
+    reproduces: init ranges mu~U(-.01,.01), lambda~U(-.5,.5) (MFsim:182,191), the log-probs are evaluated at the
+    UNMASKED weights ws (MFsim:233,237), the output is sigmoid + BCELoss(sum) (MFsim:258,287)."""
+
+    def __init__(self, in_features=20, num_batches=5.0, **layer_kwargs):
+        super().__init__()
+        kw = dict(mu_init=0.01, lambda_init=(-0.5, 0.5), logprob_on_ws=True)
+        kw.update(layer_kwargs)
+        self.l1 = BayesianLinear(in_features, 1, 1, **kw)
+        self.num_batches = num_batches
+
+    @property
+    def layers(self):
+        return [self.l1]
+
+    def forward(self, x, g1, sample=False, medimean=False, noise=None):
+        return torch.sigmoid(self.l1(x, g1, sample, medimean, noise=noise))
+
+    def log_prior(self):
+        return self.l1.log_prior
+
+    def log_variational_posterior(self):
+        return self.l1.log_variational_posterior
+
+    def sample_elbo(self, input, target, samples=1, noises=None, us=None):
+        """MFsim:272-300.  Returns (loss, log_prior, log_variational_posterior, negative_log_likelihood, out)."""
+        outs, lps, lqs, nlls = [], [], [], []
+        tgt = target.unsqueeze(1).float()
+        for i in range(samples):
+            self.l1.alpha = 1 / (1 + torch.exp(-self.l1.lambdal))
+            self.l1.gamma.alpha = self.l1.alpha
+            g1 = self.l1.gamma.rsample(None if us is None else us[i])
+            out = self.forward(input, g1, sample=True, medimean=False, noise=None if noises is None else noises[i])
+            outs.append(out)
+            lps.append(self.log_prior())
+            lqs.append(self.log_variational_posterior())
+            nlls.append(F.binary_cross_entropy(out, tgt, reduction="sum"))
+        log_prior, log_q, nll = torch.stack(lps).mean(), torch.stack(lqs).mean(), torch.stack(nlls).mean()
+        loss = nll + (log_q - log_prior) / self.num_batches
+        return loss, log_prior, log_q, nll, torch.stack(outs).mean(0)
+
+
 class MCPredictor:
     """Posterior-predictive model averaging over Monte-Carlo weight samples (test_ensemble, MF:345-436):
     for each sample, fresh hard masks gamma ~ Bernoulli(alpha) and weights per layer, a forward over the whole

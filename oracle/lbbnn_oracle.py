@@ -282,6 +282,19 @@ def mf_net_elbo(x, y, layers, noises, us, num_batches, temperature=0.001, gamma_
     return nll + (log_q - log_p) / num_batches, nll, log_p, log_q, h, gammas
 
 
+def mfsim_elbo(x, y, p, noise, u, num_batches, temperature=0.001, gamma_exact=False, gamma=None):
+    """Simulation-study objective with SAMPLES=1, MFsim:272-300: one 20->1 MF layer whose log-probs are taken at the
+    unmasked ws (MFsim:233,237), sigmoid output, BCELoss(sum); loss = nll + (log_q - log_p)/NUM_BATCHES.
+    `gamma` overrides the relaxed draw (injected-gamma parity).  Returns (loss, nll, log_p, log_q, out)."""
+    alpha = alpha_of(p["lambdal"])
+    if gamma is None:
+        gamma = exact_bernoulli_sample(alpha, u) if gamma_exact else relaxed_bernoulli_rsample(alpha, u, temperature)
+    h, lp, lq = mf_forward(x, p, gamma, noise, exact=(gamma_exact, False, False, False), logprob_on_ws=True)
+    out = torch.sigmoid(h)
+    nll = F.binary_cross_entropy(out, y.unsqueeze(1).to(out.dtype), reduction="sum")
+    return nll + (lq - lp) / num_batches, nll, lp, lq, out
+
+
 def init_mf_params(rng, in_features, out_features, dtype=torch.float32, sim=False):
     """MF:192-220 ranges (sim study MFsim:182-191: mu~U(-.01,.01), lambda~U(-.5,.5))."""
     def u(lo, hi, *shape):

@@ -161,3 +161,21 @@ def unflatten_like(p, named):
         else:
             out[k] = named[k]
     return out
+
+
+SIM_TRUE_WEIGHTS = np.array([-4., 0., 1., 0., 0., 0., 1., 0., 0., 0., 1.2, 0., 37.1, 0., 0., 50., -0.00005, 10., 3., 0.])  # MFsim:350
+
+
+def sim_study_case(seed, n=2000, batch=400, steps=5):
+    """BASELINE.json configs[0]: the reference's CSVs are not shipped, so X ~ N(0,1) (n,20) with
+    columns 6:19 standardised as MFsim:48-51, y ~ Bernoulli(sigmoid(X true_weights)) with MFsim:350's true_weights;
+    sim-study parameter init (MFsim:182-191); per-step noise draws of the layer."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal(size=(n, 20))
+    X[:, 6:19] = (X[:, 6:19] - X[:, 6:19].mean(0)) / X[:, 6:19].std(0)
+    y = (rng.uniform(size=n) < 1.0 / (1.0 + np.exp(-X @ SIM_TRUE_WEIGHTS))).astype(np.int64)
+    p = O.init_mf_params(rng, 20, 1, sim=True)
+    noises = [{"eps_w": t(rng.standard_normal(size=(1, 20))), "eps_b": t(rng.standard_normal(size=(1,))),
+               "g0_w": t(rng.gamma(1.05, size=(1,))), "g0_b": t(rng.gamma(1.05, size=(1,)))} for _ in range(steps)]
+    us = [t(rng.uniform(0.0, 1.0, size=(1, 20))) for _ in range(steps)]
+    return {"X": t(X), "y": torch.from_numpy(y), "p": p, "noises": noises, "us": us, "batch": batch, "num_batches": n / batch}

@@ -190,6 +190,26 @@ def golden_mf():
     print("mf golden written; loss", loss.item(), "log_prior", log_prior.item(), "log_q", log_q.item())
 
 
+def golden_mfsim():
+    """BASELINE.json configs[0]: the simulation-study network (LBBNN-GP-MFsim_study.py:250-300), one sample_elbo +
+    backward on the first minibatch of tests/cases.py:sim_study_case, driven by the replayed noise."""
+    case = C.sim_study_case(seed=70)
+    B, nb = case["batch"], case["num_batches"]
+    ns = H.load_reference_classes("LBBNN-GP-MFsim_study.py", BATCH_SIZE=B, NUM_BATCHES=nb, SAMPLES=1)
+    net = ns["BayesianNetwork"]()
+    _load_params(net.l1, case["p"])
+    net.train()
+    with H.replay(H.NoiseQueue([("uniform", case["us"][0])] + _mf_queue(case["noises"][0]))):
+        loss, lp, lq, nll, outp = net.sample_elbo(case["X"][:B], case["y"][:B])
+    loss.backward()
+    out = {"loss": np.float64(loss.item()), "log_prior": np.float64(lp.item()), "log_q": np.float64(lq.item()),
+           "nll": np.float64(nll.item()), "out": outp.detach().numpy(), "gamma": net.l1.gammas.detach().numpy()}
+    for k, g in _grads(net.l1, MF_NAMES).items():
+        out["d_" + k] = g.numpy()
+    np.savez_compressed(os.path.join(HERE, "mfsim_net.npz"), **out)
+    print("mfsim golden written; loss", loss.item(), "nll", nll.item())
+
+
 def _mnf_queue(nz):
     """Draw order of MNF BayesianLinear.forward in training (MNF:182-235)."""
     q = [("normal", nz["eps_z"])] + [("uniform", 1.0 - m * 0.75) for m in nz["z_masks"]]      # u < .5 <=> mask = 1
@@ -287,3 +307,5 @@ if __name__ == "__main__":
         globals()["golden_mnf"]()
     if what in ("mf", "all") and "golden_mf" in globals():
         globals()["golden_mf"]()
+    if what in ("mfsim", "all"):
+        golden_mfsim()

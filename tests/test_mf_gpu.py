@@ -208,3 +208,51 @@ def test_mc_predictor_batched_equals_one_sample_kernels(lb):
     assert torch.equal(a.result(7)["pred"], b.result(7)["pred"])
     # last sample of the last (partial, 3-sample) launch of b == the single sample a drew last: indices 3+6
     assert torch.equal(b.w[0][2], a.w[0][0]) and torch.equal(b.b[2][2], a.b[2][0])
+
+
+
+def test_sim_study_training_trajectory_matches_oracle(lb):
+    """BASELINE.json configs[0]: the 20 -> 1 simulation-study model (MFsim:250-300) trained for 5 SGD steps with the
+    script's per-group learning rates (MFsim:359-374) on the synthetic stand-in for its CSVs; every step's objective
+    terms and the parameter trajectory follow the oracle (relaxed gamma injected), and the inclusion
+    probabilities alpha = sigmoid(lambda) the study reports agree."""
+    case = C.sim_study_case(seed=70)
+    B, nb = case["batch"], case["num_batches"]
+    lrs = {"bias_mu": 1e-4, "bias_rho": 1e-4, "weight_mu": 1e-4, "weight_rho": 1e-4, "pa": 1e-3, "pb": 1e-3,
+           "weight_a": 1e-3, "weight_b": 1e-3, "bias_a": 1e-3, "bias_b": 1e-3, "lambdal": 1e-3}
+    ref = {k: v.clone().requires_grad_(True) for k, v in case["p"].items()}
+    opt_ref = torch.optim.SGD([{"params": [ref[k]], "lr": lr} for k, lr in lrs.items()], lr=0.01)
+    net = lb.mf.SimStudyNetwork(num_batches=nb).cuda()
+    with torch.no_grad():
+        for k, v in case["p"].items():
+            getattr(net.l1, k).copy_(v)
+    opt = torch.optim.SGD([{"params": [getattr(net.l1, k)], "lr": lr} for k, lr in lrs.items()], lr=0.01)
+    net.train()
+    for step in range(5):
+        xb, yb = case["X"][step * B:(step + 1) * B], case["y"][step * B:(step + 1) * B]
+        nz, u = case["noises"][step], case["us"][step]
+        g = O.relaxed_bernoulli_rsample(O.alpha_of(ref["lambdal"].detach()), u)          # the injected gamma
+        opt_ref.zero_grad()
+        loss_r, nll_r, lp_r, lq_r, out_r = O.mfsim_elbo(xb, yb, ref, nz, u, nb, gamma=g)
+        loss_r.backward()
+        opt.zero_grad()
+        net.l1.alpha = 1 / (1 + torch.exp(-net.l1.lambdal))
+        out = net(xb.cuda(), g.cuda(), sample=True, noise=_cuda_noise(nz))
+        nll = torch.nn.functional.binary_cross_entropy(out, yb.cuda().unsqueeze(1).float(), reduction="sum")
+        loss = nll + (net.log_variational_posterior() - net.log_prior()) / nb
+        loss.backward()
+        assert C.rel_err(out.detach(), out_r.detach()) < 1e-5
+        for a, b in ((nll, nll_r), (net.log_prior(), lp_r), (net.log_variational_posterior(), lq_r), (loss, loss_r)):
+            assert abs(a.item() - b.item()) <= 2e-5 * abs(b.item()) + 1e-4, step
+        for k in lrs:
+            assert C.rel_err(getattr(net.l1, k).grad, ref[k].grad) < 5e-5, (step, k)
+        opt_ref.step()
+        opt.step()
+        for k in lrs:
+            assert C.rel_err(getattr(net.l1, k).data, ref[k].data) < 1e-6, (step, k)
+    alpha = 1 / (1 + torch.exp(-net.l1.lambdal.detach().cpu()))
+    assert C.rel_err(alpha, O.alpha_of(ref["lambdal"].detach())) < 1e-6
+    assert torch.equal(alpha > 0.5, O.alpha_of(ref["lambdal"].detach()) > 0.5)      # median-probability model, bit-exact
+    # the native path of the same model (sample_elbo draws its own gamma / noise) runs and yields finite statistics
+    loss, lp, lq, nll, out = net.sample_elbo(case["X"][:B].cuda(), case["y"][:B].cuda())
+    assert all(torch.isfinite(v).all() for v in (loss, lp, lq, nll, out)) and out.shape == (B, 1)

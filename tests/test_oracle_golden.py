@@ -181,3 +181,19 @@ def test_mnf_mnist_net_matches_reference():
         for name, v in n.items():
             got = torch.from_numpy(C.grad_digest(v.grad)["sample"]) if v.numel() > 2000 else v.grad
             assert C.rel_err(got, g[f"l{li}_{name}"]) < 5e-5, (li, name)
+
+
+def test_sim_study_network_matches_reference():
+    """BASELINE.json configs[0]: sample_elbo of the 20 -> 1 simulation-study model (MFsim:250-300) on the first
+    minibatch of the synthetic stand-in data, relaxed gamma drawn from the replayed uniform."""
+    g = _npz("mfsim_net.npz")
+    case = C.sim_study_case(seed=70)
+    B = case["batch"]
+    p = {k: v.clone().requires_grad_(True) for k, v in case["p"].items()}
+    loss, nll, lp, lq, out = O.mfsim_elbo(case["X"][:B], case["y"][:B], p, case["noises"][0], case["us"][0], case["num_batches"])
+    loss.backward()
+    assert C.rel_err(out, g["out"]) < TOL
+    for name, val in (("loss", loss), ("nll", nll), ("log_prior", lp), ("log_q", lq)):
+        assert abs(val.item() - float(g[name])) <= 5e-6 * abs(float(g[name])), name
+    for k, v in p.items():
+        assert C.rel_err(v.grad, g["d_" + k]) < 5e-5, k
