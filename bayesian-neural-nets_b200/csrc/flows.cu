@@ -43,19 +43,47 @@ __device__ __forceinline__ float mask_of(const float* __restrict__ masks, const 
   return philox_uniform1(nz.seed, nz.stream + (uint64_t)t, (uint64_t)r * (uint64_t)D + (uint64_t)d) < 0.5f ? 1.0f : 0.0f;
 }
 
-// out[j] = act(b[j] + sum_i W[j,i] v[i]) for j over the warps; v in smem
+// out[j] = act(b[j] + sum_i W[j,i] v[i]) for j over the warps; v in smem (16-byte aligned).  Two output neurons per
+// warp pass and float4 loads when the row length allows: 8 independent 16-byte loads in flight per lane.
 __device__ __forceinline__ void gemv_warp(const Lin& L, const float* __restrict__ v, float* __restrict__ out, int kind, bool last,
                                           float* __restrict__ save) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int j = warp; j < L.out; j += kWarps) {
-    const float* w = L.W + (int64_t)j * L.in;
-    float acc = 0.f;
-    for (int i = lane; i < L.in; i += 32) acc = fmaf(__ldg(w + i), v[i], acc);
-    acc = warp_sum(acc);
+  const bool vec = (L.in % 4 == 0) && aligned16(L.W) && aligned16(v);
+  for (int j = warp * 2; j < L.out; j += kWarps * 2) {
+    const bool two = j + 1 < L.out;
+    const float* w0 = L.W + (int64_t)j * L.in;
+    const float* w1 = w0 + (two ? L.in : 0);
+    float a0 = 0.f, a1 = 0.f;
+    if (vec) {
+      const float4* p0 = reinterpret_cast<const float4*>(w0);
+      const float4* p1 = reinterpret_cast<const float4*>(w1);
+      const float4* pv = reinterpret_cast<const float4*>(v);
+      const int n4 = L.in >> 2;
+#pragma unroll 4
+      for (int i = lane; i < n4; i += 32) {
+        const float4 x = pv[i], q0 = __ldg(p0 + i), q1 = __ldg(p1 + i);
+        a0 = fmaf(q0.x, x.x, fmaf(q0.y, x.y, fmaf(q0.z, x.z, fmaf(q0.w, x.w, a0))));
+        a1 = fmaf(q1.x, x.x, fmaf(q1.y, x.y, fmaf(q1.z, x.z, fmaf(q1.w, x.w, a1))));
+      }
+    } else {
+#pragma unroll 4
+      for (int i = lane; i < L.in; i += 32) {
+        const float x = v[i];
+        a0 = fmaf(__ldg(w0 + i), x, a0);
+        a1 = fmaf(__ldg(w1 + i), x, a1);
+      }
+    }
+    a0 = warp_sum(a0);
+    a1 = warp_sum(a1);
     if (lane == 0) {
-      const float h = act_fwd(kind, last, acc + __ldg(L.b + j));
-      out[j] = h;
-      if (save) save[j] = h;
+      const float h0 = act_fwd(kind, last, a0 + __ldg(L.b + j));
+      out[j] = h0;
+      if (save) save[j] = h0;
+      if (two) {
+        const float h1 = act_fwd(kind, last, a1 + __ldg(L.b + j + 1));
+        out[j + 1] = h1;
+        if (save) save[j + 1] = h1;
+      }
     }
   }
 }
@@ -65,7 +93,7 @@ __global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f,
                                                                 const float* __restrict__ masks, const Noise mask_noise,
                                                                 int64_t R, float* __restrict__ z_out,
                                                                 float* __restrict__ logdet, float* __restrict__ save) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int D = f.dim;
   float* zs = sm;             // [D] current z
   float* xm = sm + D;         // [D] m * z
@@ -99,34 +127,36 @@ __global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f,
       v = cur;
       cur = (cur == ha) ? hb : ha;
     }
-    // shift / scale heads and the coupling; each output dim is one warp task
+    // shift / scale heads and the coupling: one output dim per thread (H <= 128 inputs: each thread streams its two
+    // weight rows through L1, no shuffle reductions)
     const Lin& Ls = f.shift[t];
     const Lin& Lc = f.scale[t];
     const int H = Ls.in;
     float ld = 0.f;
-    for (int d = warp; d < D; d += kWarps) {
+    for (int d = tid; d < D; d += kFlowThreads) {
       const float* ws = Ls.W + (int64_t)d * H;
       const float* wc = Lc.W + (int64_t)d * H;
-      float a1 = 0.f, a2 = 0.f;
-      for (int i = lane; i < H; i += 32) {
-        const float y = v[i];
-        a1 = fmaf(__ldg(ws + i), y, a1);
-        a2 = fmaf(__ldg(wc + i), y, a2);
+      float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+      int i = 0;
+      for (; i + 1 < H; i += 2) {
+        a1 = fmaf(__ldg(ws + i), v[i], a1);
+        b1 = fmaf(__ldg(ws + i + 1), v[i + 1], b1);
+        a2 = fmaf(__ldg(wc + i), v[i], a2);
+        b2 = fmaf(__ldg(wc + i + 1), v[i + 1], b2);
       }
-      a1 = warp_sum(a1);
-      a2 = warp_sum(a2);
-      if (lane == 0) {
-        const float sh = a1 + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-(a2 + __ldg(Lc.b + d))));
-        const float z = zs[d], m = ms[d];
-        float x;
-        if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
-        else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
-        zs[d] = x;
-        ld += (1.0f - m) * logf(g);
-        if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
+      if (i < H) {
+        a1 = fmaf(__ldg(ws + i), v[i], a1);
+        a2 = fmaf(__ldg(wc + i), v[i], a2);
       }
+      const float sh = (a1 + b1) + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-((a2 + b2) + __ldg(Lc.b + d))));
+      const float z = zs[d], m = ms[d];
+      float x;
+      if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
+      else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
+      zs[d] = x;
+      ld += (1.0f - m) * logf(g);
+      if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
     }
-    ld = (lane == 0) ? ld : 0.f;
     const float tot = block_sum(ld, red);
     if (tid == 0) ld_total += tot;
     __syncthreads();
@@ -141,7 +171,7 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
                                                                 const float* __restrict__ dz_out,
                                                                 const float* __restrict__ dlogdet,
                                                                 const float* __restrict__ save, float* __restrict__ dz_in) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int D = f.dim;
   float* dz = sm;                 // [D] gradient wrt the current transform's output, then its input
   float* dsh = sm + D;            // [D]
@@ -194,10 +224,15 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
     }
     __syncthreads();
     // head weight gradients: outer products dsh x y, dsc x y
-    for (int64_t e = tid; e < (int64_t)D * H; e += kFlowThreads) {
-      const int d = (int)(e / H), i = (int)(e % H);
-      Ls.dW[goff + e] = dsh[d] * y[i];
-      Lc.dW[goff + e] = dsc[d] * y[i];
+    for (int d = warp; d < D; d += kWarps) {      // rows over the warps, lanes along the (contiguous) row
+      const float a = dsh[d], c = dsc[d];
+      float* ps = Ls.dW + goff + (int64_t)d * H;
+      float* pc = Lc.dW + goff + (int64_t)d * H;
+      for (int i = lane; i < H; i += 32) {
+        const float yi = y[i];
+        ps[i] = a * yi;
+        pc[i] = c * yi;
+      }
     }
     // dy[i] = sum_d Wt[d,i] dsh[d] + Ws[d,i] dsc[d]: warps take slices of d, lanes run over i (coalesced rows)
     {
@@ -237,22 +272,38 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
         L.db[goff + j] = g;
       }
       __syncthreads();
-      for (int64_t e = tid; e < (int64_t)L.out * L.in; e += kFlowThreads) {
-        const int j = (int)(e / L.in), i = (int)(e % L.in);
-        L.dW[goff + e] = da[j] * (vin_smem ? xm[i] : vin[i]);
+      for (int j = warp; j < L.out; j += kWarps) {
+        const float a = da[j];
+        float* pw = L.dW + goff + (int64_t)j * L.in;
+        const float* src = vin_smem ? xm : vin;
+        for (int i = lane; i < L.in; i += 32) pw[i] = a * src[i];
       }
       // gradient wrt the layer input: dv[i] = sum_j W[j,i] da[j]; threads over i (coalesced), loop over j
       if (l == 0) {
         for (int i = tid; i < L.in; i += kFlowThreads) {
-          float s = 0.f;
-          for (int j = 0; j < L.out; ++j) s = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s);
-          dz[i] += ms[i] * s;                                              // input of the net was m * z
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = 0;
+          for (; j + 3 < L.out; j += 4) {
+            s0 = fmaf(__ldg(L.W + (int64_t)(j + 0) * L.in + i), da[j + 0], s0);
+            s1 = fmaf(__ldg(L.W + (int64_t)(j + 1) * L.in + i), da[j + 1], s1);
+            s2 = fmaf(__ldg(L.W + (int64_t)(j + 2) * L.in + i), da[j + 2], s2);
+            s3 = fmaf(__ldg(L.W + (int64_t)(j + 3) * L.in + i), da[j + 3], s3);
+          }
+          for (; j < L.out; ++j) s0 = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s0);
+          dz[i] += ms[i] * ((s0 + s1) + (s2 + s3));                       // input of the net was m * z
         }
       } else {
         for (int i = tid; i < L.in; i += kFlowThreads) {
-          float s = 0.f;
-          for (int j = 0; j < L.out; ++j) s = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s);
-          part[i] = s;
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+          int j = 0;
+          for (; j + 3 < L.out; j += 4) {
+            s0 = fmaf(__ldg(L.W + (int64_t)(j + 0) * L.in + i), da[j + 0], s0);
+            s1 = fmaf(__ldg(L.W + (int64_t)(j + 1) * L.in + i), da[j + 1], s1);
+            s2 = fmaf(__ldg(L.W + (int64_t)(j + 2) * L.in + i), da[j + 2], s2);
+            s3 = fmaf(__ldg(L.W + (int64_t)(j + 3) * L.in + i), da[j + 3], s3);
+          }
+          for (; j < L.out; ++j) s0 = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s0);
+          part[i] = (s0 + s1) + (s2 + s3);
         }
         __syncthreads();
         for (int i = tid; i < L.in; i += kFlowThreads) dh[i] = part[i];

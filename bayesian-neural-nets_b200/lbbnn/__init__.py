@@ -5,7 +5,7 @@ from . import _capi
 from ._capi import LbbnnError, philox_normal, philox_uniform
 from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
 from . import flows, mf, mnf
-from .engine import LRTTrainer, LRTTensorCoreTrainer
+from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer
 
-__all__ = ["BayesianLinear", "BayesianNetwork", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "lrt_linear",
+__all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "lrt_linear",
            "manual_seed", "mf", "mnf", "flows", "philox_normal", "philox_uniform"]

@@ -227,7 +227,30 @@ def make_layer(weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z=None, z_kl=N
                  ptr(z, allow_none=True), in_f, out_f, ptr(z_kl, allow_none=True))
 
 
+# While a whole-step CUDA graph is being warmed up / captured (engine.GraphedTrainer), every native-noise call of the
+# drop-in modules adds  *step * GRAPH_NOISE_STRIDE  to its Philox stream: the stream ids are Python integers baked into
+# the captured launches, the device step counter is what makes each replay draw fresh noise.
+GRAPH_NOISE_STRIDE = 0x9E3779B1
+_graph_noise_step = None
+
+
+class graph_noise:
+    def __init__(self, step_tensor):
+        self.step = step_tensor
+
+    def __enter__(self):
+        global _graph_noise_step
+        self.prev, _graph_noise_step = _graph_noise_step, self.step
+        return self
+
+    def __exit__(self, *exc):
+        global _graph_noise_step
+        _graph_noise_step = self.prev
+
+
 def make_noise(eps=None, seed=0, stream_id=0, step_dev=None, step_stride=0):
+    if eps is None and step_dev is None and _graph_noise_step is not None:
+        step_dev, step_stride = _graph_noise_step, GRAPH_NOISE_STRIDE
     return Noise(ptr(eps, allow_none=True), seed & (2 ** 64 - 1), stream_id & (2 ** 64 - 1),
                  ptr(step_dev, torch.int64, allow_none=True), step_stride)
 

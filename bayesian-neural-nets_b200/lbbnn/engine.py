@@ -492,3 +492,79 @@ class LRTTensorCoreTrainer:
     flush = LRTTrainer.flush
     h2d_bytes_per_step = LRTTrainer.h2d_bytes_per_step
     d2h_bytes_per_step = LRTTrainer.d2h_bytes_per_step
+
+
+class GraphedTrainer:
+    """Whole training step of ANY of the drop-in networks (LRT, MNF, MF) as one CUDA-graph replay: forward through the
+    modules' autograd Functions (liblbbnn kernels), the objective, backward and torch.optim.Adam(capturable=True) are
+    captured once; a device step counter keys the native Philox noise so every replay draws fresh noise.
+
+    Reference: the body of `train` for one minibatch -- LBBNN-GP-MF-MNF.py:263-275 (objective="kl": nll_loss(sum) +
+    net.kl()/NUM_BATCHES) and LBBNN-GP-MF.py:325-343 (objective="elbo": net.sample_elbo).  The eager modules run the
+    same kernels one Python call at a time (~8 ms per MNF step on B200, host-bound); the replay removes the host."""
+
+    def __init__(self, net, batch_size, num_batches, objective="kl", lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                 in_features=None, optimizer=None):
+        K.require_device()
+        self.net, self.B, self.num_batches, self.objective = net, int(batch_size), num_batches, objective
+        params = list(net.parameters())
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise K.LbbnnError("GraphedTrainer needs the network on a CUDA device (no CPU fallback)")
+        self.device = dev
+        in_features = in_features or net.sizes[0]
+        self.x = torch.zeros(self.B, in_features, dtype=torch.float32, device=dev)
+        self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.opt = optimizer or torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        self.stats = torch.zeros(2, dtype=torch.float32, device=dev)      # [loss, nll]
+        self.stats_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        self.x_host = torch.zeros(self.B, in_features, dtype=torch.float32).pin_memory()
+        self.y_host = torch.zeros(self.B, dtype=torch.int64).pin_memory()
+        net.train()
+        self._stream = torch.cuda.Stream(device=dev)
+        self._stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._stream), K.graph_noise(self.step_dev):
+            for _ in range(3):                      # warm-up: sizes every workspace, creates the Adam state
+                self._one_step()
+        torch.cuda.current_stream().wait_stream(self._stream)
+        torch.cuda.synchronize()
+        self.opt.zero_grad(set_to_none=True)        # gradients are re-allocated from the graph's private pool
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self._stream), K.graph_noise(self.step_dev):
+            self._one_step()
+        self.warmup_steps = 3
+
+    def _one_step(self):
+        self.opt.zero_grad(set_to_none=True)
+        if self.objective == "elbo":
+            out = self.net.sample_elbo(self.x, self.y)
+            loss, nll = out[0], out[3]
+        else:
+            logp = self.net(self.x, sample=True)
+            nll = torch.nn.functional.nll_loss(logp, self.y, reduction="sum")
+            loss = nll + self.net.kl() / self.num_batches
+        loss.backward()
+        self.opt.step()
+        self.stats.copy_(torch.stack([loss.detach(), nll.detach()]))
+        K.check(K.lib.lbbnn_counter_inc(K.ptr(self.step_dev, torch.int64), K.current_stream()))
+
+    def step_device(self):
+        self.graph.replay()
+
+    def step(self, x_host, y_host, read_loss=True):
+        """One training step from HOST tensors: H2D, replay, D2H of [loss, nll]."""
+        if x_host.is_pinned() and y_host.is_pinned() and x_host.is_contiguous():
+            self.x.copy_(x_host.reshape(self.x.shape), non_blocking=True)
+            self.y.copy_(y_host, non_blocking=True)
+        else:
+            self.x_host.copy_(x_host.reshape(self.x_host.shape))
+            self.y_host.copy_(y_host)
+            self.x.copy_(self.x_host, non_blocking=True)
+            self.y.copy_(self.y_host, non_blocking=True)
+        self.graph.replay()
+        if not read_loss:
+            return None
+        self.stats_host.copy_(self.stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return {"loss": float(self.stats_host[0]), "nll": float(self.stats_host[1])}

@@ -210,7 +210,7 @@ class BayesianLinear(nn.Module):
 
     def _tau(self, a, b, g0):
         if g0 is None:
-            return torch.distributions.Gamma(a, b).rsample()
+            return torch.distributions.Gamma(a, b, validate_args=False).rsample()   # no host sync: graph-capturable
         return _StdGammaReparam.apply(a, g0) / b
 
     def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):

@@ -685,6 +685,167 @@ def run_mc(args):
         os._exit(0)
 
 
+# ------------------------------------------------------------------------------------------------
+# MNF / MF training steps through the drop-in modules (BASELINE.json configs[2] and the MF train loop, MF:325-343):
+# the reference's own `train` body -- forward (flows / weight sampling), objective, backward, optim.Adam.step -- with
+# the modules of this repo; every kernel of the layers is liblbbnn's, the glue (autograd tape, Adam) is torch's.
+# ------------------------------------------------------------------------------------------------
+def _module_oracle_step(kind):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import lbbnn_oracle as O
+    import cases as C
+    rng = np.random.default_rng(0)
+    sizes = list(zip(MC_SIZES[:-1], MC_SIZES[1:]))
+    B = 100
+    x = torch.from_numpy(rng.random((B, 784), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, 10, size=(B,))).long()
+    if kind == "mnf_mnist":
+        named = [{k: v.clone().requires_grad_(True) for k, v in C.flat_named(O.init_mnf_params(rng, i, o)).items()} for i, o in sizes]
+        tmpl = [O.init_mnf_params(np.random.default_rng(1), i, o) for i, o in sizes]
+        layers = [C.unflatten_like(t_, n) for t_, n in zip(tmpl, named)]
+        opt = torch.optim.Adam([v for n in named for v in n.values()], lr=1e-3)
+
+        def one():
+            noises = [C.mnf_noise(rng, B, i, o) for i, o in sizes]
+            opt.zero_grad(set_to_none=True)
+            loss, _, _, _ = O.mnf_net_loss(x, y, layers, noises, NUM_BATCHES)
+            loss.backward()
+            opt.step()
+    else:
+        layers = [{k: v.clone().requires_grad_(True) for k, v in O.init_mf_params(rng, i, o).items()} for i, o in sizes]
+        opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
+
+        def one():
+            noises = [{"eps_w": torch.randn(o, i), "eps_b": torch.randn(o), "g0_w": torch._standard_gamma(torch.full((1,), 1.05)),
+                       "g0_b": torch._standard_gamma(torch.full((o,), 1.05))} for i, o in sizes]
+            us = [torch.rand(o, i) for i, o in sizes]
+            opt.zero_grad(set_to_none=True)
+            loss = O.mf_net_elbo(x, y, layers, noises, us, NUM_BATCHES)[0]
+            loss.backward()
+            opt.step()
+    return one, B
+
+
+def cpu_reference_module(kind, budget_s=15.0, max_steps=60):
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one, B = _module_oracle_step(kind)
+    one()
+    done, t0 = 0, time.perf_counter()
+    while done < max_steps and (done < 2 or time.perf_counter() - t0 < budget_s):
+        one()
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": "port", "steps": done,
+            "ms_per_step": dt / done * 1e3,
+            "sample": f"{done} training steps (fwd+objective+bwd+Adam) of {kind} batch {B}, oracle port on torch-CPU fp32, {cores} threads"}
+
+
+def module_config(kind):
+    what = ("MNF MLP 784-400-600-10 (2 RNVP transforms, h=75x4, z flow + auxiliary r flow KL)" if kind == "mnf_mnist"
+            else "MF MLP 784-400-600-10 (relaxed-Bernoulli gamma, full weight sampling, GaussGamma/BetaBinomial log-probs)")
+    return {"workload": f"{kind}: {what}, batch 100, fwd+objective+bwd+Adam through the drop-in modules (eager autograd)",
+            "batch_per_gpu": 100, "parallelism": "single GPU",
+            "l2": "inputs rotate through a pool of 512 distinct batches (161 MB > 126 MB L2)"}
+
+
+def run_module(args):
+    kind = args.workload
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        r = cpu_reference_module(kind, budget_s=60.0, max_steps=max(8, args.steps))
+        print(json.dumps({"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": r["unit"],
+                          "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"],
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": module_config(kind),
+                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                          "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}), flush=True)
+        return
+    import lbbnn
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit(f"{kind} is a single-GPU workload (replicas only)")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    lbbnn.manual_seed(99)
+    B, POOL = 100, 512
+    net = (lbbnn.mnf.BayesianNetwork() if kind == "mnf_mnist" else lbbnn.mf.BayesianNetwork()).to(dev)
+    net.train()
+    px_h, py_h = make_pool(POOL, B, 784, 10, seed=1000)
+    px_h, py_h = px_h.pin_memory(), py_h.pin_memory()
+    px, py = px_h.to(dev), py_h.to(dev)
+    if args.eager:
+        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+
+        def dev_step(x, y):
+            opt.zero_grad(set_to_none=True)
+            if kind == "mnf_mnist":
+                logp = net(x, sample=True)
+                loss = torch.nn.functional.nll_loss(logp, y, reduction="sum") + net.kl() / NUM_BATCHES
+            else:
+                loss = net.sample_elbo(x, y)[0]
+            loss.backward()
+            opt.step()
+            return loss
+
+        def host_step(xh, yh):
+            return dev_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)).item()
+    else:   # the whole step (modules' autograd Functions + objective + backward + Adam) as one CUDA-graph replay
+        tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3,
+                                  objective="kl" if kind == "mnf_mnist" else "elbo")
+
+        def dev_step(x, y):
+            tr.x.copy_(x, non_blocking=True)
+            tr.y.copy_(y, non_blocking=True)
+            tr.step_device()
+
+        def host_step(xh, yh):
+            return tr.step(xh, yh)["loss"]
+
+    for i in range(args.warmup):
+        dev_step(px[i % POOL], py[i % POOL])
+    sampler = ClockSampler(0)
+    sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        dev_step(px[(args.warmup + i) % POOL], py[(args.warmup + i) % POOL])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    te0 = time.perf_counter()
+    for i in range(args.steps):
+        lv = host_step(px_h[(i + 7) % POOL], py_h[(i + 7) % POOL])
+    torch.cuda.synchronize()
+    te1 = time.perf_counter()
+    sampler.stop()
+    from lbbnn import _capi as K
+    cpu = cpu_reference_module(kind)
+    peaks = load_peaks()
+    nparam = sum(p.numel() for p in net.parameters())
+    # algorithmic bytes of a step: every parameter read in forward and backward, gradient written, Adam 28 B/param
+    nbytes = nparam * (4 + 4 + 4 + 28)
+    us = ms / args.steps * 1e3
+    line = {"metric": "train_samples_per_sec", "value": B * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": module_config(kind),
+            "e2e": {"value": B * args.steps / (te1 - te0), "unit": "samples/s", "h2d_bytes_per_step": B * 784 * 4 + B * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": (te1 - te0) / args.steps * 1e3},
+            "gpu_launches": None, "mode": "eager" if args.eager else "cuda-graph replay of the whole step",
+            "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of one replay)", "achieved": nbytes / (us * 1e-6) / 1e9,
+                         "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                         "traffic": None, "peak_source": peaks["source"], "bytes_per_launch": nbytes, "us_per_launch": us,
+                         "note": "a step is ~10^2 small launches (flow GEMVs, prologue/finalize, Adam): latency-bound, reported "
+                                 "against HBM because the contract asks for one bound"},
+            "clocks": sampler.summary(t0, te1), "last_loss": lv, "n_parameters": nparam,
+            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -692,11 +853,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mc-batch", type=int, default=21, help="mf_mc_predict: weight samples per launch")
+    ap.add_argument("--eager", action="store_true", help="mnf_mnist / mf_mnist: eager modules instead of the graphed step")
     ap.add_argument("--unfused", action="store_true", help="lrt_mnist: per-layer launch sequence instead of the step kernel")
-    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict"])
+    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist"])
     args = ap.parse_args()
     if args.workload == "mf_mc_predict":
         run_mc(args)
+    elif args.workload in ("mnf_mnist", "mf_mnist"):
+        run_module(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
