@@ -84,6 +84,9 @@ struct DevLayer {
 
 struct DevStep {
   int L, B, phases, nll_ctas;
+  int overlap_update;   // experimental (LBBNN_STEP_OVERLAP_UPDATE=1): see the kernel; measured slower on B200, off
+  int small_last;   // the last layer is a small classifier (N <= 32): dedicated forward+loss and backward phases
+  float* mv_last;   // its M and V, (2, N, K), computed once per launch
   DevLayer ly[kMaxL];
   float *flat, *m, *v, *grad;
   const float* x;
@@ -101,7 +104,7 @@ struct DevStep {
 };
 
 __device__ __forceinline__ void stamp(const DevStep& a, int& slot) {
-  if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) a.prof[slot] = clock64();
+  if (a.prof && (int)blockIdx.x == a.prof_cta && threadIdx.x == 0) a.prof[slot] = clock64();
   ++slot;
 }
 
@@ -829,7 +832,8 @@ __device__ __forceinline__ void stq4(float* p, const Q4& q, int cnt, bool vec) {
 
 // one layer's weights: chain rule + KL + Adam over quads; VEC = all quads are full and 16-byte aligned
 template <bool VEC, bool REF>
-__device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer& y, float step_size, float inv_bc2_sqrt) {
+__device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer& y, float step_size, float inv_bc2_sqrt,
+                                                int cta, int ncta) {
   const lbbnn_priors P = y.pri;
   const float klg = a.klg;
   const float inv_sp2 = 1.0f / (P.sigma * P.sigma);
@@ -837,7 +841,7 @@ __device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer
   const int64_t n = (int64_t)y.N * y.K;
   const int64_t nq = (n + 3) >> 2;
   float kl = 0.f;
-  for (int64_t q = (int64_t)blockIdx.x * NT + threadIdx.x; q < nq; q += (int64_t)gridDim.x * NT) {
+  for (int64_t q = (int64_t)cta * NT + threadIdx.x; q < nq; q += (int64_t)ncta * NT) {
     const int64_t e0 = q * 4;
     const int cnt = VEC ? 4 : (int)min((int64_t)4, n - e0);
     Q4 mu = ldq4<false>(a.flat + y.off_mu + e0, cnt, VEC), rho = ldq4<false>(a.flat + y.off_rho + e0, cnt, VEC);
@@ -892,10 +896,13 @@ __device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer
   return kl;
 }
 
-__device__ void update_phase(const DevStep& a, int64_t step, float* __restrict__ sm) {
+// Chain rule + KL + Adam of layers [l0, l1) by the CTAs [cta0, cta0 + ncta) of the grid (every CTA of that range
+// calls this; `cta` = its index in the range).  The first CTA of the range also updates the biases.  Each CTA leaves
+// its KL partial of every layer in kl_part[l][blockIdx.x].
+__device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, int cta, int ncta, float* __restrict__ sm) {
   __shared__ float coef[2];
-  __shared__ int is_last;
   double* dred = reinterpret_cast<double*>(sm);
+  __syncthreads();
   if (threadIdx.x == 0) {
     const double t = (double)(step + 1);
     coef[0] = a.lr / (float)(1.0 - pow((double)a.b1, t));
@@ -903,19 +910,17 @@ __device__ void update_phase(const DevStep& a, int64_t step, float* __restrict__
   }
   __syncthreads();
   const float step_size = coef[0], bc2_sqrt = coef[1];  // bc2_sqrt holds 1/sqrt(1 - beta2^t)
-  SUBSTAMP(a, 8);
   const float klg = a.klg;
-  for (int l = 0; l < a.L; ++l) {
+  for (int l = l0; l < l1; ++l) {
     const DevLayer& y = a.ly[l];
     const lbbnn_priors P = y.pri;
     const bool vec = (((int64_t)y.N * y.K) % 4 == 0);
     const bool ref = y.var_mode == LBBNN_VAR_REFERENCE;
     float kl;
-    if (vec) kl = ref ? update_weights<true, true>(a, y, step_size, bc2_sqrt) : update_weights<true, false>(a, y, step_size, bc2_sqrt);
-    else kl = ref ? update_weights<false, true>(a, y, step_size, bc2_sqrt) : update_weights<false, false>(a, y, step_size, bc2_sqrt);
-    SUBSTAMP(a, 9 + 2 * l);
+    if (vec) kl = ref ? update_weights<true, true>(a, y, step_size, bc2_sqrt, cta, ncta) : update_weights<true, false>(a, y, step_size, bc2_sqrt, cta, ncta);
+    else kl = ref ? update_weights<false, true>(a, y, step_size, bc2_sqrt, cta, ncta) : update_weights<false, false>(a, y, step_size, bc2_sqrt, cta, ncta);
     // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); one CTA per layer
-    if ((int)blockIdx.x == (a.L - 1 - l) % (int)gridDim.x) {
+    if (cta == (a.L - 1 - l) % ncta) {
       const float inv = 1.0f / (P.bias_sigma * P.bias_sigma);
       for (int i = threadIdx.x; i < y.N; i += NT) {
         float bm = a.flat[y.off_bmu + i], br = a.flat[y.off_brho + i];
@@ -936,9 +941,13 @@ __device__ void update_phase(const DevStep& a, int64_t step, float* __restrict__
     const double tot = block_sum((double)kl, dred);
     if (threadIdx.x == 0) a.kl_part[(int64_t)l * gridDim.x + blockIdx.x] = tot;
     __syncthreads();
-    SUBSTAMP(a, 10 + 2 * l);
   }
-  // the last CTA to arrive sums the per-CTA partials in a fixed order (deterministic), bumps the step counter
+}
+
+// The last CTA to arrive sums the per-CTA partials in a fixed order (deterministic) and bumps the step counter.
+__device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ sm) {
+  __shared__ int is_last;
+  double* dred = reinterpret_cast<double*>(sm);
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -967,6 +976,232 @@ __device__ void update_phase(const DevStep& a, int64_t step, float* __restrict__
   }
 }
 
+// ---- small classifier head (last layer, N <= 32) --------------------------------------------------------------------
+// A 600 -> 10 layer is 0.2 % of the step's FLOPs; as generic split-K tiles it costs a GEMM phase, an epilogue phase and a
+// backward phase of fixed overheads.  Instead: M, V of the layer are computed once per launch (elementwise, at kernel
+// start); `last_fwd_loss` gives every batch row to one CTA (warps own classes, lanes stride the contraction, so the
+// sums have a fixed order) and goes straight on to log-softmax / nll / dlogits; `last_bwd` is elementwise over the
+// (batch, in) inputs for dX and over the (out, in) weights for dM, dV.
+__device__ void last_moments(const DevStep& a) {
+  const DevLayer& y = a.ly[a.L - 1];
+  const int64_t n = (int64_t)y.N * y.K;
+  const float* mu = a.flat + y.off_mu;
+  const float* rho = a.flat + y.off_rho;
+  const float* lam = a.flat + y.off_lam;
+  for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < n; e += (int64_t)gridDim.x * NT) {
+    const Moments mo = weight_moments(__ldg(mu + e), sigma_of(__ldg(rho + e)), alpha_of(__ldg(lam + e)), y.var_mode);
+    a.mv_last[e] = mo.m;
+    a.mv_last[n + e] = mo.v;
+  }
+}
+
+__device__ void last_fwd_loss(const DevStep& a, int64_t step, float* __restrict__ sm) {
+  const int l = a.L - 1;
+  const DevLayer& y = a.ly[l];
+  const int B = a.B, K = y.K, N = y.N;
+  if ((int)blockIdx.x >= a.nll_ctas) return;
+  const int rows = (B + a.nll_ctas - 1) / a.nll_ctas;
+  const int b0 = blockIdx.x * rows;
+  const int nrow = min(rows, B - b0);
+  const float* xin = l == 0 ? a.x : a.ly[l - 1].act;
+  const float* M = a.mv_last;
+  const float* V = a.mv_last + (int64_t)N * K;
+  const float* bmu = a.flat + y.off_bmu;
+  const float* brho = a.flat + y.off_brho;
+  const uint64_t stream = (uint64_t)l + (uint64_t)step * (uint64_t)a.L;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = NT / 32;
+  float* logit = sm;               // [rows][N]
+  float* wred = sm + rows * N;     // [NW][2 N] per-warp partial sums of the current row
+  for (int r = 0; r < nrow; ++r) {
+    const float* xr = xin + (int64_t)(b0 + r) * K;
+    // the epilogue's noise and bias terms do not depend on the sums: computed while the loads below are in flight
+    float ep = 0.f, sb2 = 0.f, bm = 0.f;
+    if (threadIdx.x < N) {
+      const int64_t ei = (int64_t)(b0 + r) * N + threadIdx.x;
+      ep = y.eps ? __ldg(y.eps + ei) : philox_normal1(a.seed, stream, (uint64_t)ei);
+      const float sb = sigma_of(__ldg(brho + threadIdx.x));
+      sb2 = sb * sb;
+      bm = __ldg(bmu + threadIdx.x);
+    }
+    // all threads stride the contraction; five classes' M, V loads (up to 30 per thread) are in flight together
+    for (int n0 = 0; n0 < N; n0 += 5) {
+      float e[5] = {0.f, 0.f, 0.f, 0.f, 0.f}, s_[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int k0 = threadIdx.x; k0 < K; k0 += NT * 3) {
+        float xv[3], mv[5][3], vv[5][3];
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+          const int k = k0 + q * NT;
+          xv[q] = k < K ? (l == 0 ? __ldg(xr + k) : __ldcg(xr + k)) : 0.f;
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            const bool ok = k < K && n0 + u < N;
+            mv[u][q] = ok ? __ldcg(M + (int64_t)(n0 + u) * K + k) : 0.f;
+            vv[u][q] = ok ? __ldcg(V + (int64_t)(n0 + u) * K + k) : 0.f;
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+          for (int u = 0; u < 5; ++u) {
+            e[u] = fmaf(xv[q], mv[u][q], e[u]);
+            s_[u] = fmaf(xv[q] * xv[q], vv[u][q], s_[u]);
+          }
+      }
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        const float E = warp_sum(e[u]), S = warp_sum(s_[u]);
+        if (lane == 0 && n0 + u < N) { wred[warp * 2 * N + n0 + u] = E; wred[warp * 2 * N + N + n0 + u] = S; }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+      const int n = threadIdx.x;
+      float E = 0.f, S = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) { E += wred[w * 2 * N + n]; S += wred[w * 2 * N + N + n]; }   // fixed order
+      const int64_t ei = (int64_t)(b0 + r) * N + n;
+      const float sd = sqrtf(S + sb2);
+      const float v = fmaf(sd, ep, E + bm);
+      logit[r * N + n] = v;
+      y.act[ei] = v;
+      y.dsf[ei] = ep / (2.0f * sd);
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  float local = 0.f;
+  if (warp < nrow) {
+    const int b = b0 + warp;
+    const float* row = logit + warp * N;
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, row[n]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int n = lane; n < N; n += 32) se += expf(row[n] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    const int64_t tgt = a.y[b];
+    for (int n = lane; n < N; n += 32) {
+      const int64_t e = (int64_t)b * N + n;
+      const float lp = row[n] - lse;
+      const float gd = expf(lp) - (n == tgt ? 1.0f : 0.0f);
+      y.dE[e] = gd;
+      y.dS[e] = gd * y.dsf[e];
+      if (n == tgt) local -= lp;
+    }
+  }
+  __syncthreads();
+  const float tot = block_sum(local, sm);
+  if (threadIdx.x == 0) a.nll_part[blockIdx.x] = tot;
+}
+
+__device__ void last_bwd(const DevStep& a, float* __restrict__ sm) {
+  const int l = a.L - 1;
+  const DevLayer& y = a.ly[l];
+  const int B = a.B, K = y.K, N = y.N;
+  const float* M = a.mv_last;
+  const float* V = a.mv_last + (int64_t)N * K;
+  const float* xin = l == 0 ? a.x : a.ly[l - 1].act;
+  const int G = gridDim.x;
+  // dX (+ relu mask and ds_factor of the layer below): one (b, k) per thread, contraction over the N classes;
+  // loads of up to 8 classes in flight before their FMAs.  CTAs are taken from the front of the grid.
+  if (l > 0) {
+    const DevLayer& p = a.ly[l - 1];
+    for (int64_t e = (int64_t)blockIdx.x * NT + threadIdx.x; e < (int64_t)B * K; e += (int64_t)G * NT) {
+      const int b = (int)(e / K), k = (int)(e - (int64_t)b * K);
+      const float xv = __ldcg(p.act + e), fv = __ldcg(p.dsf + e);
+      float de = 0.f, ds = 0.f;
+      for (int n0 = 0; n0 < N; n0 += 8) {
+        float ge[8], gs[8], mm[8], vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int n = n0 + u;
+          const bool ok = n < N;
+          ge[u] = ok ? __ldcg(y.dE + (int64_t)b * N + n) : 0.f;
+          gs[u] = ok ? __ldcg(y.dS + (int64_t)b * N + n) : 0.f;
+          mm[u] = ok ? __ldcg(M + (int64_t)n * K + k) : 0.f;
+          vv[u] = ok ? __ldcg(V + (int64_t)n * K + k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { de = fmaf(ge[u], mm[u], de); ds = fmaf(gs[u], vv[u], ds); }
+      }
+      const float dx = xv > 0.f ? fmaf(2.0f * xv, ds, de) : 0.f;
+      p.dE[e] = dx;
+      p.dS[e] = dx * fv;
+    }
+  }
+  // dM = dE^T x, dV = dS^T x^2 (+ the bias column sums): CTAs from the BACK of the grid take 32-wide chunks of k.  dE, dS
+  // and the chunk's columns of x are staged in shared memory (compact loops: this code runs once per launch on a few
+  // CTAs, so its instruction footprint matters more than its issue rate); one (class, k) output per thread, the batch
+  // summed in order.
+  constexpr int NW = NT / 32;
+  const int nchunk = (K + 31) / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* gE = sm;                    // [B][N]
+  float* gS = gE + B * N;            // [B][N]
+  float* xs = gS + B * N;            // [B][32]
+  for (int chunk = G - 1 - (int)blockIdx.x; chunk < nchunk; chunk += G) {
+    __syncthreads();
+    for (int i0 = threadIdx.x; i0 < B * N; i0 += NT * 4) {
+      float te[4], ts[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * NT;
+        te[q] = i < B * N ? __ldcg(y.dE + i) : 0.f;
+        ts[q] = i < B * N ? __ldcg(y.dS + i) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q * NT;
+        if (i < B * N) { gE[i] = te[q]; gS[i] = ts[q]; }
+      }
+    }
+    const int k = chunk * 32 + lane;
+    for (int b0 = warp; b0 < B; b0 += NW * 4) {
+      float xv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = b0 + q * NW;
+        xv[q] = (k < K && b < B) ? (l == 0 ? __ldg(xin + (int64_t)b * K + k) : __ldcg(xin + (int64_t)b * K + k)) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int b = b0 + q * NW;
+        if (b < B) xs[b * 32 + lane] = xv[q];
+      }
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 2 * N * 32; o += NT) {
+      const int ln = o & 31, j = o >> 5;      // j in [0, 2N): dM rows then dV rows
+      const bool sq = j >= N;
+      const float* src = (sq ? gS : gE) + (sq ? j - N : j);
+      float a0 = 0.f, a1 = 0.f;
+      int b = 0;
+#pragma unroll 4
+      for (; b + 1 < B; b += 2) {
+        const float x0 = xs[b * 32 + ln], x1 = xs[(b + 1) * 32 + ln];
+        a0 = fmaf(src[b * N], sq ? x0 * x0 : x0, a0);
+        a1 = fmaf(src[(b + 1) * N], sq ? x1 * x1 : x1, a1);
+      }
+      if (b < B) { const float x0 = xs[b * 32 + ln]; a0 = fmaf(src[b * N], sq ? x0 * x0 : x0, a0); }
+      const int kk = chunk * 32 + ln;
+      if (kk < K) (sq ? y.dV : y.dM)[(int64_t)(sq ? j - N : j) * K + kk] = a0 + a1;
+    }
+    if (chunk == nchunk - 1) {   // bias column sums over the batch: a warp per column, lanes over b, fixed shuffle tree
+      for (int n = warp; n < 2 * N; n += NW) {
+        const float* src = n < N ? gE : gS;
+        const int c = n < N ? n : n - N;
+        float s_ = 0.f;
+        for (int b = lane; b < B; b += 32) s_ += src[b * N + c];
+        s_ = warp_sum(s_);
+        if (lane == 0) y.colsum[n] = s_;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_constant__ DevStep a) {
   extern __shared__ __align__(16) float sm[];
   cg::grid_group grid = cg::this_grid();
@@ -975,6 +1210,13 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
   float* W = sm + kWOff;
   int slot = 0;
   stamp(a, slot);
+  // Update overlap: with forward+backward and update in one launch, layers >= 1 are updated during layer 0's dW phase by
+  // the CTAs that have no dW tile there (their raw gradients are final after phase B_1), if enough CTAs are idle.
+  int u_first = 0;
+  if (a.overlap_update && (a.phases & 3) == 3 && a.L >= 2) {
+    const int nw0 = a.ly[0].w_rtiles * a.ly[0].w_ctiles;
+    if (nw0 < G && (G - nw0) * 8 >= G) u_first = 1;
+  }
   if (a.phases & 1) {
     // W tiles of this CTA's first item of a backward phase (dX items come first, then dW items)
     auto bwd_stage_w = [&](int l) {
@@ -985,20 +1227,22 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
       if (item < nx + y.w_rtiles * y.w_ctiles) { dw_stage_w(a, l, item - nx, W); return true; }
       return false;
     };
+    const int Lg = a.small_last ? a.L - 1 : a.L;   // layers that go through the generic tiled phases
+    if (a.small_last) last_moments(a);
     bool staged = false;
-    if ((int)blockIdx.x < a.ly[0].f_ntiles * a.ly[0].f_splits) { fwd_stage_w(a, 0, blockIdx.x, W); staged = true; }
+    if (Lg > 0 && (int)blockIdx.x < a.ly[0].f_ntiles * a.ly[0].f_splits) { fwd_stage_w(a, 0, blockIdx.x, W); staged = true; }
     for (int rep = 0; rep < ((a.phases & 4) ? 2 : 1); ++rep)   // phases bit 2: debug, run the forward twice
-    for (int l = 0; l < a.L; ++l) {
+    for (int l = 0; l < Lg; ++l) {
       const DevLayer& y = a.ly[l];
       for (int item = blockIdx.x; item < y.f_ntiles * y.f_splits; item += G)
         fwd_item(a, l, item, sm, staged && item == (int)blockIdx.x);
       __syncthreads();
       // next GEMM phase's weight-side tiles, staged while the other CTAs finish
-      if (l + 1 < a.L) {
+      if (l + 1 < Lg) {
         staged = (int)blockIdx.x < a.ly[l + 1].f_ntiles * a.ly[l + 1].f_splits;
         if (staged) fwd_stage_w(a, l + 1, blockIdx.x, W);
       } else {
-        staged = bwd_stage_w(a.L - 1);
+        staged = a.small_last ? (Lg > 0 ? bwd_stage_w(Lg - 1) : false) : bwd_stage_w(a.L - 1);
       }
       stamp(a, slot);
       grid.sync();
@@ -1009,7 +1253,18 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
       grid.sync();
       stamp(a, slot);
     }
-    for (int l = a.L - 1; l >= 0; --l) {
+    if (a.small_last) {
+      if (Lg == 0) grid.sync();   // single-layer network: mv_last must be complete
+      last_fwd_loss(a, step, sm);
+      stamp(a, slot);
+      grid.sync();
+      stamp(a, slot);
+      last_bwd(a, sm);
+      stamp(a, slot);
+      if (Lg > 0 || (a.phases & 2)) grid.sync();
+      stamp(a, slot);
+    }
+    for (int l = Lg - 1; l >= 0; --l) {
       const DevLayer& y = a.ly[l];
       const int nx = l > 0 ? y.x_ctiles * y.x_splits : 0;
       const int nw = y.w_rtiles * y.w_ctiles;
@@ -1020,6 +1275,15 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
       }
       __syncthreads();
       staged = l > 0 ? bwd_stage_w(l - 1) : false;
+      if (l == 0 && u_first == 1) {
+        // the raw gradients of layers >= 1 are complete: the CTAs without a layer-0 dW tile update those layers now
+        const int busy = min(G, nw);
+        if ((int)blockIdx.x >= busy) {
+          update_layers(a, step, 1, a.L, blockIdx.x - busy, G - busy, sm);
+        } else if (threadIdx.x == 0) {
+          for (int ll = 1; ll < a.L; ++ll) a.kl_part[(int64_t)ll * G + blockIdx.x] = 0.0;
+        }
+      }
       stamp(a, slot);
       if (l > 0 || (a.phases & 2)) grid.sync();
       stamp(a, slot);
@@ -1031,7 +1295,10 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
       }
     }
   }
-  if (a.phases & 2) update_phase(a, step, sm);
+  if (a.phases & 2) {
+    update_layers(a, step, 0, u_first ? 1 : a.L, blockIdx.x, G, sm);   // layers >= 1 were done during B_0 if u_first
+    finish_step(a, step, sm);
+  }
   stamp(a, slot);
 }
 
@@ -1227,6 +1494,11 @@ int plan_step_uncached(const lbbnn_step* S, int G, HostPlan* out) {
   LBBNN_REQUIRE((size_t)cdiv(B, std::min(B, G)) * d.ly[d.L - 1].N + 64 <= (size_t)kWOff, "too many classes for the loss phase");
   smem = kSmemCap;
   d.nll_ctas = std::min(B, G);   // loss epilogue: ceil(B / nll_ctas) rows per CTA, one warp per row
+  {
+    const int Nl = d.ly[d.L - 1].N;
+    d.small_last = (Nl <= 32 && cdiv(B, d.nll_ctas) <= NT / 32 && 2 * B * Nl + 32 * B <= kWOff &&
+                    !getenv("LBBNN_STEP_GENERIC_HEAD")) ? 1 : 0;
+  }
   LBBNN_REQUIRE(d.nll_ctas <= G, "batch too large for the loss phase");
   P.smem = smem;
   // workspace: [raw: dM,dV,colsum per layer | act,dsf,dE,dS per layer | partials | kl partials | nll partials | ticket]
@@ -1240,6 +1512,7 @@ int plan_step_uncached(const lbbnn_step* S, int G, HostPlan* out) {
   off = align256(off * 4);
   for (int l = 0; l < d.L; ++l) off += 4 * align256((size_t)B * d.ly[l].N * 4);
   off += align256(part_floats * 4);
+  off += align256((size_t)2 * d.ly[d.L - 1].N * d.ly[d.L - 1].K * 4);   // mv_last
   off += align256((size_t)d.L * G * sizeof(double));
   off += align256((size_t)G * sizeof(float));
   off += 256;
@@ -1268,6 +1541,7 @@ void bind_workspace(HostPlan& P, char* ws, int G) {
   }
   d.part = (float*)(ws + off);
   off = P.total - 256 - align256((size_t)G * sizeof(float)) - align256((size_t)d.L * G * sizeof(double));
+  d.mv_last = (float*)(ws + off - align256((size_t)2 * d.ly[d.L - 1].N * d.ly[d.L - 1].K * 4));
   d.kl_part = (double*)(ws + off); off += align256((size_t)d.L * G * sizeof(double));
   d.nll_part = (float*)(ws + off); off += align256((size_t)G * sizeof(float));
   d.ticket = (unsigned*)(ws + off);
@@ -1332,6 +1606,7 @@ extern "C" int lbbnn_lrt_step_f32(const lbbnn_step* S, int phases, void* ws, siz
   d.lr = S->lr; d.b1 = S->beta1; d.b2 = S->beta2; d.eps = S->eps; d.klg = S->kl_scale;
   d.stats = S->stats;
   d.prof = g_step_prof;
+  d.overlap_update = getenv("LBBNN_STEP_OVERLAP_UPDATE") ? 1 : 0;
   d.prof_cta = g_step_prof_cta;
   void* args[] = {(void*)&d};
   LBBNN_CUDA(cudaLaunchCooperativeKernel((const void*)lrt_step_kernel, dim3((unsigned)G), dim3(NT), args, kSmemCap,

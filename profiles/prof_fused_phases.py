@@ -48,6 +48,14 @@ for l in (2, 1, 0):
     if l == 1:
         names += [f"Xe{l}", f"Xe{l} barrier"]
 names += ["U"]
+if len(names) != len(acc):     # small-classifier head: the last layer has its own forward+loss and backward phases
+    names = []
+    for l in range(2):
+        names += [f"F{l} items", f"F{l} barrier", f"Fe{l}", f"Fe{l} barrier"]
+    names += ["FL (last fwd+loss)", "FL barrier", "BL (last bwd)", "BL barrier", "B1 items", "B1 barrier", "Xe1", "Xe1 barrier",
+              "B0 items", "B0 barrier", "U"]
+if len(names) != len(acc):
+    names = [f"interval {i}" for i in range(len(acc))]
 mhz = 1965.0
 tot = 0
 for nm, c in zip(names, acc.tolist()):
