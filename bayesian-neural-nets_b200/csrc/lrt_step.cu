@@ -831,17 +831,16 @@ __device__ __forceinline__ void stq4(float* p, const Q4& q, int cnt, bool vec) {
 }
 
 // one layer's weights: chain rule + KL + Adam over quads; VEC = all quads are full and 16-byte aligned
+// chain rule + KL + Adam of quad q (4 consecutive weights) of one layer; returns the quad's KL contribution
 template <bool VEC, bool REF>
-__device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer& y, float step_size, float inv_bc2_sqrt,
-                                                int cta, int ncta) {
+__device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y, float step_size, float inv_bc2_sqrt, int64_t q) {
   const lbbnn_priors P = y.pri;
   const float klg = a.klg;
   const float inv_sp2 = 1.0f / (P.sigma * P.sigma);
   const float inv_omp = 1.0f / (1.0f - P.alpha), inv_ap = 1.0f / P.alpha;
   const int64_t n = (int64_t)y.N * y.K;
-  const int64_t nq = (n + 3) >> 2;
   float kl = 0.f;
-  for (int64_t q = (int64_t)cta * NT + threadIdx.x; q < nq; q += (int64_t)ncta * NT) {
+  {
     const int64_t e0 = q * 4;
     const int cnt = VEC ? 4 : (int)min((int64_t)4, n - e0);
     Q4 mu = ldq4<false>(a.flat + y.off_mu + e0, cnt, VEC), rho = ldq4<false>(a.flat + y.off_rho + e0, cnt, VEC);
@@ -897,11 +896,12 @@ __device__ __forceinline__ float update_weights(const DevStep& a, const DevLayer
 }
 
 // Chain rule + KL + Adam of layers [l0, l1) by the CTAs [cta0, cta0 + ncta) of the grid (every CTA of that range
-// calls this; `cta` = its index in the range).  The first CTA of the range also updates the biases.  Each CTA leaves
-// its KL partial of every layer in kl_part[l][blockIdx.x].
+// calls this; `cta` = its index in the range).  The quads of all those layers form ONE index space that is dealt
+// out round-robin, so every thread gets the same number of quads whatever the layer sizes; one CTA per layer also
+// updates its biases.  Each CTA leaves its KL partial of every layer in kl_part[l][blockIdx.x].
 __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, int cta, int ncta, float* __restrict__ sm) {
   __shared__ float coef[2];
-  double* dred = reinterpret_cast<double*>(sm);
+  constexpr int NW = NT / 32;
   __syncthreads();
   if (threadIdx.x == 0) {
     const double t = (double)(step + 1);
@@ -911,37 +911,67 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
   __syncthreads();
   const float step_size = coef[0], bc2_sqrt = coef[1];  // bc2_sqrt holds 1/sqrt(1 - beta2^t)
   const float klg = a.klg;
-  for (int l = l0; l < l1; ++l) {
+  float kl[kMaxL];
+#pragma unroll
+  for (int l = 0; l < kMaxL; ++l) kl[l] = 0.f;
+  int64_t total = 0;
+  for (int l = l0; l < l1; ++l) total += ((int64_t)a.ly[l].N * a.ly[l].K + 3) >> 2;
+  for (int64_t g = (int64_t)cta * NT + threadIdx.x; g < total; g += (int64_t)ncta * NT) {
+    int l = l0;
+    int64_t q = g;
+    for (;; ++l) {
+      const int64_t nq = ((int64_t)a.ly[l].N * a.ly[l].K + 3) >> 2;
+      if (q < nq) break;
+      q -= nq;
+    }
     const DevLayer& y = a.ly[l];
-    const lbbnn_priors P = y.pri;
     const bool vec = (((int64_t)y.N * y.K) % 4 == 0);
     const bool ref = y.var_mode == LBBNN_VAR_REFERENCE;
-    float kl;
-    if (vec) kl = ref ? update_weights<true, true>(a, y, step_size, bc2_sqrt, cta, ncta) : update_weights<true, false>(a, y, step_size, bc2_sqrt, cta, ncta);
-    else kl = ref ? update_weights<false, true>(a, y, step_size, bc2_sqrt, cta, ncta) : update_weights<false, false>(a, y, step_size, bc2_sqrt, cta, ncta);
-    // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); one CTA per layer
-    if (cta == (a.L - 1 - l) % ncta) {
-      const float inv = 1.0f / (P.bias_sigma * P.bias_sigma);
-      for (int i = threadIdx.x; i < y.N; i += NT) {
-        float bm = a.flat[y.off_bmu + i], br = a.flat[y.off_brho + i];
-        const float sb = sigma_of(br);
-        float dbm = __ldcg(y.colsum + i), dsb = 2.0f * sb * __ldcg(y.colsum + y.N + i);
-        kl += kl_bias_elem(bm, sb, P);
-        dbm += klg * (bm - P.bias_mu) * inv;
-        dsb += klg * (sb * inv - 1.0f / sb);
-        const float dbr = dsb * dsigma_drho(br);
-        if (a.grad) { a.grad[y.off_bmu + i] = dbm; a.grad[y.off_brho + i] = dbr; }
-        float mm0 = a.m[y.off_bmu + i], vv0 = a.v[y.off_bmu + i], mm1 = a.m[y.off_brho + i], vv1 = a.v[y.off_brho + i];
-        adam1(bm, dbm, mm0, vv0, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
-        adam1(br, dbr, mm1, vv1, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
-        a.flat[y.off_bmu + i] = bm; a.flat[y.off_brho + i] = br;
-        a.m[y.off_bmu + i] = mm0; a.v[y.off_bmu + i] = vv0; a.m[y.off_brho + i] = mm1; a.v[y.off_brho + i] = vv1;
-      }
-    }
-    const double tot = block_sum((double)kl, dred);
-    if (threadIdx.x == 0) a.kl_part[(int64_t)l * gridDim.x + blockIdx.x] = tot;
-    __syncthreads();
+    float k_;
+    if (vec) k_ = ref ? update_quad<true, true>(a, y, step_size, bc2_sqrt, q) : update_quad<true, false>(a, y, step_size, bc2_sqrt, q);
+    else k_ = ref ? update_quad<false, true>(a, y, step_size, bc2_sqrt, q) : update_quad<false, false>(a, y, step_size, bc2_sqrt, q);
+#pragma unroll
+    for (int j = 0; j < kMaxL; ++j) kl[j] += (j == l) ? k_ : 0.f;
   }
+  // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); one CTA per layer
+  for (int l = l0; l < l1; ++l) {
+    if (cta != (a.L - 1 - l) % ncta) continue;
+    const DevLayer& y = a.ly[l];
+    const lbbnn_priors P = y.pri;
+    const float inv = 1.0f / (P.bias_sigma * P.bias_sigma);
+    float kb = 0.f;
+    for (int i = threadIdx.x; i < y.N; i += NT) {
+      float bm = a.flat[y.off_bmu + i], br = a.flat[y.off_brho + i];
+      const float sb = sigma_of(br);
+      float dbm = __ldcg(y.colsum + i), dsb = 2.0f * sb * __ldcg(y.colsum + y.N + i);
+      kb += kl_bias_elem(bm, sb, P);
+      dbm += klg * (bm - P.bias_mu) * inv;
+      dsb += klg * (sb * inv - 1.0f / sb);
+      const float dbr = dsb * dsigma_drho(br);
+      if (a.grad) { a.grad[y.off_bmu + i] = dbm; a.grad[y.off_brho + i] = dbr; }
+      float mm0 = a.m[y.off_bmu + i], vv0 = a.v[y.off_bmu + i], mm1 = a.m[y.off_brho + i], vv1 = a.v[y.off_brho + i];
+      adam1(bm, dbm, mm0, vv0, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
+      adam1(br, dbr, mm1, vv1, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
+      a.flat[y.off_bmu + i] = bm; a.flat[y.off_brho + i] = br;
+      a.m[y.off_bmu + i] = mm0; a.v[y.off_bmu + i] = vv0; a.m[y.off_brho + i] = mm1; a.v[y.off_brho + i] = vv1;
+    }
+#pragma unroll
+    for (int j = 0; j < kMaxL; ++j) kl[j] += (j == l) ? kb : 0.f;
+  }
+  // per-layer KL partials of this CTA: warp shuffles, then the warps in order (one barrier for all layers)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < kMaxL; ++j) {
+    const float w = warp_sum(kl[j]);
+    if (lane == 0) sm[warp * kMaxL + j] = w;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x >= l0 && (int)threadIdx.x < l1) {
+    double tot = 0.0;
+    for (int w = 0; w < NW; ++w) tot += (double)sm[w * kMaxL + threadIdx.x];
+    a.kl_part[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = tot;
+  }
+  __syncthreads();
 }
 
 // The last CTA to arrive sums the per-CTA partials in a fixed order (deterministic) and bumps the step counter.
