@@ -102,11 +102,10 @@ class BayesianLinear(nn.Module):
     def _z0(self, eps):
         return self.q0_mean + self.q0_log_var.exp().sqrt() * eps       # MNF:183-185
 
-    def forward(self, input, sample=False, calculate_log_probs=False, noise=None):
-        nz = noise or {}
+    def _prepare(self, want_kl, nz):
+        """Everything of forward() that does not depend on the input batch: the z flow on the live rows, and (training /
+        calculate_log_probs) the whole KL branch with the auxiliary r flow.  Returns (z_k, kl or 0)."""
         dev = self.weight_mu.device
-        sample_branch = self.training or sample
-        want_kl = self.training or calculate_log_probs
         D = self.in_features
         inj = "eps_z" in nz
         # every z-flow evaluation of this call as rows of ONE launch: [activation row (last batch row), KL row]
@@ -120,13 +119,9 @@ class BayesianLinear(nn.Module):
         masks = [torch.cat([r[t] for r in mask_rows], 0) for t in range(len(mask_rows[0]))] if inj else None
         zs, logdets = self.z_flow(z0, masks)
         z_k = zs[0]
-        self._calls += 1
-        self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
-        act, _ = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z_k,
-                                    nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key)
         if not want_kl:
-            self.kl = 0
-            return act
+            self.z = z0[:1]
+            return z_k, 0
         self.z = z0[1:2]                                                # sample_z() overwrites self.z with (1,in)
         z2 = zs[1]
         log_det_q = logdets if logdets.dim() == 0 else logdets[1]       # IAF kind: one scalar over everything
@@ -143,8 +138,19 @@ class BayesianLinear(nn.Module):
         log_var_r = self.r0_b2 * a_r.mean()
         z_b, log_det_r = self.r_flow(z2, nz.get("r_masks"))
         log_rb = (-0.5 * math.log(math.pi) - 0.5 * log_var_r - 0.5 * ((z_b[-1] - mean_r) ** 2 / log_var_r.exp())).sum()
-        self.kl = kl_wb + log_q - (log_det_r + log_rb)
+        return z_k, kl_wb + log_q - (log_det_r + log_rb)
+
+    def _activation(self, input, z_k, sample_branch, nz):
+        self._calls += 1
+        self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
+        act, _ = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z_k,
+                                    nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key)
         return act
+
+    def forward(self, input, sample=False, calculate_log_probs=False, noise=None):
+        nz = noise or {}
+        z_k, self.kl = self._prepare(self.training or calculate_log_probs, nz)
+        return self._activation(input, z_k, self.training or sample, nz)
 
 
 class BayesianNetwork(nn.Module):
@@ -156,16 +162,35 @@ class BayesianNetwork(nn.Module):
         for n, (i, o) in enumerate(zip(sizes[:-1], sizes[1:]), 1):
             setattr(self, f"l{n}", BayesianLinear(i, o, num_transforms=num_transforms, **layer_kwargs))
         self._names = [f"l{n}" for n in range(1, len(sizes))]
+        self._streams = None
 
     @property
     def layers(self):
         return [getattr(self, n) for n in self._names]
 
-    def forward(self, x, sample=False, noises=None):
+    def forward(self, x, sample=False, noises=None, calculate_log_probs=False):
+        """The flows and the KL branch of a layer depend on parameters and noise only, never on the activations: they
+        are issued for all layers first, each on its own CUDA stream (concurrent GEMV chains instead of one after the
+        other; inside a captured graph they become parallel branches), then the LRT layers run on the caller's stream."""
         x = x.view(-1, self.sizes[0])
         ls = self.layers
-        for i, l in enumerate(ls):
-            x = l.forward(x, sample, noise=None if noises is None else noises[i])
+        nzs = [(None if noises is None else noises[i]) or {} for i in range(len(ls))]
+        cur = torch.cuda.current_stream()
+        if self._streams is None or self._streams[0].device != x.device:
+            self._streams = [torch.cuda.Stream(device=x.device) for _ in ls]
+        prepared = []
+        for l, s, nz in zip(ls, self._streams, nzs):
+            s.wait_stream(cur)
+            with torch.cuda.stream(s):
+                z_k, kl = l._prepare(l.training or calculate_log_probs, nz)
+            prepared.append((z_k, kl))
+        for i, (l, s, nz) in enumerate(zip(ls, self._streams, nzs)):
+            cur.wait_stream(s)
+            z_k, l.kl = prepared[i]
+            z_k.record_stream(cur)
+            if torch.is_tensor(l.kl):
+                l.kl.record_stream(cur)
+            x = l._activation(x, z_k, l.training or sample, nz)
             x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
         return x
 
