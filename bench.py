@@ -170,7 +170,7 @@ def workload_config(workload, n_gpus):
     return {"workload": f"{workload}: LRT MLP {'-'.join(map(str, sizes))}, batch {B} per GPU, "
                         f"fwd+loss+bwd+Adam, NUM_BATCHES={NUM_BATCHES}",
             "batch_per_gpu": B, "global_batch": B * n_gpus,
-            "parallelism": "single GPU" if n_gpus == 1 else f"dp{n_gpus} (NCCL all-reduce of the raw weight-moment gradients dM, dV + bias sums, then chain rule + Adam)",
+            "parallelism": "single GPU" if n_gpus == 1 else f"dp{n_gpus} (all-reduce of the raw weight-moment gradients dM, dV + bias sums, then chain rule + Adam)",
             "l2": f"inputs rotate through a pool of {POOL} distinct batches "
                   f"({POOL * B * sizes[0] * 4 / 1e6:.0f} MB > 126 MB L2); parameters are the step's own working set"}
 
@@ -475,7 +475,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": tr.h2d_bytes_per_step, "d2h_bytes_per_step": tr.d2h_bytes_per_step,
                     "ms_per_step": e2e_ms / args.steps, "api": "LRTTrainer.step_async (pipelined: stats of step i read at call i+1)",
                     "sync_api_us_per_step": e2e_sync_us},
-            "gpu_launches": tr.kernels_per_step * args.steps,
+            "gpu_launches": tr.kernels_per_step * args.steps, "allreduce": getattr(tr, "allreduce", None),
             "kernels_per_step": tr.kernels_per_step,
             "roofline": roof, "step_roofline": step_roof, "kernels": kern,
             "clocks": clocks,
