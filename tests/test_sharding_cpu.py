@@ -60,3 +60,38 @@ def test_shard_samples_partition():
             for first, c in spans:
                 assert first == pos
                 pos += c
+
+
+def _dp_worker(rank, world, port, out):
+    """The data-parallel rule of the trainers on the real objective (oracle, CPU): rows sharded, per-rank objective
+    nll(rank rows) + KL / (NUM_BATCHES * world), gradients SUM-reduced -> the single-process gradient of LRT:222-224."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    for p in (os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import cases as C
+    import lbbnn_oracle as O
+    sizes = [(24, 16), (16, 12), (12, 5)]
+    case = C.lrt_net_case(seed=21, batch=12, sizes=sizes, classes=5)
+    rows = slice(rank * 6, (rank + 1) * 6)
+    layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+    logp = O.lrt_net_forward(case["x"][rows], layers, [e[rows] for e in case["eps"]])
+    nll = torch.nn.functional.nll_loss(logp, case["y"][rows], reduction="sum")
+    kl = sum(O.lrt_kl(p) for p in layers)
+    (nll + kl / (C.NUM_BATCHES * world)).backward()
+    flat = torch.cat([v.grad.reshape(-1) for p in layers for v in p.values()])
+    dist.all_reduce(flat)
+    if rank == 0:
+        ref = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+        loss, _, _, _ = O.lrt_net_loss(case["x"], case["y"], ref, case["eps"], C.NUM_BATCHES)
+        loss.backward()
+        torch.save({"dp": flat, "single": torch.cat([v.grad.reshape(-1) for p in ref for v in p.values()])}, out)
+    dist.destroy_process_group()
+
+
+def test_dp_gradient_rule_on_the_lrt_objective_world2(tmp_path):
+    out = str(tmp_path / "dp.pt")
+    mp.spawn(_dp_worker, args=(2, 29900 + os.getpid() % 90, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert (r["dp"] - r["single"]).abs().max().item() <= 2e-6 * r["single"].abs().max().item()
