@@ -94,7 +94,7 @@ __device__ __forceinline__ float4 ld4g(const float* __restrict__ base, int row, 
 }
 
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 2) sgemm_tn_batched_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(kThreads, BN == 64 ? 3 : 2) sgemm_tn_batched_kernel(const GemmArgs a) {
   constexpr int TN = BN / 16;                  // columns per thread (8 or 4)
   constexpr int NB4 = BN * BK / 4 / kThreads;  // float4 loads of the W tile per thread (2 or 1)
   __shared__ __align__(16) float As[2][BK][BM];
@@ -147,18 +147,24 @@ __global__ void __launch_bounds__(kThreads, 2) sgemm_tn_batched_kernel(const Gem
   for (int t = 0; t < ntile; ++t) {
     const int buf = t & 1;
     if (t + 1 < ntile) gload((t + 1) * BK);   // next tile's global loads in flight during this tile's math
+    // rows ty*4..+3 and 64+ty*4..+3; columns tx*4..+3 (and BN/2 + tx*4..+3 for BN = 128): conflict-free LDS.128.
+    // The fragments of step k+1 are loaded while step k's FMAs issue (explicit register double buffering).
+    float4 fa0 = *reinterpret_cast<const float4*>(&As[buf][0][ty * 4]);
+    float4 fa1 = *reinterpret_cast<const float4*>(&As[buf][0][64 + ty * 4]);
+    float4 fb0 = *reinterpret_cast<const float4*>(&Bs[buf][0][tx * 4]);
+    float4 fb1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (TN == 8) fb1 = *reinterpret_cast<const float4*>(&Bs[buf][0][BN / 2 + tx * 4]);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      // rows ty*4..+3 and 64+ty*4..+3; columns tx*4..+3 (and BN/2 + tx*4..+3 for BN = 128): conflict-free LDS.128
-      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float av[8] = {fa0.x, fa0.y, fa0.z, fa0.w, fa1.x, fa1.y, fa1.z, fa1.w};
       float bv[TN];
-      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-      if constexpr (TN == 8) {
-        const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][BN / 2 + tx * 4]);
-        bv[TN - 4] = b1.x; bv[TN - 3] = b1.y; bv[TN - 2] = b1.z; bv[TN - 1] = b1.w;
+      bv[0] = fb0.x; bv[1] = fb0.y; bv[2] = fb0.z; bv[3] = fb0.w;
+      if constexpr (TN == 8) { bv[TN - 4] = fb1.x; bv[TN - 3] = fb1.y; bv[TN - 2] = fb1.z; bv[TN - 1] = fb1.w; }
+      if (k + 1 < BK) {
+        fa0 = *reinterpret_cast<const float4*>(&As[buf][k + 1][ty * 4]);
+        fa1 = *reinterpret_cast<const float4*>(&As[buf][k + 1][64 + ty * 4]);
+        fb0 = *reinterpret_cast<const float4*>(&Bs[buf][k + 1][tx * 4]);
+        if constexpr (TN == 8) fb1 = *reinterpret_cast<const float4*>(&Bs[buf][k + 1][BN / 2 + tx * 4]);
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i)
