@@ -228,7 +228,8 @@ def test_trainer_native_noise_changes_every_replay(lb, fused):
     assert tr.step_dev.item() == 2
 
 
-@pytest.mark.parametrize("sizes,batch", [((784, 400, 600, 10), 32), ((20, 1), 128), ((37, 23, 5), 7), ((130, 64, 64, 64, 3), 100)])
+@pytest.mark.parametrize("sizes,batch", [((784, 400, 600, 10), 32), ((20, 1), 128), ((37, 23, 5), 7), ((130, 64, 64, 64, 3), 100),
+                                         ((64, 48, 40), 9), ((100, 72), 50)])      # heads > 32 classes: the tiled last layer
 def test_fused_step_equals_per_layer_step(lb, sizes, batch):
     """The persistent step kernel and the per-layer launch sequence draw the same Philox noise and follow the same
     formulas: after 3 steps of native-noise training their parameters, Adam state and stats agree (odd shapes:
