@@ -38,6 +38,13 @@ int sm_count();
 // formulations (LBBNN-GP-MF-LRT.py:80-82,167), so fp32 rounding follows the same path.
 __device__ __forceinline__ float sigma_of(float rho) { return log1pf(expf(rho)); }
 __device__ __forceinline__ float alpha_of(float lam) { return 1.0f / (1.0f + expf(-lam)); }
+
+// x = hi + lo with hi representable in TF32 (round to nearest on the 13 dropped mantissa bits); lo = x - hi is exact
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  const uint32_t u = __float_as_uint(x);
+  hi = __uint_as_float((u + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
 // d sigma / d rho = e^rho / (1 + e^rho)
 __device__ __forceinline__ float dsigma_drho(float rho) {
   float e = expf(rho);

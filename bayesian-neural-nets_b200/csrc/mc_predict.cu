@@ -26,18 +26,21 @@ struct McSampleArgs {
   uint64_t seed, stream_base, stream_stride;   // stream of (sample, which) = stream_base + which + sample * stride
   const int64_t* first;                        // device: global index of sample 0 of this launch
   float *w, *bias;                             // (SB, n), (SB, n_bias)
+  float* w_lo;                                 // optional: w then holds the TF32-rounded value and w_lo the remainder
 };
 
 __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs a) {
   const int s = blockIdx.y;
   const uint64_t st = a.stream_base + (uint64_t)(*a.first + s) * a.stream_stride;
   float* w = a.w + (int64_t)s * a.n;
+  float* wl = a.w_lo ? a.w_lo + (int64_t)s * a.n : nullptr;
   if (blockIdx.x == 0) {
     float* bo = a.bias + (int64_t)s * a.n_bias;
     for (int64_t i = threadIdx.x; i < a.n_bias; i += blockDim.x)
       bo[i] = fmaf(sigma_of(__ldg(a.bias_rho + i)), philox_normal1(a.seed, st + 2, (uint64_t)i), __ldg(a.bias_mu + i));
   }
-  const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w);
+  const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w) &&
+                   (!a.w_lo || aligned16(a.w_lo));
   const int64_t nq = ceil_div(a.n, 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
@@ -61,12 +64,24 @@ __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs 
       const float g = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;      // Bernoulli(alpha).sample() (MF:113)
       o[j] = g * fmaf(sigma_of(rho[j]), ep[j], mu[j]);            // gamma * (mu + sigma eps)   (MF:232-233)
     }
+    float lo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (wl) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float full = o[j];
+        tf32_split(full, o[j], lo[j]);
+      }
+    }
     if (vec) {
       *reinterpret_cast<float4*>(w + e0) = make_float4(o[0], o[1], o[2], o[3]);
+      if (wl) *reinterpret_cast<float4*>(wl + e0) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     } else {
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (e0 + j < a.n) w[e0 + j] = o[j];
+        if (e0 + j < a.n) {
+          w[e0 + j] = o[j];
+          if (wl) wl[e0 + j] = lo[j];
+        }
     }
   }
 }
@@ -241,20 +256,32 @@ __global__ void __launch_bounds__(kThreads) mc_accumulate_batched_kernel(const f
 
 using namespace lbbnn;
 
-extern "C" int lbbnn_mc_sample(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
-                               uint64_t stream_base, uint64_t stream_stride, float* w, float* bias, lbbnn_stream s) {
+static int mc_sample_launch(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                            uint64_t stream_base, uint64_t stream_stride, float* w, float* w_lo, float* bias, lbbnn_stream s) {
   LBBNN_REQUIRE(L && L->weight_mu && L->weight_rho && L->lambdal && L->bias_mu && L->bias_rho, "layer has NULL parameters");
   LBBNN_REQUIRE(n_samples > 0 && n_samples <= 65535 && first_sample_dev && w && bias, "bad argument");
   McSampleArgs a;
   a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.bias_mu = L->bias_mu; a.bias_rho = L->bias_rho;
   a.n = L->in_features * L->out_features; a.n_bias = L->out_features;
   a.seed = seed; a.stream_base = stream_base; a.stream_stride = stream_stride; a.first = first_sample_dev;
-  a.w = w; a.bias = bias;
+  a.w = w; a.bias = bias; a.w_lo = w_lo;
   int64_t blocks = ceil_div(ceil_div(a.n, 4), kThreads);
   const int64_t cap = std::max<int64_t>(1, 8LL * sm_count() / n_samples);
   if (blocks > cap) blocks = cap;
   mc_sample_kernel<<<dim3((unsigned)blocks, (unsigned)n_samples), kThreads, 0, (cudaStream_t)s>>>(a);
   return check_launch("mc_sample");
+}
+
+extern "C" int lbbnn_mc_sample(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                               uint64_t stream_base, uint64_t stream_stride, float* w, float* bias, lbbnn_stream s) {
+  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w, nullptr, bias, s);
+}
+
+extern "C" int lbbnn_mc_sample_split(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                                     uint64_t stream_base, uint64_t stream_stride, float* w_hi, float* w_lo, float* bias,
+                                     lbbnn_stream s) {
+  LBBNN_REQUIRE(w_lo, "bad argument");
+  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w_hi, w_lo, bias, s);
 }
 
 extern "C" int lbbnn_linear_f32_batched(const float* x, int64_t x_stride, const float* W, const float* bias, int n_samples,

@@ -360,10 +360,14 @@ class MCPredictor:
 
     NSTREAMS = 4   # Philox streams per (sample, layer): gamma u, eps_w, eps_b, spare
 
-    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8):
+    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8, gemm="auto"):
         """samples_per_launch: weight samples pushed through every kernel of the loop together (csrc/mc_predict.cu);
-        1 = the one-sample kernels.  Results do not depend on it: every sample draws from streams keyed by its index."""
+        1 = the one-sample kernels.  Results do not depend on it: every sample draws from streams keyed by its index.
+        gemm: "simt" = fp32 CUDA-core GEMMs; "tc" = every eligible leading layer on the tensor cores at fp32 accuracy
+        (3xTF32 on tcgen05, csrc/tc_gemm_tf32.cu); "auto" = tensor cores for the leading layers at least 64 wide."""
         K.require_device()
+        if gemm not in ("auto", "simt", "tc"):
+            raise ValueError(f"gemm must be 'auto', 'simt' or 'tc', got {gemm!r}")
         self.net, self.layers, self.B = net, list(net.layers), int(batch)
         dev = self.layers[0].weight_mu.device
         self.device = dev
@@ -376,6 +380,21 @@ class MCPredictor:
         self.w = [torch.zeros(SB, o, i, **f32) for i, o in sizes]
         self.b = [torch.zeros(SB, o, **f32) for _, o in sizes]
         self.h = [torch.zeros(SB, self.B, o, **f32) for _, o in sizes]
+        # leading layers that run as 3xTF32 tensor-core GEMMs: operands travel as (hi, lo) pairs; a layer feeding another
+        # tensor-core layer writes its activations as (batch, SB * out) so the next one reads them as a strided batch
+        self.n_tc = 0
+        if SB > 1 and gemm != "simt":
+            for i, (k, o) in enumerate(sizes):
+                ok = k % 4 == 0 and (i == 0 or sizes[i - 1][1] % 4 == 0) and (gemm == "tc" or o >= 64)
+                if not ok:
+                    break
+                self.n_tc = i + 1
+        if self.n_tc:
+            self.x_lo = torch.zeros_like(self.x)
+            self.x_hi = torch.zeros_like(self.x)
+            self.w_lo = [torch.zeros_like(self.w[i]) for i in range(self.n_tc)]
+            self.h_hi = [torch.zeros(self.B, SB * sizes[i][1], **f32) for i in range(self.n_tc - 1)]
+            self.h_lo = [torch.zeros_like(t) for t in self.h_hi]
         C_ = sizes[-1][1]
         self.sum_logp = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
         self.sum_prob = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
@@ -413,6 +432,10 @@ class MCPredictor:
         h, hs = self.x, 0
         for i, l in enumerate(self.layers):
             desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+            if i < self.n_tc:
+                self._enqueue_tc_layer(i, l, desc, n, stride, st)
+                h, hs = self.h[i], self.B * l.out_features
+                continue
             K.check(K.lib.lbbnn_mc_sample(desc, n, K.ptr(self.counter, torch.int64), self.seed & (2 ** 64 - 1),
                                           i * self.NSTREAMS, stride, K.ptr(self.w[i]), K.ptr(self.b[i]), st))
             K.check(K.lib.lbbnn_linear_f32_batched(K.ptr(h), hs, K.ptr(self.w[i]), K.ptr(self.b[i]), n, self.B,
@@ -422,7 +445,35 @@ class MCPredictor:
         K.check(K.lib.lbbnn_mc_accumulate_batched(K.ptr(h), n, self.B, self.layers[-1].out_features,
                                                   self.sum_logp.data_ptr(), self.sum_prob.data_ptr(),
                                                   K.ptr(self.counter, torch.int64), st))
-        self.kernels_per_launch = 2 * L + 1
+        self.kernels_per_launch = 2 * L + 1 + (n - 1 if self.n_tc == 1 else 0)
+
+    def _enqueue_tc_layer(self, i, l, desc, n, stride, st):
+        L, SB, B = len(self.layers), self.SB, self.B
+        k, o = l.in_features, l.out_features
+        K.check(K.lib.lbbnn_mc_sample_split(desc, n, K.ptr(self.counter, torch.int64), self.seed & (2 ** 64 - 1),
+                                            i * self.NSTREAMS, stride, K.ptr(self.w[i]), K.ptr(self.w_lo[i]),
+                                            K.ptr(self.b[i]), st))
+        flags = K.FLAG_RELU if i < L - 1 else 0
+        feeds_tc = i + 1 < self.n_tc
+        if feeds_tc:      # (batch, SB * out) hi / lo for the next tensor-core layer
+            out, out_hi, out_lo, pitch, bstride = None, K.ptr(self.h_hi[i]), K.ptr(self.h_lo[i]), SB * o, o
+        else:             # (SB, batch, out) fp32 for the CUDA-core layer / the accumulation kernel
+            out, out_hi, out_lo, pitch, bstride = K.ptr(self.h[i]), None, None, o, B * o
+        if i == 0:        # all samples read the same input: ONE problem, N = n * out
+            if feeds_tc:
+                K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(self.w[i]),
+                                                     K.ptr(self.w_lo[i]), K.ptr(self.b[i]), 1, B, n * o, k, flags,
+                                                     out, out_hi, out_lo, pitch, bstride, st))
+            else:         # (SB, batch, out) wanted: one problem per sample
+                for z in range(n):
+                    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(self.w[i][z]),
+                                                         K.ptr(self.w_lo[i][z]), K.ptr(self.b[i][z]), 1, B, o, k, flags,
+                                                         K.ptr(self.h[i][z]), None, None, o, 0, st))
+        else:
+            pk = SB * k   # previous layer's row pitch; its sample z sits at column offset z * k
+            K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.h_hi[i - 1]), K.ptr(self.h_lo[i - 1]), pk, k,
+                                                 K.ptr(self.w[i]), K.ptr(self.w_lo[i]), K.ptr(self.b[i]), n, B, o, k,
+                                                 flags, out, out_hi, out_lo, pitch, bstride, st))
 
     def _enqueue_one(self):
         st = K.current_stream()
@@ -450,6 +501,9 @@ class MCPredictor:
     def run(self, x, samples, first_sample=0):
         """Accumulate `samples` weight samples with global indices first_sample.. on this rank."""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
+        if self.n_tc:
+            K.check(K.lib.lbbnn_tf32_split(K.ptr(self.x), self.x.numel(), K.ptr(self.x_hi), K.ptr(self.x_lo),
+                                           K.current_stream()))
         self.reset(first_sample)
         full, rest = divmod(int(samples), self.SB)
         for _ in range(full):

@@ -241,6 +241,25 @@ LBBNN_API int lbbnn_linear_f32_batched(const float* x, int64_t x_stride, const f
                                        lbbnn_stream s);
 LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, int64_t batch, int64_t classes,
                                           double* sum_logp, double* sum_prob, int64_t* counter, lbbnn_stream s);
+/* The F.linear of the loop (MF:255) at fp32 accuracy on the tensor cores (csrc/tc_gemm_tf32.cu): every fp32 operand is
+ * carried as hi + lo (hi = the value rounded to TF32, lo = the exact remainder) and each contraction step issues
+ * hi*hi + hi*lo + lo*hi as three tcgen05 kind::tf32 MMAs into one fp32 TMEM accumulator ("3xTF32").
+ *   tf32_split           hi / lo of n floats (the test inputs, once per batch)
+ *   mc_sample_split      = mc_sample, but the weights leave as w_hi / w_lo (w_hi + w_lo is mc_sample's w, bit for bit)
+ *   tc_linear_tf32x3     out[z][m][n] = act(sum_k a[z][m][k] w[z][n][k] + bias[z][n]),  z < batches.
+ *                        a: row m of batch z starts at a + z * a_batch_stride + m * a_row_pitch (floats, multiples of 4);
+ *                        w: (batches, N, K) contiguous; K % 4 == 0; outputs at z * out_batch_stride + m * out_row_pitch:
+ *                        `out` (fp32, may be NULL) and/or the pair out_hi / out_lo (the split the next layer consumes).
+ *                        All samples of a launch sharing one input (the first layer) = ONE problem with batches = 1 and
+ *                        N = n_samples * out_features; its (batch, n_samples * out) output is the next layer's strided a. */
+LBBNN_API int lbbnn_tf32_split(const float* x, int64_t n, float* hi, float* lo, lbbnn_stream s);
+LBBNN_API int lbbnn_mc_sample_split(const lbbnn_layer* layer, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
+                                    uint64_t stream_base, uint64_t stream_stride, float* w_hi, float* w_lo, float* bias,
+                                    lbbnn_stream s);
+LBBNN_API int lbbnn_tc_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t a_row_pitch, int64_t a_batch_stride,
+                                     const float* w_hi, const float* w_lo, const float* bias, int64_t batches, int64_t M,
+                                     int64_t N, int64_t K, int flags, float* out, float* out_hi, float* out_lo,
+                                     int64_t out_row_pitch, int64_t out_batch_stride, lbbnn_stream s);
 LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float* lambdal, const float* gamma,
                                   const float* pb, int64_t n, const lbbnn_noise* eps, int flags,
                                   const float* dw, const float* dsums,

@@ -157,8 +157,9 @@ def _oracle_mc(net_params, x, seed, samples, lb, first=0):
     return sum_logp, sum_prob
 
 
-@pytest.mark.parametrize("use_graph,spl", [(False, 1), (True, 1), (False, 5), (True, 8), (True, 16)])
-def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl):
+@pytest.mark.parametrize("use_graph,spl,gemm", [(False, 1, "simt"), (True, 1, "simt"), (False, 5, "simt"), (True, 8, "simt"),
+                                                (True, 16, "auto"), (False, 5, "tc"), (True, 8, "tc")])
+def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl, gemm):
     sizes = [(64, 48), (48, 40), (40, 10)]
     case = C.mf_net_case(seed=60, batch=50, sizes=sizes)
     rng = np.random.default_rng(1)
@@ -171,7 +172,8 @@ def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
     S = 12
-    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph, samples_per_launch=spl)
+    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph, samples_per_launch=spl, gemm=gemm)
+    assert mc.n_tc == (3 if gemm == "tc" else 0)
     mc.run(case["x"].cuda(), S)
     res = mc.result(S)
     ref_logp, ref_prob = _oracle_mc(case["layers"], case["x"], 77, S, lb)
@@ -201,13 +203,20 @@ def test_mc_predictor_batched_equals_one_sample_kernels(lb):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
     a = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=1)
-    b = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4)
+    b = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4, gemm="simt")
     a.run(case["x"].cuda(), 7, first_sample=3)
     b.run(case["x"].cuda(), 7, first_sample=3)
     assert C.rel_err(b.sum_logp, a.sum_logp) < 1e-6 and C.rel_err(b.sum_prob, a.sum_prob) < 1e-6
     assert torch.equal(a.result(7)["pred"], b.result(7)["pred"])
     # last sample of the last (partial, 3-sample) launch of b == the single sample a drew last: indices 3+6
     assert torch.equal(b.w[0][2], a.w[0][0]) and torch.equal(b.b[2][2], a.b[2][0])
+    # tensor-core (3xTF32) GEMMs for the 400- and 600-wide layers: same draws (hi + lo == the fp32 weight), fp32 accuracy
+    c = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4)
+    assert c.n_tc == 2
+    c.run(case["x"].cuda(), 7, first_sample=3)
+    assert torch.equal(c.w[0] + c.w_lo[0], b.w[0]) and torch.equal(c.w[1] + c.w_lo[1], b.w[1])
+    assert C.rel_err(c.sum_logp, a.sum_logp) < 1e-5 and C.rel_err(c.sum_prob, a.sum_prob) < 1e-5
+    assert torch.equal(a.result(7)["pred"], c.result(7)["pred"])
 
 
 

@@ -201,3 +201,79 @@ def test_tensor_core_trainer_step(use_graph, dims, B):
         for k in p:
             r = p[k].grad.double()
             assert (g[k] - r).norm() / r.norm() < 6e-2, (li, k, "vs fp32 oracle", ((g[k] - r).norm() / r.norm()).item())
+
+
+# ---- 3xTF32 linear layer (csrc/tc_gemm_tf32.cu): fp32 accuracy on tcgen05 --------------------------------------------
+# Tolerance: the same 1e-5 (max|a-b|/max|b| against an fp64 reference rounded to fp32) the CUDA-core fp32 GEMM is held
+# to -- north_star's fp32 bound.  A plain 1xTF32 product would sit near 1e-3.
+
+def _tf32_split(K, x):
+    hi, lo = torch.empty_like(x), torch.empty_like(x)
+    K.check(K.lib.lbbnn_tf32_split(K.ptr(x), x.numel(), K.ptr(hi), K.ptr(lo), K.current_stream()))
+    return hi, lo
+
+
+def test_tf32_split_is_exact(K):
+    rng = np.random.default_rng(11)
+    x = torch.from_numpy((rng.standard_normal(10007) * np.exp(rng.uniform(-20, 20, 10007))).astype(np.float32)).cuda()
+    hi, lo = _tf32_split(K, x)
+    assert torch.equal(hi + lo, x)
+    assert int((hi.view(torch.int32) & 0x1FFF).abs().max()) == 0          # hi is representable in TF32
+    assert bool(((lo.abs() <= hi.abs() * 2.0 ** -11) | (hi == 0)).all())
+
+
+@pytest.mark.parametrize("z,m,n,k,relu", [(1, 128, 128, 32, False), (1, 1000, 400, 784, True), (3, 100, 72, 200, False),
+                                          (5, 37, 600, 400, True), (2, 300, 10, 40, False), (1, 256, 1200, 64, True)])
+def test_tc_linear_tf32x3_matches_fp64(K, z, m, n, k, relu):
+    rng = np.random.default_rng(z * 1000 + m + n + k)
+    a = torch.from_numpy(rng.random((z, m, k), dtype=np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((z, n, k)) * 0.1).astype(np.float32)).cuda()
+    w = w * (torch.from_numpy(rng.random((z, n, k))).cuda() < 0.6)           # hard masks: exact zeros
+    bias = torch.from_numpy(rng.uniform(-0.2, 0.2, (z, n)).astype(np.float32)).cuda()
+    ah, al = _tf32_split(K, a)
+    wh, wl = _tf32_split(K, w)
+    out = torch.full((z, m, n), float("nan"), device="cuda")
+    oh, ol = torch.full_like(out, float("nan")), torch.full_like(out, float("nan"))
+    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(ah), K.ptr(al), k, m * k, K.ptr(wh), K.ptr(wl), K.ptr(bias), z, m, n, k,
+                                         K.FLAG_RELU if relu else 0, K.ptr(out), K.ptr(oh), K.ptr(ol), n, m * n,
+                                         K.current_stream()))
+    torch.cuda.synchronize()
+    ref = torch.einsum("zmk,znk->zmn", a.double(), w.double()) + bias.double()[:, None, :]
+    ref = torch.relu(ref) if relu else ref
+    assert C.rel_err(out, ref.float()) < 1e-5
+    assert torch.equal(oh + ol, out)
+    assert int((oh.view(torch.int32) & 0x1FFF).abs().max()) == 0
+
+
+def test_tc_linear_tf32x3_shared_input_and_strided_chain(K):
+    """The layout the MC loop uses: layer 1 = ONE problem over all samples' weights, its (batch, S*out) hi/lo output read
+    by layer 2 as a strided batch."""
+    rng = np.random.default_rng(5)
+    S, B, k0, o0, o1 = 3, 150, 64, 48, 40
+    x = torch.from_numpy(rng.random((B, k0), dtype=np.float32)).cuda()
+    w0 = torch.from_numpy((rng.standard_normal((S, o0, k0)) * 0.2).astype(np.float32)).cuda()
+    b0 = torch.from_numpy(rng.uniform(-0.2, 0.2, (S, o0)).astype(np.float32)).cuda()
+    w1 = torch.from_numpy((rng.standard_normal((S, o1, o0)) * 0.2).astype(np.float32)).cuda()
+    b1 = torch.from_numpy(rng.uniform(-0.2, 0.2, (S, o1)).astype(np.float32)).cuda()
+    xh, xl = _tf32_split(K, x)
+    w0h, w0l = _tf32_split(K, w0)
+    w1h, w1l = _tf32_split(K, w1)
+    hh, hl = torch.zeros(B, S * o0, device="cuda"), torch.zeros(B, S * o0, device="cuda")
+    st = K.current_stream()
+    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(xh), K.ptr(xl), k0, 0, K.ptr(w0h), K.ptr(w0l), K.ptr(b0), 1, B, S * o0, k0,
+                                         K.FLAG_RELU, None, K.ptr(hh), K.ptr(hl), S * o0, o0, st))
+    out = torch.zeros(S, B, o1, device="cuda")
+    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(hh), K.ptr(hl), S * o0, o0, K.ptr(w1h), K.ptr(w1l), K.ptr(b1), S, B, o1, o0,
+                                         0, K.ptr(out), None, None, o1, B * o1, st))
+    torch.cuda.synchronize()
+    h_ref = torch.relu(torch.einsum("bk,sok->sbo", x.double(), w0.double()) + b0.double()[:, None, :])
+    assert C.rel_err((hh + hl).view(B, S, o0).permute(1, 0, 2), h_ref.float()) < 1e-5
+    ref = torch.einsum("sbk,sok->sbo", h_ref, w1.double()) + b1.double()[:, None, :]
+    assert C.rel_err(out, ref.float()) < 1e-5
+
+
+def test_tc_linear_tf32x3_rejects_bad_arguments(K):
+    t = torch.zeros(128, 30, device="cuda")
+    with pytest.raises(K.LbbnnError):     # K % 4 != 0
+        K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(t), K.ptr(t), 30, 0, K.ptr(t), K.ptr(t), K.ptr(t), 1, 128, 128, 30, 0,
+                                             K.ptr(t), None, None, 128, 0, K.current_stream()))
