@@ -27,6 +27,7 @@ struct McSampleArgs {
   const int64_t* first;                        // device: global index of sample 0 of this launch
   float *w, *bias;                             // (SB, n), (SB, n_bias)
   float* w_lo;                                 // optional: w then holds the TF32-rounded value and w_lo the remainder
+  int prepared;                                // rho / lam / bias_rho already hold sigma / alpha / sigma_b (mc_prepare)
 };
 
 __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs a) {
@@ -37,7 +38,10 @@ __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs 
   if (blockIdx.x == 0) {
     float* bo = a.bias + (int64_t)s * a.n_bias;
     for (int64_t i = threadIdx.x; i < a.n_bias; i += blockDim.x)
-      bo[i] = fmaf(sigma_of(__ldg(a.bias_rho + i)), philox_normal1(a.seed, st + 2, (uint64_t)i), __ldg(a.bias_mu + i));
+    {
+      const float br = __ldg(a.bias_rho + i);
+      bo[i] = fmaf(a.prepared ? br : sigma_of(br), philox_normal1(a.seed, st + 2, (uint64_t)i), __ldg(a.bias_mu + i));
+    }
   }
   const bool vec = (a.n % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) && aligned16(a.w) &&
                    (!a.w_lo || aligned16(a.w_lo));
@@ -61,8 +65,9 @@ __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs 
     philox_normal4(a.seed, st + 1, (uint64_t)q, ep);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float g = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;      // Bernoulli(alpha).sample() (MF:113)
-      o[j] = g * fmaf(sigma_of(rho[j]), ep[j], mu[j]);            // gamma * (mu + sigma eps)   (MF:232-233)
+      const float al = a.prepared ? lam[j] : alpha_of(lam[j]), sg = a.prepared ? rho[j] : sigma_of(rho[j]);
+      const float g = u[j] < al ? 1.0f : 0.0f;                    // Bernoulli(alpha).sample() (MF:113)
+      o[j] = g * fmaf(sg, ep[j], mu[j]);                          // gamma * (mu + sigma eps)   (MF:232-233)
     }
     float lo[4] = {0.f, 0.f, 0.f, 0.f};
     if (wl) {
@@ -83,6 +88,19 @@ __global__ void __launch_bounds__(kThreads) mc_sample_kernel(const McSampleArgs 
           if (wl) wl[e0 + j] = lo[j];
         }
     }
+  }
+}
+
+// sigma = log1p(exp rho), alpha = sigmoid(lambda) once per parameter set instead of once per weight sample
+__global__ void __launch_bounds__(kThreads) mc_prepare_kernel(const float* __restrict__ rho, const float* __restrict__ lam,
+                                                              const float* __restrict__ bias_rho, int64_t n, int64_t n_bias,
+                                                              float* __restrict__ sigma, float* __restrict__ alpha,
+                                                              float* __restrict__ bias_sigma) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    sigma[i] = sigma_of(__ldg(rho + i));
+    alpha[i] = alpha_of(__ldg(lam + i));
+    if (i < n_bias) bias_sigma[i] = sigma_of(__ldg(bias_rho + i));
   }
 }
 
@@ -257,14 +275,15 @@ __global__ void __launch_bounds__(kThreads) mc_accumulate_batched_kernel(const f
 using namespace lbbnn;
 
 static int mc_sample_launch(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
-                            uint64_t stream_base, uint64_t stream_stride, float* w, float* w_lo, float* bias, lbbnn_stream s) {
+                            uint64_t stream_base, uint64_t stream_stride, float* w, float* w_lo, float* bias, int prepared,
+                            lbbnn_stream s) {
   LBBNN_REQUIRE(L && L->weight_mu && L->weight_rho && L->lambdal && L->bias_mu && L->bias_rho, "layer has NULL parameters");
   LBBNN_REQUIRE(n_samples > 0 && n_samples <= 65535 && first_sample_dev && w && bias, "bad argument");
   McSampleArgs a;
   a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.bias_mu = L->bias_mu; a.bias_rho = L->bias_rho;
   a.n = L->in_features * L->out_features; a.n_bias = L->out_features;
   a.seed = seed; a.stream_base = stream_base; a.stream_stride = stream_stride; a.first = first_sample_dev;
-  a.w = w; a.bias = bias; a.w_lo = w_lo;
+  a.w = w; a.bias = bias; a.w_lo = w_lo; a.prepared = prepared;
   int64_t blocks = ceil_div(ceil_div(a.n, 4), kThreads);
   const int64_t cap = std::max<int64_t>(1, 8LL * sm_count() / n_samples);
   if (blocks > cap) blocks = cap;
@@ -274,14 +293,24 @@ static int mc_sample_launch(const lbbnn_layer* L, int n_samples, const int64_t* 
 
 extern "C" int lbbnn_mc_sample(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
                                uint64_t stream_base, uint64_t stream_stride, float* w, float* bias, lbbnn_stream s) {
-  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w, nullptr, bias, s);
+  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w, nullptr, bias, 0, s);
 }
 
 extern "C" int lbbnn_mc_sample_split(const lbbnn_layer* L, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
-                                     uint64_t stream_base, uint64_t stream_stride, float* w_hi, float* w_lo, float* bias,
-                                     lbbnn_stream s) {
-  LBBNN_REQUIRE(w_lo, "bad argument");
-  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w_hi, w_lo, bias, s);
+                                     uint64_t stream_base, uint64_t stream_stride, int prepared, float* w_hi, float* w_lo,
+                                     float* bias, lbbnn_stream s) {
+  return mc_sample_launch(L, n_samples, first_sample_dev, seed, stream_base, stream_stride, w_hi, w_lo, bias, prepared, s);
+}
+
+extern "C" int lbbnn_mc_prepare(const lbbnn_layer* L, float* sigma, float* alpha, float* bias_sigma, lbbnn_stream s) {
+  LBBNN_REQUIRE(L && L->weight_rho && L->lambdal && L->bias_rho && sigma && alpha && bias_sigma, "NULL argument");
+  const int64_t n = L->in_features * L->out_features;
+  LBBNN_REQUIRE(n >= L->out_features, "bad shape");
+  int64_t blocks = ceil_div(n, kThreads);
+  if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+  mc_prepare_kernel<<<(unsigned)blocks, kThreads, 0, (cudaStream_t)s>>>(L->weight_rho, L->lambdal, L->bias_rho, n, L->out_features,
+                                                                      sigma, alpha, bias_sigma);
+  return check_launch("mc_prepare");
 }
 
 extern "C" int lbbnn_linear_f32_batched(const float* x, int64_t x_stride, const float* W, const float* bias, int n_samples,

@@ -4,9 +4,12 @@
 //
 // Every fp32 operand is carried as hi + lo, hi = the value rounded to TF32 (10-bit mantissa, exactly representable) and
 // lo = x - hi (exact in fp32; the tensor core keeps its top 10 mantissa bits).  Per contraction step the kernel issues
-// THREE kind::tf32 MMAs into ONE fp32 accumulator in TMEM:  A_hi W_hi + A_hi W_lo + A_lo W_hi.  The dropped lo*lo term
-// and the truncation of lo are ~2^-21 relative per product, i.e. fp32-GEMM accuracy (the parity tests hold it to the
-// same 1e-5 as the CUDA-core path), at tensor-core rate.
+// THREE kind::tf32 MMAs:  A_hi W_hi into a "main" fp32 accumulator in TMEM, A_hi W_lo + A_lo W_hi into a second, "small"
+// one; the epilogue adds the two.  The dropped lo*lo term and the truncation of lo are ~2^-21 relative per product.  The
+// tensor core truncates (rounds toward zero) when it adds into the accumulator, a bias that grows with the number of
+// accumulations into the LARGE sum -- measured 5.4e-6 of max|out| at K = 784 with all three products in one accumulator;
+// keeping the 2^-11-times-smaller cross terms out of it cuts the accumulations into the large sum (and the error) by 3x.
+// The parity tests hold the kernel to the same 1e-5 as the CUDA-core path.
 //
 // Structure = tc_gemm.cu's: persistent, one CTA per SM, warp 0 TMA producer (3-D tile loads, SWIZZLE_128B, four 16 KB
 // boxes of 128 rows x 32 fp32 per stage), warp 1 MMA issuer (M128 N128 K8), warps 2..9 epilogue (tcgen05.ld -> bias /
@@ -30,7 +33,7 @@ constexpr int kTileBytes = BM * BKE * 4;        // 16 KB per operand tile
 constexpr int kStageBytes = 4 * kTileBytes;     // A_hi, A_lo, W_hi, W_lo
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + kEpiWarps * 32;
-constexpr int kTmemCols = 256;                  // 2 accumulator stages x 128 columns
+constexpr int kTmemCols = 512;                  // 2 accumulator stages x (main + small) x 128 columns
 constexpr int EW = 16;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
 
@@ -110,7 +113,7 @@ tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + as * 128;
+        const uint32_t d = tmem_base + as * 256, dsm = d + 128;   // main / small accumulators
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -120,9 +123,10 @@ tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
 #pragma unroll
           for (int k = 0; k < BKE / UMMA_K; ++k) {
             const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);   // 32 B per step inside the swizzle row
-            umma_tf32(d, al + koff, wh + koff, (kb | k) ? 1u : 0u);    // small terms first
-            umma_tf32(d, ah + koff, wl + koff, 1u);
-            umma_tf32(d, ah + koff, wh + koff, 1u);
+            const uint32_t acc = (kb | k) ? 1u : 0u;
+            umma_tf32(dsm, al + koff, wh + koff, acc);
+            umma_tf32(dsm, ah + koff, wl + koff, 1u);
+            umma_tf32(d, ah + koff, wh + koff, acc);
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -140,18 +144,19 @@ tc_linear_tf32x3_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_c
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
-      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 128 + half * 64;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
       const float* bias = epi.bias + (int64_t)z * N;
 #pragma unroll 1
       for (int c = 0; c < 64 / EW; ++c) {
-        float v[EW];
+        float v[EW], sm[EW];
         tmem_ld16(tbase + c * EW, v);
+        tmem_ld16(tbase + 128 + c * EW, sm);
         const int64_t col0 = n0 + half * 64 + c * EW;
         if (row < M && col0 < N) {
           float hi[EW], lo[EW];
 #pragma unroll
           for (int j = 0; j < EW; ++j) {
-            float o = v[j] + (col0 + j < N ? __ldg(bias + col0 + j) : 0.f);
+            float o = (v[j] + sm[j]) + (col0 + j < N ? __ldg(bias + col0 + j) : 0.f);
             if (epi.relu) o = fmaxf(o, 0.f);
             v[j] = o;
             tf32_split(o, hi[j], lo[j]);

@@ -134,7 +134,8 @@ SIGNATURES = {
     "lbbnn_linear_f32_batched": (_INT, [_P, _I64, _P, _P, _INT, _I64, _I64, _I64, _INT, _P, _P]),
     "lbbnn_mc_accumulate_batched": (_INT, [_P, _INT, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_tf32_split": (_INT, [_P, _I64, _P, _P, _P]),
-    "lbbnn_mc_sample_split": (_INT, [C.POINTER(Layer), _INT, _P, _U64, _U64, _U64, _P, _P, _P, _P]),
+    "lbbnn_mc_prepare": (_INT, [C.POINTER(Layer), _P, _P, _P, _P]),
+    "lbbnn_mc_sample_split": (_INT, [C.POINTER(Layer), _INT, _P, _U64, _U64, _U64, _INT, _P, _P, _P, _P]),
     "lbbnn_tc_linear_tf32x3": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P,
                                       _I64, _I64, _P]),
     "lbbnn_mf_sample_bwd": (_INT, [_P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _P, _P, _P,

@@ -347,6 +347,31 @@ class SimStudyNetwork(nn.Module):
         return loss, log_prior, log_q, nll, torch.stack(outs).mean(0)
 
 
+class _McLane:
+    """Buffers, device sample counter, fp64 accumulators, stream and captured graph of one concurrent slice of the loop."""
+
+    def __init__(self, mc, dev):
+        f32 = dict(dtype=torch.float32, device=dev)
+        SB, B, sizes = mc.SB, mc.B, mc.sizes
+        self.w = [torch.zeros(SB, o, i, **f32) for i, o in sizes]
+        self.b = [torch.zeros(SB, o, **f32) for _, o in sizes]
+        self.h = [torch.zeros(SB, B, o, **f32) for _, o in sizes]
+        self.w_lo = [torch.zeros_like(self.w[i]) for i in range(mc.n_tc)]
+        self.h_hi = [torch.zeros(B, SB * sizes[i][1], **f32) for i in range(mc.n_tc - 1)]
+        self.h_lo = [torch.zeros_like(t) for t in self.h_hi]
+        C_ = sizes[-1][1]
+        self.sum_logp = torch.zeros(B, C_, dtype=torch.float64, device=dev)
+        self.sum_prob = torch.zeros(B, C_, dtype=torch.float64, device=dev)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.stream = None
+        self.graph = None
+
+    def reset(self, first_sample):
+        self.sum_logp.zero_()
+        self.sum_prob.zero_()
+        self.counter.fill_(int(first_sample))
+
+
 class MCPredictor:
     """Posterior-predictive model averaging over Monte-Carlo weight samples (test_ensemble, MF:345-436):
     for each sample, fresh hard masks gamma ~ Bernoulli(alpha) and weights per layer, a forward over the whole
@@ -354,17 +379,22 @@ class MCPredictor:
     mean row-normalised expit -> predictive probabilities / OOD entropy, MF:397-408, 478-494).
 
     samples_per_launch samples = one CUDA-graph replay (2 kernels per layer + 1).  Sample s draws from Philox streams keyed
-    by s itself (a device counter), so any split of [0, S) across ranks reproduces the same draws; partial
-    sums are fp64 and are combined with ONE all-reduce (process_group) -- argmax is independent of the split.
+    by s itself (a device counter), so any split of [0, S) across ranks, lanes or launches reproduces the same draws;
+    partial sums are fp64 and are combined in a fixed order (lanes, then ONE all-reduce over the process_group) -- argmax
+    is independent of the split.
     """
 
     NSTREAMS = 4   # Philox streams per (sample, layer): gamma u, eps_w, eps_b, spare
 
-    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8, gemm="auto"):
+    def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8, gemm="auto",
+                 lanes=None):
         """samples_per_launch: weight samples pushed through every kernel of the loop together (csrc/mc_predict.cu);
         1 = the one-sample kernels.  Results do not depend on it: every sample draws from streams keyed by its index.
         gemm: "simt" = fp32 CUDA-core GEMMs; "tc" = every eligible leading layer on the tensor cores at fp32 accuracy
-        (3xTF32 on tcgen05, csrc/tc_gemm_tf32.cu); "auto" = tensor cores for the leading layers at least 64 wide."""
+        (3xTF32 on tcgen05, csrc/tc_gemm_tf32.cu); "auto" = tensor cores for the leading layers at least 64 wide.
+        lanes: the samples of a run() are dealt to this many independent launch sequences on their own streams (own
+        buffers and accumulators), so one lane's ALU-bound weight sampling overlaps another's tensor-core GEMMs;
+        default 2 with tensor-core GEMMs, else 1."""
         K.require_device()
         if gemm not in ("auto", "simt", "tc"):
             raise ValueError(f"gemm must be 'auto', 'simt' or 'tc', got {gemm!r}")
@@ -375,11 +405,8 @@ class MCPredictor:
         self.pg = process_group
         self.SB = SB = max(1, int(samples_per_launch))
         f32 = dict(dtype=torch.float32, device=dev)
-        sizes = [(l.in_features, l.out_features) for l in self.layers]
+        self.sizes = sizes = [(l.in_features, l.out_features) for l in self.layers]
         self.x = torch.zeros(self.B, sizes[0][0], **f32)
-        self.w = [torch.zeros(SB, o, i, **f32) for i, o in sizes]
-        self.b = [torch.zeros(SB, o, **f32) for _, o in sizes]
-        self.h = [torch.zeros(SB, self.B, o, **f32) for _, o in sizes]
         # leading layers that run as 3xTF32 tensor-core GEMMs: operands travel as (hi, lo) pairs; a layer feeding another
         # tensor-core layer writes its activations as (batch, SB * out) so the next one reads them as a strided batch
         self.n_tc = 0
@@ -389,143 +416,213 @@ class MCPredictor:
                 if not ok:
                     break
                 self.n_tc = i + 1
+        self.prepared = SB > 1          # batched sampler reads sigma / alpha computed once per run()
         if self.n_tc:
-            self.x_lo = torch.zeros_like(self.x)
-            self.x_hi = torch.zeros_like(self.x)
-            self.w_lo = [torch.zeros_like(self.w[i]) for i in range(self.n_tc)]
-            self.h_hi = [torch.zeros(self.B, SB * sizes[i][1], **f32) for i in range(self.n_tc - 1)]
-            self.h_lo = [torch.zeros_like(t) for t in self.h_hi]
-        C_ = sizes[-1][1]
-        self.sum_logp = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
-        self.sum_prob = torch.zeros(self.B, C_, dtype=torch.float64, device=dev)
-        self.counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.x_hi, self.x_lo = torch.zeros_like(self.x), torch.zeros_like(self.x)
+        if self.prepared:
+            self.sigma = [torch.zeros(o, i, **f32) for i, o in sizes]
+            self.alpha = [torch.zeros(o, i, **f32) for i, o in sizes]
+            self.bias_sigma = [torch.zeros(o, **f32) for _, o in sizes]
+        n_lanes = (2 if self.n_tc else 1) if lanes is None else max(1, int(lanes))
+        self.lanes = [_McLane(self, dev) for _ in range(n_lanes)]
         self.ws = torch.empty(max(K.lrt_workspace_bytes(self.B, i, o) for i, o in sizes), dtype=torch.uint8, device=dev)
         self.kernels_per_launch = 0
-        self.graph = None
+        for lane in self.lanes:
+            lane.stream = torch.cuda.Stream(device=dev) if (use_graph or n_lanes > 1) else None
         if use_graph:
-            s = torch.cuda.Stream(device=dev)
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                self._enqueue(SB)
-            torch.cuda.current_stream().wait_stream(s)
-            torch.cuda.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._enqueue(SB)
+            self._prepare()
+            for lane in self.lanes:
+                s = lane.stream
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._enqueue(lane, SB)
+                torch.cuda.current_stream().wait_stream(s)
+                torch.cuda.synchronize()
+                lane.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(lane.graph):
+                    self._enqueue(lane, SB)
             self.reset()
+
+    # single-lane views of the buffers (tests, profiling scripts)
+    w = property(lambda self: self.lanes[0].w)
+    b = property(lambda self: self.lanes[0].b)
+    h = property(lambda self: self.lanes[0].h)
+    w_lo = property(lambda self: self.lanes[0].w_lo)
+    counter = property(lambda self: self.lanes[0].counter)
+
+    @property
+    def graph(self):
+        return self.lanes[0].graph
+
+    @graph.setter
+    def graph(self, value):
+        if value is not None:
+            raise ValueError("graphs are captured by the constructor; only None (drop them) can be assigned")
+        for lane in self.lanes:
+            lane.graph = None
+
+    @property
+    def sum_logp(self):
+        """This rank's partial sum over the samples of the last run(): lanes added in lane order."""
+        return self._lane_sum("sum_logp")
+
+    @property
+    def sum_prob(self):
+        return self._lane_sum("sum_prob")
+
+    def _lane_sum(self, name):
+        tot = getattr(self.lanes[0], name)
+        for lane in self.lanes[1:]:
+            tot = tot + getattr(lane, name)
+        return tot
 
     @property
     def kernels_per_sample(self):
         return self.kernels_per_launch / self.SB
 
-    def _noise(self, layer, which):
+    def _noise(self, lane, layer, which):
         stride = self.NSTREAMS * len(self.layers)
-        return K.make_noise(None, self.seed, layer * self.NSTREAMS + which, self.counter, stride)
+        return K.make_noise(None, self.seed, layer * self.NSTREAMS + which, lane.counter, stride)
 
-    def _enqueue(self, n):
-        """One launch sequence for the next n <= samples_per_launch samples."""
+    def _desc(self, i):
+        l = self.layers[i]
+        if self.prepared:
+            return K.make_layer(l.weight_mu.data, self.sigma[i], self.alpha[i], l.bias_mu.data, self.bias_sigma[i])
+        return K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+
+    def _prepare(self):
+        """Per-run() work on the current stream: sigma / alpha of the (possibly updated) parameters, hi / lo of the input."""
+        st = K.current_stream()
+        if self.prepared:
+            for i, l in enumerate(self.layers):
+                raw = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+                K.check(K.lib.lbbnn_mc_prepare(raw, K.ptr(self.sigma[i]), K.ptr(self.alpha[i]), K.ptr(self.bias_sigma[i]), st))
+        if self.n_tc:
+            K.check(K.lib.lbbnn_tf32_split(K.ptr(self.x), self.x.numel(), K.ptr(self.x_hi), K.ptr(self.x_lo), st))
+
+    def _enqueue(self, lane, n):
+        """One launch sequence for the next n <= samples_per_launch samples of a lane, on the current stream."""
         st = K.current_stream()
         L = len(self.layers)
         if self.SB == 1:
-            return self._enqueue_one()
+            return self._enqueue_one(lane)
         stride = self.NSTREAMS * L
         h, hs = self.x, 0
         for i, l in enumerate(self.layers):
-            desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+            desc = self._desc(i)
             if i < self.n_tc:
-                self._enqueue_tc_layer(i, l, desc, n, stride, st)
-                h, hs = self.h[i], self.B * l.out_features
+                self._enqueue_tc_layer(lane, i, l, desc, n, stride, st)
+                h, hs = lane.h[i], self.B * l.out_features
                 continue
-            K.check(K.lib.lbbnn_mc_sample(desc, n, K.ptr(self.counter, torch.int64), self.seed & (2 ** 64 - 1),
-                                          i * self.NSTREAMS, stride, K.ptr(self.w[i]), K.ptr(self.b[i]), st))
-            K.check(K.lib.lbbnn_linear_f32_batched(K.ptr(h), hs, K.ptr(self.w[i]), K.ptr(self.b[i]), n, self.B,
+            K.check(K.lib.lbbnn_mc_sample_split(desc, n, K.ptr(lane.counter, torch.int64), self.seed & (2 ** 64 - 1),
+                                                i * self.NSTREAMS, stride, 1, K.ptr(lane.w[i]), None, K.ptr(lane.b[i]), st))
+            K.check(K.lib.lbbnn_linear_f32_batched(K.ptr(h), hs, K.ptr(lane.w[i]), K.ptr(lane.b[i]), n, self.B,
                                                    l.in_features, l.out_features, K.FLAG_RELU if i < L - 1 else 0,
-                                                   K.ptr(self.h[i]), st))
-            h, hs = self.h[i], self.B * l.out_features
+                                                   K.ptr(lane.h[i]), st))
+            h, hs = lane.h[i], self.B * l.out_features
         K.check(K.lib.lbbnn_mc_accumulate_batched(K.ptr(h), n, self.B, self.layers[-1].out_features,
-                                                  self.sum_logp.data_ptr(), self.sum_prob.data_ptr(),
-                                                  K.ptr(self.counter, torch.int64), st))
+                                                  lane.sum_logp.data_ptr(), lane.sum_prob.data_ptr(),
+                                                  K.ptr(lane.counter, torch.int64), st))
         self.kernels_per_launch = 2 * L + 1 + (n - 1 if self.n_tc == 1 else 0)
 
-    def _enqueue_tc_layer(self, i, l, desc, n, stride, st):
+    def _enqueue_tc_layer(self, lane, i, l, desc, n, stride, st):
         L, SB, B = len(self.layers), self.SB, self.B
         k, o = l.in_features, l.out_features
-        K.check(K.lib.lbbnn_mc_sample_split(desc, n, K.ptr(self.counter, torch.int64), self.seed & (2 ** 64 - 1),
-                                            i * self.NSTREAMS, stride, K.ptr(self.w[i]), K.ptr(self.w_lo[i]),
-                                            K.ptr(self.b[i]), st))
+        K.check(K.lib.lbbnn_mc_sample_split(desc, n, K.ptr(lane.counter, torch.int64), self.seed & (2 ** 64 - 1),
+                                            i * self.NSTREAMS, stride, 1, K.ptr(lane.w[i]), K.ptr(lane.w_lo[i]),
+                                            K.ptr(lane.b[i]), st))
         flags = K.FLAG_RELU if i < L - 1 else 0
         feeds_tc = i + 1 < self.n_tc
         if feeds_tc:      # (batch, SB * out) hi / lo for the next tensor-core layer
-            out, out_hi, out_lo, pitch, bstride = None, K.ptr(self.h_hi[i]), K.ptr(self.h_lo[i]), SB * o, o
+            out, out_hi, out_lo, pitch, bstride = None, K.ptr(lane.h_hi[i]), K.ptr(lane.h_lo[i]), SB * o, o
         else:             # (SB, batch, out) fp32 for the CUDA-core layer / the accumulation kernel
-            out, out_hi, out_lo, pitch, bstride = K.ptr(self.h[i]), None, None, o, B * o
-        if i == 0:        # all samples read the same input: ONE problem, N = n * out
-            if feeds_tc:
-                K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(self.w[i]),
-                                                     K.ptr(self.w_lo[i]), K.ptr(self.b[i]), 1, B, n * o, k, flags,
+            out, out_hi, out_lo, pitch, bstride = K.ptr(lane.h[i]), None, None, o, B * o
+        if i == 0:        # all samples read the same input
+            if feeds_tc:  # ONE problem, N = n * out
+                K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(lane.w[i]),
+                                                     K.ptr(lane.w_lo[i]), K.ptr(lane.b[i]), 1, B, n * o, k, flags,
                                                      out, out_hi, out_lo, pitch, bstride, st))
             else:         # (SB, batch, out) wanted: one problem per sample
                 for z in range(n):
-                    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(self.w[i][z]),
-                                                         K.ptr(self.w_lo[i][z]), K.ptr(self.b[i][z]), 1, B, o, k, flags,
-                                                         K.ptr(self.h[i][z]), None, None, o, 0, st))
+                    K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.x_hi), K.ptr(self.x_lo), k, 0, K.ptr(lane.w[i][z]),
+                                                         K.ptr(lane.w_lo[i][z]), K.ptr(lane.b[i][z]), 1, B, o, k, flags,
+                                                         K.ptr(lane.h[i][z]), None, None, o, 0, st))
         else:
             pk = SB * k   # previous layer's row pitch; its sample z sits at column offset z * k
-            K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(self.h_hi[i - 1]), K.ptr(self.h_lo[i - 1]), pk, k,
-                                                 K.ptr(self.w[i]), K.ptr(self.w_lo[i]), K.ptr(self.b[i]), n, B, o, k,
+            K.check(K.lib.lbbnn_tc_linear_tf32x3(K.ptr(lane.h_hi[i - 1]), K.ptr(lane.h_lo[i - 1]), pk, k,
+                                                 K.ptr(lane.w[i]), K.ptr(lane.w_lo[i]), K.ptr(lane.b[i]), n, B, o, k,
                                                  flags, out, out_hi, out_lo, pitch, bstride, st))
 
-    def _enqueue_one(self):
+    def _enqueue_one(self, lane):
         st = K.current_stream()
         L = len(self.layers)
         h = self.x
         n = 0
         for i, l in enumerate(self.layers):
             desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
-            K.check(K.lib.lbbnn_mf_sample_predict(desc, self._noise(i, 0), self._noise(i, 1), self._noise(i, 2),
-                                                  K.ptr(self.w[i]), K.ptr(self.b[i]), st))
-            K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(h), K.ptr(self.w[i]), K.ptr(self.b[i]), self.B, l.in_features,
-                                               l.out_features, K.FLAG_RELU if i < L - 1 else 0, K.ptr(self.h[i]),
+            K.check(K.lib.lbbnn_mf_sample_predict(desc, self._noise(lane, i, 0), self._noise(lane, i, 1),
+                                                  self._noise(lane, i, 2), K.ptr(lane.w[i]), K.ptr(lane.b[i]), st))
+            K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(h), K.ptr(lane.w[i]), K.ptr(lane.b[i]), self.B, l.in_features,
+                                               l.out_features, K.FLAG_RELU if i < L - 1 else 0, K.ptr(lane.h[i]),
                                                self.ws.data_ptr(), self.ws.numel(), st))
             n += 3
-            h = self.h[i]
-        K.check(K.lib.lbbnn_mc_accumulate(K.ptr(h), self.B, self.layers[-1].out_features, self.sum_logp.data_ptr(),
-                                          self.sum_prob.data_ptr(), K.ptr(self.counter, torch.int64), st))
+            h = lane.h[i]
+        K.check(K.lib.lbbnn_mc_accumulate(K.ptr(h), self.B, self.layers[-1].out_features, lane.sum_logp.data_ptr(),
+                                          lane.sum_prob.data_ptr(), K.ptr(lane.counter, torch.int64), st))
         self.kernels_per_launch = n + 1
 
     def reset(self, first_sample=0):
-        self.sum_logp.zero_()
-        self.sum_prob.zero_()
-        self.counter.fill_(int(first_sample))
+        for lane in self.lanes:
+            lane.reset(first_sample)
 
     def run(self, x, samples, first_sample=0):
         """Accumulate `samples` weight samples with global indices first_sample.. on this rank."""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
-        if self.n_tc:
-            K.check(K.lib.lbbnn_tf32_split(K.ptr(self.x), self.x.numel(), K.ptr(self.x_hi), K.ptr(self.x_lo),
-                                           K.current_stream()))
-        self.reset(first_sample)
+        self._prepare()
+        # whole launches are dealt to the lanes as contiguous index ranges; the partial last launch goes to the last lane
         full, rest = divmod(int(samples), self.SB)
-        for _ in range(full):
-            if self.graph is not None:
-                self.graph.replay()
-            else:
-                self._enqueue(self.SB)
-        if rest:
-            self._enqueue(rest)      # a partial last launch runs outside the captured graph
+        nl = len(self.lanes)
+        main = torch.cuda.current_stream()
+        first = int(first_sample)
+        for j, lane in enumerate(self.lanes):
+            launches = full // nl + (1 if j < full % nl else 0)
+            tail = rest if j == nl - 1 else 0
+            side = lane.stream if nl > 1 else None
+            if side is not None:
+                side.wait_stream(main)
+            with torch.cuda.stream(side) if side is not None else _null_ctx():
+                lane.reset(first)
+                for _ in range(launches):
+                    if lane.graph is not None:
+                        lane.graph.replay()
+                    else:
+                        self._enqueue(lane, self.SB)
+                if tail:
+                    self._enqueue(lane, tail)      # a partial last launch runs outside the captured graph
+            first += launches * self.SB + tail
+        for lane in self.lanes:
+            if nl > 1:
+                main.wait_stream(lane.stream)
 
     def result(self, total_samples):
-        """Combine ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics."""
+        """Combine lanes and ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics."""
+        sum_logp, sum_prob = self.sum_logp, self.sum_prob
         if self.pg is not None:
-            both = torch.stack([self.sum_logp, self.sum_prob])
+            both = torch.stack([sum_logp, sum_prob])
             torch.distributed.all_reduce(both, group=self.pg)
             sum_logp, sum_prob = both[0], both[1]
-        else:
-            sum_logp, sum_prob = self.sum_logp, self.sum_prob
         mean_logp = sum_logp / total_samples
         probs = sum_prob / total_samples
         return {"mean_logp": mean_logp, "pred": mean_logp.argmax(1), "probs": probs,
                 "entropy": -(probs * torch.log(probs)).sum(1)}
+
+
+class _null_ctx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 def shard_samples(total, world, rank):

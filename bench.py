@@ -576,7 +576,8 @@ def run_mc(args):
         for l, p in zip(net.layers, layers):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
-    mc = lbbnn.mf.MCPredictor(net, batch=MC_BATCH, seed=4321, process_group=pg, samples_per_launch=args.mc_batch)
+    mc = lbbnn.mf.MCPredictor(net, batch=MC_BATCH, seed=4321, process_group=pg, samples_per_launch=args.mc_batch,
+                              gemm=args.mc_gemm, lanes=args.mc_lanes)
     first, count = lbbnn.mf.shard_samples(MC_SAMPLES, world, rank)
     xs_host = torch.from_numpy(rng.random((8, MC_BATCH, MC_SIZES[0]), dtype=np.float32)).pin_memory()
     xs = xs_host.to(dev)
@@ -623,56 +624,82 @@ def run_mc(args):
     if rank == 0:
         from lbbnn import _capi as K
         peaks = load_peaks()
-        # kernels of the layer-1 stage timed alone (CUDA events, cold L2): the batched sampler (HBM-bound: 12 B read +
-        # 4 B written per weight and sample) and the batched fp32 GEMM (CUDA-core FFMA-bound)
+        # kernels of the layer-1 stage timed alone (CUDA events, cold L2): the batched sampler (ALU-bound Philox; HBM
+        # side: 12 B read per weight + 4 or 8 B written per weight and sample) and the layer's GEMM over SB samples
         l = net.layers[0]
         SB = mc.SB
-        desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+        tc = mc.n_tc >= 2
+        desc = mc._desc(0)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
         times = {"s": [], "g": []}
         st = K.current_stream()
         stride = mc.NSTREAMS * len(net.layers)
+        lane = mc.lanes[0]
+        if tc:
+            sample = lambda: K.lib.lbbnn_mc_sample_split(desc, SB, K.ptr(lane.counter, torch.int64), 4321, 0, stride, 1,
+                                                         K.ptr(lane.w[0]), K.ptr(lane.w_lo[0]), K.ptr(lane.b[0]), st)
+            gemm = lambda: K.lib.lbbnn_tc_linear_tf32x3(K.ptr(mc.x_hi), K.ptr(mc.x_lo), 784, 0, K.ptr(lane.w[0]),
+                                                        K.ptr(lane.w_lo[0]), K.ptr(lane.b[0]), 1, MC_BATCH, SB * 400, 784,
+                                                        K.FLAG_RELU, None, K.ptr(lane.h_hi[0]), K.ptr(lane.h_lo[0]), SB * 400,
+                                                        400, st)
+            gname = f"tc_linear_tf32x3[l1] (3xTF32 on tcgen05, fp32 accuracy, {SB} weight samples per launch)"
+        else:
+            sample = lambda: K.lib.lbbnn_mc_sample_split(desc, SB, K.ptr(lane.counter, torch.int64), 4321, 0, stride, 1,
+                                                         K.ptr(lane.w[0]), None, K.ptr(lane.b[0]), st)
+            gemm = lambda: K.lib.lbbnn_linear_f32_batched(K.ptr(mc.x), 0, K.ptr(lane.w[0]), K.ptr(lane.b[0]), SB, MC_BATCH,
+                                                          784, 400, K.FLAG_RELU, K.ptr(lane.h[0]), st)
+            gname = f"sgemm_tn_batched[l1] (fp32 SIMT, {SB} weight samples per launch)"
         for _ in range(8):
-            for name, fn in (("s", lambda: K.lib.lbbnn_mc_sample(desc, SB, K.ptr(mc.counter, torch.int64), 4321, 0, stride,
-                                                                 K.ptr(mc.w[0]), K.ptr(mc.b[0]), st)),
-                             ("g", lambda: K.lib.lbbnn_linear_f32_batched(K.ptr(mc.x), 0, K.ptr(mc.w[0]), K.ptr(mc.b[0]), SB,
-                                                                          MC_BATCH, 784, 400, K.FLAG_RELU, K.ptr(mc.h[0]), st))):
+            for name, fn in (("s", sample), ("g", gemm)):
                 flush.zero_()
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a.record(); K.check(fn()); b.record(); b.synchronize()
                 times[name].append(a.elapsed_time(b) * 1e3)
         us_s = statistics.mean(times["s"][2:])
         us_g = statistics.mean(times["g"][2:])
-        nbytes = (12 + 4 * SB) * 784 * 400          # parameters read once (L2 serves the other samples) + SB x w written
-        gflop = 2.0 * MC_BATCH * 784 * 400 * SB / 1e9
+        nbytes = (12 + (8 if tc else 4) * SB) * 784 * 400   # parameters read once (L2 serves the other samples) + SB x w written
+        gflop = 2.0 * MC_BATCH * 784 * 400 * SB / 1e9        # ALGORITHMIC flops: one fp32 product per (input, weight)
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal CUDA-core FFMA peak, TFLOP/s
         cpu = cpu_reference_mc() if world == 1 else None
         ach = gflop * 1e9 / (us_g * 1e-6) / 1e12     # TFLOP/s
+        launches_per_step = sum((count // SB) // len(mc.lanes) + (1 if j < (count // SB) % len(mc.lanes) else 0)
+                                for j in range(len(mc.lanes))) + (1 if count % SB else 0)
+        note = ("fp32 parity mode (1e-5 vs the oracle, argmax bit-exact): every fp32 product is three kind::tf32 MMAs "
+                "(hi*hi + hi*lo + lo*hi) at half the bf16 rate, so 1/6 of the bf16 tensor peak is the ceiling of this "
+                "algorithmic-flops fraction; `mma_tflops` counts the MMAs actually issued") if tc else (
+                "fp32 parity mode keeps this GEMM on the CUDA cores; the fraction of the bf16 tensor peak is quoted because "
+                "the contract asks for it")
         line = {"metric": "mc_predictive_samples_per_sec", "value": MC_SAMPLES * args.steps / (ms * 1e-3),
                 "unit": "MC weight-samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": dict(mc_config(world), samples_per_launch=SB),
+                "dtype": "f32", "data": "synthetic",
+                "config": dict(mc_config(world), samples_per_launch=SB, lanes=len(mc.lanes),
+                               gemm="3xTF32 tcgen05 (layers 1-2) + fp32 SIMT (10-wide head)" if tc else "fp32 SIMT"),
                 "e2e": {"value": MC_SAMPLES * args.steps / (e2e_ms * 1e-3), "unit": "MC weight-samples/s",
                         "h2d_bytes_per_step": MC_BATCH * MC_SIZES[0] * 4, "d2h_bytes_per_step": MC_BATCH * 8,
                         "ms_per_step": e2e_ms / args.steps},
-                "gpu_launches": int(mc.kernels_per_launch * (count // SB + (1 if count % SB else 0)) * args.steps),
+                "gpu_launches": int((mc.kernels_per_launch * launches_per_step + 4) * args.steps),
                 "kernels_per_sample": mc.kernels_per_sample,
                 "input_samples_per_sec": MC_SAMPLES * MC_BATCH * args.steps / (ms * 1e-3),
-                "roofline": {"bound": "tensor", "kernel": f"sgemm_tn_batched[l1] (fp32 SIMT, {SB} weight samples per launch)",
+                "roofline": {"bound": "tensor", "kernel": gname,
                              "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                              "traffic": None, "peak_source": peaks["source"], "us_per_launch": us_g,
                              "flops_per_launch": gflop * 1e9,
-                             "frac_of_fp32_cuda_core_peak": ach / fp32_peak, "fp32_cuda_core_peak_tflops": fp32_peak,
                              "timing": "kernel alone, cold L2 (256 MB memset before each launch), CUDA events, mean of 6",
-                             "note": "fp32 parity mode (argmax bit-exact vs the oracle) keeps this GEMM on the CUDA cores; the "
-                                     "fraction of the bf16 tensor peak is quoted because the contract asks for it"},
+                             "note": note},
                 "sampling_roofline": {"bound": "hbm", "kernel": f"mc_sample[l1] (mask + weights + bias, {SB} samples per launch)",
                                       "achieved": nbytes / (us_s * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": nbytes / (us_s * 1e-6) / 1e9 / peaks["hbm_gbs"], "us_per_launch": us_s,
                                       "bytes_per_launch": nbytes},
                 "kernels": [{"name": "mc_sample[l1]", "us": round(us_s, 2)},
-                            {"name": "sgemm_tn_batched[l1]", "us": round(us_g, 2), "tflops": round(ach, 2)}],
+                            {"name": gname.split(" ")[0], "us": round(us_g, 2), "tflops": round(ach, 2)}],
                 "clocks": clocks}
+        if tc:
+            line["roofline"]["mma_tflops"] = 3 * ach
+            line["roofline"]["frac_of_3xtf32_ceiling"] = ach / (peaks["bf16_tflops"] / 6)
+        else:
+            line["roofline"]["frac_of_fp32_cuda_core_peak"] = ach / fp32_peak
+            line["roofline"]["fp32_cuda_core_peak_tflops"] = fp32_peak
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(line), flush=True)
@@ -852,7 +879,10 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mc-batch", type=int, default=21, help="mf_mc_predict: weight samples per launch")
+    ap.add_argument("--mc-batch", type=int, default=32, help="mf_mc_predict: weight samples per launch")
+    ap.add_argument("--mc-gemm", default="auto", choices=("auto", "simt", "tc"),
+                    help="mf_mc_predict: GEMMs on the tensor cores as 3xTF32 (auto / tc) or on the CUDA cores (simt)")
+    ap.add_argument("--mc-lanes", type=int, default=None, help="mf_mc_predict: concurrent launch sequences per GPU")
     ap.add_argument("--eager", action="store_true", help="mnf_mnist / mf_mnist: eager modules instead of the graphed step")
     ap.add_argument("--unfused", action="store_true", help="lrt_mnist: per-layer launch sequence instead of the step kernel")
     ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist"])

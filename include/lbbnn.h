@@ -245,7 +245,10 @@ LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, in
  * carried as hi + lo (hi = the value rounded to TF32, lo = the exact remainder) and each contraction step issues
  * hi*hi + hi*lo + lo*hi as three tcgen05 kind::tf32 MMAs into one fp32 TMEM accumulator ("3xTF32").
  *   tf32_split           hi / lo of n floats (the test inputs, once per batch)
- *   mc_sample_split      = mc_sample, but the weights leave as w_hi / w_lo (w_hi + w_lo is mc_sample's w, bit for bit)
+ *   mc_prepare           sigma = log1p(exp rho), alpha = sigmoid(lambda), sigma_b of one layer, once per parameter set
+ *   mc_sample_split      = mc_sample with optional extras: w_lo != NULL -> the weights leave as w_hi / w_lo (w_hi + w_lo
+ *                        is mc_sample's w, bit for bit); prepared != 0 -> the layer's weight_rho / lambdal / bias_rho
+ *                        pointers hold mc_prepare's sigma / alpha / sigma_b (same values, not recomputed per sample)
  *   tc_linear_tf32x3     out[z][m][n] = act(sum_k a[z][m][k] w[z][n][k] + bias[z][n]),  z < batches.
  *                        a: row m of batch z starts at a + z * a_batch_stride + m * a_row_pitch (floats, multiples of 4);
  *                        w: (batches, N, K) contiguous; K % 4 == 0; outputs at z * out_batch_stride + m * out_row_pitch:
@@ -253,9 +256,10 @@ LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, in
  *                        All samples of a launch sharing one input (the first layer) = ONE problem with batches = 1 and
  *                        N = n_samples * out_features; its (batch, n_samples * out) output is the next layer's strided a. */
 LBBNN_API int lbbnn_tf32_split(const float* x, int64_t n, float* hi, float* lo, lbbnn_stream s);
+LBBNN_API int lbbnn_mc_prepare(const lbbnn_layer* layer, float* sigma, float* alpha, float* bias_sigma, lbbnn_stream s);
 LBBNN_API int lbbnn_mc_sample_split(const lbbnn_layer* layer, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
-                                    uint64_t stream_base, uint64_t stream_stride, float* w_hi, float* w_lo, float* bias,
-                                    lbbnn_stream s);
+                                    uint64_t stream_base, uint64_t stream_stride, int prepared, float* w_hi, float* w_lo,
+                                    float* bias, lbbnn_stream s);
 LBBNN_API int lbbnn_tc_linear_tf32x3(const float* a_hi, const float* a_lo, int64_t a_row_pitch, int64_t a_batch_stride,
                                      const float* w_hi, const float* w_lo, const float* bias, int64_t batches, int64_t M,
                                      int64_t N, int64_t K, int flags, float* out, float* out_hi, float* out_lo,

@@ -63,9 +63,10 @@ with torch.no_grad():
     for l in net.layers:
         l.lambdal.normal_(0, 2)
 x = torch.rand(B, 784, device=dev)
-S = 1008
-for gemm, SB in (("simt", 21), ("auto", 8), ("auto", 16), ("auto", 21), ("auto", 32), ("auto", 48)):
-    mc = lbbnn.mf.MCPredictor(net, batch=B, seed=1, samples_per_launch=SB, gemm=gemm)
+S = 1152
+for gemm, SB, lanes in (("simt", 21, 1), ("simt", 21, 2), ("auto", 16, 1), ("auto", 32, 1), ("auto", 48, 1), ("auto", 16, 2),
+                        ("auto", 24, 2), ("auto", 32, 2), ("auto", 48, 2), ("auto", 16, 3), ("auto", 32, 3), ("auto", 16, 4)):
+    mc = lbbnn.mf.MCPredictor(net, batch=B, seed=1, samples_per_launch=SB, gemm=gemm, lanes=lanes)
     mc.run(x, S); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -74,12 +75,13 @@ for gemm, SB in (("simt", 21), ("auto", 8), ("auto", 16), ("auto", 21), ("auto",
     b.record(); b.synchronize()
     r = S * 3 / (a.elapsed_time(b) * 1e-3)
     pred = mc.result(S)["pred"]
-    out[f"mc_{gemm}_SB{SB}"] = {"samples_per_s": round(r), "n_tc": mc.n_tc}
-    if gemm == "simt":
+    key = f"mc_{gemm}_SB{SB}_L{lanes}"
+    out[key] = {"samples_per_s": round(r), "n_tc": mc.n_tc}
+    if gemm == "simt" and lanes == 1:
         base_pred, base_logp = pred.clone(), mc.sum_logp.clone()
     else:
-        out[f"mc_{gemm}_SB{SB}"]["pred_equal_simt"] = bool(torch.equal(pred, base_pred))
-        out[f"mc_{gemm}_SB{SB}"]["rel_err_logp_vs_simt"] = ((mc.sum_logp - base_logp).abs().max() / base_logp.abs().max()).item()
-    print(f"mc_{gemm}_SB{SB}", out[f"mc_{gemm}_SB{SB}"], flush=True)
+        out[key]["pred_equal_simt"] = bool(torch.equal(pred, base_pred))
+        out[key]["rel_err_logp_vs_simt"] = ((mc.sum_logp - base_logp).abs().max() / base_logp.abs().max()).item()
+    print(key, out[key], flush=True)
     del mc
 print(json.dumps(out))

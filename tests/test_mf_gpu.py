@@ -211,12 +211,26 @@ def test_mc_predictor_batched_equals_one_sample_kernels(lb):
     # last sample of the last (partial, 3-sample) launch of b == the single sample a drew last: indices 3+6
     assert torch.equal(b.w[0][2], a.w[0][0]) and torch.equal(b.b[2][2], a.b[2][0])
     # tensor-core (3xTF32) GEMMs for the 400- and 600-wide layers: same draws (hi + lo == the fp32 weight), fp32 accuracy
-    c = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4)
+    c = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=4, lanes=1)
     assert c.n_tc == 2
     c.run(case["x"].cuda(), 7, first_sample=3)
     assert torch.equal(c.w[0] + c.w_lo[0], b.w[0]) and torch.equal(c.w[1] + c.w_lo[1], b.w[1])
+    assert torch.equal(c.w[2], b.w[2]) and torch.equal(c.b[1], b.b[1])
     assert C.rel_err(c.sum_logp, a.sum_logp) < 1e-5 and C.rel_err(c.sum_prob, a.sum_prob) < 1e-5
     assert torch.equal(a.result(7)["pred"], c.result(7)["pred"])
+    # two concurrent lanes (the default with tensor-core GEMMs): same samples, fp64 partials added in lane order
+    d = lb.mf.MCPredictor(net, batch=37, seed=5, samples_per_launch=2)
+    assert len(d.lanes) == 2
+    d.run(case["x"].cuda(), 7, first_sample=3)
+    assert (d.sum_logp - c.sum_logp).abs().max().item() < 1e-9 and (d.sum_prob - c.sum_prob).abs().max().item() < 1e-9
+    assert int(d.lanes[0].counter) == 3 + 4 and int(d.lanes[1].counter) == 3 + 7
+    # parameters changed between runs are picked up (sigma / alpha are recomputed by every run())
+    with torch.no_grad():
+        net.layers[0].lambdal.add_(0.5)
+        net.layers[1].weight_rho.add_(0.3)
+    a.run(case["x"].cuda(), 4)
+    d.run(case["x"].cuda(), 4)
+    assert C.rel_err(d.sum_logp, a.sum_logp) < 1e-5 and torch.equal(a.result(4)["pred"], d.result(4)["pred"])
 
 
 
