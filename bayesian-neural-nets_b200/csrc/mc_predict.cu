@@ -269,6 +269,136 @@ __global__ void __launch_bounds__(kThreads) mc_accumulate_batched_kernel(const f
   if (counter && blockIdx.x == 0 && threadIdx.x == 0) *counter += n_samples;
 }
 
+// ---- classifier head + accumulation in one kernel ---------------------------------------------------------------
+// The last layer of the loop is a (batch, K) x (K, C) product with C = 10 classes: a 64-wide GEMM tile is 84 % padding and
+// the logits only exist to be fed to the accumulators.  Here one warp owns one input row for ALL samples of the launch:
+// per sample the block stages that sample's (C, K) weights in shared memory (cp.async, double-buffered), every warp
+// forms its row's C dot products (lanes stride K in float4, C accumulators, xor-shuffle reduction), then log_softmax and
+// the two fp64 accumulators exactly as mc_accumulate_batched_kernel (same expressions, samples in the same order, the
+// running sums held in registers by lanes 0..C-1 and written once).
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+constexpr int kHeadQ = 8;        // float4 per lane held in registers: in_features <= 1024
+
+struct HeadArgs {
+  const float *h, *W, *bias;   // (SB, B, K), (SB, C, K), (SB, C)
+  int64_t hs;                  // floats between the activations of consecutive samples
+  int B, K, n_samples;
+  double *sum_logp, *sum_prob;
+  int64_t* counter;
+};
+
+template <int C>
+__global__ void __launch_bounds__(kThreads) mc_head_accumulate_kernel(const HeadArgs a) {
+  extern __shared__ float4 wbuf[];                 // 2 x (C * K / 4)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int K4 = a.K >> 2, CK4 = C * K4;
+  const int b = blockIdx.x * (kThreads / 32) + warp;
+  const bool live = b < a.B;
+  auto stage = [&](int s, int buf) {
+    const float4* src = reinterpret_cast<const float4*>(a.W + (int64_t)s * C * a.K);
+    for (int i = tid; i < CK4; i += kThreads) cp_async16(&wbuf[buf * CK4 + i], src + i);
+    cp_async_commit();
+  };
+  stage(0, 0);
+  double run_lp = 0.0, run_pr = 0.0;
+  if (live && lane < C) {
+    run_lp = a.sum_logp[(int64_t)b * C + lane];
+    run_pr = a.sum_prob[(int64_t)b * C + lane];
+  }
+  // the warp's activation row of the NEXT sample is fetched into registers (all kHeadQ float4 loads in flight at once)
+  // while the current sample's dot products run
+  float4 hn[kHeadQ];
+  auto fetch = [&](int s) {
+    const float4* hr = reinterpret_cast<const float4*>(a.h + (int64_t)s * a.hs + (int64_t)b * a.K);
+#pragma unroll
+    for (int q = 0; q < kHeadQ; ++q) {
+      const int k4 = lane + 32 * q;
+      hn[q] = (live && k4 < K4) ? __ldg(hr + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  fetch(0);
+  for (int s = 0; s < a.n_samples; ++s) {
+    float4 hv[kHeadQ];
+#pragma unroll
+    for (int q = 0; q < kHeadQ; ++q) hv[q] = hn[q];
+    if (s + 1 < a.n_samples) {
+      stage(s + 1, (s + 1) & 1);
+      fetch(s + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();                               // sample s's weights are in wbuf[s & 1]
+    if (live) {
+      const float4* w = wbuf + (s & 1) * CK4;
+      float acc[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+      for (int q = 0; q < kHeadQ; ++q) {
+        if (q * 32 < K4) {                         // warp-uniform
+          const int k4 = min(lane + 32 * q, K4 - 1);   // lanes past the row end carry zeros in hv
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            const float4 wv = w[c * K4 + k4];
+            acc[c] = fmaf(hv[q].x, wv.x, fmaf(hv[q].y, wv.y, fmaf(hv[q].z, wv.z, fmaf(hv[q].w, wv.w, acc[c]))));
+          }
+        }
+      }
+      const float* bias = a.bias + (int64_t)s * C;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        acc[c] += __ldg(bias + c);
+        mx = fmaxf(mx, acc[c]);
+      }
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) se += expf(acc[c] - mx);
+      const float lse = mx + logf(se);
+      float ps = 0.f, mylp = 0.f, mye = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float lp = acc[c] - lse;
+        const float e = 1.0f / (1.0f + expf(-lp));
+        ps += e;
+        if (lane == c) { mylp = lp; mye = e; }
+      }
+      if (lane < C) {
+        run_lp += (double)mylp;
+        run_pr += (double)(mye / ps);
+      }
+    }
+    __syncthreads();                               // everyone is done with wbuf[s & 1] before sample s + 2 lands in it
+  }
+  if (live && lane < C) {
+    a.sum_logp[(int64_t)b * C + lane] = run_lp;
+    a.sum_prob[(int64_t)b * C + lane] = run_pr;
+  }
+  if (a.counter && blockIdx.x == 0 && tid == 0) *a.counter += a.n_samples;
+}
+
+template <int C>
+int launch_head(const HeadArgs& a, cudaStream_t s) {
+  const size_t smem = 2 * (size_t)C * a.K * sizeof(float);
+  LBBNN_REQUIRE(smem <= 200 * 1024, "head weights of one sample do not fit in shared memory twice (%zu bytes)", smem);
+  static bool attr_set = false;
+  if (!attr_set) {
+    LBBNN_CUDA(cudaFuncSetAttribute(mc_head_accumulate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  mc_head_accumulate_kernel<C><<<(unsigned)ceil_div(a.B, kThreads / 32), kThreads, smem, s>>>(a);
+  return check_launch("mc_head_accumulate");
+}
+
 }  // namespace
 }  // namespace lbbnn
 
@@ -341,4 +471,28 @@ extern "C" int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, i
   mc_accumulate_batched_kernel<<<(unsigned)ceil_div(batch, kThreads / 32), kThreads, 0, (cudaStream_t)s>>>(
       logits, batch, classes, n_samples, sum_logp, sum_prob, counter);
   return check_launch("mc_accumulate_batched");
+}
+
+extern "C" int lbbnn_mc_head_accumulate(const float* h, int64_t h_stride, const float* W, const float* bias, int n_samples,
+                                        int64_t batch, int64_t in_features, int64_t classes, double* sum_logp,
+                                        double* sum_prob, int64_t* counter, lbbnn_stream s) {
+  LBBNN_REQUIRE(h && W && bias && sum_logp && sum_prob && n_samples > 0 && batch > 0 && batch < (1LL << 31), "bad argument");
+  LBBNN_REQUIRE(classes >= 1 && classes <= 16, "fused head handles 1..16 classes, got %lld", (long long)classes);
+  LBBNN_REQUIRE(in_features <= 128 * kHeadQ, "fused head handles in_features <= %d, got %lld", 128 * kHeadQ,
+                (long long)in_features);
+  LBBNN_REQUIRE(in_features > 0 && in_features % 4 == 0 && h_stride % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
+                "in_features and the sample stride must be multiples of 4 floats, operands 16-byte aligned");
+  HeadArgs a;
+  a.h = h; a.W = W; a.bias = bias; a.hs = h_stride; a.B = (int)batch; a.K = (int)in_features; a.n_samples = n_samples;
+  a.sum_logp = sum_logp; a.sum_prob = sum_prob; a.counter = counter;
+  cudaStream_t st = (cudaStream_t)s;
+  switch ((int)classes) {
+#define LBBNN_HEAD_CASE(C) case C: return launch_head<C>(a, st);
+    LBBNN_HEAD_CASE(1) LBBNN_HEAD_CASE(2) LBBNN_HEAD_CASE(3) LBBNN_HEAD_CASE(4) LBBNN_HEAD_CASE(5) LBBNN_HEAD_CASE(6)
+    LBBNN_HEAD_CASE(7) LBBNN_HEAD_CASE(8) LBBNN_HEAD_CASE(9) LBBNN_HEAD_CASE(10) LBBNN_HEAD_CASE(11) LBBNN_HEAD_CASE(12)
+    LBBNN_HEAD_CASE(13) LBBNN_HEAD_CASE(14) LBBNN_HEAD_CASE(15) LBBNN_HEAD_CASE(16)
+#undef LBBNN_HEAD_CASE
+  }
+  return LBBNN_ERR_INVALID;
 }

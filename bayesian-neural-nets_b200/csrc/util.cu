@@ -186,6 +186,54 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+// The same update over a TABLE of tensors in one launch: block b works on 1024 consecutive elements of the tensor whose
+// [first_block, next first_block) range holds b (binary search over the table, read through L2 by every block).
+__global__ void __launch_bounds__(256) adam_multi_kernel(const lbbnn_adam_entry* __restrict__ table, int n_entries, float b1,
+                                                         float b2, float eps, const float* __restrict__ coef) {
+  int lo = 0, hi = n_entries - 1;
+  const int64_t blk = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+  }
+  const lbbnn_adam_entry e = table[lo];
+  const float step_size = __ldg(coef), bc2_sqrt = __ldg(coef + 1);
+  const int64_t e0 = (blk - e.first_block) * 1024 + (int64_t)threadIdx.x * 4;
+  if (e0 >= e.n) return;
+  float* p = e.param; const float* g = e.grad; float* m = e.exp_avg; float* v = e.exp_avg_sq;
+  const bool vec = (e0 + 3 < e.n) && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  float pv[4], gv[4], mv[4], vv[4];
+  if (vec) {
+    const float4 a = *reinterpret_cast<const float4*>(p + e0), b = *reinterpret_cast<const float4*>(g + e0);
+    const float4 c = *reinterpret_cast<const float4*>(m + e0), d = *reinterpret_cast<const float4*>(v + e0);
+    pv[0] = a.x; pv[1] = a.y; pv[2] = a.z; pv[3] = a.w; gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+    mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w; vv[0] = d.x; vv[1] = d.y; vv[2] = d.z; vv[3] = d.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const bool ok = e0 + j < e.n;
+      pv[j] = ok ? p[e0 + j] : 0.f; gv[j] = ok ? g[e0 + j] : 0.f;
+      mv[j] = ok ? m[e0 + j] : 0.f; vv[j] = ok ? v[e0 + j] : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mv[j] = mv[j] + (gv[j] - mv[j]) * (1.0f - b1);
+    vv[j] = b2 * vv[j] + (1.0f - b2) * gv[j] * gv[j];
+    const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
+    pv[j] -= step_size * (mv[j] / denom);
+  }
+  if (vec) {
+    *reinterpret_cast<float4*>(p + e0) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    *reinterpret_cast<float4*>(m + e0) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+    *reinterpret_cast<float4*>(v + e0) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (e0 + j < e.n) { p[e0 + j] = pv[j]; m[e0 + j] = mv[j]; v[e0 + j] = vv[j]; }
+  }
+}
+
 __global__ void counter_inc_kernel(int64_t* c) { *c += 1; }
 
 }  // namespace
@@ -243,6 +291,17 @@ extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, f
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
                                                              coef_scratch);
   return check_launch("adam");
+}
+
+extern "C" int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
+                                    float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
+                                    lbbnn_stream s) {
+  LBBNN_REQUIRE(table_dev && step_dev && coef_scratch && n_entries > 0 && total_blocks > 0 && total_blocks < (1LL << 31),
+                "bad argument");
+  adam_prepare<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef_scratch);
+  if (int rc = check_launch("adam_prepare")) return rc;
+  adam_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)s>>>(table_dev, n_entries, beta1, beta2, eps, coef_scratch);
+  return check_launch("adam_multi");
 }
 
 extern "C" int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s) {

@@ -5,7 +5,7 @@ from . import _capi
 from ._capi import LbbnnError, philox_normal, philox_uniform
 from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
 from . import flows, mf, mnf
-from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer
+from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer, MultiTensorAdam
 
-__all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "lrt_linear",
+__all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "MultiTensorAdam", "lrt_linear",
            "manual_seed", "mf", "mnf", "flows", "philox_normal", "philox_uniform"]

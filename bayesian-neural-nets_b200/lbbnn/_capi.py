@@ -134,6 +134,7 @@ SIGNATURES = {
     "lbbnn_linear_f32_batched": (_INT, [_P, _I64, _P, _P, _INT, _I64, _I64, _I64, _INT, _P, _P]),
     "lbbnn_mc_accumulate_batched": (_INT, [_P, _INT, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_tf32_split": (_INT, [_P, _I64, _P, _P, _P]),
+    "lbbnn_mc_head_accumulate": (_INT, [_P, _I64, _P, _P, _INT, _I64, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_mc_prepare": (_INT, [C.POINTER(Layer), _P, _P, _P, _P]),
     "lbbnn_mc_sample_split": (_INT, [C.POINTER(Layer), _INT, _P, _U64, _U64, _U64, _INT, _P, _P, _P, _P]),
     "lbbnn_tc_linear_tf32x3": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P,
@@ -150,6 +151,7 @@ SIGNATURES = {
     "lbbnn_lrt_step_describe": (_INT, [C.POINTER(Step), C.c_char_p, _SZ]),
     "lbbnn_logsoftmax_nll_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _P, _F, _P, _P, _SZ, _P]),
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
+    "lbbnn_adam_multi_f32": (_INT, [_P, _INT, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
 }
 

@@ -534,6 +534,71 @@ class LRTTensorCoreTrainer:
     d2h_bytes_per_step = LRTTrainer.d2h_bytes_per_step
 
 
+class MultiTensorAdam:
+    """torch.optim.Adam(params, lr, betas, eps) (non-amsgrad, no weight decay; MNF:352, MF:520-553 with one learning rate)
+    as ONE launch over the whole parameter list (lbbnn_adam_multi_f32): a device table names every (param, grad, exp_avg,
+    exp_avg_sq) quadruple.  Gradient addresses are whatever autograd produced for this step: eager steps rewrite the table
+    every call; under CUDA-graph capture the addresses (stable in the graph's private pool) are recorded and the table is
+    written once after the capture (`finish_capture`)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params if p.requires_grad]
+        dev = self.params[0].device
+        self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        offs, total = [], 0
+        for p in self.params:
+            offs.append(total)
+            total += _pad4(p.numel())
+        self.offs = offs
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.table = torch.zeros(len(self.params), 6, dtype=torch.int64, device=dev)
+        self.coef = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)      # 1-based index of the update being applied
+        self._pending = None
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def _rows(self):
+        rows, blocks = [], 0
+        for p, off in zip(self.params, self.offs):
+            g = p.grad
+            if g is None:
+                continue
+            if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
+                raise K.LbbnnError("MultiTensorAdam needs contiguous fp32 parameters and gradients")
+            n = p.numel()
+            rows.append([p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr() + 4 * off,
+                         self.exp_avg_sq.data_ptr() + 4 * off, n, blocks])
+            blocks += (n + 1023) // 1024
+        return rows, blocks
+
+    def step(self):
+        rows, blocks = self._rows()
+        if not rows:
+            return
+        if torch.cuda.is_current_stream_capturing():
+            if self._pending is not None and len(self._pending) != len(rows):
+                raise K.LbbnnError("the set of parameters with gradients changed during capture")
+            self._pending = rows
+        else:
+            self.table[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))
+        st = K.current_stream()
+        K.check(K.lib.lbbnn_counter_inc(K.ptr(self.t_dev, torch.int64), st))
+        K.check(K.lib.lbbnn_adam_multi_f32(self.table.data_ptr(), len(rows), blocks, self.lr, self.betas[0], self.betas[1],
+                                           self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
+
+    def finish_capture(self):
+        if self._pending is not None:
+            self.table[:len(self._pending)].copy_(torch.tensor(self._pending, dtype=torch.int64))
+            self._pending = None
+
+
 class GraphedTrainer:
     """Whole training step of ANY of the drop-in networks (LRT, MNF, MF) as one CUDA-graph replay: forward through the
     modules' autograd Functions (liblbbnn kernels), the objective, backward and torch.optim.Adam(capturable=True) are
@@ -541,10 +606,13 @@ class GraphedTrainer:
 
     Reference: the body of `train` for one minibatch -- LBBNN-GP-MF-MNF.py:263-275 (objective="kl": nll_loss(sum) +
     net.kl()/NUM_BATCHES) and LBBNN-GP-MF.py:325-343 (objective="elbo": net.sample_elbo).  The eager modules run the
-    same kernels one Python call at a time (~8 ms per MNF step on B200, host-bound); the replay removes the host."""
+    same kernels one Python call at a time (~8 ms per MNF step on B200, host-bound); the replay removes the host.  The
+    optimizer is MultiTensorAdam by default: one launch instead of torch's ~40 multi_tensor_apply launches per step."""
 
     def __init__(self, net, batch_size, num_batches, objective="kl", lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
                  in_features=None, optimizer=None):
+        """optimizer: None = MultiTensorAdam (one launch for all parameters); "torch" = torch.optim.Adam(capturable=True);
+        or any capturable torch optimizer instance over net.parameters()."""
         K.require_device()
         self.net, self.B, self.num_batches, self.objective = net, int(batch_size), num_batches, objective
         params = list(net.parameters())
@@ -556,7 +624,12 @@ class GraphedTrainer:
         self.x = torch.zeros(self.B, in_features, dtype=torch.float32, device=dev)
         self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.opt = optimizer or torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        if optimizer is None:
+            self.opt = MultiTensorAdam(params, lr=lr, betas=betas, eps=eps)
+        elif isinstance(optimizer, str) and optimizer == "torch":
+            self.opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+        else:
+            self.opt = optimizer
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)      # [loss, nll]
         self.stats_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.x_host = torch.zeros(self.B, in_features, dtype=torch.float32).pin_memory()
@@ -573,6 +646,8 @@ class GraphedTrainer:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self._stream), K.graph_noise(self.step_dev):
             self._one_step()
+        if isinstance(self.opt, MultiTensorAdam):
+            self.opt.finish_capture()
         self.warmup_steps = 3
 
     def _one_step(self):

@@ -387,14 +387,15 @@ class MCPredictor:
     NSTREAMS = 4   # Philox streams per (sample, layer): gamma u, eps_w, eps_b, spare
 
     def __init__(self, net, batch, seed=None, use_graph=True, process_group=None, samples_per_launch=8, gemm="auto",
-                 lanes=None):
+                 lanes=None, fused_head=True):
         """samples_per_launch: weight samples pushed through every kernel of the loop together (csrc/mc_predict.cu);
         1 = the one-sample kernels.  Results do not depend on it: every sample draws from streams keyed by its index.
         gemm: "simt" = fp32 CUDA-core GEMMs; "tc" = every eligible leading layer on the tensor cores at fp32 accuracy
         (3xTF32 on tcgen05, csrc/tc_gemm_tf32.cu); "auto" = tensor cores for the leading layers at least 64 wide.
         lanes: the samples of a run() are dealt to this many independent launch sequences on their own streams (own
         buffers and accumulators), so one lane's ALU-bound weight sampling overlaps another's tensor-core GEMMs;
-        default 2 with tensor-core GEMMs, else 1."""
+        default 2 with tensor-core GEMMs, else 1.
+        fused_head: a last layer of <= 16 classes runs fused with the accumulation (lbbnn_mc_head_accumulate)."""
         K.require_device()
         if gemm not in ("auto", "simt", "tc"):
             raise ValueError(f"gemm must be 'auto', 'simt' or 'tc', got {gemm!r}")
@@ -417,6 +418,9 @@ class MCPredictor:
                     break
                 self.n_tc = i + 1
         self.prepared = SB > 1          # batched sampler reads sigma / alpha computed once per run()
+        kl, cl = sizes[-1]
+        self.fused_head = (SB > 1 and fused_head and self.n_tc < len(sizes) and len(sizes) > 1 and cl <= 16 and kl % 4 == 0 and kl <= 1024
+                           and 2 * cl * kl * 4 <= 200 * 1024)
         if self.n_tc:
             self.x_hi, self.x_lo = torch.zeros_like(self.x), torch.zeros_like(self.x)
         if self.prepared:
@@ -516,6 +520,12 @@ class MCPredictor:
                 continue
             K.check(K.lib.lbbnn_mc_sample_split(desc, n, K.ptr(lane.counter, torch.int64), self.seed & (2 ** 64 - 1),
                                                 i * self.NSTREAMS, stride, 1, K.ptr(lane.w[i]), None, K.ptr(lane.b[i]), st))
+            if i == L - 1 and self.fused_head:      # classifier head and the accumulators in one kernel, no logits
+                K.check(K.lib.lbbnn_mc_head_accumulate(K.ptr(h), hs, K.ptr(lane.w[i]), K.ptr(lane.b[i]), n, self.B,
+                                                       l.in_features, l.out_features, lane.sum_logp.data_ptr(),
+                                                       lane.sum_prob.data_ptr(), K.ptr(lane.counter, torch.int64), st))
+                self.kernels_per_launch = 2 * L + (n - 1 if self.n_tc == 1 else 0)
+                return
             K.check(K.lib.lbbnn_linear_f32_batched(K.ptr(h), hs, K.ptr(lane.w[i]), K.ptr(lane.b[i]), n, self.B,
                                                    l.in_features, l.out_features, K.FLAG_RELU if i < L - 1 else 0,
                                                    K.ptr(lane.h[i]), st))

@@ -256,6 +256,13 @@ LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, in
  *                        All samples of a launch sharing one input (the first layer) = ONE problem with batches = 1 and
  *                        N = n_samples * out_features; its (batch, n_samples * out) output is the next layer's strided a. */
 LBBNN_API int lbbnn_tf32_split(const float* x, int64_t n, float* hi, float* lo, lbbnn_stream s);
+/* Classifier head + accumulation in one launch: logits[s] = h[s] W[s]^T + bias[s] for the n_samples samples of a launch
+ * (h: sample s at h + s * h_stride, (batch, in_features) row-major; W (n_samples, classes, in_features); classes <= 16,
+ * in_features % 4 == 0 and <= 1024), then exactly mc_accumulate_batched on them (same expressions, samples in order).  The logits
+ * are never written. */
+LBBNN_API int lbbnn_mc_head_accumulate(const float* h, int64_t h_stride, const float* W, const float* bias, int n_samples,
+                                       int64_t batch, int64_t in_features, int64_t classes, double* sum_logp,
+                                       double* sum_prob, int64_t* counter, lbbnn_stream s);
 LBBNN_API int lbbnn_mc_prepare(const lbbnn_layer* layer, float* sigma, float* alpha, float* bias_sigma, lbbnn_stream s);
 LBBNN_API int lbbnn_mc_sample_split(const lbbnn_layer* layer, int n_samples, const int64_t* first_sample_dev, uint64_t seed,
                                     uint64_t stream_base, uint64_t stream_stride, int prepared, float* w_hi, float* w_lo,
@@ -369,6 +376,21 @@ LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* targe
 LBBNN_API int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              float lr, float beta1, float beta2, float eps, const int64_t* step_dev,
                              float* coef_scratch, lbbnn_stream s);
+/* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF / MF scripts,
+ * MNF:352, MF:520-553 with one learning rate): table_dev = device array of n_entries records; block b of the launch
+ * updates elements [(b - first_block) * 1024, +1024) of the tensor with the largest first_block <= b, so first_block
+ * is the running sum of ceil(n / 1024) and total_blocks its final value. */
+typedef struct lbbnn_adam_entry {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  int64_t first_block;
+} lbbnn_adam_entry;
+LBBNN_API int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
+                                   float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
+                                   lbbnn_stream s);
 LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ def split(x):
 
 out = {}
 B = 1000
-for SB in (8, 16, 32):
+for SB in (32,):
     for (k, o, shared) in ((784, 400, True), (400, 600, False)):
         x = torch.rand((B, k) if shared else (SB, B, k), device=dev)
         w = torch.randn(SB, o, k, device=dev) * 0.1 * (torch.rand(SB, o, k, device=dev) < 0.5)
@@ -58,15 +58,32 @@ for SB in (8, 16, 32):
                                   "simt_us": round(us_simt, 1), "simt_tflops": round(fl / us_simt / 1e6, 1), "simt_err": err_simt}
         print(f"SB{SB}_{k}x{o}", out[f"SB{SB}_{k}x{o}"], flush=True)
 
+# classifier head: fused GEMV + accumulation kernel vs batched SIMT GEMM + accumulation kernel
+for SB in (16, 32):
+    k, c = 600, 10
+    h = torch.rand(SB, B, k, device=dev)
+    w = torch.randn(SB, c, k, device=dev) * 0.1
+    bias = torch.rand(SB, c, device=dev)
+    logits = torch.empty(SB, B, c, device=dev)
+    sl, sp = torch.zeros(B, c, dtype=torch.float64, device=dev), torch.zeros(B, c, dtype=torch.float64, device=dev)
+    sl2, sp2 = torch.zeros_like(sl), torch.zeros_like(sp)
+    us_g = timed(lambda: K.lib.lbbnn_linear_f32_batched(K.ptr(h), B * k, K.ptr(w), K.ptr(bias), SB, B, k, c, 0, K.ptr(logits), st))
+    us_a = timed(lambda: K.lib.lbbnn_mc_accumulate_batched(K.ptr(logits), SB, B, c, sl.data_ptr(), sp.data_ptr(), None, st))
+    us_f = timed(lambda: K.lib.lbbnn_mc_head_accumulate(K.ptr(h), B * k, K.ptr(w), K.ptr(bias), SB, B, k, c, sl2.data_ptr(),
+                                                        sp2.data_ptr(), None, st))
+    out[f"head_SB{SB}"] = {"sgemm_us": round(us_g, 1), "accumulate_us": round(us_a, 1), "fused_us": round(us_f, 1),
+                           "rel_diff": ((sl2 - sl).abs().max() / sl.abs().max()).item()}
+    print(f"head_SB{SB}", out[f"head_SB{SB}"], flush=True)
+
 net = lbbnn.mf.BayesianNetwork().to(dev)
 with torch.no_grad():
     for l in net.layers:
         l.lambdal.normal_(0, 2)
 x = torch.rand(B, 784, device=dev)
 S = 1152
-for gemm, SB, lanes in (("simt", 21, 1), ("simt", 21, 2), ("auto", 16, 1), ("auto", 32, 1), ("auto", 48, 1), ("auto", 16, 2),
-                        ("auto", 24, 2), ("auto", 32, 2), ("auto", 48, 2), ("auto", 16, 3), ("auto", 32, 3), ("auto", 16, 4)):
-    mc = lbbnn.mf.MCPredictor(net, batch=B, seed=1, samples_per_launch=SB, gemm=gemm, lanes=lanes)
+for gemm, SB, lanes, fh in (("simt", 21, 1, False), ("auto", 32, 1, False), ("auto", 32, 1, True), ("auto", 32, 2, False),
+                            ("auto", 32, 2, True), ("auto", 48, 2, True), ("auto", 32, 3, True), ("auto", 64, 2, True)):
+    mc = lbbnn.mf.MCPredictor(net, batch=B, seed=1, samples_per_launch=SB, gemm=gemm, lanes=lanes, fused_head=fh)
     mc.run(x, S); torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
@@ -75,7 +92,7 @@ for gemm, SB, lanes in (("simt", 21, 1), ("simt", 21, 2), ("auto", 16, 1), ("aut
     b.record(); b.synchronize()
     r = S * 3 / (a.elapsed_time(b) * 1e-3)
     pred = mc.result(S)["pred"]
-    key = f"mc_{gemm}_SB{SB}_L{lanes}"
+    key = f"mc_{gemm}_SB{SB}_L{lanes}_{'fused' if fh else 'split'}head"
     out[key] = {"samples_per_s": round(r), "n_tc": mc.n_tc}
     if gemm == "simt" and lanes == 1:
         base_pred, base_logp = pred.clone(), mc.sum_logp.clone()

@@ -291,3 +291,27 @@ def test_step_async_returns_every_steps_stats_one_call_late(lb):
         seqs.append((out, tr.flat.clone()))
     for other in seqs[1:]:
         assert other[0] == seqs[0][0] and torch.equal(other[1], seqs[0][1])
+
+
+def test_multi_tensor_adam_matches_torch_adam(lb):
+    """MultiTensorAdam (one launch over a table of tensors, lbbnn_adam_multi_f32) against torch.optim.Adam on a ragged
+    parameter list -- sizes around the 1024-element block and the float4 boundaries, a parameter without gradient."""
+    torch.manual_seed(5)
+    shapes = [(400, 784), (75,), (1,), (1023,), (1024,), (1025,), (3, 341), (75, 75), (2049,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    unused = torch.nn.Parameter(torch.randn(17, device="cuda"))
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    ours = lb.MultiTensorAdam(ps + [unused], lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    ref = torch.optim.Adam(qs, lr=1e-2, betas=(0.9, 0.999), eps=1e-8)
+    u0 = unused.detach().clone()
+    for step in range(5):
+        ours.zero_grad()
+        ref.zero_grad()
+        for p, q in zip(ps, qs):
+            g = torch.randn_like(p) * (10.0 ** (step - 2))
+            p.grad, q.grad = g.clone(), g.clone()
+        ours.step()
+        ref.step()
+        for p, q in zip(ps, qs):
+            assert C.rel_err(p.detach(), q.detach()) < 1e-6
+    assert torch.equal(unused.detach(), u0) and int(ours.t_dev) == 5

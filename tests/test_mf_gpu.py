@@ -172,8 +172,10 @@ def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl, 
             for k, v in p.items():
                 getattr(l, k).copy_(v)
     S = 12
-    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph, samples_per_launch=spl, gemm=gemm)
-    assert mc.n_tc == (3 if gemm == "tc" else 0)
+    # spl == 5 keeps the separate head GEMM + accumulation kernels covered; the others fuse the 10-class head
+    mc = lb.mf.MCPredictor(net, batch=50, seed=77, use_graph=use_graph, samples_per_launch=spl, gemm=gemm,
+                           fused_head=spl != 5)
+    assert mc.n_tc == (3 if gemm == "tc" else 0) and mc.fused_head == (spl in (8, 16) and gemm != "tc")
     mc.run(case["x"].cuda(), S)
     res = mc.result(S)
     ref_logp, ref_prob = _oracle_mc(case["layers"], case["x"], 77, S, lb)
