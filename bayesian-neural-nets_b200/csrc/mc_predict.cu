@@ -283,7 +283,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kHeadQ = 8;        // float4 per lane held in registers: in_features <= 1024
+constexpr int kHeadQ = 5;        // float4 per lane and row held in registers: in_features <= 640
+constexpr int kHeadRows = 2;     // input rows per warp: every weight float4 read from shared memory feeds two rows
+constexpr int kHeadThreads = 128;
 
 struct HeadArgs {
   const float *h, *W, *bias;   // (SB, B, K), (SB, C, K), (SB, C)
@@ -293,40 +295,90 @@ struct HeadArgs {
   int64_t* counter;
 };
 
+// v[c], c < 16, summed over the 32 lanes; lane L returns the total of class L >> 1 (16 shuffles instead of 5 per class):
+// at offset 16 / 8 / 4 / 2 a lane keeps the half of its values selected by that bit of its index and adds the partner's
+// copy of the same half, so each step halves the values per lane; offset 1 is a plain sum.
+__device__ __forceinline__ float transpose_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const bool up = lane & 16;
+    const float keep = up ? v[c + 8] : v[c], send = up ? v[c] : v[c + 8];
+    v[c] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const bool up = lane & 8;
+    const float keep = up ? v[c + 4] : v[c], send = up ? v[c] : v[c + 4];
+    v[c] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const bool up = lane & 4;
+    const float keep = up ? v[c + 2] : v[c], send = up ? v[c] : v[c + 2];
+    v[c] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const bool up = lane & 2;
+    const float keep = up ? v[1] : v[0], send = up ? v[0] : v[1];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// reductions over the 16 class slots (lanes differing in bits 1..4; bit 0 holds a duplicate)
+__device__ __forceinline__ float class_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float class_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 template <int C>
-__global__ void __launch_bounds__(kThreads) mc_head_accumulate_kernel(const HeadArgs a) {
+__global__ void __launch_bounds__(kHeadThreads) mc_head_accumulate_kernel(const HeadArgs a) {
   extern __shared__ float4 wbuf[];                 // 2 x (C * K / 4)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int K4 = a.K >> 2, CK4 = C * K4;
-  const int b = blockIdx.x * (kThreads / 32) + warp;
-  const bool live = b < a.B;
+  const int b0 = (blockIdx.x * (kHeadThreads / 32) + warp) * kHeadRows;    // this warp's rows b0 .. b0 + kHeadRows - 1
+  const int cls = lane >> 1;                                                // the class this lane accumulates
+  const bool owner = (lane & 1) == 0 && cls < C;
   auto stage = [&](int s, int buf) {
     const float4* src = reinterpret_cast<const float4*>(a.W + (int64_t)s * C * a.K);
-    for (int i = tid; i < CK4; i += kThreads) cp_async16(&wbuf[buf * CK4 + i], src + i);
+    for (int i = tid; i < CK4; i += kHeadThreads) cp_async16(&wbuf[buf * CK4 + i], src + i);
     cp_async_commit();
   };
   stage(0, 0);
-  double run_lp = 0.0, run_pr = 0.0;
-  if (live && lane < C) {
-    run_lp = a.sum_logp[(int64_t)b * C + lane];
-    run_pr = a.sum_prob[(int64_t)b * C + lane];
-  }
-  // the warp's activation row of the NEXT sample is fetched into registers (all kHeadQ float4 loads in flight at once)
-  // while the current sample's dot products run
-  float4 hn[kHeadQ];
-  auto fetch = [&](int s) {
-    const float4* hr = reinterpret_cast<const float4*>(a.h + (int64_t)s * a.hs + (int64_t)b * a.K);
+  double run_lp[kHeadRows], run_pr[kHeadRows];
 #pragma unroll
-    for (int q = 0; q < kHeadQ; ++q) {
-      const int k4 = lane + 32 * q;
-      hn[q] = (live && k4 < K4) ? __ldg(hr + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int r = 0; r < kHeadRows; ++r) {
+    const bool ok = owner && b0 + r < a.B;
+    run_lp[r] = ok ? a.sum_logp[(int64_t)(b0 + r) * C + cls] : 0.0;
+    run_pr[r] = ok ? a.sum_prob[(int64_t)(b0 + r) * C + cls] : 0.0;
+  }
+  // the warp's activation rows of the NEXT sample are fetched into registers (all loads in flight at once) while the
+  // current sample's dot products run
+  float4 hn[kHeadRows][kHeadQ];
+  auto fetch = [&](int s) {
+#pragma unroll
+    for (int r = 0; r < kHeadRows; ++r) {
+      const float4* hr = reinterpret_cast<const float4*>(a.h + (int64_t)s * a.hs + (int64_t)(b0 + r) * a.K);
+#pragma unroll
+      for (int q = 0; q < kHeadQ; ++q) {
+        const int k4 = lane + 32 * q;
+        hn[r][q] = (b0 + r < a.B && k4 < K4) ? __ldg(hr + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   };
   fetch(0);
   for (int s = 0; s < a.n_samples; ++s) {
-    float4 hv[kHeadQ];
+    float4 hv[kHeadRows][kHeadQ];
 #pragma unroll
-    for (int q = 0; q < kHeadQ; ++q) hv[q] = hn[q];
+    for (int r = 0; r < kHeadRows; ++r)
+#pragma unroll
+      for (int q = 0; q < kHeadQ; ++q) hv[r][q] = hn[r][q];
     if (s + 1 < a.n_samples) {
       stage(s + 1, (s + 1) & 1);
       fetch(s + 1);
@@ -335,11 +387,13 @@ __global__ void __launch_bounds__(kThreads) mc_head_accumulate_kernel(const Head
       cp_async_wait<0>();
     }
     __syncthreads();                               // sample s's weights are in wbuf[s & 1]
-    if (live) {
+    if (b0 < a.B) {
       const float4* w = wbuf + (s & 1) * CK4;
-      float acc[C];
+      float acc[kHeadRows][16];
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[c] = 0.f;
+      for (int r = 0; r < kHeadRows; ++r)
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
 #pragma unroll
       for (int q = 0; q < kHeadQ; ++q) {
         if (q * 32 < K4) {                         // warp-uniform
@@ -347,42 +401,35 @@ __global__ void __launch_bounds__(kThreads) mc_head_accumulate_kernel(const Head
 #pragma unroll
           for (int c = 0; c < C; ++c) {
             const float4 wv = w[c * K4 + k4];
-            acc[c] = fmaf(hv[q].x, wv.x, fmaf(hv[q].y, wv.y, fmaf(hv[q].z, wv.z, fmaf(hv[q].w, wv.w, acc[c]))));
+#pragma unroll
+            for (int r = 0; r < kHeadRows; ++r)
+              acc[r][c] = fmaf(hv[r][q].x, wv.x, fmaf(hv[r][q].y, wv.y, fmaf(hv[r][q].z, wv.z, fmaf(hv[r][q].w, wv.w, acc[r][c]))));
           }
         }
       }
-      const float* bias = a.bias + (int64_t)s * C;
-      float mx = -INFINITY;
+      const float bias = cls < C ? __ldg(a.bias + (int64_t)s * C + cls) : 0.f;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-        acc[c] += __ldg(bias + c);
-        mx = fmaxf(mx, acc[c]);
-      }
-      float se = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) se += expf(acc[c] - mx);
-      const float lse = mx + logf(se);
-      float ps = 0.f, mylp = 0.f, mye = 0.f;
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        const float lp = acc[c] - lse;
-        const float e = 1.0f / (1.0f + expf(-lp));
-        ps += e;
-        if (lane == c) { mylp = lp; mye = e; }
-      }
-      if (lane < C) {
-        run_lp += (double)mylp;
-        run_pr += (double)(mye / ps);
+      for (int r = 0; r < kHeadRows; ++r) {
+        const float logit = transpose_reduce16(acc[r], lane) + bias;          // class cls of row b0 + r
+        const float mx = class_max(cls < C ? logit : -INFINITY);
+        const float se = class_sum(cls < C ? expf(logit - mx) : 0.f);
+        const float lp = logit - (mx + logf(se));
+        const float e = cls < C ? 1.0f / (1.0f + expf(-lp)) : 0.f;
+        const float ps = class_sum(e);
+        if (owner) {
+          run_lp[r] += (double)lp;
+          run_pr[r] += (double)(e / ps);
+        }
       }
     }
     __syncthreads();                               // everyone is done with wbuf[s & 1] before sample s + 2 lands in it
   }
-  if (live && lane < C) {
-    a.sum_logp[(int64_t)b * C + lane] = run_lp;
-    a.sum_prob[(int64_t)b * C + lane] = run_pr;
-  }
+#pragma unroll
+  for (int r = 0; r < kHeadRows; ++r)
+    if (owner && b0 + r < a.B) {
+      a.sum_logp[(int64_t)(b0 + r) * C + cls] = run_lp[r];
+      a.sum_prob[(int64_t)(b0 + r) * C + cls] = run_pr[r];
+    }
   if (a.counter && blockIdx.x == 0 && tid == 0) *a.counter += a.n_samples;
 }
 
@@ -395,7 +442,7 @@ int launch_head(const HeadArgs& a, cudaStream_t s) {
     LBBNN_CUDA(cudaFuncSetAttribute(mc_head_accumulate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  mc_head_accumulate_kernel<C><<<(unsigned)ceil_div(a.B, kThreads / 32), kThreads, smem, s>>>(a);
+  mc_head_accumulate_kernel<C><<<(unsigned)ceil_div(a.B, kHeadRows * kHeadThreads / 32), kHeadThreads, smem, s>>>(a);
   return check_launch("mc_head_accumulate");
 }
 

@@ -77,6 +77,16 @@ class FlowGrads(C.Structure):
     _fields_ = [("row_stride", C.c_int64), ("t", FlowTransformGrads * FLOW_MAX_T)]
 
 
+class MnfAux(C.Structure):
+    _fields_ = [("in_features", C.c_int64), ("out_features", C.c_int64)] + [
+        (n, C.c_void_p) for n in ("q0_mean", "q0_log_var", "z0", "r0_c", "r0_b1", "r0_b2", "z2", "M0", "V", "eps_r", "z_b")]
+
+
+class MnfAuxGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("d_q0_mean", "d_q0_log_var", "d_z0", "d_r0_c", "d_r0_b1", "d_r0_b2", "d_z2",
+                                          "d_z_b", "dM0", "dV")]
+
+
 STEP_MAX_LAYERS = 8
 
 
@@ -144,6 +154,9 @@ SIGNATURES = {
     "lbbnn_flow_save_floats": (_SZ, [C.POINTER(Flow), _I64]),
     "lbbnn_flow_fwd": (_INT, [C.POINTER(Flow), _P, _I64, _P, C.POINTER(Noise), _P, _P, _P, _P]),
     "lbbnn_flow_bwd": (_INT, [C.POINTER(Flow), C.POINTER(FlowGrads), _I64, _P, C.POINTER(Noise), _P, _P, _P, _P, _P]),
+    "lbbnn_mnf_aux_save_floats": (_SZ, [_I64]),
+    "lbbnn_mnf_aux_kl_fwd": (_INT, [C.POINTER(MnfAux), _P, _P, _P, _P]),
+    "lbbnn_mnf_aux_kl_bwd": (_INT, [C.POINTER(MnfAux), _P, _P, C.POINTER(MnfAuxGrads), _P]),
     "lbbnn_lrt_step_workspace_bytes": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_raw_floats": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_f32": (_INT, [C.POINTER(Step), _INT, _P, _SZ, _P]),

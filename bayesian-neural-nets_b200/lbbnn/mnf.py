@@ -4,16 +4,15 @@ LBBNN-GP-MF-MNFsim_study.py:145-251 through the prior / init keyword arguments).
 What runs where: the z flows and the auxiliary r flow -> fused flow kernels (flows.py); the activation
 path mm(x*z, M^T), mm(x^2, V^T), eps/sqrt -> the fused LRT kernels with z folded into the weight prologue
 (MNF:197-198: mm(x*z, M^T) == mm(x, (M*z)^T) because z is a single (in,) vector); the KL over all weights
-with (mu*z2 - mu_p)^2 (MNF:230-233) and the W_mean/W_var moments -> prologue/finalize kernels; the two
-auxiliary GEMVs r0_c @ W^T (MNF:216-217) -> the fp32 GEMM kernels.  Only O(in)+O(out) vector glue
-(log q0, tanh, the outer-product means, log r_b) stays in torch.
+with (mu*z2 - mu_p)^2 (MNF:230-233) and the W_mean/W_var moments -> prologue/finalize kernels; log q0, the two
+auxiliary GEMVs r0_c @ W^T (MNF:216-217), tanh, the outer-product means and log r_b -> one fused forward and one
+fused backward kernel (csrc/mnf_aux.cu).  Only z0 = q0_mean + sqrt(exp(q0_log_var)) eps and the final scalar sum
+stay in torch.
 
 Reference quirks kept: one z (the last batch row's) is broadcast over the batch, so only
 that row is pushed through the flow; the KL branch draws its own z (self.z becomes (1,in)); z_b[-1] in
 log r_b is the last ELEMENT of the flowed vector; log pi (not log 2 pi) in both Gaussians.
 """
-import math
-
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -21,7 +20,6 @@ import torch.nn.functional as F
 from . import _capi as K
 from .flows import PropagateFlow
 from .lrt import BernoulliView, GaussianView, LayerConfig, _LRTFunction, current_seed, _layer_ids
-from .mf import _Linear
 
 
 class _MomentsKL(torch.autograd.Function):
@@ -60,6 +58,40 @@ class _MomentsKL(torch.autograd.Function):
         return (*grads, dz, None)
 
 
+class _AuxKL(torch.autograd.Function):
+    """log_q0 - log_rb of the KL branch (MNF:212-227 minus the flows) in one forward and one backward kernel
+    (csrc/mnf_aux.cu).  Inputs: q0_mean, q0_log_var, z0 (the KL row's pre-flow draw), r0_c, r0_b1, r0_b2, z2 (its flow
+    image), M0 = alpha mu, V, eps_r, z_b = r_flow(z2)."""
+
+    @staticmethod
+    def forward(ctx, q0_mean, q0_log_var, z0, r0_c, r0_b1, r0_b2, z2, M0, V, eps_r, z_b, ticket):
+        K.require_device()
+        ts = [t.contiguous() for t in (q0_mean, q0_log_var, z0, r0_c, r0_b1, r0_b2, z2, M0, V, eps_r, z_b)]
+        O, D = ts[7].shape
+        dev = ts[7].device
+        out = torch.empty(3, dtype=torch.float32, device=dev)
+        save = torch.empty(int(K.lib.lbbnn_mnf_aux_save_floats(O)), dtype=torch.float32, device=dev)
+        aux = K.MnfAux(D, O, *[K.ptr(t) for t in ts])
+        K.check(K.lib.lbbnn_mnf_aux_kl_fwd(aux, K.ptr(out), K.ptr(save), ticket.data_ptr(), K.current_stream()))
+        ctx.save_for_backward(*ts, save)
+        ctx.shapes = [t.shape for t in (q0_mean, q0_log_var, z0, r0_c, r0_b1, r0_b2, z2, z_b)]
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        *ts, save = ctx.saved_tensors
+        O, D = ts[7].shape
+        dev = ts[7].device
+        vec = torch.empty(8, D, dtype=torch.float32, device=dev)
+        dM0, dV = torch.empty_like(ts[7]), torch.empty_like(ts[8])
+        aux = K.MnfAux(D, O, *[K.ptr(t) for t in ts])
+        grads = K.MnfAuxGrads(*[vec[i].data_ptr() for i in range(8)], K.ptr(dM0), K.ptr(dV))
+        K.check(K.lib.lbbnn_mnf_aux_kl_bwd(aux, K.ptr(save), K.ptr(g.contiguous().float()), grads, K.current_stream()))
+        v = [vec[i].view(ctx.shapes[i]) for i in range(8)]
+        #      q0_mean q0_lv z0    r0_c  b1    b2    z2    M0   V   eps_r z_b  ticket
+        return v[0], v[1], v[2], v[3], v[4], v[5], v[6], dM0, dV, None, v[7], None
+
+
 class BayesianLinear(nn.Module):
     """MNF layer, drop-in for LBBNN-GP-MF-MNF.py:133-239: ctor `(in_features, out_features, num_transforms)`.
     `noise=` on forward injects the draws of SURVEY.md §3.2 (see tests/cases.py:mnf_noise)."""
@@ -92,6 +124,7 @@ class BayesianLinear(nn.Module):
         self._uid = next(_layer_ids)
         self._calls = 0
         self.last_noise_key = None
+        self._aux_ticket = None
         if device is not None:
             self.to(device)
 
@@ -126,19 +159,15 @@ class BayesianLinear(nn.Module):
         z2 = zs[1]
         log_det_q = logdets if logdets.dim() == 0 else logdets[1]       # IAF kind: one scalar over everything
         M0, V, kl_wb = _MomentsKL.apply(self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z2, self.cfg)
-        log_q0 = (-0.5 * math.log(math.pi) - 0.5 * self.q0_log_var
-                  - 0.5 * ((self.z - self.q0_mean) ** 2 / self.q0_log_var.exp())).sum()
-        log_q = -log_det_q + log_q0
-        zero_b = torch.zeros(self.out_features, device=dev)
-        act_mu = _Linear.apply((self.r0_c * z2)[None], M0, zero_b)[0]    # r0_c @ W_mean^T, W_mean = z2 mu alpha (MNF:211,216)
-        act_var = _Linear.apply((self.r0_c ** 2)[None], V, zero_b)[0]    # MNF:217
         eps_r = nz["eps_r"] if "eps_r" in nz else torch.randn(self.out_features, device=dev)
-        a_r = torch.tanh(act_mu + act_var.sqrt() * eps_r)
-        mean_r = self.r0_b1 * a_r.mean()                                 # outer(b1, act).mean(-1)  (MNF:220)
-        log_var_r = self.r0_b2 * a_r.mean()
         z_b, log_det_r = self.r_flow(z2, nz.get("r_masks"))
-        log_rb = (-0.5 * math.log(math.pi) - 0.5 * log_var_r - 0.5 * ((z_b[-1] - mean_r) ** 2 / log_var_r.exp())).sum()
-        return z_k, kl_wb + log_q - (log_det_r + log_rb)
+        if self._aux_ticket is None or self._aux_ticket.device != dev:
+            self._aux_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        # log_q0 (MNF:212-214) - log_rb (MNF:216-227): the GEMVs r0_c @ W_mean^T, r0_c^2 @ W_var^T with W_mean = z2 mu alpha
+        # (z2 folded into the vector side), tanh, the outer-product means and the two Gaussian sums, fused
+        aux = _AuxKL.apply(self.q0_mean, self.q0_log_var, self.z, self.r0_c, self.r0_b1, self.r0_b2, z2, M0, V, eps_r, z_b,
+                           self._aux_ticket)
+        return z_k, kl_wb + aux - log_det_q - log_det_r
 
     def _activation(self, input, z_k, sample_branch, nz):
         self._calls += 1

@@ -258,7 +258,7 @@ LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, in
 LBBNN_API int lbbnn_tf32_split(const float* x, int64_t n, float* hi, float* lo, lbbnn_stream s);
 /* Classifier head + accumulation in one launch: logits[s] = h[s] W[s]^T + bias[s] for the n_samples samples of a launch
  * (h: sample s at h + s * h_stride, (batch, in_features) row-major; W (n_samples, classes, in_features); classes <= 16,
- * in_features % 4 == 0 and <= 1024), then exactly mc_accumulate_batched on them (same expressions, samples in order).  The logits
+ * in_features % 4 == 0 and <= 640), then exactly mc_accumulate_batched on them (same expressions, samples in order).  The logits
  * are never written. */
 LBBNN_API int lbbnn_mc_head_accumulate(const float* h, int64_t h_stride, const float* W, const float* bias, int n_samples,
                                        int64_t batch, int64_t in_features, int64_t classes, double* sum_logp,
@@ -314,6 +314,29 @@ LBBNN_API int lbbnn_flow_fwd(const lbbnn_flow* flow, const float* z_in, int64_t 
 LBBNN_API int lbbnn_flow_bwd(const lbbnn_flow* flow, const lbbnn_flow_grads* grads, int64_t rows, const float* masks,
                              const lbbnn_noise* mask_u, const float* dz_out, const float* dlogdet, const float* save,
                              float* dz_in, lbbnn_stream s);
+
+/* ---- MNF auxiliary KL terms (MNF:208-235 minus the flows and the weight KL; csrc/mnf_aux.cu) -----------------------
+ * out3 = [log_q0 - log_rb, log_q0, log_rb] with
+ *   log_q0 = sum_i -0.5 log(pi) - 0.5 q0_log_var_i - 0.5 (z0_i - q0_mean_i)^2 / exp(q0_log_var_i)          (MNF:212-214)
+ *   a_r    = tanh(M0 (r0_c * z2) + sqrt(V r0_c^2) * eps_r),  M0 = alpha mu, V = sigma^2 alpha^2 (out,in)   (MNF:211,216-219)
+ *   log_rb = sum_i -0.5 log(pi) - 0.5 r0_b2_i mean(a_r) - 0.5 (z_b[in-1] - r0_b1_i mean(a_r))^2 / exp(r0_b2_i mean(a_r))
+ * z0 = the KL row's pre-flow draw (what the reference leaves in self.z), z2 = its z-flow image, z_b = r_flow(z2).
+ * save: lbbnn_mnf_aux_save_floats(out) floats kept for the backward; ticket: one zero-initialised device word per layer.
+ * bwd: gout = d loss / d out3[0] (device scalar); every gradient is WRITTEN (not accumulated); dM0, dV are (out,in). */
+typedef struct lbbnn_mnf_aux {
+  int64_t in_features, out_features;
+  const float *q0_mean, *q0_log_var, *z0;
+  const float *r0_c, *r0_b1, *r0_b2;
+  const float *z2, *M0, *V, *eps_r, *z_b;
+} lbbnn_mnf_aux;
+typedef struct lbbnn_mnf_aux_grads {
+  float *d_q0_mean, *d_q0_log_var, *d_z0, *d_r0_c, *d_r0_b1, *d_r0_b2, *d_z2, *d_z_b;   /* (in,) each */
+  float *dM0, *dV;                                                                      /* (out,in) */
+} lbbnn_mnf_aux_grads;
+LBBNN_API size_t lbbnn_mnf_aux_save_floats(int64_t out_features);
+LBBNN_API int lbbnn_mnf_aux_kl_fwd(const lbbnn_mnf_aux* aux, float* out3, float* save, unsigned int* ticket, lbbnn_stream s);
+LBBNN_API int lbbnn_mnf_aux_kl_bwd(const lbbnn_mnf_aux* aux, const float* save, const float* gout,
+                                   const lbbnn_mnf_aux_grads* grads, lbbnn_stream s);
 
 /* ---- whole LRT training step as ONE persistent cooperative kernel (small stacks, batch <= 128) --------
  * Replaces the body of `train` for one minibatch (LRT:217-229): forward of every layer (LRT:166-211),

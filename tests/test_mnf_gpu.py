@@ -224,3 +224,35 @@ def test_graphed_trainer_replays_the_eager_step_with_fresh_noise(lb, kind):
     tr2 = lb.GraphedTrainer(net2, batch_size=64, num_batches=C.NUM_BATCHES, lr=1e-3, objective=objective)
     nll = [tr2.step(x, y)["nll"] for _ in range(60)]
     assert np.mean(nll[-10:]) < np.mean(nll[:10])                  # it trains
+
+
+@pytest.mark.parametrize("D,O", [(784, 400), (50, 10), (33, 7)])
+def test_aux_kl_kernels_match_the_eager_formulation(lb, D, O):
+    """log_q0 - log_rb (MNF:212-227) from the fused kernels (csrc/mnf_aux.cu) against the same terms written with torch
+    ops in float64, values and every gradient."""
+    import math
+    from lbbnn.mnf import _AuxKL
+    rng = np.random.default_rng(D + O)
+    mk = lambda *s, scale=1.0, off=0.0: (C.t(rng.standard_normal(size=s)) * scale + off).cuda().requires_grad_(True)  # noqa: E731
+    q0_mean, q0_lv, r0_c, b1, b2 = mk(D, scale=0.1), mk(D, scale=0.1, off=-3.0), mk(D, scale=0.1), mk(D, scale=0.1), mk(D, scale=0.1)
+    z0, z2, z_b = mk(1, D, scale=0.3), mk(D, scale=0.5, off=1.0), mk(D)
+    M0, V = mk(O, D, scale=0.05), (C.t(rng.random(size=(O, D))) * 1e-3 + 1e-5).cuda().requires_grad_(True)
+    eps_r = C.t(rng.standard_normal(size=(O,))).cuda()
+    ins = [q0_mean, q0_lv, z0, r0_c, b1, b2, z2, M0, V, eps_r, z_b]
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = _AuxKL.apply(*ins, ticket)
+    out.backward()
+    assert int(ticket) == 0
+    got = [t.grad.clone() for t in ins if t.requires_grad]
+    d = [t.detach().double().requires_grad_(t.requires_grad) for t in ins]
+    q0_mean, q0_lv, z0, r0_c, b1, b2, z2, M0, V, eps_r, z_b = d
+    log_q0 = (-0.5 * math.log(math.pi) - 0.5 * q0_lv - 0.5 * ((z0 - q0_mean) ** 2 / q0_lv.exp())).sum()
+    a_r = torch.tanh((r0_c * z2) @ M0.T + ((r0_c ** 2) @ V.T).sqrt() * eps_r)
+    mean_r, lvr = b1 * a_r.mean(), b2 * a_r.mean()
+    log_rb = (-0.5 * math.log(math.pi) - 0.5 * lvr - 0.5 * ((z_b[-1] - mean_r) ** 2 / lvr.exp())).sum()
+    ref = log_q0 - log_rb
+    ref.backward()
+    assert abs(out.item() - ref.item()) / abs(ref.item()) < 1e-5
+    for g, t, name in zip(got, [t for t in d if t.requires_grad],
+                          ["q0_mean", "q0_log_var", "z0", "r0_c", "r0_b1", "r0_b2", "z2", "M0", "V", "z_b"]):
+        assert C.rel_err(g, t.grad.float()) < 2e-5, name
