@@ -283,9 +283,14 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-constexpr int kHeadQ = 5;        // float4 per lane and row held in registers: in_features <= 640
 constexpr int kHeadRows = 2;     // input rows per warp: every weight float4 read from shared memory feeds two rows
 constexpr int kHeadThreads = 128;
+constexpr int kHeadBlockRows = kHeadRows * kHeadThreads / 32;
+constexpr int kHeadStages = 4;   // samples in flight (cp.async): weights and activations of sample s + 3 load during s
+constexpr size_t kHeadSmemMax = 220 * 1024;
+inline size_t head_smem_bytes(int64_t classes, int64_t K) {
+  return (size_t)kHeadStages * (size_t)(classes + kHeadBlockRows) * (size_t)K * sizeof(float);
+}
 
 struct HeadArgs {
   const float *h, *W, *bias;   // (SB, B, K), (SB, C, K), (SB, C)
@@ -339,18 +344,27 @@ __device__ __forceinline__ float class_sum(float v) {
 
 template <int C>
 __global__ void __launch_bounds__(kHeadThreads) mc_head_accumulate_kernel(const HeadArgs a) {
-  extern __shared__ float4 wbuf[];                 // 2 x (C * K / 4)
+  // kHeadStages buffers of [ C x K weights of one sample | this block's kHeadBlockRows x K activations of that sample ]
+  extern __shared__ float4 sbuf[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int K4 = a.K >> 2, CK4 = C * K4;
-  const int b0 = (blockIdx.x * (kHeadThreads / 32) + warp) * kHeadRows;    // this warp's rows b0 .. b0 + kHeadRows - 1
+  const int K4 = a.K >> 2, CK4 = C * K4, stage4 = CK4 + kHeadBlockRows * K4;
+  const int blk0 = blockIdx.x * kHeadBlockRows;                             // first row of this block
+  const int rows_here = min(kHeadBlockRows, a.B - blk0);
+  const int b0 = blk0 + warp * kHeadRows;                                   // this warp's rows b0 .. b0 + kHeadRows - 1
   const int cls = lane >> 1;                                                // the class this lane accumulates
   const bool owner = (lane & 1) == 0 && cls < C;
-  auto stage = [&](int s, int buf) {
-    const float4* src = reinterpret_cast<const float4*>(a.W + (int64_t)s * C * a.K);
-    for (int i = tid; i < CK4; i += kHeadThreads) cp_async16(&wbuf[buf * CK4 + i], src + i);
+  auto stage = [&](int s) {                        // always commits a group so that group s == sample s
+    if (s < a.n_samples) {
+      float4* dst = sbuf + (s % kHeadStages) * stage4;
+      const float4* wsrc = reinterpret_cast<const float4*>(a.W + (int64_t)s * C * a.K);
+      for (int i = tid; i < CK4; i += kHeadThreads) cp_async16(dst + i, wsrc + i);
+      const float4* hsrc = reinterpret_cast<const float4*>(a.h + (int64_t)s * a.hs + (int64_t)blk0 * a.K);
+      for (int i = tid; i < rows_here * K4; i += kHeadThreads) cp_async16(dst + CK4 + i, hsrc + i);
+    }
     cp_async_commit();
   };
-  stage(0, 0);
+#pragma unroll
+  for (int s = 0; s < kHeadStages - 1; ++s) stage(s);
   double run_lp[kHeadRows], run_pr[kHeadRows];
 #pragma unroll
   for (int r = 0; r < kHeadRows; ++r) {
@@ -358,53 +372,29 @@ __global__ void __launch_bounds__(kHeadThreads) mc_head_accumulate_kernel(const 
     run_lp[r] = ok ? a.sum_logp[(int64_t)(b0 + r) * C + cls] : 0.0;
     run_pr[r] = ok ? a.sum_prob[(int64_t)(b0 + r) * C + cls] : 0.0;
   }
-  // the warp's activation rows of the NEXT sample are fetched into registers (all loads in flight at once) while the
-  // current sample's dot products run
-  float4 hn[kHeadRows][kHeadQ];
-  auto fetch = [&](int s) {
-#pragma unroll
-    for (int r = 0; r < kHeadRows; ++r) {
-      const float4* hr = reinterpret_cast<const float4*>(a.h + (int64_t)s * a.hs + (int64_t)(b0 + r) * a.K);
-#pragma unroll
-      for (int q = 0; q < kHeadQ; ++q) {
-        const int k4 = lane + 32 * q;
-        hn[r][q] = (b0 + r < a.B && k4 < K4) ? __ldg(hr + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  };
-  fetch(0);
   for (int s = 0; s < a.n_samples; ++s) {
-    float4 hv[kHeadRows][kHeadQ];
-#pragma unroll
-    for (int r = 0; r < kHeadRows; ++r)
-#pragma unroll
-      for (int q = 0; q < kHeadQ; ++q) hv[r][q] = hn[r][q];
-    if (s + 1 < a.n_samples) {
-      stage(s + 1, (s + 1) & 1);
-      fetch(s + 1);
-      cp_async_wait<1>();
-    } else {
-      cp_async_wait<0>();
-    }
-    __syncthreads();                               // sample s's weights are in wbuf[s & 1]
+    stage(s + kHeadStages - 1);                    // into the buffer sample s - 1 used (released by the barrier below)
+    cp_async_wait<kHeadStages - 1>();
+    __syncthreads();                               // sample s's weights and activations have landed
     if (b0 < a.B) {
-      const float4* w = wbuf + (s & 1) * CK4;
+      const float4* w = sbuf + (s % kHeadStages) * stage4;
+      const float4* hs = w + CK4 + warp * kHeadRows * K4;
       float acc[kHeadRows][16];
 #pragma unroll
       for (int r = 0; r < kHeadRows; ++r)
 #pragma unroll
         for (int c = 0; c < 16; ++c) acc[r][c] = 0.f;
+      for (int k4 = lane; k4 < K4; k4 += 32) {
+        float4 hv[kHeadRows];
 #pragma unroll
-      for (int q = 0; q < kHeadQ; ++q) {
-        if (q * 32 < K4) {                         // warp-uniform
-          const int k4 = min(lane + 32 * q, K4 - 1);   // lanes past the row end carry zeros in hv
+        for (int r = 0; r < kHeadRows; ++r)
+          hv[r] = (b0 + r < a.B) ? hs[r * K4 + k4] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            const float4 wv = w[c * K4 + k4];
+        for (int c = 0; c < C; ++c) {
+          const float4 wv = w[c * K4 + k4];
 #pragma unroll
-            for (int r = 0; r < kHeadRows; ++r)
-              acc[r][c] = fmaf(hv[r][q].x, wv.x, fmaf(hv[r][q].y, wv.y, fmaf(hv[r][q].z, wv.z, fmaf(hv[r][q].w, wv.w, acc[r][c]))));
-          }
+          for (int r = 0; r < kHeadRows; ++r)
+            acc[r][c] = fmaf(hv[r].x, wv.x, fmaf(hv[r].y, wv.y, fmaf(hv[r].z, wv.z, fmaf(hv[r].w, wv.w, acc[r][c]))));
         }
       }
       const float bias = cls < C ? __ldg(a.bias + (int64_t)s * C + cls) : 0.f;
@@ -422,7 +412,7 @@ __global__ void __launch_bounds__(kHeadThreads) mc_head_accumulate_kernel(const 
         }
       }
     }
-    __syncthreads();                               // everyone is done with wbuf[s & 1] before sample s + 2 lands in it
+    __syncthreads();                               // everyone is done with this buffer before it is refilled
   }
 #pragma unroll
   for (int r = 0; r < kHeadRows; ++r)
@@ -435,14 +425,15 @@ __global__ void __launch_bounds__(kHeadThreads) mc_head_accumulate_kernel(const 
 
 template <int C>
 int launch_head(const HeadArgs& a, cudaStream_t s) {
-  const size_t smem = 2 * (size_t)C * a.K * sizeof(float);
-  LBBNN_REQUIRE(smem <= 200 * 1024, "head weights of one sample do not fit in shared memory twice (%zu bytes)", smem);
+  const size_t smem = head_smem_bytes(C, a.K);
+  LBBNN_REQUIRE(smem <= kHeadSmemMax, "fused head: %d stages of weights + activations need %zu bytes of shared memory",
+                kHeadStages, smem);
   static bool attr_set = false;
   if (!attr_set) {
-    LBBNN_CUDA(cudaFuncSetAttribute(mc_head_accumulate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    LBBNN_CUDA(cudaFuncSetAttribute(mc_head_accumulate_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHeadSmemMax));
     attr_set = true;
   }
-  mc_head_accumulate_kernel<C><<<(unsigned)ceil_div(a.B, kHeadRows * kHeadThreads / 32), kHeadThreads, smem, s>>>(a);
+  mc_head_accumulate_kernel<C><<<(unsigned)ceil_div(a.B, kHeadBlockRows), kHeadThreads, smem, s>>>(a);
   return check_launch("mc_head_accumulate");
 }
 
@@ -525,8 +516,9 @@ extern "C" int lbbnn_mc_head_accumulate(const float* h, int64_t h_stride, const 
                                         double* sum_prob, int64_t* counter, lbbnn_stream s) {
   LBBNN_REQUIRE(h && W && bias && sum_logp && sum_prob && n_samples > 0 && batch > 0 && batch < (1LL << 31), "bad argument");
   LBBNN_REQUIRE(classes >= 1 && classes <= 16, "fused head handles 1..16 classes, got %lld", (long long)classes);
-  LBBNN_REQUIRE(in_features <= 128 * kHeadQ, "fused head handles in_features <= %d, got %lld", 128 * kHeadQ,
-                (long long)in_features);
+  LBBNN_REQUIRE(head_smem_bytes(classes, in_features) <= kHeadSmemMax,
+                "fused head: (classes + %d) * in_features = %lld floats per stage do not fit in shared memory %d times",
+                kHeadBlockRows, (long long)((classes + kHeadBlockRows) * in_features), kHeadStages);
   LBBNN_REQUIRE(in_features > 0 && in_features % 4 == 0 && h_stride % 4 == 0 &&
                     ((reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(W)) & 15) == 0,
                 "in_features and the sample stride must be multiples of 4 floats, operands 16-byte aligned");

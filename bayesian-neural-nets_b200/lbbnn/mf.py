@@ -419,8 +419,8 @@ class MCPredictor:
                 self.n_tc = i + 1
         self.prepared = SB > 1          # batched sampler reads sigma / alpha computed once per run()
         kl, cl = sizes[-1]
-        self.fused_head = (SB > 1 and fused_head and self.n_tc < len(sizes) and len(sizes) > 1 and cl <= 16 and kl % 4 == 0 and kl <= 640
-                           and 2 * cl * kl * 4 <= 200 * 1024)
+        self.fused_head = (SB > 1 and fused_head and self.n_tc < len(sizes) and len(sizes) > 1 and cl <= 16 and kl % 4 == 0
+                           and 16 * (cl + 8) * kl <= 220 * 1024)
         if self.n_tc:
             self.x_hi, self.x_lo = torch.zeros_like(self.x), torch.zeros_like(self.x)
         if self.prepared:

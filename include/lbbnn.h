@@ -258,7 +258,7 @@ LBBNN_API int lbbnn_mc_accumulate_batched(const float* logits, int n_samples, in
 LBBNN_API int lbbnn_tf32_split(const float* x, int64_t n, float* hi, float* lo, lbbnn_stream s);
 /* Classifier head + accumulation in one launch: logits[s] = h[s] W[s]^T + bias[s] for the n_samples samples of a launch
  * (h: sample s at h + s * h_stride, (batch, in_features) row-major; W (n_samples, classes, in_features); classes <= 16,
- * in_features % 4 == 0 and <= 640), then exactly mc_accumulate_batched on them (same expressions, samples in order).  The logits
+ * in_features % 4 == 0, 16 (classes + 8) in_features <= 220 KB of shared memory), then exactly mc_accumulate_batched on them (same expressions, samples in order).  The logits
  * are never written. */
 LBBNN_API int lbbnn_mc_head_accumulate(const float* h, int64_t h_stride, const float* W, const float* bias, int n_samples,
                                        int64_t batch, int64_t in_features, int64_t classes, double* sum_logp,
