@@ -292,8 +292,7 @@ class LRTTrainer:
             self._pipe = dict(
                 copy_stream=torch.cuda.Stream(device=dev), n=0,
                 xs=[torch.empty_like(self.x) for _ in range(2)], ys=[torch.empty_like(self.y) for _ in range(2)],
-                xh=[torch.empty_like(self.x_host).pin_memory() for _ in range(2)],
-                yh=[torch.empty_like(self.y_host).pin_memory() for _ in range(2)],
+                xh=[None, None], yh=[None, None],        # pinned staging, only allocated for pageable inputs
                 sh=[torch.empty_like(self.stats_host).pin_memory() for _ in range(2)],
                 up=[torch.cuda.Event() for _ in range(2)], used=[torch.cuda.Event() for _ in range(2)],
                 done=[None, None])
@@ -302,6 +301,9 @@ class LRTTrainer:
         cur = torch.cuda.current_stream()
         pinned = x_host.is_pinned() and y_host.is_pinned() and x_host.is_contiguous()
         if not pinned:                                   # stage through this slot's pinned buffers
+            if P["xh"][i] is None:
+                P["xh"][i] = torch.empty_like(self.x_host).pin_memory()
+                P["yh"][i] = torch.empty_like(self.y_host).pin_memory()
             if P["n"] >= 2:
                 P["up"][i].synchronize()                 # the upload that last read them has finished
             P["xh"][i].copy_(x_host.reshape(P["xh"][i].shape))
