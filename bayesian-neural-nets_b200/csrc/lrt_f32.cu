@@ -425,8 +425,28 @@ struct FinalizeArgs {
   float klg_host;
   lbbnn_priors pri;
   float *dmu, *drho, *dlam, *dbmu, *dbrho, *dz, *dz_kl;
+  lbbnn_adam_layer_state adam;     // ADAM variant: the gradients go straight into torch.optim.Adam's update
 };
 
+// torch.optim.Adam update of 4 consecutive elements (same expressions as adam_kernel in util.cu)
+__device__ __forceinline__ void adam_quad(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, int64_t e0,
+                                          int64_t n, bool vec, const float pv[4], const float g[4], float b1, float b2,
+                                          float eps, float step_size, float bc2_sqrt) {
+  float mv[4], vv[4], po[4];
+  loadq(m, e0, n, vec, mv);
+  loadq(v, e0, n, vec, vv);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mv[j] = mv[j] + (g[j] - mv[j]) * (1.0f - b1);
+    vv[j] = b2 * vv[j] + (1.0f - b2) * g[j] * g[j];
+    po[j] = pv[j] - step_size * (mv[j] / (sqrtf(vv[j]) / bc2_sqrt + eps));
+  }
+  storeq(p, e0, n, vec, po, false);
+  storeq(m, e0, n, vec, mv, false);
+  storeq(v, e0, n, vec, vv, false);
+}
+
+template <bool ADAM>
 __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs a) {
   const int64_t n = a.N * a.K;
   const bool vec = (n % 4 == 0) && (a.K % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
@@ -476,9 +496,21 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
       if (a.dz_kl) { atomicAdd(a.dz_kl + k, dzkl); if (a.dz) atomicAdd(a.dz + k, dzk); }
       else if (a.dz) atomicAdd(a.dz + k, dzk + dzkl);
     }
-    storeq(a.dmu, e0, n, vec, gm, a.accumulate);
-    storeq(a.drho, e0, n, vec, gr, a.accumulate);
-    storeq(a.dlam, e0, n, vec, gl, a.accumulate);
+    if (ADAM) {
+      const float ss = __ldg(a.adam.coef), bc = __ldg(a.adam.coef + 1);
+      const bool va = vec && aligned16(a.adam.exp_avg[0]) && aligned16(a.adam.exp_avg[1]) && aligned16(a.adam.exp_avg[2]) &&
+                      aligned16(a.adam.exp_avg_sq[0]) && aligned16(a.adam.exp_avg_sq[1]) && aligned16(a.adam.exp_avg_sq[2]);
+      adam_quad(const_cast<float*>(a.mu), a.adam.exp_avg[0], a.adam.exp_avg_sq[0], e0, n, va, mu, gm, a.adam.beta1, a.adam.beta2,
+                a.adam.eps, ss, bc);
+      adam_quad(const_cast<float*>(a.rho), a.adam.exp_avg[1], a.adam.exp_avg_sq[1], e0, n, va, rho, gr, a.adam.beta1, a.adam.beta2,
+                a.adam.eps, ss, bc);
+      adam_quad(const_cast<float*>(a.lam), a.adam.exp_avg[2], a.adam.exp_avg_sq[2], e0, n, va, lam, gl, a.adam.beta1, a.adam.beta2,
+                a.adam.eps, ss, bc);
+    } else {
+      storeq(a.dmu, e0, n, vec, gm, a.accumulate);
+      storeq(a.drho, e0, n, vec, gr, a.accumulate);
+      storeq(a.dlam, e0, n, vec, gl, a.accumulate);
+    }
   }
   // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186)
   if (blockIdx.x == 0) {
@@ -491,6 +523,20 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
         dsb += klg * (sb * inv - 1.0f / sb);
       }
       const float dbr = dsb * dsigma_drho(br);
+      if (ADAM) {
+        const float ss = __ldg(a.adam.coef), bc = __ldg(a.adam.coef + 1), b1 = a.adam.beta1, b2 = a.adam.beta2;
+        float m = a.adam.exp_avg[3][i], v = a.adam.exp_avg_sq[3][i];
+        m = m + (dbm - m) * (1.0f - b1);
+        v = b2 * v + (1.0f - b2) * dbm * dbm;
+        const_cast<float*>(a.bias_mu)[i] = bm - ss * (m / (sqrtf(v) / bc + a.adam.eps));
+        a.adam.exp_avg[3][i] = m; a.adam.exp_avg_sq[3][i] = v;
+        m = a.adam.exp_avg[4][i]; v = a.adam.exp_avg_sq[4][i];
+        m = m + (dbr - m) * (1.0f - b1);
+        v = b2 * v + (1.0f - b2) * dbr * dbr;
+        const_cast<float*>(a.bias_rho)[i] = br - ss * (m / (sqrtf(v) / bc + a.adam.eps));
+        a.adam.exp_avg[4][i] = m; a.adam.exp_avg_sq[4][i] = v;
+        continue;
+      }
       a.dbmu[i] = a.accumulate ? a.dbmu[i] + dbm : dbm;
       a.dbrho[i] = a.accumulate ? a.dbrho[i] + dbr : dbr;
     }
@@ -801,7 +847,7 @@ extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, in
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
-  lrt_f32_finalize<<<(unsigned)elementwise_blocks(N * K), kThreads, 0, st>>>(f);
+  lrt_f32_finalize<false><<<(unsigned)elementwise_blocks(N * K), kThreads, 0, st>>>(f);
   return check_launch("lrt_f32_finalize");
 }
 
@@ -878,8 +924,28 @@ extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, con
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
-  lrt_f32_finalize<<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
+  lrt_f32_finalize<false><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize");
+}
+
+extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM, const float* dV, const float* colsum,
+                                           const lbbnn_priors* pri, int var_mode, int flags, const float* kl_grad_dev,
+                                           float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(dM && colsum && pri && adam && adam->coef, "NULL argument");
+  LBBNN_REQUIRE(L->z == nullptr && L->z_kl == nullptr, "the fused update is for LRT layers (no multiplicative z)");
+  for (int i = 0; i < 5; ++i) LBBNN_REQUIRE(adam->exp_avg[i] && adam->exp_avg_sq[i], "NULL Adam state %d", i);
+  const bool sample = flags & LBBNN_FLAG_SAMPLE;
+  LBBNN_REQUIRE(!sample || dV, "sample branch needs dV");
+  FinalizeArgs f;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = nullptr; f.z_kl = nullptr; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.dM = dM; f.dV = dV ? dV : dM; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
+  f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = 0;
+  f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
+  f.dmu = f.drho = f.dlam = f.dbmu = f.dbrho = f.dz = f.dz_kl = nullptr;
+  f.adam = *adam;
+  lrt_f32_finalize<true><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
+  return check_launch("lrt_f32_finalize_adam");
 }
 
 // ---- plain linear layer on the same kernels (mean-branch GEMM: E only) ---------------------------------

@@ -293,6 +293,12 @@ extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, f
   return check_launch("adam");
 }
 
+extern "C" int lbbnn_adam_prepare(const int64_t* step_dev, float lr, float beta1, float beta2, float* coef, lbbnn_stream s) {
+  LBBNN_REQUIRE(step_dev && coef, "NULL argument");
+  adam_prepare<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef);
+  return check_launch("adam_prepare");
+}
+
 extern "C" int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
                                     float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
                                     lbbnn_stream s) {

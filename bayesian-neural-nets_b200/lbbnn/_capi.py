@@ -124,6 +124,9 @@ SIGNATURES = {
     "lbbnn_lrt_f32_prologue": (_INT, [C.POINTER(Layer), C.POINTER(Priors), _INT, _INT, _P, _P, _P, _P, _SZ, _P]),
     "lbbnn_lrt_f32_finalize": (_INT, [C.POINTER(Layer), _P, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _F,
                                       C.POINTER(LayerGrads), _P]),
+    "lbbnn_lrt_f32_finalize_adam": (_INT, [C.POINTER(Layer), _P, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _F,
+                                           C.POINTER(AdamLayerState), _P]),
+    "lbbnn_adam_prepare": (_INT, [_P, _F, _F, _F, _P, _P]),
     "lbbnn_tc_dual_gemm_raw": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
     "lbbnn_tc_lrt_fwd": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, C.POINTER(Noise), _INT,
                                 _P, _P, _P, _P, _P, _P, _P]),

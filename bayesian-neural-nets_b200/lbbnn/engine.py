@@ -358,10 +358,17 @@ class LRTTensorCoreTrainer:
     the 10-class output are zero-filled by TMA).  The input-gradient GEMM of a layer whose out_features
     is not a multiple of 8 (the classifier: its contraction dim would break the TMA pitch) runs on the
     fp32 SIMT kernel instead.  Same reference step as LRTTrainer (LBBNN-GP-MF-LRT.py:217-229).
+
+    fused_update (default): every layer owns a raw-gradient buffer [dM | dV | bias column sums]; as soon as its dW GEMM
+    is done, chain rule + KL gradient + Adam run as ONE pass over it (lbbnn_lrt_f32_finalize_adam: parameters and Adam
+    state updated in place, the three parameter gradients never stored).  Data parallel: that buffer -- 2/3 of the
+    bytes of the parameter gradients it determines -- is all-reduced on a communication stream, layer by layer, while
+    the main stream goes on with the input-gradient GEMM and the earlier layers' backward.  fused_update=False keeps the
+    separate finalize / all-reduce of .grad / Adam passes (and leaves gradients in `.grad`).
     """
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
-                 use_graph=True, inject_noise=False, process_group=None):
+                 use_graph=True, inject_noise=False, process_group=None, fused_update=True):
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
@@ -413,6 +420,9 @@ class LRTTensorCoreTrainer:
         maxnk = max(i * o for i, o in sizes)
         self.M32, self.V32 = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)     # prologue out, reused
         self.dM, self.dV = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)       # dW GEMM out, reused
+        self.fused_update = bool(fused_update)
+        self.param_off = {(id(l), name): off for l, name, off, n, shape in offs}
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.fused_update and self.world > 1) else None
         self.tc = []
         for li, (i, o) in enumerate(sizes):
             last = li == L - 1
@@ -431,6 +441,9 @@ class LRTTensorCoreTrainer:
                 dET=torch.zeros(o, B, **bf), dST=torch.zeros(o, B, **bf),
                 colsum=torch.zeros(2 * o, **f32),
                 eps=torch.zeros(B, o, **f32) if inject_noise else None)
+            if self.fused_update:      # [dM | dV | colsum]: what a data-parallel step all-reduces for this layer
+                d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
+                d["colsum"] = d["raw"][2 * o * i:]
             self.tc.append(d)
         self.inject = inject_noise
         self.stats = torch.zeros(1 + L, **f32)
@@ -492,6 +505,10 @@ class LRTTensorCoreTrainer:
             return K.LayerGrads(*[t.data_ptr() for t in (l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad,
                                                          l.bias_mu.grad, l.bias_rho.grad)], None)
 
+        if self.fused_update:
+            K.check(lib.lbbnn_adam_prepare(P(self.step_dev, torch.int64), self.lr, self.betas[0], self.betas[1],
+                                           P(self.adam_coef), st)); n += 1
+        main = torch.cuda.current_stream()
         for i in reversed(range(L)):
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
@@ -503,10 +520,17 @@ class LRTTensorCoreTrainer:
                 K.check(lib.lbbnn_colsum2(P(d["dE"], bf), P(d["dS"], bf), 1, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
             xT, x2T = (self.xT_bf, self.x2T_bf) if i == 0 else (self.tc[i - 1]["actT"], self.tc[i - 1]["act2T"])
             # dM = dE^T x, dV = dS^T x^2: (out, B) x (in, B)^T
+            if self.fused_update:
+                dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
+            else:
+                dM, dV = self.dM, self.dV
             K.check(lib.lbbnn_tc_dual_gemm_raw(P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B,
-                                               P(self.dM), P(self.dV), st)); n += 1
-            K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(self.dM), P(self.dV), P(d["colsum"]), l.cfg.priors,
-                                               l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, grads_of(l), st)); n += 1
+                                               P(dM), P(dV), st)); n += 1
+            if self.fused_update:
+                self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
+            else:
+                K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(dM), P(dV), P(d["colsum"]), l.cfg.priors,
+                                                   l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, grads_of(l), st)); n += 1
             if i == 0:
                 continue
             p = self.tc[i - 1]
@@ -519,12 +543,44 @@ class LRTTensorCoreTrainer:
                                                    fo, P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
                                                    P(p["dE"], bf), P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf),
                                                    st)); n += 1
-        if self.pg is not None:
-            torch.distributed.all_reduce(self.gflat, group=self.pg)
-        K.check(lib.lbbnn_adam_f32(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
-                                   self.lr, self.betas[0], self.betas[1], self.eps, P(self.step_dev, torch.int64),
-                                   P(self.adam_coef), st)); n += 2
+        if self.fused_update:
+            if self.comm_stream is not None:
+                main.wait_stream(self.comm_stream)
+        else:
+            if self.pg is not None:
+                torch.distributed.all_reduce(self.gflat, group=self.pg)
+            K.check(lib.lbbnn_adam_f32(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
+                                       self.lr, self.betas[0], self.betas[1], self.eps, P(self.step_dev, torch.int64),
+                                       P(self.adam_coef), st)); n += 2
         self.kernels_per_step = n
+
+    def _adam_state(self, l):
+        st = K.AdamLayerState()
+        for j, name in enumerate(_PARAM_NAMES):
+            off = self.param_off[(id(l), name)]
+            st.exp_avg[j] = self.exp_avg.data_ptr() + 4 * off
+            st.exp_avg_sq[j] = self.exp_avg_sq.data_ptr() + 4 * off
+        st.coef = self.adam_coef.data_ptr()
+        st.beta1, st.beta2, st.eps = self.betas[0], self.betas[1], self.eps
+        return st
+
+    def _fused_layer_update(self, i, desc, dM, dV, main):
+        """Layer i's raw gradients are complete on `main`: (all-reduce them and) run chain rule + KL + Adam over them.
+        Single GPU: on `main`.  Data parallel: on the communication stream, overlapping the rest of the backward; the KL
+        gradient is added once, after the reduction."""
+        l, d = self.layers[i], self.tc[i]
+        klg = 1.0 / self.num_batches
+        if self.comm_stream is None:
+            K.check(K.lib.lbbnn_lrt_f32_finalize_adam(desc, K.ptr(dM), K.ptr(dV), K.ptr(d["colsum"]), l.cfg.priors,
+                                                      l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, self._adam_state(l),
+                                                      K.current_stream()))
+            return
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            torch.distributed.all_reduce(d["raw"], group=self.pg)
+            K.check(K.lib.lbbnn_lrt_f32_finalize_adam(desc, K.ptr(dM), K.ptr(dV), K.ptr(d["colsum"]), l.cfg.priors,
+                                                      l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, self._adam_state(l),
+                                                      K.current_stream()))
 
     _capture = LRTTrainer._capture
     step_device = LRTTrainer.step_device

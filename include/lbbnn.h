@@ -399,6 +399,21 @@ LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* targe
 LBBNN_API int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                              float lr, float beta1, float beta2, float eps, const int64_t* step_dev,
                              float* coef_scratch, lbbnn_stream s);
+/* Chain rule + KL gradient + Adam in one pass (the wide trainer): lbbnn_lrt_f32_finalize with the three weight
+ * gradients and the two bias gradients consumed in registers by torch.optim.Adam's update -- the layer's parameters and
+ * their Adam state are updated IN PLACE (the layer struct's pointers are written through) and no gradient is stored.
+ * exp_avg / exp_avg_sq: [weight_mu, weight_rho, lambdal, bias_mu, bias_rho]; coef: the 2 floats lbbnn_adam_prepare
+ * wrote for this step (step size / bias-correction, computed on the device from *step_dev). */
+typedef struct lbbnn_adam_layer_state {
+  float* exp_avg[5];
+  float* exp_avg_sq[5];
+  const float* coef;
+  float beta1, beta2, eps;
+} lbbnn_adam_layer_state;
+LBBNN_API int lbbnn_adam_prepare(const int64_t* step_dev, float lr, float beta1, float beta2, float* coef, lbbnn_stream s);
+LBBNN_API int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* layer, const float* dM, const float* dV, const float* colsum,
+                                          const lbbnn_priors* priors, int var_mode, int flags, const float* kl_grad_dev,
+                                          float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s);
 /* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF / MF scripts,
  * MNF:352, MF:520-553 with one learning rate): table_dev = device array of n_entries records; block b of the launch
  * updates elements [(b - first_block) * 1024, +1024) of the tensor with the largest first_block <= b, so first_block

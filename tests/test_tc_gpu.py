@@ -178,7 +178,7 @@ def test_tensor_core_trainer_step(use_graph, dims, B):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
     tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph,
-                                    inject_noise=True)
+                                    inject_noise=True, fused_update=False)      # gradients wanted in .grad
     for d, e in zip(tr.tc, case["eps"]):
         d["eps"].copy_(e)
     out = tr.step(case["x"], case["y"])
@@ -201,6 +201,37 @@ def test_tensor_core_trainer_step(use_graph, dims, B):
         for k in p:
             r = p[k].grad.double()
             assert (g[k] - r).norm() / r.norm() < 6e-2, (li, k, "vs fp32 oracle", ((g[k] - r).norm() / r.norm()).item())
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_wide_trainer_fused_update_matches_separate_passes(use_graph):
+    """fused_update=True (chain rule + KL gradient + Adam in one pass per layer, lbbnn_lrt_f32_finalize_adam) follows the
+    same parameter trajectory as finalize -> .grad -> lbbnn_adam_f32 over three steps with injected noise."""
+    import lbbnn
+    sizes = [(136, 264), (264, 72), (72, 10)]
+    B = 64
+    case = C.lrt_net_case(seed=91, batch=B, sizes=sizes)
+    nets, trs = [], []
+    for fused in (False, True):
+        net = lbbnn.BayesianNetwork((136, 264, 72, 10)).cuda()
+        with torch.no_grad():
+            for l, p in zip(net.layers, case["layers"]):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-2, use_graph=use_graph,
+                                        inject_noise=True, fused_update=fused)
+        for d, e in zip(tr.tc, case["eps"]):
+            d["eps"].copy_(e)
+        nets.append(net)
+        trs.append(tr)
+    for step in range(3):
+        outs = [tr.step(case["x"], case["y"]) for tr in trs]
+        assert abs(outs[0]["nll"] - outs[1]["nll"]) <= 1e-5 * abs(outs[0]["nll"]), step
+        assert abs(outs[0]["kl"] - outs[1]["kl"]) <= 1e-6 * abs(outs[0]["kl"]), step
+    for la, lb_ in zip(nets[0].layers, nets[1].layers):
+        for k in case["layers"][0]:
+            assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 1e-6, k
+    assert C.rel_err(trs[1].exp_avg, trs[0].exp_avg) < 1e-6 and C.rel_err(trs[1].exp_avg_sq, trs[0].exp_avg_sq) < 1e-6
 
 
 # ---- 3xTF32 linear layer (csrc/tc_gemm_tf32.cu): fp32 accuracy on tcgen05 --------------------------------------------
