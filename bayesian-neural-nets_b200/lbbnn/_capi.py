@@ -77,6 +77,11 @@ class FlowGrads(C.Structure):
     _fields_ = [("row_stride", C.c_int64), ("t", FlowTransformGrads * FLOW_MAX_T)]
 
 
+class AdamLayerState(C.Structure):
+    _fields_ = [("exp_avg", C.c_void_p * 5), ("exp_avg_sq", C.c_void_p * 5), ("coef", C.c_void_p),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
+
+
 class MnfAux(C.Structure):
     _fields_ = [("in_features", C.c_int64), ("out_features", C.c_int64)] + [
         (n, C.c_void_p) for n in ("q0_mean", "q0_log_var", "z0", "r0_c", "r0_b1", "r0_b2", "z2", "M0", "V", "eps_r", "z_b")]
