@@ -360,7 +360,8 @@ def run_ours(args):
     net = lbbnn.BayesianNetwork(sizes).to(dev)
     _mark("process group up, building trainer")
     if wide:
-        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg)
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
+                                        fused_update=not args.unfused)
     else:   # the fused persistent step kernel unless --unfused; gradients stay in registers (no .grad written)
         tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
                               fused=not args.unfused, materialize_grads=args.unfused)
