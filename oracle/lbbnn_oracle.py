@@ -420,3 +420,42 @@ def init_mnf_params(rng, in_features, out_features, num_transforms=2, h_sizes=(7
               "z_flow": init_flow_params(rng, in_features, num_transforms, h_sizes, kind, dtype=dtype),
               "r_flow": init_flow_params(rng, in_features, num_transforms, h_sizes, kind, dtype=dtype)})
     return p
+
+
+# --------------------------------------------------------------------------------------
+# variational dropout (VD = variational_dropout.py), SURVEY.md §8(f) rank 4
+# --------------------------------------------------------------------------------------
+VD_KL_C = (1.16145124, -1.50204118, 0.58629921)       # VD:98
+
+
+def vd_forward(x, theta, alpha, zeta):
+    """BayesianLayer.forward (VD:63-68): theta is (n, m) = (in, out) -- the "NN" operand layout -- and alpha (m,) one
+    dropout rate per output neuron: phi = x theta, delta = (x^2 theta^2) alpha, act = phi + sqrt(delta) zeta."""
+    phi = torch.matmul(x, theta)
+    delta = torch.matmul(x ** 2, theta ** 2) * alpha
+    return phi + torch.sqrt(delta) * zeta
+
+
+def vd_kl(alpha):
+    """Per-layer term of loss_fn (VD:98-102): sum 0.5 log a + c1 a + c2 a^2 + c3 a^3 (added to the loss as written)."""
+    c1, c2, c3 = VD_KL_C
+    return (0.5 * torch.log(alpha) + c1 * alpha + c2 * alpha ** 2 + c3 * alpha ** 3).sum()
+
+
+def vd_net_loss(x, y, layers, zetas, num_batches):
+    """BNN.forward (VD:79-85) + loss_fn (VD:88-106): relu between layers, log_softmax at the end,
+    loss = KL / num_batches + nll_loss(sum).  layers: [{"theta", "alpha"}]."""
+    h = x.reshape(-1, layers[0]["theta"].shape[0])
+    kl = 0
+    for i, (p, z) in enumerate(zip(layers, zetas)):
+        h = vd_forward(h, p["theta"], p["alpha"], z)
+        h = F.relu(h) if i < len(layers) - 1 else F.log_softmax(h, dim=1)
+        kl = kl + vd_kl(p["alpha"])
+    nll = F.nll_loss(h, y, reduction="sum")
+    return kl / num_batches + nll, nll, kl, h
+
+
+def init_vd_params(rng, n, m, alpha=0.2, dtype=torch.float32):
+    """VD:58-61: theta ~ U(-0.1, 0.1) (n, m); alpha = 0.2 for every output neuron."""
+    return {"theta": torch.from_numpy(rng.uniform(-0.1, 0.1, size=(n, m))).to(dtype),
+            "alpha": torch.full((m,), alpha, dtype=dtype)}

@@ -179,3 +179,28 @@ def sim_study_case(seed, n=2000, batch=400, steps=5):
                "g0_w": t(rng.gamma(1.05, size=(1,))), "g0_b": t(rng.gamma(1.05, size=(1,)))} for _ in range(steps)]
     us = [t(rng.uniform(0.0, 1.0, size=(1, 20))) for _ in range(steps)]
     return {"X": t(X), "y": torch.from_numpy(y), "p": p, "noises": noises, "us": us, "batch": batch, "num_batches": n / batch}
+
+
+VD_SIZES = [(784, 1200), (1200, 1200), (1200, 1200), (1200, 10)]      # BNN of variational_dropout.py:74-77
+
+
+def vd_layer_case(seed, batch, n, m, spread_alpha=False):
+    """One variational-dropout layer (VD:55-68): theta~U(-.1,.1) (n,m), alpha = 0.2 (or spread over (0.05, 1)),
+    x ~ N(0,1) like the normalised MNIST input (VD:38-40), zeta ~ N(0,1), random upstream gradient."""
+    rng = np.random.default_rng(seed)
+    p = O.init_vd_params(rng, n, m)
+    if spread_alpha:
+        p["alpha"] = t(rng.uniform(0.05, 1.0, size=(m,)))
+    x = t(rng.standard_normal(size=(batch, n)))
+    zeta = t(rng.standard_normal(size=(batch, m)))
+    gout = t(rng.standard_normal(size=(batch, m)))
+    return {"p": p, "x": x, "zeta": zeta, "gout": gout}
+
+
+def vd_net_case(seed, batch, sizes=VD_SIZES, classes=10):
+    rng = np.random.default_rng(seed)
+    layers = [O.init_vd_params(rng, n, m) for n, m in sizes]
+    x = t(rng.standard_normal(size=(batch, sizes[0][0])))
+    y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
+    zetas = [t(rng.standard_normal(size=(batch, m))) for _, m in sizes]
+    return {"layers": layers, "x": x, "y": y, "zetas": zetas}

@@ -299,8 +299,56 @@ def golden_mnf():
     print("mnf golden written; nll", nll.item(), "kl", kl.item())
 
 
+def golden_vd():
+    """variational_dropout.py: BayesianLayer (VD:55-68) on odd shapes and the 784-1200-1200-1200-10
+    BNN (VD:71-85) with loss_fn (VD:88-106), all under replayed zeta.  The reference's alpha is `nn.Parameter(zeros)+0.2`,
+    a non-leaf tensor: it is overwritten with the case's alpha (a leaf) so that its gradient can be stored too."""
+    class _DS:
+        def __init__(self, n):
+            self.dataset = range(n)
+    ns = H.load_reference_classes("variational_dropout.py", functions=("loss_fn",), device="cpu",
+                                  config={"batch_size": 100}, train_loader=_DS(60000), val_loader=_DS(10000))
+    Layer, BNN, loss_fn = ns["BayesianLayer"], ns["BNN"], ns["loss_fn"]
+    out = {}
+    for tag, (seed, b, n, m, spread) in {"a": (81, 9, 37, 23, False), "b": (82, 33, 130, 10, True), "c": (83, 5, 64, 1, True)}.items():
+        case = C.vd_layer_case(seed, b, n, m, spread_alpha=spread)
+        layer = Layer(n, m)
+        with torch.no_grad():
+            layer.theta.copy_(case["p"]["theta"])
+        layer.alpha = case["p"]["alpha"].clone().requires_grad_(True)
+        x = case["x"].clone().requires_grad_(True)
+        with H.replay(H.NoiseQueue([("normal", case["zeta"])])):
+            act = layer(x)
+        (act * case["gout"]).sum().backward()
+        out[f"{tag}_meta"] = np.array([seed, b, n, m, int(spread)])
+        out[f"{tag}_act"] = act.detach().numpy()
+        out[f"{tag}_dx"] = x.grad.numpy()
+        out[f"{tag}_d_theta"] = layer.theta.grad.numpy()
+        out[f"{tag}_d_alpha"] = layer.alpha.grad.numpy()
+    case = C.vd_net_case(seed=80, batch=100)
+    net = BNN()
+    for lay, p in zip((net.l1, net.l2, net.l3, net.l4), case["layers"]):
+        with torch.no_grad():
+            lay.theta.copy_(p["theta"])
+        lay.alpha = p["alpha"].clone().requires_grad_(True)
+    net.train()
+    with H.replay(H.NoiseQueue([("normal", z) for z in case["zetas"]])):
+        pred = net(case["x"])
+    loss = loss_fn(pred, case["y"], net)
+    loss.backward()
+    out["net_logp"] = pred.detach().numpy()
+    out["net_loss"] = np.float64(loss.item())
+    for li, lay in enumerate((net.l1, net.l2, net.l3, net.l4)):
+        for k, v in C.grad_digest(lay.theta.grad).items():
+            out[f"net_l{li}_theta_{k}"] = v
+        out[f"net_l{li}_d_alpha"] = lay.alpha.grad.numpy()
+    np.savez_compressed(os.path.join(HERE, "vd.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("vd", "all"):
+        golden_vd()
     if what in ("lrt", "all"):
         golden_lrt()
     if what in ("mnf", "all") and "golden_mnf" in globals():

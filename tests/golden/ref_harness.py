@@ -29,15 +29,16 @@ import torch.nn.functional as F
 
 REF_ROOT = os.environ.get("LBBNN_REFERENCE", "/root/reference")
 
-_CLASSES = {"Gaussian", "Bernoulli", "GaussGamma", "BetaBinomial", "BayesianLinear", "BayesianNetwork"}
+_CLASSES = {"Gaussian", "Bernoulli", "GaussGamma", "BetaBinomial", "BayesianLinear", "BayesianNetwork", "BayesianLayer", "BNN"}
 
 
-def load_reference_classes(script, flows_module=None, **globals_override):
-    """exec the ClassDefs of `script` (e.g. 'LBBNN-GP-MF-LRT.py') and return the namespace."""
+def load_reference_classes(script, flows_module=None, functions=(), **globals_override):
+    """exec the ClassDefs (and the named FunctionDefs) of `script` (e.g. 'LBBNN-GP-MF-LRT.py') and return the namespace."""
     path = os.path.join(REF_ROOT, script)
     with open(path) as fh:
         tree = ast.parse(fh.read(), filename=path)
-    body = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in _CLASSES]
+    body = [n for n in tree.body if (isinstance(n, ast.ClassDef) and n.name in _CLASSES) or
+            (isinstance(n, ast.FunctionDef) and n.name in functions)]
     module = ast.Module(body=body, type_ignores=[])
     ns = {
         "torch": torch, "nn": nn, "F": F, "math": math, "np": np,

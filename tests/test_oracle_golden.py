@@ -197,3 +197,35 @@ def test_sim_study_network_matches_reference():
         assert abs(val.item() - float(g[name])) <= 5e-6 * abs(float(g[name])), name
     for k, v in p.items():
         assert C.rel_err(v.grad, g["d_" + k]) < 5e-5, k
+
+
+# ---- variational dropout (variational_dropout.py) -----------------------------------------------
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_vd_layer_matches_reference(tag):
+    g = _npz("vd.npz")
+    seed, b, n, m, spread = (int(v) for v in g[f"{tag}_meta"])
+    case = C.vd_layer_case(seed, b, n, m, spread_alpha=bool(spread))
+    theta = case["p"]["theta"].clone().requires_grad_(True)
+    alpha = case["p"]["alpha"].clone().requires_grad_(True)
+    x = case["x"].clone().requires_grad_(True)
+    act = O.vd_forward(x, theta, alpha, case["zeta"])
+    (act * case["gout"]).sum().backward()
+    assert C.rel_err(act, g[f"{tag}_act"]) < TOL
+    assert C.rel_err(x.grad, g[f"{tag}_dx"]) < TOL
+    assert C.rel_err(theta.grad, g[f"{tag}_d_theta"]) < TOL
+    assert C.rel_err(alpha.grad, g[f"{tag}_d_alpha"]) < TOL
+
+
+def test_vd_net_matches_reference():
+    g = _npz("vd.npz")
+    case = C.vd_net_case(seed=80, batch=100)
+    layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+    loss, nll, kl, logp = O.vd_net_loss(case["x"], case["y"], layers, case["zetas"], 600.0)
+    loss.backward()
+    assert C.rel_err(logp, g["net_logp"]) < TOL
+    assert abs(loss.item() - float(g["net_loss"])) / abs(float(g["net_loss"])) < TOL
+    for li, p in enumerate(layers):
+        d = C.grad_digest(p["theta"].grad)
+        assert C.rel_err(d["sample"], g[f"net_l{li}_theta_sample"]) < 5e-6, li
+        assert abs(d["l2"] - float(g[f"net_l{li}_theta_l2"])) / float(g[f"net_l{li}_theta_l2"]) < 5e-6, li
+        assert C.rel_err(p["alpha"].grad, g[f"net_l{li}_d_alpha"]) < 5e-6, li
