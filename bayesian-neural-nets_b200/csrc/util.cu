@@ -147,7 +147,8 @@ __global__ void adam_prepare(const int64_t* __restrict__ step_dev, float lr, flo
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, int64_t n,
-                                                   float b1, float b2, float eps, const float* __restrict__ coef) {
+                                                   float b1, float b2, float eps, const float* __restrict__ coef,
+                                                   float decay) {       // decay = lr * weight_decay (AdamW), 0 for Adam
   const float step_size = __ldg(coef), bc2_sqrt = __ldg(coef + 1);
   const bool vec = (n % 4 == 0) && aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
   const int64_t nq = ceil_div(n, 4);
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      if (decay != 0.f) pv[j] *= 1.0f - decay;         // torch.optim.AdamW: param.mul_(1 - lr * weight_decay) first
       mv[j] = mv[j] + (gv[j] - mv[j]) * (1.0f - b1);   // lerp form, as torch's _single_tensor_adam
       vv[j] = b2 * vv[j] + (1.0f - b2) * gv[j] * gv[j];
       const float denom = sqrtf(vv[j]) / bc2_sqrt + eps;
@@ -289,8 +291,21 @@ extern "C" int lbbnn_adam_f32(float* param, const float* grad, float* exp_avg, f
   const int64_t blocks = ceil_div(ceil_div(n, 4), 256);   // one quad per thread: no grid-stride loop
   LBBNN_REQUIRE(blocks < (1LL << 31), "flat buffer too large");
   adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
-                                                             coef_scratch);
+                                                             coef_scratch, 0.f);
   return check_launch("adam");
+}
+
+extern "C" int lbbnn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, const int64_t* step_dev,
+                               float* coef_scratch, lbbnn_stream s) {
+  LBBNN_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_dev && coef_scratch && n > 0, "NULL argument");
+  adam_prepare<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef_scratch);
+  if (int rc = check_launch("adam_prepare")) return rc;
+  const int64_t blocks = ceil_div(ceil_div(n, 4), 256);
+  LBBNN_REQUIRE(blocks < (1LL << 31), "flat buffer too large");
+  adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                             coef_scratch, lr * weight_decay);
+  return check_launch("adamw");
 }
 
 extern "C" int lbbnn_adam_prepare(const int64_t* step_dev, float lr, float beta1, float beta2, float* coef, lbbnn_stream s) {

@@ -6,6 +6,7 @@ from ._capi import LbbnnError, philox_normal, philox_uniform
 from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
 from . import flows, mf, mnf
 from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer, MultiTensorAdam
+from . import vd
 
 __all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "MultiTensorAdam", "lrt_linear",
-           "manual_seed", "mf", "mnf", "flows", "philox_normal", "philox_uniform"]
+           "manual_seed", "mf", "mnf", "flows", "vd", "philox_normal", "philox_uniform"]

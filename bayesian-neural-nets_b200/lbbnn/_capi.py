@@ -174,6 +174,12 @@ SIGNATURES = {
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_adam_multi_f32": (_INT, [_P, _INT, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
+    "lbbnn_adamw_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P, _P]),
+    "lbbnn_vd_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
+    "lbbnn_vd_gemm_launches": (_INT, [_I64, _I64, _I64]),
+    "lbbnn_vd_fwd": (_INT, [_P, _P, _P, _I64, _I64, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_vd_bwd": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_vd_kl": (_INT, [_P, _I64, _P, _INT, _P, _F, _P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

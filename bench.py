@@ -730,7 +730,18 @@ def _module_oracle_step(kind):
     B = 100
     x = torch.from_numpy(rng.random((B, 784), dtype=np.float32))
     y = torch.from_numpy(rng.integers(0, 10, size=(B,))).long()
-    if kind == "mnf_mnist":
+    if kind == "vd_mnist":
+        x = (x - 0.1307) / 0.3081                      # the script normalises MNIST (variational_dropout.py:38-40)
+        layers = [{k: v.clone().requires_grad_(k == "theta") for k, v in O.init_vd_params(rng, n, m).items()} for n, m in C.VD_SIZES]
+        opt = torch.optim.AdamW([p["theta"] for p in layers], lr=1e-4)
+
+        def one():
+            zetas = [torch.randn(B, m) for _, m in C.VD_SIZES]
+            opt.zero_grad(set_to_none=True)
+            loss = O.vd_net_loss(x, y, layers, zetas, NUM_BATCHES)[0]
+            loss.backward()
+            opt.step()
+    elif kind == "mnf_mnist":
         named = [{k: v.clone().requires_grad_(True) for k, v in C.flat_named(O.init_mnf_params(rng, i, o)).items()} for i, o in sizes]
         tmpl = [O.init_mnf_params(np.random.default_rng(1), i, o) for i, o in sizes]
         layers = [C.unflatten_like(t_, n) for t_, n in zip(tmpl, named)]
@@ -773,6 +784,11 @@ def cpu_reference_module(kind, budget_s=15.0, max_steps=60):
 
 
 def module_config(kind):
+    if kind == "vd_mnist":
+        return {"workload": "vd_mnist: variational-dropout MLP 784-1200-1200-1200-10 (variational_dropout.py), batch 100, "
+                            "fwd+loss_fn+bwd+AdamW(lr 1e-4), theta trained / alpha fixed at 0.2 as in the reference",
+                "batch_per_gpu": 100, "parallelism": "single GPU",
+                "l2": "inputs rotate through a pool of 512 distinct batches (161 MB > 126 MB L2)"}
     what = ("MNF MLP 784-400-600-10 (2 RNVP transforms, h=75x4, z flow + auxiliary r flow KL)" if kind == "mnf_mnist"
             else "MF MLP 784-400-600-10 (relaxed-Bernoulli gamma, full weight sampling, GaussGamma/BetaBinomial log-probs)")
     return {"workload": f"{kind}: {what}, batch 100, fwd+objective+bwd+Adam through the drop-in modules (eager autograd)",
@@ -802,17 +818,23 @@ def run_module(args):
     torch.manual_seed(0)
     lbbnn.manual_seed(99)
     B, POOL = 100, 512
-    net = (lbbnn.mnf.BayesianNetwork() if kind == "mnf_mnist" else lbbnn.mf.BayesianNetwork()).to(dev)
+    net = (lbbnn.vd.BNN() if kind == "vd_mnist" else
+           lbbnn.mnf.BayesianNetwork() if kind == "mnf_mnist" else lbbnn.mf.BayesianNetwork()).to(dev)
     net.train()
     px_h, py_h = make_pool(POOL, B, 784, 10, seed=1000)
+    if kind == "vd_mnist":
+        px_h = (px_h - 0.1307) / 0.3081
     px_h, py_h = px_h.pin_memory(), py_h.pin_memory()
     px, py = px_h.to(dev), py_h.to(dev)
+    tr = None
     if args.eager:
-        opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+        opt = (torch.optim.AdamW(net.parameters(), lr=1e-4) if kind == "vd_mnist" else torch.optim.Adam(net.parameters(), lr=1e-3))
 
         def dev_step(x, y):
             opt.zero_grad(set_to_none=True)
-            if kind == "mnf_mnist":
+            if kind == "vd_mnist":
+                loss = lbbnn.vd.loss_fn(net(x), y, net, NUM_BATCHES)
+            elif kind == "mnf_mnist":
                 logp = net(x, sample=True)
                 loss = torch.nn.functional.nll_loss(logp, y, reduction="sum") + net.kl() / NUM_BATCHES
             else:
@@ -824,8 +846,11 @@ def run_module(args):
         def host_step(xh, yh):
             return dev_step(xh.to(dev, non_blocking=True), yh.to(dev, non_blocking=True)).item()
     else:   # the whole step (modules' autograd Functions + objective + backward + Adam) as one CUDA-graph replay
-        tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3,
-                                  objective="kl" if kind == "mnf_mnist" else "elbo")
+        if kind == "vd_mnist":      # C-ABI calls on preallocated buffers (no autograd), captured once
+            tr = lbbnn.vd.VDTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-4)
+        else:
+            tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3,
+                                      objective="kl" if kind == "mnf_mnist" else "elbo")
 
         def dev_step(x, y):
             tr.x.copy_(x, non_blocking=True)
@@ -866,7 +891,8 @@ def run_module(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": module_config(kind),
             "e2e": {"value": B * args.steps / (te1 - te0), "unit": "samples/s", "h2d_bytes_per_step": B * 784 * 4 + B * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": (te1 - te0) / args.steps * 1e3},
-            "gpu_launches": None, "mode": "eager" if args.eager else "cuda-graph replay of the whole step",
+            "gpu_launches": (tr.kernels_per_step * args.steps if kind == "vd_mnist" and tr is not None else None),
+            "mode": "eager" if args.eager else "cuda-graph replay of the whole step",
             "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of one replay)", "achieved": nbytes / (us * 1e-6) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": nbytes / (us * 1e-6) / 1e9 / peaks["hbm_gbs"],
                          "traffic": None, "peak_source": peaks["source"], "bytes_per_launch": nbytes, "us_per_launch": us,
@@ -889,11 +915,11 @@ def main():
     ap.add_argument("--mc-lanes", type=int, default=None, help="mf_mc_predict: concurrent launch sequences per GPU")
     ap.add_argument("--eager", action="store_true", help="mnf_mnist / mf_mnist: eager modules instead of the graphed step")
     ap.add_argument("--unfused", action="store_true", help="lrt_mnist: per-layer launch sequence instead of the step kernel")
-    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist"])
+    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist", "vd_mnist"])
     args = ap.parse_args()
     if args.workload == "mf_mc_predict":
         run_mc(args)
-    elif args.workload in ("mnf_mnist", "mf_mnist"):
+    elif args.workload in ("mnf_mnist", "mf_mnist", "vd_mnist"):
         run_module(args)
     elif args.impl == "reference":
         run_reference(args)

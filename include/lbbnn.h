@@ -430,6 +430,35 @@ LBBNN_API int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entr
                                    float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
                                    lbbnn_stream s);
 LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
+/* torch.optim.AdamW (variational_dropout.py:110): the update above preceded by param *= 1 - lr * weight_decay */
+LBBNN_API int lbbnn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                              float lr, float beta1, float beta2, float eps, float weight_decay,
+                              const int64_t* step_dev, float* coef_scratch, lbbnn_stream s);
+
+/* ---- variational-dropout layer (VD = variational_dropout.py) -----------------------------
+ * BayesianLayer.forward VD:63-68 and autograd through it.  theta is (n, m) = (in, out) row-major -- the "NN" operand
+ * layout, unlike the (out, in) weights above -- alpha is (m,), x is (batch, n).
+ *   fwd: act = x theta + sqrt((x^2 theta^2) alpha) zeta (FLAG_RELU: relu of it, the F.relu of VD:81-83 fused in);
+ *        saved for the backward: ds_factor = zeta / (2 sqrt(delta)) and q = x^2 theta^2, both (batch, m); either may be
+ *        NULL when no backward follows.  noise: zeta, shape (batch, m) (see lbbnn_noise).
+ *   bwd: gact = dL/d(act) (with FLAG_RELU: dL/d(relu output), masked here by act > 0).  Writes d_theta (n, m)
+ *        (FLAG_ACCUMULATE: +=), d_alpha (m,) and dx (batch, n); each may be NULL.
+ *   kl:  the layer's term of loss_fn VD:98-102, sum_j 0.5 log a_j + c1 a_j + c2 a_j^2 + c3 a_j^3, written (or added)
+ *        to *kl_out; d_alpha (may be NULL) += grad_scale * d kl / d alpha.
+ * One workspace of lbbnn_vd_workspace_bytes serves fwd and bwd (stream-ordered reuse). */
+LBBNN_API size_t lbbnn_vd_workspace_bytes(int64_t batch, int64_t n, int64_t m);
+/* kernel launches of one of the path's dual GEMMs (M x K)(K x N): 2 when its contraction is split, else 1
+ * (fwd: (batch, m, n); d_theta: (n, m, batch); dx: (batch, n, m)) -- for launch accounting only */
+LBBNN_API int lbbnn_vd_gemm_launches(int64_t M, int64_t N, int64_t K);
+LBBNN_API int lbbnn_vd_fwd(const float* theta, const float* alpha, const float* x, int64_t batch, int64_t n, int64_t m,
+                           const lbbnn_noise* noise, int flags, float* act, float* ds_factor, float* q, void* workspace,
+                           size_t workspace_bytes, lbbnn_stream s);
+LBBNN_API int lbbnn_vd_bwd(const float* theta, const float* alpha, const float* x, const float* act, const float* ds_factor,
+                           const float* q, const float* gact, int64_t batch, int64_t n, int64_t m, int flags,
+                           float* d_theta, float* d_alpha, float* dx, void* workspace, size_t workspace_bytes,
+                           lbbnn_stream s);
+LBBNN_API int lbbnn_vd_kl(const float* alpha, int64_t m, float* kl_out, int kl_accumulate, float* d_alpha, float grad_scale,
+                          lbbnn_stream s);
 
 #ifdef __cplusplus
 }

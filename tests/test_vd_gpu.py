@@ -1,0 +1,176 @@
+"""GPU parity tests of the variational-dropout path (variational_dropout.py): lbbnn_vd_{fwd,bwd,kl}
+through the C-ABI vs the CPU oracle on the same seeded inputs and injected zeta, and vs the reference's own outputs
+(tests/golden/vd.npz).  Tolerance: max|a-b|/max|b| <= 1e-5 per tensor in fp32; argmax predictions bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+import lbbnn_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def vd():
+    import lbbnn.vd
+    return lbbnn.vd
+
+
+def _oracle_layer(case, dtype=torch.float64):
+    theta = case["p"]["theta"].to(dtype).clone().requires_grad_(True)
+    alpha = case["p"]["alpha"].to(dtype).clone().requires_grad_(True)
+    x = case["x"].to(dtype).clone().requires_grad_(True)
+    act = O.vd_forward(x, theta, alpha, case["zeta"].to(dtype))
+    kl = O.vd_kl(alpha)
+    ((act * case["gout"].to(dtype)).sum() + kl / 600.0).backward()
+    return act.detach(), kl.detach(), x.grad, theta.grad, alpha.grad
+
+
+def _cuda_layer(vd, case, with_kl=True):
+    theta = case["p"]["theta"].cuda().requires_grad_(True)
+    alpha = case["p"]["alpha"].cuda().requires_grad_(True)
+    x = case["x"].cuda().requires_grad_(True)
+    act = vd.vd_linear(x, theta, alpha, zeta=case["zeta"].cuda())
+    kl = vd.vd_kl(alpha)
+    ((act * case["gout"].cuda()).sum() + (kl / 600.0 if with_kl else 0.0)).backward()
+    return act.detach(), kl.detach(), x.grad, theta.grad, alpha.grad
+
+
+# odd shapes (scalar loader paths, ragged tiles), the MNIST layers (vector paths, split contraction), batch 1 and 1000
+SHAPES = [(31, 9, 37, 23, False), (32, 5, 64, 1, True), (33, 33, 130, 10, True), (34, 100, 784, 1200, False),
+          (35, 100, 1200, 1200, True), (36, 100, 1200, 10, True), (37, 1, 64, 64, False), (38, 1000, 400, 72, True),
+          (39, 64, 16, 4096, False)]
+
+
+@pytest.mark.parametrize("seed,b,n,m,spread", SHAPES)
+def test_layer_fwd_bwd_matches_oracle(vd, seed, b, n, m, spread):
+    case = C.vd_layer_case(seed, b, n, m, spread_alpha=spread)
+    ref = _oracle_layer(case)
+    got = _cuda_layer(vd, case)
+    assert C.rel_err(got[0], ref[0]) < TOL, "activations"
+    assert abs(got[1].item() - ref[1].item()) / abs(ref[1].item()) < TOL, "kl"
+    assert C.rel_err(got[2], ref[2]) < TOL, "dx"
+    assert C.rel_err(got[3], ref[3]) < TOL, "d_theta"
+    assert C.rel_err(got[4], ref[4]) < TOL, "d_alpha"
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_layer_matches_reference_golden(vd, tag):
+    g = np.load(os.path.join(C.GOLDEN, "vd.npz"))
+    seed, b, n, m, spread = (int(v) for v in g[f"{tag}_meta"])
+    case = C.vd_layer_case(seed, b, n, m, spread_alpha=bool(spread))
+    act, _, dx, d_theta, d_alpha = _cuda_layer(vd, case, with_kl=False)
+    assert C.rel_err(act, g[f"{tag}_act"]) < TOL
+    assert C.rel_err(dx, g[f"{tag}_dx"]) < TOL
+    assert C.rel_err(d_theta, g[f"{tag}_d_theta"]) < TOL
+    assert C.rel_err(d_alpha, g[f"{tag}_d_alpha"]) < TOL
+
+
+def _load_net(vd, case, **kw):
+    net = vd.BNN(sizes=[case["layers"][0]["theta"].shape[0]] + [p["theta"].shape[1] for p in case["layers"]], **kw).cuda()
+    with torch.no_grad():
+        for l, p in zip(net.layers, case["layers"]):
+            l.theta.copy_(p["theta"])
+            l.alpha.copy_(p["alpha"])
+    return net
+
+
+def test_net_objective_matches_reference_golden(vd):
+    """BNN.forward + loss_fn + backward of the 784-1200-1200-1200-10 net under replayed zeta vs the reference's outputs."""
+    g = np.load(os.path.join(C.GOLDEN, "vd.npz"))
+    case = C.vd_net_case(seed=80, batch=100)
+    net = _load_net(vd, case, alpha_trainable=True)
+    net.train()
+    logp = net(case["x"].cuda(), zetas=[z.cuda() for z in case["zetas"]])
+    loss = vd.loss_fn(logp, case["y"].cuda(), net, num_batches=600.0)
+    loss.backward()
+    assert C.rel_err(logp.detach(), g["net_logp"]) < TOL
+    assert torch.equal(logp.argmax(1).cpu(), torch.from_numpy(g["net_logp"]).argmax(1))
+    assert abs(loss.item() - float(g["net_loss"])) / abs(float(g["net_loss"])) < TOL
+    for li, l in enumerate(net.layers):
+        d = C.grad_digest(l.theta.grad.cpu())
+        assert C.rel_err(d["sample"], g[f"net_l{li}_theta_sample"]) < TOL, li
+        assert abs(d["l2"] - float(g[f"net_l{li}_theta_l2"])) / float(g[f"net_l{li}_theta_l2"]) < TOL, li
+        assert C.rel_err(l.alpha.grad, g[f"net_l{li}_d_alpha"]) < TOL, li
+
+
+def test_state_dict_and_init_follow_the_reference(vd):
+    """theta is the only registered state (the reference's alpha is a non-leaf tensor, VD:61); init consumes torch's RNG
+    like VD:59: (low - high) * rand(n, m) + high."""
+    torch.manual_seed(4)
+    layer = vd.BayesianLayer(7, 5)
+    torch.manual_seed(4)
+    want = (-0.1 - 0.1) * torch.rand(size=(7, 5)) + 0.1
+    assert torch.equal(layer.theta.detach(), want)
+    assert list(layer.state_dict()) == ["theta"] and [n for n, _ in layer.named_parameters()] == ["theta"]
+    assert torch.equal(layer.alpha, torch.full((5,), 0.2))
+    assert list(vd.BNN().state_dict()) == ["l1.theta", "l2.theta", "l3.theta", "l4.theta"]
+
+
+def test_native_noise_matches_oracle_on_exported_zeta(vd):
+    import lbbnn
+    case = C.vd_layer_case(41, 100, 784, 1200)
+    layer = vd.BayesianLayer(784, 1200).cuda()
+    with torch.no_grad():
+        layer.theta.copy_(case["p"]["theta"])
+    act = layer(case["x"].cuda())
+    zeta = lbbnn.philox_normal((100, 1200), *layer.last_noise_key).cpu()
+    assert abs(zeta.mean().item()) < 0.02 and abs(zeta.std().item() - 1) < 0.02
+    ref = O.vd_forward(case["x"].double(), case["p"]["theta"].double(), case["p"]["alpha"].double(), zeta.double())
+    assert C.rel_err(act.detach(), ref) < TOL
+    assert not torch.equal(layer(case["x"].cuda()), act)       # a fresh draw per call
+
+
+def test_cpu_tensors_are_rejected(vd):
+    import lbbnn
+    layer = vd.BayesianLayer(8, 4)
+    with pytest.raises(lbbnn.LbbnnError):
+        layer(torch.zeros(2, 8))
+
+
+@pytest.mark.parametrize("use_graph,alpha_trainable,sizes", [(False, False, (37, 23, 5)), (True, False, None), (True, True, None)])
+def test_trainer_step_matches_oracle_plus_torch_adamw(vd, use_graph, alpha_trainable, sizes):
+    """Whole captured step (fwd, loss_fn, bwd, AdamW) vs oracle autograd + torch.optim.AdamW, 3 steps."""
+    szs = C.VD_SIZES if sizes is None else list(zip(sizes[:-1], sizes[1:]))
+    case = C.vd_net_case(seed=85, batch=100, sizes=szs, classes=szs[-1][1])
+    net = _load_net(vd, case, alpha_trainable=alpha_trainable)
+    tr = vd.VDTrainer(net, batch_size=100, num_batches=600.0, lr=1e-4, use_graph=use_graph, inject_noise=True)
+    names = ("theta", "alpha") if alpha_trainable else ("theta",)
+    layers = [{k: v.clone().requires_grad_(k in names) for k, v in p.items()} for p in case["layers"]]
+    opt = torch.optim.AdamW([p[k] for p in layers for k in names], lr=1e-4)
+    # the noise seed is one for which no hidden pre-activation lands within fp32 rounding of 0 (a relu tie flips a mask bit
+    # and moves the upstream gradients by ~1e-3; seen with seed 98 at step 1 of the trainable-alpha case)
+    rng = np.random.default_rng(198 if alpha_trainable else 98)
+    for step in range(3):
+        zetas = [C.t(rng.standard_normal(size=tuple(z.shape))) for z in case["zetas"]]
+        for b, z in zip(tr.buf, zetas):
+            b["zeta"].copy_(z)
+        out = tr.step(case["x"], case["y"])
+        opt.zero_grad()
+        loss, nll, kl, _ = O.vd_net_loss(case["x"], case["y"], layers, zetas, 600.0)
+        loss.backward()
+        assert abs(out["nll"] - nll.item()) / abs(nll.item()) < 1e-4, step
+        assert abs(out["kl"] - kl.item()) / abs(kl.item()) < TOL, step
+        for li, (l, p) in enumerate(zip(net.layers, layers)):
+            for k in names:
+                assert C.rel_err(getattr(l, k).grad, p[k].grad) < 5e-5, (step, li, k, "grad")
+                p[k].grad = getattr(l, k).grad.detach().cpu().clone()      # compare the optimizer kernel exactly
+        opt.step()
+        for li, (l, p) in enumerate(zip(net.layers, layers)):
+            for k in names:
+                assert C.rel_err(getattr(l, k).data, p[k].data) < 2e-6, (step, li, k, "param")
+
+
+def test_trainer_native_noise_changes_every_replay_and_ensemble_runs(vd):
+    case = C.vd_net_case(seed=86, batch=100)
+    net = _load_net(vd, case)
+    tr = vd.VDTrainer(net, batch_size=100, lr=0.0, weight_decay=0.0, use_graph=True)
+    a = tr.step(case["x"], case["y"])["nll"]
+    b = tr.step(case["x"], case["y"])["nll"]
+    assert a != b and tr.step_dev.item() == 2
+    pred = vd.predict_ensemble(net, case["x"].cuda(), samples=4)
+    assert pred.shape == (100, 10) and torch.isfinite(pred).all()
