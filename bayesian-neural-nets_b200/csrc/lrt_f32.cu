@@ -127,6 +127,90 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_prologue(const PrologueArgs 
 }
 
 // ================================================================================================
+// prologue of the bf16 tensor-core path: M, V as bf16 operands (out,in) AND their (in,out) transposes, plus the KL
+// partial sums, in one pass over mu, rho, lambda (replaces lrt_f32_prologue -> fp32 M, V -> bf16_pack).  64x64 tile per
+// block: row-major outputs straight from registers (4 bf16 = 8 bytes per store), transposed outputs through padded
+// shared-memory tiles so both directions are written in full 8-byte pieces.
+// ================================================================================================
+struct PrologueBf16Args {
+  const float *mu, *rho, *lam;
+  int64_t rows, cols;                 // (out, in)
+  __nv_bfloat16 *M, *V, *MT, *VT;     // MT, VT may be NULL
+  float *M32, *V32;                   // optional fp32 copies (NULL = skip)
+  double* kl_part;                    // [gridDim.x * gridDim.y] or NULL
+  int var_mode;
+  lbbnn_priors pri;
+};
+
+__device__ __forceinline__ uint2 pack4_bf16(const float v[4]) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+__global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16Args a) {
+  __shared__ float tM[64][65], tV[64][65];
+  __shared__ float red[32];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  float kl = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty + 16 * i;
+    const int64_t r = r0 + rl, c = c0 + tx * 4;
+    float m[4] = {0.f, 0.f, 0.f, 0.f}, v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < a.rows && c < a.cols) {            // cols % 4 == 0: the quad is entirely inside the row
+      const int64_t e = r * a.cols + c;
+      const float4 mu = __ldg(reinterpret_cast<const float4*>(a.mu + e));
+      const float4 rho = __ldg(reinterpret_cast<const float4*>(a.rho + e));
+      const float4 lam = __ldg(reinterpret_cast<const float4*>(a.lam + e));
+      const float muv[4] = {mu.x, mu.y, mu.z, mu.w}, rhov[4] = {rho.x, rho.y, rho.z, rho.w};
+      const float lamv[4] = {lam.x, lam.y, lam.z, lam.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float sg = sigma_of(rhov[j]), al = alpha_of(lamv[j]);
+        const Moments mo = weight_moments(muv[j], sg, al, a.var_mode);
+        m[j] = mo.m;
+        v[j] = mo.v;
+        if (a.kl_part) kl += kl_weight_elem(muv[j], sg, al, a.pri);
+      }
+      *reinterpret_cast<uint2*>(a.M + e) = pack4_bf16(m);
+      *reinterpret_cast<uint2*>(a.V + e) = pack4_bf16(v);
+      if (a.M32) *reinterpret_cast<float4*>(a.M32 + e) = make_float4(m[0], m[1], m[2], m[3]);
+      if (a.V32) *reinterpret_cast<float4*>(a.V32 + e) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { tM[rl][tx * 4 + j] = m[j]; tV[rl][tx * 4 + j] = v[j]; }
+  }
+  if (a.MT) {
+    __syncthreads();
+    const bool vec = (a.rows % 4 == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cl = ty + 16 * i, rl = tx * 4;           // output row = input column c, 4 consecutive r
+      const int64_t c = c0 + cl, r = r0 + rl;
+      if (c >= a.cols || r >= a.rows) continue;
+      const float m[4] = {tM[rl][cl], tM[rl + 1][cl], tM[rl + 2][cl], tM[rl + 3][cl]};
+      const float v[4] = {tV[rl][cl], tV[rl + 1][cl], tV[rl + 2][cl], tV[rl + 3][cl]};
+      if (vec) {
+        *reinterpret_cast<uint2*>(a.MT + c * a.rows + r) = pack4_bf16(m);
+        *reinterpret_cast<uint2*>(a.VT + c * a.rows + r) = pack4_bf16(v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (r + j < a.rows) {
+            a.MT[c * a.rows + r + j] = __float2bfloat16_rn(m[j]);
+            a.VT[c * a.rows + r + j] = __float2bfloat16_rn(v[j]);
+          }
+      }
+    }
+  }
+  if (a.kl_part) {
+    const float s = block_sum(kl, red);
+    if (threadIdx.x == 0) a.kl_part[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = (double)s;
+  }
+}
+
+// ================================================================================================
 // forward: split-K partial dual GEMM  E = x M^T,  S = x^2 V^T
 // ================================================================================================
 constexpr int F_BM = 128, F_BN = 64, F_BK = 16;
@@ -742,6 +826,8 @@ WsLayout ws_layout(int64_t B, int64_t K, int64_t N) {
   return w;
 }
 
+inline bool aligned16_host(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 int check_layer(const lbbnn_layer* L) {
   LBBNN_REQUIRE(L != nullptr, "layer is NULL");
   LBBNN_REQUIRE(L->in_features > 0 && L->out_features > 0, "bad layer shape (%lld,%lld)", (long long)L->out_features,
@@ -1005,4 +1091,40 @@ extern "C" int lbbnn_linear_f32_bwd_input(const float* x, const float* W, const 
   lrt_f32_bwd_x_epilogue<<<(unsigned)blocks, kEpiThreads, 0, (cudaStream_t)s>>>(a.part, sp.splits, B * K, x,
                                                                   (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0, 0, dx);
   return check_launch("lrt_f32_bwd_x_epilogue");
+}
+
+extern "C" size_t lbbnn_lrt_bf16_prologue_workspace_bytes(int64_t in_features, int64_t out_features) {
+  if (in_features <= 0 || out_features <= 0) return 0;
+  return align_up((size_t)(ceil_div(in_features, 64) * ceil_div(out_features, 64)) * sizeof(double));
+}
+
+extern "C" int lbbnn_lrt_bf16_prologue(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, void* M_bf, void* V_bf,
+                                       void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out, void* ws,
+                                       size_t ws_bytes, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(pri && M_bf && V_bf, "NULL argument");
+  LBBNN_REQUIRE((MT_bf == nullptr) == (VT_bf == nullptr), "transposed outputs come in pairs");
+  LBBNN_REQUIRE(L->z == nullptr && L->z_kl == nullptr, "the bf16 prologue has no MNF z path");
+  const int64_t K = L->in_features, N = L->out_features;
+  LBBNN_REQUIRE(K % 4 == 0, "in_features must be a multiple of 4 (got %lld)", (long long)K);
+  LBBNN_REQUIRE(aligned16_host(L->weight_mu) && aligned16_host(L->weight_rho) && aligned16_host(L->lambdal) &&
+                    aligned16_host(M_bf) && aligned16_host(V_bf) && aligned16_host(MT_bf) && aligned16_host(VT_bf) &&
+                    aligned16_host(M32) && aligned16_host(V32),
+                "parameters and outputs must be 16-byte aligned");
+  dim3 grid((unsigned)ceil_div(K, 64), (unsigned)ceil_div(N, 64));
+  LBBNN_REQUIRE(grid.y <= 65535, "too many output features for one launch");
+  const size_t need = lbbnn_lrt_bf16_prologue_workspace_bytes(K, N);
+  LBBNN_REQUIRE(kl_out == nullptr || (ws && ws_bytes >= need), "workspace too small for the KL partials");
+  cudaStream_t st = (cudaStream_t)s;
+  PrologueBf16Args pa;
+  pa.mu = L->weight_mu; pa.rho = L->weight_rho; pa.lam = L->lambdal; pa.rows = N; pa.cols = K;
+  pa.M = (__nv_bfloat16*)M_bf; pa.V = (__nv_bfloat16*)V_bf; pa.MT = (__nv_bfloat16*)MT_bf; pa.VT = (__nv_bfloat16*)VT_bf;
+  pa.M32 = M32; pa.V32 = V32; pa.kl_part = kl_out ? (double*)ws : nullptr; pa.var_mode = var_mode; pa.pri = *pri;
+  lrt_bf16_prologue<<<grid, kThreads, 0, st>>>(pa);
+  if (int rc = check_launch("lrt_bf16_prologue")) return rc;
+  if (kl_out) {
+    lrt_kl_finalize<<<1, kThreads, 0, st>>>((const double*)ws, (int)(grid.x * grid.y), L->bias_mu, L->bias_rho, N, *pri, kl_out);
+    return check_launch("lrt_kl_finalize");
+  }
+  return LBBNN_OK;
 }

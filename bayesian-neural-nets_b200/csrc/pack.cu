@@ -85,6 +85,117 @@ __global__ void __launch_bounds__(256) colsum2_stage2(const float* __restrict__ 
   out[i] = acc;
 }
 
+// Input gradient of a layer with FEW outputs (the classifier: out <= 12, 0.04 % of the step's FLOPs) fused with the staging
+// of the previous layer's backward operands -- what lbbnn_tc_lrt_bwd_input's epilogue does for the wide layers:
+//   dx = g M + 2 x .* (gS V),  gS = g .* ds;  through the relu that produced x;  dE = dx, dS = dx .* ds_prev
+// written as bf16 (batch, in) and transposed (in, batch), plus this tile's column sums of the fp32 dE, dS (the previous
+// layer's bias gradients).  64 batch rows x 64 input columns per block; M, V and the tile's g, gS sit in shared memory.
+constexpr int kSmallMaxOut = 12;      // static shared memory: two 64x65 transpose tiles + M, V, g, gS stay under 48 KB
+
+struct BwdSmallArgs {
+  const float *g, *ds, *M, *V;            // (B, O), (B, O), (O, K), (O, K)
+  const __nv_bfloat16* x;                 // (B, K)
+  const float* ds_prev;                   // (B, K)
+  int64_t B, K;
+  int O, mask;
+  __nv_bfloat16 *de, *dse, *deT, *dsT;
+  float* partial;                         // [gridDim.y][2][K]
+};
+
+__device__ __forceinline__ uint2 pack4(const float v[4]) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+__global__ void __launch_bounds__(256) lrt_bwd_input_small_kernel(const BwdSmallArgs a) {
+  __shared__ float tE[64][65], tS[64][65];
+  __shared__ __align__(16) float sM[kSmallMaxOut][64], sV[kSmallMaxOut][64];
+  __shared__ float sG[64][kSmallMaxOut + 1], sGS[64][kSmallMaxOut + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  for (int e = tid; e < a.O * 64; e += 256) {
+    const int o = e >> 6, c = e & 63;
+    const bool ok = c0 + c < a.K;
+    sM[o][c] = ok ? __ldg(a.M + (int64_t)o * a.K + c0 + c) : 0.f;
+    sV[o][c] = ok ? __ldg(a.V + (int64_t)o * a.K + c0 + c) : 0.f;
+  }
+  for (int e = tid; e < 64 * a.O; e += 256) {
+    const int rl = e / a.O, o = e % a.O;
+    const int64_t r = r0 + rl;
+    const float gv = r < a.B ? __ldg(a.g + r * a.O + o) : 0.f;
+    sG[rl][o] = gv;
+    sGS[rl][o] = r < a.B ? gv * __ldg(a.ds + r * a.O + o) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty + 16 * i;
+    const int64_t r = r0 + rl, c = c0 + tx * 4;
+    float dE[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < a.B && c < a.K) {                  // K % 4 == 0: whole quad inside the row
+      float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int o = 0; o < a.O; ++o) {
+        const float4 m = *reinterpret_cast<const float4*>(&sM[o][tx * 4]);
+        const float4 v = *reinterpret_cast<const float4*>(&sV[o][tx * 4]);
+        const float gv = sG[rl][o], gs = sGS[rl][o];
+        e1[0] = fmaf(gv, m.x, e1[0]); e1[1] = fmaf(gv, m.y, e1[1]); e1[2] = fmaf(gv, m.z, e1[2]); e1[3] = fmaf(gv, m.w, e1[3]);
+        e2[0] = fmaf(gs, v.x, e2[0]); e2[1] = fmaf(gs, v.y, e2[1]); e2[2] = fmaf(gs, v.z, e2[2]); e2[3] = fmaf(gs, v.w, e2[3]);
+      }
+      const int64_t e = r * a.K + c;
+      const uint2 xu = __ldg(reinterpret_cast<const uint2*>(a.x + e));
+      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.x));
+      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.y));
+      const float xv[4] = {x01.x, x01.y, x23.x, x23.y};
+      const float4 f4 = a.ds_prev ? __ldg(reinterpret_cast<const float4*>(a.ds_prev + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float gx = fmaf(2.0f * xv[j], e2[j], e1[j]);
+        if (a.mask && !(xv[j] > 0.f)) gx = 0.f;
+        dE[j] = gx;
+        dS[j] = gx * fv[j];
+      }
+      *reinterpret_cast<uint2*>(a.de + e) = pack4(dE);
+      *reinterpret_cast<uint2*>(a.dse + e) = pack4(dS);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { tE[rl][tx * 4 + j] = dE[j]; tS[rl][tx * 4 + j] = dS[j]; }
+  }
+  __syncthreads();
+  const bool vec = (a.B % 4 == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = ty + 16 * i, rl = tx * 4;             // output row = input column, 4 consecutive batch rows
+    const int64_t c = c0 + cl, r = r0 + rl;
+    const float e[4] = {tE[rl][cl], tE[rl + 1][cl], tE[rl + 2][cl], tE[rl + 3][cl]};
+    const float q[4] = {tS[rl][cl], tS[rl + 1][cl], tS[rl + 2][cl], tS[rl + 3][cl]};
+    if (c < a.K && r < a.B && a.deT) {
+      if (vec) {
+        *reinterpret_cast<uint2*>(a.deT + c * a.B + r) = pack4(e);
+        *reinterpret_cast<uint2*>(a.dsT + c * a.B + r) = pack4(q);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (r + j < a.B) {
+            a.deT[c * a.B + r + j] = __float2bfloat16_rn(e[j]);
+            a.dsT[c * a.B + r + j] = __float2bfloat16_rn(q[j]);
+          }
+      }
+    }
+    // column sums over the tile's 64 rows: 16 lanes (tx) of a half-warp hold 4 rows each; fixed-order butterfly
+    float s1 = (e[0] + e[1]) + (e[2] + e[3]), s2 = (q[0] + q[1]) + (q[2] + q[3]);     // out-of-range rows hold zeros
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+      s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (tx == 0 && c < a.K && a.partial) {
+      a.partial[((int64_t)blockIdx.y * 2 + 0) * a.K + c] = s1;
+      a.partial[((int64_t)blockIdx.y * 2 + 1) * a.K + c] = s2;
+    }
+  }
+}
+
 int colsum_slices(int64_t rows) {
   int64_t s = rows / 128;
   return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
@@ -125,4 +236,38 @@ extern "C" int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_
   if (int rc = check_launch("colsum2_stage1")) return rc;
   colsum2_stage2<<<(unsigned)ceil_div(2 * cols, 256), 256, 0, (cudaStream_t)s>>>((const float*)ws, slices, cols, out);
   return check_launch("colsum2_stage2");
+}
+
+extern "C" size_t lbbnn_tc_lrt_bwd_input_small_workspace_bytes(int64_t batch, int64_t in_features) {
+  if (batch <= 0 || in_features <= 0) return 0;
+  return (size_t)ceil_div(batch, 64) * 2 * in_features * sizeof(float);
+}
+
+extern "C" int lbbnn_tc_lrt_bwd_input_small(const float* gact, const float* ds_factor, const float* M32, const float* V32,
+                                            int64_t batch, int64_t in_features, int64_t out_features, const void* x_bf,
+                                            const float* ds_prev, int flags, void* dE_bf, void* dS_bf, void* dET_bf,
+                                            void* dST_bf, float* colsum, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(gact && ds_factor && M32 && V32 && x_bf && dE_bf && dS_bf, "NULL argument");
+  LBBNN_REQUIRE(batch > 0 && in_features > 0 && out_features > 0, "empty shape");
+  LBBNN_REQUIRE(out_features <= kSmallMaxOut, "out_features %lld > %d: use lbbnn_tc_lrt_bwd_input", (long long)out_features,
+                kSmallMaxOut);
+  LBBNN_REQUIRE(in_features % 4 == 0, "in_features must be a multiple of 4");
+  LBBNN_REQUIRE((dET_bf == nullptr) == (dST_bf == nullptr), "transposed outputs come in pairs");
+  const size_t need = lbbnn_tc_lrt_bwd_input_small_workspace_bytes(batch, in_features);
+  LBBNN_REQUIRE(colsum == nullptr || (ws && ws_bytes >= need), "workspace too small for the column-sum partials");
+  dim3 grid((unsigned)ceil_div(in_features, 64), (unsigned)ceil_div(batch, 64));
+  LBBNN_REQUIRE(grid.y <= 65535, "too many rows for one launch");
+  BwdSmallArgs a;
+  a.g = gact; a.ds = ds_factor; a.M = M32; a.V = V32; a.x = (const __nv_bfloat16*)x_bf; a.ds_prev = ds_prev;
+  a.B = batch; a.K = in_features; a.O = (int)out_features; a.mask = (flags & LBBNN_FLAG_MASK_DX) ? 1 : 0;
+  a.de = (__nv_bfloat16*)dE_bf; a.dse = (__nv_bfloat16*)dS_bf; a.deT = (__nv_bfloat16*)dET_bf; a.dsT = (__nv_bfloat16*)dST_bf;
+  a.partial = colsum ? (float*)ws : nullptr;
+  lrt_bwd_input_small_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(a);
+  if (int rc = check_launch("lrt_bwd_input_small")) return rc;
+  if (colsum) {
+    colsum2_stage2<<<(unsigned)ceil_div(2 * in_features, 256), 256, 0, (cudaStream_t)s>>>((const float*)ws, (int)grid.y,
+                                                                                          in_features, colsum);
+    return check_launch("colsum2_stage2");
+  }
+  return 0;
 }

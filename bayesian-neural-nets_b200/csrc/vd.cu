@@ -139,7 +139,7 @@ __device__ __forceinline__ bool tile_vec_ok(const float* p, int64_t ld, int kc, 
   return (ld % 4 == 0) && aligned16(p) && (r0 + R <= rows) && (k0 + BK <= kend) && ((kc ? k0 : r0) % 4 == 0);
 }
 
-__global__ void __launch_bounds__(kThreads) vd_dual_gemm_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) vd_dual_gemm_kernel(const GemmArgs a) {
   __shared__ __align__(16) float As1[BK][PADM], As2[BK][PADM], Bs1[BK][PADN], Bs2[BK][PADN];
   const int tid = threadIdx.x, tx = tid % (BN / 4), ty = tid / (BN / 4);
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) vd_kl_kernel(const float* __restrict__ al
 int pick_splits(int64_t M, int64_t N, int64_t K) {
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int64_t ksteps = ceil_div(K, BK);
-  int64_t want = ceil_div(2 * (int64_t)sm_count(), tiles);          // about two CTAs per SM
+  int64_t want = ceil_div(4 * (int64_t)sm_count(), tiles);          // about four CTAs (16 warps) per SM
   want = std::min<int64_t>(want, ksteps / 4);                        // at least 4 k-steps per slice
   return (int)std::max<int64_t>(1, std::min<int64_t>(want, 32));
 }

@@ -368,10 +368,12 @@ class LRTTensorCoreTrainer:
     """
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
-                 use_graph=True, inject_noise=False, process_group=None, fused_update=True):
+                 use_graph=True, inject_noise=False, process_group=None, fused_update=True, fused_prologue=True,
+                 fused_head_dx=True):
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
+        self.fused_prologue = bool(fused_prologue)
         L = len(self.layers)
         for l in self.layers:
             if l.in_features % 8:
@@ -412,7 +414,11 @@ class LRTTensorCoreTrainer:
         B = self.B
         sizes = [(l.in_features, l.out_features) for l in self.layers]
         self.sizes = sizes
-        self.simt_dx = [o % 8 != 0 for _, o in sizes]       # input-gradient GEMM on the fp32 SIMT kernel
+        # input-gradient GEMM off the tensor cores: a head with <= 12 outputs goes through the fused CUDA-core kernel that
+        # also stages the layer below's dE / dS / column sums (lbbnn_tc_lrt_bwd_input_small); other widths that break the
+        # TMA pitch fall back to the fp32 SIMT GEMM + separate staging passes
+        self.small_dx = [o <= 12 and o % 8 != 0 and fused_head_dx for _, o in sizes]
+        self.simt_dx = [o % 8 != 0 and not sm for (_, o), sm in zip(sizes, self.small_dx)]
         self.x = torch.zeros(B, sizes[0][0], **f32)
         self.y = torch.zeros(B, dtype=torch.int64, device=dev)
         self.x_bf, self.x2_bf = torch.zeros(B, sizes[0][0], **bf), torch.zeros(B, sizes[0][0], **bf)
@@ -428,11 +434,12 @@ class LRTTensorCoreTrainer:
             last = li == L - 1
             need_g32 = last or self.simt_dx[li + 1]        # dL/d(pre-activation) arrives in fp32
             need_act32 = last or self.simt_dx[li + 1]      # fp32 activations: logits / input of a SIMT dX
-            tc_dx = li > 0 and not self.simt_dx[li]
+            tc_dx = li > 0 and not self.simt_dx[li] and not self.small_dx[li]
             d = dict(
                 M=torch.zeros(o, i, **bf), V=torch.zeros(o, i, **bf),
                 MT=torch.zeros(i, o, **bf) if tc_dx else None, VT=torch.zeros(i, o, **bf) if tc_dx else None,
-                mv32=torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) if (li > 0 and self.simt_dx[li]) else None,
+                mv32=(torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32)
+                      if (li > 0 and (self.simt_dx[li] or self.small_dx[li])) else None),
                 act=None if last else torch.zeros(B, o, **bf), act2=None if last else torch.zeros(B, o, **bf),
                 actT=None if last else torch.zeros(o, B, **bf), act2T=None if last else torch.zeros(o, B, **bf),
                 dsf=torch.zeros(B, o, **f32), act32=torch.zeros(B, o, **f32) if need_act32 else None,
@@ -449,6 +456,8 @@ class LRTTensorCoreTrainer:
         self.stats = torch.zeros(1 + L, **f32)
         nbytes = max([1 << 20, B // 8 * 4 + 1024] +
                      [int(K.lib.lbbnn_colsum2_workspace_bytes(B, o)) for _, o in sizes] +
+                     [int(K.lib.lbbnn_lrt_bf16_prologue_workspace_bytes(i, o)) for i, o in sizes] +
+                     [int(K.lib.lbbnn_tc_lrt_bwd_input_small_workspace_bytes(B, i)) for (i, o), sm in zip(sizes, self.small_dx) if sm] +
                      [K.lrt_workspace_bytes(B, i, o) for (i, o), sd in zip(sizes, self.simt_dx) if sd])
         self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         self.x_host = torch.zeros(B, sizes[0][0], dtype=torch.float32).pin_memory()
@@ -485,10 +494,16 @@ class LRTTensorCoreTrainer:
                 V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
             else:
                 M32, V32 = self.M32, self.V32
-            K.check(lib.lbbnn_lrt_f32_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, K.FLAG_SAMPLE, P(M32), P(V32),
-                                               self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
-            K.check(lib.lbbnn_bf16_pack(P(M32), P(V32), K.PACK_PAIR, fo, fi, P(d["M"], bf), P(d["V"], bf),
-                                        P(d["MT"], bf, True), P(d["VT"], bf, True), st)); n += 1
+            if self.fused_prologue:    # mu, rho, lambda -> bf16 M, V (+ transposes) + KL in one pass
+                keep = d["mv32"] is not None
+                K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf),
+                                                    P(d["MT"], bf, True), P(d["VT"], bf, True), P(M32) if keep else None,
+                                                    P(V32) if keep else None, self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
+            else:
+                K.check(lib.lbbnn_lrt_f32_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, K.FLAG_SAMPLE, P(M32), P(V32),
+                                                   self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
+                K.check(lib.lbbnn_bf16_pack(P(M32), P(V32), K.PACK_PAIR, fo, fi, P(d["M"], bf), P(d["V"], bf),
+                                            P(d["MT"], bf, True), P(d["VT"], bf, True), st)); n += 1
             K.check(lib.lbbnn_tc_lrt_fwd(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data),
                                          P(l.bias_rho.data), self._noise(i),
                                          K.FLAG_SAMPLE | (0 if last else K.FLAG_RELU),
@@ -516,7 +531,7 @@ class LRTTensorCoreTrainer:
                 K.check(lib.lbbnn_bf16_pack(P(d["g32"]), P(d["dsf"]), K.PACK_SCALE, B, fo, P(d["dE"], bf), P(d["dS"], bf),
                                             P(d["dET"], bf), P(d["dST"], bf), st)); n += 1
                 K.check(lib.lbbnn_colsum2(P(d["g32"]), P(d["dsf"]), 0, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
-            else:
+            elif not (i + 1 < L and self.small_dx[i + 1]):     # (the fused head kernel already wrote this layer's column sums)
                 K.check(lib.lbbnn_colsum2(P(d["dE"], bf), P(d["dS"], bf), 1, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
             xT, x2T = (self.xT_bf, self.x2T_bf) if i == 0 else (self.tc[i - 1]["actT"], self.tc[i - 1]["act2T"])
             # dM = dE^T x, dV = dS^T x^2: (out, B) x (in, B)^T
@@ -534,7 +549,13 @@ class LRTTensorCoreTrainer:
             if i == 0:
                 continue
             p = self.tc[i - 1]
-            if self.simt_dx[i]:
+            if self.small_dx[i]:
+                M32, V32 = d["mv32"], d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
+                K.check(lib.lbbnn_tc_lrt_bwd_input_small(P(d["g32"]), P(d["dsf"]), P(M32), P(V32), B, fi, fo, P(p["act"], bf),
+                                                         P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf),
+                                                         P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf), P(p["colsum"]),
+                                                         ws, wsn, st)); n += 2
+            elif self.simt_dx[i]:
                 K.check(lib.lbbnn_lrt_f32_bwd_input(descs[i], P(p["act32"]), B, P(d["g32"]), P(d["dsf"]), l.cfg.priors,
                                                     l.cfg.var_mode, K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(d["mv32"]),
                                                     P(p["g32"]), ws, wsn, st)); n += 2

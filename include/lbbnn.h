@@ -177,6 +177,25 @@ LBBNN_API int lbbnn_bf16_pack(const float* a, const float* b, int op, int64_t ro
                               void* out1, void* out2, void* out1T, void* out2T, lbbnn_stream s);
 /* column sums over the batch: out[0..cols) = sum_r a, out[cols..2cols) = sum_r a*b (fixed order).
  * a_is_bf16: a and b(=second operand, already the product) are bf16 tensors dE, dS instead. */
+/* Prologue of the bf16 path in one pass over mu, rho, lambda: M, V (LRT:170-171) as bf16 (out,in), their (in,out)
+ * transposes (may be NULL), optional fp32 copies (M32, V32; NULL = skip) and the layer KL (LRT:182-194) into kl_out
+ * (NULL = skip).  Same values as lbbnn_lrt_f32_prologue followed by lbbnn_bf16_pack(PACK_PAIR), without the fp32 round
+ * trip.  in_features % 4 == 0; MNF's z is not supported here. */
+LBBNN_API size_t lbbnn_lrt_bf16_prologue_workspace_bytes(int64_t in_features, int64_t out_features);
+LBBNN_API int lbbnn_lrt_bf16_prologue(const lbbnn_layer* layer, const lbbnn_priors* priors, int var_mode, void* M_bf,
+                                      void* V_bf, void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out,
+                                      void* workspace, size_t workspace_bytes, lbbnn_stream s);
+/* Input gradient of a layer with out_features <= 12 (the classifier head) on the CUDA cores, fused with what
+ * lbbnn_tc_lrt_bwd_input's epilogue produces for the layer below: dx = g M + 2 x .* ((g .* ds) V) through the relu that
+ * produced x (FLAG_MASK_DX), dE = dx, dS = dx .* ds_prev as bf16 (batch,in) + transposes (in,batch; may be NULL), and
+ * colsum = [sum_b dE; sum_b dS] (2*in floats, from the fp32 values; NULL = skip).  x_bf: the bf16 activations the
+ * layer's forward GEMM consumed.  M32, V32: fp32 (out,in) from lbbnn_lrt_bf16_prologue. */
+LBBNN_API size_t lbbnn_tc_lrt_bwd_input_small_workspace_bytes(int64_t batch, int64_t in_features);
+LBBNN_API int lbbnn_tc_lrt_bwd_input_small(const float* gact, const float* ds_factor, const float* M32, const float* V32,
+                                           int64_t batch, int64_t in_features, int64_t out_features, const void* x_bf,
+                                           const float* ds_prev, int flags, void* dE_bf, void* dS_bf, void* dET_bf,
+                                           void* dST_bf, float* colsum, void* workspace, size_t workspace_bytes,
+                                           lbbnn_stream s);
 LBBNN_API size_t lbbnn_colsum2_workspace_bytes(int64_t rows, int64_t cols);
 LBBNN_API int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols,
                             float* out, void* workspace, size_t workspace_bytes, lbbnn_stream s);

@@ -106,6 +106,69 @@ def test_tc_lrt_bwd_input_epilogue(K):
     assert torch.equal(outs[2], outs[0].T.contiguous()) and torch.equal(outs[3], outs[1].T.contiguous())
 
 
+@pytest.mark.parametrize("o,i", [(256, 192), (10, 200), (130, 72), (64, 64), (1, 8)])
+def test_bf16_prologue_equals_fp32_prologue_plus_pack(K, o, i):
+    """lbbnn_lrt_bf16_prologue (one pass over mu, rho, lambda) writes bit-identical bf16 M, V and transposes, identical fp32
+    copies and the same KL (fp32 summation order aside) as lbbnn_lrt_f32_prologue -> lbbnn_bf16_pack(PACK_PAIR)."""
+    case = C.lrt_layer_case(50 + o, 4, i, o, spread_lambda=True)
+    p = {k: v.cuda() for k, v in case["p"].items()}
+    layer = K.make_layer(p["weight_mu"], p["weight_rho"], p["lambdal"], p["bias_mu"], p["bias_rho"])
+    pri, bf = K.Priors(0.0, 1.0, 0.05, 0.0, 1.0), torch.bfloat16
+    ws = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    for var_mode in (K.VAR_REFERENCE, K.VAR_EXACT):
+        M32, V32, kl = torch.empty(o, i, device="cuda"), torch.empty(o, i, device="cuda"), torch.zeros(1, device="cuda")
+        K.check(K.lib.lbbnn_lrt_f32_prologue(layer, pri, var_mode, K.FLAG_SAMPLE, K.ptr(M32), K.ptr(V32), K.ptr(kl), ws.data_ptr(),
+                                             ws.numel(), K.current_stream()))
+        ref = K.bf16_pack(M32, V32, K.PACK_PAIR)
+        got = [torch.full((o, i), 7.0, dtype=bf, device="cuda") for _ in range(2)] + \
+              [torch.full((i, o), 7.0, dtype=bf, device="cuda") for _ in range(2)]
+        m32, v32, kl2 = torch.empty(o, i, device="cuda"), torch.empty(o, i, device="cuda"), torch.zeros(1, device="cuda")
+        assert K.lib.lbbnn_lrt_bf16_prologue_workspace_bytes(i, o) <= ws.numel()
+        K.check(K.lib.lbbnn_lrt_bf16_prologue(layer, pri, var_mode, *[K.ptr(t, bf) for t in got], K.ptr(m32), K.ptr(v32),
+                                              K.ptr(kl2), ws.data_ptr(), ws.numel(), K.current_stream()))
+        torch.cuda.synchronize()
+        for a, b in zip(got, ref):
+            assert torch.equal(a, b)
+        assert torch.equal(m32, M32) and torch.equal(v32, V32)
+        assert abs(kl2.item() - kl.item()) <= 2e-6 * abs(kl.item())
+        # without the optional outputs
+        only = [torch.empty(o, i, dtype=bf, device="cuda") for _ in range(2)]
+        K.check(K.lib.lbbnn_lrt_bf16_prologue(layer, pri, var_mode, K.ptr(only[0], bf), K.ptr(only[1], bf), None, None, None, None,
+                                              None, None, 0, K.current_stream()))
+        assert torch.equal(only[0], ref[0]) and torch.equal(only[1], ref[1])
+
+
+@pytest.mark.parametrize("b,i,o,mask", [(256, 192, 10, True), (100, 72, 3, True), (65, 64, 12, False), (8192, 256, 10, True)])
+def test_tc_lrt_bwd_input_small(K, b, i, o, mask):
+    """The fused head kernel: dx = g M + 2 x (g ds V) through the relu, dE / dS as bf16 + transposes, fp32 column sums."""
+    rng = np.random.default_rng(b + i + o)
+    bf = torch.bfloat16
+    f = lambda *shape, scale=1.0: (torch.from_numpy(rng.standard_normal(size=shape).astype(np.float32)) * scale).cuda()
+    g, ds = f(b, o), f(b, o, scale=0.3)
+    M, V = f(o, i, scale=0.1), f(o, i, scale=0.01).abs()
+    x = torch.relu(f(b, i)).to(bf)
+    ds_prev = f(b, i)
+    outs = [torch.empty(b, i, dtype=bf, device="cuda") for _ in range(2)] + [torch.empty(i, b, dtype=bf, device="cuda") for _ in range(2)]
+    colsum = torch.empty(2 * i, device="cuda")
+    ws = torch.empty(K.lib.lbbnn_tc_lrt_bwd_input_small_workspace_bytes(b, i), dtype=torch.uint8, device="cuda")
+    K.check(K.lib.lbbnn_tc_lrt_bwd_input_small(K.ptr(g), K.ptr(ds), K.ptr(M), K.ptr(V), b, i, o, K.ptr(x, bf), K.ptr(ds_prev),
+                                               K.FLAG_SAMPLE | (K.FLAG_MASK_DX if mask else 0), *[K.ptr(t, bf) for t in outs],
+                                               K.ptr(colsum), ws.data_ptr(), ws.numel(), K.current_stream()))
+    torch.cuda.synchronize()
+    xd = x.double()
+    dx = g.double() @ M.double() + 2 * xd * ((g.double() * ds.double()) @ V.double())
+    if mask:
+        dx = dx * (xd > 0)
+    dS = dx * ds_prev.double()
+    assert C.rel_err(outs[0].float(), dx) < 5e-3 and C.rel_err(outs[1].float(), dS) < 5e-3        # bf16 output rounding
+    assert torch.equal(outs[0], dx.float().to(bf)) or (outs[0].float() - dx.float().to(bf).float()).abs().max() <= 2 ** -7 * dx.abs().max()
+    assert torch.equal(outs[2], outs[0].T.contiguous()) and torch.equal(outs[3], outs[1].T.contiguous())
+    assert C.rel_err(colsum[:i], dx.sum(0)) < 1e-5 and C.rel_err(colsum[i:], dS.sum(0)) < 1e-5
+    with pytest.raises(K.LbbnnError):
+        K.check(K.lib.lbbnn_tc_lrt_bwd_input_small(K.ptr(g), K.ptr(ds), K.ptr(M), K.ptr(V), b, i, 13, K.ptr(x, bf), K.ptr(ds_prev),
+                                                   0, *[K.ptr(t, bf) for t in outs], None, None, 0, K.current_stream()))
+
+
 def _bf(t):
     return t.to(torch.bfloat16).float()
 
@@ -128,7 +191,7 @@ def emulate_bf16_step(case, num_batches):
             act = torch.relu(a @ Mb.T + layers[i]["bias_mu"] + sd * eps[i])
             ins.append((a, a2)); acts.append(act); dsfs.append(eps[i] / (2 * sd))
             a, a2 = _bf(act), _bf(act * act)
-        xl = acts[-1]                                             # fp32 copy: input of the SIMT dX of the classifier
+        xl = a                                                    # the head's dX reads the bf16 activations its forward consumed
         M, V = MV[-1]
         sd = torch.sqrt(a2 @ _bf(V).T + O.sigma_of(layers[-1]["bias_rho"]) ** 2)   # classifier fwd on bf16 operands
         logits = a @ _bf(M).T + layers[-1]["bias_mu"] + sd * eps[-1]
@@ -140,7 +203,7 @@ def emulate_bf16_step(case, num_batches):
         dMs, dVs, cE, cS = [None] * L, [None] * L, [None] * L, [None] * L
         dS = G * dsf_l
         dMs[-1], dVs[-1], cE[-1], cS[-1] = _bf(G).T @ a, _bf(dS).T @ a2, G.sum(0), dS.sum(0)
-        g = (G @ M + 2 * xl * (dS @ V)) * (xl > 0)                # SIMT fp32 dX, relu-masked
+        g = (G @ M + 2 * xl * (dS @ V)) * (xl > 0)                # CUDA-core fp32 dX (fp32 M, V), relu-masked
         dE, dS = _bf(g), _bf(g * dsfs[T - 1])
         cE[T - 1], cS[T - 1] = g.sum(0), (g * dsfs[T - 1]).sum(0)
         for i in reversed(range(T)):
@@ -201,6 +264,34 @@ def test_tensor_core_trainer_step(use_graph, dims, B):
         for k in p:
             r = p[k].grad.double()
             assert (g[k] - r).norm() / r.norm() < 6e-2, (li, k, "vs fp32 oracle", ((g[k] - r).norm() / r.norm()).item())
+
+
+def test_wide_trainer_fused_prologue_and_head_match_the_separate_passes():
+    """fused_prologue / fused_head_dx (one-pass bf16 prologue; head dX + staging + column sums in one kernel) against the
+    fp32 prologue -> pack and SIMT dX -> pack -> colsum sequence: identical forward (bit-identical bf16 operands), gradients
+    equal up to the head dX reading bf16 instead of fp32 activations."""
+    import lbbnn
+    dims, B = (136, 200, 72, 10), 264
+    case = C.lrt_net_case(seed=92, batch=B, sizes=list(zip(dims[:-1], dims[1:])))
+    outs, grads = [], []
+    for fused in (False, True):
+        net = lbbnn.BayesianNetwork(dims).cuda()
+        with torch.no_grad():
+            for l, p in zip(net.layers, case["layers"]):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=False, inject_noise=True,
+                                        fused_update=False, fused_prologue=fused, fused_head_dx=fused)
+        assert tr.small_dx == [False, False, fused] and tr.simt_dx == [False, False, not fused]
+        for d, e in zip(tr.tc, case["eps"]):
+            d["eps"].copy_(e)
+        outs.append(tr.step(case["x"], case["y"]))
+        grads.append([{k: getattr(l, k).grad.double().clone() for k in case["layers"][0]} for l in net.layers])
+    assert outs[0]["nll"] == outs[1]["nll"]
+    assert abs(outs[0]["kl"] - outs[1]["kl"]) <= 2e-6 * abs(outs[0]["kl"])
+    for li, (a, b) in enumerate(zip(*grads)):
+        for k in a:
+            assert (a[k] - b[k]).norm() / a[k].norm() < 5e-3, (li, k, ((a[k] - b[k]).norm() / a[k].norm()).item())
 
 
 @pytest.mark.parametrize("use_graph", [False, True])
