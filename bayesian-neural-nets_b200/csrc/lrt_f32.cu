@@ -126,6 +126,35 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_prologue(const PrologueArgs 
   }
 }
 
+// ---- cheaper, algebraically identical forms of the per-weight KL terms for the wide (bandwidth-bound) passes -------------
+// log(alpha) = -log1p(e^-lambda), log(1 - alpha) = log(alpha) - lambda, log(alpha / (1 - alpha)) = lambda exactly: one
+// log1p instead of two logs and two divisions, and no 0 * log(0) when alpha rounds to 1.
+struct KlConsts {
+  float log_ps, inv_2ps2, log_pa, log_1mpa, logit_pa;
+};
+__device__ __forceinline__ KlConsts kl_consts(const lbbnn_priors& p) {
+  KlConsts c;
+  c.log_ps = logf(p.sigma);
+  c.inv_2ps2 = 0.5f / (p.sigma * p.sigma);
+  c.log_pa = logf(p.alpha);
+  c.log_1mpa = logf(1.0f - p.alpha);
+  c.logit_pa = c.log_pa - c.log_1mpa;
+  return c;
+}
+// KL of one weight (LRT:189-192) from sigma, alpha, t = e^-lambda
+__device__ __forceinline__ float kl_weight_elem_shared(float mu, float sg, float al, float t, float lam, const lbbnn_priors& p,
+                                                       const KlConsts& c) {
+  const float d = mu - p.mu;
+  const float log_al = -log1pf(t);
+  const float slab = (c.log_ps - logf(sg)) - 0.5f + (log_al - c.log_pa) + (sg * sg + d * d) * c.inv_2ps2;
+  return al * slab + (1.0f - al) * ((log_al - lam) - c.log_1mpa);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // ================================================================================================
 // prologue of the bf16 tensor-core path: M, V as bf16 operands (out,in) AND their (in,out) transposes, plus the KL
 // partial sums, in one pass over mu, rho, lambda (replaces lrt_f32_prologue -> fp32 M, V -> bf16_pack).  64x64 tile per
@@ -152,6 +181,7 @@ __global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16
   __shared__ float red[32];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  const KlConsts kc = kl_consts(a.pri);
   float kl = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -167,11 +197,12 @@ __global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16
       const float lamv[4] = {lam.x, lam.y, lam.z, lam.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float sg = sigma_of(rhov[j]), al = alpha_of(lamv[j]);
+        const float sg = sigma_of(rhov[j]);
+        const float t = expf(-lamv[j]), al = 1.0f / (1.0f + t);          // = alpha_of(lambda)
         const Moments mo = weight_moments(muv[j], sg, al, a.var_mode);
         m[j] = mo.m;
         v[j] = mo.v;
-        if (a.kl_part) kl += kl_weight_elem(muv[j], sg, al, a.pri);
+        if (a.kl_part) kl += kl_weight_elem_shared(muv[j], sg, al, t, lamv[j], a.pri, kc);
       }
       *reinterpret_cast<uint2*>(a.M + e) = pack4_bf16(m);
       *reinterpret_cast<uint2*>(a.V + e) = pack4_bf16(v);
@@ -519,11 +550,14 @@ __device__ __forceinline__ void adam_quad(float* __restrict__ p, float* __restri
   float mv[4], vv[4], po[4];
   loadq(m, e0, n, vec, mv);
   loadq(v, e0, n, vec, vv);
+  const float inv_bc2_sqrt = 1.0f / bc2_sqrt;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     mv[j] = mv[j] + (g[j] - mv[j]) * (1.0f - b1);
     vv[j] = b2 * vv[j] + (1.0f - b2) * g[j] * g[j];
-    po[j] = pv[j] - step_size * (mv[j] / (sqrtf(vv[j]) / bc2_sqrt + eps));
+    // sqrt.approx / fast division: <= 2 ulp on a step of size ~lr, i.e. ~1e-10 of the parameter (adam_kernel keeps the
+    // IEEE forms; tests bound the difference)
+    po[j] = pv[j] - step_size * __fdividef(mv[j], sqrt_approx(vv[j]) * inv_bc2_sqrt + eps);
   }
   storeq(p, e0, n, vec, po, false);
   storeq(m, e0, n, vec, mv, false);
@@ -538,6 +572,7 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
   const float klg = (a.klg_dev ? __ldg(a.klg_dev) : 1.0f) * a.klg_host;
   const lbbnn_priors P = a.pri;
   const float inv_sp2 = 1.0f / (P.sigma * P.sigma);
+  const KlConsts kc = kl_consts(P);
   const int64_t nq = ceil_div(n, 4);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
@@ -551,10 +586,15 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
     for (int j = 0; j < 4; ++j) {
       gm[j] = gr[j] = gl[j] = 0.f;
       if (e0 + j >= n) continue;
-      const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]);
-      const int64_t k = (e0 + j) % a.K;
-      const float zk = a.z ? __ldg(a.z + k) : 1.0f;
-      const float zkl = a.z_kl ? __ldg(a.z_kl + k) : zk;
+      const float er = expf(rho[j]), sg = log1pf(er);                     // = sigma_of(rho); e^rho reused for d sigma / d rho
+      const float al = 1.0f / (1.0f + expf(-lam[j]));                     // = alpha_of(lambda)
+      float zk = 1.0f, zkl = 1.0f;
+      int64_t k = 0;
+      if (a.z || a.z_kl) {                                                // MNF only
+        k = (e0 + j) % a.K;
+        zk = a.z ? __ldg(a.z + k) : 1.0f;
+        zkl = a.z_kl ? __ldg(a.z_kl + k) : zk;
+      }
       const float dMz = dM[j] * zk;
       float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j], dzkl = 0.f;
       if (a.var_mode == LBBNN_VAR_REFERENCE) {
@@ -568,13 +608,13 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
       if (klg != 0.f) {
         const float d = mu[j] * zkl - P.mu;
         dmu += klg * al * d * inv_sp2 * zkl;
-        dsg += klg * al * (sg * inv_sp2 - 1.0f / sg);
-        dal += klg * (logf(P.sigma / sg) - 0.5f + logf(al / P.alpha) + (sg * sg + d * d) * 0.5f * inv_sp2 -
-                      logf((1.0f - al) / (1.0f - P.alpha)));
+        dsg += klg * al * (sg * inv_sp2 - __frcp_rn(sg));
+        // log(ps / sg) - 1/2 + log(al / pa) - log((1 - al) / (1 - pa)) + ...: log(al / (1 - al)) = lambda exactly
+        dal += klg * ((kc.log_ps - logf(sg)) - 0.5f + (lam[j] - kc.logit_pa) + (sg * sg + d * d) * 0.5f * inv_sp2);
         dzkl = klg * al * d * inv_sp2 * mu[j];
       }
       gm[j] = dmu;
-      gr[j] = dsg * dsigma_drho(rho[j]);
+      gr[j] = dsg * (er / (1.0f + er));                                   // d sigma / d rho
       gl[j] = dal * al * (1.0f - al);
       // MNF only; caller zeroes dz / dz_kl first
       if (a.dz_kl) { atomicAdd(a.dz_kl + k, dzkl); if (a.dz) atomicAdd(a.dz + k, dzk); }

@@ -230,6 +230,22 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
   }
 }
 
+// ---- tile order -----------------------------------------------------------------------------------
+// The persistent CTAs walk t = blockIdx.x, +gridDim.x, ...: at any moment the SMs work on ~148 consecutive tile indices.
+// Column-major order (all row blocks of one column block, then the next) makes every wave stream ALL of A: at the wide
+// shape A1 + A2 are 134 MB > L2 and were re-read from HBM for each of the 32 column blocks (~4.3 GB per GEMM).  Tiles are
+// therefore numbered inside groups of kGroupM row blocks: a wave covers a compact (kGroupM x ~9) patch, the group's A rows
+// (32-64 MB) stay in L2 while B streams through once per group.
+constexpr int kGroupM = 16;
+__device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb, int& nb) {
+  const int per_group = kGroupM * num_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int m_first = g * kGroupM;
+  const int gm = min(kGroupM, num_m - m_first);       // ragged last group
+  nb = r / gm;
+  mb = m_first + (r - nb * gm);
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -266,7 +282,9 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % num_m) * BM, n0 = (t / num_m) * BN;
+        int mb, nb;
+        tile_coords(t, num_m, num_n, mb, nb);
+        const int m0 = mb * BM, n0 = nb * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
@@ -316,7 +334,9 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int as = it & 1;
-      const int m0 = (t % num_m) * BM, n0 = (t / num_m) * BN;
+      int mb, nb;
+      tile_coords(t, num_m, num_n, mb, nb);
+      const int m0 = mb * BM, n0 = nb * BN;
       float* sbias = sbias_all + as * 2 * BN;
       if (epi.mode == LBBNN_TC_EPI_FWD) {                 // this tile's bias terms, once per column
         const int c = et & (BN - 1);
