@@ -177,7 +177,9 @@ __device__ __forceinline__ uint2 pack4_bf16(const float v[4]) {
 }
 
 __global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16Args a) {
-  __shared__ float tM[64][65], tV[64][65];
+  // bf16 transpose tiles (17 KB): small enough for these CTAs to share an SM with a resident tc_dual_gemm CTA (~196 KB)
+  // when the trainer issues the prologues on a side stream
+  __shared__ __align__(8) __nv_bfloat16 tM[64][68], tV[64][68];
   __shared__ float red[32];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
@@ -209,8 +211,8 @@ __global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16
       if (a.M32) *reinterpret_cast<float4*>(a.M32 + e) = make_float4(m[0], m[1], m[2], m[3]);
       if (a.V32) *reinterpret_cast<float4*>(a.V32 + e) = make_float4(v[0], v[1], v[2], v[3]);
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { tM[rl][tx * 4 + j] = m[j]; tV[rl][tx * 4 + j] = v[j]; }
+    *reinterpret_cast<uint2*>(&tM[rl][tx * 4]) = pack4_bf16(m);       // same rounding as the row-major stores
+    *reinterpret_cast<uint2*>(&tV[rl][tx * 4]) = pack4_bf16(v);
   }
   if (a.MT) {
     __syncthreads();
@@ -220,17 +222,20 @@ __global__ void __launch_bounds__(kThreads) lrt_bf16_prologue(const PrologueBf16
       const int cl = ty + 16 * i, rl = tx * 4;           // output row = input column c, 4 consecutive r
       const int64_t c = c0 + cl, r = r0 + rl;
       if (c >= a.cols || r >= a.rows) continue;
-      const float m[4] = {tM[rl][cl], tM[rl + 1][cl], tM[rl + 2][cl], tM[rl + 3][cl]};
-      const float v[4] = {tV[rl][cl], tV[rl + 1][cl], tV[rl + 2][cl], tV[rl + 3][cl]};
+      const __nv_bfloat16 m[4] = {tM[rl][cl], tM[rl + 1][cl], tM[rl + 2][cl], tM[rl + 3][cl]};
+      const __nv_bfloat16 v[4] = {tV[rl][cl], tV[rl + 1][cl], tV[rl + 2][cl], tV[rl + 3][cl]};
       if (vec) {
-        *reinterpret_cast<uint2*>(a.MT + c * a.rows + r) = pack4_bf16(m);
-        *reinterpret_cast<uint2*>(a.VT + c * a.rows + r) = pack4_bf16(v);
+        auto bits = [](const __nv_bfloat16 lo, const __nv_bfloat16 hi) {
+          return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+        };
+        *reinterpret_cast<uint2*>(a.MT + c * a.rows + r) = make_uint2(bits(m[0], m[1]), bits(m[2], m[3]));
+        *reinterpret_cast<uint2*>(a.VT + c * a.rows + r) = make_uint2(bits(v[0], v[1]), bits(v[2], v[3]));
       } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (r + j < a.rows) {
-            a.MT[c * a.rows + r + j] = __float2bfloat16_rn(m[j]);
-            a.VT[c * a.rows + r + j] = __float2bfloat16_rn(v[j]);
+            a.MT[c * a.rows + r + j] = m[j];
+            a.VT[c * a.rows + r + j] = v[j];
           }
       }
     }

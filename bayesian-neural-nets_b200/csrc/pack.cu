@@ -39,6 +39,67 @@ __global__ void __launch_bounds__(256) bf16_pack_kernel(const float* __restrict_
   }
 }
 
+// Same job on 64x64 tiles for shapes with cols % 4 == 0: float4 loads, 8-byte bf16 stores in both directions (the
+// transposes go through bf16 shared-memory tiles).  The 32x32 kernel above stays for ragged shapes.
+__device__ __forceinline__ uint2 pack4v(float a, float b, float c, float d) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+  return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+}
+
+__global__ void __launch_bounds__(256) bf16_pack64_kernel(const float* __restrict__ a, const float* __restrict__ b, int op,
+                                                          int64_t rows, int64_t cols, __nv_bfloat16* __restrict__ o1,
+                                                          __nv_bfloat16* __restrict__ o2, __nv_bfloat16* __restrict__ o1T,
+                                                          __nv_bfloat16* __restrict__ o2T) {
+  __shared__ __align__(8) __nv_bfloat16 t1[64][68], t2[64][68];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rl = ty + 16 * i;
+    const int64_t r = r0 + rl, c = c0 + tx * 4;
+    uint2 p1 = make_uint2(0u, 0u), p2 = make_uint2(0u, 0u);
+    if (r < rows && c < cols) {
+      const int64_t e = r * cols + c;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(a + e));
+      float4 w;
+      if (op == LBBNN_PACK_SQUARE) {
+        w = make_float4(v.x * v.x, v.y * v.y, v.z * v.z, v.w * v.w);
+      } else {
+        w = __ldg(reinterpret_cast<const float4*>(b + e));
+        if (op == LBBNN_PACK_SCALE) { w.x *= v.x; w.y *= v.y; w.z *= v.z; w.w *= v.w; }
+      }
+      p1 = pack4v(v.x, v.y, v.z, v.w);
+      p2 = pack4v(w.x, w.y, w.z, w.w);
+      if (o1) *reinterpret_cast<uint2*>(o1 + e) = p1;
+      if (o2) *reinterpret_cast<uint2*>(o2 + e) = p2;
+    }
+    *reinterpret_cast<uint2*>(&t1[rl][tx * 4]) = p1;
+    *reinterpret_cast<uint2*>(&t2[rl][tx * 4]) = p2;
+  }
+  if (o1T == nullptr) return;
+  __syncthreads();
+  const bool vec = (rows % 4 == 0);
+  auto bits = [](const __nv_bfloat16 lo, const __nv_bfloat16 hi) {
+    return (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+  };
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = ty + 16 * i, rl = tx * 4;
+    const int64_t c = c0 + cl, r = r0 + rl;
+    if (c >= cols || r >= rows) continue;
+    const __nv_bfloat16 u[4] = {t1[rl][cl], t1[rl + 1][cl], t1[rl + 2][cl], t1[rl + 3][cl]};
+    const __nv_bfloat16 w[4] = {t2[rl][cl], t2[rl + 1][cl], t2[rl + 2][cl], t2[rl + 3][cl]};
+    if (vec) {
+      *reinterpret_cast<uint2*>(o1T + c * rows + r) = make_uint2(bits(u[0], u[1]), bits(u[2], u[3]));
+      *reinterpret_cast<uint2*>(o2T + c * rows + r) = make_uint2(bits(w[0], w[1]), bits(w[2], w[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r + j < rows) { o1T[c * rows + r + j] = u[j]; o2T[c * rows + r + j] = w[j]; }
+    }
+  }
+}
+
 // column sums in two deterministic stages: stage 1 = grid (cols/32, S row slices), each block sums its
 // slice with 8 row-lanes per column and a fixed-order smem reduction -> partial[s][2][cols];
 // stage 2 sums the S partials in order.
@@ -107,12 +168,26 @@ __device__ __forceinline__ uint2 pack4(const float v[4]) {
   return make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
 }
 
-__global__ void __launch_bounds__(256) lrt_bwd_input_small_kernel(const BwdSmallArgs a) {
+__global__ void __launch_bounds__(256, 3) lrt_bwd_input_small_kernel(const BwdSmallArgs a) {
   __shared__ float tE[64][65], tS[64][65];
   __shared__ __align__(16) float sM[kSmallMaxOut][64], sV[kSmallMaxOut][64];
   __shared__ float sG[64][kSmallMaxOut + 1], sGS[64][kSmallMaxOut + 1];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int64_t c0 = (int64_t)blockIdx.x * 64, r0 = (int64_t)blockIdx.y * 64;
+  // this thread's x and ds_prev quads (4 rows): issued first so that HBM latency hides behind the shared-memory fill and the
+  // contraction below
+  uint2 xq[4];
+  float4 fq[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 16 * i, c = c0 + tx * 4;
+    xq[i] = make_uint2(0u, 0u);
+    fq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < a.B && c < a.K) {
+      xq[i] = __ldg(reinterpret_cast<const uint2*>(a.x + r * a.K + c));
+      if (a.ds_prev) fq[i] = __ldg(reinterpret_cast<const float4*>(a.ds_prev + r * a.K + c));
+    }
+  }
   for (int e = tid; e < a.O * 64; e += 256) {
     const int o = e >> 6, c = e & 63;
     const bool ok = c0 + c < a.K;
@@ -127,30 +202,39 @@ __global__ void __launch_bounds__(256) lrt_bwd_input_small_kernel(const BwdSmall
     sGS[rl][o] = r < a.B ? gv * __ldg(a.ds + r * a.O + o) : 0.f;
   }
   __syncthreads();
+  // the two contractions over the layer's few outputs for this thread's 4 rows x 4 columns: M, V quads read once per
+  // output, the rows' g, gS are warp-wide broadcasts
+  float e1[4][4], e2[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) e1[i][j] = e2[i][j] = 0.f;
+  for (int o = 0; o < a.O; ++o) {
+    const float4 m = *reinterpret_cast<const float4*>(&sM[o][tx * 4]);
+    const float4 v = *reinterpret_cast<const float4*>(&sV[o][tx * 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float gv = sG[ty + 16 * i][o], gs = sGS[ty + 16 * i][o];
+      e1[i][0] = fmaf(gv, m.x, e1[i][0]); e1[i][1] = fmaf(gv, m.y, e1[i][1]);
+      e1[i][2] = fmaf(gv, m.z, e1[i][2]); e1[i][3] = fmaf(gv, m.w, e1[i][3]);
+      e2[i][0] = fmaf(gs, v.x, e2[i][0]); e2[i][1] = fmaf(gs, v.y, e2[i][1]);
+      e2[i][2] = fmaf(gs, v.z, e2[i][2]); e2[i][3] = fmaf(gs, v.w, e2[i][3]);
+    }
+  }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int rl = ty + 16 * i;
     const int64_t r = r0 + rl, c = c0 + tx * 4;
     float dE[4] = {0.f, 0.f, 0.f, 0.f}, dS[4] = {0.f, 0.f, 0.f, 0.f};
     if (r < a.B && c < a.K) {                  // K % 4 == 0: whole quad inside the row
-      float e1[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int o = 0; o < a.O; ++o) {
-        const float4 m = *reinterpret_cast<const float4*>(&sM[o][tx * 4]);
-        const float4 v = *reinterpret_cast<const float4*>(&sV[o][tx * 4]);
-        const float gv = sG[rl][o], gs = sGS[rl][o];
-        e1[0] = fmaf(gv, m.x, e1[0]); e1[1] = fmaf(gv, m.y, e1[1]); e1[2] = fmaf(gv, m.z, e1[2]); e1[3] = fmaf(gv, m.w, e1[3]);
-        e2[0] = fmaf(gs, v.x, e2[0]); e2[1] = fmaf(gs, v.y, e2[1]); e2[2] = fmaf(gs, v.z, e2[2]); e2[3] = fmaf(gs, v.w, e2[3]);
-      }
       const int64_t e = r * a.K + c;
-      const uint2 xu = __ldg(reinterpret_cast<const uint2*>(a.x + e));
-      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.x));
-      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xu.y));
+      const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xq[i].x));
+      const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xq[i].y));
       const float xv[4] = {x01.x, x01.y, x23.x, x23.y};
-      const float4 f4 = a.ds_prev ? __ldg(reinterpret_cast<const float4*>(a.ds_prev + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const float fv[4] = {f4.x, f4.y, f4.z, f4.w};
+      const float fv[4] = {fq[i].x, fq[i].y, fq[i].z, fq[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float gx = fmaf(2.0f * xv[j], e2[j], e1[j]);
+        float gx = fmaf(2.0f * xv[j], e2[i][j], e1[i][j]);
         if (a.mask && !(xv[j] > 0.f)) gx = 0.f;
         dE[j] = gx;
         dS[j] = gx * fv[j];
@@ -211,6 +295,14 @@ extern "C" int lbbnn_bf16_pack(const float* a, const float* b, int op, int64_t r
   LBBNN_REQUIRE(a && rows > 0 && cols > 0, "bad input");
   LBBNN_REQUIRE(op == LBBNN_PACK_SQUARE || b, "second operand required");
   LBBNN_REQUIRE((out1T == nullptr) == (out2T == nullptr), "transposed outputs come in pairs");
+  auto al = [](const void* p, uintptr_t m) { return (reinterpret_cast<uintptr_t>(p) & m) == 0; };
+  if (cols % 4 == 0 && al(a, 15) && al(b, 15) && al(out1, 7) && al(out2, 7) && al(out1T, 7) && al(out2T, 7) &&
+      ceil_div(rows, 64) <= 65535) {
+    dim3 grid64((unsigned)ceil_div(cols, 64), (unsigned)ceil_div(rows, 64));
+    bf16_pack64_kernel<<<grid64, 256, 0, (cudaStream_t)s>>>(a, b, op, rows, cols, (__nv_bfloat16*)out1, (__nv_bfloat16*)out2,
+                                                           (__nv_bfloat16*)out1T, (__nv_bfloat16*)out2T);
+    return check_launch("bf16_pack64");
+  }
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
   LBBNN_REQUIRE(grid.y <= 65535, "too many rows for one launch (%lld)", (long long)rows);
   bf16_pack_kernel<<<grid, 256, 0, (cudaStream_t)s>>>(a, b, op, rows, cols, (__nv_bfloat16*)out1, (__nv_bfloat16*)out2,

@@ -369,11 +369,12 @@ class LRTTensorCoreTrainer:
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
                  use_graph=True, inject_noise=False, process_group=None, fused_update=True, fused_prologue=True,
-                 fused_head_dx=True):
+                 fused_head_dx=True, overlap=True):
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
         self.fused_prologue = bool(fused_prologue)
+        self.overlap = bool(overlap)
         L = len(self.layers)
         for l in self.layers:
             if l.in_features % 8:
@@ -428,7 +429,13 @@ class LRTTensorCoreTrainer:
         self.dM, self.dV = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)       # dW GEMM out, reused
         self.fused_update = bool(fused_update)
         self.param_off = {(id(l), name): off for l, name, off, n, shape in offs}
-        self.comm_stream = torch.cuda.Stream(device=dev) if (self.fused_update and self.world > 1) else None
+        # side stream: the per-layer update (all-reduce +) chain rule + Adam pass runs there while the main stream goes on
+        # with the backward GEMMs, and the next step's prologues (parameters -> bf16 operands + KL) run there ahead of the
+        # forward GEMMs that consume them.  Those kernels are bandwidth-bound, have small CTAs (<= 17 KB of shared memory) and
+        # fit on an SM next to the resident tensor-core GEMM CTA.
+        self.comm_stream = (torch.cuda.Stream(device=dev)
+                            if (self.fused_update and (self.world > 1 or self.overlap)) else None)
+        self.side_prologue = self.fused_prologue and self.overlap and self.comm_stream is not None
         self.tc = []
         for li, (i, o) in enumerate(sizes):
             last = li == L - 1
@@ -447,6 +454,7 @@ class LRTTensorCoreTrainer:
                 dE=torch.zeros(B, o, **bf), dS=torch.zeros(B, o, **bf),
                 dET=torch.zeros(o, B, **bf), dST=torch.zeros(o, B, **bf),
                 colsum=torch.zeros(2 * o, **f32),
+                klws=torch.empty(max(256, int(K.lib.lbbnn_lrt_bf16_prologue_workspace_bytes(i, o))), dtype=torch.uint8, device=dev),
                 eps=torch.zeros(B, o, **f32) if inject_noise else None)
             if self.fused_update:      # [dM | dV | colsum]: what a data-parallel step all-reduces for this layer
                 d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
@@ -485,6 +493,26 @@ class LRTTensorCoreTrainer:
         K.check(lib.lbbnn_bf16_pack(P(self.x), None, K.PACK_SQUARE, B, self.sizes[0][0], P(self.x_bf, bf),
                                     P(self.x2_bf, bf), P(self.xT_bf, bf), P(self.x2T_bf, bf), st)); n += 1
         a, a2 = self.x_bf, self.x2_bf
+        main = torch.cuda.current_stream()
+
+        def fused_prologue(i, stream):     # mu, rho, lambda -> bf16 M, V (+ transposes) + KL in one pass
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            keep = d["mv32"] is not None
+            M32 = d["mv32"] if keep else None
+            V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:] if keep else None
+            K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf),
+                                                P(d["MT"], bf, True), P(d["VT"], bf, True), P(M32, True), P(V32, True),
+                                                self.stats[1 + i:].data_ptr(), d["klws"].data_ptr(), d["klws"].numel(), stream))
+
+        ready = [None] * L
+        if self.side_prologue:             # all prologues up front on the side stream; each forward GEMM waits for its own
+            self.comm_stream.wait_stream(main)
+            with torch.cuda.stream(self.comm_stream):
+                for i in range(L):
+                    fused_prologue(i, K.current_stream()); n += 2
+                    ready[i] = torch.cuda.Event()
+                    ready[i].record(self.comm_stream)
         for i in range(L):
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
@@ -494,11 +522,10 @@ class LRTTensorCoreTrainer:
                 V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
             else:
                 M32, V32 = self.M32, self.V32
-            if self.fused_prologue:    # mu, rho, lambda -> bf16 M, V (+ transposes) + KL in one pass
-                keep = d["mv32"] is not None
-                K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf),
-                                                    P(d["MT"], bf, True), P(d["VT"], bf, True), P(M32) if keep else None,
-                                                    P(V32) if keep else None, self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
+            if self.side_prologue:
+                main.wait_event(ready[i])
+            elif self.fused_prologue:
+                fused_prologue(i, st); n += 2
             else:
                 K.check(lib.lbbnn_lrt_f32_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, K.FLAG_SAMPLE, P(M32), P(V32),
                                                    self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
@@ -523,7 +550,6 @@ class LRTTensorCoreTrainer:
         if self.fused_update:
             K.check(lib.lbbnn_adam_prepare(P(self.step_dev, torch.int64), self.lr, self.betas[0], self.betas[1],
                                            P(self.adam_coef), st)); n += 1
-        main = torch.cuda.current_stream()
         for i in reversed(range(L)):
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
@@ -598,7 +624,8 @@ class LRTTensorCoreTrainer:
             return
         self.comm_stream.wait_stream(main)
         with torch.cuda.stream(self.comm_stream):
-            torch.distributed.all_reduce(d["raw"], group=self.pg)
+            if self.pg is not None:
+                torch.distributed.all_reduce(d["raw"], group=self.pg)
             K.check(K.lib.lbbnn_lrt_f32_finalize_adam(desc, K.ptr(dM), K.ptr(dV), K.ptr(d["colsum"]), l.cfg.priors,
                                                       l.cfg.var_mode, K.FLAG_SAMPLE, None, klg, self._adam_state(l),
                                                       K.current_stream()))

@@ -443,9 +443,17 @@ def run_ours(args):
             top = max(prof, key=lambda r: r["us"])
             ach = top["flops"] / (top["us"] * 1e-6) / 1e12
             step_flops = sum(2 * 2.0 * B * i * o * (3 if li > 0 else 2) for li, (i, o) in enumerate(zip(sizes[:-1], sizes[1:])))
+            traffic, traffic_note = None, None
+            prof_path = os.path.join(ROOT, "profiles", "r01_ncu_tc_dual_gemm.json")
+            if os.path.exists(prof_path) and "tc_lrt_fwd" in top["name"]:      # DRAM bytes of the ncu capture of this call
+                nc = json.load(open(prof_path))["launches"][0]
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                traffic = sum(float(nc[k]["value"]) * scale[nc[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+                traffic_note = ("dram__bytes_read + dram__bytes_write of one ncu --set full capture of this call "
+                                "(profiles/r01_ncu_tc_dual_gemm.json): 0.27 GB of unique operands + 0.54 GB of outputs")
             roof = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                    "us_per_launch": top["us"], "flops_per_launch": top["flops"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_note": traffic_note,
+                    "peak_source": peaks["source"], "us_per_launch": top["us"], "flops_per_launch": top["flops"],
                     "timing": "kernel alone, operands larger than L2, CUDA events, mean of 5; burst peak"}
             step_roof = {"flops_per_step": step_flops, "achieved_tflops": step_flops / (ms / args.steps * 1e-3) / 1e12,
                          "frac_of_sustained_peak": step_flops / (ms / args.steps * 1e-3) / 1e12 / (peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"])}

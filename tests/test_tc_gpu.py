@@ -39,12 +39,17 @@ def test_raw_dual_gemm_matches_torch(K, m, n, k):
 
 def test_pack_and_colsum(K):
     rng = np.random.default_rng(3)
+    for rows, cols in ((70, 45), (128, 72), (66, 200), (264, 136)):      # ragged (32x32 kernel) and cols % 4 == 0 (64x64 kernel)
+        a = torch.from_numpy(rng.standard_normal(size=(rows, cols)).astype(np.float32)).cuda()
+        b = torch.from_numpy(rng.standard_normal(size=(rows, cols)).astype(np.float32)).cuda()
+        for op, second in ((K.PACK_PAIR, b), (K.PACK_SQUARE, a * a), (K.PACK_SCALE, a * b)):
+            o1, o2, o1t, o2t = K.bf16_pack(a, b, op)
+            assert torch.equal(o1, a.to(torch.bfloat16)) and torch.equal(o2, second.to(torch.bfloat16))
+            assert torch.equal(o1t, o1.T.contiguous()) and torch.equal(o2t, o2.T.contiguous())
+            p1, p2, _, _ = K.bf16_pack(a, b, op, transposed=False)
+            assert torch.equal(p1, o1) and torch.equal(p2, o2)
     a = torch.from_numpy(rng.standard_normal(size=(70, 45)).astype(np.float32)).cuda()
     b = torch.from_numpy(rng.standard_normal(size=(70, 45)).astype(np.float32)).cuda()
-    for op, second in ((K.PACK_PAIR, b), (K.PACK_SQUARE, a * a), (K.PACK_SCALE, a * b)):
-        o1, o2, o1t, o2t = K.bf16_pack(a, b, op)
-        assert torch.equal(o1, a.to(torch.bfloat16)) and torch.equal(o2, second.to(torch.bfloat16))
-        assert torch.equal(o1t, o1.T.contiguous()) and torch.equal(o2t, o2.T.contiguous())
     out = torch.empty(2 * 45, device="cuda")
     ws = torch.empty(K.lib.lbbnn_colsum2_workspace_bytes(70, 45), dtype=torch.uint8, device="cuda")
     K.check(K.lib.lbbnn_colsum2(K.ptr(a), K.ptr(b), 0, 70, 45, K.ptr(out), ws.data_ptr(), ws.numel(), K.current_stream()))
