@@ -19,6 +19,8 @@
 // (D1: 128 cols, D2: 128 cols), so the epilogue of tile i overlaps the main loop of tile i+1.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -374,6 +376,176 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
   }
 }
 
+// ---- the CTA-pair kernel ------------------------------------------------------------------------------
+// Same GEMM pair on 256 x 128 tiles owned by a cluster of two CTAs (one TPC): each CTA stages ITS 128 rows of A1, A2 and
+// HALF (64 rows) of the B1, B2 tiles; the leader's tcgen05.mma.cta_group::2 (M = 256, N = 128) reads both halves, so a stage
+// is 48 KB per SM instead of 64 KB for the same MMA work (25 % less L2 -> SM operand traffic, what the 1-CTA kernel waits
+// on: tensor pipe 54-60 % active in profiles/r01_ncu_tc_dual_gemm.json) and FOUR stages fit.  Each CTA keeps its 128 rows
+// of both accumulators in its own TMEM (2 stages x 256 columns) and runs the unchanged epilogue on them.
+//   full barrier   (leader's): 2 arrivals (each CTA's producer, with its own expect_tx) + the bytes of both CTAs' loads
+//   empty barrier  (per CTA):  the leader's tcgen05.commit multicast to both CTAs frees the stage in both
+//   tmem full      (per CTA):  commit multicast after the tile's last MMA
+//   tmem empty     (leader's): 2 x kEpiWarps arrivals, the peer's epilogue warps arrive remotely
+constexpr int kStages2 = 4;
+constexpr int kBHalfBytes = (BN / 2) * BK * 2;                 // 8 KB: this CTA's 64 rows of a B tile
+constexpr int kStageBytes2 = 2 * kTileBytes + 2 * kBHalfBytes;  // 48 KB
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kBiasBytes;
+constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+constexpr int kGroupM2 = kGroupM / 2;                          // in 256-row blocks
+
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kIdesc2), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int& mb2, int& nb) {
+  const int per_group = kGroupM2 * num_n;
+  const int g = t / per_group, r = t - g * per_group;
+  const int m_first = g * kGroupM2;
+  const int gm = min(kGroupM2, num_m2 - m_first);
+  nb = r / gm;
+  mb2 = m_first + (r - nb * gm);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                       const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
+                       int M, int N, int K) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
+  uint64_t* full_bar = bars;                       // [kStages2]  (the leader's is the live one)
+  uint64_t* empty_bar = bars + kStages2;           // [kStages2]
+  uint64_t* tfull_bar = bars + 2 * kStages2;       // [2]
+  uint64_t* tempty_bar = bars + 2 * kStages2 + 2;  // [2]         (the leader's is the live one)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages2 + 4);
+  float* sbias_all = reinterpret_cast<float*>(smem + kStages2 * kStageBytes2 + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int num_m2 = (M + 2 * BM - 1) / (2 * BM), num_n = (N + BN - 1) / BN;
+  const int num_tiles = num_m2 * num_n, num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2);
+    for (int s = 0; s < kStages2; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tfull_bar[s], 1); mbar_init(&tempty_bar[s], 2 * kEpiWarps); }
+    fence_barrier_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_pair(tmem_holder, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own A rows, own half of the B rows; bytes credited to the leader's full barrier =====
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        int mb2, nb;
+        tile_coords2(t, num_m2, num_n, mb2, nb);
+        const int m0 = mb2 * 2 * BM + (int)rank * BM, n0h = nb * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * kStageBytes2;
+          const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
+          mbar_expect_tx_cluster(lead_full, kStageBytes2);
+          tma_load_2d_pair(sa, &tmA1, lead_full, kb * BK, m0);
+          tma_load_2d_pair(sa + kTileBytes, &tmA2, lead_full, kb * BK, m0);
+          tma_load_2d_pair(sa + 2 * kTileBytes, &tmB1, lead_full, kb * BK, n0h);
+          tma_load_2d_pair(sa + 2 * kTileBytes + kBHalfBytes, &tmB2, lead_full, kb * BK, n0h);
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (leader CTA only) =====
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0; int it = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+        const int as = it & 1;
+        mbar_wait_cluster(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d1 = tmem_base + as * 256, d2 = d1 + 128;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait_cluster(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
+          const uint64_t a1 = umma_desc_kmajor_sw128(sa), a2 = umma_desc_kmajor_sw128(sa + kTileBytes);
+          const uint64_t b1 = umma_desc_kmajor_sw128(sa + 2 * kTileBytes);
+          const uint64_t b2 = umma_desc_kmajor_sw128(sa + 2 * kTileBytes + kBHalfBytes);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+            const uint32_t acc = (kb | k) ? 1u : 0u;
+            umma_bf16_pair(d1, a1 + koff, b1 + koff, acc);
+            umma_bf16_pair(d2, a2 + koff, b2 + koff, acc);
+          }
+          umma_commit_pair(&empty_bar[stage], 3);          // frees this stage in BOTH CTAs once the MMAs retire
+          if (++stage == kStages2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[as], 3);               // accumulators complete -> both epilogues
+      }
+    }
+  } else {
+    // ===== epilogue warps (both CTAs, each on its own 128 accumulator rows) =====
+    Noise nz = epi.noise;
+    nz.resolve();
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int et = threadIdx.x - 64;
+    int it = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
+      const int as = it & 1;
+      int mb2, nb;
+      tile_coords2(t, num_m2, num_n, mb2, nb);
+      const int m0 = mb2 * 2 * BM + (int)rank * BM, n0 = nb * BN;
+      float* sbias = sbias_all + as * 2 * BN;
+      if (epi.mode == LBBNN_TC_EPI_FWD) {
+        const int c = et & (BN - 1);
+        const int64_t n = n0 + c;
+        float v = 0.f;
+        if (n < N) {
+          if (et < BN) v = __ldg(epi.bias_mu + n);
+          else { const float sb = sigma_of(__ldg(epi.bias_rho + n)); v = sb * sb; }
+        }
+        sbias[(et < BN ? 0 : BN) + c] = v;
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      }
+      mbar_wait_cluster(&tfull_bar[as], (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t row = m0 + q * 32 + lane;
+      const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
+#pragma unroll 1
+      for (int c = 0; c < 64 / EW; ++c) {
+        float v1[EW], v2[EW];
+        tmem_ld16(tbase + c * EW, v1);
+        tmem_ld16(tbase + 128 + c * EW, v2);
+        const int cl = half * 64 + c * EW;
+        epilogue_chunk(epi, nz, M, N, row, n0 + cl, sbias, cl, v1, v2);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+    }
+  }
+  __syncwarp();                 // warps 0 and 1 ran single-lane loops: reconverge before the aligned cluster barrier
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
+}
+
 // ---- host: tensor maps --------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -392,14 +564,14 @@ EncodeTiledFn get_encode() {
 }
 
 // (rows, K) row-major bf16, box = 64 (K) x 128 (rows), 128B swizzle, OOB -> zeros
-int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K) {
+int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box_rows = BM) {
   EncodeTiledFn enc = get_encode();
   LBBNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
   LBBNN_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (K * 2) % 16 == 0,
                 "TMA operand must be 16B aligned with a 16B-multiple row pitch (K %% 8 == 0), K=%lld", (long long)K);
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -415,6 +587,23 @@ int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, in
   CUtensorMap mA1, mA2, mB1, mB2;
   if (int rc = make_map(&mA1, A1, M, K)) return rc;
   if (int rc = make_map(&mA2, A2, M, K)) return rc;
+  // CTA pairs (256-row tiles) for problems that fill the GPU with them; LBBNN_TC_PAIR=0 forces the 1-CTA kernel
+  // (2 = also for small problems: the tests use it to run odd shapes through the pair kernel; read per call, host only)
+  const char* pe = getenv("LBBNN_TC_PAIR");
+  const int pair_mode = pe ? atoi(pe) : 1;
+  const int64_t tiles2 = ceil_div(M, 2 * BM) * ceil_div(N, BN);
+  if (pair_mode && M > BM && (pair_mode == 2 || tiles2 >= sm_count() / 2)) {
+    if (int rc = make_map(&mB1, B1, N, K, BN / 2)) return rc;
+    if (int rc = make_map(&mB2, B2, N, K, BN / 2)) return rc;
+    static bool attr2_set = false;
+    if (!attr2_set) {
+      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
+      attr2_set = true;
+    }
+    const int clusters = (int)(tiles2 < sm_count() / 2 ? tiles2 : sm_count() / 2);
+    tc_dual_gemm_bf16_pair<<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K);
+    return check_launch("tc_dual_gemm_bf16_pair");
+  }
   if (int rc = make_map(&mB1, B1, N, K)) return rc;
   if (int rc = make_map(&mB2, B2, N, K)) return rc;
   static bool attr_set = false;

@@ -24,8 +24,8 @@ def _rand_bf16(rng, *shape, scale=1.0):
 
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 64), (128, 128, 256), (256, 384, 512), (100, 72, 200), (1000, 136, 1096),
-                                   (4096, 512, 1024)])
-def test_raw_dual_gemm_matches_torch(K, m, n, k):
+                                   (4096, 512, 1024), (2560, 1024, 320), (8192, 1280, 128)])
+def test_raw_dual_gemm_matches_torch(K, tc_mode, m, n, k):
     rng = np.random.default_rng(m * 7 + n * 3 + k)
     a1, a2 = _rand_bf16(rng, m, k), _rand_bf16(rng, m, k)
     b1, b2 = _rand_bf16(rng, n, k), _rand_bf16(rng, n, k)
@@ -35,6 +35,19 @@ def test_raw_dual_gemm_matches_torch(K, m, n, k):
     r2 = a2.float() @ b2.float().T
     assert C.rel_err(d1, r1) < 1e-4
     assert C.rel_err(d2, r2) < 1e-4
+
+
+@pytest.fixture(params=["1cta", "pair"])
+def tc_mode(request):
+    """Run a GEMM test on the 1-CTA kernel and, forced (LBBNN_TC_PAIR=2), on the CTA-pair (cta_group::2) kernel."""
+    import os
+    old = os.environ.get("LBBNN_TC_PAIR")
+    os.environ["LBBNN_TC_PAIR"] = "0" if request.param == "1cta" else "2"
+    yield request.param
+    if old is None:
+        os.environ.pop("LBBNN_TC_PAIR", None)
+    else:
+        os.environ["LBBNN_TC_PAIR"] = old
 
 
 def test_pack_and_colsum(K):
@@ -57,7 +70,7 @@ def test_pack_and_colsum(K):
 
 
 @pytest.mark.parametrize("b,i,o,relu", [(256, 128, 256, True), (200, 136, 72, False)])
-def test_tc_lrt_fwd_epilogue(K, b, i, o, relu):
+def test_tc_lrt_fwd_epilogue(K, tc_mode, b, i, o, relu):
     rng = np.random.default_rng(b + i + o)
     x = torch.from_numpy(rng.random((b, i), dtype=np.float32)).cuda()
     m = torch.from_numpy((rng.standard_normal((o, i)) * 0.1).astype(np.float32)).cuda()
@@ -91,7 +104,7 @@ def test_tc_lrt_fwd_epilogue(K, b, i, o, relu):
     assert (actf - full).norm() / full.norm() < 2e-2
 
 
-def test_tc_lrt_bwd_input_epilogue(K):
+def test_tc_lrt_bwd_input_epilogue(K, tc_mode):
     b, i, o = 256, 192, 128
     rng = np.random.default_rng(9)
     bf = torch.bfloat16
