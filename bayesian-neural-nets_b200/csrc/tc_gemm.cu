@@ -455,7 +455,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
         tile_coords2(t, num_m2, num_n, mb2, nb);
         const int m0 = mb2 * 2 * BM + (int)rank * BM, n0h = nb * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_cluster(&empty_bar[stage], phase ^ 1);
+          mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes2;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
           mbar_expect_tx_cluster(lead_full, kStageBytes2);
@@ -473,11 +473,11 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       int stage = 0; uint32_t phase = 0; int it = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int as = it & 1;
-        mbar_wait_cluster(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this accumulator stage
+        mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this accumulator stage
         tc_fence_after();
         const uint32_t d1 = tmem_base + as * 256, d2 = d1 + 128;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait_cluster(&full_bar[stage], phase);
+          mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
           const uint64_t a1 = umma_desc_kmajor_sw128(sa), a2 = umma_desc_kmajor_sw128(sa + kTileBytes);
@@ -520,7 +520,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
         sbias[(et < BN ? 0 : BN) + c] = v;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
-      mbar_wait_cluster(&tfull_bar[as], (it >> 1) & 1);
+      mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;

@@ -118,27 +118,15 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes)
                : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait on a barrier of this CTA that CTAs of the cluster (or their async operations) arrive on
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
+// (Barrier waits keep the default CTA-scope acquire and remote arrives the default CTA-scope release, as CUTLASS'
+// ClusterBarrier does: with .cluster scope ptxas brackets every arrive with MEMBAR.ALL.GPU and every successful wait with
+// CCTL.IVALL, which serialised the producer behind its own TMA loads -- ncu: tensor pipe 31 % active.)
 // tile load whose completion bytes are credited to an mbarrier of the pair's leader (cute::SM100_TMA_2SM_LOAD_2D)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c_inner,
                                                  int c_outer) {
