@@ -364,7 +364,7 @@ def test_tf32_split_is_exact(K):
 
 @pytest.mark.parametrize("z,m,n,k,relu", [(1, 128, 128, 32, False), (1, 1000, 400, 784, True), (3, 100, 72, 200, False),
                                           (5, 37, 600, 400, True), (2, 300, 10, 40, False), (1, 256, 1200, 64, True)])
-def test_tc_linear_tf32x3_matches_fp64(K, z, m, n, k, relu):
+def test_tc_linear_tf32x3_matches_fp64(K, tc_mode, z, m, n, k, relu):
     rng = np.random.default_rng(z * 1000 + m + n + k)
     a = torch.from_numpy(rng.random((z, m, k), dtype=np.float32)).cuda()
     w = torch.from_numpy((rng.standard_normal((z, n, k)) * 0.1).astype(np.float32)).cuda()
@@ -385,7 +385,7 @@ def test_tc_linear_tf32x3_matches_fp64(K, z, m, n, k, relu):
     assert int((oh.view(torch.int32) & 0x1FFF).abs().max()) == 0
 
 
-def test_tc_linear_tf32x3_shared_input_and_strided_chain(K):
+def test_tc_linear_tf32x3_shared_input_and_strided_chain(K, tc_mode):
     """The layout the MC loop uses: layer 1 = ONE problem over all samples' weights, its (batch, S*out) hi/lo output read
     by layer 2 as a strided batch."""
     rng = np.random.default_rng(5)
