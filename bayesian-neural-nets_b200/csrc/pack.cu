@@ -2,6 +2,8 @@
 // column sums over the batch that feed the bias gradients.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace lbbnn {
 namespace {
 
@@ -280,6 +282,178 @@ __global__ void __launch_bounds__(256, 3) lrt_bwd_input_small_kernel(const BwdSm
   }
 }
 
+// ---- rows-by-few dual dot products on the CUDA cores -------------------------------------------------------------------
+//   s1[r][o] = sum_c big1[r][c] small1[o][c]      s2[r][o] = sum_c big2[r][c] small2[o][c]        o < O <= 12
+// The classifier head at the wide shape (out = 10) as a GEMM on 128-wide tensor-core tiles is 64 (forward) or 32 (dW) CTAs
+// each streaming megabytes of activations: 81 + 69 us for 1.3 GFLOP.  Here every SM streams rows: the small matrices sit in
+// shared memory as bf16 (chunks of the contraction), each warp takes two rows per pass, lanes stride over the contraction
+// with 16-byte loads, fp32 accumulation, a butterfly reduction, and lane o applies the epilogue of output o.
+// Measured (r01): 138 / 136 us -- the 160 KB shared-memory fill per CTA and 8 warps per SM (227 registers) leave too few
+// bytes in flight -- so the trainer keeps the tensor-core calls by default (LRTTensorCoreTrainer(small_head=True) selects
+// these); an mma.sync formulation with the outputs padded to 16 would make it bandwidth-bound (~30 us).
+//   FWD : big = (x, x^2) (batch, in), small = (M, V) (out, in): act = s1 + b_mu + sqrt(s2 + sigma_b^2) eps, ds = eps / (2 sd)
+//   RAWT: big = (x^T, x^2^T) (in, batch), small = (dE^T, dS^T) (out, batch): dM[o][r] = s1, dV[o][r] = s2   (fp32, (out, in))
+constexpr int kSkinnyMaxO = 12;
+constexpr int kSkinnyThreads = 256;
+
+struct SkinnyArgs {
+  const __nv_bfloat16 *big1, *big2, *small1, *small2;
+  int64_t R, C;
+  int O, chunk, mode;                  // chunk: contraction elements per shared-memory fill (multiple of 256)
+  // FWD
+  const float *bias_mu, *bias_rho;
+  Noise noise;
+  int relu;
+  float *act, *ds;
+  // RAWT
+  float *d1, *d2;
+};
+enum { SKINNY_FWD = 0, SKINNY_RAWT = 1 };
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4 u, float f[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+template <int O>
+__device__ __forceinline__ void skinny_rows(const SkinnyArgs& a, const __nv_bfloat16* s1, const __nv_bfloat16* s2, int64_t c0,
+                                            int clen, bool first_chunk, bool last_chunk, const Noise& nz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_g = (int64_t)blockIdx.x * (kSkinnyThreads / 32) + (threadIdx.x >> 5);
+  const int64_t warps = (int64_t)gridDim.x * (kSkinnyThreads / 32);
+  for (int64_t r = warp_g * 2; r < a.R; r += warps * 2) {
+    const bool two = r + 1 < a.R;
+    float acc[2][2][O];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int o = 0; o < O; ++o) acc[i][0][o] = acc[i][1][o] = 0.f;
+    const __nv_bfloat16* p1 = a.big1 + r * a.C + c0;
+    const __nv_bfloat16* p2 = a.big2 + r * a.C + c0;
+    for (int k = lane * 8; k < clen; k += 256) {
+      float x[2][2][8];
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p1 + k)), x[0][0]);
+      bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p2 + k)), x[0][1]);
+      if (two) {
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p1 + a.C + k)), x[1][0]);
+        bf16x8_to_f32(__ldg(reinterpret_cast<const uint4*>(p2 + a.C + k)), x[1][1]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[1][0][j] = x[1][1][j] = 0.f;
+      }
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        float m[8], v[8];
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(s1 + (int64_t)o * a.chunk + k), m);
+        bf16x8_to_f32(*reinterpret_cast<const uint4*>(s2 + (int64_t)o * a.chunk + k), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][0][o] = fmaf(x[0][0][j], m[j], acc[0][0][o]);
+          acc[0][1][o] = fmaf(x[0][1][j], v[j], acc[0][1][o]);
+          acc[1][0][o] = fmaf(x[1][0][j], m[j], acc[1][0][o]);
+          acc[1][1][o] = fmaf(x[1][1][j], v[j], acc[1][1][o]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int w = 0; w < 2; ++w)
+#pragma unroll
+        for (int o = 0; o < O; ++o) acc[i][w][o] = warp_sum(acc[i][w][o]);
+    // lane (i * 16 + o) finishes output o of row r + i
+    const int i = lane >> 4, ol = lane & 15;
+    float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+    for (int o = 0; o < O; ++o)
+      if (ol == o) { t1 = i ? acc[1][0][o] : acc[0][0][o]; t2 = i ? acc[1][1][o] : acc[0][1][o]; }
+    const int64_t row = r + i;
+    if (ol < O && row < a.R) {
+      if (a.mode == SKINNY_RAWT) {
+        float* q1 = a.d1 + (int64_t)ol * a.R + row;
+        float* q2 = a.d2 + (int64_t)ol * a.R + row;
+        *q1 = first_chunk ? t1 : *q1 + t1;        // chunks of the contraction are added in order by the same thread
+        *q2 = first_chunk ? t2 : *q2 + t2;
+      } else if (last_chunk) {                    // FWD runs as a single chunk (checked on the host)
+        const float sb = sigma_of(__ldg(a.bias_rho + ol));
+        const int64_t idx = row * O + ol;
+        const float ep = nz.ptr ? __ldg(nz.ptr + idx) : philox_normal1(nz.seed, nz.stream, (uint64_t)idx);
+        const float sd = sqrtf(fmaxf(t2, 0.f) + sb * sb);
+        float v = t1 + __ldg(a.bias_mu + ol) + sd * ep;
+        if (a.relu) v = fmaxf(v, 0.f);
+        a.act[idx] = v;
+        if (a.ds) a.ds[idx] = ep / (2.0f * sd);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSkinnyThreads, 1) skinny_dual_kernel(const SkinnyArgs a) {
+  extern __shared__ __align__(16) uint8_t skinny_smem[];
+  __nv_bfloat16* s1 = reinterpret_cast<__nv_bfloat16*>(skinny_smem);
+  __nv_bfloat16* s2 = s1 + (int64_t)a.O * a.chunk;
+  Noise nz = a.noise;
+  nz.resolve();
+  for (int64_t c0 = 0; c0 < a.C; c0 += a.chunk) {
+    const int clen = (int)min((int64_t)a.chunk, a.C - c0);
+    if (c0) __syncthreads();
+    for (int e = threadIdx.x * 8; e < a.O * a.chunk; e += kSkinnyThreads * 8) {
+      const int o = e / a.chunk, k = e - o * a.chunk;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u), w = u;
+      if (k < clen) {
+        u = __ldg(reinterpret_cast<const uint4*>(a.small1 + (int64_t)o * a.C + c0 + k));
+        w = __ldg(reinterpret_cast<const uint4*>(a.small2 + (int64_t)o * a.C + c0 + k));
+      }
+      *reinterpret_cast<uint4*>(s1 + e) = u;
+      *reinterpret_cast<uint4*>(s2 + e) = w;
+    }
+    __syncthreads();
+    const bool first = c0 == 0, last = c0 + a.chunk >= a.C;
+    switch (a.O) {
+      case 1: skinny_rows<1>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 2: skinny_rows<2>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 3: skinny_rows<3>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 4: skinny_rows<4>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 5: skinny_rows<5>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 6: skinny_rows<6>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 7: skinny_rows<7>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 8: skinny_rows<8>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 9: skinny_rows<9>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 10: skinny_rows<10>(a, s1, s2, c0, clen, first, last, nz); break;
+      case 11: skinny_rows<11>(a, s1, s2, c0, clen, first, last, nz); break;
+      default: skinny_rows<12>(a, s1, s2, c0, clen, first, last, nz); break;
+    }
+  }
+}
+
+int launch_skinny(SkinnyArgs a, cudaStream_t st, const char* what) {
+  LBBNN_REQUIRE(a.O >= 1 && a.O <= kSkinnyMaxO, "%s: 1 <= out <= %d (got %d)", what, kSkinnyMaxO, a.O);
+  LBBNN_REQUIRE(a.C % 8 == 0, "%s: contraction length must be a multiple of 8 (got %lld)", what, (long long)a.C);
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  LBBNN_REQUIRE(al(a.big1) && al(a.big2) && al(a.small1) && al(a.small2), "%s: operands must be 16-byte aligned", what);
+  // the contraction in as few shared-memory fills as fit ~192 KB: 2 matrices x O rows x chunk x 2 B
+  const int64_t cap = (192 * 1024) / (4 * (int64_t)a.O) / 256 * 256;
+  int64_t chunks = ceil_div(a.C, cap);
+  int64_t chunk = ceil_div(ceil_div(a.C, chunks), 256) * 256;
+  LBBNN_REQUIRE(a.mode == SKINNY_RAWT || chunks == 1, "%s: in_features %lld x out %d does not fit one shared-memory fill", what,
+                (long long)a.C, a.O);
+  a.chunk = (int)chunk;
+  const size_t smem = (size_t)4 * a.O * chunk;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    LBBNN_CUDA(cudaFuncSetAttribute(skinny_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    smem_set = 200 * 1024;
+  }
+  const int64_t passes = ceil_div(a.R, 2 * (kSkinnyThreads / 32));
+  const int grid = (int)std::min<int64_t>(sm_count(), std::max<int64_t>(1, passes));
+  skinny_dual_kernel<<<grid, kSkinnyThreads, smem, st>>>(a);
+  return check_launch(what);
+}
+
 int colsum_slices(int64_t rows) {
   int64_t s = rows / 128;
   return (int)(s < 1 ? 1 : (s > 64 ? 64 : s));
@@ -362,4 +536,29 @@ extern "C" int lbbnn_tc_lrt_bwd_input_small(const float* gact, const float* ds_f
     return check_launch("colsum2_stage2");
   }
   return 0;
+}
+
+extern "C" int lbbnn_tc_lrt_fwd_small(const void* x_bf, const void* x2_bf, const void* M_bf, const void* V_bf, int64_t batch,
+                                      int64_t in_features, int64_t out_features, const float* bias_mu, const float* bias_rho,
+                                      const lbbnn_noise* nz, int flags, float* act_f32, float* ds_factor, lbbnn_stream s) {
+  LBBNN_REQUIRE(x_bf && x2_bf && M_bf && V_bf && bias_mu && bias_rho && act_f32 && nz, "NULL argument");
+  LBBNN_REQUIRE(batch > 0 && in_features > 0, "empty shape");
+  SkinnyArgs a = {};
+  a.big1 = (const __nv_bfloat16*)x_bf; a.big2 = (const __nv_bfloat16*)x2_bf;
+  a.small1 = (const __nv_bfloat16*)M_bf; a.small2 = (const __nv_bfloat16*)V_bf;
+  a.R = batch; a.C = in_features; a.O = (int)out_features; a.mode = SKINNY_FWD;
+  a.bias_mu = bias_mu; a.bias_rho = bias_rho; a.noise = make_noise(nz); a.relu = (flags & LBBNN_FLAG_RELU) ? 1 : 0;
+  a.act = act_f32; a.ds = ds_factor;
+  return launch_skinny(a, (cudaStream_t)s, "tc_lrt_fwd_small");
+}
+
+extern "C" int lbbnn_tc_dual_gemm_raw_small(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N,
+                                            int64_t K, float* D1, float* D2, lbbnn_stream s) {
+  // D1 (M, N) = A1 (M, K) B1 (N, K)^T with M <= 12 rows: the rows of B are the streamed side
+  LBBNN_REQUIRE(A1 && A2 && B1 && B2 && D1 && D2 && N > 0 && K > 0, "NULL argument");
+  SkinnyArgs a = {};
+  a.big1 = (const __nv_bfloat16*)B1; a.big2 = (const __nv_bfloat16*)B2;
+  a.small1 = (const __nv_bfloat16*)A1; a.small2 = (const __nv_bfloat16*)A2;
+  a.R = N; a.C = K; a.O = (int)M; a.mode = SKINNY_RAWT; a.d1 = D1; a.d2 = D2;
+  return launch_skinny(a, (cudaStream_t)s, "tc_dual_gemm_raw_small");
 }

@@ -369,12 +369,16 @@ class LRTTensorCoreTrainer:
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
                  use_graph=True, inject_noise=False, process_group=None, fused_update=True, fused_prologue=True,
-                 fused_head_dx=True, overlap=True):
+                 fused_head_dx=True, overlap=True, small_head=False):
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
         self.fused_prologue = bool(fused_prologue)
         self.overlap = bool(overlap)
+        # <= 12-output layers: forward (if last) and dW on the CUDA-core row-streaming kernels instead of 128-wide tensor-core
+        # tiles.  Off by default: measured 138 / 136 us against 81 / 69 us at the wide shape (shared-memory fill and too few
+        # bytes in flight per SM); kept as a tested alternative for heads whose in_features break the TMA pitch.
+        self.small_head = bool(small_head)
         L = len(self.layers)
         for l in self.layers:
             if l.in_features % 8:
@@ -531,11 +535,16 @@ class LRTTensorCoreTrainer:
                                                    self.stats[1 + i:].data_ptr(), ws, wsn, st)); n += 2
                 K.check(lib.lbbnn_bf16_pack(P(M32), P(V32), K.PACK_PAIR, fo, fi, P(d["M"], bf), P(d["V"], bf),
                                             P(d["MT"], bf, True), P(d["VT"], bf, True), st)); n += 1
-            K.check(lib.lbbnn_tc_lrt_fwd(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data),
-                                         P(l.bias_rho.data), self._noise(i),
-                                         K.FLAG_SAMPLE | (0 if last else K.FLAG_RELU),
-                                         P(d["act"], bf, True), P(d["act2"], bf, True), P(d["actT"], bf, True),
-                                         P(d["act2T"], bf, True), P(d["dsf"]), P(d["act32"], allow_none=True), st)); n += 1
+            if self.small_head and last and fo <= 12 and fi * fo * 4 <= 192 * 1024:
+                K.check(lib.lbbnn_tc_lrt_fwd_small(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
+                                                   P(l.bias_mu.data), P(l.bias_rho.data), self._noise(i), K.FLAG_SAMPLE,
+                                                   P(d["act32"]), P(d["dsf"]), st)); n += 1
+            else:
+                K.check(lib.lbbnn_tc_lrt_fwd(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data),
+                                             P(l.bias_rho.data), self._noise(i),
+                                             K.FLAG_SAMPLE | (0 if last else K.FLAG_RELU),
+                                             P(d["act"], bf, True), P(d["act2"], bf, True), P(d["actT"], bf, True),
+                                             P(d["act2T"], bf, True), P(d["dsf"]), P(d["act32"], allow_none=True), st)); n += 1
             a, a2 = d["act"], d["act2"]
         dl = self.tc[-1]
         K.check(lib.lbbnn_logsoftmax_nll_f32(P(dl["act32"]), P(self.y, torch.int64), B, self.sizes[-1][1], None,
@@ -565,8 +574,8 @@ class LRTTensorCoreTrainer:
                 dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
             else:
                 dM, dV = self.dM, self.dV
-            K.check(lib.lbbnn_tc_dual_gemm_raw(P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B,
-                                               P(dM), P(dV), st)); n += 1
+            raw_gemm = lib.lbbnn_tc_dual_gemm_raw_small if (self.small_head and fo <= 12) else lib.lbbnn_tc_dual_gemm_raw
+            K.check(raw_gemm(P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B, P(dM), P(dV), st)); n += 1
             if self.fused_update:
                 self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
             else:

@@ -196,6 +196,16 @@ LBBNN_API int lbbnn_tc_lrt_bwd_input_small(const float* gact, const float* ds_fa
                                            const float* ds_prev, int flags, void* dE_bf, void* dS_bf, void* dET_bf,
                                            void* dST_bf, float* colsum, void* workspace, size_t workspace_bytes,
                                            lbbnn_stream s);
+/* The same forward and dW GEMM pairs for a layer with out_features <= 12 (the classifier head) on the CUDA cores: every SM
+ * streams rows of the large operand against the few rows of the small one held in shared memory (bf16 operands, fp32
+ * accumulation, like the tensor-core calls they replace).  fwd_small writes the fp32 activations (logits) and ds_factor;
+ * it needs in_features * out_features * 4 B <= 192 KB.  raw_small: D1 (M, N) = A1 (M, K) B1 (N, K)^T, D2 likewise, M <= 12,
+ * K % 8 == 0 -- lbbnn_tc_dual_gemm_raw's contract for dM = dE^T x, dV = dS^T x^2 of that layer. */
+LBBNN_API int lbbnn_tc_lrt_fwd_small(const void* x_bf, const void* x2_bf, const void* M_bf, const void* V_bf, int64_t batch,
+                                     int64_t in_features, int64_t out_features, const float* bias_mu, const float* bias_rho,
+                                     const lbbnn_noise* noise, int flags, float* act_f32, float* ds_factor, lbbnn_stream s);
+LBBNN_API int lbbnn_tc_dual_gemm_raw_small(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N,
+                                           int64_t K, float* D1, float* D2, lbbnn_stream s);
 LBBNN_API size_t lbbnn_colsum2_workspace_bytes(int64_t rows, int64_t cols);
 LBBNN_API int lbbnn_colsum2(const void* a, const void* b, int a_is_bf16, int64_t rows, int64_t cols,
                             float* out, void* workspace, size_t workspace_bytes, lbbnn_stream s);
