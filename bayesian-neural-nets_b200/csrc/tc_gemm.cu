@@ -404,11 +404,11 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, 
       : "memory");
 }
 
-__device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int& mb2, int& nb) {
-  const int per_group = kGroupM2 * num_n;
+__device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int group, int& mb2, int& nb) {
+  const int per_group = group * num_n;
   const int g = t / per_group, r = t - g * per_group;
-  const int m_first = g * kGroupM2;
-  const int gm = min(kGroupM2, num_m2 - m_first);
+  const int m_first = g * group;
+  const int gm = min(group, num_m2 - m_first);
   nb = r / gm;
   mb2 = m_first + (r - nb * gm);
 }
@@ -416,7 +416,7 @@ __device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int& 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
-                       int M, int N, int K) {
+                       int M, int N, int K, int group) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages2 * kStageBytes2);
@@ -452,7 +452,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       int stage = 0; uint32_t phase = 0;
       for (int t = cluster_id; t < num_tiles; t += num_clusters) {
         int mb2, nb;
-        tile_coords2(t, num_m2, num_n, mb2, nb);
+        tile_coords2(t, num_m2, num_n, group, mb2, nb);
         const int m0 = mb2 * 2 * BM + (int)rank * BM, n0h = nb * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -506,7 +506,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
     for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
       const int as = it & 1;
       int mb2, nb;
-      tile_coords2(t, num_m2, num_n, mb2, nb);
+      tile_coords2(t, num_m2, num_n, group, mb2, nb);
       const int m0 = mb2 * 2 * BM + (int)rank * BM, n0 = nb * BN;
       float* sbias = sbias_all + as * 2 * BN;
       if (epi.mode == LBBNN_TC_EPI_FWD) {
@@ -601,7 +601,9 @@ int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, in
       attr2_set = true;
     }
     const int clusters = (int)(tiles2 < sm_count() / 2 ? tiles2 : sm_count() / 2);
-    tc_dual_gemm_bf16_pair<<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K);
+    const char* ge = getenv("LBBNN_TC_GROUP");      // 256-row blocks per tile group (experiments)
+    const int group = ge && atoi(ge) > 0 ? atoi(ge) : kGroupM2;
+    tc_dual_gemm_bf16_pair<<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K, group);
     return check_launch("tc_dual_gemm_bf16_pair");
   }
   if (int rc = make_map(&mB1, B1, N, K)) return rc;
