@@ -64,6 +64,27 @@ def test_host_only_queries_work_without_a_gpu(lib_path):
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_size_queries_of_the_wide_and_variational_dropout_paths(lib_path):
+    """Host-only size / launch-count queries added with the bf16 prologue, the fused head kernel and the variational-dropout
+    layer: consistent with the shapes they describe, and usable without a GPU."""
+    from lbbnn import _capi as K
+    lib = K.lib
+    # KL partials of the one-pass bf16 prologue: one double per 64x64 tile
+    assert lib.lbbnn_lrt_bf16_prologue_workspace_bytes(4096, 4096) >= 64 * 64 * 8
+    assert lib.lbbnn_lrt_bf16_prologue_workspace_bytes(0, 10) == 0
+    # column-sum partials of the fused head input gradient: [ceil(batch / 64)][2][in] floats
+    assert lib.lbbnn_tc_lrt_bwd_input_small_workspace_bytes(8192, 4096) == 128 * 2 * 4096 * 4
+    assert lib.lbbnn_tc_lrt_bwd_input_small_workspace_bytes(65, 8) == 2 * 2 * 8 * 4
+    # variational dropout: [gE | gS] staging + the split-contraction partials of the largest GEMM
+    for b, n, m in ((100, 784, 1200), (100, 1200, 10), (1, 8, 8), (1000, 400, 72)):
+        assert lib.lbbnn_vd_workspace_bytes(b, n, m) >= 2 * b * m * 4
+        for shape in ((b, m, n), (n, m, b), (b, n, m)):
+            assert lib.lbbnn_vd_gemm_launches(*shape) in (1, 2)
+    assert lib.lbbnn_vd_gemm_launches(100, 1200, 1200) == 2       # batch-100 forward: contraction split over gridDim.z
+    assert lib.lbbnn_vd_gemm_launches(1200, 1200, 100) == 1       # d theta: enough tiles, epilogue fused
+    assert lib.lbbnn_vd_gemm_launches(0, 5, 5) == 0
+
+
 def test_compute_fails_loudly_without_a_gpu():
     import lbbnn
     layer = lbbnn.BayesianLinear(8, 4)
