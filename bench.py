@@ -549,6 +549,16 @@ def cpu_reference_mc(budget_s=15.0, max_samples=64):
                       f"of the MF 784-400-600-10 net, oracle port on torch-CPU fp32, {cores} threads"}
 
 
+def _mc_traffic():
+    """DRAM bytes of one layer-1 launch from the ncu capture in profiles/ (1-CTA kernel; same operands and outputs)."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_tc_linear_tf32x3.json")
+    try:
+        l1 = json.load(open(path))["layer1"]
+        return (l1["dram_read_MB"] + l1["dram_write_MB"]) * 1e6
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def mc_config(world):
     return {"workload": f"mf_mc_predict: MF MLP 784-400-600-10 posterior-predictive averaging, {MC_SAMPLES} MC weight samples "
                         f"x {MC_BATCH}-input batch per step, gamma.exact=True",
@@ -695,7 +705,7 @@ def run_mc(args):
                 "input_samples_per_sec": MC_SAMPLES * MC_BATCH * args.steps / (ms * 1e-3),
                 "roofline": {"bound": "tensor", "kernel": gname,
                              "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                             "traffic": None, "peak_source": peaks["source"], "us_per_launch": us_g,
+                             "traffic": _mc_traffic() if tc else None, "peak_source": peaks["source"], "us_per_launch": us_g,
                              "flops_per_launch": gflop * 1e9,
                              "timing": "kernel alone, cold L2 (256 MB memset before each launch), CUDA events, mean of 6",
                              "note": note},

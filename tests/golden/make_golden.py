@@ -345,8 +345,47 @@ def golden_vd():
     np.savez_compressed(os.path.join(HERE, "vd.npz"), **out)
 
 
+def golden_vd_train():
+    """Two iterations of the training branch of run_epoch (VD:160-166) on the reference BNN with the script's optimizer,
+    torch.optim.AdamW(model.parameters(), lr=1e-4) (VD:110): pins what the optimizer sees -- `alpha` is NOT among
+    model.parameters() (VD:61 builds it as a non-leaf tensor), so only theta moves -- and the AdamW defaults."""
+    class _DS:
+        def __init__(self, n):
+            self.dataset = range(n)
+    ns = H.load_reference_classes("variational_dropout.py", functions=("loss_fn",), device="cpu",
+                                  config={"batch_size": 100}, train_loader=_DS(60000), val_loader=_DS(10000))
+    BNN, loss_fn = ns["BNN"], ns["loss_fn"]
+    case = C.vd_net_case(seed=87, batch=100)
+    net = BNN()
+    for lay, p in zip((net.l1, net.l2, net.l3, net.l4), case["layers"]):
+        with torch.no_grad():
+            lay.theta.copy_(p["theta"])
+    assert [n for n, _ in net.named_parameters()] == ["l1.theta", "l2.theta", "l3.theta", "l4.theta"]
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4)
+    rng = np.random.default_rng(870)
+    out = {"n_steps": np.int64(2)}
+    net.train()
+    for step in range(2):
+        zetas = [C.t(rng.standard_normal(size=tuple(z.shape))) for z in case["zetas"]]
+        net.zero_grad()
+        with H.replay(H.NoiseQueue([("normal", z) for z in zetas])):
+            pred = net(case["x"])
+        loss = loss_fn(pred, case["y"], net)
+        loss.backward()
+        opt.step()
+        out[f"loss_{step}"] = np.float64(loss.item())
+    for li, lay in enumerate((net.l1, net.l2, net.l3, net.l4)):
+        for k, v in C.grad_digest(lay.theta.detach()).items():
+            out[f"theta_l{li}_{k}"] = v
+        out[f"alpha_l{li}"] = lay.alpha.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "vd_train.npz"), **out)
+    print("vd_train golden written; losses", out["loss_0"], out["loss_1"])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("vd_train", "all"):
+        golden_vd_train()
     if what in ("vd", "all"):
         golden_vd()
     if what in ("lrt", "all"):

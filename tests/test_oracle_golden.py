@@ -229,3 +229,26 @@ def test_vd_net_matches_reference():
         assert C.rel_err(d["sample"], g[f"net_l{li}_theta_sample"]) < 5e-6, li
         assert abs(d["l2"] - float(g[f"net_l{li}_theta_l2"])) / float(g[f"net_l{li}_theta_l2"]) < 5e-6, li
         assert C.rel_err(p["alpha"].grad, g[f"net_l{li}_d_alpha"]) < 5e-6, li
+
+
+def test_vd_training_steps_match_reference():
+    """Two run_epoch training iterations (VD:160-166) with the script's AdamW(model.parameters(), lr=1e-4): the oracle's
+    loss + torch AdamW over theta ONLY (alpha is not a registered parameter of the reference, VD:61) reproduces the reference's
+    losses and parameters; alpha stays 0.2."""
+    g = _npz("vd_train.npz")
+    case = C.vd_net_case(seed=87, batch=100)
+    layers = [{k: v.clone().requires_grad_(k == "theta") for k, v in p.items()} for p in case["layers"]]
+    opt = torch.optim.AdamW([p["theta"] for p in layers], lr=1e-4)
+    rng = np.random.default_rng(870)
+    for step in range(int(g["n_steps"])):
+        zetas = [C.t(rng.standard_normal(size=tuple(z.shape))) for z in case["zetas"]]
+        opt.zero_grad()
+        loss = O.vd_net_loss(case["x"], case["y"], layers, zetas, 600.0)[0]
+        loss.backward()
+        opt.step()
+        assert abs(loss.item() - float(g[f"loss_{step}"])) / abs(float(g[f"loss_{step}"])) < TOL, step
+    for li, p in enumerate(layers):
+        d = C.grad_digest(p["theta"].detach())
+        assert C.rel_err(d["sample"], g[f"theta_l{li}_sample"]) < 5e-6, li
+        assert abs(d["l2"] - float(g[f"theta_l{li}_l2"])) / float(g[f"theta_l{li}_l2"]) < 5e-6, li
+        assert np.array_equal(g[f"alpha_l{li}"], np.full_like(g[f"alpha_l{li}"], 0.2)), li

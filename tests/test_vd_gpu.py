@@ -174,3 +174,26 @@ def test_trainer_native_noise_changes_every_replay_and_ensemble_runs(vd):
     assert a != b and tr.step_dev.item() == 2
     pred = vd.predict_ensemble(net, case["x"].cuda(), samples=4)
     assert pred.shape == (100, 10) and torch.isfinite(pred).all()
+
+
+def test_trainer_follows_the_reference_training_steps(vd):
+    """VDTrainer against tests/golden/vd_train.npz = two run_epoch training iterations of the reference itself (its BNN, loss_fn
+    and AdamW(model.parameters(), lr=1e-4), zeta replayed): the losses of both steps (the second one sees the updated theta)
+    and the updated theta; alpha is left alone, as in the reference."""
+    g = np.load(os.path.join(C.GOLDEN, "vd_train.npz"))
+    case = C.vd_net_case(seed=87, batch=100)
+    net = _load_net(vd, case)
+    tr = vd.VDTrainer(net, batch_size=100, num_batches=600.0, lr=1e-4, use_graph=True, inject_noise=True)
+    rng = np.random.default_rng(870)
+    for step in range(int(g["n_steps"])):
+        for b, z in zip(tr.buf, case["zetas"]):
+            b["zeta"].copy_(C.t(rng.standard_normal(size=tuple(z.shape))))
+        out = tr.step(case["x"], case["y"])
+        assert abs(out["loss"] - float(g[f"loss_{step}"])) / abs(float(g[f"loss_{step}"])) < 1e-4, step
+    for li, l in enumerate(net.layers):
+        d = C.grad_digest(l.theta.detach().cpu())
+        # AdamW's first steps are ~lr * sign(g): an element whose gradient is at rounding level may move the other way, so
+        # the digest is held to a fraction of one step (lr = 1e-4 against |theta| <= 0.1), not to fp32 rounding
+        assert np.abs(d["sample"] - g[f"theta_l{li}_sample"]).max() < 2.5e-4, li
+        assert abs(d["l2"] - float(g[f"theta_l{li}_l2"])) / float(g[f"theta_l{li}_l2"]) < 1e-5, li
+        assert torch.equal(l.alpha.cpu(), torch.from_numpy(g[f"alpha_l{li}"])), li
