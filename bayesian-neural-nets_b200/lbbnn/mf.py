@@ -627,6 +627,57 @@ class MCPredictor:
                 "entropy": -(probs * torch.log(probs)).sum(1)}
 
 
+# ---- ensemble / sparsity statistics of the driver loops, on the parameters' device -------------------
+# The reference computes these with a device -> host NumPy round trip per MC sample (MF:376-396, 427-433, 612-637).  They
+# are plain reductions over the inclusion probabilities and Bernoulli masks, so they stay torch expressions here (no
+# custom kernel: nothing on the hot path), run wherever the parameters live and touch the host once, at the end.
+def refresh_inclusion(net):
+    """alpha = 1 / (1 + exp(-lambdal)) for every layer and its `.gamma`, and `.gamma.exact = True` -- what the driver does
+    before `test_ensemble` (MF:612-625)."""
+    with torch.no_grad():
+        for l in net.layers:
+            l.alpha = 1 / (1 + torch.exp(-l.lambdal.detach()))
+            l.gamma.alpha = l.alpha
+            l.gamma.exact = True
+    return net
+
+
+def median_probability_masks(net):
+    """The median-probability model: one {0, 1} float mask [alpha > 0.5] per layer (the g1..g3 of `outofsample(medimod=True)`,
+    MF:462-465)."""
+    return [(l.alpha.detach() > 0.5).to(l.alpha.dtype) for l in net.layers]
+
+
+def median_probability_density(net):
+    """Fraction of weights whose inclusion probability exceeds 0.5 (`os`, MF:634-637), as a 0-dim tensor on the device."""
+    tot = sum(l.alpha.numel() for l in net.layers)
+    return sum((l.alpha.detach() > 0.5).sum() for l in net.layers).to(torch.float64) / tot
+
+
+def mask_statistics(net, samples, draws=None):
+    """`spars / ctr`, `ps` and `np.mean(density)` of `test_ensemble` (MF:376-396, 427-433) for one test batch: per MC sample
+    the reference draws one set of masks for the sparsity / ever-active counters and ANOTHER set for `density` (the
+    forward uses a third).  draws[i] = (masks_a, masks_b) injects them (lists of per-layer tensors); None = Bernoulli(alpha)
+    on the device.  Returns 0-dim float64 device tensors {"sparsity", "ever_active", "density"}; `ever_active` is the
+    reference's `ps` without its hard-coded division by the 10 test batches."""
+    layers = list(net.layers)
+    tot = sum(l.alpha.numel() for l in layers)
+    dev = layers[0].alpha.device
+    spars = torch.zeros((), dtype=torch.float64, device=dev)
+    dens = torch.zeros((), dtype=torch.float64, device=dev)
+    ever = [torch.zeros_like(l.alpha, dtype=torch.bool) for l in layers]
+    with torch.no_grad():
+        for i in range(samples):
+            ga = draws[i][0] if draws is not None else [torch.bernoulli(l.alpha) for l in layers]
+            gb = draws[i][1] if draws is not None else [torch.bernoulli(l.alpha) for l in layers]
+            on = [g > 0.5 for g in ga]
+            spars += sum(o.sum() for o in on).to(torch.float64) / tot
+            ever = [e | o for e, o in zip(ever, on)]
+            dens += torch.cat([g.flatten() for g in gb]).mean().to(torch.float64)
+    return {"sparsity": spars / samples, "ever_active": sum(e.sum() for e in ever).to(torch.float64) / tot,
+            "density": dens / samples}
+
+
 class _null_ctx:
     def __enter__(self):
         return self
