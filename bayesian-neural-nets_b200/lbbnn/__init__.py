@@ -3,10 +3,10 @@ LarsELund/Bayesian-Neural-Nets.  Python host code over the C-ABI of liblbbnn.so 
 CUDA only: importing this package without the built library raises."""
 from . import _capi
 from ._capi import LbbnnError, philox_normal, philox_uniform
-from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed
+from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manual_seed, predict_ensemble
 from . import flows, mf, mnf
 from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer, MultiTensorAdam
 from . import vd
 
 __all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "MultiTensorAdam", "lrt_linear",
-           "manual_seed", "mf", "mnf", "flows", "vd", "philox_normal", "philox_uniform"]
+           "manual_seed", "predict_ensemble", "mf", "mnf", "flows", "vd", "philox_normal", "philox_uniform"]

@@ -233,3 +233,43 @@ class BayesianNetwork(nn.Module):
 
     def kl(self):
         return sum(l.kl for l in self.layers)
+
+
+def predict_ensemble(net, x, samples, ensemble_first=10, forward=None):
+    """The per-batch body of `test_ensemble` for the LRT / MNF networks (LRT:239-265, MNF:287-318) without its device ->
+    host NumPy round trip per MC sample: `samples` stochastic forwards `net(x, sample=True)`, accumulating on the device
+
+      * mean_prob  = mean over samples of the row-normalised expit of the log-probabilities (`mydata_means`, LRT:249-258),
+      * ensemble   = argmax of the mean of the FIRST `ensemble_first` outputs (`outputs[0:10].mean(0)`, LRT:262-263),
+      * posterior_mean = argmax of `net(x, sample=False)` (LRT:264-265),
+      * density    = mean over samples of one Bernoulli(alpha_q) draw per layer (LRT:242-246), when the layers expose
+                     `.gamma.rsample()`; None otherwise.
+
+    Sums are kept in fp64 so the argmax does not depend on how the samples are split over calls.  `forward(x, sample)`
+    overrides the call (the MNF network draws its own z inside)."""
+    call = forward if forward is not None else (lambda inp, sample: net(inp, sample=sample))
+    layers = list(getattr(net, "layers", []))
+    has_gamma = bool(layers) and all(hasattr(l, "gamma") and hasattr(l.gamma, "rsample") for l in layers)
+    was_training = net.training if hasattr(net, "training") else False
+    if hasattr(net, "eval"):
+        net.eval()
+    sum_prob = sum_first = None
+    dens = None
+    with torch.no_grad():
+        for i in range(samples):
+            if has_gamma:
+                d = torch.cat([l.gamma.rsample().flatten() for l in layers]).mean().to(torch.float64)
+                dens = d if dens is None else dens + d
+            out = call(x, True).to(torch.float64)
+            p = torch.sigmoid(out)
+            p = p / p.sum(dim=1, keepdim=True)
+            sum_prob = p if sum_prob is None else sum_prob + p
+            if i < ensemble_first:
+                sum_first = out if sum_first is None else sum_first + out
+        mean_out = call(x, False)
+    if was_training and hasattr(net, "train"):
+        net.train()
+    n_first = min(samples, ensemble_first)
+    mean_prob = sum_prob / samples
+    return {"mean_prob": mean_prob, "ensemble": (sum_first / n_first).argmax(1), "posterior_mean": mean_out.argmax(1),
+            "entropy": -(mean_prob * torch.log(mean_prob)).sum(1), "density": None if dens is None else dens / samples}

@@ -56,3 +56,42 @@ def test_mask_statistics_follow_the_reference_counters():
     mean_alpha = sum(l.alpha.sum().item() for l in net.layers) / tot
     assert abs(nat["sparsity"].item() - mean_alpha) < 0.02 and abs(nat["density"].item() - mean_alpha) < 0.02
     assert nat["ever_active"].item() >= nat["sparsity"].item()
+
+
+def test_lrt_predict_ensemble_follows_the_reference_loop():
+    """lbbnn.lrt.predict_ensemble against the reference's test_ensemble body (LRT:239-265) restated with NumPy, on a stub
+    stochastic network (the helper is plain torch around `net(x, sample=...)`; the lbbnn layers themselves are CUDA-only)."""
+    import lbbnn
+    from scipy.special import expit
+
+    class Stub(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            g = torch.Generator().manual_seed(1)
+            self.w = torch.randn(12, 5, generator=g)
+            self.noise = [torch.randn(7, 5, generator=g) * 0.7 for _ in range(14)]
+            self.calls = 0
+
+        def forward(self, x, sample=False):
+            z = x @ self.w
+            if sample:
+                z = z + self.noise[self.calls]
+                self.calls += 1
+            return torch.log_softmax(z, dim=1)
+
+    x = torch.randn(7, 12, generator=torch.Generator().manual_seed(2))
+    S = 14
+    got = lbbnn.lrt.predict_ensemble(Stub(), x, S)
+    ref = Stub()
+    outputs = np.stack([ref(x, sample=True).numpy() for _ in range(S)])
+    means = np.zeros((7, 5))
+    for i in range(S):                                            # LRT:249-258
+        tmp = expit(outputs[i].astype(np.float64))
+        tmp /= tmp.sum(1, keepdims=True)
+        means += tmp
+    means /= S
+    assert np.allclose(got["mean_prob"].numpy(), means, atol=1e-7)
+    assert np.array_equal(got["ensemble"].numpy(), outputs[0:10].mean(0).argmax(1))          # LRT:262-263
+    assert np.array_equal(got["posterior_mean"].numpy(), ref(x, sample=False).numpy().argmax(1))
+    assert np.allclose(got["entropy"].numpy(), -(means * np.log(means)).sum(1), atol=1e-7)     # outofsample, MF:487-490
+    assert got["density"] is None
