@@ -63,7 +63,6 @@ def test_host_only_queries_work_without_a_gpu(lib_path):
     assert K.lib.lbbnn_lrt_step_workspace_bytes(st) == 0 and b"batch" in K.lib.lbbnn_last_error()
 
 
-@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_size_queries_of_the_wide_and_variational_dropout_paths(lib_path):
     """Host-only size / launch-count queries added with the bf16 prologue, the fused head kernel and the variational-dropout
     layer: consistent with the shapes they describe, and usable without a GPU."""
@@ -85,6 +84,7 @@ def test_size_queries_of_the_wide_and_variational_dropout_paths(lib_path):
     assert lib.lbbnn_vd_gemm_launches(0, 5, 5) == 0
 
 
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_compute_fails_loudly_without_a_gpu():
     import lbbnn
     layer = lbbnn.BayesianLinear(8, 4)
