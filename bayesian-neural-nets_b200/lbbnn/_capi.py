@@ -204,15 +204,20 @@ def check(rc):
 
 
 def ptr(t, dtype=torch.float32, allow_none=False):
-    if isinstance(dtype, bool):          # ptr(t, True) shorthand: fp32, None allowed
+    """Raw device pointer of a contiguous CUDA tensor on the CURRENT device (the only kind the library accepts: every
+    wrapper launches on the current device's current stream, so a tensor living elsewhere would be dereferenced by the
+    wrong GPU).  ptr(t, True) is shorthand for fp32 with None allowed."""
+    if isinstance(dtype, bool):
         dtype, allow_none = torch.float32, dtype
-    """Raw device pointer of a contiguous CUDA tensor (the only kind the library accepts)."""
     if t is None:
         if allow_none:
             return None
         raise LbbnnError("required tensor is None")
     if not t.is_cuda:
         raise LbbnnError("lbbnn kernels take CUDA tensors only (no CPU fallback); got a CPU tensor")
+    if t.device.index != torch.cuda.current_device():
+        raise LbbnnError(f"tensor lives on cuda:{t.device.index} but the current device is cuda:{torch.cuda.current_device()}; "
+                         "wrap the call in torch.cuda.device(tensor.device) (kernels launch on the current device's stream)")
     if t.dtype != dtype:
         raise LbbnnError(f"expected {dtype}, got {t.dtype}")
     if not t.is_contiguous():
@@ -224,18 +229,19 @@ def current_stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-_device_checked = False
+_device_checked = set()
 
 
 def require_device():
-    global _device_checked
-    if _device_checked:
-        return
+    """Raises unless the current CUDA device is a compute-capability-10.x GPU (checked once per device)."""
     if not torch.cuda.is_available():
         raise LbbnnError("no CUDA device: lbbnn runs on B200 (sm_100a) only and has no CPU fallback")
+    dev = torch.cuda.current_device()
+    if dev in _device_checked:
+        return
     if not lib.lbbnn_device_ok():
         raise LbbnnError("the current CUDA device is not compute capability 10.x; liblbbnn is sm_100a-only")
-    _device_checked = True
+    _device_checked.add(dev)
 
 
 # ---- workspace: one growable buffer per (device, stream) -------------------------------------------

@@ -115,7 +115,10 @@ class LRTTrainer:
         st.x, st.y, st.step_dev = K.ptr(self.x), K.ptr(self.y, torch.int64), K.ptr(self.step_dev, torch.int64)
         st.seed = (self.seed + 0x9E3779B97F4A7C15 * self.rank) & (2 ** 64 - 1)
         st.lr, st.beta1, st.beta2, st.eps = self.lr, self.betas[0], self.betas[1], self.eps
-        st.kl_scale = 1.0 / (self.num_batches * self.world)     # KL is replicated on every rank: its grad is added once
+        # the update phase adds the KL gradient AFTER the raw gradients were sum-reduced, once and identically on every rank
+        # (SURVEY.md §8e), so it is NOT pre-divided by the world size -- unlike the per-layer path below, whose finalize
+        # kernels add it on every rank BEFORE the all-reduce of .grad
+        st.kl_scale = 1.0 / self.num_batches
         st.stats = K.ptr(self.stats)
         self._step_desc = st
         nbytes = int(K.lib.lbbnn_lrt_step_workspace_bytes(st))
@@ -279,6 +282,8 @@ class LRTTrainer:
         return self._stats_dict(self.stats_host)
 
     def _stats_dict(self, st):
+        """[nll, kl_1..kl_L] of the step.  Data parallel: `nll` (and so `loss`) is THIS RANK's shard of the minibatch only
+        (the sum over ranks is never formed on the device); the KL terms are replicated."""
         nll = float(st[0])
         kl = float(st[1:].sum())
         return {"nll": nll, "kl": kl, "loss": nll + kl / self.num_batches}

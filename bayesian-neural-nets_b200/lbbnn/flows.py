@@ -139,10 +139,12 @@ class PropagateFlow(nn.Module):
                 out += [m.weight, m.bias]
         return out
 
-    def forward(self, z, masks=None):
+    def forward(self, z, masks=None, per_row=False):
         """z: (B, dim) or (dim,).  masks: optional injected list/tensor of {0,1} masks, one per transform, each
         shaped like z.  Returns (z_out, logdet) with the reference's shapes: logdet (B,) / scalar for RNVP, a
-        scalar summed over everything for the 'MNF' kind (flows2:241)."""
+        scalar summed over everything for the 'MNF' kind (flows2:241).  per_row=True returns the (B,) per-row
+        log-determinants for either kind (a caller that batched independent flow evaluations into one launch
+        takes the rows apart itself)."""
         one_d = z.dim() == 1
         z2 = z.reshape(1, -1) if one_d else z
         if masks is not None:
@@ -150,6 +152,8 @@ class PropagateFlow(nn.Module):
         self._calls += 1
         self.last_noise_key = (current_seed(), (self._uid << 44) | (self._calls << 8))
         zo, ld = _FlowFunction.apply(z2, masks, self.kind, self.n_hidden, self.last_noise_key, *self._params())
+        if per_row:
+            return (zo[0], ld[0]) if one_d else (zo, ld)
         if self.kind == K.FLOW_IAF:
             return (zo[0] if one_d else zo), ld.sum()
         return (zo[0], ld[0]) if one_d else (zo, ld)

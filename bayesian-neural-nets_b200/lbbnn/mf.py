@@ -428,6 +428,8 @@ class MCPredictor:
             self.alpha = [torch.zeros(o, i, **f32) for i, o in sizes]
             self.bias_sigma = [torch.zeros(o, **f32) for _, o in sizes]
         n_lanes = (2 if self.n_tc else 1) if lanes is None else max(1, int(lanes))
+        if SB == 1:
+            n_lanes = 1     # the one-sample kernels share self.ws (split-K scratch of lbbnn_linear_f32_fwd): no concurrent lanes
         self.lanes = [_McLane(self, dev) for _ in range(n_lanes)]
         self.ws = torch.empty(max(K.lrt_workspace_bytes(self.B, i, o) for i, o in sizes), dtype=torch.uint8, device=dev)
         self.kernels_per_launch = 0
@@ -615,7 +617,11 @@ class MCPredictor:
                 main.wait_stream(lane.stream)
 
     def result(self, total_samples):
-        """Combine lanes and ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics."""
+        """Combine lanes and ranks (one all-reduce of the two fp64 accumulators) and form the reference's statistics.
+
+        `pred` is the argmax of the mean log-softmax over ALL `total_samples` samples.  The reference's ensemble
+        prediction is `outputs[0:10].mean(0)` (MF:416): the first TEN samples whatever TEST_SAMPLES is -- identical to
+        `pred` at the reference's TEST_SAMPLES = 10; `predict(x, samples, ensemble_first=10)` returns both."""
         sum_logp, sum_prob = self.sum_logp, self.sum_prob
         if self.pg is not None:
             both = torch.stack([sum_logp, sum_prob])
@@ -625,6 +631,24 @@ class MCPredictor:
         probs = sum_prob / total_samples
         return {"mean_logp": mean_logp, "pred": mean_logp.argmax(1), "probs": probs,
                 "entropy": -(probs * torch.log(probs)).sum(1)}
+
+
+    def predict(self, x, samples, ensemble_first=10):
+        """test_ensemble's per-batch statistics (MF:366-418) for `samples` MC weight samples on this rank's group:
+        result(samples) plus `pred_first` = argmax of the mean of the FIRST `ensemble_first` samples' log-softmax outputs
+        (`outputs[0:10].mean(0)`, MF:416-417).  Sample streams are keyed by the sample index, so the first-k statistics are
+        those very samples: they are run first as their own (short) pass, then the whole range."""
+        k = min(int(ensemble_first), int(samples))
+        world = 1 if self.pg is None else torch.distributed.get_world_size(self.pg)
+        rank = 0 if self.pg is None else torch.distributed.get_rank(self.pg)
+        first, count = shard_samples(k, world, rank)
+        self.run(x, count, first_sample=first)
+        pred_first = self.result(k)["pred"]
+        first, count = shard_samples(int(samples), world, rank)
+        self.run(x, count, first_sample=first)
+        out = self.result(int(samples))
+        out["pred_first"] = pred_first
+        return out
 
 
 # ---- ensemble / sparsity statistics of the driver loops, on the parameters' device (SURVEY.md §8f rank 2) -------------------

@@ -150,14 +150,16 @@ class BayesianLinear(nn.Module):
                 mask_rows.append(list(nz["z_masks2"]))
         z0 = self._z0(torch.cat(eps_rows, 0))
         masks = [torch.cat([r[t] for r in mask_rows], 0) for t in range(len(mask_rows[0]))] if inj else None
-        zs, logdets = self.z_flow(z0, masks)
+        # per-row log-determinants: the rows are independent evaluations (the reference calls sample_z() once per row set,
+        # MNF:194 and MNF:210), so the IAF kind's "sum over everything" (flows2:241) must not mix them
+        zs, logdets = self.z_flow(z0, masks, per_row=True)
         z_k = zs[0]
         if not want_kl:
             self.z = z0[:1]
             return z_k, 0
         self.z = z0[1:2]                                                # sample_z() overwrites self.z with (1,in)
         z2 = zs[1]
-        log_det_q = logdets if logdets.dim() == 0 else logdets[1]       # IAF kind: one scalar over everything
+        log_det_q = logdets[1]                                          # the KL row's own log-det (sample_z() with batch 1)
         M0, V, kl_wb = _MomentsKL.apply(self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z2, self.cfg)
         eps_r = nz["eps_r"] if "eps_r" in nz else torch.randn(self.out_features, device=dev)
         z_b, log_det_r = self.r_flow(z2, nz.get("r_masks"))

@@ -382,6 +382,82 @@ def golden_vd_train():
     print("vd_train golden written; losses", out["loss_0"], out["loss_1"])
 
 
+def golden_mnf_iaf():
+    """MNF layer whose z / r flows are the IAF-style 'MNF' transform (flows2:225-241; Z_FLOW_TYPE = R_FLOW_TYPE = 'MNF'):
+    the KL branch's log_det_q is the KL row's own log-determinant (sample_z() with batch 1, MNF:210)."""
+    ns = H.load_reference_classes("LBBNN-GP-MF-MNF.py", flows_module="flows2", Z_FLOW_TYPE="MNF", R_FLOW_TYPE="MNF")
+    Layer = ns["BayesianLinear"]
+    out = {}
+    for tag, (seed, b, i, o) in {"a": (171, 6, 37, 23), "b": (172, 5, 64, 10)}.items():
+        case = C.mnf_layer_case(seed, b, i, o, kind="MNF")
+        layer = Layer(i, o, 2)
+        _load_named(layer, C.flat_named(case["p"]))
+        layer.train()
+        x = case["x"].clone().requires_grad_(True)
+        with H.replay(H.NoiseQueue(_mnf_queue(case["noise"]))):
+            act = layer(x, sample=True)
+        kl = layer.kl
+        ((act * case["gout"]).sum() + kl / C.NUM_BATCHES).backward()
+        out[tag + "_meta"] = np.array([seed, b, i, o])
+        out[tag + "_act"] = act.detach().numpy()
+        out[tag + "_kl"] = np.float64(kl.item())
+        out[tag + "_z"] = layer.z.detach().numpy()
+        out[tag + "_dx"] = x.grad.numpy()
+        for name, prm in layer.named_parameters():
+            out[tag + "_d_" + name] = prm.grad.numpy() if prm.numel() <= 4000 else C.grad_digest(prm.grad)["sample"]
+    np.savez_compressed(os.path.join(HERE, "mnf_layer_iaf.npz"), **out)
+    print("mnf iaf golden written; kl", out["a_kl"], out["b_kl"])
+
+
+def tensor_digest(v):
+    """Position-sensitive fingerprint of a parameter tensor: shape, fp64 sum and abs-sum, head and strided sample."""
+    f = v.detach().reshape(-1)
+    return {"shape": np.array(v.shape, dtype=np.int64), "sum": np.float64(f.double().sum().item()),
+            "abs": np.float64(f.double().abs().sum().item()), "head": f[:8].numpy().copy(),
+            "sample": f[::max(1, f.numel() // 64)].numpy().copy()}
+
+
+def golden_ctor():
+    """state_dict keys (in order) and parameter fingerprints of the reference's own constructors under torch.manual_seed:
+    the drop-in constructors must consume torch's RNG in the same order (a2, a8)."""
+    out = {}
+
+    def put(tag, module, extra=()):
+        sd = module.state_dict()
+        out[tag + "_keys"] = np.array(list(sd.keys()))
+        for k, v in sd.items():
+            for n, d in tensor_digest(v).items():
+                out[f"{tag}|{k}|{n}"] = d
+        for name in extra:     # non-parameter tensors drawn in the ctor (MF: gammas, alpha)
+            for li, lay in enumerate(extra[name]):
+                for n, d in tensor_digest(getattr(lay, name)).items():
+                    out[f"{tag}|extra.l{li + 1}.{name}|{n}"] = d
+
+    for seed in (0, 7):
+        ns = H.load_reference_classes("LBBNN-GP-MF-LRT.py")
+        torch.manual_seed(seed)
+        put(f"lrt{seed}", ns["BayesianNetwork"]())
+        ns = H.load_reference_classes("LBBNN-GP-MF-MNF.py", flows_module="flows2")
+        torch.manual_seed(seed)
+        put(f"mnf{seed}", ns["BayesianNetwork"]())
+        ns = H.load_reference_classes("LBBNN-GP-MF.py")
+        torch.manual_seed(seed)
+        net = ns["BayesianNetwork"]()
+        put(f"mf{seed}", net, {"gammas": (net.l1, net.l2, net.l3), "alpha": (net.l1, net.l2, net.l3)})
+    ns = H.load_reference_classes("LBBNN-GP-MFsim_study.py")
+    torch.manual_seed(3)
+    net = ns["BayesianNetwork"]()
+    put("mfsim3", net, {"gammas": (net.l1,), "alpha": (net.l1,)})
+    ns = H.load_reference_classes("LBBNN-GP-MF-MNFsim_study.py", flows_module="flows_simstudy", p=21)
+    torch.manual_seed(3)
+    put("mnfsim3", ns["BayesianNetwork"]())
+    ns = H.load_reference_classes("LBBNN-GP-MF-MNF.py", flows_module="flows2", Z_FLOW_TYPE="MNF", R_FLOW_TYPE="MNF")
+    torch.manual_seed(5)
+    put("mnfiaf5", ns["BayesianLinear"](40, 12, 2))
+    np.savez_compressed(os.path.join(HERE, "ctor.npz"), **out)
+    print("ctor golden written;", len(out), "entries")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("vd_train", "all"):
@@ -396,3 +472,7 @@ if __name__ == "__main__":
         globals()["golden_mf"]()
     if what in ("mfsim", "all"):
         golden_mfsim()
+    if what in ("mnf_iaf", "all"):
+        golden_mnf_iaf()
+    if what in ("ctor", "all"):
+        golden_ctor()

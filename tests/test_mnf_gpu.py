@@ -162,6 +162,40 @@ def test_mnf_layer_matches_oracle_and_reference(lb, key):
         assert C.rel_err(mine, ref) < GTOL, name
 
 
+@pytest.mark.parametrize("key", ["a", "b"])
+def test_mnf_layer_with_iaf_flows_matches_oracle_and_reference(lb, key):
+    """z_flow_type = r_flow_type = 'MNF' (the IAF-style transform, flows2:225-241) as the layer's flows: the KL branch's
+    log_det_q must be the KL row's own log-determinant although the activation row shares the flow launch."""
+    g = np.load(os.path.join(C.GOLDEN, "mnf_layer_iaf.npz"))
+    seed, b, i, o = (int(v) for v in g[f"{key}_meta"])
+    case = C.mnf_layer_case(seed, b, i, o, kind="MNF")
+    named64 = {k: v.double().clone().requires_grad_(True) for k, v in C.flat_named(case["p"]).items()}
+    p64 = C.unflatten_like(case["p"], named64)
+    x64 = case["x"].double().clone().requires_grad_(True)
+    nz64 = {k: ([m.double() for m in v] if isinstance(v, list) else v.double()) for k, v in case["noise"].items()}
+    act64, kl64 = O.mnf_forward(x64, p64, nz64, kind="MNF")
+    ((act64 * case["gout"].double()).sum() + kl64 / C.NUM_BATCHES).backward()
+
+    layer = lb.mnf.BayesianLinear(i, o, 2, z_flow_type="MNF", r_flow_type="MNF")
+    layer.load_state_dict(C.flat_named(case["p"]))
+    layer = layer.cuda().train()
+    x = case["x"].cuda().requires_grad_(True)
+    act = layer(x, noise=_cuda_noise(case["noise"]))
+    ((act * case["gout"].cuda()).sum() + layer.kl / C.NUM_BATCHES).backward()
+    assert C.rel_err(act.detach(), g[f"{key}_act"]) < TOL
+    assert abs(layer.kl.item() - float(g[f"{key}_kl"])) / abs(float(g[f"{key}_kl"])) < TOL
+    assert abs(layer.kl.item() - kl64.item()) / abs(kl64.item()) < TOL
+    assert C.rel_err(x.grad, g[f"{key}_dx"]) < TOL
+    got = dict(layer.named_parameters())
+    assert set(got) == set(named64)
+    for name, v in named64.items():
+        assert got[name].grad is not None, name
+        assert C.rel_err(got[name].grad, v.grad) < GTOL, name
+        ref = g[f"{key}_d_{name}"]
+        mine = got[name].grad if v.numel() <= 4000 else torch.from_numpy(C.grad_digest(got[name].grad.cpu())["sample"])
+        assert C.rel_err(mine, ref) < GTOL, name
+
+
 def test_mnf_layer_eval_branches(lb):
     """eval: posterior-mean branch is still stochastic in z (MNF:202-206), .kl == 0 unless calculate_log_probs."""
     case = C.mnf_layer_case(71, 9, 50, 13)

@@ -125,12 +125,12 @@ def test_mf_mnist_elbo_matches_reference():
                 assert C.rel_err(v.grad, g[f"l{li}_{k}_full"]) < 2e-5, (li, k)
 
 
-def _mnf_oracle(case, priors=O.Priors(), dtype=torch.float32):
+def _mnf_oracle(case, priors=O.Priors(), dtype=torch.float32, kind="RNVP"):
     named = {k: v.to(dtype).clone().requires_grad_(True) for k, v in C.flat_named(case["p"]).items()}
     p = C.unflatten_like(case["p"], named)
     x = case["x"].to(dtype).clone().requires_grad_(True)
     nz = {k: ([m.to(dtype) for m in v] if isinstance(v, list) else v.to(dtype)) for k, v in case["noise"].items()}
-    act, kl = O.mnf_forward(x, p, nz, priors=priors)
+    act, kl = O.mnf_forward(x, p, nz, priors=priors, kind=kind)
     ((act * case["gout"].to(dtype)).sum() + kl / C.NUM_BATCHES).backward()
     return act, kl, x, named
 
@@ -142,6 +142,22 @@ def test_mnf_layer_matches_reference(key):
     case = C.mnf_layer_case(seed, b, i, o, h_sizes=(hw,) * nh)
     pri = O.Priors(0.1, 1.3, 0.3, 0.0, 1.3) if key == "sa" else O.Priors()        # MNFsim:157-174
     act, kl, x, named = _mnf_oracle(case, pri)
+    assert C.rel_err(act, g[f"{key}_act"]) < TOL
+    assert abs(kl.item() - float(g[f"{key}_kl"])) / abs(float(g[f"{key}_kl"])) < 5e-6
+    assert C.rel_err(x.grad, g[f"{key}_dx"]) < 5e-6
+    for name, v in named.items():
+        ref = g[f"{key}_d_{name}"]
+        got = v.grad if v.numel() <= 4000 else torch.from_numpy(C.grad_digest(v.grad)["sample"])
+        assert C.rel_err(got, ref) < 5e-5, name
+
+
+@pytest.mark.parametrize("key", ["a", "b"])
+def test_mnf_layer_with_iaf_flows_matches_reference(key):
+    """Z_FLOW_TYPE = R_FLOW_TYPE = 'MNF' (flows2:225-241): the KL branch's log_det_q covers the KL row only (MNF:210)."""
+    g = _npz("mnf_layer_iaf.npz")
+    seed, b, i, o = (int(v) for v in g[f"{key}_meta"])
+    case = C.mnf_layer_case(seed, b, i, o, kind="MNF")
+    act, kl, x, named = _mnf_oracle(case, kind="MNF")
     assert C.rel_err(act, g[f"{key}_act"]) < TOL
     assert abs(kl.item() - float(g[f"{key}_kl"])) / abs(float(g[f"{key}_kl"])) < 5e-6
     assert C.rel_err(x.grad, g[f"{key}_dx"]) < 5e-6
