@@ -1,10 +1,17 @@
 #!/usr/bin/env python3
-"""Benchmark of the variational-layer hot path (BASELINE.json metric: train samples/s).
+"""Benchmark of the variational-layer hot path (BASELINE.json metric: train samples/s & MC-predictive samples/s at
+1/2/4/8 B200; % TC peak).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-Default workload = BASELINE.json configs[1]: LRT MNIST-shape MLP 784-400-600-10, batch 100 per GPU,
-one step = forward + loss + backward + Adam on one synthetic minibatch (LBBNN-GP-MF-LRT.py:217-229).
+Default (`--workload headline`): the configuration the metric's "% TC peak" is quoted on -- BASELINE.json configs[4], the
+widened LRT stack 4096-4096-4096-10 in bf16 at batch 8192 per GPU (tcgen05 / TMEM / TMA kernels; data-parallel over the N
+ranks) -- timed for EXACTLY --steps steps, with two sub-records under "also" measured in the same process on the same
+GPUs: `lrt_mnist` (configs[1], the reference's own MNIST-shape training step, fp32; data parallel) and `mf_mc_predict`
+(configs[3], posterior-predictive averaging over 1024 MC weight samples x 1000 inputs, samples sharded over the N ranks).
+One step = forward + loss + backward + Adam on one synthetic minibatch (LBBNN-GP-MF-LRT.py:217-229).
+`--workload NAME` runs one workload alone.  `--impl reference` times the REFERENCE's own classes and `train` function
+(oracle/_ref, built by oracle/make_ref.py from /root/reference) on the host cores.
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for how every field is obtained.
 """
 import argparse
@@ -29,6 +36,20 @@ DTYPE = {"lrt_mnist": "f32", "lrt_wide": "bf16"}
 POOLS = {"lrt_mnist": 512, "lrt_wide": 4}      # lrt_wide: one 134 MB batch already exceeds L2
 NUM_BATCHES = 600
 POOL = 512          # default number of distinct input batches (lrt_mnist: 512 x 313.6 KB = 160 MB > 126 MB L2)
+
+
+NCU_SUMMARY = "r02_ncu_summary.json"     # {kernel key: {"dram_bytes_read": .., "dram_bytes_write": .., ...}}, written from this
+                                         # round's `ncu --set full` captures by profiles/ncu_summary.py
+
+
+def ncu_traffic(key):
+    """DRAM bytes (read + write) per launch of kernel `key` from THIS round's ncu capture, or None (never a stale file)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", NCU_SUMMARY)) as fh:
+            d = json.load(fh)[key]
+        return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"])
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def load_peaks():
@@ -110,27 +131,75 @@ def make_pool(pool, batch, in_features, classes, seed):
 # ------------------------------------------------------------------------------------------------
 # CPU baseline: the oracle port of the reference step, timed on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(workload, steps, warmup, budget_s=20.0):
+def _ref_modules():
+    """oracle/_ref (the reference's own classes + train(), sliced at build time by oracle/make_ref.py) or None."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import lbbnn_oracle as O
+    import make_ref
+    return make_ref if make_ref.available() else None
+
+
+def _ref_lrt_net(m, sizes):
+    """The reference's BayesianNetwork (LRT:199-214).  Its layer sizes are hard-coded to 784-400-600-10; the widened stack
+    of configs[4] composes the reference's own BayesianLinear exactly as LRT:206-214 does."""
+    if tuple(sizes) == (784, 400, 600, 10):
+        return m.BayesianNetwork()
+    F = torch.nn.functional
+
+    class WideNetwork(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1, self.l2, self.l3 = (m.BayesianLinear(i, o) for i, o in zip(sizes[:-1], sizes[1:]))
+
+        def forward(self, x, sample=False):
+            x = x.view(-1, sizes[0])
+            x = F.relu(self.l1(x, sample))
+            x = F.relu(self.l2(x, sample))
+            return F.log_softmax(self.l3(x, sample), dim=1)
+
+        def kl(self):
+            return self.l1.kl + self.l2.kl + self.l3.kl
+
+    return WideNetwork()
+
+
+def cpu_reference_steps(workload, steps, warmup, budget_s=20.0):
+    """The reference's training step on the host cores: `train(net, optimizer)` of LBBNN-GP-MF-LRT.py:217-229 (unmodified,
+    from oracle/_ref) over one injected synthetic minibatch per call; falls back to the oracle port when oracle/_ref is
+    absent (kind says which)."""
     sizes, B = SIZES[workload], BATCH[workload]
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     rng = np.random.default_rng(0)
-    layers = [{k: v.clone().requires_grad_(True) for k, v in O.init_lrt_params(rng, i, o).items()}
-              for i, o in zip(sizes[:-1], sizes[1:])]
-    opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
     nb = 8 if B <= 1000 else 1
     x = torch.from_numpy(rng.random((nb, B, sizes[0]), dtype=np.float32))
     y = torch.from_numpy(rng.integers(0, sizes[-1], size=(nb, B))).long()
+    R = _ref_modules()
+    if R is not None:
+        m = R.load("ref_lrt")
+        m.NUM_BATCHES = NUM_BATCHES
+        torch.manual_seed(0)
+        net = _ref_lrt_net(m, sizes)
+        opt = m.optim.Adam(net.parameters(), lr=1e-3)          # LRT:358
 
-    def one(i):
-        eps = [torch.randn(B, o) for o in sizes[1:]]            # LRT:174
-        opt.zero_grad(set_to_none=True)
-        loss, _, _, _ = O.lrt_net_loss(x[i % nb], y[i % nb], layers, eps, NUM_BATCHES)
-        loss.backward()
-        opt.step()
-        return loss
+        def one(i):
+            m.train_loader = [(x[i % nb], y[i % nb])]
+            return m.train(net, opt)[1]
+        kind, what = "reference", "the reference's own BayesianLinear classes and train() (oracle/_ref, sliced from LBBNN-GP-MF-LRT.py)"
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import lbbnn_oracle as O
+        layers = [{k: v.clone().requires_grad_(True) for k, v in O.init_lrt_params(rng, i, o).items()}
+                  for i, o in zip(sizes[:-1], sizes[1:])]
+        opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
+
+        def one(i):
+            eps = [torch.randn(B, o) for o in sizes[1:]]            # LRT:174
+            opt.zero_grad(set_to_none=True)
+            loss, _, _, _ = O.lrt_net_loss(x[i % nb], y[i % nb], layers, eps, NUM_BATCHES)
+            loss.backward()
+            opt.step()
+            return loss
+        kind, what = "port", "oracle port (oracle/lbbnn_oracle.py; oracle/_ref absent)"
 
     for i in range(warmup):
         one(i)
@@ -142,25 +211,34 @@ def cpu_reference_steps(workload, steps, warmup, budget_s=20.0):
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": f"{done} training steps (fwd+loss+bwd+Adam) of {workload} batch {B}, oracle port "
-                      f"(oracle/lbbnn_oracle.py) on torch-CPU fp32, {cores} threads",
+    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": kind,
+            "sample": f"{done} training steps (fwd+loss+bwd+Adam) of {workload} batch {B}: {what}, torch-CPU fp32, "
+                      f"{cores} threads",
             "ms_per_step": dt / done * 1e3, "steps": done}
+
+
+def reference_record(workload, args, steps, warmup, budget_s):
+    r = cpu_reference_steps(workload, steps, warmup, budget_s=budget_s)
+    return {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": r["steps"], "warmup": warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(workload, 1),  # the CPU reference computes in fp32, one process
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_steps(args.workload, args.steps, args.warmup, budget_s=120.0)
-    B = BATCH[args.workload]
-    line = {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": "samples/s",
-            "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.workload, 1),  # the CPU reference computes in fp32
-            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+    if args.workload != "headline":
+        print(json.dumps(reference_record(args.workload, args, args.steps, args.warmup, 120.0)), flush=True)
+        return
+    # headline: the wide stack for (up to) --steps steps within ~2.5 minutes, then bounded samples of the two sub-records
+    line = reference_record("lrt_wide", args, args.steps, min(args.warmup, 1), 150.0)
+    line["also"] = {"lrt_mnist": reference_record("lrt_mnist", args, 200, 3, 20.0),
+                    "mf_mc_predict": mc_reference_record(args, 20.0, 64)}
     print(json.dumps(line), flush=True)
 
 
@@ -262,18 +340,12 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20, replays=True):
         e1.synchronize()
         us_warm = e0.elapsed_time(e1) * 1e3 / 200
     ach = nbytes / (us_per_step * 1e-6) / 1e9
-    traffic = None      # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_lrt_step_kernel.json")) as fh:
-            nc = json.load(fh)
-        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        traffic = sum(float(nc[k]["value"]) * scale[nc[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-    except Exception:  # noqa: BLE001
-        pass
+    # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of THIS round's kernel, else null
+    traffic = ncu_traffic("lrt_step_kernel")
     roof = {"bound": "hbm", "kernel": "lrt_step_kernel (persistent: fwd + loss + bwd + KL + Adam of the whole stack)",
             "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": traffic,
             "traffic_note": "ncu replays flush the caches, so this is the cold-L2 DRAM traffic of one launch "
-                            "(profiles/r01_ncu_lrt_step_kernel.json); in steady state the 27 MB of state stay in L2",
+                            f"(profiles/{NCU_SUMMARY}); in steady state the 27 MB of state stay in L2",
             "peak_source": peaks["source"], "us_per_launch": us_per_step, "bytes_per_launch": nbytes,
             "us_per_launch_back_to_back": us_warm, "us_per_launch_cold_l2": us_cold,
             "timing": "average launch over the timed region (CUDA events, one launch per step, inputs rotate through a "
@@ -323,7 +395,7 @@ def profile_calls_wide(tr, reps=5):
             K.check(fn())
         e1.record()
         e1.synchronize()
-        out.append({"name": name, "us": e0.elapsed_time(e1) / reps * 1e3, "flops": flops})
+        out.append({"name": name, "key": name.split(" ")[0], "us": e0.elapsed_time(e1) / reps * 1e3, "flops": flops})
     return out
 
 
@@ -333,26 +405,58 @@ def _mark(msg):
         print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
 
 
-def run_ours(args):
+class Ctx:
+    """Process-wide state of one bench run: rank / device / process group, created once for all workloads of the run."""
+
+    def __init__(self, args):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        if self.world != args.gpus and self.world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.pg = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.pg = dist.group.WORLD
+
+    def barrier(self):
+        if self.world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def shutdown(self):
+        """Leave the process group cleanly: every captured graph that holds NCCL / symmetric-memory kernels has been
+        dropped by its workload, the device is idle, all ranks are here.  destroy_process_group() is given 30 s (it was
+        seen to block on one box while graphs were still alive); a watchdog then ends the process, the JSON line being
+        already flushed."""
+        if self.world == 1:
+            return
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        torch.distributed.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        t = threading.Timer(30.0, lambda: os._exit(0))
+        t.daemon = True
+        t.start()
+        torch.distributed.destroy_process_group()
+        t.cancel()
+
+
+def bench_lrt(ctx, workload, steps, warmup, unfused=False, cpu_budget_s=15.0):
+    """One LRT training workload (lrt_mnist / lrt_wide) on this run's GPUs; returns the record on rank 0, None elsewhere."""
     import lbbnn
     if os.environ.get("LBBNN_HANG_DUMP"):
         import faulthandler
         faulthandler.dump_traceback_later(int(os.environ["LBBNN_HANG_DUMP"]), exit=True)
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    pg = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        pg = dist.group.WORLD
+    rank, local_rank, world, dev, pg = ctx.rank, ctx.local_rank, ctx.world, ctx.dev, ctx.pg
+    args = argparse.Namespace(steps=steps, warmup=warmup, unfused=unfused)
 
-    workload = args.workload
     sizes, B, POOL = SIZES[workload], BATCH[workload], POOLS[workload]
     wide = workload == "lrt_wide"
     torch.manual_seed(0)                       # identical initial parameters on every rank
@@ -371,10 +475,7 @@ def run_ours(args):
     pool_x_host, pool_y_host = pool_x_host.pin_memory(), pool_y_host.pin_memory()
     pool_x, pool_y = pool_x_host.to(dev), pool_y_host.to(dev)
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
+    barrier = ctx.barrier
 
     # ---- device-resident throughput ("value") ---------------------------------------------------------
     def dev_step(i):
@@ -443,14 +544,9 @@ def run_ours(args):
             top = max(prof, key=lambda r: r["us"])
             ach = top["flops"] / (top["us"] * 1e-6) / 1e12
             step_flops = sum(2 * 2.0 * B * i * o * (3 if li > 0 else 2) for li, (i, o) in enumerate(zip(sizes[:-1], sizes[1:])))
-            traffic, traffic_note = None, None
-            prof_path = os.path.join(ROOT, "profiles", "r01_ncu_tc_dual_gemm.json")
-            if os.path.exists(prof_path) and "tc_lrt_fwd" in top["name"]:      # DRAM bytes of the ncu capture of this call
-                nc = json.load(open(prof_path))["launches"][0]
-                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-                traffic = sum(float(nc[k]["value"]) * scale[nc[k]["unit"]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
-                traffic_note = ("dram__bytes_read + dram__bytes_write of one ncu --set full capture of this call "
-                                "(profiles/r01_ncu_tc_dual_gemm.json): 0.27 GB of unique operands + 0.54 GB of outputs")
+            traffic = ncu_traffic(top["key"])
+            traffic_note = (f"dram__bytes_read + dram__bytes_write of this round's ncu --set full capture of this call "
+                            f"(profiles/{NCU_SUMMARY})") if traffic is not None else None
             roof = {"bound": "tensor", "kernel": top["name"], "achieved": ach, "peak": peaks["bf16_tflops"],
                     "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": peaks["source"], "us_per_launch": top["us"], "flops_per_launch": top["flops"],
@@ -476,8 +572,8 @@ def run_ours(args):
             kern = [{"name": r["name"], "us": round(r["us"], 2), "bytes": r["bytes"],
                      "gbps": round(r["bytes"] / r["us"] / 1e3, 1)} for r in prof]
         cpu = None
-        if world == 1:
-            cpu = cpu_reference_steps(workload, steps=2 if wide else 60, warmup=1 if wide else 3, budget_s=15.0)
+        if world == 1 and cpu_budget_s > 0:
+            cpu = cpu_reference_steps(workload, steps=2 if wide else 60, warmup=1 if wide else 3, budget_s=cpu_budget_s)
         line = {
             "metric": "train_samples_per_sec", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -490,21 +586,19 @@ def run_ours(args):
             "gpu_launches": tr.kernels_per_step * args.steps, "allreduce": getattr(tr, "allreduce", None),
             "kernels_per_step": tr.kernels_per_step,
             "roofline": roof, "step_roofline": step_roof, "kernels": kern,
-            "clocks": clocks,
+            "clocks": clocks, "timed_region_s": ms * 1e-3,
             "last_loss": out["loss"],
         }
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        # destroy_process_group() hangs while a CUDA graph still holds captured NCCL kernels (seen on the box:
-        # both ranks stuck there until the 600 s collective timeout): drop the graph, sync, and leave without it.
-        torch.distributed.barrier()
-        tr.graph = None
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    else:
+        line = None
+    # captured NCCL / symmetric-memory work must be gone before the process group is torn down
+    tr.graph = None
+    del tr, pool_x, pool_y, pool_x_host, pool_y_host
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -524,15 +618,52 @@ def _mc_net_params(rng):
 
 
 def cpu_reference_mc(budget_s=15.0, max_samples=64):
+    """The per-sample body of the reference's test_ensemble loop (LBBNN-GP-MF.py:367-406) with the reference's own MF
+    classes (oracle/_ref): refresh alpha, draw the statistics masks, the stochastic forward with fresh masks, the density
+    masks, and the host-side row-normalised expit accumulation; gamma.exact = True as the driver sets it (MF:612-627).
+    Falls back to the oracle port when oracle/_ref is absent."""
     rng = np.random.default_rng(0)
     layers, O = _mc_net_params(rng)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     x = torch.from_numpy(rng.random((MC_BATCH, MC_SIZES[0]), dtype=np.float32))
-    acc = torch.zeros(MC_BATCH, MC_SIZES[-1])
-    done, t0 = 0, time.perf_counter()
-    with torch.no_grad():
-        while done < max_samples and (done < 2 or time.perf_counter() - t0 < budget_s):
+    R = _ref_modules()
+    if R is not None:
+        from scipy.special import expit
+        m = R.load("ref_mf")
+        m.BATCH_SIZE = MC_BATCH
+        net = m.BayesianNetwork()
+        with torch.no_grad():
+            for l, p in zip((net.l1, net.l2, net.l3), layers):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        net.eval()
+        ls = (net.l1, net.l2, net.l3)
+        for l in ls:
+            l.gamma.exact = True
+        state = {"means": None, "sum": torch.zeros(MC_BATCH, MC_SIZES[-1]), "spars": 0.0, "dens": 0.0}
+        ntot = float(sum(i * o for i, o in zip(MC_SIZES[:-1], MC_SIZES[1:])))
+
+        def one():
+            for l in ls:                                                             # MF:369-374
+                l.alpha = 1 / (1 + torch.exp(-l.lambdal))
+                l.gamma.alpha = l.alpha
+            g = [l.gamma.rsample() for l in ls]                                      # MF:377-379
+            state["spars"] += sum(torch.sum(t > 0.5).cpu().detach().numpy() for t in g) / ntot   # MF:382-385
+            out = net.forward(x, sample=True, medimean=False, g1=net.l1.gamma.rsample(), g2=net.l2.gamma.rsample(),
+                              g3=net.l3.gamma.rsample())                             # MF:389-390
+            g = [l.gamma.rsample() for l in ls]                                      # MF:391-393
+            state["dens"] += torch.cat([t.flatten() for t in g]).mean().item()       # MF:394-395
+            tmp = expit(out.detach().cpu().numpy())                                  # MF:398-406
+            for j in range(MC_BATCH):
+                tmp[j] /= np.sum(tmp[j])
+            state["means"] = tmp if state["means"] is None else state["means"] + tmp
+            state["sum"] += out
+        kind, what = "reference", "the reference's own MF classes (oracle/_ref, sliced from LBBNN-GP-MF.py), loop body MF:367-406"
+    else:
+        acc = torch.zeros(MC_BATCH, MC_SIZES[-1])
+
+        def one():
             h = x
             for i, p in enumerate(layers):
                 alpha = O.alpha_of(p["lambdal"])
@@ -540,23 +671,35 @@ def cpu_reference_mc(budget_s=15.0, max_samples=64):
                 nz = {"eps_w": torch.randn_like(alpha), "eps_b": torch.randn(alpha.shape[0])}
                 h, _, _ = O.mf_forward(h, p, g, nz, calc_log_probs=False)
                 h = torch.relu(h) if i < len(layers) - 1 else torch.log_softmax(h, 1)
-            acc += h
+            acc.add_(h)
+        kind, what = "port", "oracle port (oracle/_ref absent)"
+    done, t0 = 0, None
+    with torch.no_grad():
+        one()                                                                      # warm-up
+        t0 = time.perf_counter()
+        while done < max_samples and (done < 2 or time.perf_counter() - t0 < budget_s):
+            one()
             done += 1
     dt = time.perf_counter() - t0
-    return {"value": done / dt, "unit": "MC weight-samples/s", "cores": cores, "kind": "port", "steps": done,
+    return {"value": done / dt, "unit": "MC weight-samples/s", "cores": cores, "kind": kind, "steps": done,
             "ms_per_step": dt / done * 1e3,
             "sample": f"{done} MC weight samples (masks+weights+bias sampled, forward over {MC_BATCH} inputs, accumulate) "
-                      f"of the MF 784-400-600-10 net, oracle port on torch-CPU fp32, {cores} threads"}
+                      f"of the MF 784-400-600-10 net: {what}, torch-CPU fp32, {cores} threads"}
+
+
+def mc_reference_record(args, budget_s, max_samples):
+    r = cpu_reference_mc(budget_s=budget_s, max_samples=max_samples)
+    return {"impl": "reference", "metric": "mc_predictive_samples_per_sec", "value": r["value"],
+            "unit": r["unit"], "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mc_config(1),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
 
 
 def _mc_traffic():
-    """DRAM bytes of one layer-1 launch from the ncu capture in profiles/ (1-CTA kernel; same operands and outputs)."""
-    path = os.path.join(ROOT, "profiles", "r01_ncu_tc_linear_tf32x3.json")
-    try:
-        l1 = json.load(open(path))["layer1"]
-        return (l1["dram_read_MB"] + l1["dram_write_MB"]) * 1e6
-    except (OSError, KeyError, ValueError):
-        return None
+    return ncu_traffic("tc_linear_tf32x3_pair[l1]")
 
 
 def mc_config(world):
@@ -570,27 +713,22 @@ def mc_config(world):
 
 def run_mc(args):
     if args.impl == "reference":
-        if int(os.environ.get("RANK", "0")) != 0:
-            return
-        r = cpu_reference_mc(budget_s=60.0, max_samples=max(8, args.steps))
-        print(json.dumps({"impl": "reference", "metric": "mc_predictive_samples_per_sec", "value": r["value"],
-                          "unit": r["unit"], "n_gpus": args.gpus, "steps": r["steps"], "warmup": 0,
-                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": mc_config(1),
-                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                          "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}), flush=True)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(mc_reference_record(args, 60.0, max(8, args.steps))), flush=True)
         return
+    ctx = Ctx(args)
+    line = bench_mc(ctx, args, args.steps, args.warmup)
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.shutdown()
+
+
+def bench_mc(ctx, args, steps, warmup, cpu_budget_s=15.0):
+    """configs[3] on this run's GPUs; a step = 1024 MC weight samples over one 1000-input test batch, samples sharded over
+    the ranks, one fp64 all-reduce of the accumulators.  Returns the record on rank 0, None elsewhere."""
     import lbbnn
-    rank, local_rank = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    pg = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
-        pg = dist.group.WORLD
+    rank, local_rank, world, dev, pg = ctx.rank, ctx.local_rank, ctx.world, ctx.dev, ctx.pg
+    args = argparse.Namespace(steps=steps, warmup=warmup, mc_batch=args.mc_batch, mc_gemm=args.mc_gemm, mc_lanes=args.mc_lanes)
     rng = np.random.default_rng(0)
     layers, _ = _mc_net_params(rng)
     net = lbbnn.mf.BayesianNetwork(MC_SIZES).to(dev)
@@ -605,10 +743,7 @@ def run_mc(args):
     xs = xs_host.to(dev)
     pred_host = torch.zeros(MC_BATCH, dtype=torch.int64).pin_memory()
 
-    def barrier():
-        if world > 1:
-            torch.distributed.barrier()
-        torch.cuda.synchronize()
+    barrier = ctx.barrier
 
     def step(i, host):
         mc.run((xs_host if host else xs)[i % 8], count, first_sample=first)
@@ -682,7 +817,7 @@ def run_mc(args):
         nbytes = (12 + (8 if tc else 4) * SB) * 784 * 400   # parameters read once (L2 serves the other samples) + SB x w written
         gflop = 2.0 * MC_BATCH * 784 * 400 * SB / 1e9        # ALGORITHMIC flops: one fp32 product per (input, weight)
         fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12   # nominal CUDA-core FFMA peak, TFLOP/s
-        cpu = cpu_reference_mc() if world == 1 else None
+        cpu = cpu_reference_mc(budget_s=cpu_budget_s) if (world == 1 and cpu_budget_s > 0) else None
         ach = gflop * 1e9 / (us_g * 1e-6) / 1e12     # TFLOP/s
         launches_per_step = sum((count // SB) // len(mc.lanes) + (1 if j < (count // SB) % len(mc.lanes) else 0)
                                 for j in range(len(mc.lanes))) + (1 if count % SB else 0)
@@ -713,6 +848,7 @@ def run_mc(args):
                                       "achieved": nbytes / (us_s * 1e-6) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                       "frac": nbytes / (us_s * 1e-6) / 1e9 / peaks["hbm_gbs"], "us_per_launch": us_s,
                                       "bytes_per_launch": nbytes},
+                "timed_region_s": ms * 1e-3,
                 "kernels": [{"name": "mc_sample[l1]", "us": round(us_s, 2)},
                             {"name": gname.split(" ")[0], "us": round(us_g, 2), "tflops": round(ach, 2)}],
                 "clocks": clocks}
@@ -724,14 +860,13 @@ def run_mc(args):
             line["roofline"]["fp32_cuda_core_peak_tflops"] = fp32_peak
         if cpu is not None:
             line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        torch.distributed.barrier()
-        mc.graph = None
-        torch.cuda.synchronize()
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    else:
+        line = None
+    mc.graph = None
+    del mc
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return line
 
 
 # ------------------------------------------------------------------------------------------------
@@ -921,26 +1056,54 @@ def run_module(args):
     print(json.dumps(line), flush=True)
 
 
+def run_headline(args):
+    """lrt_wide for exactly --steps steps, plus bounded runs of lrt_mnist and mf_mc_predict on the same GPUs (`also`)."""
+    ctx = Ctx(args)
+    line = bench_lrt(ctx, "lrt_wide", args.steps, args.warmup, unfused=args.unfused)
+    small = bench_lrt(ctx, "lrt_mnist", 2000, 50)
+    mc = bench_mc(ctx, args, 8, 3)
+    if ctx.rank == 0:
+        line["also"] = {"lrt_mnist": small, "mf_mc_predict": mc}
+        print(json.dumps(line), flush=True)
+    ctx.shutdown()
+
+
+def run_ours(args):
+    ctx = Ctx(args)
+    line = bench_lrt(ctx, args.workload, args.steps, args.warmup, unfused=args.unfused)
+    if ctx.rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.shutdown()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mc-batch", type=int, default=32, help="mf_mc_predict: weight samples per launch")
     ap.add_argument("--mc-gemm", default="auto", choices=("auto", "simt", "tc"),
                     help="mf_mc_predict: GEMMs on the tensor cores as 3xTF32 (auto / tc) or on the CUDA cores (simt)")
     ap.add_argument("--mc-lanes", type=int, default=None, help="mf_mc_predict: concurrent launch sequences per GPU")
     ap.add_argument("--eager", action="store_true", help="mnf_mnist / mf_mnist: eager modules instead of the graphed step")
-    ap.add_argument("--unfused", action="store_true", help="lrt_mnist: per-layer launch sequence instead of the step kernel")
-    ap.add_argument("--workload", default="lrt_mnist", choices=sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist", "vd_mnist"])
+    ap.add_argument("--unfused", action="store_true", help="lrt_*: per-layer launch sequence / separate update passes")
+    ap.add_argument("--workload", default="headline",
+                    choices=["headline"] + sorted(SIZES) + ["mf_mc_predict", "mnf_mnist", "mf_mnist", "vd_mnist"])
     args = ap.parse_args()
+    big = args.workload in ("headline", "lrt_wide")
+    if args.steps is None:
+        args.steps = 100 if big else (20 if args.workload == "mf_mc_predict" else 2000)
+    if args.warmup is None:
+        args.warmup = 5 if big or args.workload == "mf_mc_predict" else 50
     if args.workload == "mf_mc_predict":
         run_mc(args)
     elif args.workload in ("mnf_mnist", "mf_mnist", "vd_mnist"):
         run_module(args)
     elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "headline":
+        run_headline(args)
     else:
         run_ours(args)
 
