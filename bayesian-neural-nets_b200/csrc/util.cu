@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const lbbnn_adam_entry*
     if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
   }
   const lbbnn_adam_entry e = table[lo];
-  const float step_size = __ldg(coef), bc2_sqrt = __ldg(coef + 1);
+  const float step_size = __ldg(coef) * e.lr_scale, bc2_sqrt = __ldg(coef + 1);
   const int64_t e0 = (blk - e.first_block) * 1024 + (int64_t)threadIdx.x * 4;
   if (e0 >= e.n) return;
   float* p = e.param; const float* g = e.grad; float* m = e.exp_avg; float* v = e.exp_avg_sq;

@@ -662,16 +662,36 @@ class LRTTensorCoreTrainer:
 
 
 class MultiTensorAdam:
-    """torch.optim.Adam(params, lr, betas, eps) (non-amsgrad, no weight decay; MNF:352, MF:520-553 with one learning rate)
-    as ONE launch over the whole parameter list (lbbnn_adam_multi_f32): a device table names every (param, grad, exp_avg,
-    exp_avg_sq) quadruple.  Gradient addresses are whatever autograd produced for this step: eager steps rewrite the table
-    every call; under CUDA-graph capture the addresses (stable in the graph's private pool) are recorded and the table is
-    written once after the capture (`finish_capture`)."""
+    """torch.optim.Adam(params, lr, betas, eps) (non-amsgrad, no weight decay) as ONE launch over the whole parameter list
+    (lbbnn_adam_multi_f32): a device table names every (param, grad, exp_avg, exp_avg_sq, lr) record.  `params` is what
+    torch.optim takes: an iterable of tensors (MNF:352) or of parameter-group dicts {"params": ..., "lr": ...} -- the MF
+    script's 33 groups with learning rates from 1e-5 to 0.1 (MF:520-553; `lbbnn.mf.reference_param_groups(net)`).  A
+    group without "lr" uses the optimizer's.  Gradient addresses are whatever autograd produced for this step: eager steps
+    rewrite the table every call; under CUDA-graph capture the addresses (stable in the graph's private pool) are recorded
+    and the table is written once after the capture (`finish_capture`)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
-        self.params = [p for p in params if p.requires_grad]
-        dev = self.params[0].device
         self.lr, self.betas, self.eps = float(lr), (float(betas[0]), float(betas[1])), float(eps)
+        params = list(params)
+        groups = params if (params and isinstance(params[0], dict)) else [{"params": params}]
+        self.param_groups = []
+        self.params, self.lr_scale = [], []
+        seen = set()
+        # the launch takes ONE base learning rate (bias correction folded in on the device); groups carry a factor
+        lrs = [float(g.get("lr", self.lr)) for g in groups]
+        self.base_lr = self.lr if self.lr != 0.0 else (max(lrs) or 1.0)
+        for g, glr in zip(groups, lrs):
+            ps = g["params"]
+            ps = [ps] if torch.is_tensor(ps) else list(ps)
+            self.param_groups.append({"params": ps, "lr": glr})
+            for p in ps:
+                if id(p) in seen:
+                    raise ValueError("some parameters appear in more than one parameter group")
+                seen.add(id(p))
+                if p.requires_grad:
+                    self.params.append(p)
+                    self.lr_scale.append(glr / self.base_lr)
+        dev = self.params[0].device
         offs, total = [], 0
         for p in self.params:
             offs.append(total)
@@ -679,7 +699,7 @@ class MultiTensorAdam:
         self.offs = offs
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.table = torch.zeros(len(self.params), 6, dtype=torch.int64, device=dev)
+        self.table = torch.zeros(len(self.params), 7, dtype=torch.int64, device=dev)
         self.coef = torch.zeros(2, dtype=torch.float32, device=dev)
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)      # 1-based index of the update being applied
         self._pending = None
@@ -692,16 +712,18 @@ class MultiTensorAdam:
                 p.grad.zero_()
 
     def _rows(self):
+        import struct
         rows, blocks = [], 0
-        for p, off in zip(self.params, self.offs):
+        for p, off, sc in zip(self.params, self.offs, self.lr_scale):
             g = p.grad
             if g is None:
                 continue
             if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
                 raise K.LbbnnError("MultiTensorAdam needs contiguous fp32 parameters and gradients")
             n = p.numel()
+            lr_bits = struct.unpack("<q", struct.pack("<ff", sc, 0.0))[0]       # {float lr_scale; float reserved}
             rows.append([p.data_ptr(), g.data_ptr(), self.exp_avg.data_ptr() + 4 * off,
-                         self.exp_avg_sq.data_ptr() + 4 * off, n, blocks])
+                         self.exp_avg_sq.data_ptr() + 4 * off, n, blocks, lr_bits])
             blocks += (n + 1023) // 1024
         return rows, blocks
 
@@ -717,7 +739,7 @@ class MultiTensorAdam:
             self.table[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))
         st = K.current_stream()
         K.check(K.lib.lbbnn_counter_inc(K.ptr(self.t_dev, torch.int64), st))
-        K.check(K.lib.lbbnn_adam_multi_f32(self.table.data_ptr(), len(rows), blocks, self.lr, self.betas[0], self.betas[1],
+        K.check(K.lib.lbbnn_adam_multi_f32(self.table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0], self.betas[1],
                                            self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
 
     def finish_capture(self):
@@ -737,9 +759,11 @@ class GraphedTrainer:
     optimizer is MultiTensorAdam by default: one launch instead of torch's ~40 multi_tensor_apply launches per step."""
 
     def __init__(self, net, batch_size, num_batches, objective="kl", lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 in_features=None, optimizer=None):
+                 in_features=None, optimizer=None, param_groups=None):
         """optimizer: None = MultiTensorAdam (one launch for all parameters); "torch" = torch.optim.Adam(capturable=True);
-        or any capturable torch optimizer instance over net.parameters()."""
+        or any capturable torch optimizer instance over net.parameters().
+        param_groups: torch.optim-style parameter groups with their own learning rates (the MF script's 33 groups,
+        MF:520-553: `lbbnn.mf.reference_param_groups(net)`), for the first two optimizer choices."""
         K.require_device()
         self.net, self.B, self.num_batches, self.objective = net, int(batch_size), num_batches, objective
         params = list(net.parameters())
@@ -752,9 +776,10 @@ class GraphedTrainer:
         self.y = torch.zeros(self.B, dtype=torch.int64, device=dev)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         if optimizer is None:
-            self.opt = MultiTensorAdam(params, lr=lr, betas=betas, eps=eps)
+            self.opt = MultiTensorAdam(param_groups if param_groups is not None else params, lr=lr, betas=betas, eps=eps)
         elif isinstance(optimizer, str) and optimizer == "torch":
-            self.opt = torch.optim.Adam(params, lr=lr, betas=betas, eps=eps, capturable=True)
+            self.opt = torch.optim.Adam(param_groups if param_groups is not None else params, lr=lr, betas=betas, eps=eps,
+                                        capturable=True)
         else:
             self.opt = optimizer
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)      # [loss, nll]

@@ -655,6 +655,19 @@ class MCPredictor:
 # The reference computes these with a device -> host NumPy round trip per MC sample (MF:376-396, 427-433, 612-637).  They
 # are plain reductions over the inclusion probabilities and Bernoulli masks, so they stay torch expressions here (no
 # custom kernel: nothing on the hot path), run wherever the parameters live and touch the host once, at the end.
+def reference_param_groups(net):
+    """The 33 optimizer groups of the MF script (MF:520-553), in its order: lr 1e-4 for bias_mu, bias_rho, weight_mu,
+    weight_rho; 1e-3 for pa, pb; 1e-5 for weight_a, weight_b, bias_a, bias_b; 0.1 for lambdal.  Feed to torch.optim.Adam,
+    lbbnn.MultiTensorAdam or GraphedTrainer(param_groups=..., lr=1e-4)."""
+    groups = []
+    for names, lr in ((("bias_mu", "bias_rho", "weight_mu", "weight_rho"), 1e-4), (("pa", "pb"), 1e-3),
+                      (("weight_a", "weight_b", "bias_a", "bias_b"), 1e-5), (("lambdal",), 0.1)):
+        for name in names:
+            for l in net.layers:
+                groups.append({"params": getattr(l, name), "lr": lr})
+    return groups
+
+
 def refresh_inclusion(net):
     """alpha = 1 / (1 + exp(-lambdal)) for every layer and its `.gamma`, and `.gamma.exact = True` -- what the driver does
     before `test_ensemble` (MF:612-625)."""

@@ -981,7 +981,9 @@ def run_module(args):
     px, py = px_h.to(dev), py_h.to(dev)
     tr = None
     if args.eager:
-        opt = (torch.optim.AdamW(net.parameters(), lr=1e-4) if kind == "vd_mnist" else torch.optim.Adam(net.parameters(), lr=1e-3))
+        opt = (torch.optim.AdamW(net.parameters(), lr=1e-4) if kind == "vd_mnist" else
+               torch.optim.Adam(lbbnn.mf.reference_param_groups(net), lr=1e-4) if kind == "mf_mnist" else
+               torch.optim.Adam(net.parameters(), lr=1e-3))
 
         def dev_step(x, y):
             opt.zero_grad(set_to_none=True)
@@ -1002,8 +1004,11 @@ def run_module(args):
         if kind == "vd_mnist":      # C-ABI calls on preallocated buffers (no autograd), captured once
             tr = lbbnn.vd.VDTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-4)
         else:
-            tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3,
-                                      objective="kl" if kind == "mnf_mnist" else "elbo")
+            if kind == "mf_mnist":   # the reference's own optimizer: 33 parameter groups, lr 1e-5 .. 0.1 (MF:520-553)
+                tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-4, objective="elbo",
+                                          param_groups=lbbnn.mf.reference_param_groups(net))
+            else:
+                tr = lbbnn.GraphedTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, objective="kl")
 
         def dev_step(x, y):
             tr.x.copy_(x, non_blocking=True)

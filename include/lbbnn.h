@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define LBBNN_ABI_VERSION 1
+#define LBBNN_ABI_VERSION 2
 
 enum { LBBNN_OK = 0, LBBNN_ERR_INVALID = -1, LBBNN_ERR_CUDA = -2, LBBNN_ERR_UNSUPPORTED = -3 };
 
@@ -443,10 +443,12 @@ LBBNN_API int lbbnn_adam_prepare(const int64_t* step_dev, float lr, float beta1,
 LBBNN_API int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* layer, const float* dM, const float* dV, const float* colsum,
                                           const lbbnn_priors* priors, int var_mode, int flags, const float* kl_grad_dev,
                                           float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s);
-/* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF / MF scripts,
- * MNF:352, MF:520-553 with one learning rate): table_dev = device array of n_entries records; block b of the launch
- * updates elements [(b - first_block) * 1024, +1024) of the tensor with the largest first_block <= b, so first_block
- * is the running sum of ceil(n / 1024) and total_blocks its final value. */
+/* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF script, MNF:352,
+ * and the 33 per-tensor parameter groups of the MF script, MF:520-553: learning rates 1e-4 for weights / biases, 1e-3
+ * for pa / pb, 1e-5 for the Gamma hyper-parameters, 0.1 for lambdal): table_dev = device array of n_entries records;
+ * block b of the launch updates elements [(b - first_block) * 1024, +1024) of the tensor with the largest
+ * first_block <= b, so first_block is the running sum of ceil(n / 1024) and total_blocks its final value.  Each entry's
+ * learning rate is lr * lr_scale (its parameter group's lr relative to the call's). */
 typedef struct lbbnn_adam_entry {
   float* param;
   const float* grad;
@@ -454,6 +456,8 @@ typedef struct lbbnn_adam_entry {
   float* exp_avg_sq;
   int64_t n;
   int64_t first_block;
+  float lr_scale;
+  float reserved;
 } lbbnn_adam_entry;
 LBBNN_API int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
                                    float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,

@@ -39,7 +39,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib_path):
 
 def test_host_only_queries_work_without_a_gpu(lib_path):
     from lbbnn import _capi as K
-    assert K.lib.lbbnn_abi_version() == 1
+    assert K.lib.lbbnn_abi_version() == 2
     assert K.lib.lbbnn_lrt_f32_workspace_bytes(100, 784, 400) > 0
     assert K.lib.lbbnn_lrt_f32_workspace_bytes(0, 784, 400) == 0
     # the fused-step scheduler is host code: every phase of the MNIST stack fits one round of the persistent grid (2 CTAs per SM)

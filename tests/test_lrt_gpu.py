@@ -315,3 +315,39 @@ def test_multi_tensor_adam_matches_torch_adam(lb):
         for p, q in zip(ps, qs):
             assert C.rel_err(p.detach(), q.detach()) < 1e-6
     assert torch.equal(unused.detach(), u0) and int(ours.t_dev) == 5
+
+
+def test_multi_tensor_adam_parameter_groups_match_torch_adam(lb):
+    """f1: per-group learning rates.  The MF script's 33 parameter groups (MF:520-553: 1e-4 weights / biases, 1e-3 pa / pb,
+    1e-5 Gamma hyper-parameters, 0.1 lambdal) through MultiTensorAdam (per-row lr in the device table) against
+    torch.optim.Adam with the same groups, five steps of random gradients; plus a zero-lr group and a default-lr group."""
+    torch.manual_seed(6)
+    nets = [lb.mf.BayesianNetwork((72, 40, 24, 10)).cuda() for _ in range(2)]
+    nets[1].load_state_dict(nets[0].state_dict())
+    groups = [lb.mf.reference_param_groups(n) for n in nets]
+    assert len(groups[0]) == 33 and sorted({g["lr"] for g in groups[0]}) == [1e-5, 1e-4, 1e-3, 0.1]
+    assert {id(p) for g in groups[0] for p in [g["params"]]} == {id(p) for p in nets[0].parameters()}
+    ours = lb.MultiTensorAdam(groups[0], lr=1e-4)
+    ref = torch.optim.Adam(groups[1], lr=1e-4)
+    for step in range(5):
+        for p, q in zip(nets[0].parameters(), nets[1].parameters()):
+            g = torch.randn_like(p) * (10.0 ** (step - 2))
+            p.grad, q.grad = g.clone(), g.clone()
+        ours.step()
+        ref.step()
+        for (name, p), q in zip(nets[0].named_parameters(), nets[1].parameters()):
+            assert C.rel_err(p.detach(), q.detach()) < 1e-6, (step, name)
+    # a frozen group (lr 0), a group that inherits the optimizer's lr, base lr 0 (GraphedTrainer's noise-only test uses it)
+    ps = [torch.nn.Parameter(torch.randn(n, device="cuda")) for n in (5, 1030, 64)]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    mk = lambda t: [{"params": [t[0]], "lr": 0.0}, {"params": [t[1]]}, {"params": t[2], "lr": 0.05}]  # noqa: E731
+    for base in (1e-2, 0.0):
+        ours, ref = lb.MultiTensorAdam(mk(ps), lr=base), torch.optim.Adam(mk(qs), lr=base)
+        for step in range(3):
+            for p, q in zip(ps, qs):
+                g = torch.randn_like(p)
+                p.grad, q.grad = g.clone(), g.clone()
+            ours.step()
+            ref.step()
+        for p, q in zip(ps, qs):
+            assert C.rel_err(p.detach(), q.detach()) < 1e-6

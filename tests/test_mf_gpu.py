@@ -134,11 +134,17 @@ def test_mf_mnist_sample_elbo_matches_reference(lb):
             assert torch.isfinite(getattr(l, k).grad).all(), k
 
 
-def _oracle_mc(net_params, x, seed, samples, lb, first=0):
-    """Oracle predictive average fed with the kernels' exported Philox noise for sample indices first.."""
+def _oracle_mc(net_params, x, seed, samples, lb, first=0, device="cpu", dtype=torch.float32):
+    """Oracle predictive average fed with the kernels' exported Philox noise for sample indices first...  device / dtype:
+    where and in which precision the oracle's torch expressions run (fp32 on the CPU = what the reference computes;
+    fp64 = the truth both fp32 implementations are judged against).  The hard masks [u < alpha] are always formed from
+    the fp32 alpha and the fp32 uniform, as the kernels (and torch.bernoulli) do."""
     L = len(net_params)
     stride = lb.mf.MCPredictor.NSTREAMS * L
-    sum_logp = torch.zeros(x.shape[0], net_params[-1]["weight_mu"].shape[0], dtype=torch.float64)
+    alphas = [O.alpha_of(p["lambdal"]) for p in net_params]          # fp32 on the CPU: the reference's own arithmetic
+    net_params = [{k: v.to(device=device, dtype=dtype) for k, v in p.items()} for p in net_params]
+    x = x.to(device=device, dtype=dtype)
+    sum_logp = torch.zeros(x.shape[0], net_params[-1]["weight_mu"].shape[0], dtype=torch.float64, device=device)
     sum_prob = torch.zeros_like(sum_logp)
     for s in range(first, first + samples):
         h = x
@@ -146,9 +152,9 @@ def _oracle_mc(net_params, x, seed, samples, lb, first=0):
             o, k = p["weight_mu"].shape
             base = i * lb.mf.MCPredictor.NSTREAMS + s * stride
             u = lb.philox_uniform((o, k), seed, base + 0).cpu()
-            ew = lb.philox_normal((o, k), seed, base + 1).cpu()
-            eb = lb.philox_normal((o,), seed, base + 2).cpu()
-            g = O.exact_bernoulli_sample(O.alpha_of(p["weight_mu"] * 0 + p["lambdal"]), u)
+            ew = lb.philox_normal((o, k), seed, base + 1).to(device=device, dtype=dtype)
+            eb = lb.philox_normal((o,), seed, base + 2).to(device=device, dtype=dtype)
+            g = O.exact_bernoulli_sample(alphas[i], u).to(device=device, dtype=dtype)
             h, _, _ = O.mf_forward(h, p, g, {"eps_w": ew, "eps_b": eb}, calc_log_probs=False)
             h = torch.relu(h) if i < L - 1 else torch.log_softmax(h, 1)
         sum_logp += h.double()
@@ -190,6 +196,48 @@ def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl, 
         tot_p += mc.sum_prob
     assert (tot_l - res["mean_logp"] * S).abs().max().item() < 1e-9
     assert torch.equal((tot_l / S).argmax(1), res["pred"])
+
+
+@pytest.mark.parametrize("gemm", ["auto", "simt"])
+def test_mc_predictor_at_the_real_shape_matches_oracle(lb, gemm):
+    """BASELINE.json configs[3] at its real shape: the MF 784-400-600-10 net (reference init, UN-scaled weight_mu,
+    inclusion probabilities spread over (0,1)), a 1000-input test batch, 64 MC weight samples, default launch
+    configuration (3xTF32 tcgen05 GEMMs + fused head, two lanes) and the CUDA-core configuration -- against the oracle
+    driven by the kernels' exported Philox draws, in fp64 (the truth).  Accumulators within 1e-5; ensemble argmax
+    bit-exact on every row whose top-2 margin exceeds the fp32 tolerance (near-tie rows are counted and reported)."""
+    case = C.mf_net_case(seed=63, batch=1000)
+    rng = np.random.default_rng(3)
+    for p in case["layers"]:
+        p["lambdal"] = C.t(rng.normal(0.0, 2.0, size=tuple(p["lambdal"].shape)))
+    net = lb.mf.BayesianNetwork().cuda()
+    with torch.no_grad():
+        for l, p in zip(net.layers, case["layers"]):
+            for k, v in p.items():
+                getattr(l, k).copy_(v)
+    S = 64
+    mc = lb.mf.MCPredictor(net, batch=1000, seed=4321, samples_per_launch=32, gemm=gemm)
+    assert mc.n_tc == (2 if gemm == "auto" else 0) and mc.fused_head
+    res = mc.predict(case["x"].cuda(), S)
+    ref_logp, ref_prob = _oracle_mc(case["layers"], case["x"], 4321, S, lb, device="cuda", dtype=torch.float64)
+    e_l, e_p = C.rel_err(mc.sum_logp, ref_logp), C.rel_err(mc.sum_prob, ref_prob)
+    mean_ref = ref_logp / S
+    top2 = mean_ref.topk(2, dim=1).values
+    margin = (top2[:, 0] - top2[:, 1])
+    near_tie = margin < 2e-5 * mean_ref.abs().max()
+    agree = res["pred"] == mean_ref.argmax(1)
+    print(f"[real-shape] MCPredictor {gemm}: sum_logp err {e_l:.2e}, sum_prob err {e_p:.2e}, near-tie rows {int(near_tie.sum())}, "
+          f"smallest margin {margin.min().item():.3e}, argmax mismatches {int((~agree).sum())}", flush=True)
+    assert e_l < 1e-5 and e_p < 1e-5
+    assert bool((agree | near_tie).all()) and int(near_tie.sum()) <= 2
+    # the reference's ensemble statistic: the first ten samples only (MF:416)
+    first_logp, _ = _oracle_mc(case["layers"], case["x"], 4321, 10, lb, device="cuda", dtype=torch.float64)
+    t2 = (first_logp / 10).topk(2, dim=1).values
+    tie10 = (t2[:, 0] - t2[:, 1]) < 2e-5 * first_logp.abs().max() / 10
+    assert bool(((res["pred_first"] == first_logp.argmax(1)) | tie10).all()) and int(tie10.sum()) <= 2
+    # and the fp32 reference arithmetic on the CPU (what the reference itself computes) for the first samples
+    cpu_logp, _ = _oracle_mc(case["layers"], case["x"], 4321, 4, lb)
+    mc.run(case["x"].cuda(), 4)
+    assert C.rel_err(mc.sum_logp, cpu_logp) < 1e-5
 
 
 def test_mc_predictor_batched_equals_one_sample_kernels(lb):
