@@ -541,6 +541,7 @@ struct FinalizeArgs {
   const float *dM, *dV, *colsum;
   int64_t N, K;
   int var_mode, sample, accumulate;
+  int bias_only;                   // skip the weights (their update ran in the dW GEMM's epilogue)
   const float* klg_dev;
   float klg_host;
   lbbnn_priors pri;
@@ -571,7 +572,7 @@ __device__ __forceinline__ void adam_quad(float* __restrict__ p, float* __restri
 
 template <bool ADAM>
 __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs a) {
-  const int64_t n = a.N * a.K;
+  const int64_t n = a.bias_only ? 0 : a.N * a.K;
   const bool vec = (n % 4 == 0) && (a.K % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
                    aligned16(a.dM) && aligned16(a.dV) && aligned16(a.dmu) && aligned16(a.drho) && aligned16(a.dlam);
   const float klg = (a.klg_dev ? __ldg(a.klg_dev) : 1.0f) * a.klg_host;
@@ -973,6 +974,7 @@ extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, in
   if (int rc = check_launch("lrt_f32_bwd_w_gemm")) return rc;
 
   FinalizeArgs f;
+  f.bias_only = 0;
   f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.z_kl = L->z_kl; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
   f.dM = a.dM; f.dV = a.dV; f.colsum = a.colsum; f.N = N; f.K = K;
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
@@ -1050,6 +1052,7 @@ extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, con
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
   LBBNN_REQUIRE(!sample || dV, "sample branch needs dV");
   FinalizeArgs f;
+  f.bias_only = 0;
   f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = L->z; f.z_kl = L->z_kl; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
   f.dM = dM; f.dV = dV ? dV : dM; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
@@ -1069,6 +1072,7 @@ extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM
   const bool sample = flags & LBBNN_FLAG_SAMPLE;
   LBBNN_REQUIRE(!sample || dV, "sample branch needs dV");
   FinalizeArgs f;
+  f.bias_only = 0;
   f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = nullptr; f.z_kl = nullptr; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
   f.dM = dM; f.dV = dV ? dV : dM; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = 0;
@@ -1077,6 +1081,23 @@ extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM
   f.adam = *adam;
   lrt_f32_finalize<true><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize_adam");
+}
+
+extern "C" int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* L, const float* colsum, const lbbnn_priors* pri, int flags,
+                                                float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(colsum && pri && adam && adam->coef, "NULL argument");
+  for (int i = 3; i < 5; ++i) LBBNN_REQUIRE(adam->exp_avg[i] && adam->exp_avg_sq[i], "NULL Adam state %d", i);
+  FinalizeArgs f;
+  f.bias_only = 1;
+  f.mu = L->weight_mu; f.rho = L->weight_rho; f.lam = L->lambdal; f.z = nullptr; f.z_kl = nullptr; f.bias_mu = L->bias_mu; f.bias_rho = L->bias_rho;
+  f.dM = nullptr; f.dV = nullptr; f.colsum = colsum; f.N = L->out_features; f.K = L->in_features;
+  f.var_mode = 0; f.sample = (flags & LBBNN_FLAG_SAMPLE) ? 1 : 0; f.accumulate = 0;
+  f.klg_dev = nullptr; f.klg_host = kl_grad_host; f.pri = *pri;
+  f.dmu = f.drho = f.dlam = f.dbmu = f.dbrho = f.dz = f.dz_kl = nullptr;
+  f.adam = *adam;
+  lrt_f32_finalize<true><<<1, kThreads, 0, (cudaStream_t)s>>>(f);
+  return check_launch("lrt_f32_finalize_adam_bias");
 }
 
 // ---- plain linear layer on the same kernels (mean-branch GEMM: E only) ---------------------------------

@@ -2,12 +2,16 @@
 //
 //   D1[m,n] = sum_k A1[m,k] B1[n,k]        D2[m,n] = sum_k A2[m,k] B2[n,k]
 //
-// All four operands are K-major bf16 (row-major (rows, K)); both accumulators are fp32 in TMEM and
+// Operands are bf16, each either K-major (row-major (rows, K)) or MN-major (row-major (K, rows): the transposed view of
+// a tensor that is stored with the contraction index as its ROW index); both accumulators are fp32 in TMEM and
 // meet in ONE epilogue.  This is the LRT hot op (LBBNN-GP-MF-LRT.py:172-175: two torch.mm + the
 // sqrt/eps FMA) and, with the operands re-bound, both backward GEMM pairs:
-//   forward   A = (x, x^2)        B = (M, V)          epilogue: act = D1 + b_mu + sqrt(D2 + s_b^2) eps
-//   dX        A = (dE, dS)        B = (M^T, V^T)      epilogue: dx = D1 + 2 x D2, relu mask, next dE/dS
-//   dW        A = (dE^T, dS^T)    B = (x^T, x^2^T)    epilogue: dM = D1, dV = D2 (fp32, for finalize)
+//   forward   A = (x, x^2)   K-major    B = (M, V)     K-major    epilogue: act = D1 + b_mu + sqrt(D2 + s_b^2) eps
+//   dX        A = (dE, dS)   K-major    B = (M, V)     MN-major   epilogue: dx = D1 + 2 x D2, relu mask, next dE/dS, bias sums
+//   dW        A = (dE, dS)   MN-major   B = (x, x^2)   MN-major   epilogue: dM = D1, dV = D2 -> chain rule + KL + Adam
+// The MN-major forms read the SAME row-major tensors the other GEMMs use (TMA boxes of 64 contraction rows x 64 elements,
+// tcgen05 "MN-major" canonical SWIZZLE_128B layout), so no transposed copy of an activation, gradient or weight moment is
+// ever written.  (K-major transposed operands are still accepted: the r01 entry points and the tests use them.)
 //
 // Kernel shape: persistent, one CTA per SM, 320 threads =
 //   warp 0      TMA producer   (cp.async.bulk.tensor.2d, SWIZZLE_128B, 4 boxes of 128x64 bf16 per stage)
@@ -22,6 +26,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "lrt_chain.cuh"
 #include "tc_ptx.cuh"
 
 namespace lbbnn {
@@ -41,19 +46,43 @@ constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*
 
 using namespace tc;
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at bit 17, M>>4 at bit 24
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, a_major / b_major (0 = K-major, 1 = MN-major) at bits 15 / 16,
+// N>>3 at bit 17, M>>4 at bit 24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+
+// MN-major operand tile in shared memory: TMA boxes of (64 contraction rows) x (64 elements = 128 B), SWIZZLE_128B, one
+// box per 64 elements of the M / N extent, boxes kMnBoxBytes apart.  In tcgen05's canonical MN-major SWIZZLE_128B layout
+// ((8,n),(8,k)) : ((1,LBO),(8,SBO)) in 16-byte units that is SBO = 1024 B (8 contraction rows) and LBO = one box; one MMA
+// (K = 16) spans two 8-row groups, so consecutive MMAs start 2048 B apart.
+constexpr int kMnBoxBytes = 64 * 128;           // 8 KB
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(kMnBoxBytes >> 4) << 16;      // LBO: next 64 elements along M / N
+  d |= (uint64_t)(1024 >> 4) << 32;             // SBO: next 8 rows along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int mn) {
+  return mn ? umma_desc_mn_sw128(smem_addr) : umma_desc_kmajor_sw128(smem_addr);
+}
+// descriptor advance (in 16-byte units) from one K = 16 MMA to the next
+__device__ __forceinline__ uint64_t umma_kstep(int mn) { return mn ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -74,15 +103,76 @@ struct TcEpi {
   const __nv_bfloat16* x_bf;                             // (M,N): the input this dx belongs to
   const float* dsf_prev;                                 // (M,N): ds factor of the layer that produced x
   __nv_bfloat16 *de, *ds, *deT, *dsT;                    // next (previous-layer) dE, dS and transposes
+  float* colsum_part;                                    // optional [ceil(M/32)][2N]: per-32-row sums of dE | dS (fp32)
+  // DW_ADAM: (M,N) = (out,in); chain rule + KL gradient + Adam on the accumulators, parameters updated in place
+  float *p_mu, *p_rho, *p_lam;
+  float *m_mu, *m_rho, *m_lam, *v_mu, *v_rho, *v_lam;
+  const float* coef;
+  lbbnn_priors pri;
+  int var_mode;
+  float klg, beta1, beta2, adam_eps;
+  // operand majors
+  int a_mn, b_mn;
 };
 
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+
+// fused dW epilogue: 16 consecutive weights of one output row (N % 4 == 0)
+__device__ __forceinline__ void dw_adam_chunk(const TcEpi& e, const chain::Consts& cc, int64_t N, int64_t row, int64_t col0,
+                                              const float d1[EW], const float d2[EW]) {
+#pragma unroll
+  for (int j = 0; j < EW; j += 4) {
+    if (col0 + j >= N) break;
+    const int64_t off = row * N + col0 + j;
+    const float4 mu4 = ld4(e.p_mu + off), rho4 = ld4(e.p_rho + off), lam4 = ld4(e.p_lam + off);
+    const float4 mm4 = ld4(e.m_mu + off), mr4 = ld4(e.m_rho + off), ml4 = ld4(e.m_lam + off);
+    const float4 vm4 = ld4(e.v_mu + off), vr4 = ld4(e.v_rho + off), vl4 = ld4(e.v_lam + off);
+    float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rho[4] = {rho4.x, rho4.y, rho4.z, rho4.w}, lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w};
+    float mm[4] = {mm4.x, mm4.y, mm4.z, mm4.w}, mr[4] = {mr4.x, mr4.y, mr4.z, mr4.w}, ml[4] = {ml4.x, ml4.y, ml4.z, ml4.w};
+    float vm[4] = {vm4.x, vm4.y, vm4.z, vm4.w}, vr[4] = {vr4.x, vr4.y, vr4.z, vr4.w}, vl[4] = {vl4.x, vl4.y, vl4.z, vl4.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float gm, gr, gl;
+      chain::grads(cc, mu[t], rho[t], lam[t], d1[j + t], d2[j + t], gm, gr, gl);
+      chain::adam(cc, mu[t], mm[t], vm[t], gm);
+      chain::adam(cc, rho[t], mr[t], vr[t], gr);
+      chain::adam(cc, lam[t], ml[t], vl[t], gl);
+    }
+    st4(e.p_mu + off, mu[0], mu[1], mu[2], mu[3]); st4(e.p_rho + off, rho[0], rho[1], rho[2], rho[3]);
+    st4(e.p_lam + off, lam[0], lam[1], lam[2], lam[3]);
+    st4(e.m_mu + off, mm[0], mm[1], mm[2], mm[3]); st4(e.m_rho + off, mr[0], mr[1], mr[2], mr[3]);
+    st4(e.m_lam + off, ml[0], ml[1], ml[2], ml[3]);
+    st4(e.v_mu + off, vm[0], vm[1], vm[2], vm[3]); st4(e.v_rho + off, vr[0], vr[1], vr[2], vr[3]);
+    st4(e.v_lam + off, vl[0], vl[1], vl[2], vl[3]);
+  }
+}
+
+// sum of 32 per-lane values over the 32 lanes of a warp: lane l ends with the total of vals[l] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_sum32(float (&vals)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = lane & s;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const float send = up ? vals[i] : vals[i + s];
+      const float keep = up ? vals[i + s] : vals[i];
+      vals[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return vals[0];
+}
+
 // one thread = one output row (TMEM lane), EW consecutive columns; sbias = this tile's b_mu[BN] | sigma_b^2[BN]
-__device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, int64_t M, int64_t N, int64_t row, int64_t col0,
-                                               const float* __restrict__ sbias, int cl, const float d1[EW],
-                                               const float d2[EW]) {
-  if (row >= M) return;
+template <int MODE>
+__device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, const chain::Consts& cc, int64_t M, int64_t N,
+                                               int64_t row, int64_t col0, const float* __restrict__ sbias, int cl,
+                                               const float d1[EW], const float d2[EW]) {
+  const bool row_ok = row < M;
+  if (!row_ok && !(MODE == LBBNN_TC_EPI_DX && e.colsum_part)) return;      // (the bias sums below shuffle across the warp)
+  if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) { dw_adam_chunk(e, cc, N, row, col0, d1, d2); return; }
   const bool fullc = col0 + EW - 1 < N;
-  if (e.mode == LBBNN_TC_EPI_RAW) {
+  if constexpr (MODE == LBBNN_TC_EPI_RAW) {
     float* p1 = e.d1 + row * N + col0;
     float* p2 = e.d2 + row * N + col0;
     if (fullc && (N % 4 == 0)) {
@@ -99,7 +189,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     return;
   }
   float o[EW], o2[EW];
-  if (e.mode == LBBNN_TC_EPI_FWD) {
+  if constexpr (MODE == LBBNN_TC_EPI_FWD) {
     // act = D1 + b_mu + sqrt(D2 + sigma_b^2) eps  (LRT:172-175); ds factor = eps / (2 sd)
     float ep[EW];
     if (nz.ptr) {
@@ -172,9 +262,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
     }
     return;
   }
-  // LBBNN_TC_EPI_DX: dx = D1 + 2 x D2; through the relu that produced x; dS_prev = dx * dsf_prev
+  if constexpr (MODE == LBBNN_TC_EPI_DX) {
+  // dx = D1 + 2 x D2; through the relu that produced x; dS_prev = dx * dsf_prev
   float xv[EW], fv[EW];
-  if (fullc && (N % 8 == 0)) {
+  if (!row_ok) {
+#pragma unroll
+    for (int j = 0; j < EW; ++j) { xv[j] = 0.f; fv[j] = 0.f; }
+  } else if (fullc && (N % 8 == 0)) {
 #pragma unroll
     for (int j = 0; j < EW; j += 8) {
       const uint4 u = *reinterpret_cast<const uint4*>(e.x_bf + row * N + col0 + j);
@@ -202,9 +296,21 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
   for (int j = 0; j < EW; ++j) {
     float g = fmaf(2.0f * xv[j], d2[j], d1[j]);
     if ((e.flags & LBBNN_FLAG_MASK_DX) && !(xv[j] > 0.f)) g = 0.f;
+    if (!row_ok || col0 + j >= N) g = 0.f;
     o[j] = g;
     o2[j] = g * fv[j];
   }
+  if (e.colsum_part) {          // bias gradients of the layer below: sums over this warp's 32 rows, fp32, fixed order
+    float vals[32];
+#pragma unroll
+    for (int j = 0; j < EW; ++j) { vals[j] = o[j]; vals[EW + j] = o2[j]; }
+    const int lane = threadIdx.x & 31;
+    const float tot = warp_transpose_sum32(vals, lane);
+    const int64_t c = col0 + (lane & (EW - 1));
+    const int64_t row0 = row - lane;                      // first row of this warp's 32-row group (always < M)
+    if (row0 < M && c < N) e.colsum_part[(row0 >> 5) * (2 * N) + (lane < EW ? 0 : N) + c] = tot;
+  }
+  if (!row_ok) return;
   if (fullc && (N % 8 == 0)) {
 #pragma unroll
     for (int j = 0; j < EW; j += 8) {
@@ -230,6 +336,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
         e.dsT[(col0 + j) * M + row] = __float2bfloat16_rn(o2[j]);
       }
   }
+  }
 }
 
 // ---- tile order -----------------------------------------------------------------------------------
@@ -249,6 +356,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
@@ -291,10 +399,26 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
-          tma_load_2d(sa + 0 * kTileBytes, &tmA1, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + 1 * kTileBytes, &tmA2, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + 2 * kTileBytes, &tmB1, &full_bar[stage], kb * BK, n0);
-          tma_load_2d(sa + 3 * kTileBytes, &tmB2, &full_bar[stage], kb * BK, n0);
+          if (!epi.a_mn) {
+            tma_load_2d(sa + 0 * kTileBytes, &tmA1, &full_bar[stage], kb * BK, m0);
+            tma_load_2d(sa + 1 * kTileBytes, &tmA2, &full_bar[stage], kb * BK, m0);
+          } else {   // (K, M) row-major: two boxes of 64 rows of K x 64 elements of M per operand
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d(sa + 0 * kTileBytes + h * kMnBoxBytes, &tmA1, &full_bar[stage], m0 + 64 * h, kb * BK);
+              tma_load_2d(sa + 1 * kTileBytes + h * kMnBoxBytes, &tmA2, &full_bar[stage], m0 + 64 * h, kb * BK);
+            }
+          }
+          if (!epi.b_mn) {
+            tma_load_2d(sa + 2 * kTileBytes, &tmB1, &full_bar[stage], kb * BK, n0);
+            tma_load_2d(sa + 3 * kTileBytes, &tmB2, &full_bar[stage], kb * BK, n0);
+          } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d(sa + 2 * kTileBytes + h * kMnBoxBytes, &tmB1, &full_bar[stage], n0 + 64 * h, kb * BK);
+              tma_load_2d(sa + 3 * kTileBytes + h * kMnBoxBytes, &tmB2, &full_bar[stage], n0 + 64 * h, kb * BK);
+            }
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -303,6 +427,8 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
+      const uint32_t idesc = make_idesc(BM, BN, epi.a_mn, epi.b_mn);
+      const uint64_t ka = umma_kstep(epi.a_mn), kbs = umma_kstep(epi.b_mn);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator stage
@@ -312,14 +438,14 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t a1 = umma_desc_kmajor_sw128(sa + 0 * kTileBytes), a2 = umma_desc_kmajor_sw128(sa + 1 * kTileBytes);
-          const uint64_t b1 = umma_desc_kmajor_sw128(sa + 2 * kTileBytes), b2 = umma_desc_kmajor_sw128(sa + 3 * kTileBytes);
+          const uint64_t a1 = umma_desc(sa + 0 * kTileBytes, epi.a_mn), a2 = umma_desc(sa + 1 * kTileBytes, epi.a_mn);
+          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, epi.b_mn), b2 = umma_desc(sa + 3 * kTileBytes, epi.b_mn);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance the start address inside the swizzle row
+            // K-major: advance the start address inside the swizzle row; MN-major: by two 8-row groups
             const uint32_t acc = (kb | k) ? 1u : 0u;
-            umma_bf16(d1, a1 + koff, b1 + koff, acc);
-            umma_bf16(d2, a2 + koff, b2 + koff, acc);
+            umma_bf16(d1, a1 + k * ka, b1 + k * kbs, idesc, acc);
+            umma_bf16(d2, a2 + k * ka, b2 + k * kbs, idesc, acc);
           }
           umma_commit(&empty_bar[stage]);                  // frees the smem stage once these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -331,6 +457,9 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ===== epilogue warps (2..9): TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
     Noise nz = epi.noise;
     nz.resolve();
+    chain::Consts cc = {};
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM)
+      cc = chain::make_consts(epi.pri, epi.var_mode, epi.klg, epi.beta1, epi.beta2, epi.adam_eps, epi.coef);
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
     int it = 0;
@@ -340,7 +469,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       tile_coords(t, num_m, num_n, mb, nb);
       const int m0 = mb * BM, n0 = nb * BN;
       float* sbias = sbias_all + as * 2 * BN;
-      if (epi.mode == LBBNN_TC_EPI_FWD) {                 // this tile's bias terms, once per column
+      if constexpr (MODE == LBBNN_TC_EPI_FWD) {                 // this tile's bias terms, once per column
         const int c = et & (BN - 1);
         const int64_t n = n0 + c;
         float v = 0.f;
@@ -361,7 +490,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         tmem_ld16(tbase + c * EW, v1);
         tmem_ld16(tbase + 128 + c * EW, v2);
         const int cl = half * 64 + c * EW;
-        epilogue_chunk(epi, nz, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
       }
       tc_fence_before();
       __syncwarp();
@@ -390,17 +519,16 @@ constexpr int kStages2 = 4;
 constexpr int kBHalfBytes = (BN / 2) * BK * 2;                 // 8 KB: this CTA's 64 rows of a B tile
 constexpr int kStageBytes2 = 2 * kTileBytes + 2 * kBHalfBytes;  // 48 KB
 constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kBiasBytes;
-constexpr uint32_t kIdesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 constexpr int kGroupM2 = kGroupM / 2;                          // in 256-row blocks
 
-__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(kIdesc2), "r"(accumulate)
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 
@@ -413,6 +541,7 @@ __device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int g
   mb2 = m_first + (r - nb * gm);
 }
 
+template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
@@ -459,10 +588,23 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
           uint8_t* sa = smem + stage * kStageBytes2;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
           mbar_expect_tx_cluster(lead_full, kStageBytes2);
-          tma_load_2d_pair(sa, &tmA1, lead_full, kb * BK, m0);
-          tma_load_2d_pair(sa + kTileBytes, &tmA2, lead_full, kb * BK, m0);
-          tma_load_2d_pair(sa + 2 * kTileBytes, &tmB1, lead_full, kb * BK, n0h);
-          tma_load_2d_pair(sa + 2 * kTileBytes + kBHalfBytes, &tmB2, lead_full, kb * BK, n0h);
+          if (!epi.a_mn) {
+            tma_load_2d_pair(sa, &tmA1, lead_full, kb * BK, m0);
+            tma_load_2d_pair(sa + kTileBytes, &tmA2, lead_full, kb * BK, m0);
+          } else {   // (K, M) row-major: two boxes of 64 rows of K x 64 elements of M per operand
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d_pair(sa + h * kMnBoxBytes, &tmA1, lead_full, m0 + 64 * h, kb * BK);
+              tma_load_2d_pair(sa + kTileBytes + h * kMnBoxBytes, &tmA2, lead_full, m0 + 64 * h, kb * BK);
+            }
+          }
+          if (!epi.b_mn) {
+            tma_load_2d_pair(sa + 2 * kTileBytes, &tmB1, lead_full, kb * BK, n0h);
+            tma_load_2d_pair(sa + 2 * kTileBytes + kBHalfBytes, &tmB2, lead_full, kb * BK, n0h);
+          } else {   // this CTA's 64 elements of N: one box
+            tma_load_2d_pair(sa + 2 * kTileBytes, &tmB1, lead_full, n0h, kb * BK);
+            tma_load_2d_pair(sa + 2 * kTileBytes + kBHalfBytes, &tmB2, lead_full, n0h, kb * BK);
+          }
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
         }
       }
@@ -471,6 +613,8 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
     // ===== MMA issuer (leader CTA only) =====
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
+      const uint32_t idesc = make_idesc(2 * BM, BN, epi.a_mn, epi.b_mn);
+      const uint64_t ka = umma_kstep(epi.a_mn), kbs = umma_kstep(epi.b_mn);
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this accumulator stage
@@ -480,15 +624,14 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
-          const uint64_t a1 = umma_desc_kmajor_sw128(sa), a2 = umma_desc_kmajor_sw128(sa + kTileBytes);
-          const uint64_t b1 = umma_desc_kmajor_sw128(sa + 2 * kTileBytes);
-          const uint64_t b2 = umma_desc_kmajor_sw128(sa + 2 * kTileBytes + kBHalfBytes);
+          const uint64_t a1 = umma_desc(sa, epi.a_mn), a2 = umma_desc(sa + kTileBytes, epi.a_mn);
+          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, epi.b_mn);
+          const uint64_t b2 = umma_desc(sa + 2 * kTileBytes + kBHalfBytes, epi.b_mn);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
             const uint32_t acc = (kb | k) ? 1u : 0u;
-            umma_bf16_pair(d1, a1 + koff, b1 + koff, acc);
-            umma_bf16_pair(d2, a2 + koff, b2 + koff, acc);
+            umma_bf16_pair(d1, a1 + k * ka, b1 + k * kbs, idesc, acc);
+            umma_bf16_pair(d2, a2 + k * ka, b2 + k * kbs, idesc, acc);
           }
           umma_commit_pair(&empty_bar[stage], 3);          // frees this stage in BOTH CTAs once the MMAs retire
           if (++stage == kStages2) { stage = 0; phase ^= 1; }
@@ -500,6 +643,9 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
     // ===== epilogue warps (both CTAs, each on its own 128 accumulator rows) =====
     Noise nz = epi.noise;
     nz.resolve();
+    chain::Consts cc = {};
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM)
+      cc = chain::make_consts(epi.pri, epi.var_mode, epi.klg, epi.beta1, epi.beta2, epi.adam_eps, epi.coef);
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
     int it = 0;
@@ -509,7 +655,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       tile_coords2(t, num_m2, num_n, group, mb2, nb);
       const int m0 = mb2 * 2 * BM + (int)rank * BM, n0 = nb * BN;
       float* sbias = sbias_all + as * 2 * BN;
-      if (epi.mode == LBBNN_TC_EPI_FWD) {
+      if constexpr (MODE == LBBNN_TC_EPI_FWD) {
         const int c = et & (BN - 1);
         const int64_t n = n0 + c;
         float v = 0.f;
@@ -530,7 +676,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
         tmem_ld16(tbase + c * EW, v1);
         tmem_ld16(tbase + 128 + c * EW, v2);
         const int cl = half * 64 + c * EW;
-        epilogue_chunk(epi, nz, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
       }
       tc_fence_before();
       __syncwarp();
@@ -580,42 +726,99 @@ int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K, int box
   return LBBNN_OK;
 }
 
+// MN-major operand: the tensor is (K, rows) row-major bf16; box = 64 (rows) x 64 (K), 128B swizzle, OOB -> zeros
+int make_map_mn(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K) {
+  EncodeTiledFn enc = get_encode();
+  LBBNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+  LBBNN_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0 && (rows * 2) % 16 == 0,
+                "MN-major TMA operand must be 16B aligned with a 16B-multiple row pitch (rows %% 8 == 0), rows=%lld", (long long)rows);
+  cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)K};
+  cuuint64_t strides[1] = {(cuuint64_t)rows * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  LBBNN_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (MN-major) failed (%d) rows=%lld K=%lld", (int)r, (long long)rows, (long long)K);
+  return LBBNN_OK;
+}
+
 int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N, int64_t K, const TcEpi& epi,
               cudaStream_t st) {
   LBBNN_REQUIRE(A1 && A2 && B1 && B2 && M > 0 && N > 0 && K > 0, "bad GEMM operands");
   LBBNN_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "GEMM dims must fit int32");
   CUtensorMap mA1, mA2, mB1, mB2;
-  if (int rc = make_map(&mA1, A1, M, K)) return rc;
-  if (int rc = make_map(&mA2, A2, M, K)) return rc;
+  if (epi.a_mn) {
+    if (int rc = make_map_mn(&mA1, A1, M, K)) return rc;
+    if (int rc = make_map_mn(&mA2, A2, M, K)) return rc;
+  } else {
+    if (int rc = make_map(&mA1, A1, M, K)) return rc;
+    if (int rc = make_map(&mA2, A2, M, K)) return rc;
+  }
   // CTA pairs (256-row tiles) for problems that fill the GPU with them; LBBNN_TC_PAIR=0 forces the 1-CTA kernel
   // (2 = also for small problems: the tests use it to run odd shapes through the pair kernel; read per call, host only)
   const char* pe = getenv("LBBNN_TC_PAIR");
   const int pair_mode = pe ? atoi(pe) : 1;
   const int64_t tiles2 = ceil_div(M, 2 * BM) * ceil_div(N, BN);
   if (pair_mode && M > BM && (pair_mode == 2 || tiles2 >= sm_count() / 2)) {
-    if (int rc = make_map(&mB1, B1, N, K, BN / 2)) return rc;
-    if (int rc = make_map(&mB2, B2, N, K, BN / 2)) return rc;
-    static bool attr2_set = false;
-    if (!attr2_set) {
-      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));
-      attr2_set = true;
+    if (epi.b_mn) {
+      if (int rc = make_map_mn(&mB1, B1, N, K)) return rc;
+      if (int rc = make_map_mn(&mB2, B2, N, K)) return rc;
+    } else {
+      if (int rc = make_map(&mB1, B1, N, K, BN / 2)) return rc;
+      if (int rc = make_map(&mB2, B2, N, K, BN / 2)) return rc;
     }
     const int clusters = (int)(tiles2 < sm_count() / 2 ? tiles2 : sm_count() / 2);
     const char* ge = getenv("LBBNN_TC_GROUP");      // 256-row blocks per tile group (experiments)
     const int group = ge && atoi(ge) > 0 ? atoi(ge) : kGroupM2;
-    tc_dual_gemm_bf16_pair<<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K, group);
+    switch (epi.mode) {
+#define LBBNN_PAIR_CASE(MODE_)                                                                                                       \
+  case MODE_: {                                                                                                                      \
+    static bool attr_set_ = false;                                                                                                   \
+    if (!attr_set_) {                                                                                                                \
+      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16_pair<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));    \
+      attr_set_ = true;                                                                                                              \
+    }                                                                                                                                \
+    tc_dual_gemm_bf16_pair<MODE_><<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K,   \
+                                                                                  group);                                           \
+    break;                                                                                                                           \
+  }
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_FWD)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DX)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DW_ADAM)
+#undef LBBNN_PAIR_CASE
+      default: LBBNN_REQUIRE(false, "bad epilogue mode %d", epi.mode);
+    }
     return check_launch("tc_dual_gemm_bf16_pair");
   }
-  if (int rc = make_map(&mB1, B1, N, K)) return rc;
-  if (int rc = make_map(&mB2, B2, N, K)) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    attr_set = true;
+  if (epi.b_mn) {
+    if (int rc = make_map_mn(&mB1, B1, N, K)) return rc;
+    if (int rc = make_map_mn(&mB2, B2, N, K)) return rc;
+  } else {
+    if (int rc = make_map(&mB1, B1, N, K)) return rc;
+    if (int rc = make_map(&mB2, B2, N, K)) return rc;
   }
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  tc_dual_gemm_bf16<<<grid, kTcThreads, kSmemBytes, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K);
+  switch (epi.mode) {
+#define LBBNN_ONE_CASE(MODE_)                                                                                                  \
+  case MODE_: {                                                                                                                \
+    static bool attr_set_ = false;                                                                                             \
+    if (!attr_set_) {                                                                                                          \
+      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));    \
+      attr_set_ = true;                                                                                                        \
+    }                                                                                                                          \
+    tc_dual_gemm_bf16<MODE_><<<grid, kTcThreads, kSmemBytes, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K);           \
+    break;                                                                                                                     \
+  }
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_FWD)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_DX)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_DW_ADAM)
+#undef LBBNN_ONE_CASE
+    default: LBBNN_REQUIRE(false, "bad epilogue mode %d", epi.mode);
+  }
   return check_launch("tc_dual_gemm_bf16");
 }
 
@@ -660,4 +863,76 @@ extern "C" int lbbnn_tc_lrt_bwd_input(const void* dE_bf, const void* dS_bf, cons
   e.dsT = (__nv_bfloat16*)dS_prevT_bf;
   // contraction over the out features: A = (dE, dS) (batch, out), B = (M^T, V^T) (in, out)
   return launch_tc(dE_bf, dS_bf, MT_bf, VT_bf, batch, in_features, out_features, e, (cudaStream_t)s);
+}
+
+// ---- r02: operands in place (MN-major), fused dW update, bias sums from the dX epilogue ---------------------------------
+namespace lbbnn {
+namespace {
+// out[c] = sum over the per-32-row partial sums written by the dX epilogue, fixed order
+__global__ void __launch_bounds__(256) colsum_part_reduce(const float* __restrict__ part, int n_part, int64_t cols2,
+                                                          float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols2) return;
+  float s = 0.f;
+  for (int r = 0; r < n_part; ++r) s += part[(int64_t)r * cols2 + c];
+  out[c] = s;
+}
+}  // namespace
+}  // namespace lbbnn
+
+extern "C" int lbbnn_tc_dual_gemm_raw_ex(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N,
+                                         int64_t K, int a_mn, int b_mn, float* D1, float* D2, lbbnn_stream s) {
+  LBBNN_REQUIRE(D1 && D2, "NULL output");
+  TcEpi e = {};
+  e.mode = LBBNN_TC_EPI_RAW;
+  e.d1 = D1; e.d2 = D2;
+  e.a_mn = a_mn ? 1 : 0; e.b_mn = b_mn ? 1 : 0;
+  return launch_tc(A1, A2, B1, B2, M, N, K, e, (cudaStream_t)s);
+}
+
+extern "C" size_t lbbnn_tc_colsum_part_floats(int64_t batch, int64_t in_features) {
+  return (size_t)(ceil_div(batch, 32) * 2 * in_features);
+}
+
+extern "C" int lbbnn_tc_colsum_reduce(const float* part, int64_t batch, int64_t in_features, float* colsum, lbbnn_stream s) {
+  LBBNN_REQUIRE(part && colsum && batch > 0 && in_features > 0, "bad argument");
+  const int64_t cols2 = 2 * in_features;
+  colsum_part_reduce<<<(unsigned)ceil_div(cols2, 256), 256, 0, (cudaStream_t)s>>>(part, (int)ceil_div(batch, 32), cols2, colsum);
+  return check_launch("colsum_part_reduce");
+}
+
+extern "C" int lbbnn_tc_lrt_bwd_input_mn(const void* dE_bf, const void* dS_bf, const void* M_bf, const void* V_bf, int64_t batch,
+                                         int64_t in_features, int64_t out_features, const void* x_bf, const float* ds_factor_prev,
+                                         int flags, void* dE_prev_bf, void* dS_prev_bf, float* colsum_part, lbbnn_stream s) {
+  LBBNN_REQUIRE(x_bf && dE_prev_bf && dS_prev_bf, "NULL argument");
+  TcEpi e = {};
+  e.mode = LBBNN_TC_EPI_DX; e.flags = flags;
+  e.x_bf = (const __nv_bfloat16*)x_bf; e.dsf_prev = ds_factor_prev;
+  e.de = (__nv_bfloat16*)dE_prev_bf; e.ds = (__nv_bfloat16*)dS_prev_bf;
+  e.colsum_part = colsum_part;
+  // contraction over the out features: A = (dE, dS) (batch, out) K-major; B = (M, V) (out, in) = MN-major (N = in)
+  e.a_mn = 0; e.b_mn = 1;
+  return launch_tc(dE_bf, dS_bf, M_bf, V_bf, batch, in_features, out_features, e, (cudaStream_t)s);
+}
+
+extern "C" int lbbnn_tc_lrt_dw_adam(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
+                                    const lbbnn_layer* L, int64_t batch, const lbbnn_priors* pri, int var_mode,
+                                    float kl_grad, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
+  LBBNN_REQUIRE(L && pri && adam && adam->coef, "NULL argument");
+  LBBNN_REQUIRE(L->weight_mu && L->weight_rho && L->lambdal && L->in_features > 0 && L->out_features > 0, "bad layer");
+  LBBNN_REQUIRE(L->z == nullptr && L->z_kl == nullptr, "the fused update is for LRT layers (no multiplicative z)");
+  LBBNN_REQUIRE(L->in_features % 8 == 0 && L->out_features % 8 == 0, "fused dW update needs in/out features divisible by 8");
+  for (int i = 0; i < 3; ++i) LBBNN_REQUIRE(adam->exp_avg[i] && adam->exp_avg_sq[i], "NULL Adam state %d", i);
+  TcEpi e = {};
+  e.mode = LBBNN_TC_EPI_DW_ADAM;
+  e.p_mu = const_cast<float*>(L->weight_mu); e.p_rho = const_cast<float*>(L->weight_rho); e.p_lam = const_cast<float*>(L->lambdal);
+  e.m_mu = adam->exp_avg[0]; e.m_rho = adam->exp_avg[1]; e.m_lam = adam->exp_avg[2];
+  e.v_mu = adam->exp_avg_sq[0]; e.v_rho = adam->exp_avg_sq[1]; e.v_lam = adam->exp_avg_sq[2];
+  const float* ptrs[9] = {e.p_mu, e.p_rho, e.p_lam, e.m_mu, e.m_rho, e.m_lam, e.v_mu, e.v_rho, e.v_lam};
+  for (int i = 0; i < 9; ++i) LBBNN_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, "parameters / Adam state must be 16B aligned");
+  e.coef = adam->coef; e.pri = *pri; e.var_mode = var_mode; e.klg = kl_grad;
+  e.beta1 = adam->beta1; e.beta2 = adam->beta2; e.adam_eps = adam->eps;
+  // dM = dE^T x, dV = dS^T x^2 (out, in), contraction over the batch: both operands read in place as MN-major
+  e.a_mn = 1; e.b_mn = 1;
+  return launch_tc(dE_bf, dS_bf, x_bf, x2_bf, L->out_features, L->in_features, batch, e, (cudaStream_t)s);
 }

@@ -143,6 +143,13 @@ SIGNATURES = {
     "lbbnn_tc_lrt_bwd_input_small": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "lbbnn_tc_lrt_fwd_small": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, C.POINTER(Noise), _INT, _P, _P, _P]),
     "lbbnn_tc_dual_gemm_raw_small": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P]),
+    "lbbnn_tc_dual_gemm_raw_ex": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _INT, _P, _P, _P]),
+    "lbbnn_tc_colsum_part_floats": (_SZ, [_I64, _I64]),
+    "lbbnn_tc_colsum_reduce": (_INT, [_P, _I64, _I64, _P, _P]),
+    "lbbnn_tc_lrt_bwd_input_mn": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P]),
+    "lbbnn_tc_lrt_dw_adam": (_INT, [_P, _P, _P, _P, C.POINTER(Layer), _I64, C.POINTER(Priors), _INT, _F,
+                                    C.POINTER(AdamLayerState), _P]),
+    "lbbnn_lrt_f32_finalize_adam_bias": (_INT, [C.POINTER(Layer), _P, C.POINTER(Priors), _INT, _F, C.POINTER(AdamLayerState), _P]),
     "lbbnn_colsum2_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _SZ, _P]),
     "lbbnn_linear_f32_fwd": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _SZ, _P]),
@@ -333,13 +340,14 @@ def bf16_pack(a, b, op, transposed=True):
     return o1, o2, o1t, o2t
 
 
-def tc_dual_gemm_raw(a1, a2, b1, b2):
-    """D1 = a1 @ b1.T, D2 = a2 @ b2.T (bf16 in, fp32 out) on tcgen05."""
+def tc_dual_gemm_raw(a1, a2, b1, b2, a_mn=False, b_mn=False):
+    """D1 = A1 @ B1.T, D2 = A2 @ B2.T (bf16 in, fp32 out) on tcgen05.  K-major operands are (rows, K) tensors; with
+    a_mn / b_mn the operand is passed as the (K, rows) tensor it is the transpose of (read in place, "MN-major")."""
     require_device()
-    m, k = a1.shape
-    n = b1.shape[0]
+    k, m = a1.shape if a_mn else a1.shape[::-1]
+    n = b1.shape[1] if b_mn else b1.shape[0]
     d1 = torch.empty(m, n, dtype=torch.float32, device=a1.device)
     d2 = torch.empty(m, n, dtype=torch.float32, device=a1.device)
-    check(lib.lbbnn_tc_dual_gemm_raw(ptr(a1, BF16), ptr(a2, BF16), ptr(b1, BF16), ptr(b2, BF16), m, n, k,
-                                     ptr(d1), ptr(d2), current_stream()))
+    check(lib.lbbnn_tc_dual_gemm_raw_ex(ptr(a1, BF16), ptr(a2, BF16), ptr(b1, BF16), ptr(b2, BF16), m, n, k,
+                                        int(bool(a_mn)), int(bool(b_mn)), ptr(d1), ptr(d2), current_stream()))
     return d1, d2

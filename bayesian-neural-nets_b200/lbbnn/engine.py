@@ -374,7 +374,12 @@ class LRTTensorCoreTrainer:
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
                  use_graph=True, inject_noise=False, process_group=None, fused_update=True, fused_prologue=True,
-                 fused_head_dx=True, overlap=True, small_head=False):
+                 fused_head_dx=True, overlap=True, small_head=False, in_place=None):
+        """in_place (default: whenever the stack allows it -- every layer but a <= 12-output head has out_features % 8 == 0):
+        the backward GEMMs read dE, dS, x, x^2, M, V where the forward left them (tcgen05 MN-major operands) instead of
+        transposed copies, the dX epilogue emits the bias-gradient partial sums, and on one GPU with fused_update the dW
+        GEMM's epilogue applies chain rule + KL gradient + Adam to its accumulators (lbbnn_tc_lrt_dw_adam): dM / dV never
+        reach memory.  in_place=False keeps the r01 sequence (transposed K-major operands, separate update pass)."""
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
@@ -424,19 +429,26 @@ class LRTTensorCoreTrainer:
         B = self.B
         sizes = [(l.in_features, l.out_features) for l in self.layers]
         self.sizes = sizes
+        self.fused_update = bool(fused_update)
         # input-gradient GEMM off the tensor cores: a head with <= 12 outputs goes through the fused CUDA-core kernel that
         # also stages the layer below's dE / dS / column sums (lbbnn_tc_lrt_bwd_input_small); other widths that break the
         # TMA pitch fall back to the fp32 SIMT GEMM + separate staging passes
         self.small_dx = [o <= 12 and o % 8 != 0 and fused_head_dx for _, o in sizes]
         self.simt_dx = [o % 8 != 0 and not sm for (_, o), sm in zip(sizes, self.small_dx)]
+        can_in_place = (self.fused_prologue and L >= 2 and all(o % 8 == 0 for _, o in sizes[:-1]) and
+                        (sizes[-1][1] % 8 == 0 or self.small_dx[-1]) and not self.small_head)
+        if in_place and not can_in_place:
+            raise K.LbbnnError("in_place needs out_features % 8 == 0 for every layer but a <= 12-output head (fused_head_dx)")
+        self.in_place = can_in_place if in_place is None else bool(in_place)
         self.x = torch.zeros(B, sizes[0][0], **f32)
         self.y = torch.zeros(B, dtype=torch.int64, device=dev)
         self.x_bf, self.x2_bf = torch.zeros(B, sizes[0][0], **bf), torch.zeros(B, sizes[0][0], **bf)
-        self.xT_bf, self.x2T_bf = torch.zeros(sizes[0][0], B, **bf), torch.zeros(sizes[0][0], B, **bf)
         maxnk = max(i * o for i, o in sizes)
-        self.M32, self.V32 = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)     # prologue out, reused
-        self.dM, self.dV = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)       # dW GEMM out, reused
-        self.fused_update = bool(fused_update)
+        if not self.in_place:
+            self.xT_bf, self.x2T_bf = torch.zeros(sizes[0][0], B, **bf), torch.zeros(sizes[0][0], B, **bf)
+            self.M32, self.V32 = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)     # prologue out, reused
+        if not self.in_place or not bool(fused_update):
+            self.dM, self.dV = torch.zeros(maxnk, **f32), torch.zeros(maxnk, **f32)       # dW GEMM out, reused
         self.param_off = {(id(l), name): off for l, name, off, n, shape in offs}
         # side stream: the per-layer update (all-reduce +) chain rule + Adam pass runs there while the main stream goes on
         # with the backward GEMMs, and the next step's prologues (parameters -> bf16 operands + KL) run there ahead of the
@@ -446,7 +458,7 @@ class LRTTensorCoreTrainer:
                             if (self.fused_update and (self.world > 1 or self.overlap)) else None)
         self.side_prologue = self.fused_prologue and self.overlap and self.comm_stream is not None
         self.tc = []
-        for li, (i, o) in enumerate(sizes):
+        for li, (i, o) in enumerate(sizes if not self.in_place else []):
             last = li == L - 1
             need_g32 = last or self.simt_dx[li + 1]        # dL/d(pre-activation) arrives in fp32
             need_act32 = last or self.simt_dx[li + 1]      # fp32 activations: logits / input of a SIMT dX
@@ -469,6 +481,33 @@ class LRTTensorCoreTrainer:
                 d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
                 d["colsum"] = d["raw"][2 * o * i:]
             self.tc.append(d)
+        for li, (i, o) in enumerate(sizes if self.in_place else []):
+            last = li == L - 1
+            head = last and self.small_dx[li]        # <= 12 outputs: CUDA-core dX, K-major dE^T / dS^T for its dW
+            # the dW GEMM's epilogue does the update: one GPU, fused update, tensor-core-sized layer
+            epi_update = self.fused_update and self.world == 1 and not head
+            d = dict(
+                head=head, epi_update=epi_update,
+                M=torch.zeros(o, i, **bf), V=torch.zeros(o, i, **bf), MT=None, VT=None,
+                mv32=torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) if head else None,
+                act=None if last else torch.zeros(B, o, **bf), act2=None if last else torch.zeros(B, o, **bf),
+                dsf=torch.zeros(B, o, **f32), act32=torch.zeros(B, o, **f32) if last else None,
+                g32=torch.zeros(B, o, **f32) if last else None,
+                dE=torch.zeros(B, o, **bf), dS=torch.zeros(B, o, **bf),
+                dET=torch.zeros(o, B, **bf) if head else None, dST=torch.zeros(o, B, **bf) if head else None,
+                colsum=torch.zeros(2 * o, **f32),
+                colpart=(torch.zeros(int(K.lib.lbbnn_tc_colsum_part_floats(B, o)), **f32)
+                         if (not last and not (li + 1 == L - 1 and self.small_dx[li + 1])) else None),
+                klws=torch.empty(max(256, int(K.lib.lbbnn_lrt_bf16_prologue_workspace_bytes(i, o))), dtype=torch.uint8, device=dev),
+                eps=torch.zeros(B, o, **f32) if inject_noise else None)
+            if self.fused_update and not epi_update:   # [dM | dV | colsum]: what a data-parallel step all-reduces
+                d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
+                d["colsum"] = d["raw"][2 * o * i:]
+            self.tc.append(d)
+        if self.in_place:          # no transposed input staging, no fp32 M / V scratch; dM / dV only for the unfused update
+            self.xT_bf = self.x2T_bf = self.M32 = self.V32 = None
+            if self.fused_update:
+                self.dM = self.dV = None
         self.inject = inject_noise
         self.stats = torch.zeros(1 + L, **f32)
         nbytes = max([1 << 20, B // 8 * 4 + 1024] +
@@ -490,7 +529,134 @@ class LRTTensorCoreTrainer:
             return K.make_noise(self.tc[i]["eps"])
         return K.make_noise(None, self.seed + 0x9E3779B97F4A7C15 * self.rank, i, self.step_dev, len(self.layers))
 
+    def _enqueue_in_place(self):
+        """The r02 launch sequence: every GEMM reads its operands where the producing kernel left them (see __init__)."""
+        st = K.current_stream()
+        L, B, bf = len(self.layers), self.B, torch.bfloat16
+        ws, wsn = self.ws.data_ptr(), self.ws.numel()
+        lib, P = K.lib, K.ptr
+        n = 0
+        descs = [K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+                 for l in self.layers]
+        main = torch.cuda.current_stream()
+        side = self.comm_stream
+        K.check(lib.lbbnn_bf16_pack(P(self.x), None, K.PACK_SQUARE, B, self.sizes[0][0], P(self.x_bf, bf), P(self.x2_bf, bf),
+                                    None, None, st)); n += 1
+
+        def prologue(i, stream):           # mu, rho, lambda -> bf16 M, V (+ fp32 copies for the head's CUDA-core dX) + KL
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            M32 = d["mv32"]
+            V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:] if M32 is not None else None
+            K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf), None, None,
+                                                P(M32, True), P(V32, True), self.stats[1 + i:].data_ptr(), d["klws"].data_ptr(),
+                                                d["klws"].numel(), stream))
+
+        ready = [None] * L
+        if self.side_prologue:             # all prologues up front on the side stream; each forward GEMM waits for its own
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for i in range(L):
+                    prologue(i, K.current_stream()); n += 2
+                    ready[i] = torch.cuda.Event()
+                    ready[i].record(side)
+        a, a2 = self.x_bf, self.x2_bf
+        for i in range(L):
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            last = i == L - 1
+            if self.side_prologue:
+                main.wait_event(ready[i])
+            else:
+                prologue(i, st); n += 2
+            K.check(lib.lbbnn_tc_lrt_fwd(P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data),
+                                         P(l.bias_rho.data), self._noise(i), K.FLAG_SAMPLE | (0 if last else K.FLAG_RELU),
+                                         P(d["act"], bf, True), P(d["act2"], bf, True), None, None, P(d["dsf"]),
+                                         P(d["act32"], allow_none=True), st)); n += 1
+            a, a2 = d["act"], d["act2"]
+        dl = self.tc[-1]
+        K.check(lib.lbbnn_logsoftmax_nll_f32(P(dl["act32"]), P(self.y, torch.int64), B, self.sizes[-1][1], None,
+                                             self.stats.data_ptr(), P(dl["g32"]), 1.0,
+                                             P(self.step_dev, torch.int64), ws, wsn, st)); n += 2 if B > 512 else 1
+        klg_pre = 1.0 / (self.num_batches * self.world)    # KL added on every rank before a reduction of .grad
+        klg_post = 1.0 / self.num_batches                  # KL added once (single GPU, or after the raw-gradient all-reduce)
+        if self.fused_update:
+            K.check(lib.lbbnn_adam_prepare(P(self.step_dev, torch.int64), self.lr, self.betas[0], self.betas[1],
+                                           P(self.adam_coef), st)); n += 1
+
+        def grads_of(l):
+            return K.LayerGrads(*[t.data_ptr() for t in (l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad,
+                                                         l.bias_mu.grad, l.bias_rho.grad)], None)
+
+        for i in reversed(range(L)):
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            xin, xin2 = (self.x_bf, self.x2_bf) if i == 0 else (self.tc[i - 1]["act"], self.tc[i - 1]["act2"])
+            if i == L - 1:                 # fp32 upstream gradient of the loss head: stage dE, dS (+ K-major transposes for a
+                # <= 12-output head, whose (batch, out) rows are too short for a TMA pitch) and the bias sums
+                K.check(lib.lbbnn_bf16_pack(P(d["g32"]), P(d["dsf"]), K.PACK_SCALE, B, fo, P(d["dE"], bf), P(d["dS"], bf),
+                                            P(d["dET"], bf, True), P(d["dST"], bf, True), st)); n += 1
+                K.check(lib.lbbnn_colsum2(P(d["g32"]), P(d["dsf"]), 0, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
+            elif d["colpart"] is not None:  # bias sums of this layer: partials written by the dX epilogue of the layer above
+                K.check(lib.lbbnn_tc_colsum_reduce(P(d["colpart"]), B, fo, P(d["colsum"]), st)); n += 1
+            # ---- dM = dE^T x, dV = dS^T x^2 (+ update) ----
+            if d["epi_update"]:            # chain rule + KL + Adam in the GEMM's epilogue; biases in a one-block kernel
+                K.check(lib.lbbnn_tc_lrt_dw_adam(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), descs[i], B,
+                                                 l.cfg.priors, l.cfg.var_mode, klg_post, self._adam_state(l), st)); n += 1
+                K.check(lib.lbbnn_lrt_f32_finalize_adam_bias(descs[i], P(d["colsum"]), l.cfg.priors, K.FLAG_SAMPLE, klg_post,
+                                                             self._adam_state(l), st)); n += 1
+            else:
+                if self.fused_update:
+                    dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
+                else:
+                    dM, dV = self.dM, self.dV
+
+                def dw(stream):
+                    if d["head"]:          # A = dE^T, dS^T (out, batch) K-major; B = x, x^2 (batch, in) in place
+                        K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dET"], bf), P(d["dST"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
+                                                              0, 1, P(dM), P(dV), stream))
+                    else:
+                        K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
+                                                              1, 1, P(dM), P(dV), stream))
+                if self.fused_update and side is not None and self.overlap and d["head"] and i > 0:
+                    # the head's dW GEMM occupies 32 of 148 SMs: on the side stream, under the head's input-gradient kernel
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        dw(K.current_stream()); n += 1
+                else:
+                    dw(st); n += 1
+                if self.fused_update:
+                    self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
+                else:
+                    K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(dM), P(dV), P(d["colsum"]), l.cfg.priors, l.cfg.var_mode,
+                                                       K.FLAG_SAMPLE, None, klg_pre, grads_of(l), st)); n += 1
+            if i == 0:
+                continue
+            # ---- dx = dE M + 2 x (dS V) -> the layer below's dE, dS (+ bias partial sums) ----
+            p = self.tc[i - 1]
+            if d["head"]:
+                M32, V32 = d["mv32"], d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
+                K.check(lib.lbbnn_tc_lrt_bwd_input_small(P(d["g32"]), P(d["dsf"]), P(M32), P(V32), B, fi, fo, P(p["act"], bf),
+                                                         P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf),
+                                                         P(p["dS"], bf), None, None, P(p["colsum"]), ws, wsn, st)); n += 2
+            else:
+                K.check(lib.lbbnn_tc_lrt_bwd_input_mn(P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
+                                                      P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
+                                                      P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"]), st)); n += 1
+        if self.fused_update:
+            if side is not None:
+                main.wait_stream(side)
+        else:
+            if self.pg is not None:
+                torch.distributed.all_reduce(self.gflat, group=self.pg)
+            K.check(lib.lbbnn_adam_f32(P(self.flat), P(self.gflat), P(self.exp_avg), P(self.exp_avg_sq), self.n_flat,
+                                       self.lr, self.betas[0], self.betas[1], self.eps, P(self.step_dev, torch.int64),
+                                       P(self.adam_coef), st)); n += 2
+        self.kernels_per_step = n
+
     def _enqueue(self):
+        if self.in_place:
+            return self._enqueue_in_place()
         st = K.current_stream()
         L, B, bf = len(self.layers), self.B, torch.bfloat16
         ws, wsn = self.ws.data_ptr(), self.ws.numel()

@@ -364,7 +364,7 @@ def profile_fused(tr, sizes, B, us_per_step, peaks, reps=20, replays=True):
 
 def profile_calls_wide(tr, reps=5):
     """Tensor-core GEMM calls of one wide step timed on their own (CUDA events, operands > L2): FLOPs are the
-    ALGORITHMIC 2 GEMMs x 2 B in out per call."""
+    ALGORITHMIC 2 GEMMs x 2 B in out per call.  Layer 2 of the stack (4096 x 4096, batch 8192)."""
     from lbbnn import _capi as K
     bf, st, B = torch.bfloat16, K.current_stream(), tr.B
     P = K.ptr
@@ -373,18 +373,39 @@ def profile_calls_wide(tr, reps=5):
     l, d = tr.layers[i], tr.tc[i]
     fi, fo = tr.sizes[i]
     a, a2 = (tr.x_bf, tr.x2_bf) if i == 0 else (tr.tc[i - 1]["act"], tr.tc[i - 1]["act2"])
-    xT, x2T = (tr.xT_bf, tr.x2T_bf) if i == 0 else (tr.tc[i - 1]["actT"], tr.tc[i - 1]["act2T"])
-    calls = [(f"tc_lrt_fwd[l{i + 1}] (tcgen05 dual GEMM + eps/sqrt/relu epilogue)", lambda: K.lib.lbbnn_tc_lrt_fwd(
-        P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data), P(l.bias_rho.data), tr._noise(i),
-        K.FLAG_SAMPLE | K.FLAG_RELU, P(d["act"], bf), P(d["act2"], bf), P(d["actT"], bf), P(d["act2T"], bf), P(d["dsf"]),
-        P(d["act32"], allow_none=True), st)),
-        (f"tc_dual_gemm_raw[l{i + 1}] (dM, dV)", lambda: K.lib.lbbnn_tc_dual_gemm_raw(
-            P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B, P(tr.dM), P(tr.dV), st))]
-    if i > 0:
-        p = tr.tc[i - 1]
-        calls.append((f"tc_lrt_bwd_input[l{i + 1}] (dx + relu mask + next dE/dS epilogue)", lambda: K.lib.lbbnn_tc_lrt_bwd_input(
-            P(d["dE"], bf), P(d["dS"], bf), P(d["MT"], bf), P(d["VT"], bf), B, fi, fo, P(p["act"], bf), P(p["dsf"]),
-            K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf), P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf), st)))
+    desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+    if tr.in_place:
+        calls = [(f"tc_lrt_fwd[l{i + 1}] (tcgen05 dual GEMM + eps/sqrt/relu epilogue)", lambda: K.lib.lbbnn_tc_lrt_fwd(
+            P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data), P(l.bias_rho.data), tr._noise(i),
+            K.FLAG_SAMPLE | K.FLAG_RELU, P(d["act"], bf), P(d["act2"], bf), None, None, P(d["dsf"]), None, st))]
+        if d["epi_update"]:
+            calls.append((f"tc_lrt_dw_adam[l{i + 1}] (dM, dV from operands in place + chain rule + KL + Adam epilogue)",
+                          lambda: K.lib.lbbnn_tc_lrt_dw_adam(P(d["dE"], bf), P(d["dS"], bf), P(a, bf), P(a2, bf), desc, B,
+                                                             l.cfg.priors, l.cfg.var_mode, 1.0 / NUM_BATCHES, tr._adam_state(l), st)))
+        else:
+            dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
+            calls.append((f"tc_dual_gemm_raw_ex[l{i + 1}] (dM, dV from operands in place)", lambda: K.lib.lbbnn_tc_dual_gemm_raw_ex(
+                P(d["dE"], bf), P(d["dS"], bf), P(a, bf), P(a2, bf), fo, fi, B, 1, 1, P(dM), P(dV), st)))
+        if i > 0:
+            p = tr.tc[i - 1]
+            calls.append((f"tc_lrt_bwd_input_mn[l{i + 1}] (dx + relu mask + next dE/dS + bias partial sums epilogue)",
+                          lambda: K.lib.lbbnn_tc_lrt_bwd_input_mn(
+                              P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(p["act"], bf), P(p["dsf"]),
+                              K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"], True), st)))
+    else:
+        xT, x2T = (tr.xT_bf, tr.x2T_bf) if i == 0 else (tr.tc[i - 1]["actT"], tr.tc[i - 1]["act2T"])
+        dM, dV = (d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]) if tr.fused_update else (tr.dM, tr.dV)
+        calls = [(f"tc_lrt_fwd[l{i + 1}] (tcgen05 dual GEMM + eps/sqrt/relu epilogue)", lambda: K.lib.lbbnn_tc_lrt_fwd(
+            P(a, bf), P(a2, bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo, P(l.bias_mu.data), P(l.bias_rho.data), tr._noise(i),
+            K.FLAG_SAMPLE | K.FLAG_RELU, P(d["act"], bf), P(d["act2"], bf), P(d["actT"], bf), P(d["act2T"], bf), P(d["dsf"]),
+            P(d["act32"], allow_none=True), st)),
+            (f"tc_dual_gemm_raw[l{i + 1}] (dM, dV)", lambda: K.lib.lbbnn_tc_dual_gemm_raw(
+                P(d["dET"], bf), P(d["dST"], bf), P(xT, bf), P(x2T, bf), fo, fi, B, P(dM), P(dV), st))]
+        if i > 0:
+            p = tr.tc[i - 1]
+            calls.append((f"tc_lrt_bwd_input[l{i + 1}] (dx + relu mask + next dE/dS epilogue)", lambda: K.lib.lbbnn_tc_lrt_bwd_input(
+                P(d["dE"], bf), P(d["dS"], bf), P(d["MT"], bf), P(d["VT"], bf), B, fi, fo, P(p["act"], bf), P(p["dsf"]),
+                K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf), P(p["dS"], bf), P(p["dET"], bf), P(p["dST"], bf), st)))
     flops = 2 * 2.0 * B * fi * fo
     for name, fn in calls:
         for _ in range(2):
@@ -465,7 +486,8 @@ def bench_lrt(ctx, workload, steps, warmup, unfused=False, cpu_budget_s=15.0):
     _mark("process group up, building trainer")
     if wide:
         tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
-                                        fused_update=not args.unfused)
+                                        fused_update=not args.unfused,
+                                        in_place=False if os.environ.get("LBBNN_WIDE_R01") else None)
     else:   # the fused persistent step kernel unless --unfused; gradients stay in registers (no .grad written)
         tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
                               fused=not args.unfused, materialize_grads=args.unfused)

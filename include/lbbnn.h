@@ -156,7 +156,7 @@ LBBNN_API int lbbnn_lrt_f32_finalize(const lbbnn_layer* layer, const float* dM, 
  *              fp32 ds_factor and an fp32 copy of act.  bf16(act^2) is rounded from the fp32 act.
  *   lrt_bwd_input  dx = dE M + 2 x (dS V) [relu mask] = previous layer's dE; dS_prev = dE_prev *
  *              ds_factor_prev; both in bf16 (batch,in) and optionally transposed (in,batch). */
-enum { LBBNN_TC_EPI_RAW = 0, LBBNN_TC_EPI_FWD = 1, LBBNN_TC_EPI_DX = 2 };
+enum { LBBNN_TC_EPI_RAW = 0, LBBNN_TC_EPI_FWD = 1, LBBNN_TC_EPI_DX = 2, LBBNN_TC_EPI_DW_ADAM = 3 };
 enum { LBBNN_PACK_PAIR = 0, LBBNN_PACK_SQUARE = 1, LBBNN_PACK_SCALE = 2 };
 
 LBBNN_API int lbbnn_tc_dual_gemm_raw(const void* A1, const void* A2, const void* B1, const void* B2,
@@ -443,6 +443,40 @@ LBBNN_API int lbbnn_adam_prepare(const int64_t* step_dev, float lr, float beta1,
 LBBNN_API int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* layer, const float* dM, const float* dV, const float* colsum,
                                           const lbbnn_priors* priors, int var_mode, int flags, const float* kl_grad_dev,
                                           float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s);
+/* Biases only (sum_b dE, sum_b dS -> d bias_mu, d bias_rho + KL gradient -> Adam): the companion of lbbnn_tc_lrt_dw_adam,
+ * whose GEMM epilogue updates the three weight tensors. */
+LBBNN_API int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* layer, const float* colsum, const lbbnn_priors* priors,
+                                               int flags, float kl_grad_host, const lbbnn_adam_layer_state* adam,
+                                               lbbnn_stream s);
+
+/* ---- bf16 tensor-core path, operands read in place (r02) -------------------------------------------------------------
+ * The GEMM kernels also take "MN-major" operands: the row-major (K, rows) tensor, i.e. one whose ROW index is the
+ * contraction index, fetched by TMA as 64 x 64 boxes into tcgen05's MN-major SWIZZLE_128B layout.  With them the three
+ * GEMM pairs of a layer read the same row-major tensors and no transposed copy of x, act, dE, dS, M or V exists:
+ *   raw_ex        lbbnn_tc_dual_gemm_raw with a major flag per operand side (a_mn: A1, A2 are (K, M); b_mn: B1, B2 are
+ *                 (K, N)); rows % 8 == 0 for an MN-major side (TMA pitch).
+ *   bwd_input_mn  lbbnn_tc_lrt_bwd_input reading M_bf, V_bf (out, in) as they are (no M^T, V^T), without transposed
+ *                 outputs, and optionally writing the bias-gradient partial sums of the layer below: colsum_part
+ *                 [ceil(batch/32)][2*in] (sum over each 32 batch rows of dE | dS, from the fp32 values);
+ *                 lbbnn_tc_colsum_reduce sums them in a fixed order into colsum[2*in] -- replaces lbbnn_colsum2 there.
+ *   dw_adam       the dW pair dM = dE^T x, dV = dS^T x^2 (contraction over the batch; dE, dS (batch, out) and x, x^2
+ *                 (batch, in) read in place) with chain rule + closed-form KL gradient (weight kl_grad = 1/NUM_BATCHES)
+ *                 + torch.optim.Adam applied to the accumulators in the epilogue: weight_mu, weight_rho, lambdal and
+ *                 their Adam moments are updated IN PLACE, dM / dV never reach memory (LRT:225-226 for the weights of
+ *                 one layer).  in/out_features % 8 == 0.  Biases: lbbnn_lrt_f32_finalize_adam_bias. */
+LBBNN_API int lbbnn_tc_dual_gemm_raw_ex(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N,
+                                        int64_t K, int a_mn, int b_mn, float* D1, float* D2, lbbnn_stream s);
+LBBNN_API size_t lbbnn_tc_colsum_part_floats(int64_t batch, int64_t in_features);
+LBBNN_API int lbbnn_tc_colsum_reduce(const float* colsum_part, int64_t batch, int64_t in_features, float* colsum,
+                                     lbbnn_stream s);
+LBBNN_API int lbbnn_tc_lrt_bwd_input_mn(const void* dE_bf, const void* dS_bf, const void* M_bf, const void* V_bf,
+                                        int64_t batch, int64_t in_features, int64_t out_features, const void* x_bf,
+                                        const float* ds_factor_prev, int flags, void* dE_prev_bf, void* dS_prev_bf,
+                                        float* colsum_part, lbbnn_stream s);
+LBBNN_API int lbbnn_tc_lrt_dw_adam(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
+                                   const lbbnn_layer* layer, int64_t batch, const lbbnn_priors* priors, int var_mode,
+                                   float kl_grad, const lbbnn_adam_layer_state* adam, lbbnn_stream s);
+
 /* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF script, MNF:352,
  * and the 33 per-tensor parameter groups of the MF script, MF:520-553: learning rates 1e-4 for weights / biases, 1e-3
  * for pa / pb, 1e-5 for the Gamma hyper-parameters, 0.1 for lambdal): table_dev = device array of n_entries records;

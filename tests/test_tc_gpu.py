@@ -37,6 +37,73 @@ def test_raw_dual_gemm_matches_torch(K, tc_mode, m, n, k):
     assert C.rel_err(d2, r2) < 1e-4
 
 
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, True), (True, False)])
+@pytest.mark.parametrize("m,n,k", [(128, 128, 64), (256, 384, 512), (200, 72, 200), (1000, 136, 1096), (4096, 512, 1024),
+                                   (10, 1024, 520), (2560, 1024, 320)])
+def test_raw_dual_gemm_mn_major_operands_match_torch(K, tc_mode, m, n, k, a_mn, b_mn):
+    """Operands read in place as tcgen05 MN-major tiles: A given as the (K, M) tensor and / or B as the (K, N) tensor.
+    Ragged M, N, K (TMA zero fill); M = 10 with a K-major A is the classifier head's dW call."""
+    if (a_mn and m % 8) or (b_mn and n % 8):
+        pytest.skip("MN-major operands need rows % 8 == 0 (TMA pitch)")
+    rng = np.random.default_rng(m * 7 + n * 3 + k + 2 * a_mn + b_mn)
+    a1, a2 = _rand_bf16(rng, m, k), _rand_bf16(rng, m, k)
+    b1, b2 = _rand_bf16(rng, n, k), _rand_bf16(rng, n, k)
+    A = [t.T.contiguous() if a_mn else t for t in (a1, a2)]
+    B = [t.T.contiguous() if b_mn else t for t in (b1, b2)]
+    d1, d2 = K.tc_dual_gemm_raw(A[0], A[1], B[0], B[1], a_mn=a_mn, b_mn=b_mn)
+    torch.cuda.synchronize()
+    assert d1.shape == (m, n)
+    assert C.rel_err(d1, a1.float() @ b1.float().T) < 1e-4
+    assert C.rel_err(d2, a2.float() @ b2.float().T) < 1e-4
+
+
+@pytest.mark.parametrize("b,i,o,var_mode", [(256, 128, 256, "reference"), (264, 136, 200, "exact"), (512, 512, 128, "reference")])
+def test_fused_dw_adam_epilogue_matches_gemm_plus_finalize_adam(K, tc_mode, b, i, o, var_mode):
+    """lbbnn_tc_lrt_dw_adam (dW GEMM pair whose epilogue applies chain rule + KL gradient + Adam to the accumulators) against
+    lbbnn_tc_dual_gemm_raw -> lbbnn_lrt_f32_finalize_adam on the same operands: parameters and both Adam moments after two
+    consecutive updates; the biases through lbbnn_lrt_f32_finalize_adam_bias."""
+    import lbbnn
+    case = C.lrt_layer_case(300 + b + i, b, i, o, spread_lambda=True)
+    rng = np.random.default_rng(b + o)
+    bf = torch.bfloat16
+    de, ds = _rand_bf16(rng, b, o, scale=0.5), _rand_bf16(rng, b, o, scale=0.05)
+    x = torch.from_numpy(rng.random((b, i), dtype=np.float32)).cuda()
+    xb, x2b, xT, x2T = K.bf16_pack(x, None, K.PACK_SQUARE)
+    colsum = torch.from_numpy(rng.standard_normal(2 * o).astype(np.float32)).cuda()
+    cfg = lbbnn.LayerConfig(var_mode=var_mode)
+    step_dev = torch.ones(1, dtype=torch.int64, device="cuda")
+    results = []
+    for fused in (False, True):
+        p = {k: v.clone().cuda() for k, v in case["p"].items()}
+        names = ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho")
+        m = {k: torch.zeros_like(p[k]) for k in names}
+        v = {k: torch.zeros_like(p[k]) for k in names}
+        coef = torch.zeros(2, device="cuda")
+        st = K.AdamLayerState()
+        for j, k in enumerate(names):
+            st.exp_avg[j], st.exp_avg_sq[j] = m[k].data_ptr(), v[k].data_ptr()
+        st.coef, st.beta1, st.beta2, st.eps = coef.data_ptr(), 0.9, 0.999, 1e-8
+        layer = K.make_layer(*[p[k] for k in names])
+        for t in (1, 2):
+            step_dev.fill_(t)
+            K.check(K.lib.lbbnn_adam_prepare(K.ptr(step_dev, torch.int64), 1e-2, 0.9, 0.999, K.ptr(coef), K.current_stream()))
+            if fused:
+                K.check(K.lib.lbbnn_tc_lrt_dw_adam(K.ptr(de, bf), K.ptr(ds, bf), K.ptr(xb, bf), K.ptr(x2b, bf), layer, b, cfg.priors,
+                                                   cfg.var_mode, 1.0 / 600, st, K.current_stream()))
+                K.check(K.lib.lbbnn_lrt_f32_finalize_adam_bias(layer, K.ptr(colsum), cfg.priors, K.FLAG_SAMPLE, 1.0 / 600, st,
+                                                               K.current_stream()))
+            else:
+                dM, dV = K.tc_dual_gemm_raw(de.T.contiguous(), ds.T.contiguous(), xT, x2T)
+                K.check(K.lib.lbbnn_lrt_f32_finalize_adam(layer, K.ptr(dM), K.ptr(dV), K.ptr(colsum), cfg.priors, cfg.var_mode,
+                                                          K.FLAG_SAMPLE, None, 1.0 / 600, st, K.current_stream()))
+        torch.cuda.synchronize()
+        results.append((p, m, v))
+    for k in results[0][0]:
+        for which, name in enumerate(("param", "exp_avg", "exp_avg_sq")):
+            a, r = results[1][which][k], results[0][which][k]
+            assert C.rel_err(a, r) < 2e-6, (k, name, C.rel_err(a, r))
+
+
 @pytest.fixture(params=["1cta", "pair"])
 def tc_mode(request):
     """Run a GEMM test on the 1-CTA kernel and, forced (LBBNN_TC_PAIR=2), on the CTA-pair (cta_group::2) kernel."""
@@ -221,11 +288,13 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-def emulate_bf16_step(case, num_batches, device="cpu"):
+def emulate_bf16_step(case, num_batches, device="cpu", fp32_bias_sums=True):
     """The tensor-core pipeline restated in torch with the SAME rounding points (operands of every GEMM
     rounded to bf16, fp32 accumulation, elementwise math in fp32; the classifier layer in fp32).  The
     elementwise chain rule is taken from autograd through the oracle's own functions.  device="cuda" runs the same
-    torch expressions on the GPU (fp32 matmuls, TF32 off) -- the full-size configs[4] case takes minutes on CPU."""
+    torch expressions on the GPU (fp32 matmuls, TF32 off) -- the full-size configs[4] case takes minutes on CPU.
+    fp32_bias_sums: the bias gradients of the hidden layers are column sums of the fp32 dx values (the in-place path: the dX
+    epilogue sums what it holds in registers); False = of the bf16-rounded dE / dS tensors (the r01 path's colsum kernel)."""
     import lbbnn_oracle as O
     assert not torch.backends.cuda.matmul.allow_tf32
     layers = [{k: v.to(device).double().float().clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
@@ -264,7 +333,7 @@ def emulate_bf16_step(case, num_batches, device="cpu"):
                 Mb, Vb = _bf(MV[i][0]), _bf(MV[i][1])
                 g = (dE @ Mb + 2 * xin * (dS @ Vb)) * (xin > 0)
                 dE, dS = _bf(g), _bf(g * dsfs[i - 1])
-                cE[i - 1], cS[i - 1] = dE.sum(0), dS.sum(0)       # bias sums come from the bf16 tensors
+                cE[i - 1], cS[i - 1] = (g.sum(0), (g * dsfs[i - 1]).sum(0)) if fp32_bias_sums else (dE.sum(0), dS.sum(0))
     kl = sum(O.lrt_kl(p) for p in layers)
     surrogate = kl / num_batches
     for i, p in enumerate(layers):
@@ -275,9 +344,10 @@ def emulate_bf16_step(case, num_batches, device="cpu"):
     return nll.item(), kl.item(), layers
 
 
+@pytest.mark.parametrize("in_place", [True, False])
 @pytest.mark.parametrize("use_graph", [False, True])
-@pytest.mark.parametrize("dims,B", [((256, 384, 256, 10), 256), ((136, 200, 10), 264)])
-def test_tensor_core_trainer_step(use_graph, dims, B):
+@pytest.mark.parametrize("dims,B", [((256, 384, 256, 10), 256), ((136, 200, 10), 264), ((136, 200, 72, 16), 264)])
+def test_tensor_core_trainer_step(use_graph, dims, B, in_place):
     """Wide-stack step in bf16 on tcgen05, same injected noise:
     (i)  vs the bf16-rounding emulation above: <= 5e-3 relative Frobenius per gradient tensor (what is left
          is fp32 summation order and roundings that flip at a tie), KL and NLL 1e-4;
@@ -291,14 +361,17 @@ def test_tensor_core_trainer_step(use_graph, dims, B):
         for l, p in zip(net.layers, case["layers"]):
             for k, v in p.items():
                 getattr(l, k).copy_(v)
+    if dims[-1] % 8 == 0 and not in_place:
+        pytest.skip("the r01 path sends a 16-output head through the SIMT dX; covered by the in-place run")
     tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph,
-                                    inject_noise=True, fused_update=False)      # gradients wanted in .grad
+                                    inject_noise=True, fused_update=False, in_place=in_place)      # gradients wanted in .grad
+    assert tr.in_place == in_place
     for d, e in zip(tr.tc, case["eps"]):
         d["eps"].copy_(e)
     out = tr.step(case["x"], case["y"])
     grads = [{k: getattr(l, k).grad.cpu().double() for k in case["layers"][0]} for l in net.layers]
 
-    nll_e, kl_e, emu = emulate_bf16_step(case, C.NUM_BATCHES)
+    nll_e, kl_e, emu = emulate_bf16_step(case, C.NUM_BATCHES, fp32_bias_sums=in_place)
     assert abs(out["kl"] - kl_e) / kl_e < 1e-5
     assert abs(out["nll"] - nll_e) / nll_e < 1e-4
     for li, (g, p) in enumerate(zip(grads, emu)):
@@ -505,7 +578,7 @@ def test_wide_gemm_calls_at_the_real_shape(K):
     e_dm, e_dv = C.rel_err(dM, deT.float() @ xb.float()), C.rel_err(dV, dsT.float() @ x2b.float())
     _report("tc_dual_gemm_raw 4096x4096x8192", dM=e_dm, dV=e_dv)
     assert e_dm < 1e-4 and e_dv < 1e-4
-    del dM, dV, xT, x2T
+    del dM, dV
     # dX: g = dE M + 2 x (dS V) through the relu mask, then the layer below's dE / dS (bf16) and transposes
     xin = act                                       # relu output of a layer: the mask source
     dsf_prev = f(b, i)
@@ -513,14 +586,33 @@ def test_wide_gemm_calls_at_the_real_shape(K):
     K.check(K.lib.lbbnn_tc_lrt_bwd_input(K.ptr(de, bf), K.ptr(ds, bf), K.ptr(mt, bf), K.ptr(vt, bf), b, i, o, K.ptr(xin, bf),
                                          K.ptr(dsf_prev), K.FLAG_SAMPLE | K.FLAG_MASK_DX, *[K.ptr(t, bf) for t in outs],
                                          K.current_stream()))
+    # the in-place form: M, V (out, in) read as MN-major B operands, bias partial sums from the epilogue
+    outs_mn = [torch.empty(b, i, dtype=bf, device="cuda") for _ in range(2)]
+    part = torch.empty(int(K.lib.lbbnn_tc_colsum_part_floats(b, i)), device="cuda")
+    colsum = torch.empty(2 * i, device="cuda")
+    K.check(K.lib.lbbnn_tc_lrt_bwd_input_mn(K.ptr(de, bf), K.ptr(ds, bf), K.ptr(mb, bf), K.ptr(vb, bf), b, i, o, K.ptr(xin, bf),
+                                            K.ptr(dsf_prev), K.FLAG_SAMPLE | K.FLAG_MASK_DX, K.ptr(outs_mn[0], bf),
+                                            K.ptr(outs_mn[1], bf), K.ptr(part), K.current_stream()))
+    K.check(K.lib.lbbnn_tc_colsum_reduce(K.ptr(part), b, i, K.ptr(colsum), K.current_stream()))
     torch.cuda.synchronize()
+    assert torch.equal(outs_mn[0], outs[0]) and torch.equal(outs_mn[1], outs[1])       # same MMAs, same order: bit-identical
     g = de.float() @ mt.float().T + 2 * xin.float() * (ds.float() @ vt.float().T)
     g = g * (xin.float() > 0)
+    e_c1, e_c2 = C.rel_err(colsum[:i], g.double().sum(0)), C.rel_err(colsum[i:], (g.double() * dsf_prev.double()).sum(0))
+    _report("tc_lrt_bwd_input_mn bias sums", dE=e_c1, dS=e_c2)
+    assert e_c1 < 1e-4 and e_c2 < 1e-4
+    # the dW pair with every operand read in place (MN-major A and B): same products as the transposed K-major call
+    dM2, dV2 = K.tc_dual_gemm_raw(de, ds, xb, x2b, a_mn=True, b_mn=True)
+    torch.cuda.synchronize()
+    e_dm2, e_dv2 = C.rel_err(dM2, deT.float() @ xb.float()), C.rel_err(dV2, dsT.float() @ x2b.float())
+    _report("tc_dual_gemm_raw_ex (MN, MN) 4096x4096x8192", dM=e_dm2, dV=e_dv2)
+    assert e_dm2 < 1e-4 and e_dv2 < 1e-4
+    del dM2, dV2
     # the outputs are bf16: exact rounding of the fp32 value, or its neighbour where the two fp32 sums straddle a tie
     exact = (outs[0] == g.to(bf)).float().mean().item()
     e_g = C.rel_err(outs[0].float(), g)
     _report("tc_lrt_bwd_input 8192x4096x4096", dx=e_g, frac_identical_bf16=exact)
-    assert e_g < 4e-3 and exact > 0.999
+    assert e_g < 4e-3 and exact > 0.99
     assert C.rel_err(outs[1].float(), g * dsf_prev) < 8e-3
     assert torch.equal(outs[2], outs[0].T.contiguous()) and torch.equal(outs[3], outs[1].T.contiguous())
 
