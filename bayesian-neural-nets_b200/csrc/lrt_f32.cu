@@ -256,6 +256,10 @@ struct FwdArgs {
   int64_t B, K, N;
   int chunks_per_split, splits, sample;
   float* part;  // [splits][2][B][N]
+  // optional: rows [g * rows_per_group, (g + 1) * rows_per_group) use x .* rowscale[g] in the MEAN product only (the
+  // variance product keeps x^2): MNF's multiplicative z, one per stacked MC sample (MNF:197-198)
+  const float* rowscale;
+  int64_t rows_per_group;
 };
 
 __global__ void __launch_bounds__(kThreads, 2) lrt_f32_fwd_partial(const FwdArgs a) {
@@ -277,14 +281,17 @@ __global__ void __launch_bounds__(kThreads, 2) lrt_f32_fwd_partial(const FwdArgs
 #pragma unroll
     for (int j = 0; j < 4; ++j) accE[i][j] = accS[i][j] = 0.f;
 
-  float4 xr[2], pm, pv;
+  float4 xr[2], zr[2], pm, pv;
   const int prow = tid >> 2, pkq = (tid & 3) * 4;  // loader coordinates for the weight tiles
+  const bool vecz = a.rowscale != nullptr && (a.K % 4 == 0) && aligned16(a.rowscale);
+  const int64_t ngroups = a.rowscale ? ceil_div(a.B, a.rows_per_group) : 0;
 
   auto gload = [&](int64_t k0) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int id = tid + i * kThreads;
       xr[i] = load4(a.x, m0 + (id >> 2), k0 + (id & 3) * 4, a.B, kend, a.K, vec);
+      if (a.rowscale) zr[i] = load4(a.rowscale, (m0 + (id >> 2)) / a.rows_per_group, k0 + (id & 3) * 4, ngroups, kend, a.K, vecz);
     }
     pm = load4(a.M, n0 + prow, k0 + pkq, a.N, kend, a.K, vec);
     pv = a.sample ? load4(a.V, n0 + prow, k0 + pkq, a.N, kend, a.K, vec) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -295,9 +302,10 @@ __global__ void __launch_bounds__(kThreads, 2) lrt_f32_fwd_partial(const FwdArgs
       const int id = tid + i * kThreads;
       const int r = id >> 2, kq = (id & 3) * 4;
       const float e[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
+      const float z[4] = {zr[i].x, zr[i].y, zr[i].z, zr[i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        xs[kq + j][r] = e[j];
+        xs[kq + j][r] = a.rowscale ? e[j] * z[j] : e[j];
         xq[kq + j][r] = e[j] * e[j];
       }
     }
@@ -360,6 +368,10 @@ struct FwdEpiArgs {
   const double* kl_part;
   int n_kl_part;
   lbbnn_priors pri;
+  // optional: native noise drawn per row group -- rows [g R, (g + 1) R) take stream + g * group_stride, element index
+  // (row - g R) * N + col: stacked MC samples each draw what a batch-R call on their own stream would (R N % 4 == 0)
+  int64_t noise_group_rows;
+  uint64_t noise_group_stride;
 };
 
 constexpr int kEpiThreads = 128;
@@ -397,9 +409,13 @@ __global__ void __launch_bounds__(kEpiThreads) lrt_f32_fwd_epilogue(const FwdEpi
         }
       }
     }
-    if (sample) {
+    const bool moments = a.flags & LBBNN_FLAG_MOMENTS;
+    if (sample && !moments) {
       if (nz.ptr) loadq(nz.ptr, e0, total, vec, ep);
-      else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+      else if (a.noise_group_rows > 0) {
+        const int64_t per = a.noise_group_rows * a.N, g = e0 / per;      // per % 4 == 0: the quad stays inside one group
+        philox_normal4(nz.seed, nz.stream + (uint64_t)g * a.noise_group_stride, (uint64_t)((e0 - g * per) >> 2), ep);
+      } else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
     }
     float out[4], df[4];
 #pragma unroll
@@ -408,6 +424,12 @@ __global__ void __launch_bounds__(kEpiThreads) lrt_f32_fwd_epilogue(const FwdEpi
       if (e0 + j < total) {
         const int64_t n = (e0 + j) % a.N;
         float v = E[j] + __ldg(a.bias_mu + n);
+        if (moments) {            // e_b and var_b themselves (LRT:172-173), no noise: act <- e_b, dsf <- var_b
+          const float sb = sigma_of(__ldg(a.bias_rho + n));
+          out[j] = v;
+          df[j] = S[j] + sb * sb;
+          continue;
+        }
         if (sample) {
           const float sb = sigma_of(__ldg(a.bias_rho + n));
           const float sd = sqrtf(S[j] + sb * sb);
@@ -908,10 +930,65 @@ extern "C" size_t lbbnn_lrt_f32_mv_bytes(int64_t K, int64_t N) {
   return 2 * align_up((size_t)N * K * sizeof(float));
 }
 
-extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B, const lbbnn_noise* nz,
-                                 const lbbnn_priors* pri, int var_mode, int flags, float* act, float* ds_factor,
-                                 float* kl_out, float* mv_cache, void* ws, size_t ws_bytes, lbbnn_stream s) {
+// act[s, b, n] = [relu](e_b[b, n] + sqrt(var_b[b, n]) eps_s[b, n]) for the samples of one launch (LRT:174-175 with the e_b, var_b
+// of LRT:172-173 shared by all samples of a test batch, LRT:247); eps_s from stream + s * group_stride, or injected (S, B, N)
+struct ExpandArgs {
+  const float *e, *var;
+  int64_t total;     // B * N
+  int n_samples, relu;
+  Noise noise;
+  uint64_t group_stride;
+  float* act;
+};
+__global__ void __launch_bounds__(kThreads) lrt_sample_expand_kernel(const ExpandArgs a) {
+  Noise nz = a.noise;
+  nz.resolve();
+  const int64_t nq = ceil_div(a.total, 4);
+  const bool vec = (a.total % 4 == 0) && aligned16(a.e) && aligned16(a.var) && aligned16(a.act) && (nz.ptr == nullptr || aligned16(nz.ptr));
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    float ev[4], sd[4];
+    loadq(a.e, e0, a.total, vec, ev);
+    loadq(a.var, e0, a.total, vec, sd);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sd[j] = sqrtf(sd[j]);
+    for (int s = 0; s < a.n_samples; ++s) {
+      float ep[4], out[4];
+      if (nz.ptr) loadq(nz.ptr + (int64_t)s * a.total, e0, a.total, vec, ep);
+      else if (a.total % 4 == 0) philox_normal4(nz.seed, nz.stream + (uint64_t)s * a.group_stride, (uint64_t)q, ep);
+      else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ep[j] = philox_normal1(nz.seed, nz.stream + (uint64_t)s * a.group_stride, (uint64_t)(e0 + j));
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float v = fmaf(sd[j], ep[j], ev[j]);
+        out[j] = a.relu ? fmaxf(v, 0.f) : v;
+      }
+      storeq(a.act + (int64_t)s * a.total, e0, a.total, vec, out, false);
+    }
+  }
+}
+
+extern "C" int lbbnn_lrt_sample_expand(const float* e_b, const float* var_b, int64_t batch, int64_t out_features, int n_samples,
+                                       const lbbnn_noise* nz, uint64_t noise_group_stride, int flags, float* act, lbbnn_stream s) {
+  LBBNN_REQUIRE(e_b && var_b && act && nz && batch > 0 && out_features > 0 && n_samples > 0, "bad argument");
+  ExpandArgs a;
+  a.e = e_b; a.var = var_b; a.total = batch * out_features; a.n_samples = n_samples; a.relu = (flags & LBBNN_FLAG_RELU) ? 1 : 0;
+  a.noise = make_noise(nz); a.group_stride = noise_group_stride; a.act = act;
+  lrt_sample_expand_kernel<<<(unsigned)elementwise_blocks(a.total), kThreads, 0, (cudaStream_t)s>>>(a);
+  return check_launch("lrt_sample_expand");
+}
+
+extern "C" int lbbnn_lrt_f32_fwd_ex(const lbbnn_layer* L, const float* x, int64_t B, const lbbnn_noise* nz,
+                                    const lbbnn_priors* pri, int var_mode, int flags, float* act, float* ds_factor,
+                                    float* kl_out, float* mv_cache, const float* rowscale, int64_t rows_per_group,
+                                    uint64_t noise_group_stride, void* ws, size_t ws_bytes, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(rows_per_group >= 0 && (rowscale == nullptr || rows_per_group > 0), "rowscale needs rows_per_group > 0");
+  LBBNN_REQUIRE(!(flags & LBBNN_FLAG_MOMENTS) || ((flags & LBBNN_FLAG_SAMPLE) && ds_factor), "FLAG_MOMENTS writes var_b into ds_factor");
+  LBBNN_REQUIRE(noise_group_stride == 0 || (rows_per_group > 0 && (rows_per_group * L->out_features) % 4 == 0),
+                "per-group noise streams need rows_per_group * out_features %% 4 == 0");
   LBBNN_REQUIRE(x && act && B > 0, "x/act NULL or empty batch");
   LBBNN_REQUIRE(pri != nullptr, "priors NULL");
   LBBNN_REQUIRE(var_mode == LBBNN_VAR_REFERENCE || var_mode == LBBNN_VAR_EXACT, "bad var_mode %d", var_mode);
@@ -933,6 +1010,7 @@ extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B
   fa.B = B; fa.K = K; fa.N = N;
   fa.chunks_per_split = sp.chunks_per_split; fa.splits = sp.splits; fa.sample = sample ? 1 : 0;
   fa.part = (float*)(base + w.off_scratch);
+  fa.rowscale = rowscale; fa.rows_per_group = rows_per_group;
   dim3 grid((unsigned)ceil_div(N, F_BN), (unsigned)ceil_div(B, F_BM), (unsigned)sp.splits);
   lrt_f32_fwd_partial<<<grid, kThreads, 0, st>>>(fa);
   if (int rc = check_launch("lrt_f32_fwd_partial")) return rc;
@@ -943,10 +1021,18 @@ extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B
   ea.noise = make_noise(nz);
   ea.flags = flags; ea.act = act; ea.dsf = ds_factor; ea.kl_out = kl_out;
   ea.kl_part = kl_part; ea.n_kl_part = (int)elementwise_blocks(N * K); ea.pri = *pri;
+  ea.noise_group_rows = noise_group_stride ? rows_per_group : 0; ea.noise_group_stride = noise_group_stride;
   int64_t blocks = ceil_div(ceil_div(B * N, 4), kEpiThreads);
   if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
   lrt_f32_fwd_epilogue<<<(unsigned)blocks, kEpiThreads, 0, st>>>(ea);
   return check_launch("lrt_f32_fwd_epilogue");
+}
+
+extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B, const lbbnn_noise* nz,
+                                 const lbbnn_priors* pri, int var_mode, int flags, float* act, float* ds_factor,
+                                 float* kl_out, float* mv_cache, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  return lbbnn_lrt_f32_fwd_ex(L, x, B, nz, pri, var_mode, flags & ~LBBNN_FLAG_MOMENTS, act, ds_factor, kl_out, mv_cache, nullptr, 0,
+                              0, ws, ws_bytes, s);
 }
 
 extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, int64_t B, const float* gact,

@@ -42,7 +42,13 @@ constexpr int kTcThreads = 64 + kEpiWarps * 32; // warp 0 TMA, warp 1 MMA, warps
 constexpr int kTmemCols = 512;
 constexpr int EW = 16;                          // epilogue chunk: columns per tcgen05.ld
 constexpr int kBiasBytes = 2 * 2 * BN * 4;      // [accumulator stage][b_mu | sigma_b^2][BN]
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
+// epilogue scratch after the barriers: the forward's bias terms, or (fused dW update) 4 KB per epilogue warp through which a
+// 32-row x 16-column piece of both accumulators is re-dealt to the lanes row-contiguously (see dw_adam_tile)
+constexpr int kEpiScratchBytes = kEpiWarps * 4096;
+static_assert(kEpiScratchBytes >= kBiasBytes, "scratch holds the bias terms too");
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiScratchBytes;
+// only the fused-update kernels ask for the large scratch (the others keep the shared-memory carve-out, and so L1, as it was)
+constexpr int smem_for(int full, int mode) { return mode == LBBNN_TC_EPI_DW_ADAM ? full : full - kEpiScratchBytes + kBiasBytes; }
 
 using namespace tc;
 
@@ -81,8 +87,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
 __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, int mn) {
   return mn ? umma_desc_mn_sw128(smem_addr) : umma_desc_kmajor_sw128(smem_addr);
 }
-// descriptor advance (in 16-byte units) from one K = 16 MMA to the next
-__device__ __forceinline__ uint64_t umma_kstep(int mn) { return mn ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -118,33 +123,60 @@ struct TcEpi {
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
-// fused dW epilogue: 16 consecutive weights of one output row (N % 4 == 0)
-__device__ __forceinline__ void dw_adam_chunk(const TcEpi& e, const chain::Consts& cc, int64_t N, int64_t row, int64_t col0,
-                                              const float d1[EW], const float d2[EW]) {
+// fused dW epilogue: chain rule + KL gradient + Adam on 4 consecutive weights of one output row (N % 4 == 0)
+__device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts& cc, int64_t off, const float4 dM, const float4 dV) {
+  const float4 mu4 = ld4(e.p_mu + off), rho4 = ld4(e.p_rho + off), lam4 = ld4(e.p_lam + off);
+  const float4 mm4 = ld4(e.m_mu + off), mr4 = ld4(e.m_rho + off), ml4 = ld4(e.m_lam + off);
+  const float4 vm4 = ld4(e.v_mu + off), vr4 = ld4(e.v_rho + off), vl4 = ld4(e.v_lam + off);
+  float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rho[4] = {rho4.x, rho4.y, rho4.z, rho4.w}, lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w};
+  float mm[4] = {mm4.x, mm4.y, mm4.z, mm4.w}, mr[4] = {mr4.x, mr4.y, mr4.z, mr4.w}, ml[4] = {ml4.x, ml4.y, ml4.z, ml4.w};
+  float vm[4] = {vm4.x, vm4.y, vm4.z, vm4.w}, vr[4] = {vr4.x, vr4.y, vr4.z, vr4.w}, vl[4] = {vl4.x, vl4.y, vl4.z, vl4.w};
+  const float d1[4] = {dM.x, dM.y, dM.z, dM.w}, d2[4] = {dV.x, dV.y, dV.z, dV.w};
 #pragma unroll
-  for (int j = 0; j < EW; j += 4) {
-    if (col0 + j >= N) break;
-    const int64_t off = row * N + col0 + j;
-    const float4 mu4 = ld4(e.p_mu + off), rho4 = ld4(e.p_rho + off), lam4 = ld4(e.p_lam + off);
-    const float4 mm4 = ld4(e.m_mu + off), mr4 = ld4(e.m_rho + off), ml4 = ld4(e.m_lam + off);
-    const float4 vm4 = ld4(e.v_mu + off), vr4 = ld4(e.v_rho + off), vl4 = ld4(e.v_lam + off);
-    float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rho[4] = {rho4.x, rho4.y, rho4.z, rho4.w}, lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w};
-    float mm[4] = {mm4.x, mm4.y, mm4.z, mm4.w}, mr[4] = {mr4.x, mr4.y, mr4.z, mr4.w}, ml[4] = {ml4.x, ml4.y, ml4.z, ml4.w};
-    float vm[4] = {vm4.x, vm4.y, vm4.z, vm4.w}, vr[4] = {vr4.x, vr4.y, vr4.z, vr4.w}, vl[4] = {vl4.x, vl4.y, vl4.z, vl4.w};
+  for (int t = 0; t < 4; ++t) {
+    float gm, gr, gl;
+    chain::grads(cc, mu[t], rho[t], lam[t], d1[t], d2[t], gm, gr, gl);
+    chain::adam(cc, mu[t], mm[t], vm[t], gm);
+    chain::adam(cc, rho[t], mr[t], vr[t], gr);
+    chain::adam(cc, lam[t], ml[t], vl[t], gl);
+  }
+  st4(e.p_mu + off, mu[0], mu[1], mu[2], mu[3]); st4(e.p_rho + off, rho[0], rho[1], rho[2], rho[3]);
+  st4(e.p_lam + off, lam[0], lam[1], lam[2], lam[3]);
+  st4(e.m_mu + off, mm[0], mm[1], mm[2], mm[3]); st4(e.m_rho + off, mr[0], mr[1], mr[2], mr[3]);
+  st4(e.m_lam + off, ml[0], ml[1], ml[2], ml[3]);
+  st4(e.v_mu + off, vm[0], vm[1], vm[2], vm[3]); st4(e.v_rho + off, vr[0], vr[1], vr[2], vr[3]);
+  st4(e.v_lam + off, vl[0], vl[1], vl[2], vl[3]);
+}
+
+// One warp's 32 rows x 64 columns of both accumulators.  tcgen05.ld hands every lane ONE ROW (16 columns per load), but the
+// update streams nine fp32 tensors from and to memory: row-per-lane addressing would scatter each warp access over 32 lines,
+// 16 bytes each (r02 first cut: 1.26 ms per 4096^2 layer, 0.9 TB/s).  So each 32 x 16 piece goes through 4 KB of shared memory
+// (row = 8 quads of dM | dV, quad index XOR-swizzled by the row so the row-per-lane stores are conflict-free) and comes back
+// with 4 lanes per row: a warp access covers 8 rows x 64 contiguous bytes, whole sectors.
+__device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts& cc, int64_t M, int64_t N, int64_t row0,
+                                             int64_t col0, uint32_t tbase, float* __restrict__ stg, int lane) {
+#pragma unroll 1
+  for (int c = 0; c < 64 / EW; ++c) {
+    float v1[EW], v2[EW];
+    tmem_ld16(tbase + c * EW, v1);
+    tmem_ld16(tbase + 128 + c * EW, v2);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float gm, gr, gl;
-      chain::grads(cc, mu[t], rho[t], lam[t], d1[j + t], d2[j + t], gm, gr, gl);
-      chain::adam(cc, mu[t], mm[t], vm[t], gm);
-      chain::adam(cc, rho[t], mr[t], vr[t], gr);
-      chain::adam(cc, lam[t], ml[t], vl[t], gl);
+    for (int jj = 0; jj < 4; ++jj) {
+      st4(stg + lane * 32 + ((jj ^ (lane & 7)) << 2), v1[4 * jj], v1[4 * jj + 1], v1[4 * jj + 2], v1[4 * jj + 3]);
+      st4(stg + lane * 32 + (((4 + jj) ^ (lane & 7)) << 2), v2[4 * jj], v2[4 * jj + 1], v2[4 * jj + 2], v2[4 * jj + 3]);
     }
-    st4(e.p_mu + off, mu[0], mu[1], mu[2], mu[3]); st4(e.p_rho + off, rho[0], rho[1], rho[2], rho[3]);
-    st4(e.p_lam + off, lam[0], lam[1], lam[2], lam[3]);
-    st4(e.m_mu + off, mm[0], mm[1], mm[2], mm[3]); st4(e.m_rho + off, mr[0], mr[1], mr[2], mr[3]);
-    st4(e.m_lam + off, ml[0], ml[1], ml[2], ml[3]);
-    st4(e.v_mu + off, vm[0], vm[1], vm[2], vm[3]); st4(e.v_rho + off, vr[0], vr[1], vr[2], vr[3]);
-    st4(e.v_lam + off, vl[0], vl[1], vl[2], vl[3]);
+    __syncwarp();
+    const int qd = lane & 3;
+    const int64_t col = col0 + c * EW + qd * 4;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int rr = it * 8 + (lane >> 2);
+      const float4 dM = ld4(stg + rr * 32 + ((qd ^ (rr & 7)) << 2));
+      const float4 dV = ld4(stg + rr * 32 + (((4 + qd) ^ (rr & 7)) << 2));
+      const int64_t row = row0 + rr;
+      if (row < M && col < N) dw_adam_quad(e, cc, row * N + col, dM, dV);
+    }
+    __syncwarp();
   }
 }
 
@@ -170,7 +202,6 @@ __device__ __forceinline__ void epilogue_chunk(const TcEpi& e, const Noise& nz, 
                                                const float d1[EW], const float d2[EW]) {
   const bool row_ok = row < M;
   if (!row_ok && !(MODE == LBBNN_TC_EPI_DX && e.colsum_part)) return;      // (the bias sums below shuffle across the warp)
-  if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) { dw_adam_chunk(e, cc, N, row, col0, d1, d2); return; }
   const bool fullc = col0 + EW - 1 < N;
   if constexpr (MODE == LBBNN_TC_EPI_RAW) {
     float* p1 = e.d1 + row * N + col0;
@@ -356,7 +387,7 @@ __device__ __forceinline__ void tile_coords(int t, int num_m, int num_n, int& mb
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int MODE>
+template <int MODE, int AMN, int BMN>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                   const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
@@ -399,7 +430,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes;
           mbar_expect_tx(&full_bar[stage], kStageBytes);
-          if (!epi.a_mn) {
+          if constexpr (!AMN) {
             tma_load_2d(sa + 0 * kTileBytes, &tmA1, &full_bar[stage], kb * BK, m0);
             tma_load_2d(sa + 1 * kTileBytes, &tmA2, &full_bar[stage], kb * BK, m0);
           } else {   // (K, M) row-major: two boxes of 64 rows of K x 64 elements of M per operand
@@ -409,7 +440,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
               tma_load_2d(sa + 1 * kTileBytes + h * kMnBoxBytes, &tmA2, &full_bar[stage], m0 + 64 * h, kb * BK);
             }
           }
-          if (!epi.b_mn) {
+          if constexpr (!BMN) {
             tma_load_2d(sa + 2 * kTileBytes, &tmB1, &full_bar[stage], kb * BK, n0);
             tma_load_2d(sa + 3 * kTileBytes, &tmB2, &full_bar[stage], kb * BK, n0);
           } else {
@@ -427,8 +458,9 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
-      const uint32_t idesc = make_idesc(BM, BN, epi.a_mn, epi.b_mn);
-      const uint64_t ka = umma_kstep(epi.a_mn), kbs = umma_kstep(epi.b_mn);
+      constexpr uint32_t idesc = make_idesc(BM, BN, AMN, BMN);
+      constexpr uint64_t ka = AMN ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);   // descriptor advance per K = 16 MMA
+      constexpr uint64_t kbs = BMN ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // epilogue drained this accumulator stage
@@ -438,8 +470,8 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes);
-          const uint64_t a1 = umma_desc(sa + 0 * kTileBytes, epi.a_mn), a2 = umma_desc(sa + 1 * kTileBytes, epi.a_mn);
-          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, epi.b_mn), b2 = umma_desc(sa + 3 * kTileBytes, epi.b_mn);
+          const uint64_t a1 = umma_desc(sa + 0 * kTileBytes, AMN), a2 = umma_desc(sa + 1 * kTileBytes, AMN);
+          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, BMN), b2 = umma_desc(sa + 3 * kTileBytes, BMN);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // K-major: advance the start address inside the swizzle row; MN-major: by two 8-row groups
@@ -484,13 +516,17 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
+      if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
+        dw_adam_tile(epi, cc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < 64 / EW; ++c) {
-        float v1[EW], v2[EW];
-        tmem_ld16(tbase + c * EW, v1);
-        tmem_ld16(tbase + 128 + c * EW, v2);
-        const int cl = half * 64 + c * EW;
-        epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        for (int c = 0; c < 64 / EW; ++c) {
+          float v1[EW], v2[EW];
+          tmem_ld16(tbase + c * EW, v1);
+          tmem_ld16(tbase + 128 + c * EW, v2);
+          const int cl = half * 64 + c * EW;
+          epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -518,7 +554,8 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
 constexpr int kStages2 = 4;
 constexpr int kBHalfBytes = (BN / 2) * BK * 2;                 // 8 KB: this CTA's 64 rows of a B tile
 constexpr int kStageBytes2 = 2 * kTileBytes + 2 * kBHalfBytes;  // 48 KB
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kBiasBytes;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kEpiScratchBytes;
+static_assert(kSmemBytes <= 232448 && kSmemBytes2 <= 232448, "over the 227 KB shared-memory limit");
 constexpr int kGroupM2 = kGroupM / 2;                          // in 256-row blocks
 
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -541,7 +578,7 @@ __device__ __forceinline__ void tile_coords2(int t, int num_m2, int num_n, int g
   mb2 = m_first + (r - nb * gm);
 }
 
-template <int MODE>
+template <int MODE, int AMN, int BMN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                        const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, const TcEpi epi,
@@ -588,7 +625,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
           uint8_t* sa = smem + stage * kStageBytes2;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
           mbar_expect_tx_cluster(lead_full, kStageBytes2);
-          if (!epi.a_mn) {
+          if constexpr (!AMN) {
             tma_load_2d_pair(sa, &tmA1, lead_full, kb * BK, m0);
             tma_load_2d_pair(sa + kTileBytes, &tmA2, lead_full, kb * BK, m0);
           } else {   // (K, M) row-major: two boxes of 64 rows of K x 64 elements of M per operand
@@ -598,7 +635,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
               tma_load_2d_pair(sa + kTileBytes + h * kMnBoxBytes, &tmA2, lead_full, m0 + 64 * h, kb * BK);
             }
           }
-          if (!epi.b_mn) {
+          if constexpr (!BMN) {
             tma_load_2d_pair(sa + 2 * kTileBytes, &tmB1, lead_full, kb * BK, n0h);
             tma_load_2d_pair(sa + 2 * kTileBytes + kBHalfBytes, &tmB2, lead_full, kb * BK, n0h);
           } else {   // this CTA's 64 elements of N: one box
@@ -613,8 +650,9 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
     // ===== MMA issuer (leader CTA only) =====
     if (lane == 0 && rank == 0) {
       int stage = 0; uint32_t phase = 0; int it = 0;
-      const uint32_t idesc = make_idesc(2 * BM, BN, epi.a_mn, epi.b_mn);
-      const uint64_t ka = umma_kstep(epi.a_mn), kbs = umma_kstep(epi.b_mn);
+      constexpr uint32_t idesc = make_idesc(2 * BM, BN, AMN, BMN);
+      constexpr uint64_t ka = AMN ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);   // descriptor advance per K = 16 MMA
+      constexpr uint64_t kbs = BMN ? (uint64_t)(2048 >> 4) : (uint64_t)((UMMA_K * 2) >> 4);
       for (int t = cluster_id; t < num_tiles; t += num_clusters, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], ((it >> 1) & 1) ^ 1);   // both CTAs' epilogues drained this accumulator stage
@@ -624,9 +662,9 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * kStageBytes2);
-          const uint64_t a1 = umma_desc(sa, epi.a_mn), a2 = umma_desc(sa + kTileBytes, epi.a_mn);
-          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, epi.b_mn);
-          const uint64_t b2 = umma_desc(sa + 2 * kTileBytes + kBHalfBytes, epi.b_mn);
+          const uint64_t a1 = umma_desc(sa, AMN), a2 = umma_desc(sa + kTileBytes, AMN);
+          const uint64_t b1 = umma_desc(sa + 2 * kTileBytes, BMN);
+          const uint64_t b2 = umma_desc(sa + 2 * kTileBytes + kBHalfBytes, BMN);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint32_t acc = (kb | k) ? 1u : 0u;
@@ -670,13 +708,17 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
+      if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
+        dw_adam_tile(epi, cc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < 64 / EW; ++c) {
-        float v1[EW], v2[EW];
-        tmem_ld16(tbase + c * EW, v1);
-        tmem_ld16(tbase + 128 + c * EW, v2);
-        const int cl = half * 64 + c * EW;
-        epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        for (int c = 0; c < 64 / EW; ++c) {
+          float v1[EW], v2[EW];
+          tmem_ld16(tbase + c * EW, v1);
+          tmem_ld16(tbase + 128 + c * EW, v2);
+          const int cl = half * 64 + c * EW;
+          epilogue_chunk<MODE>(epi, nz, cc, M, N, row, n0 + cl, sbias, cl, v1, v2);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -771,24 +813,31 @@ int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, in
     const int clusters = (int)(tiles2 < sm_count() / 2 ? tiles2 : sm_count() / 2);
     const char* ge = getenv("LBBNN_TC_GROUP");      // 256-row blocks per tile group (experiments)
     const int group = ge && atoi(ge) > 0 ? atoi(ge) : kGroupM2;
-    switch (epi.mode) {
-#define LBBNN_PAIR_CASE(MODE_)                                                                                                       \
-  case MODE_: {                                                                                                                      \
+    const int key = epi.mode * 4 + epi.a_mn * 2 + epi.b_mn;
+    switch (key) {
+#define LBBNN_PAIR_CASE(MODE_, A_, B_)                                                                                                \
+  case (MODE_) * 4 + (A_) * 2 + (B_): {                                                                                              \
     static bool attr_set_ = false;                                                                                                   \
     if (!attr_set_) {                                                                                                                \
-      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16_pair<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2));    \
+      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16_pair<MODE_, A_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                      smem_for(kSmemBytes2, MODE_)));                                                               \
       attr_set_ = true;                                                                                                              \
     }                                                                                                                                \
-    tc_dual_gemm_bf16_pair<MODE_><<<2 * clusters, kTcThreads, kSmemBytes2, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K,   \
-                                                                                  group);                                           \
+    tc_dual_gemm_bf16_pair<MODE_, A_, B_><<<2 * clusters, kTcThreads, smem_for(kSmemBytes2, MODE_), st>>>(mA1, mA2, mB1, mB2, epi, \
+                                                                                                           (int)M, (int)N, (int)K, \
+                                                                                                           group);                 \
     break;                                                                                                                           \
   }
-      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW)
-      LBBNN_PAIR_CASE(LBBNN_TC_EPI_FWD)
-      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DX)
-      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DW_ADAM)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW, 0, 0)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW, 0, 1)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW, 1, 0)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_RAW, 1, 1)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_FWD, 0, 0)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DX, 0, 0)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DX, 0, 1)
+      LBBNN_PAIR_CASE(LBBNN_TC_EPI_DW_ADAM, 1, 1)
 #undef LBBNN_PAIR_CASE
-      default: LBBNN_REQUIRE(false, "bad epilogue mode %d", epi.mode);
+      default: LBBNN_REQUIRE(false, "no kernel for epilogue mode %d with operand majors (%d, %d)", epi.mode, epi.a_mn, epi.b_mn);
     }
     return check_launch("tc_dual_gemm_bf16_pair");
   }
@@ -801,23 +850,30 @@ int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, in
   }
   const int64_t tiles = ceil_div(M, BM) * ceil_div(N, BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  switch (epi.mode) {
-#define LBBNN_ONE_CASE(MODE_)                                                                                                  \
-  case MODE_: {                                                                                                                \
+  const int key = epi.mode * 4 + epi.a_mn * 2 + epi.b_mn;
+  switch (key) {
+#define LBBNN_ONE_CASE(MODE_, A_, B_)                                                                                          \
+  case (MODE_) * 4 + (A_) * 2 + (B_): {                                                                                       \
     static bool attr_set_ = false;                                                                                             \
     if (!attr_set_) {                                                                                                          \
-      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16<MODE_>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));    \
+      LBBNN_CUDA(cudaFuncSetAttribute(tc_dual_gemm_bf16<MODE_, A_, B_>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                      smem_for(kSmemBytes, MODE_)));                                                          \
       attr_set_ = true;                                                                                                        \
     }                                                                                                                          \
-    tc_dual_gemm_bf16<MODE_><<<grid, kTcThreads, kSmemBytes, st>>>(mA1, mA2, mB1, mB2, epi, (int)M, (int)N, (int)K);           \
+    tc_dual_gemm_bf16<MODE_, A_, B_><<<grid, kTcThreads, smem_for(kSmemBytes, MODE_), st>>>(mA1, mA2, mB1, mB2, epi, (int)M,   \
+                                                                                             (int)N, (int)K);                   \
     break;                                                                                                                     \
   }
-    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW)
-    LBBNN_ONE_CASE(LBBNN_TC_EPI_FWD)
-    LBBNN_ONE_CASE(LBBNN_TC_EPI_DX)
-    LBBNN_ONE_CASE(LBBNN_TC_EPI_DW_ADAM)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW, 0, 0)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW, 0, 1)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW, 1, 0)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_RAW, 1, 1)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_FWD, 0, 0)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_DX, 0, 0)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_DX, 0, 1)
+    LBBNN_ONE_CASE(LBBNN_TC_EPI_DW_ADAM, 1, 1)
 #undef LBBNN_ONE_CASE
-    default: LBBNN_REQUIRE(false, "bad epilogue mode %d", epi.mode);
+    default: LBBNN_REQUIRE(false, "no kernel for epilogue mode %d with operand majors (%d, %d)", epi.mode, epi.a_mn, epi.b_mn);
   }
   return check_launch("tc_dual_gemm_bf16");
 }

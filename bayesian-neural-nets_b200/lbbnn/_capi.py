@@ -21,7 +21,7 @@ if not os.path.exists(LIB_PATH):
 lib = C.CDLL(LIB_PATH)
 
 VAR_REFERENCE, VAR_EXACT = 0, 1
-FLAG_SAMPLE, FLAG_RELU, FLAG_KL, FLAG_ACCUMULATE, FLAG_MASK_DX = 1, 2, 4, 8, 16
+FLAG_SAMPLE, FLAG_RELU, FLAG_KL, FLAG_ACCUMULATE, FLAG_MASK_DX, FLAG_MOMENTS = 1, 2, 4, 8, 16, 32
 PACK_PAIR, PACK_SQUARE, PACK_SCALE = 0, 1, 2
 MF_SAMPLE, MF_MEDIMEAN, MF_JOINTMEAN = 0, 1, 2
 MF_FLAG_LOGPROBS, MF_FLAG_LP_ON_WS, MF_FLAG_EXACT_GAMMA, MF_FLAG_EXACT_WPRIOR, MF_FLAG_EXACT_GPRIOR = 1, 2, 4, 8, 16
@@ -122,6 +122,9 @@ SIGNATURES = {
     "lbbnn_lrt_f32_mv_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_lrt_f32_fwd": (_INT, [C.POINTER(Layer), _P, _I64, C.POINTER(Noise), C.POINTER(Priors), _INT, _INT,
                                  _P, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_lrt_f32_fwd_ex": (_INT, [C.POINTER(Layer), _P, _I64, C.POINTER(Noise), C.POINTER(Priors), _INT, _INT,
+                                    _P, _P, _P, _P, _P, _I64, _U64, _P, _SZ, _P]),
+    "lbbnn_lrt_sample_expand": (_INT, [_P, _P, _I64, _I64, _INT, C.POINTER(Noise), _U64, _INT, _P, _P]),
     "lbbnn_lrt_f32_bwd_params": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _F,
                                         C.POINTER(LayerGrads), _P, _SZ, _P]),
     "lbbnn_lrt_f32_bwd_input": (_INT, [C.POINTER(Layer), _P, _I64, _P, _P, C.POINTER(Priors), _INT, _INT, _P, _P,

@@ -37,7 +37,8 @@ enum {
   LBBNN_FLAG_RELU = 2,        /* fwd: write relu(act) (the F.relu of LRT:208-209 fused in) */
   LBBNN_FLAG_KL = 4,          /* fwd: also reduce the layer's KL (LRT:182-194) into kl_out */
   LBBNN_FLAG_ACCUMULATE = 8,  /* bwd: grads += instead of = */
-  LBBNN_FLAG_MASK_DX = 16     /* bwd: dx *= (x > 0), i.e. back through the relu that produced x */
+  LBBNN_FLAG_MASK_DX = 16,    /* bwd: dx *= (x > 0), i.e. back through the relu that produced x */
+  LBBNN_FLAG_MOMENTS = 32     /* fwd_ex: no noise; act <- e_b, ds_factor <- var_b (LRT:172-173) */
 };
 
 typedef void* lbbnn_stream; /* cudaStream_t */
@@ -120,6 +121,25 @@ LBBNN_API int lbbnn_lrt_f32_fwd(const lbbnn_layer* layer, const float* x, int64_
                                 const lbbnn_noise* noise, const lbbnn_priors* priors, int var_mode, int flags,
                                 float* act, float* ds_factor, float* kl_out, float* mv_cache,
                                 void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+/* The same forward for the batched posterior-predictive loop (test_ensemble, LRT:239-265 / MNF:287-318), where `batch`
+ * stacks rows_per_group input rows for each of several MC samples:
+ *   rowscale (groups, in) or NULL: rows of group g enter the MEAN product as x .* rowscale[g] (MNF's z of that sample,
+ *     MNF:197; the variance product keeps x^2, MNF:198) -- layer->z must then be NULL;
+ *   noise_group_stride != 0: native noise per group -- rows of group g draw from stream_id + g * noise_group_stride with
+ *     element index (row - g * rows_per_group) * out + col, i.e. what a rows_per_group-row call on that stream draws;
+ *   FLAG_MOMENTS: no noise at all; act <- e_b (LRT:172), ds_factor <- var_b (LRT:173): what layer 1 computes ONCE per
+ *     test batch when all samples share the input (LRT:247), expanded per sample by lbbnn_lrt_sample_expand. */
+LBBNN_API int lbbnn_lrt_f32_fwd_ex(const lbbnn_layer* layer, const float* x, int64_t batch, const lbbnn_noise* noise,
+                                   const lbbnn_priors* priors, int var_mode, int flags, float* act, float* ds_factor,
+                                   float* kl_out, float* mv_cache, const float* rowscale, int64_t rows_per_group,
+                                   uint64_t noise_group_stride, void* workspace, size_t workspace_bytes, lbbnn_stream s);
+
+/* act (n_samples, batch, out) = [relu](e_b + sqrt(var_b) eps_s): the per-sample part of layer 1 of that loop; eps_s is
+ * injected ((n_samples, batch, out) in noise->eps) or drawn from stream_id + s * noise_group_stride (FLAG_RELU honoured). */
+LBBNN_API int lbbnn_lrt_sample_expand(const float* e_b, const float* var_b, int64_t batch, int64_t out_features,
+                                      int n_samples, const lbbnn_noise* noise, uint64_t noise_group_stride, int flags,
+                                      float* act, lbbnn_stream s);
 
 LBBNN_API int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* layer, const float* x, int64_t batch,
                                        const float* gact, const float* ds_factor,

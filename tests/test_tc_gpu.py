@@ -445,8 +445,8 @@ def test_wide_trainer_fused_update_matches_separate_passes(use_graph):
         assert abs(outs[0]["kl"] - outs[1]["kl"]) <= 1e-6 * abs(outs[0]["kl"]), step
     for la, lb_ in zip(nets[0].layers, nets[1].layers):
         for k in case["layers"][0]:
-            assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 1e-6, k
-    assert C.rel_err(trs[1].exp_avg, trs[0].exp_avg) < 1e-6 and C.rel_err(trs[1].exp_avg_sq, trs[0].exp_avg_sq) < 1e-6
+            assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 5e-6, k
+    assert C.rel_err(trs[1].exp_avg, trs[0].exp_avg) < 5e-6 and C.rel_err(trs[1].exp_avg_sq, trs[0].exp_avg_sq) < 5e-6
 
 
 # ---- 3xTF32 linear layer (csrc/tc_gemm_tf32.cu): fp32 accuracy on tcgen05 --------------------------------------------
