@@ -7,6 +7,8 @@ from .lrt import BayesianLinear, BayesianNetwork, LayerConfig, lrt_linear, manua
 from . import flows, mf, mnf
 from .engine import GraphedTrainer, LRTTrainer, LRTTensorCoreTrainer, MultiTensorAdam
 from . import vd
+from . import predict
+from .predict import EnsemblePredictor, mf_outofsample
 
 __all__ = ["BayesianLinear", "BayesianNetwork", "GraphedTrainer", "LayerConfig", "LRTTrainer", "LRTTensorCoreTrainer", "LbbnnError", "MultiTensorAdam", "lrt_linear",
-           "manual_seed", "predict_ensemble", "mf", "mnf", "flows", "vd", "philox_normal", "philox_uniform"]
+           "manual_seed", "predict_ensemble", "predict", "EnsemblePredictor", "mf_outofsample", "mf", "mnf", "flows", "vd", "philox_normal", "philox_uniform"]

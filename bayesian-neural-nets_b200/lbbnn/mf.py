@@ -587,10 +587,18 @@ class MCPredictor:
         for lane in self.lanes:
             lane.reset(first_sample)
 
-    def run(self, x, samples, first_sample=0):
-        """Accumulate `samples` weight samples with global indices first_sample.. on this rank."""
+    def run(self, x, samples, first_sample=0, masks=None):
+        """Accumulate `samples` weight samples with global indices first_sample.. on this rank.
+        masks: per-layer {0, 1} tensors that REPLACE the Bernoulli(alpha) draw of the inclusion masks -- the
+        median-probability model [alpha > 0.5] of `outofsample(medimod=True)` (MF:462-465); weights and biases are still
+        sampled.  (A mask value of 1 / 0 is drawn with certainty: the sampler compares a uniform in (0, 1) with it.)"""
         self.x.copy_(x.reshape(self.x.shape), non_blocking=True)
         self._prepare()
+        if masks is not None:
+            if not self.prepared:
+                raise K.LbbnnError("fixed masks need samples_per_launch > 1 (the batched sampler reads alpha from a buffer)")
+            for a, m in zip(self.alpha, masks):
+                a.copy_(m)
         # whole launches are dealt to the lanes as contiguous index ranges; the partial last launch goes to the last lane
         full, rest = divmod(int(samples), self.SB)
         nl = len(self.lanes)

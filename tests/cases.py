@@ -204,3 +204,26 @@ def vd_net_case(seed, batch, sizes=VD_SIZES, classes=10):
     y = torch.from_numpy(rng.integers(0, classes, size=(batch,))).long()
     zetas = [t(rng.standard_normal(size=(batch, m))) for _, m in sizes]
     return {"layers": layers, "x": x, "y": y, "zetas": zetas}
+
+
+def ensemble_case(seed, batch, samples, sizes=MNIST_SIZES, kind="lrt", T=2):
+    """Inputs of the posterior-predictive loops (test_ensemble / outofsample): a network (reference init; lambdal spread so
+    the inclusion probabilities span (0,1)), a test batch and the noise of every MC sample: LRT eps[l] (S, B, out); MNF
+    additionally eps_z[l] (S, B, in) and z_masks[l] = T x (S, B, in) -- the reference pushes all B rows through the flow
+    and keeps the last (MNF:187)."""
+    rng = np.random.default_rng(seed)
+    init = O.init_lrt_params if kind == "lrt" else (lambda r, i, o: O.init_mnf_params(r, i, o, T))
+    layers = [init(rng, i, o) for i, o in sizes]
+    for p in layers:
+        p["lambdal"] = t(rng.normal(0.0, 2.0, size=tuple(p["lambdal"].shape)))
+        if kind != "lrt":      # a q0 wide enough for z to matter
+            p["q0_log_var"] = t(-2.0 + 0.3 * rng.standard_normal(size=tuple(p["q0_log_var"].shape)))
+            p["q0_mean"] = t(1.0 + 0.1 * rng.standard_normal(size=tuple(p["q0_mean"].shape)))
+    x = t(rng.uniform(0.0, 1.0, size=(batch, sizes[0][0])))
+    eps = [t(rng.standard_normal(size=(samples, batch, o))) for _, o in sizes]
+    out = {"layers": layers, "x": x, "eps": eps}
+    if kind != "lrt":
+        out["eps_z"] = [t(rng.standard_normal(size=(samples, batch, i))) for i, _ in sizes]
+        out["z_masks"] = [[t((rng.uniform(0.0, 1.0, size=(samples, batch, i)) < 0.5).astype(np.float32)) for _ in range(T)]
+                          for i, _ in sizes]
+    return out

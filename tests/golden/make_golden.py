@@ -458,6 +458,71 @@ def golden_ctor():
     print("ctor golden written;", len(out), "entries")
 
 
+def _reference_ensemble_statistics(outputs):
+    """The NumPy side of the reference's loops on the stacked outputs (S, B, C): `mydata_means` (LRT:249-260), the ensemble
+    prediction outputs[0:10].mean(0) (LRT:262-263), outofsample's entropies (LRT:325-330) and its prediction from
+    outputs[1:S].mean(0) (LRT:332-334)."""
+    from scipy.special import expit
+    S, B, _ = outputs.shape
+    means = None
+    for i in range(S):
+        tmp = expit(outputs[i].detach().cpu().numpy())
+        for j in range(B):
+            tmp[j] /= np.sum(tmp[j])
+        means = tmp if means is None else means + tmp
+    means /= S
+    ent = np.array([-np.sum(means[j] * np.log(means[j])) for j in range(B)])
+    return {"mean_prob": means, "ensemble": outputs[0:10].mean(0).max(1)[1].numpy(), "entropy": ent,
+            "oos_pred": outputs[1:S].mean(0).max(1)[1].numpy()}
+
+
+def golden_ensemble():
+    """test_ensemble / outofsample bodies run with the reference's own LRT and MNF networks under replayed noise."""
+    out = {}
+    # ---- LRT ----
+    S, B = 12, 52
+    case = C.ensemble_case(seed=120, batch=B, samples=S, kind="lrt")
+    ns = H.load_reference_classes("LBBNN-GP-MF-LRT.py")
+    net = ns["BayesianNetwork"]()
+    for lay, p in zip((net.l1, net.l2, net.l3), case["layers"]):
+        _load_params(lay, p)
+    net.eval()
+    outputs = torch.zeros(S, B, 10)
+    with torch.no_grad():
+        for s in range(S):
+            with H.replay(H.NoiseQueue([("normal", case["eps"][l][s]) for l in range(3)])):
+                outputs[s] = net(case["x"].view(B, 1, 28, 28), sample=True)
+        mean_out = net(case["x"].view(B, 1, 28, 28), sample=False)
+    st = _reference_ensemble_statistics(outputs)
+    out["lrt_outputs"] = outputs.numpy()
+    out["lrt_posterior_mean_logp"] = mean_out.numpy()
+    for k, v in st.items():
+        out["lrt_" + k] = v
+    # ---- MNF ----
+    S, B = 6, 52
+    case = C.ensemble_case(seed=121, batch=B, samples=S, kind="mnf")
+    ns = H.load_reference_classes("LBBNN-GP-MF-MNF.py", flows_module="flows2")
+    net = ns["BayesianNetwork"]()
+    for lay, p in zip((net.l1, net.l2, net.l3), case["layers"]):
+        _load_named(lay, C.flat_named(p))
+    net.eval()
+    outputs = torch.zeros(S, B, 10)
+    with torch.no_grad():
+        for s in range(S):
+            q = []
+            for l in range(3):      # eval + sample=True: sample_z(B) then eps (MNF:193-200); no KL branch
+                q += [("normal", case["eps_z"][l][s])] + [("uniform", 1.0 - m[s] * 0.75) for m in case["z_masks"][l]]
+                q += [("normal", case["eps"][l][s])]
+            with H.replay(H.NoiseQueue(q)):
+                outputs[s] = net(case["x"].view(B, 1, 28, 28), sample=True)
+    st = _reference_ensemble_statistics(outputs)
+    out["mnf_outputs"] = outputs.numpy()
+    for k, v in st.items():
+        out["mnf_" + k] = v
+    np.savez_compressed(os.path.join(HERE, "ensemble.npz"), **out)
+    print("ensemble golden written; lrt ensemble acc-agnostic preds", out["lrt_ensemble"][:8], "mnf", out["mnf_ensemble"][:8])
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
     if what in ("vd_train", "all"):
@@ -476,3 +541,5 @@ if __name__ == "__main__":
         golden_mnf_iaf()
     if what in ("ctor", "all"):
         golden_ctor()
+    if what in ("ensemble", "all"):
+        golden_ensemble()

@@ -268,3 +268,24 @@ def test_vd_training_steps_match_reference():
         assert C.rel_err(d["sample"], g[f"theta_l{li}_sample"]) < 5e-6, li
         assert abs(d["l2"] - float(g[f"theta_l{li}_l2"])) / float(g[f"theta_l{li}_l2"]) < 5e-6, li
         assert np.array_equal(g[f"alpha_l{li}"], np.full_like(g[f"alpha_l{li}"], 0.2)), li
+
+
+def test_ensemble_outputs_of_the_reference_networks():
+    """tests/golden/ensemble.npz: the oracle's LRT / MNF forwards reproduce every MC sample's log-softmax output of the
+    reference networks in eval mode (the inputs of test_ensemble / outofsample's statistics)."""
+    g = _npz("ensemble.npz")
+    S, B = 12, 52
+    case = C.ensemble_case(seed=120, batch=B, samples=S, kind="lrt")
+    for s in (0, 5, 11):
+        logp = O.lrt_net_forward(case["x"], case["layers"], [e[s] for e in case["eps"]], True)
+        assert C.rel_err(logp, g["lrt_outputs"][s]) < TOL
+    assert C.rel_err(O.lrt_net_forward(case["x"], case["layers"], None, False), g["lrt_posterior_mean_logp"]) < TOL
+    S = 6
+    case = C.ensemble_case(seed=121, batch=B, samples=S, kind="mnf")
+    for s in (0, 5):
+        h = case["x"]
+        for l, p in enumerate(case["layers"]):
+            nz = {"eps_z": case["eps_z"][l][s], "z_masks": [m[s] for m in case["z_masks"][l]], "eps": case["eps"][l][s]}
+            h, _ = O.mnf_forward(h, p, nz, sample=True, calc_kl=False)
+            h = torch.relu(h) if l < 2 else torch.log_softmax(h, 1)
+        assert C.rel_err(h, g["mnf_outputs"][s]) < TOL
