@@ -124,27 +124,14 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
 // ---- fused dW epilogue: chain rule + KL gradient + Adam on the accumulators --------------------------------------------------
-// nine fp32 tensors stream through: parameters mu, rho, lambda and both Adam moments of each.  They are touched once per step:
-// loads / stores carry the streaming (evict-first) hint so that they do not displace the GEMM's operand panels from L2.
-struct Quad9 { float4 mu, rho, lam, mm, mr, ml, vm, vr, vl; };
-__device__ __forceinline__ Quad9 load9(const TcEpi& e, int64_t off) {
-  Quad9 q;
-  q.mu = __ldcs(reinterpret_cast<const float4*>(e.p_mu + off)); q.rho = __ldcs(reinterpret_cast<const float4*>(e.p_rho + off));
-  q.lam = __ldcs(reinterpret_cast<const float4*>(e.p_lam + off));
-  q.mm = __ldcs(reinterpret_cast<const float4*>(e.m_mu + off)); q.mr = __ldcs(reinterpret_cast<const float4*>(e.m_rho + off));
-  q.ml = __ldcs(reinterpret_cast<const float4*>(e.m_lam + off));
-  q.vm = __ldcs(reinterpret_cast<const float4*>(e.v_mu + off)); q.vr = __ldcs(reinterpret_cast<const float4*>(e.v_rho + off));
-  q.vl = __ldcs(reinterpret_cast<const float4*>(e.v_lam + off));
-  return q;
-}
-__device__ __forceinline__ void stcs4(float* p, const float v[4]) {
-  __stcs(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
-}
-__device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts& cc, int64_t off, const Quad9& q, const float4 dM,
-                                             const float4 dV) {
-  float mu[4] = {q.mu.x, q.mu.y, q.mu.z, q.mu.w}, rho[4] = {q.rho.x, q.rho.y, q.rho.z, q.rho.w}, lam[4] = {q.lam.x, q.lam.y, q.lam.z, q.lam.w};
-  float mm[4] = {q.mm.x, q.mm.y, q.mm.z, q.mm.w}, mr[4] = {q.mr.x, q.mr.y, q.mr.z, q.mr.w}, ml[4] = {q.ml.x, q.ml.y, q.ml.z, q.ml.w};
-  float vm[4] = {q.vm.x, q.vm.y, q.vm.z, q.vm.w}, vr[4] = {q.vr.x, q.vr.y, q.vr.z, q.vr.w}, vl[4] = {q.vl.x, q.vl.y, q.vl.z, q.vl.w};
+// 4 consecutive weights of one output row (N % 4 == 0): nine fp32 tensors stream through (mu, rho, lambda + both Adam moments)
+__device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts& cc, int64_t off, const float4 dM, const float4 dV) {
+  const float4 mu4 = ld4(e.p_mu + off), rho4 = ld4(e.p_rho + off), lam4 = ld4(e.p_lam + off);
+  const float4 mm4 = ld4(e.m_mu + off), mr4 = ld4(e.m_rho + off), ml4 = ld4(e.m_lam + off);
+  const float4 vm4 = ld4(e.v_mu + off), vr4 = ld4(e.v_rho + off), vl4 = ld4(e.v_lam + off);
+  float mu[4] = {mu4.x, mu4.y, mu4.z, mu4.w}, rho[4] = {rho4.x, rho4.y, rho4.z, rho4.w}, lam[4] = {lam4.x, lam4.y, lam4.z, lam4.w};
+  float mm[4] = {mm4.x, mm4.y, mm4.z, mm4.w}, mr[4] = {mr4.x, mr4.y, mr4.z, mr4.w}, ml[4] = {ml4.x, ml4.y, ml4.z, ml4.w};
+  float vm[4] = {vm4.x, vm4.y, vm4.z, vm4.w}, vr[4] = {vr4.x, vr4.y, vr4.z, vr4.w}, vl[4] = {vl4.x, vl4.y, vl4.z, vl4.w};
   const float d1[4] = {dM.x, dM.y, dM.z, dM.w}, d2[4] = {dV.x, dV.y, dV.z, dV.w};
 #pragma unroll
   for (int t = 0; t < 4; ++t) {
@@ -154,48 +141,25 @@ __device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts
     chain::adam(cc, rho[t], mr[t], vr[t], gr);
     chain::adam(cc, lam[t], ml[t], vl[t], gl);
   }
-  stcs4(e.p_mu + off, mu); stcs4(e.p_rho + off, rho); stcs4(e.p_lam + off, lam);
-  stcs4(e.m_mu + off, mm); stcs4(e.m_rho + off, mr); stcs4(e.m_lam + off, ml);
-  stcs4(e.v_mu + off, vm); stcs4(e.v_rho + off, vr); stcs4(e.v_lam + off, vl);
-}
-
-// L2 prefetch of the nine (32 rows x 64 columns) fp32 pieces one warp will update in its next tile: issued while the warp
-// would otherwise only wait for that tile's MMAs, so the update's loads find their lines in L2 instead of paying HBM latency
-// (with 8 epilogue warps per SM the loads in flight bound the update: 36 KB per SM per round trip).
-__device__ __forceinline__ void dw_adam_prefetch(const TcEpi& e, int64_t M, int64_t N, int64_t row0, int64_t col0, int lane) {
-  const float* base[9] = {e.p_mu, e.p_rho, e.p_lam, e.m_mu, e.m_rho, e.m_lam, e.v_mu, e.v_rho, e.v_lam};
-  // 32 rows x 2 lines of 128 B per tensor: lane = row, two lines each
-  const int64_t row = row0 + lane;
-  if (row >= M) return;
-#pragma unroll
-  for (int t = 0; t < 9; ++t) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t col = col0 + h * 32;
-      if (col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(base[t] + row * N + col));
-    }
-  }
+  st4(e.p_mu + off, mu[0], mu[1], mu[2], mu[3]); st4(e.p_rho + off, rho[0], rho[1], rho[2], rho[3]);
+  st4(e.p_lam + off, lam[0], lam[1], lam[2], lam[3]);
+  st4(e.m_mu + off, mm[0], mm[1], mm[2], mm[3]); st4(e.m_rho + off, mr[0], mr[1], mr[2], mr[3]);
+  st4(e.m_lam + off, ml[0], ml[1], ml[2], ml[3]);
+  st4(e.v_mu + off, vm[0], vm[1], vm[2], vm[3]); st4(e.v_rho + off, vr[0], vr[1], vr[2], vr[3]);
+  st4(e.v_lam + off, vl[0], vl[1], vl[2], vl[3]);
 }
 
 // One warp's 32 rows x 64 columns of both accumulators.  tcgen05.ld hands every lane ONE ROW (16 columns per load), but the
 // update streams nine fp32 tensors from and to memory: row-per-lane addressing would scatter each warp access over 32 lines,
-// 16 bytes each (r02 first cut: 1.26 ms per 4096^2 layer, 0.9 TB/s).  So each 32 x 16 piece goes through 4 KB of shared memory
+// 16 bytes each (first cut: 1.26 ms per 4096^2 layer, 0.9 TB/s).  So each 32 x 16 piece goes through 4 KB of shared memory
 // (row = 8 quads of dM | dV, quad index XOR-swizzled by the row so the row-per-lane stores are conflict-free) and comes back
-// with 4 lanes per row: a warp access covers 8 rows x 64 contiguous bytes, whole sectors.  The 16 (piece, row-group) steps of a
-// tile are software-pipelined: the nine loads of step i + 1 are in flight while step i is computed and stored.
+// with 4 lanes per row: a warp access covers 8 rows x 64 contiguous bytes, whole sectors (0.56-0.63 ms; raw GEMM 0.42-0.48,
+// GEMM + separate update pass 0.69-0.74 on the same boxes).  Measured and dropped (profiles/r02_ab_wide_calls.txt): a 2-deep
+// register pipeline of the nine loads (spills at the 168-register cap of a 10-warp CTA), an L2 prefetch of the next tile's
+// parameters during the MMA wait, streaming (evict-first) hints -- each 5-15 % SLOWER: the fused kernel moves
+// 1.2 GB of optimiser state next to ~0.75 GB of operand traffic and is bound by HBM / the power cap, not by load latency.
 __device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts& cc, int64_t M, int64_t N, int64_t row0,
                                              int64_t col0, uint32_t tbase, float* __restrict__ stg, int lane) {
-  const int qd = lane & 3, rl = lane >> 2;
-  auto offset_of = [&](int step, bool& ok) {
-    const int c = step >> 2, it = step & 3;
-    const int64_t row = row0 + it * 8 + rl, col = col0 + c * EW + qd * 4;
-    ok = row < M && col < N;
-    return row * N + col;
-  };
-  bool ok_cur, ok_nxt = false;
-  int64_t off_cur = offset_of(0, ok_cur), off_nxt = 0;
-  Quad9 cur = {}, nxt = {};
-  if (ok_cur) cur = load9(e, off_cur);
 #pragma unroll 1
   for (int c = 0; c < 64 / EW; ++c) {
     float v1[EW], v2[EW];
@@ -207,18 +171,15 @@ __device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts
       st4(stg + lane * 32 + (((4 + jj) ^ (lane & 7)) << 2), v2[4 * jj], v2[4 * jj + 1], v2[4 * jj + 2], v2[4 * jj + 3]);
     }
     __syncwarp();
+    const int qd = lane & 3;
+    const int64_t col = col0 + c * EW + qd * 4;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
-      const int step = c * 4 + it;
-      if (step + 1 < 16) {
-        off_nxt = offset_of(step + 1, ok_nxt);
-        if (ok_nxt) nxt = load9(e, off_nxt);
-      }
-      const int rr = it * 8 + rl;
+      const int rr = it * 8 + (lane >> 2);
       const float4 dM = ld4(stg + rr * 32 + ((qd ^ (rr & 7)) << 2));
       const float4 dV = ld4(stg + rr * 32 + (((4 + qd) ^ (rr & 7)) << 2));
-      if (ok_cur) dw_adam_quad(e, cc, off_cur, cur, dM, dV);
-      cur = nxt; off_cur = off_nxt; ok_cur = ok_nxt;
+      const int64_t row = row0 + rr;
+      if (row < M && col < N) dw_adam_quad(e, cc, row * N + col, dM, dV);
     }
     __syncwarp();
   }
@@ -556,7 +517,6 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         sbias[(et < BN ? 0 : BN) + c] = v;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
-      if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) dw_adam_prefetch(epi, M, N, m0 + q * 32, n0 + half * 64, lane);
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;
@@ -749,7 +709,6 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
         sbias[(et < BN ? 0 : BN) + c] = v;
         asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       }
-      if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) dw_adam_prefetch(epi, M, N, m0 + q * 32, n0 + half * 64, lane);
       mbar_wait(&tfull_bar[as], (it >> 1) & 1);
       tc_fence_after();
       const int64_t row = m0 + q * 32 + lane;

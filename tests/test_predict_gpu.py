@@ -74,8 +74,9 @@ def test_lrt_ensemble_predictor_matches_the_reference_loop(lb, spl):
 
 
 def test_lrt_ensemble_predictor_native_noise_is_launch_width_invariant(lb):
-    """Sample s of layer l draws from its own Philox stream: the sums do not depend on how many samples share a launch,
-    equal the run with those streams exported and injected, and layer 1's e_b / var_b are computed once per batch."""
+    """Sample s of layer l draws from its own Philox stream: the sums do not depend on how many samples share a launch
+    (beyond the fp32 summation order of the GEMMs, whose contraction split follows the stacked batch: 1e-6), equal the run
+    with those streams exported and injected, and layer 1's e_b / var_b are computed once per batch."""
     S, B = 9, 52
     case = C.ensemble_case(seed=122, batch=B, samples=S, kind="lrt")
     net = _load_lrt(lb, case)
@@ -88,16 +89,16 @@ def test_lrt_ensemble_predictor_native_noise_is_launch_width_invariant(lb):
         assert p.kernels_per_launch == 1 + 3 * 2 + 2         # expand + 2 fused layers + the two accumulations
     for r in runs[1:]:
         for a, b in zip(r, runs[0]):
-            assert (a - b).abs().max().item() < 1e-9
+            assert C.rel_err(a, b) < 1e-6
     p = lb.EnsemblePredictor(net, batch=B, samples_per_launch=9, seed=77)
     eps = [torch.stack([lb.philox_normal((B, o), 77, p._stream(li, s)) for s in range(S)]) for li, (_, o) in enumerate(p.sizes)]
     p.run(x, S, eps=eps)
-    assert (p.sum_logp - runs[0][0]).abs().max().item() < 1e-9
+    assert C.rel_err(p.sum_logp, runs[0][0]) < 1e-6
     # shards of the sample range add up (first_sample): what an MC-sample sharding over ranks relies on
     p.run(x, 4, first_sample=0)
     part = p.sum_logp.clone()
     p.run(x, 5, first_sample=4)
-    assert (part + p.sum_logp - runs[0][0]).abs().max().item() < 1e-9
+    assert C.rel_err(part + p.sum_logp, runs[0][0]) < 1e-6
 
 
 def test_mnf_ensemble_predictor_matches_the_reference_loop(lb):
