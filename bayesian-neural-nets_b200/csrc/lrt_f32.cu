@@ -13,6 +13,7 @@
 //   finalize  elementwise chain rule (dM,dV) -> (dmu,drho,dlambda) + closed-form KL gradient
 //   dX GEMM   split-N  dx = dE M + 2 x (dS V) -> partials; epilogue sums (+ relu mask)
 #include "common.cuh"
+#include "lrt_chain.cuh"
 
 namespace lbbnn {
 namespace {
@@ -695,6 +696,105 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
   }
 }
 
+
+// ================================================================================================
+// data-parallel sharded update over NVSwitch multicast (NVLS)
+// ================================================================================================
+// Every rank holds this layer's raw gradients [dM | dV | colsum] of ITS minibatch shard in a buffer that is mapped into a
+// multicast object spanning all ranks, and so are the parameters.  Rank r owns a contiguous 1/world of the weight quads:
+//   multimem.ld_reduce  sums the owners' quads of dM, dV over all ranks inside the switch (the reduce-scatter),
+//   chain rule + KL gradient (added once) + Adam run on the owner (its Adam moments are the only ones ever touched),
+//   multimem.st         writes the updated mu, rho, lambda quads to every rank's copy (the all-gather).
+// Per rank that is 1/world of the optimiser traffic of the replicated update and (8 + 12) B / weight over NVLink instead of
+// the 2 x 8 B of an all-reduce of (dM, dV) followed by a full update on every rank.  The caller brackets the launch with
+// cross-rank barriers (all ranks' dW GEMMs done before; all stores landed before the parameters are read again).
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* p) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st4(float* p, const float v[4]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* p) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+struct DpUpdateArgs {
+  const float *mu, *rho, *lam, *bias_mu, *bias_rho;     // this rank's copies (read)
+  float *mu_mc, *rho_mc, *lam_mc, *bias_mu_mc, *bias_rho_mc;   // multicast addresses (written)
+  const float* raw_mc;                                    // multicast address of [dM | dV | colsum]
+  int64_t N, K;
+  int world, rank, var_mode, sample;
+  float klg;
+  lbbnn_priors pri;
+  lbbnn_adam_layer_state adam;
+};
+
+__global__ void __launch_bounds__(kThreads) lrt_f32_finalize_adam_dp_kernel(const DpUpdateArgs a) {
+  const int64_t nq = a.N * a.K / 4;                        // N K % 4 == 0 (checked on the host)
+  const int64_t per = ceil_div(nq, a.world), q0 = a.rank * per, q1 = min(nq, q0 + per);
+  const chain::Consts cc = chain::make_consts(a.pri, a.var_mode, a.klg, a.adam.beta1, a.adam.beta2, a.adam.eps, a.adam.coef);
+  const float* dM_mc = a.raw_mc;
+  const float* dV_mc = a.raw_mc + a.N * a.K;
+  for (int64_t q = q0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < q1; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = q * 4;
+    const float4 dM = mc_ld_reduce4(dM_mc + e0);
+    const float4 dV = a.sample ? mc_ld_reduce4(dV_mc + e0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mu[4], rho[4], lam[4], mm[4], mr[4], ml[4], vm[4], vr[4], vl[4];
+    loadq(a.mu, e0, nq * 4, true, mu); loadq(a.rho, e0, nq * 4, true, rho); loadq(a.lam, e0, nq * 4, true, lam);
+    loadq(a.adam.exp_avg[0], e0, nq * 4, true, mm); loadq(a.adam.exp_avg[1], e0, nq * 4, true, mr); loadq(a.adam.exp_avg[2], e0, nq * 4, true, ml);
+    loadq(a.adam.exp_avg_sq[0], e0, nq * 4, true, vm); loadq(a.adam.exp_avg_sq[1], e0, nq * 4, true, vr);
+    loadq(a.adam.exp_avg_sq[2], e0, nq * 4, true, vl);
+    const float d1[4] = {dM.x, dM.y, dM.z, dM.w}, d2[4] = {dV.x, dV.y, dV.z, dV.w};
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float gm, gr, gl;
+      chain::grads(cc, mu[t], rho[t], lam[t], d1[t], d2[t], gm, gr, gl);
+      chain::adam(cc, mu[t], mm[t], vm[t], gm);
+      chain::adam(cc, rho[t], mr[t], vr[t], gr);
+      chain::adam(cc, lam[t], ml[t], vl[t], gl);
+    }
+    mc_st4(a.mu_mc + e0, mu); mc_st4(a.rho_mc + e0, rho); mc_st4(a.lam_mc + e0, lam);
+    storeq(a.adam.exp_avg[0], e0, nq * 4, true, mm, false); storeq(a.adam.exp_avg[1], e0, nq * 4, true, mr, false);
+    storeq(a.adam.exp_avg[2], e0, nq * 4, true, ml, false);
+    storeq(a.adam.exp_avg_sq[0], e0, nq * 4, true, vm, false); storeq(a.adam.exp_avg_sq[1], e0, nq * 4, true, vr, false);
+    storeq(a.adam.exp_avg_sq[2], e0, nq * 4, true, vl, false);
+  }
+  // biases: owned by rank 0 (2 N floats of column sums reduced in the switch, then the same bias update as lrt_f32_finalize)
+  if (a.rank == 0 && blockIdx.x == 0) {
+    const float* cs_mc = a.raw_mc + 2 * a.N * a.K;
+    const float ss = __ldg(a.adam.coef), bc = __ldg(a.adam.coef + 1), b1 = a.adam.beta1, b2 = a.adam.beta2;
+    for (int64_t i = threadIdx.x; i < a.N; i += blockDim.x) {
+      const float bm = a.bias_mu[i], br = a.bias_rho[i], sb = sigma_of(br);
+      float dbm = mc_ld_reduce1(cs_mc + i), dsb = a.sample ? 2.0f * sb * mc_ld_reduce1(cs_mc + a.N + i) : 0.f;
+      if (a.klg != 0.f) {
+        const float inv = 1.0f / (a.pri.bias_sigma * a.pri.bias_sigma);
+        dbm += a.klg * (bm - a.pri.bias_mu) * inv;
+        dsb += a.klg * (sb * inv - 1.0f / sb);
+      }
+      const float dbr = dsb * dsigma_drho(br);
+      float m = a.adam.exp_avg[3][i], v = a.adam.exp_avg_sq[3][i];
+      m = m + (dbm - m) * (1.0f - b1);
+      v = b2 * v + (1.0f - b2) * dbm * dbm;
+      mc_st1(a.bias_mu_mc + i, bm - ss * (m / (sqrtf(v) / bc + a.adam.eps)));
+      a.adam.exp_avg[3][i] = m; a.adam.exp_avg_sq[3][i] = v;
+      m = a.adam.exp_avg[4][i]; v = a.adam.exp_avg_sq[4][i];
+      m = m + (dbr - m) * (1.0f - b1);
+      v = b2 * v + (1.0f - b2) * dbr * dbr;
+      mc_st1(a.bias_rho_mc + i, br - ss * (m / (sqrtf(v) / bc + a.adam.eps)));
+      a.adam.exp_avg[4][i] = m; a.adam.exp_avg_sq[4][i] = v;
+    }
+  }
+}
+
 // ================================================================================================
 // backward wrt the input: dx = dE M + 2 x (dS V), split over the out-feature contraction
 // ================================================================================================
@@ -1184,6 +1284,30 @@ extern "C" int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* L, const floa
   f.adam = *adam;
   lrt_f32_finalize<true><<<1, kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize_adam_bias");
+}
+
+extern "C" int lbbnn_lrt_f32_finalize_adam_dp(const lbbnn_layer* L, const lbbnn_dp_layer* dp, const lbbnn_priors* pri, int var_mode,
+                                              int flags, float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(dp && pri && adam && adam->coef, "NULL argument");
+  LBBNN_REQUIRE(dp->world >= 1 && dp->rank >= 0 && dp->rank < dp->world, "bad rank %d of %d", dp->rank, dp->world);
+  LBBNN_REQUIRE(dp->raw_mc && dp->weight_mu_mc && dp->weight_rho_mc && dp->lambdal_mc && dp->bias_mu_mc && dp->bias_rho_mc,
+                "NULL multicast address");
+  LBBNN_REQUIRE(L->z == nullptr && L->z_kl == nullptr, "the fused update is for LRT layers (no multiplicative z)");
+  LBBNN_REQUIRE((L->in_features * L->out_features) % 4 == 0, "in_features * out_features must be a multiple of 4");
+  for (int i = 0; i < 5; ++i) LBBNN_REQUIRE(adam->exp_avg[i] && adam->exp_avg_sq[i], "NULL Adam state %d", i);
+  const void* al[] = {L->weight_mu, L->weight_rho, L->lambdal, dp->raw_mc, dp->weight_mu_mc, dp->weight_rho_mc, dp->lambdal_mc,
+                      adam->exp_avg[0], adam->exp_avg[1], adam->exp_avg[2], adam->exp_avg_sq[0], adam->exp_avg_sq[1], adam->exp_avg_sq[2]};
+  for (const void* p : al) LBBNN_REQUIRE((reinterpret_cast<uintptr_t>(p) & 15) == 0, "weight tensors / raw gradients must be 16B aligned");
+  DpUpdateArgs a;
+  a.mu = L->weight_mu; a.rho = L->weight_rho; a.lam = L->lambdal; a.bias_mu = L->bias_mu; a.bias_rho = L->bias_rho;
+  a.mu_mc = dp->weight_mu_mc; a.rho_mc = dp->weight_rho_mc; a.lam_mc = dp->lambdal_mc; a.bias_mu_mc = dp->bias_mu_mc;
+  a.bias_rho_mc = dp->bias_rho_mc; a.raw_mc = dp->raw_mc;
+  a.N = L->out_features; a.K = L->in_features; a.world = dp->world; a.rank = dp->rank; a.var_mode = var_mode;
+  a.sample = (flags & LBBNN_FLAG_SAMPLE) ? 1 : 0; a.klg = kl_grad_host; a.pri = *pri; a.adam = *adam;
+  const int64_t shard = ceil_div(a.N * a.K / 4, (int64_t)dp->world);
+  lrt_f32_finalize_adam_dp_kernel<<<(unsigned)elementwise_blocks(shard * 4), kThreads, 0, (cudaStream_t)s>>>(a);
+  return check_launch("lrt_f32_finalize_adam_dp");
 }
 
 // ---- plain linear layer on the same kernels (mean-branch GEMM: E only) ---------------------------------

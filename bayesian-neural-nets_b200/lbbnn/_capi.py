@@ -82,6 +82,11 @@ class AdamLayerState(C.Structure):
                 ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float)]
 
 
+class DpLayer(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("raw_mc", C.c_void_p), ("weight_mu_mc", C.c_void_p),
+                ("weight_rho_mc", C.c_void_p), ("lambdal_mc", C.c_void_p), ("bias_mu_mc", C.c_void_p), ("bias_rho_mc", C.c_void_p)]
+
+
 class MnfAux(C.Structure):
     _fields_ = [("in_features", C.c_int64), ("out_features", C.c_int64)] + [
         (n, C.c_void_p) for n in ("q0_mean", "q0_log_var", "z0", "r0_c", "r0_b1", "r0_b2", "z2", "M0", "V", "eps_r", "z_b")]
@@ -153,6 +158,8 @@ SIGNATURES = {
     "lbbnn_tc_lrt_dw_adam": (_INT, [_P, _P, _P, _P, C.POINTER(Layer), _I64, C.POINTER(Priors), _INT, _F,
                                     C.POINTER(AdamLayerState), _P]),
     "lbbnn_lrt_f32_finalize_adam_bias": (_INT, [C.POINTER(Layer), _P, C.POINTER(Priors), _INT, _F, C.POINTER(AdamLayerState), _P]),
+    "lbbnn_lrt_f32_finalize_adam_dp": (_INT, [C.POINTER(Layer), C.POINTER(DpLayer), C.POINTER(Priors), _INT, _INT, _F,
+                                              C.POINTER(AdamLayerState), _P]),
     "lbbnn_colsum2_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_colsum2": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _SZ, _P]),
     "lbbnn_linear_f32_fwd": (_INT, [_P, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _SZ, _P]),

@@ -405,27 +405,6 @@ class LRTTensorCoreTrainer:
         dev = self.layers[0].weight_mu.device
         self.device = dev
 
-        offs, total = [], 0
-        for l in self.layers:
-            for name in _PARAM_NAMES:
-                p = getattr(l, name)
-                offs.append((l, name, total, p.numel(), p.shape))
-                total += _pad4(p.numel())
-        self.n_flat = total
-        f32 = dict(dtype=torch.float32, device=dev)
-        bf = dict(dtype=torch.bfloat16, device=dev)
-        self.flat, self.gflat = torch.zeros(total, **f32), torch.zeros(total, **f32)
-        self.exp_avg, self.exp_avg_sq = torch.zeros(total, **f32), torch.zeros(total, **f32)
-        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        self.adam_coef = torch.zeros(2, dtype=torch.float32, device=dev)
-        with torch.no_grad():
-            for l, name, off, n, shape in offs:
-                p = getattr(l, name)
-                view = self.flat[off:off + n].view(shape)
-                view.copy_(p.data)
-                p.data = view
-                p.grad = self.gflat[off:off + n].view(shape)
-
         B = self.B
         sizes = [(l.in_features, l.out_features) for l in self.layers]
         self.sizes = sizes
@@ -440,6 +419,41 @@ class LRTTensorCoreTrainer:
         if in_place and not can_in_place:
             raise K.LbbnnError("in_place needs out_features % 8 == 0 for every layer but a <= 12-output head (fused_head_dx)")
         self.in_place = can_in_place if in_place is None else bool(in_place)
+
+        offs, total = [], 0
+        for l in self.layers:
+            for name in _PARAM_NAMES:
+                p = getattr(l, name)
+                offs.append((l, name, total, p.numel(), p.shape))
+                total += _pad4(p.numel())
+        self.n_flat = total
+        f32 = dict(dtype=torch.float32, device=dev)
+        bf = dict(dtype=torch.bfloat16, device=dev)
+        # data parallel, fused update, operands in place: parameters and raw gradients live in ONE symmetric-memory arena
+        # bound to an NVSwitch multicast object, and every layer's update is the sharded NVLS kernel
+        # (lbbnn_lrt_f32_finalize_adam_dp: in-switch reduce-scatter of (dM, dV) -> chain rule + KL + Adam on the owner ->
+        # multicast store of the new parameters).  LBBNN_DP_UPDATE = auto (default) | sharded | nccl.
+        self.dp_sharded = False
+        self.allreduce = "nccl" if self.world > 1 else "none"
+        self._raw_off = {}
+        arena_floats = total
+        for li, (i, o) in enumerate(sizes):
+            self._raw_off[li] = arena_floats
+            arena_floats += _pad4(2 * o * i + 2 * o)
+        if self.world > 1 and self.fused_update and self.in_place:
+            self._setup_dp_arena(arena_floats, dev)
+        self.flat = self.arena[:total] if self.dp_sharded else torch.zeros(total, **f32)
+        self.gflat = torch.zeros(total, **f32)
+        self.exp_avg, self.exp_avg_sq = torch.zeros(total, **f32), torch.zeros(total, **f32)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.adam_coef = torch.zeros(2, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for l, name, off, n, shape in offs:
+                p = getattr(l, name)
+                view = self.flat[off:off + n].view(shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.gflat[off:off + n].view(shape)
         self.x = torch.zeros(B, sizes[0][0], **f32)
         self.y = torch.zeros(B, dtype=torch.int64, device=dev)
         self.x_bf, self.x2_bf = torch.zeros(B, sizes[0][0], **bf), torch.zeros(B, sizes[0][0], **bf)
@@ -500,8 +514,11 @@ class LRTTensorCoreTrainer:
                          if (not last and not (li + 1 == L - 1 and self.small_dx[li + 1])) else None),
                 klws=torch.empty(max(256, int(K.lib.lbbnn_lrt_bf16_prologue_workspace_bytes(i, o))), dtype=torch.uint8, device=dev),
                 eps=torch.zeros(B, o, **f32) if inject_noise else None)
-            if self.fused_update and not epi_update:   # [dM | dV | colsum]: what a data-parallel step all-reduces
-                d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
+            if self.fused_update and not epi_update:   # [dM | dV | colsum]: what a data-parallel step reduces over the ranks
+                if self.dp_sharded:
+                    d["raw"] = self.arena[self._raw_off[li]:self._raw_off[li] + 2 * o * i + 2 * o]
+                else:
+                    d["raw"] = torch.zeros(2 * o * i + 2 * o, **f32)
                 d["colsum"] = d["raw"][2 * o * i:]
             self.tc.append(d)
         if self.in_place:          # no transposed input staging, no fp32 M / V scratch; dM / dV only for the unfused update
@@ -528,6 +545,51 @@ class LRTTensorCoreTrainer:
         if self.inject:
             return K.make_noise(self.tc[i]["eps"])
         return K.make_noise(None, self.seed + 0x9E3779B97F4A7C15 * self.rank, i, self.step_dev, len(self.layers))
+
+    def _setup_dp_arena(self, arena_floats, dev):
+        """Symmetric (peer-mapped) memory with an NVSwitch multicast mapping for [parameters | raw gradients of every layer]
+        (torch.distributed._symmetric_memory: cuMemCreate + cuMulticastBindMem under the hood).  Leaves dp_sharded False --
+        the NCCL all-reduce + replicated update path -- when the fabric has no multicast support or LBBNN_DP_UPDATE=nccl."""
+        import os
+        mode = os.environ.get("LBBNN_DP_UPDATE", "auto")
+        if mode == "nccl":
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            arena = symm_mem.empty(arena_floats, dtype=torch.float32, device=dev)
+            arena.zero_()
+            hdl = symm_mem.rendezvous(arena, self.pg.group_name)
+            mc = int(hdl.multicast_ptr)
+            if mc == 0:
+                raise RuntimeError("no multicast support on this fabric")
+            hdl.barrier(channel=0)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            if mode == "sharded":
+                raise
+            self._dp_error = repr(e)
+            return
+        self.arena, self._symm, self._mc_base = arena, hdl, mc
+        self.dp_sharded = True
+        self.allreduce = "nvls-sharded-update"
+
+    def _dp_layer(self, i):
+        """Multicast addresses of layer i's parameters and raw-gradient buffer inside the arena."""
+        l = self.layers[i]
+        mc = lambda name: self._mc_base + 4 * self.param_off[(id(l), name)]  # noqa: E731
+        return K.DpLayer(self.world, self.rank, self._mc_base + 4 * self._raw_off[i], mc("weight_mu"), mc("weight_rho"),
+                         mc("lambdal"), mc("bias_mu"), mc("bias_rho"))
+
+    def _sharded_layer_update(self, i, desc, main):
+        """Layer i's raw gradients are complete on `main` on THIS rank: on the communication stream, wait for the other
+        ranks (cross-rank barrier), run the sharded NVLS update, and fence it with a second barrier."""
+        l = self.layers[i]
+        self.comm_stream.wait_stream(main)
+        with torch.cuda.stream(self.comm_stream):
+            self._symm.barrier(channel=0)
+            K.check(K.lib.lbbnn_lrt_f32_finalize_adam_dp(desc, self._dp_layer(i), l.cfg.priors, l.cfg.var_mode, K.FLAG_SAMPLE,
+                                                         1.0 / self.num_batches, self._adam_state(l), K.current_stream()))
+            self._symm.barrier(channel=0)
 
     def _enqueue_in_place(self):
         """The r02 launch sequence: every GEMM reads its operands where the producing kernel left them (see __init__)."""
@@ -625,7 +687,9 @@ class LRTTensorCoreTrainer:
                         dw(K.current_stream()); n += 1
                 else:
                     dw(st); n += 1
-                if self.fused_update:
+                if self.fused_update and self.dp_sharded:
+                    self._sharded_layer_update(i, descs[i], main); n += 1
+                elif self.fused_update:
                     self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
                 else:
                     K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(dM), P(dV), P(d["colsum"]), l.cfg.priors, l.cfg.var_mode,

@@ -469,6 +469,26 @@ LBBNN_API int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* layer, const f
                                                int flags, float kl_grad_host, const lbbnn_adam_layer_state* adam,
                                                lbbnn_stream s);
 
+/* ---- data-parallel update over NVSwitch multicast (NVLS) ------------------------------------------------------------------
+ * The reference has no multi-GPU path; this is the data-parallel exchange of SURVEY.md §8(e) as ONE kernel per layer instead of
+ * an all-reduce of the raw gradients followed by the full update on every rank.  Setup (the binder's job: cuMemCreate /
+ * cuMulticastCreate + cuMulticastBindMem, or torch.distributed._symmetric_memory as lbbnn/engine.py does): every rank places
+ * the layer's parameters and its raw gradient buffer [dM (out,in) | dV (out,in) | sum_b dE (out) | sum_b dS (out)] at the SAME
+ * offsets of a buffer bound to a multicast object spanning all ranks; *_mc are the multicast virtual addresses.
+ * finalize_adam_dp, launched by every rank after ALL ranks' dW GEMMs of the layer have completed (cross-rank barrier):
+ *   rank r reduces its contiguous 1/world of the (dM, dV) quads over all ranks in the switch (multimem.ld_reduce), applies
+ *   chain rule + KL gradient (once) + Adam with ITS shard of the Adam moments, and stores the updated mu, rho, lambda to every
+ *   rank's copy (multimem.st); rank 0 does the same for the biases.  A second cross-rank barrier must precede the next read
+ *   of the parameters.  `layer` holds this rank's LOCAL addresses (the old values are read from them). */
+typedef struct lbbnn_dp_layer {
+  int world, rank;
+  const float* raw_mc;
+  float *weight_mu_mc, *weight_rho_mc, *lambdal_mc, *bias_mu_mc, *bias_rho_mc;
+} lbbnn_dp_layer;
+LBBNN_API int lbbnn_lrt_f32_finalize_adam_dp(const lbbnn_layer* layer, const lbbnn_dp_layer* dp, const lbbnn_priors* priors,
+                                             int var_mode, int flags, float kl_grad_host, const lbbnn_adam_layer_state* adam,
+                                             lbbnn_stream s);
+
 /* ---- bf16 tensor-core path, operands read in place (r02) -------------------------------------------------------------
  * The GEMM kernels also take "MN-major" operands: the row-major (K, rows) tensor, i.e. one whose ROW index is the
  * contraction index, fetched by TMA as 64 x 64 boxes into tcgen05's MN-major SWIZZLE_128B layout.  With them the three
