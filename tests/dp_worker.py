@@ -51,17 +51,31 @@ def run_case(name, make_trainer, dims, per_rank, rank, world, pg, tol):
     _set_eps(tr_1, case["eps"])
     out_1 = tr_1.step(case["x"], case["y"])
     torch.cuda.synchronize()
-    # Adam's first moment after step 1 is 0.1 x the gradient the update consumed
+    # Adam's first moment after step 1 is 0.1 x the gradient the update consumed.  With the sharded NVLS update a rank only
+    # keeps the moments of the weight quads it owns (a contiguous 1 / world of every weight tensor; rank 0 owns the biases)
+    sharded = getattr(tr_dp, "dp_sharded", False)
     worst = 0.0
     for l_dp, l_1 in zip(net_dp.layers, net_1.layers):
         for k in ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"):
             off = tr_dp._offsets[(id(l_dp), k)] if hasattr(tr_dp, "_offsets") else tr_dp.param_off[(id(l_dp), k)]
             off1 = tr_1._offsets[(id(l_1), k)] if hasattr(tr_1, "_offsets") else tr_1.param_off[(id(l_1), k)]
             n = getattr(l_dp, k).numel()
-            g_dp, g_1 = tr_dp.exp_avg[off:off + n], tr_1.exp_avg[off1:off1 + n]
+            lo_e, hi_e = 0, n
+            if sharded:
+                if k.startswith("bias"):
+                    if rank != 0:
+                        continue
+                else:
+                    per = -(-(n // 4) // world)
+                    lo_e, hi_e = 4 * rank * per, min(n, 4 * (rank + 1) * per)
+            g_dp, g_1 = tr_dp.exp_avg[off + lo_e:off + hi_e], tr_1.exp_avg[off1 + lo_e:off1 + hi_e]
             err = ((g_dp - g_1).double().norm() / g_1.double().norm()).item()
             worst = max(worst, err)
             assert err < tol, (name, k, "gradient (exp_avg) of the DP step differs from the single-GPU step", err)
+            # the updated parameters are replicated on every rank whatever the update scheme
+            p_dp, p_1 = tr_dp.flat[off:off + n], tr_1.flat[off1:off1 + n]
+            perr = C.rel_err(p_dp, p_1)
+            assert perr < 1e-5, (name, k, "updated parameters of the DP step differ from the single-GPU step", perr)
     assert abs(out_dp["kl"] - out_1["kl"]) <= 1e-6 * abs(out_1["kl"]), (name, out_dp["kl"], out_1["kl"])
     # the nll each rank reports is its shard's; the sum over ranks is the whole batch's
     nll = torch.tensor([out_dp["nll"]], dtype=torch.float64, device="cuda")
