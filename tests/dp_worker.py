@@ -75,7 +75,7 @@ def run_case(name, make_trainer, dims, per_rank, rank, world, pg, tol):
             # the updated parameters are replicated on every rank whatever the update scheme
             p_dp, p_1 = tr_dp.flat[off:off + n], tr_1.flat[off1:off1 + n]
             perr = C.rel_err(p_dp, p_1)
-            assert perr < 1e-5, (name, k, "updated parameters of the DP step differ from the single-GPU step", perr)
+            assert perr < max(1e-5, tol), (name, k, "updated parameters of the DP step differ from the single-GPU step", perr)
     assert abs(out_dp["kl"] - out_1["kl"]) <= 1e-6 * abs(out_1["kl"]), (name, out_dp["kl"], out_1["kl"])
     # the nll each rank reports is its shard's; the sum over ranks is the whole batch's
     nll = torch.tensor([out_dp["nll"]], dtype=torch.float64, device="cuda")
