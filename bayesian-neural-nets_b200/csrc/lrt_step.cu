@@ -101,7 +101,50 @@ struct DevStep {
   float* stats;
   long long* prof;  // optional: clock64 of CTA 0 at every phase boundary
   int prof_cta;     // CTA whose work items are stamped
+  // data parallel inside the launch (lbbnn_step_dp): world > 1 switches it on
+  int dp_world, dp_rank;
+  float* flat_mc;
+  const float* raw_mc;       // multicast address of the workspace head = the raw gradients of all layers
+  const float* raw_base;     // local address of the same
+  unsigned* dp_signal[8];
+  double* dp_klx[8];
+  unsigned long long* dp_epoch;
 };
+
+// ---- NVLink flags / NVSwitch multicast (data parallel inside the launch) -------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// one thread: tell every peer this rank reached `epoch`, wait until all of them did
+__device__ __forceinline__ void dp_flag_exchange(const DevStep& a, unsigned epoch) {
+  __threadfence_system();
+  for (int p = 0; p < a.dp_world; ++p) st_release_sys(a.dp_signal[p] + a.dp_rank, epoch);
+  for (int q = 0; q < a.dp_world; ++q)
+    while ((int)(ld_acquire_sys(a.dp_signal[a.dp_rank] + q) - epoch) < 0) {}
+}
+__device__ __forceinline__ float4 mc_ld_reduce4(const float* p) {
+  float4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st4(float* p, const float v[4]) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ float mc_ld_reduce1(const float* p) {
+  float r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void mc_st1(float* p, float v) {
+  asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
 
 __device__ __forceinline__ void stamp(const DevStep& a, int& slot) {
   if (a.prof && (int)blockIdx.x == a.prof_cta && threadIdx.x == 0) a.prof[slot] = clock64();
@@ -845,7 +888,15 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
     const int cnt = VEC ? 4 : (int)min((int64_t)4, n - e0);
     Q4 mu = ldq4<false>(a.flat + y.off_mu + e0, cnt, VEC), rho = ldq4<false>(a.flat + y.off_rho + e0, cnt, VEC);
     Q4 lam = ldq4<false>(a.flat + y.off_lam + e0, cnt, VEC);
-    const Q4 dM = ldq4<true>(y.dM + e0, cnt, VEC), dV = ldq4<true>(y.dV + e0, cnt, VEC);
+    Q4 dM, dV;
+    if (VEC && a.dp_world > 1) {   // summed over the ranks inside the switch (this rank owns the quad)
+      const float4 t0 = mc_ld_reduce4(a.raw_mc + (y.dM - a.raw_base) + e0), t1 = mc_ld_reduce4(a.raw_mc + (y.dV - a.raw_base) + e0);
+      dM.v[0] = t0.x; dM.v[1] = t0.y; dM.v[2] = t0.z; dM.v[3] = t0.w;
+      dV.v[0] = t1.x; dV.v[1] = t1.y; dV.v[2] = t1.z; dV.v[3] = t1.w;
+    } else {
+      dM = ldq4<true>(y.dM + e0, cnt, VEC);
+      dV = ldq4<true>(y.dV + e0, cnt, VEC);
+    }
     Q4 m0 = ldq4<false>(a.m + y.off_mu + e0, cnt, VEC), m1 = ldq4<false>(a.m + y.off_rho + e0, cnt, VEC);
     Q4 m2 = ldq4<false>(a.m + y.off_lam + e0, cnt, VEC);
     Q4 v0 = ldq4<false>(a.v + y.off_mu + e0, cnt, VEC), v1 = ldq4<false>(a.v + y.off_rho + e0, cnt, VEC);
@@ -883,8 +934,12 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
       adam1(rho.v[j], g1.v[j], m1.v[j], v1.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
       adam1(lam.v[j], g2.v[j], m2.v[j], v2.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
     }
-    stq4(a.flat + y.off_mu + e0, mu, cnt, VEC); stq4(a.flat + y.off_rho + e0, rho, cnt, VEC);
-    stq4(a.flat + y.off_lam + e0, lam, cnt, VEC);
+    if (VEC && a.dp_world > 1) {   // the new parameters go to every rank's copy
+      mc_st4(a.flat_mc + y.off_mu + e0, mu.v); mc_st4(a.flat_mc + y.off_rho + e0, rho.v); mc_st4(a.flat_mc + y.off_lam + e0, lam.v);
+    } else {
+      stq4(a.flat + y.off_mu + e0, mu, cnt, VEC); stq4(a.flat + y.off_rho + e0, rho, cnt, VEC);
+      stq4(a.flat + y.off_lam + e0, lam, cnt, VEC);
+    }
     stq4(a.m + y.off_mu + e0, m0, cnt, VEC); stq4(a.m + y.off_rho + e0, m1, cnt, VEC); stq4(a.m + y.off_lam + e0, m2, cnt, VEC);
     stq4(a.v + y.off_mu + e0, v0, cnt, VEC); stq4(a.v + y.off_rho + e0, v1, cnt, VEC); stq4(a.v + y.off_lam + e0, v2, cnt, VEC);
     if (a.grad) {
@@ -916,7 +971,14 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
   for (int l = 0; l < kMaxL; ++l) kl[l] = 0.f;
   int64_t total = 0;
   for (int l = l0; l < l1; ++l) total += ((int64_t)a.ly[l].N * a.ly[l].K + 3) >> 2;
-  for (int64_t g = (int64_t)cta * NT + threadIdx.x; g < total; g += (int64_t)ncta * NT) {
+  // data parallel: this rank updates a contiguous 1 / world of the quads (and rank 0 the biases)
+  int64_t g_first = 0, g_end = total;
+  if (a.dp_world > 1) {
+    const int64_t per = (total + a.dp_world - 1) / a.dp_world;
+    g_first = min(total, (int64_t)a.dp_rank * per);
+    g_end = min(total, g_first + per);
+  }
+  for (int64_t g = g_first + (int64_t)cta * NT + threadIdx.x; g < g_end; g += (int64_t)ncta * NT) {
     int l = l0;
     int64_t q = g;
     for (;; ++l) {
@@ -934,16 +996,20 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
     for (int j = 0; j < kMaxL; ++j) kl[j] += (j == l) ? k_ : 0.f;
   }
   // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); one CTA per layer
+  const bool dp = a.dp_world > 1;
   for (int l = l0; l < l1; ++l) {
     if (cta != (a.L - 1 - l) % ncta) continue;
+    if (dp && a.dp_rank != 0) continue;
     const DevLayer& y = a.ly[l];
     const lbbnn_priors P = y.pri;
     const float inv = 1.0f / (P.bias_sigma * P.bias_sigma);
     float kb = 0.f;
+    const float* cs_mc = dp ? a.raw_mc + (y.colsum - a.raw_base) : nullptr;
     for (int i = threadIdx.x; i < y.N; i += NT) {
       float bm = a.flat[y.off_bmu + i], br = a.flat[y.off_brho + i];
       const float sb = sigma_of(br);
-      float dbm = __ldcg(y.colsum + i), dsb = 2.0f * sb * __ldcg(y.colsum + y.N + i);
+      float dbm = dp ? mc_ld_reduce1(cs_mc + i) : __ldcg(y.colsum + i);
+      float dsb = 2.0f * sb * (dp ? mc_ld_reduce1(cs_mc + y.N + i) : __ldcg(y.colsum + y.N + i));
       kb += kl_bias_elem(bm, sb, P);
       dbm += klg * (bm - P.bias_mu) * inv;
       dsb += klg * (sb * inv - 1.0f / sb);
@@ -952,7 +1018,8 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
       float mm0 = a.m[y.off_bmu + i], vv0 = a.v[y.off_bmu + i], mm1 = a.m[y.off_brho + i], vv1 = a.v[y.off_brho + i];
       adam1(bm, dbm, mm0, vv0, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
       adam1(br, dbr, mm1, vv1, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
-      a.flat[y.off_bmu + i] = bm; a.flat[y.off_brho + i] = br;
+      if (dp) { mc_st1(a.flat_mc + y.off_bmu + i, bm); mc_st1(a.flat_mc + y.off_brho + i, br); }
+      else { a.flat[y.off_bmu + i] = bm; a.flat[y.off_brho + i] = br; }
       a.m[y.off_bmu + i] = mm0; a.v[y.off_bmu + i] = vv0; a.m[y.off_brho + i] = mm1; a.v[y.off_brho + i] = vv1;
     }
 #pragma unroll
@@ -978,7 +1045,8 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
 __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ sm) {
   __shared__ int is_last;
   double* dred = reinterpret_cast<double*>(sm);
-  __threadfence();
+  if (a.dp_world > 1) __threadfence_system();   // this CTA's multicast stores of parameters, before the closing flags
+  else __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
     const unsigned tk = atomicAdd(a.ticket, 1u);
@@ -991,8 +1059,23 @@ __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ 
     double acc = 0.0;
     for (int c = threadIdx.x; c < (int)gridDim.x; c += NT) acc += __ldcg(a.kl_part + (int64_t)l * gridDim.x + c);
     const double tot = block_sum(acc, dred);
-    if (threadIdx.x == 0) a.stats[1 + l] = (float)tot;
+    if (threadIdx.x == 0) {
+      if (a.dp_world > 1) {          // this rank's part of the layer's KL (its shard; rank 0: + the biases) -> every rank
+        for (int p = 0; p < a.dp_world; ++p) a.dp_klx[p][a.dp_rank * kMaxL + l] = tot;
+      } else a.stats[1 + l] = (float)tot;
+    }
     __syncthreads();
+  }
+  if (a.dp_world > 1 && threadIdx.x == 0) {
+    // closing exchange: every rank's parameter stores and KL partials have landed before anyone's next launch reads them
+    const unsigned e = (unsigned)(*(volatile unsigned long long*)a.dp_epoch) + 1u;
+    dp_flag_exchange(a, e);
+    *a.dp_epoch = e;
+    for (int l = 0; l < a.L; ++l) {
+      double tot = 0.0;
+      for (int q = 0; q < a.dp_world; ++q) tot += *(volatile double*)(a.dp_klx[a.dp_rank] + q * kMaxL + l);
+      a.stats[1 + l] = (float)tot;
+    }
   }
   {  // nll partials of the loss phase (written by this launch or, data-parallel, by the preceding one)
     double acc = 0.0;
@@ -1326,6 +1409,15 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
     }
   }
   if (a.phases & 2) {
+    if (a.dp_world > 1) {
+      // every rank's raw gradients are complete (the grid barrier above + the peers' flags) before anyone reduces them
+      if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned e = (unsigned)(*(volatile unsigned long long*)a.dp_epoch) + 1u;
+        dp_flag_exchange(a, e);
+        *a.dp_epoch = e;
+      }
+      grid.sync();
+    }
     update_layers(a, step, 0, u_first ? 1 : a.L, blockIdx.x, G, sm);   // layers >= 1 were done during B_0 if u_first
     finish_step(a, step, sm);
   }
@@ -1636,7 +1728,21 @@ extern "C" int lbbnn_lrt_step_f32(const lbbnn_step* S, int phases, void* ws, siz
   d.lr = S->lr; d.b1 = S->beta1; d.b2 = S->beta2; d.eps = S->eps; d.klg = S->kl_scale;
   d.stats = S->stats;
   d.prof = g_step_prof;
-  d.overlap_update = getenv("LBBNN_STEP_OVERLAP_UPDATE") ? 1 : 0;
+  d.dp_world = 1; d.dp_rank = 0; d.flat_mc = nullptr; d.raw_mc = nullptr; d.raw_base = (const float*)ws; d.dp_epoch = nullptr;
+  for (int p = 0; p < 8; ++p) { d.dp_signal[p] = nullptr; d.dp_klx[p] = nullptr; }
+  if (S->dp && S->dp->world > 1) {
+    const lbbnn_step_dp* D = S->dp;
+    LBBNN_REQUIRE(phases == 3, "the in-launch data-parallel exchange needs phases == 3");
+    LBBNN_REQUIRE(D->world <= 8 && D->rank >= 0 && D->rank < D->world, "bad data-parallel rank %d of %d", D->rank, D->world);
+    LBBNN_REQUIRE(D->flat_mc && D->ws_mc && D->epoch, "NULL multicast address / epoch");
+    LBBNN_REQUIRE(S->grad == nullptr, "the sharded update does not materialise gradients (grad must be NULL)");
+    for (int p = 0; p < D->world; ++p) LBBNN_REQUIRE(D->signal[p] && D->klx[p], "NULL peer mapping %d", p);
+    for (int l = 0; l < d.L; ++l)
+      LBBNN_REQUIRE(((int64_t)d.ly[l].N * d.ly[l].K) % 4 == 0, "sharded update needs in*out %% 4 == 0 (layer %d)", l);
+    d.dp_world = D->world; d.dp_rank = D->rank; d.flat_mc = D->flat_mc; d.raw_mc = D->ws_mc; d.dp_epoch = D->epoch;
+    for (int p = 0; p < D->world; ++p) { d.dp_signal[p] = D->signal[p]; d.dp_klx[p] = D->klx[p]; }
+  }
+  d.overlap_update = (getenv("LBBNN_STEP_OVERLAP_UPDATE") && d.dp_world == 1) ? 1 : 0;
   d.prof_cta = g_step_prof_cta;
   void* args[] = {(void*)&d};
   LBBNN_CUDA(cudaLaunchCooperativeKernel((const void*)lrt_step_kernel, dim3((unsigned)G), dim3(NT), args, kSmemCap,

@@ -106,12 +106,17 @@ class StepLayer(C.Structure):
                 ("off_bias_rho", C.c_int64), ("eps", C.c_void_p), ("priors", Priors), ("var_mode", C.c_int)]
 
 
+class StepDp(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("flat_mc", C.c_void_p), ("ws_mc", C.c_void_p),
+                ("signal", C.c_void_p * 8), ("klx", C.c_void_p * 8), ("epoch", C.c_void_p)]
+
+
 class Step(C.Structure):
     _fields_ = [("n_layers", C.c_int), ("batch", C.c_int64), ("layer", StepLayer * STEP_MAX_LAYERS),
                 ("flat", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("grad", C.c_void_p),
                 ("x", C.c_void_p), ("y", C.c_void_p), ("step_dev", C.c_void_p), ("seed", C.c_uint64),
                 ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float),
-                ("kl_scale", C.c_float), ("stats", C.c_void_p)]
+                ("kl_scale", C.c_float), ("stats", C.c_void_p), ("dp", C.POINTER(StepDp))]
 
 
 _P, _I64, _U64, _INT, _F, _SZ = C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_float, C.c_size_t

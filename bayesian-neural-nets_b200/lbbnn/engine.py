@@ -57,7 +57,11 @@ class LRTTrainer:
                 offs.append((l, name, total, p.numel(), p.shape))
                 total += _pad4(p.numel())
         self.n_flat = total
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        # data parallel + fused step kernel: parameters and workspace in one NVSwitch-multicast arena, exchange inside the launch
+        self._dp_arena = None
+        if self.fused and self.pg is not None and not self.materialize_grads:
+            self._try_dp_arena(total, [(l.in_features, l.out_features) for l in self.layers])
+        self.flat = self._dp_arena["flat"] if self._dp_arena else torch.zeros(total, dtype=torch.float32, device=dev)
         self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -97,6 +101,43 @@ class LRTTrainer:
             self._capture()
 
     # ---- fused single-kernel step (csrc/lrt_step.cu) ------------------------------------------------
+    def _try_dp_arena(self, n_flat, sizes):
+        """LBBNN_DP_ALLREDUCE = auto | sharded: one symmetric-memory arena [parameters | step workspace | signal pad | KL
+        exchange] bound to an NVSwitch multicast object, for the in-launch sharded update (lbbnn_step_dp).  Leaves
+        self._dp_arena None (two launches around an all-reduce of the raw gradients) when the fabric has no multicast."""
+        import os
+        mode = os.environ.get("LBBNN_DP_ALLREDUCE", "auto")
+        if mode not in ("auto", "sharded"):
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            probe = K.Step()
+            probe.n_layers, probe.batch = len(sizes), self.B
+            for i, (fi, fo) in enumerate(sizes):
+                probe.layer[i].in_features, probe.layer[i].out_features = fi, fo
+            ws_bytes = int(K.lib.lbbnn_lrt_step_workspace_bytes(probe))
+            if ws_bytes == 0 or any((fi * fo) % 4 for fi, fo in sizes):
+                raise RuntimeError("shape not supported by the sharded update")
+            a256 = lambda v: (v + 255) // 256 * 256  # noqa: E731
+            off_ws = a256(4 * n_flat)
+            off_sig = off_ws + a256(ws_bytes)
+            off_klx = off_sig + 256
+            nbytes = off_klx + a256(8 * self.world * K.STEP_MAX_LAYERS)
+            arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+            arena.zero_()
+            hdl = symm_mem.rendezvous(arena, self.pg.group_name)
+            if int(hdl.multicast_ptr) == 0:
+                raise RuntimeError("no multicast support on this fabric")
+            hdl.barrier(channel=0)
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            if mode == "sharded":
+                raise
+            self._ar_error = repr(e)
+            return
+        self._dp_arena = dict(arena=arena, hdl=hdl, flat=arena[:4 * n_flat].view(torch.float32), off_ws=off_ws, ws_bytes=ws_bytes,
+                              off_sig=off_sig, off_klx=off_klx, epoch=torch.zeros(1, dtype=torch.int64, device=self.device))
+
     def _init_fused(self, sizes, inject_noise, use_graph):
         dev, f32 = self.device, dict(dtype=torch.float32, device=self.device)
         self.eps_in = [torch.zeros(self.B, o, **f32) for _, o in sizes] if inject_noise else None
@@ -126,7 +167,23 @@ class LRTTrainer:
             raise K.LbbnnError("fused step: " + K.lib.lbbnn_last_error().decode())
         self.allreduce = "none"
         self.ws = None
-        if self.pg is not None:
+        self._step_dp = None
+        if self._dp_arena is not None:
+            A = self._dp_arena
+            assert nbytes <= A["ws_bytes"]
+            self.ws = A["arena"][A["off_ws"]:A["off_ws"] + A["ws_bytes"]]
+            mc, peers = int(A["hdl"].multicast_ptr), [int(p) for p in A["hdl"].buffer_ptrs]
+            dp = K.StepDp()
+            dp.world, dp.rank = self.world, self.rank
+            dp.flat_mc, dp.ws_mc = mc, mc + A["off_ws"]
+            for p in range(self.world):
+                dp.signal[p], dp.klx[p] = peers[p] + A["off_sig"], peers[p] + A["off_klx"]
+            dp.epoch = A["epoch"].data_ptr()
+            self._step_dp = dp
+            import ctypes
+            st.dp = ctypes.pointer(dp)
+            self.allreduce = "nvls-sharded-update (inside the step kernel)"
+        elif self.pg is not None:
             self.ws = self._symmetric_workspace(nbytes)                   # NVLink/NVSwitch peer-mapped, for the all-reduce
         if self.ws is None:
             self.ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # zero-filled once (barrier ticket lives in it)
@@ -138,10 +195,27 @@ class LRTTrainer:
         self.x_host = torch.zeros(self.B, sizes[0][0], dtype=torch.float32).pin_memory()
         self.y_host = torch.zeros(self.B, dtype=torch.int64).pin_memory()
         self.stats_host = torch.zeros(1 + len(sizes), dtype=torch.float32).pin_memory()
-        self.kernels_per_step = 1 if self.pg is None else 2
+        self.kernels_per_step = 1 if (self.pg is None or self._step_dp is not None) else 2
         self.graph = None
         if use_graph:
             self._capture()
+
+    def owned_range(self, layer_index, name):
+        """Element range [lo, hi) of parameter `name` of layer `layer_index` whose Adam moments THIS rank maintains: all of it,
+        except under the in-launch sharded data-parallel update, where a rank owns a contiguous 1 / world of the weight quads of
+        ALL layers taken as one index space (layer 0 first) and rank 0 owns the biases."""
+        n = getattr(self.layers[layer_index], name).numel()
+        if getattr(self, "_step_dp", None) is None:
+            return 0, n
+        if name.startswith("bias"):
+            return (0, n) if self.rank == 0 else (0, 0)
+        nq = [l.weight_mu.numel() // 4 for l in self.layers]
+        total = sum(nq)
+        per = -(-total // self.world)
+        g0, g1 = min(total, self.rank * per), min(total, (self.rank + 1) * per)
+        base = sum(nq[:layer_index])
+        lo, hi = max(g0, base) - base, min(g1, base + nq[layer_index]) - base
+        return (4 * lo, 4 * hi) if hi > lo else (0, 0)
 
     def _symmetric_workspace(self, nbytes):
         """The step workspace in symmetric (peer-mapped) memory so that the all-reduce of its raw-gradient head can be
@@ -176,7 +250,7 @@ class LRTTrainer:
 
     def _enqueue_fused(self):
         st, ws = K.current_stream(), self.ws
-        if self.pg is None:
+        if self.pg is None or self._step_dp is not None:     # one launch; data parallel: the exchange happens inside it
             K.check(K.lib.lbbnn_lrt_step_f32(self._step_desc, 3, ws.data_ptr(), ws.numel(), st))
         else:   # data parallel: sum-reduce the raw (dM, dV, bias column sums), then chain rule + KL + Adam
             K.check(K.lib.lbbnn_lrt_step_f32(self._step_desc, 1, ws.data_ptr(), ws.numel(), st))
@@ -572,6 +646,17 @@ class LRTTensorCoreTrainer:
         self.arena, self._symm, self._mc_base = arena, hdl, mc
         self.dp_sharded = True
         self.allreduce = "nvls-sharded-update"
+
+    def owned_range(self, layer_index, name):
+        """Element range [lo, hi) of parameter `name` of layer `layer_index` whose Adam moments THIS rank maintains: all of it,
+        except under the sharded NVLS update (a contiguous 1 / world of each weight tensor's quads; rank 0 owns the biases)."""
+        n = getattr(self.layers[layer_index], name).numel()
+        if not self.dp_sharded:
+            return 0, n
+        if name.startswith("bias"):
+            return (0, n) if self.rank == 0 else (0, 0)
+        per = -(-(n // 4) // self.world)
+        return min(n, 4 * self.rank * per), min(n, 4 * (self.rank + 1) * per)
 
     def _dp_layer(self, i):
         """Multicast addresses of layer i's parameters and raw-gradient buffer inside the arena."""

@@ -421,7 +421,26 @@ typedef struct lbbnn_step {
   uint64_t seed;
   float lr, beta1, beta2, eps, kl_scale;
   float* stats;       /* 1 + n_layers floats */
+  const struct lbbnn_step_dp* dp;   /* NULL, or the data-parallel exchange fused into the launch (phases == 3 only) */
 } lbbnn_step;
+/* Data-parallel training inside the ONE launch (the reference has no multi-GPU path): after the backward
+ * phases every rank signals its peers and waits for them (NVLink flags), the update phase then runs SHARDED -- rank r
+ * reduces its contiguous 1/world of all weight quads over the ranks in the switch (multimem.ld_reduce on the raw gradients at
+ * the head of the workspace), applies chain rule + KL gradient (kl_scale, added once) + Adam with its shard of the moments
+ * and stores the new parameters to every rank (multimem.st); rank 0 owns the biases -- and a second flag exchange ends
+ * the launch, also carrying every rank's per-layer KL partial so that stats[1..] is the whole KL on every rank (stats[0] stays
+ * this rank's nll).  Setup: `flat` and the workspace lie at the same offsets of buffers bound to an NVSwitch multicast object
+ * on every rank (flat_mc / ws_mc = their multicast addresses); signal[p] / klx[p] = rank p's signal pad (world uint32) and
+ * KL exchange array (world * LBBNN_STEP_MAX_LAYERS doubles) as addressable from THIS rank (peer mappings; [rank] = own),
+ * all zero-initialised once; epoch = one zero-initialised local device uint64.  grad must be NULL; every in*out % 4 == 0. */
+typedef struct lbbnn_step_dp {
+  int world, rank;
+  float* flat_mc;
+  const float* ws_mc;
+  unsigned int* signal[8];
+  double* klx[8];
+  unsigned long long* epoch;
+} lbbnn_step_dp;
 LBBNN_API size_t lbbnn_lrt_step_workspace_bytes(const lbbnn_step* step);
 LBBNN_API size_t lbbnn_lrt_step_raw_floats(const lbbnn_step* step);
 LBBNN_API int lbbnn_lrt_step_f32(const lbbnn_step* step, int phases, void* workspace, size_t workspace_bytes,

@@ -53,25 +53,23 @@ def run_case(name, make_trainer, dims, per_rank, rank, world, pg, tol):
     torch.cuda.synchronize()
     # Adam's first moment after step 1 is 0.1 x the gradient the update consumed.  With the sharded NVLS update a rank only
     # keeps the moments of the weight quads it owns (a contiguous 1 / world of every weight tensor; rank 0 owns the biases)
-    sharded = getattr(tr_dp, "dp_sharded", False)
     worst = 0.0
-    for l_dp, l_1 in zip(net_dp.layers, net_1.layers):
+    owned = 0
+    for li, (l_dp, l_1) in enumerate(zip(net_dp.layers, net_1.layers)):
         for k in ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"):
             off = tr_dp._offsets[(id(l_dp), k)] if hasattr(tr_dp, "_offsets") else tr_dp.param_off[(id(l_dp), k)]
             off1 = tr_1._offsets[(id(l_1), k)] if hasattr(tr_1, "_offsets") else tr_1.param_off[(id(l_1), k)]
             n = getattr(l_dp, k).numel()
-            lo_e, hi_e = 0, n
-            if sharded:
-                if k.startswith("bias"):
-                    if rank != 0:
-                        continue
-                else:
-                    per = -(-(n // 4) // world)
-                    lo_e, hi_e = 4 * rank * per, min(n, 4 * (rank + 1) * per)
-            g_dp, g_1 = tr_dp.exp_avg[off + lo_e:off + hi_e], tr_1.exp_avg[off1 + lo_e:off1 + hi_e]
-            err = ((g_dp - g_1).double().norm() / g_1.double().norm()).item()
-            worst = max(worst, err)
-            assert err < tol, (name, k, "gradient (exp_avg) of the DP step differs from the single-GPU step", err)
+            lo_e, hi_e = tr_dp.owned_range(li, k)
+            owned += hi_e - lo_e
+            if hi_e > lo_e:
+                g_dp, g_1 = tr_dp.exp_avg[off + lo_e:off + hi_e], tr_1.exp_avg[off1 + lo_e:off1 + hi_e]
+                err = ((g_dp - g_1).double().norm() / g_1.double().norm()).item()
+                worst = max(worst, err)
+                assert err < tol, (name, k, "gradient (exp_avg) of the DP step differs from the single-GPU step", err)
+                # ... and nothing outside the owned range was touched
+                rest = torch.cat([tr_dp.exp_avg[off:off + lo_e], tr_dp.exp_avg[off + hi_e:off + n]])
+                assert not rest.numel() or float(rest.abs().max()) == 0.0, (name, k, "moments outside the owned shard changed")
             # the updated parameters are replicated on every rank whatever the update scheme
             p_dp, p_1 = tr_dp.flat[off:off + n], tr_1.flat[off1:off1 + n]
             perr = C.rel_err(p_dp, p_1)
@@ -81,6 +79,12 @@ def run_case(name, make_trainer, dims, per_rank, rank, world, pg, tol):
     nll = torch.tensor([out_dp["nll"]], dtype=torch.float64, device="cuda")
     dist.all_reduce(nll, group=pg)
     assert abs(nll.item() - out_1["nll"]) <= 2e-5 * abs(out_1["nll"]), (name, nll.item(), out_1["nll"])
+    # the shards of all ranks cover every parameter exactly once
+    cover = torch.tensor([owned], dtype=torch.int64, device="cuda")
+    dist.all_reduce(cover, group=pg)
+    n_all = sum(getattr(l, k).numel() for l in net_dp.layers for k in ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"))
+    assert int(cover) == (n_all if tr_dp.owned_range(0, "weight_mu") != (0, net_dp.layers[0].weight_mu.numel()) or world == 1
+                          else n_all * world), (name, int(cover), n_all)
     # every rank holds the same updated parameters
     flat = tr_dp.flat.clone()
     ref = flat.clone()
@@ -104,6 +108,13 @@ def main():
     run_case("lrt_step_kernel", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3, inject_noise=True,
                                                                    process_group=g, fused=True, materialize_grads=True),
              (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
+    # the same kernel with the exchange INSIDE the launch: flags over NVLink, in-switch reduction of each rank's shard of the
+    # raw gradients, sharded chain rule + KL + Adam, multicast store of the parameters (needs NVSwitch multicast)
+    run_case("lrt_step_kernel_in_launch", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3,
+                                                                             inject_noise=True, process_group=g, fused=True,
+                                                                             materialize_grads=False),
+             (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
+    # ... and three more steps of it: the parameter trajectories of the ranks stay identical to the single-GPU run
     # the per-layer launch sequence: .grad all-reduced, KL pre-scaled by 1/world
     run_case("lrt_per_layer", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3, inject_noise=True,
                                                                  process_group=g, fused=False),
