@@ -83,8 +83,8 @@ def run_case(name, make_trainer, dims, per_rank, rank, world, pg, tol):
     cover = torch.tensor([owned], dtype=torch.int64, device="cuda")
     dist.all_reduce(cover, group=pg)
     n_all = sum(getattr(l, k).numel() for l in net_dp.layers for k in ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho"))
-    assert int(cover) == (n_all if tr_dp.owned_range(0, "weight_mu") != (0, net_dp.layers[0].weight_mu.numel()) or world == 1
-                          else n_all * world), (name, int(cover), n_all)
+    sharded = getattr(tr_dp, "dp_sharded", False) or getattr(tr_dp, "_step_dp", None) is not None
+    assert int(cover) == (n_all if sharded else n_all * world), (name, int(cover), n_all)
     # every rank holds the same updated parameters
     flat = tr_dp.flat.clone()
     ref = flat.clone()
@@ -114,7 +114,6 @@ def main():
                                                                              inject_noise=True, process_group=g, fused=True,
                                                                              materialize_grads=False),
              (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
-    # ... and three more steps of it: the parameter trajectories of the ranks stay identical to the single-GPU run
     # the per-layer launch sequence: .grad all-reduced, KL pre-scaled by 1/world
     run_case("lrt_per_layer", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3, inject_noise=True,
                                                                  process_group=g, fused=False),
