@@ -109,6 +109,9 @@ struct DevStep {
   unsigned* dp_signal[8];
   double* dp_klx[8];
   unsigned long long* dp_epoch;
+  int dp_p2p;                // peer-to-peer loads / stores instead of the multicast object
+  float* flat_peer[8];
+  const float* raw_peer[8];
 };
 
 // ---- NVLink flags / NVSwitch multicast (data parallel inside the launch) -------------------------------------------------
@@ -889,7 +892,24 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
     Q4 mu = ldq4<false>(a.flat + y.off_mu + e0, cnt, VEC), rho = ldq4<false>(a.flat + y.off_rho + e0, cnt, VEC);
     Q4 lam = ldq4<false>(a.flat + y.off_lam + e0, cnt, VEC);
     Q4 dM, dV;
-    if (VEC && a.dp_world > 1) {   // summed over the ranks inside the switch (this rank owns the quad)
+    if (VEC && a.dp_world > 1 && a.dp_p2p) {   // this rank owns the quad: sum the ranks' copies over NVLink, in rank order
+      const int64_t om = (y.dM - a.raw_base) + e0, ov = (y.dV - a.raw_base) + e0;
+      float4 t0[8], t1[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < a.dp_world) {
+          t0[q] = __ldcg(reinterpret_cast<const float4*>(a.raw_peer[q] + om));
+          t1[q] = __ldcg(reinterpret_cast<const float4*>(a.raw_peer[q] + ov));
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dM.v[j] = dV.v[j] = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < a.dp_world) {
+          dM.v[0] += t0[q].x; dM.v[1] += t0[q].y; dM.v[2] += t0[q].z; dM.v[3] += t0[q].w;
+          dV.v[0] += t1[q].x; dV.v[1] += t1[q].y; dV.v[2] += t1[q].z; dV.v[3] += t1[q].w;
+        }
+    } else if (VEC && a.dp_world > 1) {   // summed over the ranks inside the switch (this rank owns the quad)
       const float4 t0 = mc_ld_reduce4(a.raw_mc + (y.dM - a.raw_base) + e0), t1 = mc_ld_reduce4(a.raw_mc + (y.dV - a.raw_base) + e0);
       dM.v[0] = t0.x; dM.v[1] = t0.y; dM.v[2] = t0.z; dM.v[3] = t0.w;
       dV.v[0] = t1.x; dV.v[1] = t1.y; dV.v[2] = t1.z; dV.v[3] = t1.w;
@@ -934,7 +954,14 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
       adam1(rho.v[j], g1.v[j], m1.v[j], v1.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
       adam1(lam.v[j], g2.v[j], m2.v[j], v2.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
     }
-    if (VEC && a.dp_world > 1) {   // the new parameters go to every rank's copy
+    if (VEC && a.dp_world > 1 && a.dp_p2p) {   // the new parameters go to every rank's copy (posted stores over NVLink)
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < a.dp_world) {
+          stq4(a.flat_peer[q] + y.off_mu + e0, mu, 4, true); stq4(a.flat_peer[q] + y.off_rho + e0, rho, 4, true);
+          stq4(a.flat_peer[q] + y.off_lam + e0, lam, 4, true);
+        }
+    } else if (VEC && a.dp_world > 1) {   // the new parameters go to every rank's copy
       mc_st4(a.flat_mc + y.off_mu + e0, mu.v); mc_st4(a.flat_mc + y.off_rho + e0, rho.v); mc_st4(a.flat_mc + y.off_lam + e0, lam.v);
     } else {
       stq4(a.flat + y.off_mu + e0, mu, cnt, VEC); stq4(a.flat + y.off_rho + e0, rho, cnt, VEC);
@@ -1008,8 +1035,22 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
     for (int i = threadIdx.x; i < y.N; i += NT) {
       float bm = a.flat[y.off_bmu + i], br = a.flat[y.off_brho + i];
       const float sb = sigma_of(br);
-      float dbm = dp ? mc_ld_reduce1(cs_mc + i) : __ldcg(y.colsum + i);
-      float dsb = 2.0f * sb * (dp ? mc_ld_reduce1(cs_mc + y.N + i) : __ldcg(y.colsum + y.N + i));
+      float dbm, dss;
+      if (dp && a.dp_p2p) {
+        dbm = dss = 0.f;
+        for (int q = 0; q < a.dp_world; ++q) {
+          const float* cq = a.raw_peer[q] + (y.colsum - a.raw_base);
+          dbm += __ldcg(cq + i);
+          dss += __ldcg(cq + y.N + i);
+        }
+      } else if (dp) {
+        dbm = mc_ld_reduce1(cs_mc + i);
+        dss = mc_ld_reduce1(cs_mc + y.N + i);
+      } else {
+        dbm = __ldcg(y.colsum + i);
+        dss = __ldcg(y.colsum + y.N + i);
+      }
+      float dsb = 2.0f * sb * dss;
       kb += kl_bias_elem(bm, sb, P);
       dbm += klg * (bm - P.bias_mu) * inv;
       dsb += klg * (sb * inv - 1.0f / sb);
@@ -1018,7 +1059,9 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
       float mm0 = a.m[y.off_bmu + i], vv0 = a.v[y.off_bmu + i], mm1 = a.m[y.off_brho + i], vv1 = a.v[y.off_brho + i];
       adam1(bm, dbm, mm0, vv0, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
       adam1(br, dbr, mm1, vv1, a.b1, a.b2, a.eps, step_size, bc2_sqrt);
-      if (dp) { mc_st1(a.flat_mc + y.off_bmu + i, bm); mc_st1(a.flat_mc + y.off_brho + i, br); }
+      if (dp && a.dp_p2p) {
+        for (int q = 0; q < a.dp_world; ++q) { a.flat_peer[q][y.off_bmu + i] = bm; a.flat_peer[q][y.off_brho + i] = br; }
+      } else if (dp) { mc_st1(a.flat_mc + y.off_bmu + i, bm); mc_st1(a.flat_mc + y.off_brho + i, br); }
       else { a.flat[y.off_bmu + i] = bm; a.flat[y.off_brho + i] = br; }
       a.m[y.off_bmu + i] = mm0; a.v[y.off_bmu + i] = vv0; a.m[y.off_brho + i] = mm1; a.v[y.off_brho + i] = vv1;
     }
@@ -1055,6 +1098,7 @@ __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ 
   __syncthreads();
   if (!is_last) return;
   __threadfence();
+  if (a.prof && threadIdx.x == 0) a.prof[200] = clock64();
   for (int l = 0; l < a.L; ++l) {
     double acc = 0.0;
     for (int c = threadIdx.x; c < (int)gridDim.x; c += NT) acc += __ldcg(a.kl_part + (int64_t)l * gridDim.x + c);
@@ -1069,7 +1113,9 @@ __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ 
   if (a.dp_world > 1 && threadIdx.x == 0) {
     // closing exchange: every rank's parameter stores and KL partials have landed before anyone's next launch reads them
     const unsigned e = (unsigned)(*(volatile unsigned long long*)a.dp_epoch) + 1u;
+    if (a.prof) a.prof[201] = clock64();
     dp_flag_exchange(a, e);
+    if (a.prof) a.prof[202] = clock64();
     *a.dp_epoch = e;
     for (int l = 0; l < a.L; ++l) {
       double tot = 0.0;
@@ -1416,9 +1462,12 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
         dp_flag_exchange(a, e);
         *a.dp_epoch = e;
       }
+      stamp(a, slot);
       grid.sync();
+      stamp(a, slot);
     }
     update_layers(a, step, 0, u_first ? 1 : a.L, blockIdx.x, G, sm);   // layers >= 1 were done during B_0 if u_first
+    stamp(a, slot);
     finish_step(a, step, sm);
   }
   stamp(a, slot);
@@ -1728,19 +1777,26 @@ extern "C" int lbbnn_lrt_step_f32(const lbbnn_step* S, int phases, void* ws, siz
   d.lr = S->lr; d.b1 = S->beta1; d.b2 = S->beta2; d.eps = S->eps; d.klg = S->kl_scale;
   d.stats = S->stats;
   d.prof = g_step_prof;
+  d.dp_p2p = 0;
+  for (int p = 0; p < 8; ++p) { d.flat_peer[p] = nullptr; d.raw_peer[p] = nullptr; }
   d.dp_world = 1; d.dp_rank = 0; d.flat_mc = nullptr; d.raw_mc = nullptr; d.raw_base = (const float*)ws; d.dp_epoch = nullptr;
   for (int p = 0; p < 8; ++p) { d.dp_signal[p] = nullptr; d.dp_klx[p] = nullptr; }
   if (S->dp && S->dp->world > 1) {
     const lbbnn_step_dp* D = S->dp;
     LBBNN_REQUIRE(phases == 3, "the in-launch data-parallel exchange needs phases == 3");
     LBBNN_REQUIRE(D->world <= 8 && D->rank >= 0 && D->rank < D->world, "bad data-parallel rank %d of %d", D->rank, D->world);
-    LBBNN_REQUIRE(D->flat_mc && D->ws_mc && D->epoch, "NULL multicast address / epoch");
+    LBBNN_REQUIRE(D->epoch && (D->use_p2p || (D->flat_mc && D->ws_mc)), "NULL multicast address / epoch");
     LBBNN_REQUIRE(S->grad == nullptr, "the sharded update does not materialise gradients (grad must be NULL)");
     for (int p = 0; p < D->world; ++p) LBBNN_REQUIRE(D->signal[p] && D->klx[p], "NULL peer mapping %d", p);
     for (int l = 0; l < d.L; ++l)
       LBBNN_REQUIRE(((int64_t)d.ly[l].N * d.ly[l].K) % 4 == 0, "sharded update needs in*out %% 4 == 0 (layer %d)", l);
     d.dp_world = D->world; d.dp_rank = D->rank; d.flat_mc = D->flat_mc; d.raw_mc = D->ws_mc; d.dp_epoch = D->epoch;
     for (int p = 0; p < D->world; ++p) { d.dp_signal[p] = D->signal[p]; d.dp_klx[p] = D->klx[p]; }
+    d.dp_p2p = D->use_p2p ? 1 : 0;
+    for (int p = 0; p < D->world; ++p) {
+      LBBNN_REQUIRE(!D->use_p2p || (D->flat_peer[p] && D->ws_peer[p]), "NULL peer buffer %d", p);
+      d.flat_peer[p] = D->flat_peer[p]; d.raw_peer[p] = D->ws_peer[p];
+    }
   }
   d.overlap_update = (getenv("LBBNN_STEP_OVERLAP_UPDATE") && d.dp_world == 1) ? 1 : 0;
   d.prof_cta = g_step_prof_cta;

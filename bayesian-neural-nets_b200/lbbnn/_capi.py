@@ -108,7 +108,8 @@ class StepLayer(C.Structure):
 
 class StepDp(C.Structure):
     _fields_ = [("world", C.c_int), ("rank", C.c_int), ("flat_mc", C.c_void_p), ("ws_mc", C.c_void_p),
-                ("signal", C.c_void_p * 8), ("klx", C.c_void_p * 8), ("epoch", C.c_void_p)]
+                ("signal", C.c_void_p * 8), ("klx", C.c_void_p * 8), ("epoch", C.c_void_p), ("use_p2p", C.c_int),
+                ("flat_peer", C.c_void_p * 8), ("ws_peer", C.c_void_p * 8)]
 
 
 class Step(C.Structure):

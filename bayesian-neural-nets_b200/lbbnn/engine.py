@@ -107,7 +107,7 @@ class LRTTrainer:
         self._dp_arena None (two launches around an all-reduce of the raw gradients) when the fabric has no multicast."""
         import os
         mode = os.environ.get("LBBNN_DP_ALLREDUCE", "auto")
-        if mode not in ("auto", "sharded"):
+        if mode not in ("auto", "sharded", "sharded_p2p"):
             return
         try:
             import torch.distributed._symmetric_memory as symm_mem
@@ -126,16 +126,16 @@ class LRTTrainer:
             arena = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
             arena.zero_()
             hdl = symm_mem.rendezvous(arena, self.pg.group_name)
-            if int(hdl.multicast_ptr) == 0:
+            if int(hdl.multicast_ptr) == 0 and mode != "sharded_p2p":
                 raise RuntimeError("no multicast support on this fabric")
             hdl.barrier(channel=0)
             torch.cuda.synchronize()
         except Exception as e:  # noqa: BLE001
-            if mode == "sharded":
+            if mode != "auto":
                 raise
             self._ar_error = repr(e)
             return
-        self._dp_arena = dict(arena=arena, hdl=hdl, flat=arena[:4 * n_flat].view(torch.float32), off_ws=off_ws, ws_bytes=ws_bytes,
+        self._dp_arena = dict(p2p=(mode == "sharded_p2p"), arena=arena, hdl=hdl, flat=arena[:4 * n_flat].view(torch.float32), off_ws=off_ws, ws_bytes=ws_bytes,
                               off_sig=off_sig, off_klx=off_klx, epoch=torch.zeros(1, dtype=torch.int64, device=self.device))
 
     def _init_fused(self, sizes, inject_noise, use_graph):
@@ -179,10 +179,13 @@ class LRTTrainer:
             for p in range(self.world):
                 dp.signal[p], dp.klx[p] = peers[p] + A["off_sig"], peers[p] + A["off_klx"]
             dp.epoch = A["epoch"].data_ptr()
+            dp.use_p2p = 1 if A["p2p"] else 0
+            for p in range(self.world):
+                dp.flat_peer[p], dp.ws_peer[p] = peers[p], peers[p] + A["off_ws"]
             self._step_dp = dp
             import ctypes
             st.dp = ctypes.pointer(dp)
-            self.allreduce = "nvls-sharded-update (inside the step kernel)"
+            self.allreduce = ("p2p-sharded-update" if A["p2p"] else "nvls-sharded-update") + " (inside the step kernel)"
         elif self.pg is not None:
             self.ws = self._symmetric_workspace(nbytes)                   # NVLink/NVSwitch peer-mapped, for the all-reduce
         if self.ws is None:

@@ -440,6 +440,13 @@ typedef struct lbbnn_step_dp {
   unsigned int* signal[8];
   double* klx[8];
   unsigned long long* epoch;
+  /* optional peer-to-peer form of the same exchange (no multicast object needed): flat_peer[p] / ws_peer[p] = rank p's
+   * parameter buffer / workspace as addressable from this rank.  When use_p2p != 0 the owner sums its shard of the raw
+   * gradients with plain loads from every peer (rank order: deterministic) and writes the new parameters to every peer
+   * with plain stores; flat_mc / ws_mc are then ignored. */
+  int use_p2p;
+  float* flat_peer[8];
+  const float* ws_peer[8];
 } lbbnn_step_dp;
 LBBNN_API size_t lbbnn_lrt_step_workspace_bytes(const lbbnn_step* step);
 LBBNN_API size_t lbbnn_lrt_step_raw_floats(const lbbnn_step* step);
