@@ -106,8 +106,12 @@ class LRTTrainer:
         exchange] bound to an NVSwitch multicast object, for the in-launch sharded update (lbbnn_step_dp).  Leaves
         self._dp_arena None (two launches around an all-reduce of the raw gradients) when the fabric has no multicast."""
         import os
+        # measured at 2 GPUs (us / step, 109-112 on one): two launches around torch's two-shot all-reduce 137; the exchange
+        # inside the launch 140 (multicast) / 135-150 (peer-to-peer) -- four dependent NVLink round trips of ~6 us each
+        # (flags, pull, push + fence, flags) cost what the second launch and the all-reduce kernel cost, so "auto" keeps the
+        # two-launch form and the in-launch forms are opt-in (profiles/r02_step_dp_phases.txt)
         mode = os.environ.get("LBBNN_DP_ALLREDUCE", "auto")
-        if mode not in ("auto", "sharded", "sharded_p2p"):
+        if mode not in ("sharded", "sharded_p2p"):
             return
         try:
             import torch.distributed._symmetric_memory as symm_mem

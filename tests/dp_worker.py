@@ -110,10 +110,13 @@ def main():
              (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
     # the same kernel with the exchange INSIDE the launch: flags over NVLink, in-switch reduction of each rank's shard of the
     # raw gradients, sharded chain rule + KL + Adam, multicast store of the parameters (needs NVSwitch multicast)
-    run_case("lrt_step_kernel_in_launch", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3,
-                                                                             inject_noise=True, process_group=g, fused=True,
-                                                                             materialize_grads=False),
-             (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
+    for mode in ("sharded", "sharded_p2p"):
+        os.environ["LBBNN_DP_ALLREDUCE"] = mode
+        run_case(f"lrt_step_kernel_in_launch[{mode}]",
+                 lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3, inject_noise=True, process_group=g,
+                                                    fused=True, materialize_grads=False),
+                 (136, 72, 40, 10), 32, rank, world, pg, 2e-5)
+    os.environ.pop("LBBNN_DP_ALLREDUCE")
     # the per-layer launch sequence: .grad all-reduced, KL pre-scaled by 1/world
     run_case("lrt_per_layer", lambda net, B, g: lbbnn.LRTTrainer(net, batch_size=B, num_batches=NB, lr=1e-3, inject_noise=True,
                                                                  process_group=g, fused=False),

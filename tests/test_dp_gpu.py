@@ -20,4 +20,4 @@ def test_data_parallel_step_equals_single_gpu_step_on_the_concatenated_batch():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     sys.stdout.write(r.stdout[-4000:])
     assert r.returncode == 0, r.stdout[-3000:] + "\n" + r.stderr[-6000:]
-    assert r.stdout.count(" OK, ") == 5
+    assert r.stdout.count(" OK, ") == 6
