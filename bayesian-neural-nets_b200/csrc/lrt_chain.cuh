@@ -62,6 +62,30 @@ __device__ __forceinline__ void grads(const Consts& c, float mu, float rho, floa
   glam = dal * al * (1.0f - al);
 }
 
+// The NEXT step's operands and KL term from the just-updated parameters -- what lrt_bf16_prologue computes (same expressions:
+// sigma = log1p(e^rho), alpha = 1 / (1 + e^-lambda), M = alpha mu, V per var_mode; KL of LRT:189-192 in the shared-exponential
+// form of kl_weight_elem_shared in lrt_f32.cu).
+struct KlC { float log_ps, inv_2ps2, log_pa, log_1mpa, mu_p; };
+__device__ __forceinline__ KlC make_klc(const lbbnn_priors& p) {
+  KlC c;
+  c.log_ps = logf(p.sigma);
+  c.inv_2ps2 = 0.5f / (p.sigma * p.sigma);
+  c.log_pa = logf(p.alpha);
+  c.log_1mpa = logf(1.0f - p.alpha);
+  c.mu_p = p.mu;
+  return c;
+}
+__device__ __forceinline__ void next_moments(const KlC& c, int var_mode, float mu, float rho, float lam, float& M, float& V, float& kl) {
+  const float sg = log1pf(expf(rho));
+  const float t = expf(-lam), al = 1.0f / (1.0f + t);
+  M = mu * al;
+  V = (var_mode == LBBNN_VAR_REFERENCE) ? (sg * sg) * (al * al) : al * (sg * sg + (1.0f - al) * mu * mu);
+  const float d = mu - c.mu_p;
+  const float log_al = -log1pf(t);
+  const float slab = (c.log_ps - logf(sg)) - 0.5f + (log_al - c.log_pa) + (sg * sg + d * d) * c.inv_2ps2;
+  kl = al * slab + (1.0f - al) * ((log_al - lam) - c.log_1mpa);
+}
+
 // torch.optim.Adam (no amsgrad / weight decay) on one element; same approximations as adam_quad in lrt_f32.cu
 __device__ __forceinline__ void adam(const Consts& c, float& p, float& m, float& v, float g) {
   m = m + (g - m) * (1.0f - c.b1);

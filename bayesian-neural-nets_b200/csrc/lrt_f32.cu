@@ -1269,6 +1269,14 @@ extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM
   return check_launch("lrt_f32_finalize_adam");
 }
 
+extern "C" int lbbnn_lrt_kl_finalize(const double* kl_part, int64_t n_part, const lbbnn_layer* L, const lbbnn_priors* pri,
+                                     float* kl_out, lbbnn_stream s) {
+  if (int rc = check_layer(L)) return rc;
+  LBBNN_REQUIRE(kl_part && pri && kl_out && n_part > 0 && n_part < (1LL << 31), "bad argument");
+  lrt_kl_finalize<<<1, kThreads, 0, (cudaStream_t)s>>>(kl_part, (int)n_part, L->bias_mu, L->bias_rho, L->out_features, *pri, kl_out);
+  return check_launch("lrt_kl_finalize");
+}
+
 extern "C" int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* L, const float* colsum, const lbbnn_priors* pri, int flags,
                                                 float kl_grad_host, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;

@@ -116,8 +116,14 @@ struct TcEpi {
   lbbnn_priors pri;
   int var_mode;
   float klg, beta1, beta2, adam_eps;
+  // optional: the NEXT step's bf16 operands M, V (out,in) and per-warp KL partials from the updated parameters
+  __nv_bfloat16 *next_M, *next_V;
+  double* next_kl_part;                                  // [gridDim.x * kEpiWarps]
   // operand majors
   int a_mn, b_mn;
+  // TMA L2 prefetch distance in K blocks (0 = off): the producer asks L2 for the boxes it will load `l2_prefetch` K blocks
+  // later, so the loads that miss L2 (~20 % at the wide shape) do not expose HBM latency to a 4-stage ring
+  int l2_prefetch;
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -125,7 +131,8 @@ __device__ __forceinline__ void st4(float* p, float a, float b, float c, float d
 
 // ---- fused dW epilogue: chain rule + KL gradient + Adam on the accumulators --------------------------------------------------
 // 4 consecutive weights of one output row (N % 4 == 0): nine fp32 tensors stream through (mu, rho, lambda + both Adam moments)
-__device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts& cc, int64_t off, const float4 dM, const float4 dV) {
+__device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts& cc, const chain::KlC& kc, float& kl_acc, int64_t off,
+                                             const float4 dM, const float4 dV) {
   const float4 mu4 = ld4(e.p_mu + off), rho4 = ld4(e.p_rho + off), lam4 = ld4(e.p_lam + off);
   const float4 mm4 = ld4(e.m_mu + off), mr4 = ld4(e.m_rho + off), ml4 = ld4(e.m_lam + off);
   const float4 vm4 = ld4(e.v_mu + off), vr4 = ld4(e.v_rho + off), vl4 = ld4(e.v_lam + off);
@@ -147,6 +154,20 @@ __device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts
   st4(e.m_lam + off, ml[0], ml[1], ml[2], ml[3]);
   st4(e.v_mu + off, vm[0], vm[1], vm[2], vm[3]); st4(e.v_rho + off, vr[0], vr[1], vr[2], vr[3]);
   st4(e.v_lam + off, vl[0], vl[1], vl[2], vl[3]);
+  if (e.next_M) {   // the next forward's operands + KL term, from the values just written (replaces that step's prologue pass)
+    float M[4], V[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float k_;
+      chain::next_moments(kc, cc.var_mode, mu[t], rho[t], lam[t], M[t], V[t], k_);
+      kl_acc += k_;
+    }
+    uint2 pm, pv;
+    pm.x = pack_bf16(M[0], M[1]); pm.y = pack_bf16(M[2], M[3]);
+    pv.x = pack_bf16(V[0], V[1]); pv.y = pack_bf16(V[2], V[3]);
+    *reinterpret_cast<uint2*>(e.next_M + off) = pm;
+    *reinterpret_cast<uint2*>(e.next_V + off) = pv;
+  }
 }
 
 // One warp's 32 rows x 64 columns of both accumulators.  tcgen05.ld hands every lane ONE ROW (16 columns per load), but the
@@ -158,8 +179,9 @@ __device__ __forceinline__ void dw_adam_quad(const TcEpi& e, const chain::Consts
 // register pipeline of the nine loads (spills at the 168-register cap of a 10-warp CTA), an L2 prefetch of the next tile's
 // parameters during the MMA wait, streaming (evict-first) hints -- each 5-15 % SLOWER: the fused kernel moves
 // 1.2 GB of optimiser state next to ~0.75 GB of operand traffic and is bound by HBM / the power cap, not by load latency.
-__device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts& cc, int64_t M, int64_t N, int64_t row0,
-                                             int64_t col0, uint32_t tbase, float* __restrict__ stg, int lane) {
+__device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts& cc, const chain::KlC& kc, float& kl_acc, int64_t M,
+                                             int64_t N, int64_t row0, int64_t col0, uint32_t tbase, float* __restrict__ stg,
+                                             int lane) {
 #pragma unroll 1
   for (int c = 0; c < 64 / EW; ++c) {
     float v1[EW], v2[EW];
@@ -179,7 +201,7 @@ __device__ __forceinline__ void dw_adam_tile(const TcEpi& e, const chain::Consts
       const float4 dM = ld4(stg + rr * 32 + ((qd ^ (rr & 7)) << 2));
       const float4 dV = ld4(stg + rr * 32 + (((4 + qd) ^ (rr & 7)) << 2));
       const int64_t row = row0 + rr;
-      if (row < M && col < N) dw_adam_quad(e, cc, row * N + col, dM, dV);
+      if (row < M && col < N) dw_adam_quad(e, cc, kc, kl_acc, row * N + col, dM, dV);
     }
     __syncwarp();
   }
@@ -495,8 +517,12 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     Noise nz = epi.noise;
     nz.resolve();
     chain::Consts cc = {};
-    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM)
+    chain::KlC kc = {};
+    float kl_acc = 0.f;
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
       cc = chain::make_consts(epi.pri, epi.var_mode, epi.klg, epi.beta1, epi.beta2, epi.adam_eps, epi.coef);
+      kc = chain::make_klc(epi.pri);
+    }
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;                      // 0..255 among the epilogue threads
     int it = 0;
@@ -522,7 +548,7 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       const int64_t row = m0 + q * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
       if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
-        dw_adam_tile(epi, cc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
+        dw_adam_tile(epi, cc, kc, kl_acc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
       } else {
 #pragma unroll 1
         for (int c = 0; c < 64 / EW; ++c) {
@@ -536,6 +562,12 @@ tc_dual_gemm_bf16(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[as]);
+    }
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
+      if (epi.next_kl_part) {     // this warp's share of the next step's KL (fixed tile -> CTA -> warp assignment: deterministic)
+        const float w = warp_sum(kl_acc);
+        if (lane == 0) epi.next_kl_part[(int64_t)blockIdx.x * kEpiWarps + (warp - 2)] = (double)w;
+      }
     }
   }
   tc_fence_before();
@@ -562,6 +594,7 @@ constexpr int kStageBytes2 = 2 * kTileBytes + 2 * kBHalfBytes;  // 48 KB
 constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256 + kEpiScratchBytes;
 static_assert(kSmemBytes <= 232448 && kSmemBytes2 <= 232448, "over the 227 KB shared-memory limit");
 constexpr int kGroupM2 = kGroupM / 2;                          // in 256-row blocks
+constexpr int kL2Prefetch = 0;                                 // default TMA L2 prefetch distance (K blocks); see TcEpi::l2_prefetch
 
 __device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -626,6 +659,29 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
         tile_coords2(t, num_m2, num_n, group, mb2, nb);
         const int m0 = mb2 * 2 * BM + (int)rank * BM, n0h = nb * BN + (int)rank * (BN / 2);
         for (int kb = 0; kb < num_kb; ++kb) {
+          if (epi.l2_prefetch > 0) {       // the boxes of K block kb + distance (this tile, or the head of this cluster's next one)
+            int pk = kb + epi.l2_prefetch, pm0 = m0, pn0 = n0h;
+            bool ok = true;
+            if (pk >= num_kb) {
+              pk -= num_kb;
+              const int tn = t + num_clusters;
+              ok = tn < num_tiles && pk < num_kb;
+              if (ok) {
+                int pmb2, pnb;
+                tile_coords2(tn, num_m2, num_n, group, pmb2, pnb);
+                pm0 = pmb2 * 2 * BM + (int)rank * BM; pn0 = pnb * BN + (int)rank * (BN / 2);
+              }
+            }
+            if (ok) {
+              if constexpr (!AMN) { tma_prefetch_l2_2d(&tmA1, pk * BK, pm0); tma_prefetch_l2_2d(&tmA2, pk * BK, pm0); }
+              else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) { tma_prefetch_l2_2d(&tmA1, pm0 + 64 * h, pk * BK); tma_prefetch_l2_2d(&tmA2, pm0 + 64 * h, pk * BK); }
+              }
+              if constexpr (!BMN) { tma_prefetch_l2_2d(&tmB1, pk * BK, pn0); tma_prefetch_l2_2d(&tmB2, pk * BK, pn0); }
+              else { tma_prefetch_l2_2d(&tmB1, pn0, pk * BK); tma_prefetch_l2_2d(&tmB2, pn0, pk * BK); }
+            }
+          }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * kStageBytes2;
           const uint32_t lead_full = mapa_u32(&full_bar[stage], 0);
@@ -687,8 +743,12 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
     Noise nz = epi.noise;
     nz.resolve();
     chain::Consts cc = {};
-    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM)
+    chain::KlC kc = {};
+    float kl_acc = 0.f;
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
       cc = chain::make_consts(epi.pri, epi.var_mode, epi.klg, epi.beta1, epi.beta2, epi.adam_eps, epi.coef);
+      kc = chain::make_klc(epi.pri);
+    }
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int et = threadIdx.x - 64;
     int it = 0;
@@ -714,7 +774,7 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       const int64_t row = m0 + q * 32 + lane;
       const uint32_t tbase = tmem_base + ((uint32_t)(q * 32) << 16) + as * 256 + half * 64;
       if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
-        dw_adam_tile(epi, cc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
+        dw_adam_tile(epi, cc, kc, kl_acc, M, N, m0 + q * 32, n0 + half * 64, tbase, sbias_all + (warp - 2) * 1024, lane);
       } else {
 #pragma unroll 1
         for (int c = 0; c < 64 / EW; ++c) {
@@ -728,6 +788,12 @@ tc_dual_gemm_bf16_pair(const __grid_constant__ CUtensorMap tmA1, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[as], 0));
+    }
+    if constexpr (MODE == LBBNN_TC_EPI_DW_ADAM) {
+      if (epi.next_kl_part) {
+        const float w = warp_sum(kl_acc);
+        if (lane == 0) epi.next_kl_part[(int64_t)blockIdx.x * kEpiWarps + (warp - 2)] = (double)w;
+      }
     }
   }
   __syncwarp();                 // warps 0 and 1 ran single-lane loops: reconverge before the aligned cluster barrier
@@ -790,9 +856,14 @@ int make_map_mn(CUtensorMap* map, const void* ptr, int64_t rows, int64_t K) {
   return LBBNN_OK;
 }
 
-int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N, int64_t K, const TcEpi& epi,
+int launch_tc(const void* A1, const void* A2, const void* B1, const void* B2, int64_t M, int64_t N, int64_t K, const TcEpi& epi_in,
               cudaStream_t st) {
   LBBNN_REQUIRE(A1 && A2 && B1 && B2 && M > 0 && N > 0 && K > 0, "bad GEMM operands");
+  TcEpi epi = epi_in;
+  {
+    const char* pf = getenv("LBBNN_TC_L2_PREFETCH");     // K blocks ahead; default kL2Prefetch
+    epi.l2_prefetch = pf ? atoi(pf) : kL2Prefetch;
+  }
   LBBNN_REQUIRE(M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31), "GEMM dims must fit int32");
   CUtensorMap mA1, mA2, mB1, mB2;
   if (epi.a_mn) {
@@ -976,9 +1047,25 @@ extern "C" int lbbnn_tc_lrt_bwd_input_mn(const void* dE_bf, const void* dS_bf, c
   return launch_tc(dE_bf, dS_bf, M_bf, V_bf, batch, in_features, out_features, e, (cudaStream_t)s);
 }
 
+extern "C" size_t lbbnn_tc_lrt_dw_adam_kl_parts(void) { return (size_t)sm_count() * kEpiWarps; }
+
+extern "C" int lbbnn_tc_lrt_dw_adam_next(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
+                                         const lbbnn_layer* L, int64_t batch, const lbbnn_priors* pri, int var_mode,
+                                         float kl_grad, const lbbnn_adam_layer_state* adam, void* next_M_bf, void* next_V_bf,
+                                         double* next_kl_part, lbbnn_stream s);
+
 extern "C" int lbbnn_tc_lrt_dw_adam(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
                                     const lbbnn_layer* L, int64_t batch, const lbbnn_priors* pri, int var_mode,
                                     float kl_grad, const lbbnn_adam_layer_state* adam, lbbnn_stream s) {
+  return lbbnn_tc_lrt_dw_adam_next(dE_bf, dS_bf, x_bf, x2_bf, L, batch, pri, var_mode, kl_grad, adam, nullptr, nullptr, nullptr, s);
+}
+
+extern "C" int lbbnn_tc_lrt_dw_adam_next(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
+                                         const lbbnn_layer* L, int64_t batch, const lbbnn_priors* pri, int var_mode,
+                                         float kl_grad, const lbbnn_adam_layer_state* adam, void* next_M_bf, void* next_V_bf,
+                                         double* next_kl_part, lbbnn_stream s) {
+  LBBNN_REQUIRE((next_M_bf == nullptr) == (next_V_bf == nullptr), "next_M / next_V come in pairs");
+  LBBNN_REQUIRE(next_kl_part == nullptr || next_M_bf != nullptr, "next_kl_part needs next_M / next_V");
   LBBNN_REQUIRE(L && pri && adam && adam->coef, "NULL argument");
   LBBNN_REQUIRE(L->weight_mu && L->weight_rho && L->lambdal && L->in_features > 0 && L->out_features > 0, "bad layer");
   LBBNN_REQUIRE(L->z == nullptr && L->z_kl == nullptr, "the fused update is for LRT layers (no multiplicative z)");
@@ -993,6 +1080,9 @@ extern "C" int lbbnn_tc_lrt_dw_adam(const void* dE_bf, const void* dS_bf, const 
   for (int i = 0; i < 9; ++i) LBBNN_REQUIRE((reinterpret_cast<uintptr_t>(ptrs[i]) & 15) == 0, "parameters / Adam state must be 16B aligned");
   e.coef = adam->coef; e.pri = *pri; e.var_mode = var_mode; e.klg = kl_grad;
   e.beta1 = adam->beta1; e.beta2 = adam->beta2; e.adam_eps = adam->eps;
+  e.next_M = (__nv_bfloat16*)next_M_bf; e.next_V = (__nv_bfloat16*)next_V_bf; e.next_kl_part = next_kl_part;
+  if (next_kl_part)   // CTAs without a tile (small problems) leave their slots untouched: clear all of them first
+    LBBNN_CUDA(cudaMemsetAsync(next_kl_part, 0, lbbnn_tc_lrt_dw_adam_kl_parts() * sizeof(double), (cudaStream_t)s));
   // dM = dE^T x, dV = dS^T x^2 (out, in), contraction over the batch: both operands read in place as MN-major
   e.a_mn = 1; e.b_mn = 1;
   return launch_tc(dE_bf, dS_bf, x_bf, x2_bf, L->out_features, L->in_features, batch, e, (cudaStream_t)s);

@@ -46,6 +46,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+// bring a tile of the tensor map into L2 without a shared-memory destination (cute::SM90_TMA_LOAD_2D::PREFETCH)
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c_inner), "r"(c_outer) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -163,6 +163,10 @@ SIGNATURES = {
     "lbbnn_tc_lrt_bwd_input_mn": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P]),
     "lbbnn_tc_lrt_dw_adam": (_INT, [_P, _P, _P, _P, C.POINTER(Layer), _I64, C.POINTER(Priors), _INT, _F,
                                     C.POINTER(AdamLayerState), _P]),
+    "lbbnn_tc_lrt_dw_adam_kl_parts": (_SZ, []),
+    "lbbnn_tc_lrt_dw_adam_next": (_INT, [_P, _P, _P, _P, C.POINTER(Layer), _I64, C.POINTER(Priors), _INT, _F,
+                                         C.POINTER(AdamLayerState), _P, _P, _P, _P]),
+    "lbbnn_lrt_kl_finalize": (_INT, [_P, _I64, C.POINTER(Layer), C.POINTER(Priors), _P, _P]),
     "lbbnn_lrt_f32_finalize_adam_bias": (_INT, [C.POINTER(Layer), _P, C.POINTER(Priors), _INT, _F, C.POINTER(AdamLayerState), _P]),
     "lbbnn_lrt_f32_finalize_adam_dp": (_INT, [C.POINTER(Layer), C.POINTER(DpLayer), C.POINTER(Priors), _INT, _INT, _F,
                                               C.POINTER(AdamLayerState), _P]),

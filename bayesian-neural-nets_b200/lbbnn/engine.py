@@ -332,6 +332,8 @@ class LRTTrainer:
         torch.cuda.synchronize()
         for t, saved in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_dev), state):
             t.copy_(saved)   # the warm-up step must not count as training
+        if hasattr(self, "_after_restore"):
+            self._after_restore()   # state derived from the parameters (carried bf16 operands)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._enqueue()
@@ -455,12 +457,15 @@ class LRTTensorCoreTrainer:
 
     def __init__(self, net, batch_size, num_batches, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, seed=None,
                  use_graph=True, inject_noise=False, process_group=None, fused_update=True, fused_prologue=True,
-                 fused_head_dx=True, overlap=True, small_head=False, in_place=None):
+                 fused_head_dx=True, overlap=True, small_head=False, in_place=None, carry_operands=True):
         """in_place (default: whenever the stack allows it -- every layer but a <= 12-output head has out_features % 8 == 0):
         the backward GEMMs read dE, dS, x, x^2, M, V where the forward left them (tcgen05 MN-major operands) instead of
         transposed copies, the dX epilogue emits the bias-gradient partial sums, and on one GPU with fused_update the dW
         GEMM's epilogue applies chain rule + KL gradient + Adam to its accumulators (lbbnn_tc_lrt_dw_adam): dM / dV never
-        reach memory.  in_place=False keeps the r01 sequence (transposed K-major operands, separate update pass)."""
+        reach memory.  in_place=False keeps the r01 sequence (transposed K-major operands, separate update pass).
+        carry_operands: with that fused update the epilogue also writes the NEXT step's bf16 M, V and KL partial sums from the
+        parameters it has just updated (lbbnn_tc_lrt_dw_adam_next), so the layer needs no prologue pass per step; its
+        operands are derived state: call refresh_operands() after changing parameters from outside (load_state_dict ...)."""
         K.require_device()
         self.net = net
         self.layers = list(net.layers)
@@ -581,8 +586,10 @@ class LRTTensorCoreTrainer:
             head = last and self.small_dx[li]        # <= 12 outputs: CUDA-core dX, K-major dE^T / dS^T for its dW
             # the dW GEMM's epilogue does the update: one GPU, fused update, tensor-core-sized layer
             epi_update = self.fused_update and self.world == 1 and not head
+            carry = epi_update and bool(carry_operands)
             d = dict(
-                head=head, epi_update=epi_update,
+                head=head, epi_update=epi_update, carry=carry,
+                klpart=torch.zeros(int(K.lib.lbbnn_tc_lrt_dw_adam_kl_parts()), dtype=torch.float64, device=dev) if carry else None,
                 M=torch.zeros(o, i, **bf), V=torch.zeros(o, i, **bf), MT=None, VT=None,
                 mv32=torch.zeros(K.lrt_mv_bytes(i, o) // 4, **f32) if head else None,
                 act=None if last else torch.zeros(B, o, **bf), act2=None if last else torch.zeros(B, o, **bf),
@@ -606,6 +613,8 @@ class LRTTensorCoreTrainer:
             self.xT_bf = self.x2T_bf = self.M32 = self.V32 = None
             if self.fused_update:
                 self.dM = self.dV = None
+        self.kl_next = torch.zeros(L, **f32)     # KL of the layers whose operands are carried from the previous update
+        self.carry_any = self.in_place and any(d["carry"] for d in self.tc)
         self.inject = inject_noise
         self.stats = torch.zeros(1 + L, **f32)
         nbytes = max([1 << 20, B // 8 * 4 + 1024] +
@@ -619,8 +628,25 @@ class LRTTensorCoreTrainer:
         self.stats_host = torch.zeros(1 + L, dtype=torch.float32).pin_memory()
         self.kernels_per_step = 0
         self.graph = None
+        self.refresh_operands()
         if use_graph:
             self._capture()
+
+    def refresh_operands(self):
+        """bf16 M, V and the KL term of every layer whose operands are carried from update to update (carry_operands),
+        recomputed from the current parameters: at construction, after the capture's warm-up step was rolled back, and to be
+        called by the user after changing parameters from outside the trainer."""
+        if not getattr(self, "carry_any", False):
+            return
+        st, bf = K.current_stream(), torch.bfloat16
+        for i, (l, d) in enumerate(zip(self.layers, self.tc)):
+            if not d["carry"]:
+                continue
+            desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
+            K.check(K.lib.lbbnn_lrt_bf16_prologue(desc, l.cfg.priors, l.cfg.var_mode, K.ptr(d["M"], bf), K.ptr(d["V"], bf), None, None,
+                                                  None, None, self.kl_next[i:].data_ptr(), d["klws"].data_ptr(), d["klws"].numel(), st))
+
+    _after_restore = refresh_operands
 
     def _noise(self, i):
         if self.inject:
@@ -706,11 +732,15 @@ class LRTTensorCoreTrainer:
                                                 P(M32, True), P(V32, True), self.stats[1 + i:].data_ptr(), d["klws"].data_ptr(),
                                                 d["klws"].numel(), stream))
 
+        if self.carry_any:                 # KL of the carried layers: computed by the previous step's update epilogues
+            self.stats[1:].copy_(self.kl_next); n += 1
         ready = [None] * L
-        if self.side_prologue:             # all prologues up front on the side stream; each forward GEMM waits for its own
+        if self.side_prologue:             # prologues up front on the side stream; each forward GEMM waits for its own
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 for i in range(L):
+                    if self.tc[i]["carry"]:
+                        continue
                     prologue(i, K.current_stream()); n += 2
                     ready[i] = torch.cuda.Event()
                     ready[i].record(side)
@@ -719,7 +749,9 @@ class LRTTensorCoreTrainer:
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
             last = i == L - 1
-            if self.side_prologue:
+            if d["carry"]:
+                pass                        # M, V were written by the previous step's dW epilogue (or refresh_operands)
+            elif self.side_prologue:
                 main.wait_event(ready[i])
             else:
                 prologue(i, st); n += 2
@@ -753,12 +785,30 @@ class LRTTensorCoreTrainer:
                 K.check(lib.lbbnn_colsum2(P(d["g32"]), P(d["dsf"]), 0, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
             elif d["colpart"] is not None:  # bias sums of this layer: partials written by the dX epilogue of the layer above
                 K.check(lib.lbbnn_tc_colsum_reduce(P(d["colpart"]), B, fo, P(d["colsum"]), st)); n += 1
+            def dx():
+                # ---- dx = dE M + 2 x (dS V) -> the layer below's dE, dS (+ bias partial sums) ----
+                p = self.tc[i - 1]
+                K.check(lib.lbbnn_tc_lrt_bwd_input_mn(P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
+                                                      P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
+                                                      P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"]), st))
+
             # ---- dM = dE^T x, dV = dS^T x^2 (+ update) ----
             if d["epi_update"]:            # chain rule + KL + Adam in the GEMM's epilogue; biases in a one-block kernel
-                K.check(lib.lbbnn_tc_lrt_dw_adam(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), descs[i], B,
-                                                 l.cfg.priors, l.cfg.var_mode, klg_post, self._adam_state(l), st)); n += 1
+                if d["carry"]:
+                    if i > 0:              # the epilogue below overwrites M, V with the next step's: their last reader goes first
+                        dx(); n += 1
+                    K.check(lib.lbbnn_tc_lrt_dw_adam_next(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), descs[i], B,
+                                                          l.cfg.priors, l.cfg.var_mode, klg_post, self._adam_state(l),
+                                                          P(d["M"], bf), P(d["V"], bf), d["klpart"].data_ptr(), st)); n += 2
+                else:
+                    K.check(lib.lbbnn_tc_lrt_dw_adam(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), descs[i], B,
+                                                     l.cfg.priors, l.cfg.var_mode, klg_post, self._adam_state(l), st)); n += 1
                 K.check(lib.lbbnn_lrt_f32_finalize_adam_bias(descs[i], P(d["colsum"]), l.cfg.priors, K.FLAG_SAMPLE, klg_post,
                                                              self._adam_state(l), st)); n += 1
+                if d["carry"]:             # next step's KL of this layer: weight partials + the (updated) bias term
+                    K.check(lib.lbbnn_lrt_kl_finalize(d["klpart"].data_ptr(), d["klpart"].numel(), descs[i], l.cfg.priors,
+                                                      self.kl_next[i:].data_ptr(), st)); n += 1
+                    continue
             else:
                 if self.fused_update:
                     dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
@@ -796,9 +846,7 @@ class LRTTensorCoreTrainer:
                                                          P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf),
                                                          P(p["dS"], bf), None, None, P(p["colsum"]), ws, wsn, st)); n += 2
             else:
-                K.check(lib.lbbnn_tc_lrt_bwd_input_mn(P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
-                                                      P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
-                                                      P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"]), st)); n += 1
+                dx(); n += 1
         if self.fused_update:
             if side is not None:
                 main.wait_stream(side)

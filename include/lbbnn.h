@@ -542,6 +542,18 @@ LBBNN_API int lbbnn_tc_lrt_bwd_input_mn(const void* dE_bf, const void* dS_bf, co
 LBBNN_API int lbbnn_tc_lrt_dw_adam(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
                                    const lbbnn_layer* layer, int64_t batch, const lbbnn_priors* priors, int var_mode,
                                    float kl_grad, const lbbnn_adam_layer_state* adam, lbbnn_stream s);
+/* dw_adam that also emits what the NEXT step's forward needs from the updated parameters, so that step runs without a
+ * prologue pass for this layer: next_M_bf, next_V_bf (out,in) bf16 = lbbnn_lrt_bf16_prologue's M, V of the new mu, rho,
+ * lambda, and next_kl_part = lbbnn_tc_lrt_dw_adam_kl_parts() doubles, per-warp partial sums of the weights' KL terms
+ * (LRT:189-192); lbbnn_lrt_kl_finalize adds them in a fixed order together with the bias term (LRT:185-186) of the
+ * layer's (already updated) biases into kl_out.  The arrays may be NULL (then identical to lbbnn_tc_lrt_dw_adam). */
+LBBNN_API size_t lbbnn_tc_lrt_dw_adam_kl_parts(void);
+LBBNN_API int lbbnn_tc_lrt_dw_adam_next(const void* dE_bf, const void* dS_bf, const void* x_bf, const void* x2_bf,
+                                        const lbbnn_layer* layer, int64_t batch, const lbbnn_priors* priors, int var_mode,
+                                        float kl_grad, const lbbnn_adam_layer_state* adam, void* next_M_bf, void* next_V_bf,
+                                        double* next_kl_part, lbbnn_stream s);
+LBBNN_API int lbbnn_lrt_kl_finalize(const double* kl_part, int64_t n_part, const lbbnn_layer* layer,
+                                    const lbbnn_priors* priors, float* kl_out, lbbnn_stream s);
 
 /* The same update for a whole parameter list in ONE launch (optim.Adam(net.parameters()) of the MNF script, MNF:352,
  * and the 33 per-tensor parameter groups of the MF script, MF:520-553: learning rates 1e-4 for weights / biases, 1e-3

@@ -57,6 +57,12 @@ timeit("fwd   r01: act, act^2 + transposes, dsf", lambda: K.lib.lbbnn_tc_lrt_fwd
 timeit("fwd   r02: act, act^2, dsf (no transposed outputs)", lambda: K.lib.lbbnn_tc_lrt_fwd(
     P(xb, bf), P(x2b, bf), P(Mb, bf), P(Vb, bf), B, I, O, P(l.bias_mu.data), P(l.bias_rho.data), noise, fl, P(act, bf), P(act2, bf),
     None, None, P(dsf), None, st))
+for dist in (os.environ.get("LBBNN_AB_PREFETCH", "").split() or []):
+    os.environ["LBBNN_TC_L2_PREFETCH"] = dist
+    timeit(f"fwd   r02 with TMA L2 prefetch {dist} K blocks ahead", lambda: K.lib.lbbnn_tc_lrt_fwd(
+        P(xb, bf), P(x2b, bf), P(Mb, bf), P(Vb, bf), B, I, O, P(l.bias_mu.data), P(l.bias_rho.data), noise, fl, P(act, bf), P(act2, bf),
+        None, None, P(dsf), None, st))
+os.environ.pop("LBBNN_TC_L2_PREFETCH", None)
 
 de = (torch.randn(B, O, device="cuda") * 0.1).to(bf)
 ds = (torch.randn(B, O, device="cuda") * 0.01).to(bf)
@@ -66,6 +72,11 @@ t_raw = timeit("dW    r01: raw, K-major transposed operands", lambda: K.lib.lbbn
     P(deT, bf), P(dsT, bf), P(xT, bf), P(x2T, bf), O, I, B, P(dM), P(dV), st))
 timeit("dW    r02: raw_ex, operands in place (MN-major A and B)", lambda: K.lib.lbbnn_tc_dual_gemm_raw_ex(
     P(de, bf), P(ds, bf), P(xb, bf), P(x2b, bf), O, I, B, 1, 1, P(dM), P(dV), st))
+for dist in (os.environ.get("LBBNN_AB_PREFETCH", "").split() or []):
+    os.environ["LBBNN_TC_L2_PREFETCH"] = dist
+    timeit(f"dW    r02 raw_ex with TMA L2 prefetch {dist} K blocks ahead", lambda: K.lib.lbbnn_tc_dual_gemm_raw_ex(
+        P(de, bf), P(ds, bf), P(xb, bf), P(x2b, bf), O, I, B, 1, 1, P(dM), P(dV), st))
+os.environ.pop("LBBNN_TC_L2_PREFETCH", None)
 names = ("weight_mu", "weight_rho", "lambdal", "bias_mu", "bias_rho")
 m = {k: torch.zeros_like(getattr(l, k).data) for k in names}
 v = {k: torch.zeros_like(getattr(l, k).data) for k in names}
