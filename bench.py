@@ -488,7 +488,7 @@ def bench_lrt(ctx, workload, steps, warmup, unfused=False, cpu_budget_s=15.0):
         tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
                                         fused_update=not args.unfused,
                                         in_place=False if os.environ.get("LBBNN_WIDE_R01") else None,
-                                        carry_operands=os.environ.get("LBBNN_WIDE_CARRY", "1") != "0")
+                                        carry_operands=os.environ.get("LBBNN_WIDE_CARRY", "0") == "1")
     else:   # the fused persistent step kernel unless --unfused; gradients stay in registers (no .grad written)
         tr = lbbnn.LRTTrainer(net, batch_size=B, num_batches=NUM_BATCHES, lr=1e-3, process_group=pg,
                               fused=not args.unfused, materialize_grads=args.unfused)

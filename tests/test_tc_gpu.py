@@ -418,8 +418,9 @@ def test_wide_trainer_fused_prologue_and_head_match_the_separate_passes():
             assert (a[k] - b[k]).norm() / a[k].norm() < 5e-3, (li, k, ((a[k] - b[k]).norm() / a[k].norm()).item())
 
 
+@pytest.mark.parametrize("carry", [False, True])
 @pytest.mark.parametrize("use_graph", [False, True])
-def test_wide_trainer_fused_update_matches_separate_passes(use_graph):
+def test_wide_trainer_fused_update_matches_separate_passes(use_graph, carry):
     """fused_update=True (chain rule + KL gradient + Adam in one pass per layer, lbbnn_lrt_f32_finalize_adam) follows the
     same parameter trajectory as finalize -> .grad -> lbbnn_adam_f32 over three steps with injected noise."""
     import lbbnn
@@ -434,7 +435,8 @@ def test_wide_trainer_fused_update_matches_separate_passes(use_graph):
                 for k, v in p.items():
                     getattr(l, k).copy_(v)
         tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-2, use_graph=use_graph,
-                                        inject_noise=True, fused_update=fused)
+                                        inject_noise=True, fused_update=fused, carry_operands=carry and fused)
+        assert tr.in_place and (not fused or tr.tc[0]["epi_update"]) and tr.carry_any == (carry and fused)
         for d, e in zip(tr.tc, case["eps"]):
             d["eps"].copy_(e)
         nets.append(net)
