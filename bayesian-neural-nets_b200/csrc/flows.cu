@@ -48,33 +48,64 @@ __device__ __forceinline__ float mask_of(const float* __restrict__ masks, const 
   return philox_uniform1(nz.seed, nz.stream + (uint64_t)t, (uint64_t)r * (uint64_t)D + (uint64_t)d) < 0.5f ? 1.0f : 0.0f;
 }
 
-// One warp per output neuron j of a caller-chosen subset (j = first, first + step, ...): out[j] = act(b[j] + W[j,:] v).
-// `bcast` > 0: the result is written into the `out` array of EVERY CTA of the cluster (distributed shared memory).
+// Every GEMV of a flow evaluation is a LATENCY chain (a few hundred weights per thread-block, one row of z): the mappings
+// below put all weight loads of a phase in flight at once (fully unrolled, predicated) so a phase costs about one L2 round
+// trip instead of one per loop iteration / per warp pass (r01: 65 us forward, 113 us backward for dim 784, 2 transforms).
+constexpr int kQ = 4;                 // threads per output of the narrow GEMVs
+constexpr int kHK = kMaxH / kQ;       // weights per thread (in <= kMaxH)
+constexpr int kGroup = kFlowThreads / kQ;   // outputs per pass of a narrow GEMV (= kMaxH)
+static_assert(kGroup == kMaxH, "one pass of the narrow GEMV covers the widest hidden layer");
+
+// dot(w0[0..n), v[0..n)) by one warp; lanes take float4 columns, 8 independent loads in flight per lane
+__device__ __forceinline__ float dot_row_warp(const float* __restrict__ w0, const float* __restrict__ v, int n, bool vec, int lane) {
+  float a = 0.f;
+  if (vec) {
+    const float4* p0 = reinterpret_cast<const float4*>(w0);
+    const float4* pv = reinterpret_cast<const float4*>(v);
+    const int n4 = n >> 2;
+    for (int base = 0; base < n4; base += 256) {
+      float4 q[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        q[k] = i < n4 ? __ldg(p0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        if (i < n4) {
+          const float4 x = pv[i];
+          a = fmaf(q[k].x, x.x, fmaf(q[k].y, x.y, fmaf(q[k].z, x.z, fmaf(q[k].w, x.w, a))));
+        }
+      }
+    }
+  } else {
+    for (int base = 0; base < n; base += 256) {
+      float q[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        q[k] = i < n ? __ldg(w0 + i) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        if (i < n) a = fmaf(q[k], v[i], a);
+      }
+    }
+  }
+  return warp_sum(a);
+}
+
+// Wide-input layer (in = D): one warp per output neuron j of a caller-chosen subset (j = first, first + step, ...):
+// out[j] = act(b[j] + W[j,:] v).  `bcast` > 0: the result is written into the `out` array of EVERY CTA of the cluster
+// (distributed shared memory).
 __device__ __forceinline__ void gemv_rows(const Lin& L, const float* __restrict__ v, float* __restrict__ out, int kind, bool last,
                                           float* __restrict__ save, int first, int step, cg::cluster_group& cl, int bcast) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool vec = (L.in % 4 == 0) && aligned16(L.W) && aligned16(v);
   for (int j = first + warp * step; j < L.out; j += kWarps * step) {
-    const float* w0 = L.W + (int64_t)j * L.in;
-    float a0 = 0.f, a1 = 0.f;
-    if (vec) {
-      const float4* p0 = reinterpret_cast<const float4*>(w0);
-      const float4* pv = reinterpret_cast<const float4*>(v);
-      const int n4 = L.in >> 2;
-      int i = lane;
-      for (; i + 32 < n4; i += 64) {
-        const float4 x = pv[i], q = __ldg(p0 + i), y = pv[i + 32], u = __ldg(p0 + i + 32);
-        a0 = fmaf(q.x, x.x, fmaf(q.y, x.y, fmaf(q.z, x.z, fmaf(q.w, x.w, a0))));
-        a1 = fmaf(u.x, y.x, fmaf(u.y, y.y, fmaf(u.z, y.z, fmaf(u.w, y.w, a1))));
-      }
-      if (i < n4) {
-        const float4 x = pv[i], q = __ldg(p0 + i);
-        a0 = fmaf(q.x, x.x, fmaf(q.y, x.y, fmaf(q.z, x.z, fmaf(q.w, x.w, a0))));
-      }
-    } else {
-      for (int i = lane; i < L.in; i += 32) a0 = fmaf(__ldg(w0 + i), v[i], a0);
-    }
-    a0 = warp_sum(a0 + a1);
+    const float a0 = dot_row_warp(L.W + (int64_t)j * L.in, v, L.in, vec, lane);
     const float h = act_fwd(kind, last, a0 + __ldg(L.b + j));
     if (bcast > 0) {
       if (lane < bcast) cl.map_shared_rank(out, lane)[j] = h;
@@ -82,6 +113,34 @@ __device__ __forceinline__ void gemv_rows(const Lin& L, const float* __restrict_
       out[j] = h;
     }
     if (save && lane == 0) save[j] = h;
+  }
+}
+
+// Narrow layer (in, out <= kMaxH), whole layer in one pass: kQ threads per neuron, thread p of a quad takes inputs p, p + 4, ...
+__device__ __forceinline__ void gemv_small(const Lin& L, const float* __restrict__ v, float* __restrict__ out, int kind, bool last,
+                                           float* __restrict__ save) {
+  const int j = threadIdx.x >> 2, p = threadIdx.x & 3;
+  float acc = 0.f;
+  if (j < L.out) {
+    const float* w = L.W + (int64_t)j * L.in;
+    float wr[kHK];
+#pragma unroll
+    for (int k = 0; k < kHK; ++k) {
+      const int i = p + kQ * k;
+      wr[k] = i < L.in ? __ldg(w + i) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < kHK; ++k) {
+      const int i = p + kQ * k;
+      if (i < L.in) acc = fmaf(wr[k], v[i], acc);
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (j < L.out && p == 0) {
+    const float h = act_fwd(kind, last, acc + __ldg(L.b + j));
+    out[j] = h;
+    if (save) save[j] = h;
   }
 }
 
@@ -131,38 +190,62 @@ __global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f,
     float* cur = hb;
     if (svh) svh += f.hidden[t][0].out;
     for (int l = 1; l < f.n_hidden; ++l) {
-      gemv_rows(f.hidden[t][l], v, cur, f.kind, l == f.n_hidden - 1, c == 0 ? svh : nullptr, 0, 1, cl, 0);
+      gemv_small(f.hidden[t][l], v, cur, f.kind, l == f.n_hidden - 1, c == 0 ? svh : nullptr);
       if (svh) svh += f.hidden[t][l].out;
       __syncthreads();
       v = cur;
       cur = (cur == ha) ? hb : ha;
     }
-    // shift / scale heads and the coupling for the dims of this CTA's slice: one warp per dim, lanes over the hidden units
+    // shift / scale heads and the coupling for the dims of this CTA's slice: kQ threads per dim, each with its quarter of
+    // both weight rows in flight at once
     const Lin& Ls = f.shift[t];
     const Lin& Lc = f.scale[t];
     const int H = Ls.in;
     float ld = 0.f;
-    for (int d = d0 + warp; d < d1; d += kWarps) {
-      const float* ws = Ls.W + (int64_t)d * H;
-      const float* wc = Lc.W + (int64_t)d * H;
+    const int p = tid & 3;
+    for (int base = d0; base < d1; base += kGroup) {
+      const int d = base + (tid >> 2);
+      const bool ok = d < d1;
       float a1 = 0.f, a2 = 0.f;
-      for (int i = lane; i < H; i += 32) {
-        const float vi = v[i];
-        a1 = fmaf(__ldg(ws + i), vi, a1);
-        a2 = fmaf(__ldg(wc + i), vi, a2);
+      if (ok) {
+        const float* ws = Ls.W + (int64_t)d * H;
+        const float* wc = Lc.W + (int64_t)d * H;
+        float w1[kHK], w2[kHK];
+#pragma unroll
+        for (int k = 0; k < kHK; ++k) {
+          const int i = p + kQ * k;
+          w1[k] = i < H ? __ldg(ws + i) : 0.f;
+          w2[k] = i < H ? __ldg(wc + i) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < kHK; ++k) {
+          const int i = p + kQ * k;
+          if (i < H) {
+            const float vi = v[i];
+            a1 = fmaf(w1[k], vi, a1);
+            a2 = fmaf(w2[k], vi, a2);
+          }
+        }
       }
-      a1 = warp_sum(a1);
-      a2 = warp_sum(a2);
-      const float sh = a1 + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-(a2 + __ldg(Lc.b + d))));
-      const float z = zs[d], m = ms[d];
-      float x;
-      if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
-      else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
-      if (lane < C) cl.map_shared_rank(zs, lane)[d] = x;          // the new z of this dim, into every CTA
-      if (lane == 0) {
-        ld += (1.0f - m) * logf(g);
-        if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
+      float x = 0.f;
+      if (ok) {
+        const float sh = a1 + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-(a2 + __ldg(Lc.b + d))));
+        const float z = zs[d], m = ms[d];
+        if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
+        else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
+        if (p == 0) {
+          ld += (1.0f - m) * logf(g);
+          if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
+        }
       }
+      __syncwarp();      // every thread of the quad has read zs[d] before one of them overwrites it (own CTA included)
+      // the new z of this dim into every CTA (the quad shares the remote stores); no CTA reads another's dims in this phase
+      if (ok)
+        for (int k = p; k < C; k += kQ) cl.map_shared_rank(zs, k)[d] = x;
     }
     const float tot = block_sum(ld, red);
     if (tid == 0) cl.map_shared_rank(ldp, 0)[c] = tot;
@@ -197,15 +280,18 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
   float* ms = sm + 4 * Dp;        // [D] this transform's mask, all dims
   float* da = sm + 5 * Dp;        // [kMaxH] gradient wrt a hidden layer's pre-activation
   float* dh = da + kMaxH;         // [kMaxH] gradient wrt a hidden layer's output
-  float* part = dh + kMaxH;       // [kWarps][kMaxH]
-  float* dyp = part + kWarps * kMaxH;   // [kMaxCluster][kMaxH] per-CTA partials of the conditioner-output gradient
+  float* part = dh + kMaxH;       // [kQ][kMaxH] partial sums of the narrow transposed GEMVs
+  float* dyp = part + kQ * kMaxH; // [kMaxCluster][kMaxH] per-CTA partials of the conditioner-output gradient
+  float* hall = dyp + kMaxCluster * kMaxH;   // [LBBNN_FLOW_MAX_HIDDEN][kMaxH] this transform's saved hidden activations
   Noise nz = mask_noise;
   nz.resolve();
   const int64_t r = blockIdx.x / C;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int per = (D + C - 1) / C, d0 = c * per, d1 = min(D, d0 + per);
   const float dld = dlogdet ? dlogdet[r] : 0.f;
   const int64_t goff = r * f.grad_row_stride;
+  const int gi = tid & (kMaxH - 1), gp = tid >> 7;      // narrow transposed GEMVs: output index, quarter of the reduction
+  static_assert(kFlowThreads == kQ * kMaxH, "thread = (output, quarter)");
   for (int d = d0 + tid; d < d1; d += kFlowThreads) dz[d] = dz_out ? dz_out[r * D + d] : 0.f;
   cl.sync();
   for (int t = f.n_transforms - 1; t >= 0; --t) {
@@ -217,9 +303,16 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
     const Lin& Ls = f.shift[t];
     const Lin& Lc = f.scale[t];
     const int H = Ls.in;
-    int hoff_last = 0;
-    for (int l = 0; l + 1 < f.n_hidden; ++l) hoff_last += f.hidden[t][l].out;
-    const float* y = hsave + hoff_last;   // output of the conditioner net
+    // saved hidden activations of this transform -> shared memory (layer l at hall + l * kMaxH)
+    {
+      int off = 0;
+      for (int l = 0; l < f.n_hidden; ++l) {
+        const int n = f.hidden[t][l].out;
+        if (tid < n) hall[l * kMaxH + tid] = hsave[off + tid];
+        off += n;
+      }
+    }
+    const float* y = hall + (f.n_hidden - 1) * kMaxH;   // output of the conditioner net
     // masks and conditioner input for all dims (the first layer's weight gradient needs them); coupling backward for
     // the dims of this CTA's slice
     for (int d = tid; d < D; d += kFlowThreads) {
@@ -246,36 +339,43 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
       }
     }
     __syncthreads();
-    // head weight gradients (outer products dsh x y, dsc x y) and the partial of dy[i] = sum_d Wt[d,i] dsh[d] + Ws[d,i] dsc[d]
-    // over this CTA's dims: warps take dims, lanes run over i (coalesced rows)
+    // head weight gradients: the outer products dsh x y, dsc x y of this CTA's dims, one flat coalesced sweep
     {
-      float acc[kMaxH / 32];
+      const int n = (d1 - d0) * H;
+      float* ps = Ls.dW + goff + (int64_t)d0 * H;
+      float* pc = Lc.dW + goff + (int64_t)d0 * H;
+      for (int idx = tid; idx < n; idx += kFlowThreads) {
+        const int dl = idx / H, i = idx - dl * H;
+        const float yi = y[i];
+        ps[idx] = dsh[d0 + dl] * yi;
+        pc[idx] = dsc[d0 + dl] * yi;
+      }
+    }
+    // partial of dy[i] = sum_d Wt[d,i] dsh[d] + Ws[d,i] dsc[d] over this CTA's dims: thread (i, quarter of the dims),
+    // consecutive threads read consecutive i (coalesced rows), 16 dims = 32 loads in flight per thread
+    {
+      float acc = 0.f;
+      if (gi < H) {
+        for (int base = d0 + gp; base < d1; base += kQ * 16) {
+          float w1[16], w2[16];
 #pragma unroll
-      for (int k = 0; k < kMaxH / 32; ++k) acc[k] = 0.f;
-      for (int d = d0 + warp; d < d1; d += kWarps) {
-        const float a = dsh[d], cc = dsc[d];
-        const float* ws = Ls.W + (int64_t)d * H;
-        const float* wc = Lc.W + (int64_t)d * H;
-        float* ps = Ls.dW + goff + (int64_t)d * H;
-        float* pc = Lc.dW + goff + (int64_t)d * H;
+          for (int k = 0; k < 16; ++k) {
+            const int d = base + kQ * k;
+            w1[k] = d < d1 ? __ldg(Ls.W + (int64_t)d * H + gi) : 0.f;
+            w2[k] = d < d1 ? __ldg(Lc.W + (int64_t)d * H + gi) : 0.f;
+          }
 #pragma unroll
-        for (int k = 0; k < kMaxH / 32; ++k) {
-          const int i = lane + 32 * k;
-          if (i < H) {
-            const float yi = y[i];
-            ps[i] = a * yi;
-            pc[i] = cc * yi;
-            acc[k] = fmaf(__ldg(ws + i), a, fmaf(__ldg(wc + i), cc, acc[k]));
+          for (int k = 0; k < 16; ++k) {
+            const int d = base + kQ * k;
+            if (d < d1) acc = fmaf(w1[k], dsh[d], fmaf(w2[k], dsc[d], acc));
           }
         }
       }
-#pragma unroll
-      for (int k = 0; k < kMaxH / 32; ++k) part[warp * kMaxH + lane + 32 * k] = acc[k];
+      part[gp * kMaxH + gi] = acc;
     }
     __syncthreads();
     for (int i = tid; i < H; i += kFlowThreads) {
-      float s = 0.f;
-      for (int w = 0; w < kWarps; ++w) s += part[w * kMaxH + i];
+      const float s = (part[i] + part[kMaxH + i]) + (part[2 * kMaxH + i] + part[3 * kMaxH + i]);
       for (int k = 0; k < C; ++k) cl.map_shared_rank(dyp, k)[c * kMaxH + i] = s;   // this CTA's partial, into every CTA
     }
     cl.sync();
@@ -286,54 +386,74 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
     }
     __syncthreads();
     // conditioner net backward, last hidden layer first (every CTA carries the full (H,) gradients)
-    int hoff = hoff_last;
     for (int l = f.n_hidden - 1; l >= 0; --l) {
       const Lin& L = f.hidden[t][l];
-      const float* hout = hsave + hoff;                                  // this layer's post-activation output
-      const float* vin = (l == 0) ? xm : (hsave + hoff - f.hidden[t][l - 1].out);   // its input
+      const float* hout = hall + l * kMaxH;                              // this layer's post-activation output
+      const float* vin = (l == 0) ? xm : (hall + (l - 1) * kMaxH);       // its input
       for (int j = tid; j < L.out; j += kFlowThreads) {
         const float g = dh[j] * act_bwd(f.kind, l == f.n_hidden - 1, hout[j]);
         da[j] = g;
         if (c == 0) L.db[goff + j] = g;
       }
       __syncthreads();
-      for (int j = c + warp * C; j < L.out; j += kWarps * C) {          // weight-gradient rows j = c (mod C)
-        const float a = da[j];
-        float* pw = L.dW + goff + (int64_t)j * L.in;
-        for (int i = lane; i < L.in; i += 32) pw[i] = a * vin[i];
+      // weight-gradient rows j = c (mod C): outer product da[j] x vin, one flat coalesced sweep over (own rows) x in
+      {
+        const int rows = c < L.out ? (L.out - c + C - 1) / C : 0;
+        const int n = rows * L.in;
+        for (int idx = tid; idx < n; idx += kFlowThreads) {
+          const int jr = idx / L.in, i = idx - jr * L.in;
+          const int j = c + jr * C;
+          L.dW[goff + (int64_t)j * L.in + i] = da[j] * vin[i];
+        }
       }
-      // gradient wrt the layer input: dv[i] = sum_j W[j,i] da[j]; threads over i (coalesced), loop over j
+      // gradient wrt the layer input: dv[i] = sum_j W[j,i] da[j]; thread (i, quarter of j): consecutive threads read
+      // consecutive i of a weight row, all of a thread's loads in flight at once
       if (l == 0) {
-        for (int i = d0 + tid; i < d1; i += kFlowThreads) {               // only this CTA's dims
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int j = 0;
-          for (; j + 3 < L.out; j += 4) {
-            s0 = fmaf(__ldg(L.W + (int64_t)(j + 0) * L.in + i), da[j + 0], s0);
-            s1 = fmaf(__ldg(L.W + (int64_t)(j + 1) * L.in + i), da[j + 1], s1);
-            s2 = fmaf(__ldg(L.W + (int64_t)(j + 2) * L.in + i), da[j + 2], s2);
-            s3 = fmaf(__ldg(L.W + (int64_t)(j + 3) * L.in + i), da[j + 3], s3);
+        for (int base = d0; base < d1; base += kMaxH) {                    // only this CTA's dims
+          const int i = base + gi;
+          float acc = 0.f;
+          if (i < d1) {
+            float wr[kHK];
+#pragma unroll
+            for (int k = 0; k < kHK; ++k) {
+              const int j = gp + kQ * k;
+              wr[k] = j < L.out ? __ldg(L.W + (int64_t)j * L.in + i) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < kHK; ++k) {
+              const int j = gp + kQ * k;
+              if (j < L.out) acc = fmaf(wr[k], da[j], acc);
+            }
           }
-          for (; j < L.out; ++j) s0 = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s0);
-          dz[i] += ms[i] * ((s0 + s1) + (s2 + s3));                       // input of the net was m * z
+          part[gp * kMaxH + gi] = acc;
+          __syncthreads();
+          if (tid < kMaxH && base + tid < d1) {
+            const int d = base + tid;
+            dz[d] += ms[d] * ((part[tid] + part[kMaxH + tid]) + (part[2 * kMaxH + tid] + part[3 * kMaxH + tid]));   // net input was m * z
+          }
+          __syncthreads();
         }
       } else {
-        for (int i = tid; i < L.in; i += kFlowThreads) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-          int j = 0;
-          for (; j + 3 < L.out; j += 4) {
-            s0 = fmaf(__ldg(L.W + (int64_t)(j + 0) * L.in + i), da[j + 0], s0);
-            s1 = fmaf(__ldg(L.W + (int64_t)(j + 1) * L.in + i), da[j + 1], s1);
-            s2 = fmaf(__ldg(L.W + (int64_t)(j + 2) * L.in + i), da[j + 2], s2);
-            s3 = fmaf(__ldg(L.W + (int64_t)(j + 3) * L.in + i), da[j + 3], s3);
+        float acc = 0.f;
+        if (gi < L.in) {
+          float wr[kHK];
+#pragma unroll
+          for (int k = 0; k < kHK; ++k) {
+            const int j = gp + kQ * k;
+            wr[k] = j < L.out ? __ldg(L.W + (int64_t)j * L.in + gi) : 0.f;
           }
-          for (; j < L.out; ++j) s0 = fmaf(__ldg(L.W + (int64_t)j * L.in + i), da[j], s0);
-          part[i] = (s0 + s1) + (s2 + s3);
+#pragma unroll
+          for (int k = 0; k < kHK; ++k) {
+            const int j = gp + kQ * k;
+            if (j < L.out) acc = fmaf(wr[k], da[j], acc);
+          }
         }
+        part[gp * kMaxH + gi] = acc;
         __syncthreads();
-        for (int i = tid; i < L.in; i += kFlowThreads) dh[i] = part[i];
-        hoff -= f.hidden[t][l - 1].out;
+        for (int i = tid; i < L.in; i += kFlowThreads)
+          dh[i] = (part[i] + part[kMaxH + i]) + (part[2 * kMaxH + i] + part[3 * kMaxH + i]);
+        __syncthreads();
       }
-      __syncthreads();
     }
     cl.sync();     // nobody writes the next transform's partials into a CTA that is still summing this one's
   }
@@ -432,7 +552,7 @@ extern "C" int lbbnn_flow_bwd(const lbbnn_flow* F, const lbbnn_flow_grads* G, in
   if (int rc = to_dev(F, G, &d)) return rc;
   LBBNN_REQUIRE(save && dz_in && rows > 0, "NULL argument");
   LBBNN_REQUIRE(rows < (1 << 20), "too many rows");
-  const size_t smem = (size_t)(5 * ((d.dim + 3) & ~3) + 2 * kMaxH + kWarps * kMaxH + kMaxCluster * kMaxH) * sizeof(float);
+  const size_t smem = (size_t)(5 * ((d.dim + 3) & ~3) + 2 * kMaxH + kQ * kMaxH + kMaxCluster * kMaxH + LBBNN_FLOW_MAX_HIDDEN * kMaxH) * sizeof(float);
   if (smem > 48 * 1024) LBBNN_CUDA(cudaFuncSetAttribute(flow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (int rc = launch_cluster(flow_bwd_kernel, (int)rows, cluster_for(d.dim), smem, (cudaStream_t)s, (const FlowDev)d, masks,
                               (const Noise)make_noise(mask_u), rows, dz_out, dlogdet, save, dz_in))

@@ -878,7 +878,9 @@ __device__ __forceinline__ void stq4(float* p, const Q4& q, int cnt, bool vec) {
 
 // one layer's weights: chain rule + KL + Adam over quads; VEC = all quads are full and 16-byte aligned
 // chain rule + KL + Adam of quad q (4 consecutive weights) of one layer; returns the quad's KL contribution
-template <bool VEC, bool REF>
+// DP: the data-parallel exchange of lbbnn_step_dp is compiled in (a separate instantiation: its peer / multicast paths cost
+// the single-GPU kernel registers -- 109 -> 128 us/step with spills when they shared one body)
+template <bool VEC, bool REF, bool DP>
 __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y, float step_size, float inv_bc2_sqrt, int64_t q) {
   const lbbnn_priors P = y.pri;
   const float klg = a.klg;
@@ -892,7 +894,7 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
     Q4 mu = ldq4<false>(a.flat + y.off_mu + e0, cnt, VEC), rho = ldq4<false>(a.flat + y.off_rho + e0, cnt, VEC);
     Q4 lam = ldq4<false>(a.flat + y.off_lam + e0, cnt, VEC);
     Q4 dM, dV;
-    if (VEC && a.dp_world > 1 && a.dp_p2p) {   // this rank owns the quad: sum the ranks' copies over NVLink, in rank order
+    if (DP && VEC && a.dp_p2p) {   // this rank owns the quad: sum the ranks' copies over NVLink, in rank order
       const int64_t om = (y.dM - a.raw_base) + e0, ov = (y.dV - a.raw_base) + e0;
       float4 t0[8], t1[8];
 #pragma unroll
@@ -909,7 +911,7 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
           dM.v[0] += t0[q].x; dM.v[1] += t0[q].y; dM.v[2] += t0[q].z; dM.v[3] += t0[q].w;
           dV.v[0] += t1[q].x; dV.v[1] += t1[q].y; dV.v[2] += t1[q].z; dV.v[3] += t1[q].w;
         }
-    } else if (VEC && a.dp_world > 1) {   // summed over the ranks inside the switch (this rank owns the quad)
+    } else if (DP && VEC) {   // summed over the ranks inside the switch (this rank owns the quad)
       const float4 t0 = mc_ld_reduce4(a.raw_mc + (y.dM - a.raw_base) + e0), t1 = mc_ld_reduce4(a.raw_mc + (y.dV - a.raw_base) + e0);
       dM.v[0] = t0.x; dM.v[1] = t0.y; dM.v[2] = t0.z; dM.v[3] = t0.w;
       dV.v[0] = t1.x; dV.v[1] = t1.y; dV.v[2] = t1.z; dV.v[3] = t1.w;
@@ -954,14 +956,14 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
       adam1(rho.v[j], g1.v[j], m1.v[j], v1.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
       adam1(lam.v[j], g2.v[j], m2.v[j], v2.v[j], a.b1, a.b2, a.eps, step_size, inv_bc2_sqrt);
     }
-    if (VEC && a.dp_world > 1 && a.dp_p2p) {   // the new parameters go to every rank's copy (posted stores over NVLink)
+    if (DP && VEC && a.dp_p2p) {   // the new parameters go to every rank's copy (posted stores over NVLink)
 #pragma unroll
       for (int q = 0; q < 8; ++q)
         if (q < a.dp_world) {
           stq4(a.flat_peer[q] + y.off_mu + e0, mu, 4, true); stq4(a.flat_peer[q] + y.off_rho + e0, rho, 4, true);
           stq4(a.flat_peer[q] + y.off_lam + e0, lam, 4, true);
         }
-    } else if (VEC && a.dp_world > 1) {   // the new parameters go to every rank's copy
+    } else if (DP && VEC) {   // the new parameters go to every rank's copy
       mc_st4(a.flat_mc + y.off_mu + e0, mu.v); mc_st4(a.flat_mc + y.off_rho + e0, rho.v); mc_st4(a.flat_mc + y.off_lam + e0, lam.v);
     } else {
       stq4(a.flat + y.off_mu + e0, mu, cnt, VEC); stq4(a.flat + y.off_rho + e0, rho, cnt, VEC);
@@ -981,6 +983,7 @@ __device__ __forceinline__ float update_quad(const DevStep& a, const DevLayer& y
 // calls this; `cta` = its index in the range).  The quads of all those layers form ONE index space that is dealt
 // out round-robin, so every thread gets the same number of quads whatever the layer sizes; one CTA per layer also
 // updates its biases.  Each CTA leaves its KL partial of every layer in kl_part[l][blockIdx.x].
+template <bool DP>
 __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, int cta, int ncta, float* __restrict__ sm) {
   __shared__ float coef[2];
   constexpr int NW = NT / 32;
@@ -1000,7 +1003,7 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
   for (int l = l0; l < l1; ++l) total += ((int64_t)a.ly[l].N * a.ly[l].K + 3) >> 2;
   // data parallel: this rank updates a contiguous 1 / world of the quads (and rank 0 the biases)
   int64_t g_first = 0, g_end = total;
-  if (a.dp_world > 1) {
+  if (DP) {
     const int64_t per = (total + a.dp_world - 1) / a.dp_world;
     g_first = min(total, (int64_t)a.dp_rank * per);
     g_end = min(total, g_first + per);
@@ -1017,13 +1020,13 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
     const bool vec = (((int64_t)y.N * y.K) % 4 == 0);
     const bool ref = y.var_mode == LBBNN_VAR_REFERENCE;
     float k_;
-    if (vec) k_ = ref ? update_quad<true, true>(a, y, step_size, bc2_sqrt, q) : update_quad<true, false>(a, y, step_size, bc2_sqrt, q);
-    else k_ = ref ? update_quad<false, true>(a, y, step_size, bc2_sqrt, q) : update_quad<false, false>(a, y, step_size, bc2_sqrt, q);
+    if (vec) k_ = ref ? update_quad<true, true, DP>(a, y, step_size, bc2_sqrt, q) : update_quad<true, false, DP>(a, y, step_size, bc2_sqrt, q);
+    else k_ = ref ? update_quad<false, true, DP>(a, y, step_size, bc2_sqrt, q) : update_quad<false, false, DP>(a, y, step_size, bc2_sqrt, q);
 #pragma unroll
     for (int j = 0; j < kMaxL; ++j) kl[j] += (j == l) ? k_ : 0.f;
   }
   // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); one CTA per layer
-  const bool dp = a.dp_world > 1;
+  constexpr bool dp = DP;
   for (int l = l0; l < l1; ++l) {
     if (cta != (a.L - 1 - l) % ncta) continue;
     if (dp && a.dp_rank != 0) continue;
@@ -1085,10 +1088,11 @@ __device__ void update_layers(const DevStep& a, int64_t step, int l0, int l1, in
 }
 
 // The last CTA to arrive sums the per-CTA partials in a fixed order (deterministic) and bumps the step counter.
+template <bool DP>
 __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ sm) {
   __shared__ int is_last;
   double* dred = reinterpret_cast<double*>(sm);
-  if (a.dp_world > 1) __threadfence_system();   // this CTA's multicast stores of parameters, before the closing flags
+  if (DP) __threadfence_system();   // this CTA's multicast stores of parameters, before the closing flags
   else __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -1104,13 +1108,13 @@ __device__ void finish_step(const DevStep& a, int64_t step, float* __restrict__ 
     for (int c = threadIdx.x; c < (int)gridDim.x; c += NT) acc += __ldcg(a.kl_part + (int64_t)l * gridDim.x + c);
     const double tot = block_sum(acc, dred);
     if (threadIdx.x == 0) {
-      if (a.dp_world > 1) {          // this rank's part of the layer's KL (its shard; rank 0: + the biases) -> every rank
+      if (DP) {          // this rank's part of the layer's KL (its shard; rank 0: + the biases) -> every rank
         for (int p = 0; p < a.dp_world; ++p) a.dp_klx[p][a.dp_rank * kMaxL + l] = tot;
       } else a.stats[1 + l] = (float)tot;
     }
     __syncthreads();
   }
-  if (a.dp_world > 1 && threadIdx.x == 0) {
+  if (DP && threadIdx.x == 0) {
     // closing exchange: every rank's parameter stores and KL partials have landed before anyone's next launch reads them
     const unsigned e = (unsigned)(*(volatile unsigned long long*)a.dp_epoch) + 1u;
     if (a.prof) a.prof[201] = clock64();
@@ -1361,6 +1365,7 @@ __device__ void last_bwd(const DevStep& a, float* __restrict__ sm) {
   }
 }
 
+template <bool DP>
 __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_constant__ DevStep a) {
   extern __shared__ __align__(16) float sm[];
   cg::grid_group grid = cg::this_grid();
@@ -1438,7 +1443,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
         // the raw gradients of layers >= 1 are complete: the CTAs without a layer-0 dW tile update those layers now
         const int busy = min(G, nw);
         if ((int)blockIdx.x >= busy) {
-          update_layers(a, step, 1, a.L, blockIdx.x - busy, G - busy, sm);
+          update_layers<DP>(a, step, 1, a.L, blockIdx.x - busy, G - busy, sm);
         } else if (threadIdx.x == 0) {
           for (int ll = 1; ll < a.L; ++ll) a.kl_part[(int64_t)ll * G + blockIdx.x] = 0.0;
         }
@@ -1455,7 +1460,7 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
     }
   }
   if (a.phases & 2) {
-    if (a.dp_world > 1) {
+    if (DP) {
       // every rank's raw gradients are complete (the grid barrier above + the peers' flags) before anyone reduces them
       if (blockIdx.x == 0 && threadIdx.x == 0) {
         const unsigned e = (unsigned)(*(volatile unsigned long long*)a.dp_epoch) + 1u;
@@ -1466,9 +1471,9 @@ __global__ void __launch_bounds__(NT, kCtasPerSm) lrt_step_kernel(const __grid_c
       grid.sync();
       stamp(a, slot);
     }
-    update_layers(a, step, 0, u_first ? 1 : a.L, blockIdx.x, G, sm);   // layers >= 1 were done during B_0 if u_first
+    update_layers<DP>(a, step, 0, u_first ? 1 : a.L, blockIdx.x, G, sm);   // layers >= 1 were done during B_0 if u_first
     stamp(a, slot);
-    finish_step(a, step, sm);
+    finish_step<DP>(a, step, sm);
   }
   stamp(a, slot);
 }
@@ -1722,10 +1727,12 @@ int step_grid(size_t smem, int* G) {
   static int cached_blocks = -1;
   static size_t cached_smem = 0;
   if (cached_blocks < 0 || smem > cached_smem) {
-    LBBNN_CUDA(cudaFuncSetAttribute(lrt_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
-    int per_sm = 0;
-    LBBNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lrt_step_kernel, NT, kSmemCap));
-    LBBNN_REQUIRE(per_sm >= kCtasPerSm, "lrt_step_kernel does not fit %d CTAs on an SM", kCtasPerSm);
+    LBBNN_CUDA(cudaFuncSetAttribute(lrt_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
+    LBBNN_CUDA(cudaFuncSetAttribute(lrt_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemCap));
+    int per_sm = 0, per_sm_dp = 0;
+    LBBNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lrt_step_kernel<false>, NT, kSmemCap));
+    LBBNN_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_dp, lrt_step_kernel<true>, NT, kSmemCap));
+    LBBNN_REQUIRE(per_sm >= kCtasPerSm && per_sm_dp >= kCtasPerSm, "lrt_step_kernel does not fit %d CTAs on an SM", kCtasPerSm);
     cached_blocks = sm_count() * kCtasPerSm;
     cached_smem = kSmemCap;
   }
@@ -1801,8 +1808,8 @@ extern "C" int lbbnn_lrt_step_f32(const lbbnn_step* S, int phases, void* ws, siz
   d.overlap_update = (getenv("LBBNN_STEP_OVERLAP_UPDATE") && d.dp_world == 1) ? 1 : 0;
   d.prof_cta = g_step_prof_cta;
   void* args[] = {(void*)&d};
-  LBBNN_CUDA(cudaLaunchCooperativeKernel((const void*)lrt_step_kernel, dim3((unsigned)G), dim3(NT), args, kSmemCap,
-                                         (cudaStream_t)s));
+  const void* kern = d.dp_world > 1 ? (const void*)lrt_step_kernel<true> : (const void*)lrt_step_kernel<false>;
+  LBBNN_CUDA(cudaLaunchCooperativeKernel(kern, dim3((unsigned)G), dim3(NT), args, kSmemCap, (cudaStream_t)s));
   return check_launch("lrt_step_kernel");
 }
 
