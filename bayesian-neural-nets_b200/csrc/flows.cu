@@ -19,6 +19,13 @@ namespace cg = cooperative_groups;
 namespace lbbnn {
 namespace {
 
+#ifdef LBBNN_FLOW_PROF   // profiles/flow_phase_prof.cu: clock64 of CTA 0 / thread 0 at the phase boundaries
+__device__ long long g_flow_prof[128];
+#define FLOW_STAMP(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_flow_prof[i] = clock64(); } while (0)
+#else
+#define FLOW_STAMP(i) do { } while (0)
+#endif
+
 constexpr int kMaxCluster = 8;   // portable cluster size
 constexpr int kFlowThreads = 512;
 constexpr int kWarps = kFlowThreads / 32;
@@ -47,16 +54,35 @@ __device__ __forceinline__ float mask_of(const float* __restrict__ masks, const 
   if (masks) return masks[((int64_t)t * R + r) * D + d];
   return philox_uniform1(nz.seed, nz.stream + (uint64_t)t, (uint64_t)r * (uint64_t)D + (uint64_t)d) < 0.5f ? 1.0f : 0.0f;
 }
+// the masks of dims [4q, 4q + 4) of row r (same values as mask_of): one Philox call when the row starts on a quad boundary
+__device__ __forceinline__ void mask_quad(const float* __restrict__ masks, const Noise& nz, int t, int64_t r, int64_t R, int q, int D,
+                                          float m[4]) {
+  const uint64_t e0 = (uint64_t)r * (uint64_t)D + (uint64_t)(4 * q);
+  if (!masks && (e0 & 3) == 0) {
+    float u[4];
+    philox_uniform4(nz.seed, nz.stream + (uint64_t)t, e0 >> 2, u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = u[k] < 0.5f ? 1.0f : 0.0f;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m[k] = 4 * q + k < D ? mask_of(masks, nz, t, r, R, 4 * q + k, D) : 0.f;
+  }
+}
 
 // Every GEMV of a flow evaluation is a LATENCY chain (a few hundred weights per thread-block, one row of z): the mappings
 // below put all weight loads of a phase in flight at once (fully unrolled, predicated) so a phase costs about one L2 round
 // trip instead of one per loop iteration / per warp pass (r01: 65 us forward, 113 us backward for dim 784, 2 transforms).
+// compiler-level fence: every load above it is issued before the first use below (ptxas otherwise interleaves the unrolled
+// loads with their uses four at a time, i.e. one L2 round trip per group instead of one per phase)
+#define LOADS_ISSUED() asm volatile("" ::: "memory")
 constexpr int kQ = 4;                 // threads per output of the narrow GEMVs
-constexpr int kHK = kMaxH / kQ;       // weights per thread (in <= kMaxH)
+constexpr int kHK = kMaxH / kQ;       // weights per thread (in <= kMaxH); the kernels are instantiated for HK = 20 (hidden <= 80) and kHK
 constexpr int kGroup = kFlowThreads / kQ;   // outputs per pass of a narrow GEMV (= kMaxH)
 static_assert(kGroup == kMaxH, "one pass of the narrow GEMV covers the widest hidden layer");
 
-// dot(w0[0..n), v[0..n)) by one warp; lanes take float4 columns, 8 independent loads in flight per lane
+// dot(w0[0..n), v[0..n)) by one warp; lanes take float4 columns, 8 independent loads in flight per lane.  Branch-free
+// (out-of-range lanes re-read the last element and multiply by zero): a branch per element would fence the loads into
+// separate basic blocks and ptxas then issues them one L2 round trip at a time.
 __device__ __forceinline__ float dot_row_warp(const float* __restrict__ w0, const float* __restrict__ v, int n, bool vec, int lane) {
   float a = 0.f;
   if (vec) {
@@ -66,31 +92,26 @@ __device__ __forceinline__ float dot_row_warp(const float* __restrict__ w0, cons
     for (int base = 0; base < n4; base += 256) {
       float4 q[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = base + lane + 32 * k;
-        q[k] = i < n4 ? __ldg(p0 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      for (int k = 0; k < 8; ++k) q[k] = __ldg(p0 + min(base + lane + 32 * k, n4 - 1));
+      LOADS_ISSUED();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int i = base + lane + 32 * k;
-        if (i < n4) {
-          const float4 x = pv[i];
-          a = fmaf(q[k].x, x.x, fmaf(q[k].y, x.y, fmaf(q[k].z, x.z, fmaf(q[k].w, x.w, a))));
-        }
+        const float4 x = pv[min(i, n4 - 1)];
+        const float s = fmaf(q[k].x, x.x, fmaf(q[k].y, x.y, fmaf(q[k].z, x.z, q[k].w * x.w)));
+        a += i < n4 ? s : 0.f;
       }
     }
   } else {
     for (int base = 0; base < n; base += 256) {
       float q[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int i = base + lane + 32 * k;
-        q[k] = i < n ? __ldg(w0 + i) : 0.f;
-      }
+      for (int k = 0; k < 8; ++k) q[k] = __ldg(w0 + min(base + lane + 32 * k, n - 1));
+      LOADS_ISSUED();
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int i = base + lane + 32 * k;
-        if (i < n) a = fmaf(q[k], v[i], a);
+        a = fmaf(i < n ? q[k] : 0.f, v[min(i, n - 1)], a);
       }
     }
   }
@@ -116,29 +137,97 @@ __device__ __forceinline__ void gemv_rows(const Lin& L, const float* __restrict_
   }
 }
 
-// Narrow layer (in, out <= kMaxH), whole layer in one pass: kQ threads per neuron, thread p of a quad takes inputs p, p + 4, ...
-__device__ __forceinline__ void gemv_small(const Lin& L, const float* __restrict__ v, float* __restrict__ out, int kind, bool last,
-                                           float* __restrict__ save) {
-  const int j = threadIdx.x >> 2, p = threadIdx.x & 3;
-  float acc = 0.f;
-  if (j < L.out) {
-    const float* w = L.W + (int64_t)j * L.in;
-    float wr[kHK];
+// Narrow GEMV rows (in <= 32 * HL), coalesced: each warp takes RW consecutive rows, lanes run along the contiguous weight
+// row (row-per-thread-quad reads cost 8 L1 tag lookups per load instruction and made a 75 x 75 layer take 1.5 us); all
+// RW * HL loads of a lane are in flight at once, then RW interleaved shuffle reductions.  sums[r] = W[row_r, :] . v on EVERY
+// lane.  Rows past `nrows` redo the last row (branch-free, see dot_row_warp).
+template <int RW, int HL>
+__device__ __forceinline__ void warp_rows_dot(const float* __restrict__ W, int in, int row_first, int nrows,
+                                              const float* __restrict__ v, float (&sums)[RW]) {
+  const int lane = threadIdx.x & 31;
+  float w[RW][HL];
 #pragma unroll
-    for (int k = 0; k < kHK; ++k) {
-      const int i = p + kQ * k;
-      wr[k] = i < L.in ? __ldg(w + i) : 0.f;
-    }
+  for (int r = 0; r < RW; ++r) {
+    const float* wr = W + (int64_t)min(row_first + r, nrows - 1) * in;
 #pragma unroll
-    for (int k = 0; k < kHK; ++k) {
-      const int i = p + kQ * k;
-      if (i < L.in) acc = fmaf(wr[k], v[i], acc);
+    for (int k = 0; k < HL; ++k) w[r][k] = __ldg(wr + min(lane + 32 * k, in - 1));
+  }
+  LOADS_ISSUED();
+  float x[HL];
+#pragma unroll
+  for (int k = 0; k < HL; ++k) x[k] = lane + 32 * k < in ? v[lane + 32 * k] : 0.f;
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    float a = 0.f;
+#pragma unroll
+    for (int k = 0; k < HL; ++k) a = fmaf(w[r][k], x[k], a);
+    sums[r] = a;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) sums[r] += __shfl_xor_sync(0xffffffffu, sums[r], o);
+  }
+}
+
+// the same for two weight matrices sharing v (the shift / scale heads): both sets of loads in flight together
+template <int RW, int HL>
+__device__ __forceinline__ void warp_rows_dot2(const float* __restrict__ W1, const float* __restrict__ W2, int in, int row_first,
+                                               int nrows, const float* __restrict__ v, float (&s1)[RW], float (&s2)[RW]) {
+  const int lane = threadIdx.x & 31;
+  float w1[RW][HL], w2[RW][HL];
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    const int64_t ro = (int64_t)min(row_first + r, nrows - 1) * in;
+#pragma unroll
+    for (int k = 0; k < HL; ++k) {
+      const int i = min(lane + 32 * k, in - 1);
+      w1[r][k] = __ldg(W1 + ro + i);
+      w2[r][k] = __ldg(W2 + ro + i);
     }
   }
-  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-  if (j < L.out && p == 0) {
-    const float h = act_fwd(kind, last, acc + __ldg(L.b + j));
+  LOADS_ISSUED();
+  float x[HL];
+#pragma unroll
+  for (int k = 0; k < HL; ++k) x[k] = lane + 32 * k < in ? v[lane + 32 * k] : 0.f;
+#pragma unroll
+  for (int r = 0; r < RW; ++r) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < HL; ++k) { a = fmaf(w1[r][k], x[k], a); b = fmaf(w2[r][k], x[k], b); }
+    s1[r] = a;
+    s2[r] = b;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int r = 0; r < RW; ++r) {
+      s1[r] += __shfl_xor_sync(0xffffffffu, s1[r], o);
+      s2[r] += __shfl_xor_sync(0xffffffffu, s2[r], o);
+    }
+  }
+}
+
+// lane-indexed pick from a register array without dynamic indexing
+template <int RW>
+__device__ __forceinline__ float pick(const float (&a)[RW], int r) {
+  float m = a[0];
+#pragma unroll
+  for (int k = 1; k < RW; ++k) m = (r == k) ? a[k] : m;
+  return m;
+}
+
+// Narrow layer (in, out <= kMaxH), whole layer in one pass of the CTA's 16 warps: out[j] = act(b[j] + W[j,:] v)
+template <int HK>
+__device__ __forceinline__ void gemv_small(const Lin& L, const float* __restrict__ v, float* __restrict__ out, int kind, bool last,
+                                           float* __restrict__ save) {
+  constexpr int RW = (4 * HK + kWarps - 1) / kWarps, HL = (4 * HK + 31) / 32;     // rows per warp, loads per lane and row
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float sums[RW];
+  warp_rows_dot<RW, HL>(L.W, L.in, warp * RW, L.out, v, sums);
+  const int j = warp * RW + lane;
+  if (lane < RW && j < L.out) {
+    const float h = act_fwd(kind, last, pick<RW>(sums, lane) + __ldg(L.b + j));
     out[j] = h;
     if (save) save[j] = h;
   }
@@ -149,7 +238,8 @@ __device__ __forceinline__ void gemv_small(const Lin& L, const float* __restrict
 // are split across the cluster -- the first hidden layer by output neuron (results broadcast into every CTA's shared
 // memory through DSMEM), the shift / scale heads and the coupling by output dimension (each CTA broadcasts its slice
 // of the new z) -- with one cluster barrier after each.  The small hidden layers are recomputed by every CTA.
-__global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f, const float* __restrict__ z_in,
+template <int HK>
+__global__ void __launch_bounds__(kFlowThreads, 1) flow_fwd_kernel(const FlowDev f, const float* __restrict__ z_in,
                                                                 const float* __restrict__ masks, const Noise mask_noise,
                                                                 int64_t R, float* __restrict__ z_out,
                                                                 float* __restrict__ logdet, float* __restrict__ save) {
@@ -171,85 +261,83 @@ __global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f,
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int per = (D + C - 1) / C, d0 = c * per, d1 = min(D, d0 + per);    // this CTA's slice of the output dims
   for (int d = tid; d < D; d += kFlowThreads) zs[d] = z_in[r * D + d];
+  FLOW_STAMP(0);
   cl.sync();                   // every CTA of the cluster is running before any remote shared-memory access
+  FLOW_STAMP(1);
   float ld_total = 0.f;
   for (int t = 0; t < f.n_transforms; ++t) {
     float* sv = save ? save + ((int64_t)r * f.n_transforms + t) * f.save_stride : nullptr;
-    for (int d = tid; d < D; d += kFlowThreads) {
-      const float m = mask_of(masks, nz, t, r, R, d, D);
-      ms[d] = m;
-      xm[d] = m * zs[d];
-      if (sv && d >= d0 && d < d1) sv[d] = zs[d];
+    for (int q = tid; 4 * q < D; q += kFlowThreads) {
+      float m4[4];
+      mask_quad(masks, nz, t, r, R, q, D, m4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = 4 * q + k;
+        if (d < D) {
+          ms[d] = m4[k];
+          xm[d] = m4[k] * zs[d];
+          if (sv && d >= d0 && d < d1) sv[d] = zs[d];
+        }
+      }
     }
     __syncthreads();
+    FLOW_STAMP(2 + 8 * t);
     float* svh = sv ? sv + 3 * D : nullptr;
     // first hidden layer: neurons c, c + C, ... of this CTA, broadcast to the whole cluster
     gemv_rows(f.hidden[t][0], xm, ha, f.kind, f.n_hidden == 1, svh, c, C, cl, C);
+    FLOW_STAMP(3 + 8 * t);
     cl.sync();
+    FLOW_STAMP(4 + 8 * t);
     const float* v = ha;
     float* cur = hb;
     if (svh) svh += f.hidden[t][0].out;
     for (int l = 1; l < f.n_hidden; ++l) {
-      gemv_small(f.hidden[t][l], v, cur, f.kind, l == f.n_hidden - 1, c == 0 ? svh : nullptr);
+      gemv_small<HK>(f.hidden[t][l], v, cur, f.kind, l == f.n_hidden - 1, c == 0 ? svh : nullptr);
       if (svh) svh += f.hidden[t][l].out;
       __syncthreads();
       v = cur;
       cur = (cur == ha) ? hb : ha;
     }
-    // shift / scale heads and the coupling for the dims of this CTA's slice: kQ threads per dim, each with its quarter of
-    // both weight rows in flight at once
+    FLOW_STAMP(5 + 8 * t);
+    // shift / scale heads and the coupling for the dims of this CTA's slice: each warp takes 8 consecutive dims per pass
+    // (coalesced weight rows, all loads of both heads in flight), lane (r, q) then owns dim r and the remote stores to
+    // CTAs q, q + 4
     const Lin& Ls = f.shift[t];
     const Lin& Lc = f.scale[t];
     const int H = Ls.in;
     float ld = 0.f;
-    const int p = tid & 3;
-    for (int base = d0; base < d1; base += kGroup) {
-      const int d = base + (tid >> 2);
-      const bool ok = d < d1;
-      float a1 = 0.f, a2 = 0.f;
-      if (ok) {
-        const float* ws = Ls.W + (int64_t)d * H;
-        const float* wc = Lc.W + (int64_t)d * H;
-        float w1[kHK], w2[kHK];
-#pragma unroll
-        for (int k = 0; k < kHK; ++k) {
-          const int i = p + kQ * k;
-          w1[k] = i < H ? __ldg(ws + i) : 0.f;
-          w2[k] = i < H ? __ldg(wc + i) : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < kHK; ++k) {
-          const int i = p + kQ * k;
-          if (i < H) {
-            const float vi = v[i];
-            a1 = fmaf(w1[k], vi, a1);
-            a2 = fmaf(w2[k], vi, a2);
+    {
+      constexpr int RW = 8, HL = (4 * HK + 31) / 32;
+      const int r_ = lane & 7, q_ = lane >> 3;
+      for (int base = d0; base < d1; base += kWarps * RW) {
+        float s1[RW], s2[RW];
+        const int first = base + warp * RW;
+        warp_rows_dot2<RW, HL>(Ls.W, Lc.W, H, first, d1, v, s1, s2);
+        const int d = first + r_;
+        const bool ok = d < d1;
+        float x = 0.f;
+        if (ok) {
+          const float sh = pick<RW>(s1, r_) + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-(pick<RW>(s2, r_) + __ldg(Lc.b + d))));
+          const float z = zs[d], m = ms[d];
+          if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
+          else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
+          if (q_ == 0) {
+            ld += (1.0f - m) * logf(g);
+            if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
           }
         }
+        __syncwarp();      // every lane has read zs[d] before one of them overwrites it (own CTA included)
+        // the new z of this dim into every CTA; no CTA reads another's dims in this phase
+        if (ok)
+          for (int k = q_; k < C; k += 4) cl.map_shared_rank(zs, k)[d] = x;
       }
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, 2);
-      float x = 0.f;
-      if (ok) {
-        const float sh = a1 + __ldg(Ls.b + d), g = 1.0f / (1.0f + expf(-(a2 + __ldg(Lc.b + d))));
-        const float z = zs[d], m = ms[d];
-        if (f.kind == LBBNN_FLOW_RNVP) x = (1.0f - m) * z * g + (1.0f - g) * sh + m * z;       // flows2:215
-        else x = m * z + (1.0f - m) * (z * g + (1.0f - g) * sh);                               // flows2:238
-        if (p == 0) {
-          ld += (1.0f - m) * logf(g);
-          if (sv) { sv[D + d] = g; sv[2 * D + d] = sh; }
-        }
-      }
-      __syncwarp();      // every thread of the quad has read zs[d] before one of them overwrites it (own CTA included)
-      // the new z of this dim into every CTA (the quad shares the remote stores); no CTA reads another's dims in this phase
-      if (ok)
-        for (int k = p; k < C; k += kQ) cl.map_shared_rank(zs, k)[d] = x;
     }
+    FLOW_STAMP(6 + 8 * t);
     const float tot = block_sum(ld, red);
     if (tid == 0) cl.map_shared_rank(ldp, 0)[c] = tot;
+    FLOW_STAMP(7 + 8 * t);
     cl.sync();
+    FLOW_STAMP(8 + 8 * t);
     if (c == 0 && tid == 0)
       for (int k = 0; k < C; ++k) ld_total += ldp[k];             // fixed order
   }
@@ -263,7 +351,8 @@ __global__ void __launch_bounds__(kFlowThreads) flow_fwd_kernel(const FlowDev f,
 // the (H,) gradient wrt the conditioner output, whose contraction over D is split across the cluster.  Parameter
 // gradients: heads by dim slice, hidden layers by output row (row j belongs to CTA j mod C), into the row's slice of
 // the (rows, n_params) buffer with plain stores.
-__global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f, const float* __restrict__ masks,
+template <int HK>
+__global__ void __launch_bounds__(kFlowThreads, 1) flow_bwd_kernel(const FlowDev f, const float* __restrict__ masks,
                                                                 const Noise mask_noise, int64_t R,
                                                                 const float* __restrict__ dz_out,
                                                                 const float* __restrict__ dlogdet,
@@ -293,7 +382,9 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
   const int gi = tid & (kMaxH - 1), gp = tid >> 7;      // narrow transposed GEMVs: output index, quarter of the reduction
   static_assert(kFlowThreads == kQ * kMaxH, "thread = (output, quarter)");
   for (int d = d0 + tid; d < d1; d += kFlowThreads) dz[d] = dz_out ? dz_out[r * D + d] : 0.f;
+  FLOW_STAMP(64);
   cl.sync();
+  FLOW_STAMP(65);
   for (int t = f.n_transforms - 1; t >= 0; --t) {
     const float* sv = save + ((int64_t)r * f.n_transforms + t) * f.save_stride;
     const float* zin = sv;
@@ -315,60 +406,69 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
     const float* y = hall + (f.n_hidden - 1) * kMaxH;   // output of the conditioner net
     // masks and conditioner input for all dims (the first layer's weight gradient needs them); coupling backward for
     // the dims of this CTA's slice
-    for (int d = tid; d < D; d += kFlowThreads) {
-      const float m = mask_of(masks, nz, t, r, R, d, D);
-      const float z = zin[d];
-      ms[d] = m;
-      xm[d] = m * z;
-      if (d >= d0 && d < d1) {
-        const float g = gate[d], sh = shf[d], dx = dz[d];
-        float dg, ds;
-        if (f.kind == LBBNN_FLOW_RNVP) {
-          dg = dx * ((1.0f - m) * z - sh) + dld * (1.0f - m) / g;
-          ds = dx * (1.0f - g);
-        } else {
-          dg = dx * (1.0f - m) * (z - sh) + dld * (1.0f - m) / g;
-          ds = dx * (1.0f - m) * (1.0f - g);
+    for (int q = tid; 4 * q < D; q += kFlowThreads) {
+      float m4[4];
+      mask_quad(masks, nz, t, r, R, q, D, m4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int d = 4 * q + k;
+        if (d >= D) continue;
+        const float m = m4[k];
+        const float z = zin[d];
+        ms[d] = m;
+        xm[d] = m * z;
+        if (d >= d0 && d < d1) {
+          const float g = gate[d], sh = shf[d], dx = dz[d];
+          float dg, ds;
+          if (f.kind == LBBNN_FLOW_RNVP) {
+            dg = dx * ((1.0f - m) * z - sh) + dld * (1.0f - m) / g;
+            ds = dx * (1.0f - g);
+          } else {
+            dg = dx * (1.0f - m) * (z - sh) + dld * (1.0f - m) / g;
+            ds = dx * (1.0f - m) * (1.0f - g);
+          }
+          const float dc = dg * g * (1.0f - g);
+          dsh[d] = ds;
+          dsc[d] = dc;
+          dz[d] = dx * ((1.0f - m) * g + m);     // direct path; the path through the conditioner is added below
+          Ls.db[goff + d] = ds;
+          Lc.db[goff + d] = dc;
         }
-        const float dc = dg * g * (1.0f - g);
-        dsh[d] = ds;
-        dsc[d] = dc;
-        dz[d] = dx * ((1.0f - m) * g + m);     // direct path; the path through the conditioner is added below
-        Ls.db[goff + d] = ds;
-        Lc.db[goff + d] = dc;
       }
     }
     __syncthreads();
+    FLOW_STAMP(66 + 16 * t);
     // head weight gradients: the outer products dsh x y, dsc x y of this CTA's dims, one flat coalesced sweep
-    {
-      const int n = (d1 - d0) * H;
-      float* ps = Ls.dW + goff + (int64_t)d0 * H;
-      float* pc = Lc.dW + goff + (int64_t)d0 * H;
-      for (int idx = tid; idx < n; idx += kFlowThreads) {
-        const int dl = idx / H, i = idx - dl * H;
-        const float yi = y[i];
-        ps[idx] = dsh[d0 + dl] * yi;
-        pc[idx] = dsc[d0 + dl] * yi;
+    if (gi < H) {
+      const float yi = y[gi];
+      float* ps = Ls.dW + goff + gi;
+      float* pc = Lc.dW + goff + gi;
+#pragma unroll 4
+      for (int d = d0 + gp; d < d1; d += kQ) {
+        ps[(int64_t)d * H] = dsh[d] * yi;
+        pc[(int64_t)d * H] = dsc[d] * yi;
       }
     }
+    FLOW_STAMP(67 + 16 * t);
     // partial of dy[i] = sum_d Wt[d,i] dsh[d] + Ws[d,i] dsc[d] over this CTA's dims: thread (i, quarter of the dims),
     // consecutive threads read consecutive i (coalesced rows), 16 dims = 32 loads in flight per thread
     {
       float acc = 0.f;
-      if (gi < H) {
-        for (int base = d0 + gp; base < d1; base += kQ * 16) {
-          float w1[16], w2[16];
+      const int ic = min(gi, H - 1);
+      for (int base = d0 + gp; base < d1; base += kQ * 16) {
+        float w1[16], w2[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int d = base + kQ * k;
-            w1[k] = d < d1 ? __ldg(Ls.W + (int64_t)d * H + gi) : 0.f;
-            w2[k] = d < d1 ? __ldg(Lc.W + (int64_t)d * H + gi) : 0.f;
-          }
+        for (int k = 0; k < 16; ++k) {
+          const int d = min(base + kQ * k, d1 - 1);
+          w1[k] = __ldg(Ls.W + (int64_t)d * H + ic);
+          w2[k] = __ldg(Lc.W + (int64_t)d * H + ic);
+        }
+        LOADS_ISSUED();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int d = base + kQ * k;
-            if (d < d1) acc = fmaf(w1[k], dsh[d], fmaf(w2[k], dsc[d], acc));
-          }
+        for (int k = 0; k < 16; ++k) {
+          const int d = base + kQ * k, dc = min(d, d1 - 1);
+          const float t_ = fmaf(w1[k], dsh[dc], w2[k] * dsc[dc]);
+          acc += d < d1 ? t_ : 0.f;
         }
       }
       part[gp * kMaxH + gi] = acc;
@@ -378,7 +478,9 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
       const float s = (part[i] + part[kMaxH + i]) + (part[2 * kMaxH + i] + part[3 * kMaxH + i]);
       for (int k = 0; k < C; ++k) cl.map_shared_rank(dyp, k)[c * kMaxH + i] = s;   // this CTA's partial, into every CTA
     }
+    FLOW_STAMP(68 + 16 * t);
     cl.sync();
+    FLOW_STAMP(69 + 16 * t);
     for (int i = tid; i < H; i += kFlowThreads) {
       float s = 0.f;
       for (int k = 0; k < C; ++k) s += dyp[k * kMaxH + i];                          // fixed order
@@ -396,6 +498,7 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
         if (c == 0) L.db[goff + j] = g;
       }
       __syncthreads();
+      FLOW_STAMP(70 + 16 * t + 3 * (f.n_hidden - 1 - l));
       // weight-gradient rows j = c (mod C): outer product da[j] x vin, one flat coalesced sweep over (own rows) x in
       {
         const int rows = c < L.out ? (L.out - c + C - 1) / C : 0;
@@ -406,23 +509,22 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
           L.dW[goff + (int64_t)j * L.in + i] = da[j] * vin[i];
         }
       }
+      FLOW_STAMP(71 + 16 * t + 3 * (f.n_hidden - 1 - l));
       // gradient wrt the layer input: dv[i] = sum_j W[j,i] da[j]; thread (i, quarter of j): consecutive threads read
       // consecutive i of a weight row, all of a thread's loads in flight at once
       if (l == 0) {
         for (int base = d0; base < d1; base += kMaxH) {                    // only this CTA's dims
-          const int i = base + gi;
+          const int i = min(base + gi, d1 - 1);
           float acc = 0.f;
-          if (i < d1) {
-            float wr[kHK];
+          {
+            float wr[HK];
 #pragma unroll
-            for (int k = 0; k < kHK; ++k) {
-              const int j = gp + kQ * k;
-              wr[k] = j < L.out ? __ldg(L.W + (int64_t)j * L.in + i) : 0.f;
-            }
+            for (int k = 0; k < HK; ++k) wr[k] = __ldg(L.W + (int64_t)min(gp + kQ * k, L.out - 1) * L.in + i);
+            LOADS_ISSUED();
 #pragma unroll
-            for (int k = 0; k < kHK; ++k) {
+            for (int k = 0; k < HK; ++k) {
               const int j = gp + kQ * k;
-              if (j < L.out) acc = fmaf(wr[k], da[j], acc);
+              acc = fmaf(j < L.out ? wr[k] : 0.f, da[min(j, L.out - 1)], acc);
             }
           }
           part[gp * kMaxH + gi] = acc;
@@ -435,17 +537,16 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
         }
       } else {
         float acc = 0.f;
-        if (gi < L.in) {
-          float wr[kHK];
+        {
+          const int ic = min(gi, L.in - 1);
+          float wr[HK];
 #pragma unroll
-          for (int k = 0; k < kHK; ++k) {
-            const int j = gp + kQ * k;
-            wr[k] = j < L.out ? __ldg(L.W + (int64_t)j * L.in + gi) : 0.f;
-          }
+          for (int k = 0; k < HK; ++k) wr[k] = __ldg(L.W + (int64_t)min(gp + kQ * k, L.out - 1) * L.in + ic);
+          LOADS_ISSUED();
 #pragma unroll
-          for (int k = 0; k < kHK; ++k) {
+          for (int k = 0; k < HK; ++k) {
             const int j = gp + kQ * k;
-            if (j < L.out) acc = fmaf(wr[k], da[j], acc);
+            acc = fmaf(j < L.out ? wr[k] : 0.f, da[min(j, L.out - 1)], acc);
           }
         }
         part[gp * kMaxH + gi] = acc;
@@ -455,9 +556,18 @@ __global__ void __launch_bounds__(kFlowThreads) flow_bwd_kernel(const FlowDev f,
         __syncthreads();
       }
     }
+    FLOW_STAMP(82 + 16 * t);
     cl.sync();     // nobody writes the next transform's partials into a CTA that is still summing this one's
   }
   for (int d = d0 + tid; d < d1; d += kFlowThreads) dz_in[r * D + d] = dz[d];
+}
+
+// widest hidden layer of the conditioner nets (selects the HK instantiation)
+int max_hidden(const FlowDev& d) {
+  int h = 0;
+  for (int t = 0; t < d.n_transforms; ++t)
+    for (int l = 0; l < d.n_hidden; ++l) h = d.hidden[t][l].out > h ? d.hidden[t][l].out : h;
+  return h;
 }
 
 // cluster width for a flow of dimension D: enough dims per CTA to keep its warps busy
@@ -537,8 +647,10 @@ extern "C" int lbbnn_flow_fwd(const lbbnn_flow* F, const float* z_in, int64_t ro
   LBBNN_REQUIRE(z_in && z_out && logdet && rows > 0, "NULL argument");
   LBBNN_REQUIRE(rows < (1 << 20), "too many rows");
   const size_t smem = (size_t)(3 * ((d.dim + 3) & ~3) + 2 * kMaxH + kMaxCluster) * sizeof(float);
-  if (smem > 48 * 1024) LBBNN_CUDA(cudaFuncSetAttribute(flow_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (int rc = launch_cluster(flow_fwd_kernel, (int)rows, cluster_for(d.dim), smem, (cudaStream_t)s, (const FlowDev)d, z_in, masks,
+  const bool narrow = max_hidden(d) <= 4 * 20;
+  auto kernel = narrow ? flow_fwd_kernel<20> : flow_fwd_kernel<kMaxH / kQ>;
+  if (smem > 48 * 1024) LBBNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = launch_cluster(kernel, (int)rows, cluster_for(d.dim), smem, (cudaStream_t)s, (const FlowDev)d, z_in, masks,
                               (const Noise)make_noise(mask_u), rows, z_out, logdet, save))
     return rc;
   return check_launch("flow_fwd");
@@ -553,8 +665,10 @@ extern "C" int lbbnn_flow_bwd(const lbbnn_flow* F, const lbbnn_flow_grads* G, in
   LBBNN_REQUIRE(save && dz_in && rows > 0, "NULL argument");
   LBBNN_REQUIRE(rows < (1 << 20), "too many rows");
   const size_t smem = (size_t)(5 * ((d.dim + 3) & ~3) + 2 * kMaxH + kQ * kMaxH + kMaxCluster * kMaxH + LBBNN_FLOW_MAX_HIDDEN * kMaxH) * sizeof(float);
-  if (smem > 48 * 1024) LBBNN_CUDA(cudaFuncSetAttribute(flow_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (int rc = launch_cluster(flow_bwd_kernel, (int)rows, cluster_for(d.dim), smem, (cudaStream_t)s, (const FlowDev)d, masks,
+  const bool narrow = max_hidden(d) <= 4 * 20;
+  auto kernel = narrow ? flow_bwd_kernel<20> : flow_bwd_kernel<kMaxH / kQ>;
+  if (smem > 48 * 1024) LBBNN_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (int rc = launch_cluster(kernel, (int)rows, cluster_for(d.dim), smem, (cudaStream_t)s, (const FlowDev)d, masks,
                               (const Noise)make_noise(mask_u), rows, dz_out, dlogdet, save, dz_in))
     return rc;
   return check_launch("flow_bwd");

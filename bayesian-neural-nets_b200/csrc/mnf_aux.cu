@@ -35,10 +35,23 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_fwd_kernel(const lbbnn_mnf_a
     const float* m = a.M0 + (int64_t)j * D;
     const float* v = a.V + (int64_t)j * D;
     float d1 = 0.f, d2 = 0.f;
-    for (int i = lane; i < D; i += 32) {
-      const float c = __ldg(a.r0_c + i);
-      d1 = fmaf(c * __ldg(a.z2 + i), __ldg(m + i), d1);
-      d2 = fmaf(c * c, __ldg(v + i), d2);
+    for (int base = 0; base < D; base += 256) {      // 8 independent (M0, V) load pairs in flight per lane
+      float mv[8], vv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        mv[k] = i < D ? __ldg(m + i) : 0.f;
+        vv[k] = i < D ? __ldg(v + i) : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int i = base + lane + 32 * k;
+        if (i < D) {
+          const float c = __ldg(a.r0_c + i);
+          d1 = fmaf(c * __ldg(a.z2 + i), mv[k], d1);
+          d2 = fmaf(c * c, vv[k], d2);
+        }
+      }
     }
     d1 = warp_sum(d1);
     d2 = warp_sum(d2);
@@ -109,16 +122,31 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
   const float c = ok ? __ldg(a.r0_c + i) : 0.f, z2 = ok ? __ldg(a.z2 + i) : 0.f;
   const float cz = c * z2, cc = c * c;
   float p = 0.f, q = 0.f;
-  for (int j = ty; j < O; j += 8) {
-    const float ar = __ldg(save + j), av = __ldg(save + O + j);
-    const float dpre = (1.0f - ar * ar) * d_ar;
-    const float dvar = dpre * __ldg(a.eps_r + j) * (0.5f / sqrtf(av));
-    if (ok) {
-      const int64_t e = (int64_t)j * D + i;
-      p = fmaf(dpre, __ldg(a.M0 + e), p);
-      q = fmaf(dvar, __ldg(a.V + e), q);
-      g.dM0[e] = dpre * cz;
-      g.dV[e] = dvar * cc;
+  for (int j0 = ty; j0 < O; j0 += 8 * 8) {      // 8 rows = 16 independent loads in flight per thread
+    float mv[8], vv[8], dpre[8], dvar[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = j0 + 8 * k;
+      const bool okj = ok && j < O;
+      mv[k] = okj ? __ldg(a.M0 + (int64_t)j * D + i) : 0.f;
+      vv[k] = okj ? __ldg(a.V + (int64_t)j * D + i) : 0.f;
+      dpre[k] = dvar[k] = 0.f;
+      if (j < O) {
+        const float ar = __ldg(save + j), av = __ldg(save + O + j);
+        dpre[k] = (1.0f - ar * ar) * d_ar;
+        dvar[k] = dpre[k] * __ldg(a.eps_r + j) * (0.5f / sqrtf(av));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = j0 + 8 * k;
+      if (ok && j < O) {
+        const int64_t e = (int64_t)j * D + i;
+        p = fmaf(dpre[k], mv[k], p);
+        q = fmaf(dvar[k], vv[k], q);
+        g.dM0[e] = dpre[k] * cz;
+        g.dV[e] = dvar[k] * cc;
+      }
     }
   }
   ps[ty][tx] = p;
@@ -138,6 +166,67 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
     g.d_r0_c[i] = p * z2 + 2.0f * c * q;
     g.d_z2[i] = p * c;
     g.d_z_b[i] = (i == D - 1) ? bc[1] : 0.f;
+  }
+}
+
+// ---- the glue of one layer call, fused (each of these replaces 3-8 elementwise launches of the eager formulation) --------------
+// z0[r,i] = q0_mean[i] + sqrt(exp(q0_log_var[i])) eps[r,i]   (MNF:183-185), eps injected or Philox; + the eps_r draw (out,)
+__global__ void __launch_bounds__(kThreads) mnf_draw_kernel(const float* __restrict__ q0_mean, const float* __restrict__ q0_log_var,
+                                                            Noise nz, int R, int D, float* __restrict__ eps_out,
+                                                            float* __restrict__ z0, Noise nzr, int O, float* __restrict__ eps_r) {
+  nz.resolve();
+  nzr.resolve();
+  const int n = R * D;
+  for (int idx = blockIdx.x * kThreads + threadIdx.x; idx < n + O; idx += gridDim.x * kThreads) {
+    if (idx < n) {
+      const int i = idx % D;
+      const float e = nz.ptr ? __ldg(nz.ptr + idx) : philox_normal1(nz.seed, nz.stream, (uint64_t)idx);
+      eps_out[idx] = e;
+      z0[idx] = __ldg(q0_mean + i) + sqrtf(expf(__ldg(q0_log_var + i))) * e;
+    } else if (eps_r) {
+      const int j = idx - n;
+      eps_r[j] = nzr.ptr ? __ldg(nzr.ptr + j) : philox_normal1(nzr.seed, nzr.stream, (uint64_t)j);
+    }
+  }
+}
+
+// gradients of q0_mean / q0_log_var: through z0 (all rows) + the auxiliary term's direct ones; the auxiliary term also reads
+// z0's KL row directly (d_z0_aux)
+__global__ void __launch_bounds__(kThreads) mnf_draw_bwd_kernel(const float* __restrict__ q0_log_var, const float* __restrict__ eps,
+                                                                const float* __restrict__ dz0, int R, int D, int kl_row,
+                                                                const float* __restrict__ aux_dmean, const float* __restrict__ aux_dlv,
+                                                                const float* __restrict__ aux_dz0, float* __restrict__ d_mean,
+                                                                float* __restrict__ d_lv) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (i >= D) return;
+  float dm = 0.f, de = 0.f;
+  for (int r = 0; r < R; ++r) {
+    float g = dz0[(int64_t)r * D + i];
+    if (r == kl_row && aux_dz0) g += aux_dz0[i];
+    dm += g;
+    de = fmaf(g, eps[(int64_t)r * D + i], de);
+  }
+  const float sd = sqrtf(expf(__ldg(q0_log_var + i)));
+  d_mean[i] = dm + (aux_dmean ? aux_dmean[i] : 0.f);
+  d_lv[i] = 0.5f * sd * de + (aux_dlv ? aux_dlv[i] : 0.f);
+}
+
+// kl = kl_wb + (log_q0 - log_rb) - log_det_q - log_det_r   (MNF:235)
+__global__ void mnf_kl_combine_kernel(const float* kl_wb, const float* aux, const float* ldq, const float* ldr, float* out) {
+  out[0] = (kl_wb[0] + aux[0]) - ldq[0] - ldr[0];
+}
+
+// backward staging: dld = [0, -g] (log-det gradients of the activation row / the KL row; dld + 1 serves the r flow),
+// and -- second form -- the z-flow's output gradient rows: row 0 = d z_k (activation path), row 1 = a + b (the KL row's
+// direct terms; the weight KL's share is accumulated on top by lbbnn_lrt_f32_finalize)
+__global__ void __launch_bounds__(kThreads) mnf_bwd_rows_kernel(const float* __restrict__ g, float* __restrict__ dld,
+                                                                const float* __restrict__ dz_k, const float* __restrict__ a,
+                                                                const float* __restrict__ b, int D, float* __restrict__ rows) {
+  const int i = blockIdx.x * kThreads + threadIdx.x;
+  if (dld && i < 2) dld[i] = i == 0 ? 0.f : -__ldg(g);
+  if (rows && i < D) {
+    rows[i] = dz_k ? dz_k[i] : 0.f;
+    rows[D + i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
   }
 }
 
@@ -172,4 +261,43 @@ extern "C" int lbbnn_mnf_aux_kl_bwd(const lbbnn_mnf_aux* aux, const float* save,
   const unsigned blocks = (unsigned)ceil_div(aux->in_features, 32);
   mnf_aux_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(*aux, save, gout, *grads);
   return check_launch("mnf_aux_bwd");
+}
+
+extern "C" int lbbnn_mnf_draw(const float* q0_mean, const float* q0_log_var, const lbbnn_noise* eps_z, int64_t rows,
+                              int64_t in_features, float* eps_out, float* z0, const lbbnn_noise* eps_r_noise,
+                              int64_t out_features, float* eps_r, lbbnn_stream s) {
+  LBBNN_REQUIRE(q0_mean && q0_log_var && eps_z && eps_out && z0 && rows > 0 && in_features > 0, "bad argument");
+  LBBNN_REQUIRE(rows * in_features < (1LL << 30) && out_features < (1LL << 30), "too large");
+  LBBNN_REQUIRE(eps_r == nullptr || (eps_r_noise && out_features > 0), "eps_r needs its noise source");
+  const int64_t n = rows * in_features + (eps_r ? out_features : 0);
+  mnf_draw_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)s>>>(
+      q0_mean, q0_log_var, make_noise(eps_z), (int)rows, (int)in_features, eps_out, z0, make_noise(eps_r_noise),
+      eps_r ? (int)out_features : 0, eps_r);
+  return check_launch("mnf_draw");
+}
+
+extern "C" int lbbnn_mnf_draw_bwd(const float* q0_log_var, const float* eps, const float* dz0, int64_t rows, int64_t in_features,
+                                  int kl_row, const float* aux_d_q0_mean, const float* aux_d_q0_log_var, const float* aux_d_z0,
+                                  float* d_q0_mean, float* d_q0_log_var, lbbnn_stream s) {
+  LBBNN_REQUIRE(q0_log_var && eps && dz0 && d_q0_mean && d_q0_log_var && rows > 0 && in_features > 0, "bad argument");
+  LBBNN_REQUIRE(kl_row < rows, "kl_row out of range");
+  mnf_draw_bwd_kernel<<<(unsigned)ceil_div(in_features, kThreads), kThreads, 0, (cudaStream_t)s>>>(
+      q0_log_var, eps, dz0, (int)rows, (int)in_features, kl_row, aux_d_q0_mean, aux_d_q0_log_var, aux_d_z0, d_q0_mean, d_q0_log_var);
+  return check_launch("mnf_draw_bwd");
+}
+
+extern "C" int lbbnn_mnf_kl_combine(const float* kl_wb, const float* aux_out, const float* log_det_q, const float* log_det_r,
+                                    float* kl_out, lbbnn_stream s) {
+  LBBNN_REQUIRE(kl_wb && aux_out && log_det_q && log_det_r && kl_out, "NULL argument");
+  mnf_kl_combine_kernel<<<1, 1, 0, (cudaStream_t)s>>>(kl_wb, aux_out, log_det_q, log_det_r, kl_out);
+  return check_launch("mnf_kl_combine");
+}
+
+extern "C" int lbbnn_mnf_bwd_rows(const float* g, float* dld2, const float* dz_k, const float* a, const float* b,
+                                  int64_t in_features, float* rows2, lbbnn_stream s) {
+  LBBNN_REQUIRE((dld2 && g) || rows2, "nothing to do");
+  LBBNN_REQUIRE(rows2 == nullptr || in_features > 0, "bad shape");
+  const int64_t n = rows2 ? (in_features > 2 ? in_features : 2) : 2;
+  mnf_bwd_rows_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)s>>>(g, dld2, dz_k, a, b, (int)in_features, rows2);
+  return check_launch("mnf_bwd_rows");
 }

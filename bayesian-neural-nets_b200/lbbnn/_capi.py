@@ -198,6 +198,10 @@ SIGNATURES = {
     "lbbnn_mnf_aux_save_floats": (_SZ, [_I64]),
     "lbbnn_mnf_aux_kl_fwd": (_INT, [C.POINTER(MnfAux), _P, _P, _P, _P]),
     "lbbnn_mnf_aux_kl_bwd": (_INT, [C.POINTER(MnfAux), _P, _P, C.POINTER(MnfAuxGrads), _P]),
+    "lbbnn_mnf_draw": (_INT, [_P, _P, C.POINTER(Noise), _I64, _I64, _P, _P, C.POINTER(Noise), _I64, _P, _P]),
+    "lbbnn_mnf_draw_bwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "lbbnn_mnf_kl_combine": (_INT, [_P, _P, _P, _P, _P, _P]),
+    "lbbnn_mnf_bwd_rows": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _P]),
     "lbbnn_lrt_step_workspace_bytes": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_raw_floats": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_f32": (_INT, [C.POINTER(Step), _INT, _P, _SZ, _P]),

@@ -139,6 +139,12 @@ class PropagateFlow(nn.Module):
                 out += [m.weight, m.bias]
         return out
 
+    def _next_key(self):
+        """Philox (seed, stream) of the next evaluation's native masks (transform t draws from stream + t)."""
+        self._calls += 1
+        self.last_noise_key = (current_seed(), (self._uid << 44) | (self._calls << 8))
+        return self.last_noise_key
+
     def forward(self, z, masks=None, per_row=False):
         """z: (B, dim) or (dim,).  masks: optional injected list/tensor of {0,1} masks, one per transform, each
         shaped like z.  Returns (z_out, logdet) with the reference's shapes: logdet (B,) / scalar for RNVP, a
@@ -149,9 +155,7 @@ class PropagateFlow(nn.Module):
         z2 = z.reshape(1, -1) if one_d else z
         if masks is not None:
             masks = torch.stack([m.reshape(z2.shape) for m in masks]) if not torch.is_tensor(masks) else masks.reshape(-1, *z2.shape)
-        self._calls += 1
-        self.last_noise_key = (current_seed(), (self._uid << 44) | (self._calls << 8))
-        zo, ld = _FlowFunction.apply(z2, masks, self.kind, self.n_hidden, self.last_noise_key, *self._params())
+        zo, ld = _FlowFunction.apply(z2, masks, self.kind, self.n_hidden, self._next_key(), *self._params())
         if per_row:
             return (zo[0], ld[0]) if one_d else (zo, ld)
         if self.kind == K.FLOW_IAF:

@@ -18,7 +18,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _capi as K
-from .flows import PropagateFlow
+from .flows import PropagateFlow, _build_flow
 from .lrt import BernoulliView, GaussianView, LayerConfig, _LRTFunction, current_seed, _layer_ids
 
 
@@ -92,6 +92,198 @@ class _AuxKL(torch.autograd.Function):
         return v[0], v[1], v[2], v[3], v[4], v[5], v[6], dM0, dV, None, v[7], None
 
 
+_N_LAYER_PARAMS = 10      # weight_mu, weight_rho, lambdal, bias_mu, bias_rho, q0_mean, q0_log_var, r0_c, r0_b1, r0_b2
+_zero_colsums = {}
+
+
+def _zeros_const(n, dev):
+    """A never-written zero buffer (the weight-KL finalize's `colsum` input: the KL branch has no activation gradient)."""
+    key = (dev.index, n)
+    t = _zero_colsums.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise K.LbbnnError("constant buffer would be created during CUDA-graph capture; run one eager step first")
+        t = torch.zeros(n, dtype=torch.float32, device=dev)
+        _zero_colsums[key] = t
+    return t
+
+
+def _flow_grad_table(flow, params, gbuf):
+    """lbbnn_flow_grads over a (rows, P) buffer laid out like `params` (PropagateFlow._params() order); returns it with
+    the per-parameter offsets."""
+    sizes = [p.numel() for p in params]
+    offs = [0]
+    for n in sizes:
+        offs.append(offs[-1] + n)
+    grads = K.FlowGrads()
+    grads.row_stride = gbuf.shape[1]
+    base = gbuf.data_ptr()
+    i = 0
+    for t in range(flow.n_transforms):
+        for l in range(flow.n_hidden):
+            grads.t[t].hidden[l].dW, grads.t[t].hidden[l].db = base + 4 * offs[i], base + 4 * offs[i + 1]
+            i += 2
+        grads.t[t].shift.dW, grads.t[t].shift.db = base + 4 * offs[i], base + 4 * offs[i + 1]
+        grads.t[t].scale.dW, grads.t[t].scale.db = base + 4 * offs[i + 2], base + 4 * offs[i + 3]
+        i += 4
+    return grads, offs
+
+
+class _Prepare(torch.autograd.Function):
+    """Everything of an MNF layer call that does not depend on the input batch, as ONE autograd node (MNF:183-194 for the
+    activation row and the whole KL branch MNF:208-235): the z0 draw, the z flow on [activation row, KL row], the weight
+    moments + weight/bias KL with the KL row's z, the auxiliary r flow, log q0 - log r_b, and the combination into the
+    layer's kl.  Forward = 6 launches, backward = 9 (eager formulation with one autograd node per piece: ~45 per layer,
+    most of them elementwise glue and gradient accumulation).  Returns (z_k, kl, z0 row the reference leaves in self.z)."""
+
+    @staticmethod
+    def forward(ctx, meta, *params):
+        K.require_device()
+        layer, want_kl, nz = meta
+        ps = [p.contiguous() for p in params]
+        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2 = ps[:_N_LAYER_PARAMS]
+        nzp = len(layer.z_flow._params())
+        zp, rp = ps[_N_LAYER_PARAMS:_N_LAYER_PARAMS + nzp], ps[_N_LAYER_PARAMS + nzp:]
+        dev, D, O = wmu.device, layer.in_features, layer.out_features
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = K.current_stream()
+        R = 2 if want_kl else 1
+        inj = "eps_z" in nz
+        # ---- z0 rows [activation row (the last batch row's draw, SURVEY quirk #4), KL row] + eps_r
+        layer._prep_calls += 1
+        skey = (layer._uid << 40) | (1 << 39) | (layer._prep_calls << 2)
+        if inj:
+            eps_rows = torch.cat([nz["eps_z"][-1:], nz["eps_z2"]], 0) if want_kl else nz["eps_z"][-1:].contiguous()
+            noise_z = K.make_noise(eps_rows.contiguous())
+        else:
+            noise_z = K.make_noise(None, current_seed(), skey)
+        eps, z0 = torch.empty(R, D, **f32), torch.empty(R, D, **f32)
+        eps_r = torch.empty(O, **f32) if want_kl else None
+        noise_r = K.make_noise(nz["eps_r"].contiguous()) if "eps_r" in nz else K.make_noise(None, current_seed(), skey + 1)
+        K.check(K.lib.lbbnn_mnf_draw(K.ptr(q0m), K.ptr(q0lv), noise_z, R, D, K.ptr(eps), K.ptr(z0), noise_r, O,
+                                     K.ptr(eps_r, allow_none=True), st))
+        # ---- z flow on both rows (per-row log-determinants: the rows are independent sample_z() calls, MNF:194 / MNF:210)
+        zf, rf = layer.z_flow, layer.r_flow
+        masks_z = None
+        if inj:
+            rows = [[m[-1:] for m in nz["z_masks"]]] + ([list(nz["z_masks2"])] if want_kl else [])
+            masks_z = torch.stack([torch.cat([r[t].reshape(1, D) for r in rows], 0) for t in range(len(rows[0]))]).contiguous()
+        key_z = zf._next_key()
+        flow_z = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
+        zs, ld = torch.empty(R, D, **f32), torch.empty(R, **f32)
+        save_z = torch.empty(int(K.lib.lbbnn_flow_save_floats(flow_z, R)), **f32)
+        K.check(K.lib.lbbnn_flow_fwd(flow_z, K.ptr(z0), R, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z),
+                                     K.ptr(zs), K.ptr(ld), K.ptr(save_z), st))
+        ctx.meta = (layer, want_kl, key_z)
+        if not want_kl:
+            ctx.save_for_backward(*ps, eps, masks_z, save_z)
+            z_row, kl0 = z0[:1], z0.new_zeros(())
+            ctx.mark_non_differentiable(z_row, kl0)
+            return zs[0], kl0, z_row
+        z2 = zs[1]
+        # ---- weight moments + weight / bias KL with the KL row's z (MNF:211, 228-234)
+        M0, V = torch.empty_like(wmu), torch.empty_like(wmu)
+        kls = torch.empty(4, **f32)                       # [kl_wb, kl, unused, unused]
+        out3 = torch.empty(3, **f32)
+        ws = K.workspace(1 << 20, dev)
+        lay = K.make_layer(wmu, wrho, lam, bmu, brho, None, z2)
+        K.check(K.lib.lbbnn_lrt_f32_prologue(lay, layer.cfg.priors, layer.cfg.var_mode, K.FLAG_SAMPLE, K.ptr(M0), K.ptr(V),
+                                             kls.data_ptr(), ws.data_ptr(), ws.numel(), st))
+        # ---- auxiliary r flow on z2 (MNF:222-223)
+        masks_r = None
+        if "r_masks" in nz:
+            masks_r = torch.stack([m.reshape(1, D) for m in nz["r_masks"]]).contiguous()
+        key_r = rf._next_key()
+        flow_r = _build_flow(rf.kind, D, len(rf.transforms), rf.n_hidden, rp)
+        z_b, ld_r = torch.empty(1, D, **f32), torch.empty(1, **f32)
+        save_r = torch.empty(int(K.lib.lbbnn_flow_save_floats(flow_r, 1)), **f32)
+        K.check(K.lib.lbbnn_flow_fwd(flow_r, z2.data_ptr(), 1, K.ptr(masks_r, allow_none=True), K.make_noise(None, *key_r),
+                                     K.ptr(z_b), K.ptr(ld_r), K.ptr(save_r), st))
+        # ---- log q0 - log r_b (MNF:212-227) and the layer's kl (MNF:235)
+        if layer._aux_ticket is None or layer._aux_ticket.device != dev:
+            layer._aux_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        save_a = torch.empty(int(K.lib.lbbnn_mnf_aux_save_floats(O)), **f32)
+        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), z0[1].data_ptr(), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), z2.data_ptr(),
+                       K.ptr(M0), K.ptr(V), K.ptr(eps_r), K.ptr(z_b))
+        K.check(K.lib.lbbnn_mnf_aux_kl_fwd(aux, K.ptr(out3), K.ptr(save_a), layer._aux_ticket.data_ptr(), st))
+        K.check(K.lib.lbbnn_mnf_kl_combine(kls.data_ptr(), out3.data_ptr(), ld[1:].data_ptr(), ld_r.data_ptr(),
+                                           kls[1:].data_ptr(), st))
+        ctx.meta = (layer, want_kl, key_z, key_r)
+        ctx.save_for_backward(*ps, eps, masks_z, save_z, z0, zs, M0, V, eps_r, z_b, masks_r, save_r, save_a)
+        z_row = z0[1:2]
+        ctx.mark_non_differentiable(z_row)
+        return zs[0], kls[1], z_row
+
+    @staticmethod
+    def backward(ctx, d_zk, d_kl, _d_z0):
+        layer, want_kl, key_z = ctx.meta[:3]
+        zf, rf = layer.z_flow, layer.r_flow
+        nzp = len(zf._params())
+        saved = ctx.saved_tensors
+        n_par = _N_LAYER_PARAMS + nzp + len(rf._params())
+        ps = saved[:n_par]
+        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2 = ps[:_N_LAYER_PARAMS]
+        zp, rp = ps[_N_LAYER_PARAMS:_N_LAYER_PARAMS + nzp], ps[_N_LAYER_PARAMS + nzp:]
+        dev, D, O = wmu.device, layer.in_features, layer.out_features
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = K.current_stream()
+        dz_k = d_zk.contiguous() if d_zk is not None else None
+        flow_z = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
+        Pz = sum(p.numel() for p in zp)
+        d_mean, d_lv = torch.empty(D, **f32), torch.empty(D, **f32)
+        if not want_kl:
+            eps, masks_z, save_z = saved[n_par:]
+            rows = dz_k.reshape(1, D) if dz_k is not None else torch.zeros(1, D, **f32)
+            gz = torch.empty(1, Pz, **f32)
+            gt, offs = _flow_grad_table(flow_z, zp, gz)
+            dz0 = torch.empty(1, D, **f32)
+            K.check(K.lib.lbbnn_flow_bwd(flow_z, gt, 1, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z), K.ptr(rows),
+                                         None, K.ptr(save_z), K.ptr(dz0), st))
+            K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), 1, D, -1, None, None, None, K.ptr(d_mean),
+                                             K.ptr(d_lv), st))
+            gzp = [gz[0, offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))]
+            return (None, None, None, None, None, None, d_mean, d_lv, None, None, None, *gzp, *([None] * len(rp)))
+        key_r = ctx.meta[3]
+        eps, masks_z, save_z, z0, zs, M0, V, eps_r, z_b, masks_r, save_r, save_a = saved[n_par:]
+        z2 = zs[1]
+        g = d_kl.reshape(1).contiguous().float() if d_kl is not None else torch.zeros(1, **f32)
+        dld = torch.empty(2, **f32)
+        K.check(K.lib.lbbnn_mnf_bwd_rows(K.ptr(g), K.ptr(dld), None, None, None, D, None, st))
+        # auxiliary term: every direct gradient + the rank-one dM0, dV
+        vec = torch.empty(8, D, **f32)
+        dM0, dV = torch.empty_like(M0), torch.empty_like(V)
+        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), z0[1].data_ptr(), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), z2.data_ptr(),
+                       K.ptr(M0), K.ptr(V), K.ptr(eps_r), K.ptr(z_b))
+        ag = K.MnfAuxGrads(*[vec[i].data_ptr() for i in range(8)], K.ptr(dM0), K.ptr(dV))
+        K.check(K.lib.lbbnn_mnf_aux_kl_bwd(aux, K.ptr(save_a), K.ptr(g), ag, st))
+        # r flow: d z_b from the auxiliary term, d log_det_r = -g
+        flow_r = _build_flow(rf.kind, D, len(rf.transforms), rf.n_hidden, rp)
+        gr = torch.empty(1, sum(p.numel() for p in rp), **f32)
+        grt, roffs = _flow_grad_table(flow_r, rp, gr)
+        dzr = torch.empty(1, D, **f32)
+        K.check(K.lib.lbbnn_flow_bwd(flow_r, grt, 1, K.ptr(masks_r, allow_none=True), K.make_noise(None, *key_r),
+                                     vec[7].data_ptr(), dld[1:].data_ptr(), K.ptr(save_r), K.ptr(dzr), st))
+        # z flow's output gradient rows: [d z_k ; d z2 = auxiliary + r flow (+ the weight KL, accumulated by finalize)]
+        rows = torch.empty(2, D, **f32)
+        K.check(K.lib.lbbnn_mnf_bwd_rows(None, None, K.ptr(dz_k, allow_none=True), vec[6].data_ptr(), K.ptr(dzr), D, K.ptr(rows), st))
+        grads = [torch.empty_like(t) for t in (wmu, wrho, lam, bmu, brho)]
+        lay = K.make_layer(wmu, wrho, lam, bmu, brho, None, z2)
+        lg = K.LayerGrads(*[K.ptr(t) for t in grads], None, rows[1].data_ptr())
+        K.check(K.lib.lbbnn_lrt_f32_finalize(lay, K.ptr(dM0), K.ptr(dV), K.ptr(_zeros_const(2 * O, dev)), layer.cfg.priors,
+                                             layer.cfg.var_mode, K.FLAG_SAMPLE, K.ptr(g), 1.0, lg, st))
+        gz = torch.empty(2, Pz, **f32)
+        gt, offs = _flow_grad_table(flow_z, zp, gz)
+        dz0 = torch.empty(2, D, **f32)
+        K.check(K.lib.lbbnn_flow_bwd(flow_z, gt, 2, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z), K.ptr(rows),
+                                     K.ptr(dld), K.ptr(save_z), K.ptr(dz0), st))
+        gzs = gz[0] + gz[1]
+        K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), 2, D, 1, vec[0].data_ptr(), vec[1].data_ptr(),
+                                         vec[2].data_ptr(), K.ptr(d_mean), K.ptr(d_lv), st))
+        gzp = [gzs[offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))]
+        grp = [gr[0, roffs[j]:roffs[j + 1]].view_as(rp[j]) for j in range(len(rp))]
+        return (None, *grads, d_mean, d_lv, vec[3], vec[4], vec[5], *gzp, *grp)
+
+
 class BayesianLinear(nn.Module):
     """MNF layer, drop-in for LBBNN-GP-MF-MNF.py:133-239: ctor `(in_features, out_features, num_transforms)`.
     `noise=` on forward injects the draws of SURVEY.md §3.2 (see tests/cases.py:mnf_noise)."""
@@ -123,6 +315,7 @@ class BayesianLinear(nn.Module):
         self.z = 0
         self._uid = next(_layer_ids)
         self._calls = 0
+        self._prep_calls = 0
         self.last_noise_key = None
         self._aux_ticket = None
         if device is not None:
@@ -137,39 +330,13 @@ class BayesianLinear(nn.Module):
 
     def _prepare(self, want_kl, nz):
         """Everything of forward() that does not depend on the input batch: the z flow on the live rows, and (training /
-        calculate_log_probs) the whole KL branch with the auxiliary r flow.  Returns (z_k, kl or 0)."""
-        dev = self.weight_mu.device
-        D = self.in_features
-        inj = "eps_z" in nz
-        # every z-flow evaluation of this call as rows of ONE launch: [activation row (last batch row), KL row]
-        eps_rows = [nz["eps_z"][-1:] if inj else torch.randn(1, D, device=dev)]
-        mask_rows = [[m[-1:] for m in nz["z_masks"]]] if inj else None
-        if want_kl:
-            eps_rows.append(nz["eps_z2"] if inj else torch.randn(1, D, device=dev))
-            if inj:
-                mask_rows.append(list(nz["z_masks2"]))
-        z0 = self._z0(torch.cat(eps_rows, 0))
-        masks = [torch.cat([r[t] for r in mask_rows], 0) for t in range(len(mask_rows[0]))] if inj else None
-        # per-row log-determinants: the rows are independent evaluations (the reference calls sample_z() once per row set,
-        # MNF:194 and MNF:210), so the IAF kind's "sum over everything" (flows2:241) must not mix them
-        zs, logdets = self.z_flow(z0, masks, per_row=True)
-        z_k = zs[0]
-        if not want_kl:
-            self.z = z0[:1]
-            return z_k, 0
-        self.z = z0[1:2]                                                # sample_z() overwrites self.z with (1,in)
-        z2 = zs[1]
-        log_det_q = logdets[1]                                          # the KL row's own log-det (sample_z() with batch 1)
-        M0, V, kl_wb = _MomentsKL.apply(self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z2, self.cfg)
-        eps_r = nz["eps_r"] if "eps_r" in nz else torch.randn(self.out_features, device=dev)
-        z_b, log_det_r = self.r_flow(z2, nz.get("r_masks"))
-        if self._aux_ticket is None or self._aux_ticket.device != dev:
-            self._aux_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-        # log_q0 (MNF:212-214) - log_rb (MNF:216-227): the GEMVs r0_c @ W_mean^T, r0_c^2 @ W_var^T with W_mean = z2 mu alpha
-        # (z2 folded into the vector side), tanh, the outer-product means and the two Gaussian sums, fused
-        aux = _AuxKL.apply(self.q0_mean, self.q0_log_var, self.z, self.r0_c, self.r0_b1, self.r0_b2, z2, M0, V, eps_r, z_b,
-                           self._aux_ticket)
-        return z_k, kl_wb + aux - log_det_q - log_det_r
+        calculate_log_probs) the whole KL branch with the auxiliary r flow -- one fused autograd node (_Prepare).
+        Returns (z_k, kl or 0)."""
+        params = [self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, self.q0_mean, self.q0_log_var,
+                  self.r0_c, self.r0_b1, self.r0_b2, *self.z_flow._params(), *self.r_flow._params()]
+        z_k, kl, z_row = _Prepare.apply((self, bool(want_kl), nz), *params)
+        self.z = z_row                                                  # sample_z() leaves its last draw in self.z
+        return z_k, (kl if want_kl else 0)
 
     def _activation(self, input, z_k, sample_branch, nz):
         self._calls += 1

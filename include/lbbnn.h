@@ -387,6 +387,25 @@ LBBNN_API int lbbnn_mnf_aux_kl_fwd(const lbbnn_mnf_aux* aux, float* out3, float*
 LBBNN_API int lbbnn_mnf_aux_kl_bwd(const lbbnn_mnf_aux* aux, const float* save, const float* gout,
                                    const lbbnn_mnf_aux_grads* grads, lbbnn_stream s);
 
+/* The elementwise glue of one MNF layer call, fused (csrc/mnf_aux.cu):
+ *   draw      z0 (rows,in) = q0_mean + sqrt(exp(q0_log_var)) eps (MNF:183-185; eps injected (rows,in) or Philox, kept in eps_out for
+ *             the backward) and, when eps_r != NULL, the auxiliary branch's eps_r (out,) (MNF:218) from its own noise source;
+ *   draw_bwd  d q0_mean, d q0_log_var from d z0 (rows,in) + the auxiliary term's direct gradients (aux_* may be NULL; aux_d_z0 is
+ *             added to row kl_row of d z0: the reference's log_q0 reads self.z = that row, MNF:212-214);
+ *   kl_combine  kl = kl_wb + (log_q0 - log_rb) - log_det_q - log_det_r (MNF:235), device scalars;
+ *   bwd_rows  dld2 = [0, -g] (log-det gradients of the activation row / the KL row) when dld2 != NULL, and, when rows2 != NULL,
+ *             rows2 (2,in) = [dz_k or 0; a + b]: the z flow's output-gradient rows before the weight KL's share is accumulated. */
+LBBNN_API int lbbnn_mnf_draw(const float* q0_mean, const float* q0_log_var, const lbbnn_noise* eps_z, int64_t rows,
+                             int64_t in_features, float* eps_out, float* z0, const lbbnn_noise* eps_r_noise,
+                             int64_t out_features, float* eps_r, lbbnn_stream s);
+LBBNN_API int lbbnn_mnf_draw_bwd(const float* q0_log_var, const float* eps, const float* dz0, int64_t rows, int64_t in_features,
+                                 int kl_row, const float* aux_d_q0_mean, const float* aux_d_q0_log_var, const float* aux_d_z0,
+                                 float* d_q0_mean, float* d_q0_log_var, lbbnn_stream s);
+LBBNN_API int lbbnn_mnf_kl_combine(const float* kl_wb, const float* aux_out, const float* log_det_q, const float* log_det_r,
+                                   float* kl_out, lbbnn_stream s);
+LBBNN_API int lbbnn_mnf_bwd_rows(const float* g, float* dld2, const float* dz_k, const float* a, const float* b,
+                                 int64_t in_features, float* rows2, lbbnn_stream s);
+
 /* ---- whole LRT training step as ONE persistent cooperative kernel (small stacks, batch <= 128) --------
  * Replaces the body of `train` for one minibatch (LRT:217-229): forward of every layer (LRT:166-211),
  * nll_loss(sum) + kl/NUM_BATCHES (LRT:223-224), backward, optim.Adam step (LRT:358); see csrc/lrt_step.cu.
