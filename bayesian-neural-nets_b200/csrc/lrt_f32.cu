@@ -593,7 +593,76 @@ __device__ __forceinline__ void adam_quad(float* __restrict__ p, float* __restri
   storeq(v, e0, n, vec, vv, false);
 }
 
+// chain rule + KL gradient (+ Adam) of the 4 consecutive weights e0 .. e0 + 3; the MNF z gradients of the quad's columns
+// come back in dzk / dzkl (the caller reduces them)
 template <bool ADAM>
+__device__ __forceinline__ void finalize_quad(const FinalizeArgs& a, int64_t e0, int64_t n, bool vec, float klg, const lbbnn_priors& P,
+                                              float inv_sp2, const KlConsts& kc, float (&dzk4)[4], float (&dzkl4)[4]) {
+  float mu[4], rho[4], lam[4], dM[4], dV[4] = {0.f, 0.f, 0.f, 0.f}, gm[4], gr[4], gl[4];
+  loadq(a.mu, e0, n, vec, mu);
+  loadq(a.rho, e0, n, vec, rho);
+  loadq(a.lam, e0, n, vec, lam);
+  loadq(a.dM, e0, n, vec, dM);
+  if (a.sample) loadq(a.dV, e0, n, vec, dV);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    gm[j] = gr[j] = gl[j] = 0.f;
+    dzk4[j] = dzkl4[j] = 0.f;
+    if (e0 + j >= n) continue;
+    const float er = expf(rho[j]), sg = log1pf(er);                     // = sigma_of(rho); e^rho reused for d sigma / d rho
+    const float al = 1.0f / (1.0f + expf(-lam[j]));                     // = alpha_of(lambda)
+    float zk = 1.0f, zkl = 1.0f;
+    if (a.z || a.z_kl) {                                                // MNF only
+      const int64_t k = (e0 + j) % a.K;
+      zk = a.z ? __ldg(a.z + k) : 1.0f;
+      zkl = a.z_kl ? __ldg(a.z_kl + k) : zk;
+    }
+    const float dMz = dM[j] * zk;
+    float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j], dzkl = 0.f;
+    if (a.var_mode == LBBNN_VAR_REFERENCE) {
+      dsg = 2.0f * al * al * sg * dV[j];
+      dal = mu[j] * dMz + 2.0f * al * sg * sg * dV[j];
+    } else {
+      dmu += 2.0f * al * (1.0f - al) * mu[j] * dV[j];
+      dsg = 2.0f * al * sg * dV[j];
+      dal = mu[j] * dMz + (sg * sg + (1.0f - 2.0f * al) * mu[j] * mu[j]) * dV[j];
+    }
+    if (klg != 0.f) {
+      const float d = mu[j] * zkl - P.mu;
+      dmu += klg * al * d * inv_sp2 * zkl;
+      dsg += klg * al * (sg * inv_sp2 - __frcp_rn(sg));
+      // log(ps / sg) - 1/2 + log(al / pa) - log((1 - al) / (1 - pa)) + ...: log(al / (1 - al)) = lambda exactly
+      dal += klg * ((kc.log_ps - logf(sg)) - 0.5f + (lam[j] - kc.logit_pa) + (sg * sg + d * d) * 0.5f * inv_sp2);
+      dzkl = klg * al * d * inv_sp2 * mu[j];
+    }
+    gm[j] = dmu;
+    gr[j] = dsg * (er / (1.0f + er));                                   // d sigma / d rho
+    gl[j] = dal * al * (1.0f - al);
+    dzk4[j] = dzk;
+    dzkl4[j] = dzkl;
+  }
+  if (ADAM) {
+    const float ss = __ldg(a.adam.coef), bc = __ldg(a.adam.coef + 1);
+    const bool va = vec && aligned16(a.adam.exp_avg[0]) && aligned16(a.adam.exp_avg[1]) && aligned16(a.adam.exp_avg[2]) &&
+                    aligned16(a.adam.exp_avg_sq[0]) && aligned16(a.adam.exp_avg_sq[1]) && aligned16(a.adam.exp_avg_sq[2]);
+    adam_quad(const_cast<float*>(a.mu), a.adam.exp_avg[0], a.adam.exp_avg_sq[0], e0, n, va, mu, gm, a.adam.beta1, a.adam.beta2,
+              a.adam.eps, ss, bc);
+    adam_quad(const_cast<float*>(a.rho), a.adam.exp_avg[1], a.adam.exp_avg_sq[1], e0, n, va, rho, gr, a.adam.beta1, a.adam.beta2,
+              a.adam.eps, ss, bc);
+    adam_quad(const_cast<float*>(a.lam), a.adam.exp_avg[2], a.adam.exp_avg_sq[2], e0, n, va, lam, gl, a.adam.beta1, a.adam.beta2,
+              a.adam.eps, ss, bc);
+  } else {
+    storeq(a.dmu, e0, n, vec, gm, a.accumulate);
+    storeq(a.drho, e0, n, vec, gr, a.accumulate);
+    storeq(a.dlam, e0, n, vec, gl, a.accumulate);
+  }
+}
+
+// ZRED (MNF, K % 4 == 0): the block is a (16 rows) x (32 column quads) patch, so the z gradients -- column sums over the
+// out features -- are reduced in registers and shared memory first and reach memory as ONE atomic per column and block
+// (one atomic per WEIGHT serialised on the <= 784 addresses in L2: 18-26 us per layer at MNIST shape)
+constexpr int kZRows = 16;
+template <bool ADAM, bool ZRED>
 __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs a) {
   const int64_t n = a.bias_only ? 0 : a.N * a.K;
   const bool vec = (n % 4 == 0) && (a.K % 4 == 0) && aligned16(a.mu) && aligned16(a.rho) && aligned16(a.lam) &&
@@ -602,67 +671,51 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
   const lbbnn_priors P = a.pri;
   const float inv_sp2 = 1.0f / (P.sigma * P.sigma);
   const KlConsts kc = kl_consts(P);
-  const int64_t nq = ceil_div(n, 4);
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = q * 4;
-    float mu[4], rho[4], lam[4], dM[4], dV[4] = {0.f, 0.f, 0.f, 0.f}, gm[4], gr[4], gl[4];
-    loadq(a.mu, e0, n, vec, mu);
-    loadq(a.rho, e0, n, vec, rho);
-    loadq(a.lam, e0, n, vec, lam);
-    loadq(a.dM, e0, n, vec, dM);
-    if (a.sample) loadq(a.dV, e0, n, vec, dV);
+  if constexpr (ZRED) {
+    static_assert(kThreads == 256, "8 warps: 32 column quads x 8 row lanes");
+    __shared__ float red[2][8][32][4];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int qpr = (int)(a.K >> 2), ncb = (qpr + 31) / 32;
+    const int cb = blockIdx.x % ncb, rb = blockIdx.x / ncb;
+    const int cq = cb * 32 + tx;
+    float sk[4] = {0.f, 0.f, 0.f, 0.f}, skl[4] = {0.f, 0.f, 0.f, 0.f};
+    if (cq < qpr) {
+      for (int64_t r = (int64_t)rb * kZRows + ty; r < min((int64_t)(rb + 1) * kZRows, a.N); r += 8) {
+        float d1[4], d2[4];
+        finalize_quad<ADAM>(a, r * a.K + 4 * cq, n, vec, klg, P, inv_sp2, kc, d1, d2);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      gm[j] = gr[j] = gl[j] = 0.f;
-      if (e0 + j >= n) continue;
-      const float er = expf(rho[j]), sg = log1pf(er);                     // = sigma_of(rho); e^rho reused for d sigma / d rho
-      const float al = 1.0f / (1.0f + expf(-lam[j]));                     // = alpha_of(lambda)
-      float zk = 1.0f, zkl = 1.0f;
-      int64_t k = 0;
-      if (a.z || a.z_kl) {                                                // MNF only
-        k = (e0 + j) % a.K;
-        zk = a.z ? __ldg(a.z + k) : 1.0f;
-        zkl = a.z_kl ? __ldg(a.z_kl + k) : zk;
+        for (int j = 0; j < 4; ++j) { sk[j] += d1[j]; skl[j] += d2[j]; }
       }
-      const float dMz = dM[j] * zk;
-      float dmu = al * dMz, dsg, dal, dzk = al * mu[j] * dM[j], dzkl = 0.f;
-      if (a.var_mode == LBBNN_VAR_REFERENCE) {
-        dsg = 2.0f * al * al * sg * dV[j];
-        dal = mu[j] * dMz + 2.0f * al * sg * sg * dV[j];
-      } else {
-        dmu += 2.0f * al * (1.0f - al) * mu[j] * dV[j];
-        dsg = 2.0f * al * sg * dV[j];
-        dal = mu[j] * dMz + (sg * sg + (1.0f - 2.0f * al) * mu[j] * mu[j]) * dV[j];
-      }
-      if (klg != 0.f) {
-        const float d = mu[j] * zkl - P.mu;
-        dmu += klg * al * d * inv_sp2 * zkl;
-        dsg += klg * al * (sg * inv_sp2 - __frcp_rn(sg));
-        // log(ps / sg) - 1/2 + log(al / pa) - log((1 - al) / (1 - pa)) + ...: log(al / (1 - al)) = lambda exactly
-        dal += klg * ((kc.log_ps - logf(sg)) - 0.5f + (lam[j] - kc.logit_pa) + (sg * sg + d * d) * 0.5f * inv_sp2);
-        dzkl = klg * al * d * inv_sp2 * mu[j];
-      }
-      gm[j] = dmu;
-      gr[j] = dsg * (er / (1.0f + er));                                   // d sigma / d rho
-      gl[j] = dal * al * (1.0f - al);
-      // MNF only; caller zeroes dz / dz_kl first
-      if (a.dz_kl) { atomicAdd(a.dz_kl + k, dzkl); if (a.dz) atomicAdd(a.dz + k, dzk); }
-      else if (a.dz) atomicAdd(a.dz + k, dzk + dzkl);
     }
-    if (ADAM) {
-      const float ss = __ldg(a.adam.coef), bc = __ldg(a.adam.coef + 1);
-      const bool va = vec && aligned16(a.adam.exp_avg[0]) && aligned16(a.adam.exp_avg[1]) && aligned16(a.adam.exp_avg[2]) &&
-                      aligned16(a.adam.exp_avg_sq[0]) && aligned16(a.adam.exp_avg_sq[1]) && aligned16(a.adam.exp_avg_sq[2]);
-      adam_quad(const_cast<float*>(a.mu), a.adam.exp_avg[0], a.adam.exp_avg_sq[0], e0, n, va, mu, gm, a.adam.beta1, a.adam.beta2,
-                a.adam.eps, ss, bc);
-      adam_quad(const_cast<float*>(a.rho), a.adam.exp_avg[1], a.adam.exp_avg_sq[1], e0, n, va, rho, gr, a.adam.beta1, a.adam.beta2,
-                a.adam.eps, ss, bc);
-      adam_quad(const_cast<float*>(a.lam), a.adam.exp_avg[2], a.adam.exp_avg_sq[2], e0, n, va, lam, gl, a.adam.beta1, a.adam.beta2,
-                a.adam.eps, ss, bc);
-    } else {
-      storeq(a.dmu, e0, n, vec, gm, a.accumulate);
-      storeq(a.drho, e0, n, vec, gr, a.accumulate);
-      storeq(a.dlam, e0, n, vec, gl, a.accumulate);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { red[0][ty][tx][j] = sk[j]; red[1][ty][tx][j] = skl[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+      const int c = threadIdx.x >> 2, j = threadIdx.x & 3;     // column quad, element
+      float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { t0 += red[0][w][c][j]; t1 += red[1][w][c][j]; }
+      const int k = (cb * 32 + c) * 4 + j;
+      if (k < a.K) {
+        if (a.dz_kl) { atomicAdd(a.dz_kl + k, t1); if (a.dz) atomicAdd(a.dz + k, t0); }
+        else if (a.dz) atomicAdd(a.dz + k, t0 + t1);
+      }
+    }
+  } else {
+    const int64_t nq = ceil_div(n, 4);
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t e0 = q * 4;
+      float d1[4], d2[4];
+      finalize_quad<ADAM>(a, e0, n, vec, klg, P, inv_sp2, kc, d1, d2);
+      if (a.dz || a.dz_kl) {                                                // MNF with K % 4 != 0; caller zeroes dz / dz_kl first
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (e0 + j >= n) continue;
+          const int64_t k = (e0 + j) % a.K;
+          if (a.dz_kl) { atomicAdd(a.dz_kl + k, d2[j]); if (a.dz) atomicAdd(a.dz + k, d1[j]); }
+          else atomicAdd(a.dz + k, d1[j] + d2[j]);
+        }
+      }
     }
   }
   // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186)
@@ -1135,6 +1188,22 @@ extern "C" int lbbnn_lrt_f32_fwd(const lbbnn_layer* L, const float* x, int64_t B
                               0, ws, ws_bytes, s);
 }
 
+namespace lbbnn {
+namespace {
+// parameter gradients from (dM, dV, colsum); MNF layers with in_features % 4 == 0 take the patch-shaped launch whose z
+// gradients are reduced per block (see lrt_f32_finalize<., true>)
+int launch_finalize(const FinalizeArgs& f, cudaStream_t st) {
+  if ((f.dz || f.dz_kl) && f.K % 4 == 0 && !f.bias_only) {
+    const int64_t ncb = ceil_div(f.K / 4, 32), nrb = ceil_div(f.N, kZRows);
+    lrt_f32_finalize<false, true><<<(unsigned)(ncb * nrb), kThreads, 0, st>>>(f);
+  } else {
+    lrt_f32_finalize<false, false><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, st>>>(f);
+  }
+  return check_launch("lrt_f32_finalize");
+}
+}  // namespace
+}  // namespace lbbnn
+
 extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, int64_t B, const float* gact,
                                         const float* ds_factor, const lbbnn_priors* pri, int var_mode, int flags,
                                         const float* kl_grad_dev, float kl_grad_host, const lbbnn_layer_grads* G,
@@ -1166,8 +1235,7 @@ extern "C" int lbbnn_lrt_f32_bwd_params(const lbbnn_layer* L, const float* x, in
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
-  lrt_f32_finalize<false><<<(unsigned)elementwise_blocks(N * K), kThreads, 0, st>>>(f);
-  return check_launch("lrt_f32_finalize");
+  return launch_finalize(f, st);
 }
 
 extern "C" int lbbnn_lrt_f32_bwd_input(const lbbnn_layer* L, const float* x, int64_t B, const float* gact,
@@ -1244,8 +1312,7 @@ extern "C" int lbbnn_lrt_f32_finalize(const lbbnn_layer* L, const float* dM, con
   f.var_mode = var_mode; f.sample = sample ? 1 : 0; f.accumulate = (flags & LBBNN_FLAG_ACCUMULATE) ? 1 : 0;
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = G->weight_mu; f.drho = G->weight_rho; f.dlam = G->lambdal; f.dbmu = G->bias_mu; f.dbrho = G->bias_rho; f.dz = G->z; f.dz_kl = G->z_kl;
-  lrt_f32_finalize<false><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
-  return check_launch("lrt_f32_finalize");
+  return launch_finalize(f, (cudaStream_t)s);
 }
 
 extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM, const float* dV, const float* colsum,
@@ -1265,7 +1332,7 @@ extern "C" int lbbnn_lrt_f32_finalize_adam(const lbbnn_layer* L, const float* dM
   f.klg_dev = kl_grad_dev; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = f.drho = f.dlam = f.dbmu = f.dbrho = f.dz = f.dz_kl = nullptr;
   f.adam = *adam;
-  lrt_f32_finalize<true><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
+  lrt_f32_finalize<true, false><<<(unsigned)elementwise_blocks(f.N * f.K), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize_adam");
 }
 
@@ -1290,7 +1357,7 @@ extern "C" int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* L, const floa
   f.klg_dev = nullptr; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = f.drho = f.dlam = f.dbmu = f.dbrho = f.dz = f.dz_kl = nullptr;
   f.adam = *adam;
-  lrt_f32_finalize<true><<<1, kThreads, 0, (cudaStream_t)s>>>(f);
+  lrt_f32_finalize<true, false><<<1, kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize_adam_bias");
 }
 

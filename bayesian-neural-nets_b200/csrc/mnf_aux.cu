@@ -216,14 +216,14 @@ __global__ void mnf_kl_combine_kernel(const float* kl_wb, const float* aux, cons
   out[0] = (kl_wb[0] + aux[0]) - ldq[0] - ldr[0];
 }
 
-// backward staging: dld = [0, -g] (log-det gradients of the activation row / the KL row; dld + 1 serves the r flow),
+// backward staging: dld = [0, g_scale * g] (log-det gradients of the activation row / the KL row; dld + 1 serves the r flow),
 // and -- second form -- the z-flow's output gradient rows: row 0 = d z_k (activation path), row 1 = a + b (the KL row's
 // direct terms; the weight KL's share is accumulated on top by lbbnn_lrt_f32_finalize)
-__global__ void __launch_bounds__(kThreads) mnf_bwd_rows_kernel(const float* __restrict__ g, float* __restrict__ dld,
+__global__ void __launch_bounds__(kThreads) mnf_bwd_rows_kernel(const float* __restrict__ g, float g_scale, float* __restrict__ dld,
                                                                 const float* __restrict__ dz_k, const float* __restrict__ a,
                                                                 const float* __restrict__ b, int D, float* __restrict__ rows) {
   const int i = blockIdx.x * kThreads + threadIdx.x;
-  if (dld && i < 2) dld[i] = i == 0 ? 0.f : -__ldg(g);
+  if (dld && i < 2) dld[i] = i == 0 ? 0.f : g_scale * __ldg(g);
   if (rows && i < D) {
     rows[i] = dz_k ? dz_k[i] : 0.f;
     rows[D + i] = (a ? a[i] : 0.f) + (b ? b[i] : 0.f);
@@ -293,11 +293,11 @@ extern "C" int lbbnn_mnf_kl_combine(const float* kl_wb, const float* aux_out, co
   return check_launch("mnf_kl_combine");
 }
 
-extern "C" int lbbnn_mnf_bwd_rows(const float* g, float* dld2, const float* dz_k, const float* a, const float* b,
+extern "C" int lbbnn_mnf_bwd_rows(const float* g, float g_scale, float* dld2, const float* dz_k, const float* a, const float* b,
                                   int64_t in_features, float* rows2, lbbnn_stream s) {
   LBBNN_REQUIRE((dld2 && g) || rows2, "nothing to do");
   LBBNN_REQUIRE(rows2 == nullptr || in_features > 0, "bad shape");
   const int64_t n = rows2 ? (in_features > 2 ? in_features : 2) : 2;
-  mnf_bwd_rows_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)s>>>(g, dld2, dz_k, a, b, (int)in_features, rows2);
+  mnf_bwd_rows_kernel<<<(unsigned)ceil_div(n, kThreads), kThreads, 0, (cudaStream_t)s>>>(g, g_scale, dld2, dz_k, a, b, (int)in_features, rows2);
   return check_launch("mnf_bwd_rows");
 }

@@ -263,6 +263,27 @@ extern "C" int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64
   return philox_export(out, n, seed, stream_id, 0, s);
 }
 
+namespace lbbnn {
+namespace {
+// N(0,1) draws of a full noise descriptor (its device step counter resolved in the kernel: fresh values on every replay of a
+// captured graph), element i = what a fused kernel drawing from the same descriptor sees at index i
+__global__ void __launch_bounds__(256) philox_noise_kernel(Noise nz, int64_t n, float* __restrict__ out) {
+  nz.resolve();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = nz.ptr ? nz.ptr[i] : philox_normal1(nz.seed, nz.stream, (uint64_t)i);
+}
+}  // namespace
+}  // namespace lbbnn
+
+extern "C" int lbbnn_philox_normal_ex(float* out, int64_t n, const lbbnn_noise* noise, lbbnn_stream s) {
+  LBBNN_REQUIRE(out && noise && n >= 0, "bad argument");
+  if (n == 0) return LBBNN_OK;
+  int64_t blocks = ceil_div(n, 256);
+  if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
+  philox_noise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)s>>>(make_noise(noise), n, out);
+  return check_launch("philox_noise");
+}
+
 extern "C" int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t B, int64_t C, float* logp,
                                         float* nll_sum, float* dlogits, float grad_scale, int64_t* step_inc,
                                         void* ws, size_t ws_bytes, lbbnn_stream s) {

@@ -129,6 +129,7 @@ SIGNATURES = {
     "lbbnn_device_ok": (_INT, []),
     "lbbnn_philox_normal": (_INT, [_P, _I64, _U64, _U64, _P]),
     "lbbnn_philox_uniform": (_INT, [_P, _I64, _U64, _U64, _P]),
+    "lbbnn_philox_normal_ex": (_INT, [_P, _I64, C.POINTER(Noise), _P]),
     "lbbnn_lrt_f32_workspace_bytes": (_SZ, [_I64, _I64, _I64]),
     "lbbnn_lrt_f32_mv_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_lrt_f32_fwd": (_INT, [C.POINTER(Layer), _P, _I64, C.POINTER(Noise), C.POINTER(Priors), _INT, _INT,
@@ -201,7 +202,7 @@ SIGNATURES = {
     "lbbnn_mnf_draw": (_INT, [_P, _P, C.POINTER(Noise), _I64, _I64, _P, _P, C.POINTER(Noise), _I64, _P, _P]),
     "lbbnn_mnf_draw_bwd": (_INT, [_P, _P, _P, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "lbbnn_mnf_kl_combine": (_INT, [_P, _P, _P, _P, _P, _P]),
-    "lbbnn_mnf_bwd_rows": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _P]),
+    "lbbnn_mnf_bwd_rows": (_INT, [_P, _F, _P, _P, _P, _P, _I64, _P, _P]),
     "lbbnn_lrt_step_workspace_bytes": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_raw_floats": (_SZ, [C.POINTER(Step)]),
     "lbbnn_lrt_step_f32": (_INT, [C.POINTER(Step), _INT, _P, _SZ, _P]),

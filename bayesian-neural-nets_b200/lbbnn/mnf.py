@@ -129,131 +129,154 @@ def _flow_grad_table(flow, params, gbuf):
     return grads, offs
 
 
-class _Prepare(torch.autograd.Function):
-    """Everything of an MNF layer call that does not depend on the input batch, as ONE autograd node (MNF:183-194 for the
-    activation row and the whole KL branch MNF:208-235): the z0 draw, the z flow on [activation row, KL row], the weight
-    moments + weight/bias KL with the KL row's z, the auxiliary r flow, log q0 - log r_b, and the combination into the
-    layer's kl.  Forward = 6 launches, backward = 9 (eager formulation with one autograd node per piece: ~45 per layer,
-    most of them elementwise glue and gradient accumulation).  Returns (z_k, kl, z0 row the reference leaves in self.z)."""
+class _ZDraw(torch.autograd.Function):
+    """The z0 draw (MNF:183-185) and the z flow (MNF:186-189) of one layer call, both rows in ONE launch each: row 0 is the
+    activation's z (the last batch row's draw), row 1 -- training / calculate_log_probs -- the KL branch's
+    own sample_z() (MNF:210).  Returns (z_k, z2, log_det_q of row 1, z0 row 1 = what the reference leaves in self.z)
+    or, without the KL row, (z_k, z0 row 0)."""
 
     @staticmethod
-    def forward(ctx, meta, *params):
+    def forward(ctx, meta, q0m, q0lv, *zp):
         K.require_device()
         layer, want_kl, nz = meta
-        ps = [p.contiguous() for p in params]
-        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2 = ps[:_N_LAYER_PARAMS]
-        nzp = len(layer.z_flow._params())
-        zp, rp = ps[_N_LAYER_PARAMS:_N_LAYER_PARAMS + nzp], ps[_N_LAYER_PARAMS + nzp:]
-        dev, D, O = wmu.device, layer.in_features, layer.out_features
+        q0m, q0lv = q0m.contiguous(), q0lv.contiguous()
+        zp = [p.contiguous() for p in zp]
+        dev, D = q0m.device, layer.in_features
         f32 = dict(dtype=torch.float32, device=dev)
         st = K.current_stream()
         R = 2 if want_kl else 1
         inj = "eps_z" in nz
-        # ---- z0 rows [activation row (the last batch row's draw, SURVEY quirk #4), KL row] + eps_r
         layer._prep_calls += 1
         skey = (layer._uid << 40) | (1 << 39) | (layer._prep_calls << 2)
         if inj:
-            eps_rows = torch.cat([nz["eps_z"][-1:], nz["eps_z2"]], 0) if want_kl else nz["eps_z"][-1:].contiguous()
+            eps_rows = torch.cat([nz["eps_z"][-1:], nz["eps_z2"]], 0) if want_kl else nz["eps_z"][-1:]
             noise_z = K.make_noise(eps_rows.contiguous())
         else:
             noise_z = K.make_noise(None, current_seed(), skey)
         eps, z0 = torch.empty(R, D, **f32), torch.empty(R, D, **f32)
-        eps_r = torch.empty(O, **f32) if want_kl else None
-        noise_r = K.make_noise(nz["eps_r"].contiguous()) if "eps_r" in nz else K.make_noise(None, current_seed(), skey + 1)
-        K.check(K.lib.lbbnn_mnf_draw(K.ptr(q0m), K.ptr(q0lv), noise_z, R, D, K.ptr(eps), K.ptr(z0), noise_r, O,
-                                     K.ptr(eps_r, allow_none=True), st))
-        # ---- z flow on both rows (per-row log-determinants: the rows are independent sample_z() calls, MNF:194 / MNF:210)
-        zf, rf = layer.z_flow, layer.r_flow
-        masks_z = None
+        K.check(K.lib.lbbnn_mnf_draw(K.ptr(q0m), K.ptr(q0lv), noise_z, R, D, K.ptr(eps), K.ptr(z0), None, 0, None, st))
+        zf = layer.z_flow
+        masks = None
         if inj:
             rows = [[m[-1:] for m in nz["z_masks"]]] + ([list(nz["z_masks2"])] if want_kl else [])
-            masks_z = torch.stack([torch.cat([r[t].reshape(1, D) for r in rows], 0) for t in range(len(rows[0]))]).contiguous()
-        key_z = zf._next_key()
-        flow_z = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
+            masks = torch.stack([torch.cat([r[t].reshape(1, D) for r in rows], 0) for t in range(len(rows[0]))]).contiguous()
+        key = zf._next_key()
+        flow = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
         zs, ld = torch.empty(R, D, **f32), torch.empty(R, **f32)
-        save_z = torch.empty(int(K.lib.lbbnn_flow_save_floats(flow_z, R)), **f32)
-        K.check(K.lib.lbbnn_flow_fwd(flow_z, K.ptr(z0), R, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z),
-                                     K.ptr(zs), K.ptr(ld), K.ptr(save_z), st))
-        ctx.meta = (layer, want_kl, key_z)
+        save = torch.empty(int(K.lib.lbbnn_flow_save_floats(flow, R)), **f32)
+        K.check(K.lib.lbbnn_flow_fwd(flow, K.ptr(z0), R, K.ptr(masks, allow_none=True), K.make_noise(None, *key), K.ptr(zs),
+                                     K.ptr(ld), K.ptr(save), st))
+        ctx.meta = (layer, want_kl, key)
+        ctx.save_for_backward(q0lv, eps, masks, save, *zp)
         if not want_kl:
-            ctx.save_for_backward(*ps, eps, masks_z, save_z)
-            z_row, kl0 = z0[:1], z0.new_zeros(())
-            ctx.mark_non_differentiable(z_row, kl0)
-            return zs[0], kl0, z_row
-        z2 = zs[1]
+            z_row = z0[:1]
+            ctx.mark_non_differentiable(z_row)
+            return zs[0], z_row
+        return zs[0], zs[1], ld[1:], z0[1:2]
+
+    @staticmethod
+    def backward(ctx, d_zk, *rest):
+        layer, want_kl, key = ctx.meta
+        q0lv, eps, masks, save, *zp = ctx.saved_tensors
+        zf = layer.z_flow
+        dev, D = q0lv.device, layer.in_features
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = K.current_stream()
+        R = 2 if want_kl else 1
+        flow = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
+        gz = torch.empty(R, sum(p.numel() for p in zp), **f32)
+        gt, offs = _flow_grad_table(flow, zp, gz)
+        dz0 = torch.empty(R, D, **f32)
+        d_mean, d_lv = torch.empty(D, **f32), torch.empty(D, **f32)
+        cz = lambda t: None if t is None else t.contiguous()
+        d_zk = cz(d_zk)
+        if not want_kl:
+            rows = d_zk.reshape(1, D) if d_zk is not None else torch.zeros(1, D, **f32)
+            dld, d_z0row = None, None
+        else:
+            d_z2, d_ld, d_z0row = (cz(t) for t in rest)
+            rows, dld = torch.empty(2, D, **f32), torch.empty(2, **f32)
+            if d_ld is None:
+                dld.zero_()
+            K.check(K.lib.lbbnn_mnf_bwd_rows(K.ptr(d_ld, allow_none=True), 1.0, K.ptr(dld) if d_ld is not None else None,
+                                             K.ptr(d_zk, allow_none=True), K.ptr(d_z2, allow_none=True), None, D, K.ptr(rows), st))
+        K.check(K.lib.lbbnn_flow_bwd(flow, gt, R, K.ptr(masks, allow_none=True), K.make_noise(None, *key), K.ptr(rows),
+                                     K.ptr(dld, allow_none=True), K.ptr(save), K.ptr(dz0), st))
+        K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), R, D, 1 if want_kl else -1, None, None,
+                                         K.ptr(d_z0row, allow_none=True), K.ptr(d_mean), K.ptr(d_lv), st))
+        gzs = gz[0] + gz[1] if R == 2 else gz[0]
+        return (None, d_mean, d_lv, *[gzs[offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))])
+
+
+class _KLBranch(torch.autograd.Function):
+    """The KL branch of one layer call after its z draw (MNF:211-235) as ONE autograd node: weight moments + weight / bias KL
+    with the KL row's z2, the auxiliary r flow on z2, log q0 - log r_b, and the combination into the layer's kl.  Nothing
+    here depends on the input batch, so network forward and backward run it on a side stream under the activation path.
+    Forward = 5 launches, backward = 5 (one autograd node per piece: ~40 per layer, mostly elementwise glue)."""
+
+    @staticmethod
+    def forward(ctx, meta, wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2, z2, ld_q, z0row, *rp):
+        K.require_device()
+        layer, nz = meta
+        ts = [t.contiguous() for t in (wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2, z2, ld_q, z0row)]
+        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2, z2, ld_q, z0row = ts
+        rp = [p.contiguous() for p in rp]
+        dev, D, O = wmu.device, layer.in_features, layer.out_features
+        f32 = dict(dtype=torch.float32, device=dev)
+        st = K.current_stream()
         # ---- weight moments + weight / bias KL with the KL row's z (MNF:211, 228-234)
         M0, V = torch.empty_like(wmu), torch.empty_like(wmu)
-        kls = torch.empty(4, **f32)                       # [kl_wb, kl, unused, unused]
-        out3 = torch.empty(3, **f32)
+        kls, out3 = torch.empty(2, **f32), torch.empty(3, **f32)     # kls = [kl_wb, kl]
         ws = K.workspace(1 << 20, dev)
         lay = K.make_layer(wmu, wrho, lam, bmu, brho, None, z2)
         K.check(K.lib.lbbnn_lrt_f32_prologue(lay, layer.cfg.priors, layer.cfg.var_mode, K.FLAG_SAMPLE, K.ptr(M0), K.ptr(V),
                                              kls.data_ptr(), ws.data_ptr(), ws.numel(), st))
-        # ---- auxiliary r flow on z2 (MNF:222-223)
-        masks_r = None
-        if "r_masks" in nz:
-            masks_r = torch.stack([m.reshape(1, D) for m in nz["r_masks"]]).contiguous()
+        # ---- auxiliary r flow on z2 (MNF:222-223); eps_r (MNF:218) rides in the flow-independent draw kernel's second half
+        rf = layer.r_flow
+        masks_r = torch.stack([m.reshape(1, D) for m in nz["r_masks"]]).contiguous() if "r_masks" in nz else None
         key_r = rf._next_key()
         flow_r = _build_flow(rf.kind, D, len(rf.transforms), rf.n_hidden, rp)
         z_b, ld_r = torch.empty(1, D, **f32), torch.empty(1, **f32)
         save_r = torch.empty(int(K.lib.lbbnn_flow_save_floats(flow_r, 1)), **f32)
-        K.check(K.lib.lbbnn_flow_fwd(flow_r, z2.data_ptr(), 1, K.ptr(masks_r, allow_none=True), K.make_noise(None, *key_r),
+        K.check(K.lib.lbbnn_flow_fwd(flow_r, K.ptr(z2), 1, K.ptr(masks_r, allow_none=True), K.make_noise(None, *key_r),
                                      K.ptr(z_b), K.ptr(ld_r), K.ptr(save_r), st))
+        if "eps_r" in nz:
+            eps_r = nz["eps_r"].contiguous()
+        else:
+            eps_r = torch.empty(O, **f32)
+            skey = (layer._uid << 40) | (1 << 39) | (layer._prep_calls << 2) | 1
+            K.check(K.lib.lbbnn_philox_normal_ex(K.ptr(eps_r), O, K.make_noise(None, current_seed(), skey), st))
         # ---- log q0 - log r_b (MNF:212-227) and the layer's kl (MNF:235)
         if layer._aux_ticket is None or layer._aux_ticket.device != dev:
             layer._aux_ticket = torch.zeros(1, dtype=torch.int32, device=dev)
         save_a = torch.empty(int(K.lib.lbbnn_mnf_aux_save_floats(O)), **f32)
-        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), z0[1].data_ptr(), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), z2.data_ptr(),
-                       K.ptr(M0), K.ptr(V), K.ptr(eps_r), K.ptr(z_b))
+        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), K.ptr(z0row), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), K.ptr(z2), K.ptr(M0), K.ptr(V),
+                       K.ptr(eps_r), K.ptr(z_b))
         K.check(K.lib.lbbnn_mnf_aux_kl_fwd(aux, K.ptr(out3), K.ptr(save_a), layer._aux_ticket.data_ptr(), st))
-        K.check(K.lib.lbbnn_mnf_kl_combine(kls.data_ptr(), out3.data_ptr(), ld[1:].data_ptr(), ld_r.data_ptr(),
-                                           kls[1:].data_ptr(), st))
-        ctx.meta = (layer, want_kl, key_z, key_r)
-        ctx.save_for_backward(*ps, eps, masks_z, save_z, z0, zs, M0, V, eps_r, z_b, masks_r, save_r, save_a)
-        z_row = z0[1:2]
-        ctx.mark_non_differentiable(z_row)
-        return zs[0], kls[1], z_row
+        K.check(K.lib.lbbnn_mnf_kl_combine(kls.data_ptr(), out3.data_ptr(), K.ptr(ld_q), K.ptr(ld_r), kls[1:].data_ptr(), st))
+        ctx.meta = (layer, key_r)
+        ctx.save_for_backward(*ts, *rp, M0, V, eps_r, z_b, masks_r, save_r, save_a)
+        return kls[1]
 
     @staticmethod
-    def backward(ctx, d_zk, d_kl, _d_z0):
-        layer, want_kl, key_z = ctx.meta[:3]
-        zf, rf = layer.z_flow, layer.r_flow
-        nzp = len(zf._params())
+    def backward(ctx, d_kl):
+        layer, key_r = ctx.meta
         saved = ctx.saved_tensors
-        n_par = _N_LAYER_PARAMS + nzp + len(rf._params())
-        ps = saved[:n_par]
-        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2 = ps[:_N_LAYER_PARAMS]
-        zp, rp = ps[_N_LAYER_PARAMS:_N_LAYER_PARAMS + nzp], ps[_N_LAYER_PARAMS + nzp:]
+        wmu, wrho, lam, bmu, brho, q0m, q0lv, r0c, rb1, rb2, z2, ld_q, z0row = saved[:13]
+        M0, V, eps_r, z_b, masks_r, save_r, save_a = saved[-7:]
+        rp = saved[13:-7]
+        rf = layer.r_flow
         dev, D, O = wmu.device, layer.in_features, layer.out_features
         f32 = dict(dtype=torch.float32, device=dev)
         st = K.current_stream()
-        dz_k = d_zk.contiguous() if d_zk is not None else None
-        flow_z = _build_flow(zf.kind, D, len(zf.transforms), zf.n_hidden, zp)
-        Pz = sum(p.numel() for p in zp)
-        d_mean, d_lv = torch.empty(D, **f32), torch.empty(D, **f32)
-        if not want_kl:
-            eps, masks_z, save_z = saved[n_par:]
-            rows = dz_k.reshape(1, D) if dz_k is not None else torch.zeros(1, D, **f32)
-            gz = torch.empty(1, Pz, **f32)
-            gt, offs = _flow_grad_table(flow_z, zp, gz)
-            dz0 = torch.empty(1, D, **f32)
-            K.check(K.lib.lbbnn_flow_bwd(flow_z, gt, 1, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z), K.ptr(rows),
-                                         None, K.ptr(save_z), K.ptr(dz0), st))
-            K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), 1, D, -1, None, None, None, K.ptr(d_mean),
-                                             K.ptr(d_lv), st))
-            gzp = [gz[0, offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))]
-            return (None, None, None, None, None, None, d_mean, d_lv, None, None, None, *gzp, *([None] * len(rp)))
-        key_r = ctx.meta[3]
-        eps, masks_z, save_z, z0, zs, M0, V, eps_r, z_b, masks_r, save_r, save_a = saved[n_par:]
-        z2 = zs[1]
-        g = d_kl.reshape(1).contiguous().float() if d_kl is not None else torch.zeros(1, **f32)
-        dld = torch.empty(2, **f32)
-        K.check(K.lib.lbbnn_mnf_bwd_rows(K.ptr(g), K.ptr(dld), None, None, None, D, None, st))
+        g = d_kl.reshape(1).contiguous().float()
+        neg = torch.empty(2, **f32)                                  # [0, -g]: d kl / d log_det_q = d kl / d log_det_r = -1
+        K.check(K.lib.lbbnn_mnf_bwd_rows(K.ptr(g), -1.0, K.ptr(neg), None, None, None, D, None, st))
         # auxiliary term: every direct gradient + the rank-one dM0, dV
         vec = torch.empty(8, D, **f32)
         dM0, dV = torch.empty_like(M0), torch.empty_like(V)
-        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), z0[1].data_ptr(), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), z2.data_ptr(),
-                       K.ptr(M0), K.ptr(V), K.ptr(eps_r), K.ptr(z_b))
+        aux = K.MnfAux(D, O, K.ptr(q0m), K.ptr(q0lv), K.ptr(z0row), K.ptr(r0c), K.ptr(rb1), K.ptr(rb2), K.ptr(z2), K.ptr(M0), K.ptr(V),
+                       K.ptr(eps_r), K.ptr(z_b))
         ag = K.MnfAuxGrads(*[vec[i].data_ptr() for i in range(8)], K.ptr(dM0), K.ptr(dV))
         K.check(K.lib.lbbnn_mnf_aux_kl_bwd(aux, K.ptr(save_a), K.ptr(g), ag, st))
         # r flow: d z_b from the auxiliary term, d log_det_r = -g
@@ -262,26 +285,18 @@ class _Prepare(torch.autograd.Function):
         grt, roffs = _flow_grad_table(flow_r, rp, gr)
         dzr = torch.empty(1, D, **f32)
         K.check(K.lib.lbbnn_flow_bwd(flow_r, grt, 1, K.ptr(masks_r, allow_none=True), K.make_noise(None, *key_r),
-                                     vec[7].data_ptr(), dld[1:].data_ptr(), K.ptr(save_r), K.ptr(dzr), st))
-        # z flow's output gradient rows: [d z_k ; d z2 = auxiliary + r flow (+ the weight KL, accumulated by finalize)]
+                                     vec[7].data_ptr(), neg[1:].data_ptr(), K.ptr(save_r), K.ptr(dzr), st))
+        # d z2 = auxiliary + r flow, then the weight KL's share accumulated on top by the finalize pass
         rows = torch.empty(2, D, **f32)
-        K.check(K.lib.lbbnn_mnf_bwd_rows(None, None, K.ptr(dz_k, allow_none=True), vec[6].data_ptr(), K.ptr(dzr), D, K.ptr(rows), st))
+        K.check(K.lib.lbbnn_mnf_bwd_rows(None, 0.0, None, None, vec[6].data_ptr(), K.ptr(dzr), D, K.ptr(rows), st))
         grads = [torch.empty_like(t) for t in (wmu, wrho, lam, bmu, brho)]
         lay = K.make_layer(wmu, wrho, lam, bmu, brho, None, z2)
         lg = K.LayerGrads(*[K.ptr(t) for t in grads], None, rows[1].data_ptr())
         K.check(K.lib.lbbnn_lrt_f32_finalize(lay, K.ptr(dM0), K.ptr(dV), K.ptr(_zeros_const(2 * O, dev)), layer.cfg.priors,
                                              layer.cfg.var_mode, K.FLAG_SAMPLE, K.ptr(g), 1.0, lg, st))
-        gz = torch.empty(2, Pz, **f32)
-        gt, offs = _flow_grad_table(flow_z, zp, gz)
-        dz0 = torch.empty(2, D, **f32)
-        K.check(K.lib.lbbnn_flow_bwd(flow_z, gt, 2, K.ptr(masks_z, allow_none=True), K.make_noise(None, *key_z), K.ptr(rows),
-                                     K.ptr(dld), K.ptr(save_z), K.ptr(dz0), st))
-        gzs = gz[0] + gz[1]
-        K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), 2, D, 1, vec[0].data_ptr(), vec[1].data_ptr(),
-                                         vec[2].data_ptr(), K.ptr(d_mean), K.ptr(d_lv), st))
-        gzp = [gzs[offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))]
         grp = [gr[0, roffs[j]:roffs[j + 1]].view_as(rp[j]) for j in range(len(rp))]
-        return (None, *grads, d_mean, d_lv, vec[3], vec[4], vec[5], *gzp, *grp)
+        #       meta  5 LRT params  q0_mean  q0_log_var  r0_c  r0_b1  r0_b2   z2      ld_q     z0 row
+        return (None, *grads, vec[0], vec[1], vec[3], vec[4], vec[5], rows[1], neg[1:], vec[2].view(1, D), *grp)
 
 
 class BayesianLinear(nn.Module):
@@ -328,15 +343,24 @@ class BayesianLinear(nn.Module):
     def _z0(self, eps):
         return self.q0_mean + self.q0_log_var.exp().sqrt() * eps       # MNF:183-185
 
+    def _draw(self, want_kl, nz):
+        """z0 draw + z flow of this call (one autograd node); returns the handle _kl_branch() continues from."""
+        out = _ZDraw.apply((self, bool(want_kl), nz), self.q0_mean, self.q0_log_var, *self.z_flow._params())
+        self.z = out[-1]                                                # sample_z() leaves its last draw in self.z
+        return out
+
+    def _kl_branch(self, drawn, nz):
+        """The layer's kl from the KL row of _draw() (one autograd node)."""
+        _, z2, ld_q, z0row = drawn
+        return _KLBranch.apply((self, nz), self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho,
+                               self.q0_mean, self.q0_log_var, self.r0_c, self.r0_b1, self.r0_b2, z2, ld_q, z0row,
+                               *self.r_flow._params())
+
     def _prepare(self, want_kl, nz):
         """Everything of forward() that does not depend on the input batch: the z flow on the live rows, and (training /
-        calculate_log_probs) the whole KL branch with the auxiliary r flow -- one fused autograd node (_Prepare).
-        Returns (z_k, kl or 0)."""
-        params = [self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, self.q0_mean, self.q0_log_var,
-                  self.r0_c, self.r0_b1, self.r0_b2, *self.z_flow._params(), *self.r_flow._params()]
-        z_k, kl, z_row = _Prepare.apply((self, bool(want_kl), nz), *params)
-        self.z = z_row                                                  # sample_z() leaves its last draw in self.z
-        return z_k, (kl if want_kl else 0)
+        calculate_log_probs) the whole KL branch with the auxiliary r flow.  Returns (z_k, kl or 0)."""
+        drawn = self._draw(want_kl, nz)
+        return drawn[0], (self._kl_branch(drawn, nz) if want_kl else 0)
 
     def _activation(self, input, z_k, sample_branch, nz):
         self._calls += 1
@@ -367,29 +391,38 @@ class BayesianNetwork(nn.Module):
         return [getattr(self, n) for n in self._names]
 
     def forward(self, x, sample=False, noises=None, calculate_log_probs=False):
-        """The flows and the KL branch of a layer depend on parameters and noise only, never on the activations: they
-        are issued for all layers first, each on its own CUDA stream (concurrent GEMV chains instead of one after the
-        other; inside a captured graph they become parallel branches), then the LRT layers run on the caller's stream."""
+        """The flows and the KL branch of a layer depend on parameters and noise only, never on the activations.  Every
+        layer gets its own CUDA stream: the z draw + z flow first (the activation path only waits for THAT), then the KL
+        branch (weight KL, auxiliary r flow, log q0 - log r_b), which runs under the LRT layers of the caller's stream --
+        and, because autograd replays a node on its forward stream, so does its backward.  Inside a captured graph these
+        are parallel branches."""
         x = x.view(-1, self.sizes[0])
         ls = self.layers
         nzs = [(None if noises is None else noises[i]) or {} for i in range(len(ls))]
         cur = torch.cuda.current_stream()
         if self._streams is None or self._streams[0].device != x.device:
             self._streams = [torch.cuda.Stream(device=x.device) for _ in ls]
-        prepared = []
+        drawn, ready = [], []
         for l, s, nz in zip(ls, self._streams, nzs):
+            want_kl = l.training or calculate_log_probs
             s.wait_stream(cur)
             with torch.cuda.stream(s):
-                z_k, kl = l._prepare(l.training or calculate_log_probs, nz)
-            prepared.append((z_k, kl))
-        for i, (l, s, nz) in enumerate(zip(ls, self._streams, nzs)):
-            cur.wait_stream(s)
-            z_k, l.kl = prepared[i]
+                d = l._draw(want_kl, nz)
+                ev = torch.cuda.Event()
+                ev.record(s)
+                l.kl = l._kl_branch(d, nz) if want_kl else 0
+            drawn.append(d)
+            ready.append(ev)
+        for i, (l, nz) in enumerate(zip(ls, nzs)):
+            cur.wait_event(ready[i])
+            z_k = drawn[i][0]
             z_k.record_stream(cur)
-            if torch.is_tensor(l.kl):
-                l.kl.record_stream(cur)
             x = l._activation(x, z_k, l.training or sample, nz)
             x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
+        for l, s in zip(ls, self._streams):
+            cur.wait_stream(s)
+            if torch.is_tensor(l.kl):
+                l.kl.record_stream(cur)
         return x
 
     def kl(self):

@@ -101,6 +101,8 @@ LBBNN_API int lbbnn_device_ok(void);
  * (replaces torch.randn LRT:174 / torch.bernoulli's uniform, flows2:209). */
 LBBNN_API int lbbnn_philox_normal(float* out, int64_t n, uint64_t seed, uint64_t stream_id, lbbnn_stream s);
 LBBNN_API int lbbnn_philox_uniform(float* out, int64_t n, uint64_t seed, uint64_t stream_id, lbbnn_stream s);
+/* the same for a full noise descriptor (step_dev honoured: a captured graph draws fresh values on every replay) */
+LBBNN_API int lbbnn_philox_normal_ex(float* out, int64_t n, const lbbnn_noise* noise, lbbnn_stream s);
 
 /* ---- LRT layer, fp32 SIMT path (parity mode) ---------------------------------------------------
  * fwd replaces BayesianLinear.forward LRT:166-196: an elementwise prologue (alpha, sigma, M, V, KL
@@ -393,7 +395,7 @@ LBBNN_API int lbbnn_mnf_aux_kl_bwd(const lbbnn_mnf_aux* aux, const float* save, 
  *   draw_bwd  d q0_mean, d q0_log_var from d z0 (rows,in) + the auxiliary term's direct gradients (aux_* may be NULL; aux_d_z0 is
  *             added to row kl_row of d z0: the reference's log_q0 reads self.z = that row, MNF:212-214);
  *   kl_combine  kl = kl_wb + (log_q0 - log_rb) - log_det_q - log_det_r (MNF:235), device scalars;
- *   bwd_rows  dld2 = [0, -g] (log-det gradients of the activation row / the KL row) when dld2 != NULL, and, when rows2 != NULL,
+ *   bwd_rows  dld2 = [0, g_scale * g] (log-det gradients of the activation row / the KL row) when dld2 != NULL, and, when rows2 != NULL,
  *             rows2 (2,in) = [dz_k or 0; a + b]: the z flow's output-gradient rows before the weight KL's share is accumulated. */
 LBBNN_API int lbbnn_mnf_draw(const float* q0_mean, const float* q0_log_var, const lbbnn_noise* eps_z, int64_t rows,
                              int64_t in_features, float* eps_out, float* z0, const lbbnn_noise* eps_r_noise,
@@ -403,7 +405,7 @@ LBBNN_API int lbbnn_mnf_draw_bwd(const float* q0_log_var, const float* eps, cons
                                  float* d_q0_mean, float* d_q0_log_var, lbbnn_stream s);
 LBBNN_API int lbbnn_mnf_kl_combine(const float* kl_wb, const float* aux_out, const float* log_det_q, const float* log_det_r,
                                    float* kl_out, lbbnn_stream s);
-LBBNN_API int lbbnn_mnf_bwd_rows(const float* g, float* dld2, const float* dz_k, const float* a, const float* b,
+LBBNN_API int lbbnn_mnf_bwd_rows(const float* g, float g_scale, float* dld2, const float* dz_k, const float* a, const float* b,
                                  int64_t in_features, float* rows2, lbbnn_stream s);
 
 /* ---- whole LRT training step as ONE persistent cooperative kernel (small stacks, batch <= 128) --------

@@ -75,6 +75,30 @@ int main(int argc, char** argv) {
     cudaEventElapsedTime(&ms, e0, e1);
     printf("%s: %.2f us per launch (back to back, D=%d rows=%d)\n", pass == 0 ? "flow_fwd" : "flow_bwd", ms * 1e3 / reps, D, R);
   }
+  {   // do independent evaluations on different streams overlap?  (3 streams x 10 launches each vs 30 on one stream)
+    cudaStream_t st[3];
+    for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    float *zo2[3], *ld2[3], *save2[3];
+    for (int i = 0; i < 3; ++i) { cudaMalloc(&zo2[i], (size_t)R * D * 4); cudaMalloc(&ld2[i], R * 4); cudaMalloc(&save2[i], lbbnn_flow_save_floats(&F, R) * 4); }
+    for (int mode = 0; mode < 2; ++mode) {
+      cudaDeviceSynchronize();
+      cudaEventRecord(e0, st[0]);
+      cudaStreamWaitEvent(st[1], e0); cudaStreamWaitEvent(st[2], e0);
+      for (int i = 0; i < 30; ++i) {
+        const int k = mode == 0 ? 0 : i % 3;
+        lbbnn_flow_fwd(&F, z, R, nullptr, &nz, zo2[k], ld2[k], save2[k], st[k]);
+      }
+      cudaEvent_t j1, j2;
+      cudaEventCreate(&j1); cudaEventCreate(&j2);
+      cudaEventRecord(j1, st[1]); cudaEventRecord(j2, st[2]);
+      cudaStreamWaitEvent(st[0], j1); cudaStreamWaitEvent(st[0], j2);
+      cudaEventRecord(e1, st[0]);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      printf("30 flow_fwd launches on %s: %.1f us total\n", mode == 0 ? "one stream" : "three streams", ms * 1e3);
+    }
+  }
   long long prof[128];
   cudaMemcpyFromSymbol(prof, lbbnn::g_flow_prof, sizeof(prof));
   int clk_khz = 0;
