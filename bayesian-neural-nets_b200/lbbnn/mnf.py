@@ -402,23 +402,21 @@ class BayesianNetwork(nn.Module):
         cur = torch.cuda.current_stream()
         if self._streams is None or self._streams[0].device != x.device:
             self._streams = [torch.cuda.Stream(device=x.device) for _ in ls]
-        drawn, ready = [], []
-        for l, s, nz in zip(ls, self._streams, nzs):
-            want_kl = l.training or calculate_log_probs
+        for s in self._streams:
             s.wait_stream(cur)
+        for i, (l, s, nz) in enumerate(zip(ls, self._streams, nzs)):
+            want_kl = l.training or calculate_log_probs
             with torch.cuda.stream(s):
                 d = l._draw(want_kl, nz)
                 ev = torch.cuda.Event()
                 ev.record(s)
-                l.kl = l._kl_branch(d, nz) if want_kl else 0
-            drawn.append(d)
-            ready.append(ev)
-        for i, (l, nz) in enumerate(zip(ls, nzs)):
-            cur.wait_event(ready[i])
-            z_k = drawn[i][0]
+            cur.wait_event(ev)
+            z_k = d[0]
             z_k.record_stream(cur)
             x = l._activation(x, z_k, l.training or sample, nz)
             x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
+            with torch.cuda.stream(s):
+                l.kl = l._kl_branch(d, nz) if want_kl else 0
         for l, s in zip(ls, self._streams):
             cur.wait_stream(s)
             if torch.is_tensor(l.kl):
