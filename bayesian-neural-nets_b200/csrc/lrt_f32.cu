@@ -718,9 +718,12 @@ __global__ void __launch_bounds__(kThreads) lrt_f32_finalize(const FinalizeArgs 
       }
     }
   }
-  // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186)
-  if (blockIdx.x == 0) {
-    for (int64_t i = threadIdx.x; i < a.N; i += blockDim.x) {
+  // biases: db_mu = sum_b dE, dsigma_b = 2 sigma_b sum_b dS, + KL (LRT:185-186); block 0 after its weights, or -- the
+  // bias-only launch of the fused-update path -- every block a slice (one block took 33 us for 4096 biases)
+  if (blockIdx.x == 0 || a.bias_only) {
+    const int64_t i0 = a.bias_only ? (int64_t)blockIdx.x * blockDim.x + threadIdx.x : threadIdx.x;
+    const int64_t di = a.bias_only ? (int64_t)gridDim.x * blockDim.x : blockDim.x;
+    for (int64_t i = i0; i < a.N; i += di) {
       const float bm = __ldg(a.bias_mu + i), br = __ldg(a.bias_rho + i), sb = sigma_of(br);
       float dbm = a.colsum[i], dsb = a.sample ? 2.0f * sb * a.colsum[a.N + i] : 0.f;
       if (klg != 0.f) {
@@ -1357,7 +1360,7 @@ extern "C" int lbbnn_lrt_f32_finalize_adam_bias(const lbbnn_layer* L, const floa
   f.klg_dev = nullptr; f.klg_host = kl_grad_host; f.pri = *pri;
   f.dmu = f.drho = f.dlam = f.dbmu = f.dbrho = f.dz = f.dz_kl = nullptr;
   f.adam = *adam;
-  lrt_f32_finalize<true, false><<<1, kThreads, 0, (cudaStream_t)s>>>(f);
+  lrt_f32_finalize<true, false><<<(unsigned)ceil_div(f.N, kThreads), kThreads, 0, (cudaStream_t)s>>>(f);
   return check_launch("lrt_f32_finalize_adam_bias");
 }
 
@@ -1449,9 +1452,29 @@ extern "C" size_t lbbnn_lrt_bf16_prologue_workspace_bytes(int64_t in_features, i
   return align_up((size_t)(ceil_div(in_features, 64) * ceil_div(out_features, 64)) * sizeof(double));
 }
 
+static int bf16_prologue_impl(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, void* M_bf, void* V_bf,
+                              void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out, bool kl_parts_only, void* ws,
+                              size_t ws_bytes, lbbnn_stream s);
+
 extern "C" int lbbnn_lrt_bf16_prologue(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, void* M_bf, void* V_bf,
                                        void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out, void* ws,
                                        size_t ws_bytes, lbbnn_stream s) {
+  return bf16_prologue_impl(L, pri, var_mode, M_bf, V_bf, MT_bf, VT_bf, M32, V32, kl_out, false, ws, ws_bytes, s);
+}
+
+extern "C" size_t lbbnn_lrt_bf16_prologue_kl_parts(int64_t in_features, int64_t out_features) {
+  return (size_t)(ceil_div(in_features, 64) * ceil_div(out_features, 64));
+}
+
+extern "C" int lbbnn_lrt_bf16_prologue_parts(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, void* M_bf, void* V_bf,
+                                             float* M32, float* V32, void* ws, size_t ws_bytes, lbbnn_stream s) {
+  LBBNN_REQUIRE(ws != nullptr, "the KL partials need the workspace");
+  return bf16_prologue_impl(L, pri, var_mode, M_bf, V_bf, nullptr, nullptr, M32, V32, nullptr, true, ws, ws_bytes, s);
+}
+
+static int bf16_prologue_impl(const lbbnn_layer* L, const lbbnn_priors* pri, int var_mode, void* M_bf, void* V_bf,
+                              void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out, bool kl_parts_only, void* ws,
+                              size_t ws_bytes, lbbnn_stream s) {
   if (int rc = check_layer(L)) return rc;
   LBBNN_REQUIRE(pri && M_bf && V_bf, "NULL argument");
   LBBNN_REQUIRE((MT_bf == nullptr) == (VT_bf == nullptr), "transposed outputs come in pairs");
@@ -1465,12 +1488,12 @@ extern "C" int lbbnn_lrt_bf16_prologue(const lbbnn_layer* L, const lbbnn_priors*
   dim3 grid((unsigned)ceil_div(K, 64), (unsigned)ceil_div(N, 64));
   LBBNN_REQUIRE(grid.y <= 65535, "too many output features for one launch");
   const size_t need = lbbnn_lrt_bf16_prologue_workspace_bytes(K, N);
-  LBBNN_REQUIRE(kl_out == nullptr || (ws && ws_bytes >= need), "workspace too small for the KL partials");
+  LBBNN_REQUIRE((kl_out == nullptr && !kl_parts_only) || (ws && ws_bytes >= need), "workspace too small for the KL partials");
   cudaStream_t st = (cudaStream_t)s;
   PrologueBf16Args pa;
   pa.mu = L->weight_mu; pa.rho = L->weight_rho; pa.lam = L->lambdal; pa.rows = N; pa.cols = K;
   pa.M = (__nv_bfloat16*)M_bf; pa.V = (__nv_bfloat16*)V_bf; pa.MT = (__nv_bfloat16*)MT_bf; pa.VT = (__nv_bfloat16*)VT_bf;
-  pa.M32 = M32; pa.V32 = V32; pa.kl_part = kl_out ? (double*)ws : nullptr; pa.var_mode = var_mode; pa.pri = *pri;
+  pa.M32 = M32; pa.V32 = V32; pa.kl_part = (kl_out || kl_parts_only) ? (double*)ws : nullptr; pa.var_mode = var_mode; pa.pri = *pri;
   lrt_bf16_prologue<<<grid, kThreads, 0, st>>>(pa);
   if (int rc = check_launch("lrt_bf16_prologue")) return rc;
   if (kl_out) {

@@ -154,6 +154,8 @@ SIGNATURES = {
     "lbbnn_bf16_pack": (_INT, [_P, _P, _INT, _I64, _I64, _P, _P, _P, _P, _P]),
     "lbbnn_lrt_bf16_prologue_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_lrt_bf16_prologue": (_INT, [C.POINTER(Layer), C.POINTER(Priors), _INT, _P, _P, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "lbbnn_lrt_bf16_prologue_kl_parts": (_SZ, [_I64, _I64]),
+    "lbbnn_lrt_bf16_prologue_parts": (_INT, [C.POINTER(Layer), C.POINTER(Priors), _INT, _P, _P, _P, _P, _P, _SZ, _P]),
     "lbbnn_tc_lrt_bwd_input_small_workspace_bytes": (_SZ, [_I64, _I64]),
     "lbbnn_tc_lrt_bwd_input_small": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "lbbnn_tc_lrt_fwd_small": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _P, _P, C.POINTER(Noise), _INT, _P, _P, _P]),

@@ -10,6 +10,8 @@ module keeps working (state_dict, eager forward) while the trainer owns the stor
 """
 from ctypes import create_string_buffer as C_create_string_buffer
 
+import os
+
 import torch
 
 from . import _capi as K
@@ -335,7 +337,12 @@ class LRTTrainer:
         if hasattr(self, "_after_restore"):
             self._after_restore()   # state derived from the parameters (carried bf16 operands)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # wide trainer: the main path is captured on a HIGH-priority stream (kernel nodes inherit it): whenever a GEMM and a
+        # side-stream pass (next layer's prologue, an update) become ready together, the block scheduler places the GEMM's
+        # persistent CTAs first and the side kernel fills what is left of each SM -- a 4096-CTA prologue that got there first
+        # kept the next forward GEMM (one ~200 KB CTA per SM) off the SMs until it had drained
+        cap = getattr(self, "capture_stream", None)
+        with (torch.cuda.graph(self.graph, stream=cap) if cap is not None else torch.cuda.graph(self.graph)):
             self._enqueue()
 
     # ---- public API -----------------------------------------------------------------------------------
@@ -560,6 +567,8 @@ class LRTTensorCoreTrainer:
         self.comm_stream = (torch.cuda.Stream(device=dev)
                             if (self.fused_update and (self.world > 1 or self.overlap)) else None)
         self.side_prologue = self.fused_prologue and self.overlap and self.comm_stream is not None
+        self.capture_stream = (torch.cuda.Stream(device=dev, priority=-1)
+                               if (self.comm_stream is not None and os.environ.get("LBBNN_WIDE_PRIORITY", "1") == "1") else None)
         self.tc = []
         for li, (i, o) in enumerate(sizes if not self.in_place else []):
             last = li == L - 1
@@ -723,30 +732,48 @@ class LRTTensorCoreTrainer:
                  for l in self.layers]
         main = torch.cuda.current_stream()
         side = self.comm_stream
+        if self.side_prologue:             # fork BEFORE the input staging: the first prologue runs next to it, not after it
+            side.wait_stream(main)
         K.check(lib.lbbnn_bf16_pack(P(self.x), None, K.PACK_SQUARE, B, self.sizes[0][0], P(self.x_bf, bf), P(self.x2_bf, bf),
                                     None, None, st)); n += 1
 
-        def prologue(i, stream):           # mu, rho, lambda -> bf16 M, V (+ fp32 copies for the head's CUDA-core dX) + KL
+        def prologue(i, stream, finalize=True):   # mu, rho, lambda -> bf16 M, V (+ fp32 copies for the head's CUDA-core dX) + KL
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
             M32 = d["mv32"]
             V32 = d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:] if M32 is not None else None
-            K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf), None, None,
-                                                P(M32, True), P(V32, True), self.stats[1 + i:].data_ptr(), d["klws"].data_ptr(),
-                                                d["klws"].numel(), stream))
+            if finalize:
+                K.check(lib.lbbnn_lrt_bf16_prologue(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf), None, None,
+                                                    P(M32, True), P(V32, True), self.stats[1 + i:].data_ptr(), d["klws"].data_ptr(),
+                                                    d["klws"].numel(), stream))
+            else:                          # KL partials stay in the layer's workspace; kl_finalize(i) closes them later
+                K.check(lib.lbbnn_lrt_bf16_prologue_parts(descs[i], l.cfg.priors, l.cfg.var_mode, P(d["M"], bf), P(d["V"], bf),
+                                                          P(M32, True), P(V32, True), d["klws"].data_ptr(), d["klws"].numel(),
+                                                          stream))
+
+        def kl_finalize(i, stream):
+            l, d = self.layers[i], self.tc[i]
+            fi, fo = self.sizes[i]
+            K.check(lib.lbbnn_lrt_kl_finalize(d["klws"].data_ptr(), int(lib.lbbnn_lrt_bf16_prologue_kl_parts(fi, fo)), descs[i],
+                                              l.cfg.priors, self.stats[1 + i:].data_ptr(), stream))
 
         if self.carry_any:                 # KL of the carried layers: computed by the previous step's update epilogues
             self.stats[1:].copy_(self.kl_next); n += 1
         ready = [None] * L
-        if self.side_prologue:             # prologues up front on the side stream; each forward GEMM waits for its own
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
+        kl_done = None
+        if self.side_prologue:             # prologues up front on the side stream; each forward GEMM waits for its own M, V
+            with torch.cuda.stream(side):  # only; the scalar KL reductions follow once every layer's operands are out
                 for i in range(L):
                     if self.tc[i]["carry"]:
                         continue
-                    prologue(i, K.current_stream()); n += 2
+                    prologue(i, K.current_stream(), finalize=False); n += 1
                     ready[i] = torch.cuda.Event()
                     ready[i].record(side)
+                for i in range(L):
+                    if not self.tc[i]["carry"]:
+                        kl_finalize(i, K.current_stream()); n += 1
+                kl_done = torch.cuda.Event()     # they read the biases: before the first bias update of the backward
+                kl_done.record(side)
         a, a2 = self.x_bf, self.x2_bf
         for i in range(L):
             l, d = self.layers[i], self.tc[i]
@@ -772,6 +799,8 @@ class LRTTensorCoreTrainer:
         if self.fused_update:
             K.check(lib.lbbnn_adam_prepare(P(self.step_dev, torch.int64), self.lr, self.betas[0], self.betas[1],
                                            P(self.adam_coef), st)); n += 1
+        if kl_done is not None:
+            main.wait_event(kl_done)
 
         def grads_of(l):
             return K.LayerGrads(*[t.data_ptr() for t in (l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad,

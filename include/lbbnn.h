@@ -207,6 +207,13 @@ LBBNN_API size_t lbbnn_lrt_bf16_prologue_workspace_bytes(int64_t in_features, in
 LBBNN_API int lbbnn_lrt_bf16_prologue(const lbbnn_layer* layer, const lbbnn_priors* priors, int var_mode, void* M_bf,
                                       void* V_bf, void* MT_bf, void* VT_bf, float* M32, float* V32, float* kl_out,
                                       void* workspace, size_t workspace_bytes, lbbnn_stream s);
+/* The same pass without the closing one-block KL reduction: the per-tile KL partials (lbbnn_lrt_bf16_prologue_kl_parts
+ * doubles) stay in `workspace` for a later lbbnn_lrt_kl_finalize(workspace, parts, ...), so that the forward GEMM waiting
+ * for M, V does not wait for a scalar it does not read. */
+LBBNN_API size_t lbbnn_lrt_bf16_prologue_kl_parts(int64_t in_features, int64_t out_features);
+LBBNN_API int lbbnn_lrt_bf16_prologue_parts(const lbbnn_layer* layer, const lbbnn_priors* priors, int var_mode, void* M_bf,
+                                            void* V_bf, float* M32, float* V32, void* workspace, size_t workspace_bytes,
+                                            lbbnn_stream s);
 /* Input gradient of a layer with out_features <= 12 (the classifier head) on the CUDA cores, fused with what
  * lbbnn_tc_lrt_bwd_input's epilogue produces for the layer below: dx = g M + 2 x .* ((g .* ds) V) through the relu that
  * produced x (FLAG_MASK_DX), dE = dx, dS = dx .* ds_prev as bf16 (batch,in) + transposes (in,batch; may be NULL), and
