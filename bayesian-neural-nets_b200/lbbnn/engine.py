@@ -598,6 +598,10 @@ class LRTTensorCoreTrainer:
             head = last and self.small_dx[li]        # <= 12 outputs: CUDA-core dX, K-major dE^T / dS^T for its dW
             # the dW GEMM's epilogue does the update: one GPU, fused update, tensor-core-sized layer
             epi_update = self.fused_update and self.world == 1 and not head
+            # LBBNN_WIDE_EPI_LAYERS="0,2": only these layers update in their dW GEMM's epilogue; the others run raw dW GEMM +
+            # the update pass on the side stream under the following GEMMs (A/B knob; default: every wide layer)
+            if epi_update and os.environ.get("LBBNN_WIDE_EPI_LAYERS") is not None:
+                epi_update = str(li) in os.environ["LBBNN_WIDE_EPI_LAYERS"].split(",")
             carry = epi_update and bool(carry_operands)
             d = dict(
                 head=head, epi_update=epi_update, carry=carry,

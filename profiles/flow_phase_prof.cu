@@ -99,6 +99,38 @@ int main(int argc, char** argv) {
       printf("30 flow_fwd launches on %s: %.1f us total\n", mode == 0 ? "one stream" : "three streams", ms * 1e3);
     }
   }
+  {   // the same three-stream pattern captured into ONE graph (what a captured training step replays)
+    cudaStream_t st[3];
+    for (int i = 0; i < 3; ++i) cudaStreamCreateWithFlags(&st[i], cudaStreamNonBlocking);
+    float *zo2[3], *ld2[3], *save2[3];
+    for (int i = 0; i < 3; ++i) { cudaMalloc(&zo2[i], (size_t)R * D * 4); cudaMalloc(&ld2[i], R * 4); cudaMalloc(&save2[i], lbbnn_flow_save_floats(&F, R) * 4); }
+    for (int mode = 0; mode < 2; ++mode) {
+      cudaGraph_t g;
+      cudaGraphExec_t ge;
+      cudaEvent_t f0, j1, j2;
+      cudaEventCreate(&f0); cudaEventCreate(&j1); cudaEventCreate(&j2);
+      cudaStreamBeginCapture(st[0], cudaStreamCaptureModeThreadLocal);
+      cudaEventRecord(f0, st[0]);
+      cudaStreamWaitEvent(st[1], f0); cudaStreamWaitEvent(st[2], f0);
+      for (int i = 0; i < 30; ++i) {
+        const int k = mode == 0 ? 0 : i % 3;
+        lbbnn_flow_fwd(&F, z, R, nullptr, &nz, zo2[k], ld2[k], save2[k], st[k]);
+      }
+      cudaEventRecord(j1, st[1]); cudaEventRecord(j2, st[2]);
+      cudaStreamWaitEvent(st[0], j1); cudaStreamWaitEvent(st[0], j2);
+      cudaStreamEndCapture(st[0], &g);
+      cudaGraphInstantiate(&ge, g, 0);
+      cudaGraphLaunch(ge, st[0]);
+      cudaStreamSynchronize(st[0]);
+      cudaEventRecord(e0, st[0]);
+      cudaGraphLaunch(ge, st[0]);
+      cudaEventRecord(e1, st[0]);
+      cudaEventSynchronize(e1);
+      float ms;
+      cudaEventElapsedTime(&ms, e0, e1);
+      printf("graph of 30 flow_fwd launches, %s: %.1f us per replay\n", mode == 0 ? "one branch" : "three branches", ms * 1e3);
+    }
+  }
   long long prof[128];
   cudaMemcpyFromSymbol(prof, lbbnn::g_flow_prof, sizeof(prof));
   int clk_khz = 0;
