@@ -16,6 +16,8 @@
 // backward: one block per 32 input columns, 8 row groups: d act_mu[j], d act_var[j] are per-row scalars (every block
 //           recomputes the O(in) reductions they hang off), so dM0 / dV are rank-1 and the column sums
 //           sum_j d act_mu[j] M0[j,i], sum_j d act_var[j] V[j,i] come from one coalesced sweep over M0 and V.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace lbbnn {
@@ -122,16 +124,19 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
   const float c = ok ? __ldg(a.r0_c + i) : 0.f, z2 = ok ? __ldg(a.z2 + i) : 0.f;
   const float cz = c * z2, cc = c * c;
   float p = 0.f, q = 0.f;
-  for (int j0 = ty; j0 < O; j0 += 8 * 8) {      // 8 rows = 16 independent loads in flight per thread
+  // rows are split over gridDim.y (25 blocks of 32 columns alone left most of the GPU idle: 30 us for 5 MB); each row slice adds
+  // its share of the two column sums to d_r0_c / d_z2 (zeroed by the host call), slice 0 also writes the per-column terms
+  const int rs = (O + gridDim.y - 1) / gridDim.y, j_lo = blockIdx.y * rs, j_hi = min(O, j_lo + rs);
+  for (int j0 = j_lo + ty; j0 < j_hi; j0 += 8 * 8) {      // 8 rows = 16 independent loads in flight per thread
     float mv[8], vv[8], dpre[8], dvar[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + 8 * k;
-      const bool okj = ok && j < O;
+      const bool okj = ok && j < j_hi;
       mv[k] = okj ? __ldg(a.M0 + (int64_t)j * D + i) : 0.f;
       vv[k] = okj ? __ldg(a.V + (int64_t)j * D + i) : 0.f;
       dpre[k] = dvar[k] = 0.f;
-      if (j < O) {
+      if (j < j_hi) {
         const float ar = __ldg(save + j), av = __ldg(save + O + j);
         dpre[k] = (1.0f - ar * ar) * d_ar;
         dvar[k] = dpre[k] * __ldg(a.eps_r + j) * (0.5f / sqrtf(av));
@@ -140,7 +145,7 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int j = j0 + 8 * k;
-      if (ok && j < O) {
+      if (ok && j < j_hi) {
         const int64_t e = (int64_t)j * D + i;
         p = fmaf(dpre[k], mv[k], p);
         q = fmaf(dvar[k], vv[k], q);
@@ -155,6 +160,9 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
   if (ty == 0 && ok) {
 #pragma unroll
     for (int r = 1; r < 8; ++r) { p += ps[r][tx]; q += qs[r][tx]; }
+    atomicAdd(g.d_r0_c + i, p * z2 + 2.0f * c * q);
+    atomicAdd(g.d_z2 + i, p * c);
+    if (blockIdx.y != 0) return;
     const float lv = __ldg(a.q0_log_var + i), dz = __ldg(a.z0 + i) - __ldg(a.q0_mean + i), iv0 = 1.0f / expf(lv);
     g.d_q0_mean[i] = gq * dz * iv0;
     g.d_q0_log_var[i] = gq * (-0.5f + 0.5f * dz * dz * iv0);
@@ -163,8 +171,6 @@ __global__ void __launch_bounds__(kThreads) mnf_aux_bwd_kernel(const lbbnn_mnf_a
     const float lvr = b2 * amean, u = zb - b1 * amean, iv = 1.0f / expf(lvr);
     g.d_r0_b1[i] = gr * u * iv * amean;
     g.d_r0_b2[i] = gr * (-0.5f + 0.5f * u * u * iv) * amean;
-    g.d_r0_c[i] = p * z2 + 2.0f * c * q;
-    g.d_z2[i] = p * c;
     g.d_z_b[i] = (i == D - 1) ? bc[1] : 0.f;
   }
 }
@@ -258,8 +264,15 @@ extern "C" int lbbnn_mnf_aux_kl_bwd(const lbbnn_mnf_aux* aux, const float* save,
   if (int rc = check_aux(aux)) return rc;
   LBBNN_REQUIRE(save && gout && grads && grads->d_q0_mean && grads->d_q0_log_var && grads->d_z0 && grads->d_r0_c &&
                     grads->d_r0_b1 && grads->d_r0_b2 && grads->d_z2 && grads->d_z_b && grads->dM0 && grads->dV, "NULL output");
+  LBBNN_CUDA(cudaMemsetAsync(grads->d_r0_c, 0, (size_t)aux->in_features * sizeof(float), (cudaStream_t)s));
+  LBBNN_CUDA(cudaMemsetAsync(grads->d_z2, 0, (size_t)aux->in_features * sizeof(float), (cudaStream_t)s));
   const unsigned blocks = (unsigned)ceil_div(aux->in_features, 32);
-  mnf_aux_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(*aux, save, gout, *grads);
+  unsigned slices = (unsigned)(2 * sm_count() / blocks);                 // ~2 blocks per SM in total
+  const unsigned max_slices = (unsigned)ceil_div(aux->out_features, 64);   // at least one 64-row pass per slice
+  if (slices > max_slices) slices = max_slices;
+  if (slices < 1) slices = 1;
+  if (const char* e = getenv("LBBNN_AUX_SLICES")) slices = (unsigned)(atoi(e) > 0 ? atoi(e) : 1);   // A/B knob
+  mnf_aux_bwd_kernel<<<dim3(blocks, slices), kThreads, 0, (cudaStream_t)s>>>(*aux, save, gout, *grads);
   return check_launch("mnf_aux_bwd");
 }
 

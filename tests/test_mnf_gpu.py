@@ -290,3 +290,4 @@ def test_aux_kl_kernels_match_the_eager_formulation(lb, D, O):
     for g, t, name in zip(got, [t for t in d if t.requires_grad],
                           ["q0_mean", "q0_log_var", "z0", "r0_c", "r0_b1", "r0_b2", "z2", "M0", "V", "z_b"]):
         assert C.rel_err(g, t.grad.float()) < 2e-5, name
+
