@@ -123,12 +123,16 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint64_t seed, uint64_t stream,
 // uniform in (0,1): 24 random bits, never 0 or 1
 __device__ __forceinline__ float u01(uint32_t w) { return ((float)(w >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
+// Box-Muller on the special-function unit: log and sin / cos through MUFU (__logf, __sincosf: absolute error 2^-21 on
+// the angle range (-pi, pi) used here) -- the accurate logf / sincospif cost ~90 of the ~250 instructions of a quad of
+// draws and made every sampling kernel issue-bound.  lbbnn_philox_normal exports exactly these values, so the oracle's
+// noise and the fused kernels' noise stay identical.
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t stream, uint64_t idx, float out[4]) {
   Philox4 p = philox4x32_10(seed, stream, idx);
-  float r0 = sqrtf(-2.0f * logf(u01(p.x))), r1 = sqrtf(-2.0f * logf(u01(p.z)));
+  float r0 = sqrtf(-2.0f * __logf(u01(p.x))), r1 = sqrtf(-2.0f * __logf(u01(p.z)));
   float s0, c0, s1, c1;
-  sincospif(2.0f * u01(p.y), &s0, &c0);
-  sincospif(2.0f * u01(p.w), &s1, &c1);
+  __sincosf(6.28318530717958647692f * (u01(p.y) - 0.5f), &s0, &c0);
+  __sincosf(6.28318530717958647692f * (u01(p.w) - 0.5f), &s1, &c1);
   out[0] = r0 * c0; out[1] = r0 * s0; out[2] = r1 * c1; out[3] = r1 * s1;
 }
 __device__ __forceinline__ void philox_uniform4(uint64_t seed, uint64_t stream, uint64_t idx, float out[4]) {
