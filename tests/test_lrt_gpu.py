@@ -153,6 +153,22 @@ def test_native_philox_noise_is_reproducible_and_normal(lb):
     assert 0 < u.min().item() and u.max().item() < 1 and abs(u.mean().item() - 0.5) < 5e-3
     # odd length: the tail elements come from the same quads
     assert torch.equal(lb.philox_normal((10,), 7, 3), a.flatten()[:10])
+    # the noise-descriptor form (lbbnn_philox_normal_ex): same values; with a device step counter the stream moves with it
+    from lbbnn import _capi as K
+    out = torch.empty(4000, device="cuda")
+    K.check(K.lib.lbbnn_philox_normal_ex(K.ptr(out), out.numel(), K.make_noise(None, 7, 3), K.current_stream()))
+    assert torch.equal(out, a.flatten()[:4000])
+    step = torch.full((1,), 2, dtype=torch.int64, device="cuda")
+    K.check(K.lib.lbbnn_philox_normal_ex(K.ptr(out), out.numel(), K.make_noise(None, 7, 1, step, 1), K.current_stream()))
+    assert torch.equal(out, a.flatten()[:4000])            # stream 1 + 2 * 1 = stream 3
+    inj = torch.arange(4000, dtype=torch.float32, device="cuda")
+    K.check(K.lib.lbbnn_philox_normal_ex(K.ptr(out), out.numel(), K.make_noise(inj), K.current_stream()))
+    assert torch.equal(out, inj)                           # injected values pass through
+    # tails: Box-Muller through the MUFU log / sincos still reaches |z| > 4 at this sample size and stays finite
+    big = lb.philox_normal((4000, 1000), seed=11, stream_id=0)
+    assert torch.isfinite(big).all() and big.abs().max().item() > 4.0
+    frac = (big.abs() > 1.959964).float().mean().item()
+    assert abs(frac - 0.05) < 1e-3
 
 
 @pytest.mark.parametrize("b,i,o", [(100, 784, 400), (33, 130, 10), (7, 37, 23)])
