@@ -239,6 +239,9 @@ def run_reference(args):
     line = reference_record("lrt_wide", args, args.steps, min(args.warmup, 1), 150.0)
     line["also"] = {"lrt_mnist": reference_record("lrt_mnist", args, 200, 3, 20.0),
                     "mf_mc_predict": mc_reference_record(args, 20.0, 64)}
+    if args.gpus == 1:
+        line["also"]["mnf_mnist"] = module_reference_record("mnf_mnist", 1, 15.0, 200)
+        line["also"]["mf_mnist"] = module_reference_record("mf_mnist", 1, 15.0, 200)
     print(json.dumps(line), flush=True)
 
 
@@ -944,19 +947,65 @@ def _module_oracle_step(kind):
     return one, B
 
 
+# the 33 Adam parameter groups of LBBNN-GP-MF.py:520-553 (name -> learning rate), for the reference's own network
+_MF_REF_LRS = (("bias_mu", 1e-4), ("bias_rho", 1e-4), ("weight_mu", 1e-4), ("weight_rho", 1e-4), ("pa", 1e-3), ("pb", 1e-3),
+               ("weight_a", 1e-5), ("weight_b", 1e-5), ("bias_a", 1e-5), ("bias_b", 1e-5), ("lambdal", 0.1))
+
+
+def _module_reference_step(kind):
+    """One minibatch of the reference's own `train()` (oracle/_ref: LBBNN-GP-MF-MNF.py:263-275 over its BayesianNetwork with
+    optim.Adam(net.parameters(), lr=1e-4), MNF:416; LBBNN-GP-MF.py:325-343 with the script's 33 parameter groups, MF:520-553)
+    or None when oracle/_ref does not hold that script."""
+    R = _ref_modules()
+    if R is None or kind not in ("mnf_mnist", "mf_mnist"):
+        return None
+    try:
+        m = R.load("ref_mnf" if kind == "mnf_mnist" else "ref_mf")
+    except Exception:
+        return None
+    m.NUM_BATCHES = NUM_BATCHES
+    rng = np.random.default_rng(0)
+    B = 100
+    x = torch.from_numpy(rng.random((8, B, 784), dtype=np.float32))
+    y = torch.from_numpy(rng.integers(0, 10, size=(8, B))).long()
+    torch.manual_seed(0)
+    net = m.BayesianNetwork()
+    if kind == "mnf_mnist":
+        opt = m.optim.Adam(net.parameters(), lr=1e-4)
+        step = lambda: m.train(net, opt)                                    # noqa: E731
+    else:
+        opt = m.optim.Adam([{"params": getattr(l, name), "lr": lr} for name, lr in _MF_REF_LRS for l in (net.l1, net.l2, net.l3)],
+                           lr=1e-4)
+        step = lambda: m.train(net, opt, 0, 0)                              # noqa: E731
+    state = {"i": 0}
+
+    def one():
+        m.train_loader = [(x[state["i"] % 8], y[state["i"] % 8])]
+        state["i"] += 1
+        step()
+    return one, B
+
+
 def cpu_reference_module(kind, budget_s=15.0, max_steps=60):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    one, B = _module_oracle_step(kind)
+    ref = _module_reference_step(kind)
+    if ref is not None:
+        one, B = ref
+        who, what = "reference", ("the reference's own classes and train() (oracle/_ref, sliced from "
+                                  + ("LBBNN-GP-MF-MNF.py" if kind == "mnf_mnist" else "LBBNN-GP-MF.py, 33 Adam groups") + ")")
+    else:
+        one, B = _module_oracle_step(kind)
+        who, what = "port", "oracle port"
     one()
     done, t0 = 0, time.perf_counter()
     while done < max_steps and (done < 2 or time.perf_counter() - t0 < budget_s):
         one()
         done += 1
     dt = time.perf_counter() - t0
-    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": "port", "steps": done,
+    return {"value": B * done / dt, "unit": "samples/s", "cores": cores, "kind": who, "steps": done,
             "ms_per_step": dt / done * 1e3,
-            "sample": f"{done} training steps (fwd+objective+bwd+Adam) of {kind} batch {B}, oracle port on torch-CPU fp32, {cores} threads"}
+            "sample": f"{done} training steps (fwd+objective+bwd+Adam) of {kind} batch {B}: {what}, torch-CPU fp32, {cores} threads"}
 
 
 def module_config(kind):
@@ -972,25 +1021,34 @@ def module_config(kind):
             "l2": "inputs rotate through a pool of 512 distinct batches (161 MB > 126 MB L2)"}
 
 
+def module_reference_record(kind, n_gpus, budget_s, max_steps):
+    r = cpu_reference_module(kind, budget_s=budget_s, max_steps=max_steps)
+    return {"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": r["unit"],
+            "n_gpus": n_gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": module_config(kind),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
 def run_module(args):
     kind = args.workload
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
             return
-        r = cpu_reference_module(kind, budget_s=60.0, max_steps=max(8, args.steps))
-        print(json.dumps({"impl": "reference", "metric": "train_samples_per_sec", "value": r["value"], "unit": r["unit"],
-                          "n_gpus": args.gpus, "steps": r["steps"], "warmup": 1, "ms_per_step": r["ms_per_step"],
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                          "config": module_config(kind),
-                          "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
-                          "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                          "gpu_launches": 0}), flush=True)
+        print(json.dumps(module_reference_record(kind, args.gpus, 60.0, max(8, args.steps))), flush=True)
         return
-    import lbbnn
     if int(os.environ.get("WORLD_SIZE", "1")) != 1:
         raise SystemExit(f"{kind} is a single-GPU workload (replicas only)")
-    torch.cuda.set_device(0)
-    dev = torch.device("cuda", 0)
+    print(json.dumps(bench_module(kind, args.steps, args.warmup, eager=args.eager)), flush=True)
+
+
+def bench_module(kind, steps, warmup, eager=False, cpu_budget_s=15.0):
+    """One module-level training workload (mnf_mnist / mf_mnist / vd_mnist) on cuda:<current device>; returns the record."""
+    import lbbnn
+    args = argparse.Namespace(steps=steps, warmup=warmup, eager=eager)
+    dev = torch.device("cuda", torch.cuda.current_device())
     torch.manual_seed(0)
     lbbnn.manual_seed(99)
     B, POOL = 100, 512
@@ -1043,7 +1101,7 @@ def run_module(args):
 
     for i in range(args.warmup):
         dev_step(px[i % POOL], py[i % POOL])
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -1060,8 +1118,7 @@ def run_module(args):
     torch.cuda.synchronize()
     te1 = time.perf_counter()
     sampler.stop()
-    from lbbnn import _capi as K
-    cpu = cpu_reference_module(kind)
+    cpu = cpu_reference_module(kind, budget_s=cpu_budget_s) if cpu_budget_s > 0 else None
     peaks = load_peaks()
     nparam = sum(p.numel() for p in net.parameters())
     # algorithmic bytes of a step: every parameter read in forward and backward, gradient written, Adam 28 B/param
@@ -1079,9 +1136,15 @@ def run_module(args):
                          "traffic": None, "peak_source": peaks["source"], "bytes_per_launch": nbytes, "us_per_launch": us,
                          "note": "a step is ~10^2 small launches (flow GEMVs, prologue/finalize, Adam): latency-bound, reported "
                                  "against HBM because the contract asks for one bound"},
-            "clocks": sampler.summary(t0, te1), "last_loss": lv, "n_parameters": nparam,
-            "cpu_baseline": {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}}
-    print(json.dumps(line), flush=True)
+            "clocks": sampler.summary(t0, te1), "last_loss": lv, "n_parameters": nparam}
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if tr is not None:
+        tr.graph = None
+    del tr, net, px, py
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_headline(args):
@@ -1090,8 +1153,12 @@ def run_headline(args):
     line = bench_lrt(ctx, "lrt_wide", args.steps, args.warmup, unfused=args.unfused)
     small = bench_lrt(ctx, "lrt_mnist", 2000, 50)
     mc = bench_mc(ctx, args, 8, 3)
+    also = {"lrt_mnist": small, "mf_mc_predict": mc}
+    if ctx.world == 1:     # the module-level training loops of the other two scripts (single-GPU workloads: replicas only)
+        also["mnf_mnist"] = bench_module("mnf_mnist", 500, 20, cpu_budget_s=10.0)
+        also["mf_mnist"] = bench_module("mf_mnist", 300, 20, cpu_budget_s=10.0)
     if ctx.rank == 0:
-        line["also"] = {"lrt_mnist": small, "mf_mc_predict": mc}
+        line["also"] = also
         print(json.dumps(line), flush=True)
     ctx.shutdown()
 
