@@ -321,6 +321,97 @@ int64_t ew_blocks(int64_t n) {
   return b < 1 ? 1 : (b > cap ? cap : b);
 }
 
+// ---- the scalar tail of the MF layer's log-probabilities (MF:148-150, 167-173, 246-251) as one forward and one backward kernel ----
+// Given the five sums s[0..4] of lbbnn_mf_sample_fwd, the Gamma draws tau_w (1) and tau_b (out) and the hyper-parameters:
+//   bias      = bias_mu + sigma_b eps_b                  (sample branch; bias_mu otherwise)
+//   c_w       = a log b + (a - 1/2) tau_w - b tau_w - lgamma(a) - log sqrt(2 pi)
+//   log_prior = [s0 c_w - tau_w s1 + (n - s0) + n 1e-8]                                        GaussGamma on the weights
+//             + sum_i [ba_i log bb_i + (ba_i - 1/2) tau_b_i - bb_i tau_b_i - lgamma(ba_i) - log sqrt(2 pi) - tau_b_i bias_i^2 + 1e-8]
+//             + s2 + n (lgamma(pa + pb) - lgamma(1 + pa + pb) - lgamma(pa) - lgamma(pb))        BetaBinomial
+//   log_q     = s3 + s4 + sum_i [-log sqrt(2 pi) - log sigma_b_i - (bias_i - bias_mu_i)^2 / (2 sigma_b_i^2)]
+// (the reference's own expressions, term for term: ~70 elementwise / reduction launches per layer forward and ~140 backward
+// in the eager formulation, on (1,) and (out,) tensors).  One block: out <= a few thousand.
+struct PriorArgs {
+  const float *s, *a, *b, *tau_w, *pa, *pb;                 // (5), (1) each
+  const float *ba, *bb, *tau_b, *bias_mu, *bias_rho;        // (out) each
+  Noise eps;                                                // eps_b: injected (out) or Philox
+  int out, sample;                                          // sample: bias is drawn (training / sample=True)
+  float n;                                                  // number of weights
+  float *bias, *eps_out;                                    // (out) each; eps_out keeps the draw for the backward
+  float* lp;                                                // [log_prior, log_q]
+};
+
+__global__ void __launch_bounds__(kThreads) mf_prior_fwd_kernel(PriorArgs a) {
+  __shared__ float red[32];
+  a.eps.resolve();
+  float gb = 0.f, lq = 0.f;
+  for (int i = threadIdx.x; i < a.out; i += kThreads) {
+    const float mu = __ldg(a.bias_mu + i), sb = sigma_of(__ldg(a.bias_rho + i));
+    float e = 0.f;
+    if (a.sample) e = a.eps.ptr ? __ldg(a.eps.ptr + i) : philox_normal1(a.eps.seed, a.eps.stream, (uint64_t)i);
+    const float bias = a.sample ? mu + sb * e : mu;
+    a.bias[i] = bias;
+    a.eps_out[i] = e;
+    const float ba = __ldg(a.ba + i), bb = __ldg(a.bb + i), tb = __ldg(a.tau_b + i);
+    const float cb = ba * logf(bb) + (ba - 0.5f) * tb - bb * tb - lgammaf(ba) - kLogSqrt2Pi;
+    gb += cb - tb * bias * bias + 1e-8f;
+    const float d = bias - mu;
+    lq += -kLogSqrt2Pi - logf(sb) - (d * d) / (2.0f * sb * sb);
+  }
+  gb = block_sum(gb, red);
+  lq = block_sum(lq, red);
+  if (threadIdx.x == 0) {
+    const float av = a.a[0], bv = a.b[0], tw = a.tau_w[0], pa = a.pa[0], pb = a.pb[0];
+    const float cw = av * logf(bv) + (av - 0.5f) * tw - bv * tw - lgammaf(av) - kLogSqrt2Pi;
+    const float ggw = a.s[0] * cw - tw * a.s[1] + (a.n - a.s[0]) + a.n * 1e-8f;
+    const float bbin = a.s[2] + a.n * (lgammaf(pa + pb) - lgammaf(1.0f + pa + pb) - lgammaf(pa) - lgammaf(pb));
+    a.lp[0] = ggw + gb + bbin;
+    a.lp[1] = a.s[3] + a.s[4] + lq;
+  }
+}
+
+struct PriorBwdArgs {
+  const float *s, *a, *b, *tau_w, *pa, *pb, *ba, *bb, *tau_b, *bias_mu, *bias_rho, *bias, *eps;
+  const float *g_lp, *g_lq, *g_bias;                        // d loss / d log_prior, d log_q (device scalars), d bias (out) or NULL
+  int out, sample;
+  float n;
+  float* d_scalar;                                          // [ds0..ds4, da, db, dtau_w, dpa, dpb]
+  float *d_ba, *d_bb, *d_tau_b, *d_bias_mu, *d_bias_rho;    // (out) each
+};
+
+__global__ void __launch_bounds__(kThreads) mf_prior_bwd_kernel(const PriorBwdArgs a) {
+  const float gp = a.g_lp ? __ldg(a.g_lp) : 0.f, gq = a.g_lq ? __ldg(a.g_lq) : 0.f;
+  for (int i = threadIdx.x; i < a.out; i += kThreads) {
+    const float mu = __ldg(a.bias_mu + i), rho = __ldg(a.bias_rho + i), sb = sigma_of(rho);
+    const float bias = __ldg(a.bias + i), e = __ldg(a.eps + i), d = bias - mu;
+    const float ba = __ldg(a.ba + i), bb = __ldg(a.bb + i), tb = __ldg(a.tau_b + i);
+    a.d_ba[i] = gp * (logf(bb) + tb - digammaf(ba));
+    a.d_bb[i] = gp * (ba / bb - tb);
+    a.d_tau_b[i] = gp * ((ba - 0.5f) - bb - bias * bias);
+    const float inv2 = 1.0f / (sb * sb);
+    const float G = (a.g_bias ? __ldg(a.g_bias + i) : 0.f) + gp * (-2.0f * tb * bias) + gq * (-d * inv2);   // d loss / d bias
+    a.d_bias_mu[i] = G + gq * (d * inv2);
+    const float dsb = (a.sample ? G * e : 0.f) + gq * (-1.0f / sb + d * d * inv2 / sb);
+    a.d_bias_rho[i] = dsb * dsigma_drho(rho);
+  }
+  if (threadIdx.x == 0) {
+    const float av = a.a[0], bv = a.b[0], tw = a.tau_w[0], pa = a.pa[0], pb = a.pb[0];
+    const float cw = av * logf(bv) + (av - 0.5f) * tw - bv * tw - lgammaf(av) - kLogSqrt2Pi;
+    const float s0 = a.s[0], s1 = a.s[1];
+    a.d_scalar[0] = gp * (cw - 1.0f);
+    a.d_scalar[1] = gp * (-tw);
+    a.d_scalar[2] = gp;
+    a.d_scalar[3] = gq;
+    a.d_scalar[4] = gq;
+    a.d_scalar[5] = gp * s0 * (logf(bv) + tw - digammaf(av));
+    a.d_scalar[6] = gp * s0 * (av / bv - tw);
+    a.d_scalar[7] = gp * (s0 * ((av - 0.5f) - bv) - s1);
+    const float psi_s = digammaf(pa + pb) - digammaf(1.0f + pa + pb);
+    a.d_scalar[8] = gp * a.n * (psi_s - digammaf(pa));
+    a.d_scalar[9] = gp * a.n * (psi_s - digammaf(pb));
+  }
+}
+
 }  // namespace
 }  // namespace lbbnn
 
@@ -425,4 +516,40 @@ extern "C" int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const floa
   if (int rc = check_launch("mf_sum_partials")) return rc;
   scale_scalar_kernel<<<1, 1, 0, (cudaStream_t)s>>>(dpb, dsums, 2);   // dpb = dL/ds2 * sum psi(1+pb-g)
   return check_launch("mf_scale");
+}
+
+extern "C" int lbbnn_mf_prior_fwd(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                  const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                  const float* bias_mu, const float* bias_rho, const lbbnn_noise* eps_b, int sample_bias,
+                                  int64_t out_features, double n_weights, float* bias, float* eps_out, float* logprobs2,
+                                  lbbnn_stream s) {
+  LBBNN_REQUIRE(sums5 && a && b && tau_w && pa && pb && bias_a && bias_b && tau_b && bias_mu && bias_rho && bias && eps_out &&
+                    logprobs2, "NULL argument");
+  LBBNN_REQUIRE(out_features > 0 && out_features < (1LL << 24), "bad shape");
+  LBBNN_REQUIRE(!sample_bias || eps_b, "the sampled bias needs its noise source");
+  PriorArgs p;
+  p.s = sums5; p.a = a; p.b = b; p.tau_w = tau_w; p.pa = pa; p.pb = pb; p.ba = bias_a; p.bb = bias_b; p.tau_b = tau_b;
+  p.bias_mu = bias_mu; p.bias_rho = bias_rho; p.eps = make_noise(eps_b); p.out = (int)out_features; p.sample = sample_bias ? 1 : 0;
+  p.n = (float)n_weights; p.bias = bias; p.eps_out = eps_out; p.lp = logprobs2;
+  mf_prior_fwd_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>(p);
+  return check_launch("mf_prior_fwd");
+}
+
+extern "C" int lbbnn_mf_prior_bwd(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                  const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                  const float* bias_mu, const float* bias_rho, const float* bias, const float* eps,
+                                  int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
+                                  const float* g_log_q, const float* g_bias, float* d_scalars10, float* d_bias_a, float* d_bias_b,
+                                  float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s) {
+  LBBNN_REQUIRE(sums5 && a && b && tau_w && pa && pb && bias_a && bias_b && tau_b && bias_mu && bias_rho && bias && eps,
+                "NULL argument");
+  LBBNN_REQUIRE(d_scalars10 && d_bias_a && d_bias_b && d_tau_b && d_bias_mu && d_bias_rho, "NULL output");
+  LBBNN_REQUIRE(out_features > 0 && out_features < (1LL << 24), "bad shape");
+  PriorBwdArgs p;
+  p.s = sums5; p.a = a; p.b = b; p.tau_w = tau_w; p.pa = pa; p.pb = pb; p.ba = bias_a; p.bb = bias_b; p.tau_b = tau_b;
+  p.bias_mu = bias_mu; p.bias_rho = bias_rho; p.bias = bias; p.eps = eps; p.g_lp = g_log_prior; p.g_lq = g_log_q; p.g_bias = g_bias;
+  p.out = (int)out_features; p.sample = sample_bias ? 1 : 0; p.n = (float)n_weights;
+  p.d_scalar = d_scalars10; p.d_ba = d_bias_a; p.d_bb = d_bias_b; p.d_tau_b = d_tau_b; p.d_bias_mu = d_bias_mu; p.d_bias_rho = d_bias_rho;
+  mf_prior_bwd_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>(p);
+  return check_launch("mf_prior_bwd");
 }

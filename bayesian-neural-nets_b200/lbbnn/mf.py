@@ -124,6 +124,45 @@ class _Linear(torch.autograd.Function):
         return dx, dW, db
 
 
+class _MFLogProbs(torch.autograd.Function):
+    """(bias, log_prior, log_variational_posterior) of one MF layer call from the sampler's five sums, the two Gamma draws and
+    the hyper-parameters (MF:148-150, 167-173, 246-251) -- the scalar tail of the layer as ONE launch each way
+    (lbbnn_mf_prior_fwd / _bwd) instead of ~70 forward and ~140 backward elementwise launches on (1,) and (out,) tensors."""
+
+    @staticmethod
+    def forward(ctx, s, a, b, tau_w, ba, bb, tau_b, bias_mu, bias_rho, pa, pb, eps_b, meta):
+        K.require_device()
+        sample_bias, n, key = meta
+        ts = [t.contiguous() for t in (s, a, b, tau_w, pa, pb, ba, bb, tau_b, bias_mu, bias_rho)]
+        out_f = bias_mu.numel()
+        dev = bias_mu.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        bias, eps, lp = torch.empty(out_f, **f32), torch.empty(out_f, **f32), torch.empty(2, **f32)
+        noise = K.make_noise(eps_b.contiguous() if eps_b is not None else None, key[0], key[1])
+        K.check(K.lib.lbbnn_mf_prior_fwd(*[K.ptr(t) for t in ts], noise, int(sample_bias), out_f, float(n), K.ptr(bias), K.ptr(eps),
+                                         K.ptr(lp), K.current_stream()))
+        ctx.save_for_backward(*ts, bias, eps)
+        ctx.meta = (sample_bias, n)
+        return bias, lp[0], lp[1]
+
+    @staticmethod
+    def backward(ctx, g_bias, g_lp, g_lq):
+        *ts, bias, eps = ctx.saved_tensors
+        sample_bias, n = ctx.meta
+        out_f = bias.numel()
+        f32 = dict(dtype=torch.float32, device=bias.device)
+        d10 = torch.empty(10, **f32)
+        d_ba, d_bb, d_tb, d_mu, d_rho = (torch.empty(out_f, **f32) for _ in range(5))
+        cz = lambda t: None if t is None else t.contiguous().float()   # noqa: E731
+        g_bias, g_lp, g_lq = cz(g_bias), cz(g_lp), cz(g_lq)
+        K.check(K.lib.lbbnn_mf_prior_bwd(*[K.ptr(t) for t in ts], K.ptr(bias), K.ptr(eps), int(sample_bias), out_f, float(n),
+                                         K.ptr(g_lp, allow_none=True), K.ptr(g_lq, allow_none=True), K.ptr(g_bias, allow_none=True),
+                                         K.ptr(d10), K.ptr(d_ba), K.ptr(d_bb), K.ptr(d_tb), K.ptr(d_mu), K.ptr(d_rho),
+                                         K.current_stream()))
+        #       s        a         b         tau_w     ba    bb    tau_b bias_mu bias_rho pa        pb        eps_b meta
+        return (d10[:5], d10[5:6], d10[6:7], d10[7:8], d_ba, d_bb, d_tb, d_mu, d_rho, d10[8:9], d10[9:10], None, None)
+
+
 class _StdGammaReparam(torch.autograd.Function):
     """Injected standard-gamma draw with torch's implicit reparameterisation gradient (gamma.py:79-87)."""
 
@@ -217,17 +256,15 @@ class BayesianLinear(nn.Module):
         noise = noise or {}
         sample_branch = self.training or sample
         want_lp = self.training or calculate_log_probs
-        sb = self.bias.sigma
         alpha_stale = None
+        eb = noise.get("eps_b")
         if sample_branch:
             self.gammas = cgamma
             mode = K.MF_SAMPLE
-            eb = noise.get("eps_b")
-            bias = self.bias_mu + sb * (eb if eb is not None else torch.randn_like(sb))
         elif medimean:
-            mode, bias = K.MF_MEDIMEAN, self.bias_mu
+            mode = K.MF_MEDIMEAN
         else:
-            mode, bias = K.MF_JOINTMEAN, self.bias_mu
+            mode = K.MF_JOINTMEAN
             alpha_stale = self.alpha.detach().contiguous()
         flags = (K.MF_FLAG_LOGPROBS if want_lp else 0) | (K.MF_FLAG_LP_ON_WS if self.logprob_on_ws else 0) \
             | (K.MF_FLAG_EXACT_GAMMA if self.gamma.exact else 0) | (K.MF_FLAG_EXACT_WPRIOR if self.weight_prior.exact else 0) \
@@ -239,19 +276,20 @@ class BayesianLinear(nn.Module):
         if want_lp:
             self.alpha = 1 / (1 + torch.exp(-self.lambdal))                                   # MF:246
             n = float(self.weight_mu.numel())
-            a, b, ba, bb, pa, pb = self.weight_a, self.weight_b, self.bias_a, self.bias_b, self.pa, self.pb
-            tau_w = self._tau(a, b, noise.get("g0_w"))
-            tau_b = self._tau(ba, bb, noise.get("g0_b"))
-            c_w = a * torch.log(b) + (a - 0.5) * tau_w - b * tau_w - torch.lgamma(a) - 0.5 * math.log(2 * math.pi)
-            gg_w = (s[0] * c_w - tau_w * s[1] + (n - s[0]) + n * 1e-8).sum()                   # MF:148-150
-            c_b = ba * torch.log(bb) + (ba - 0.5) * tau_b - bb * tau_b - torch.lgamma(ba) - 0.5 * math.log(2 * math.pi)
-            gg_b = (c_b - tau_b * bias ** 2 + 1e-8).sum()                                      # gamma = ones (MF:248)
-            bbin = s[2] + n * (torch.lgamma(pa + pb) - torch.lgamma(1 + pa + pb) - torch.lgamma(pa) - torch.lgamma(pb)).sum()
-            self.log_prior = gg_w + gg_b + bbin
-            lq_bias = (-_LOG_SQRT_2PI - torch.log(sb) - ((bias - self.bias_mu) ** 2) / (2 * sb ** 2)).sum()
-            self.log_variational_posterior = s[3] + s[4] + lq_bias
+            tau_w = self._tau(self.weight_a, self.weight_b, noise.get("g0_w"))
+            tau_b = self._tau(self.bias_a, self.bias_b, noise.get("g0_b"))
+            # bias draw (stream + 2 of the call's noise key), GaussGamma / BetaBinomial / Gaussian log-probabilities: one launch
+            bias_key = (self.last_noise_key[0], self.last_noise_key[1] + (2 << 32))
+            bias, self.log_prior, self.log_variational_posterior = _MFLogProbs.apply(
+                s, self.weight_a, self.weight_b, tau_w, self.bias_a, self.bias_b, tau_b, self.bias_mu, self.bias_rho, self.pa,
+                self.pb, eb, (sample_branch, n, bias_key))
         else:
             self.log_prior, self.log_variational_posterior = 0, 0
+            if sample_branch:
+                sb = self.bias.sigma
+                bias = self.bias_mu + sb * (eb if eb is not None else torch.randn_like(sb))
+            else:
+                bias = self.bias_mu
         return _Linear.apply(input, w, bias)
 
 

@@ -335,6 +335,24 @@ LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float
                                   float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
                                   void* workspace, size_t workspace_bytes, lbbnn_stream s);
 
+/* The scalar tail of the MF layer's log-probabilities (MF:148-150 GaussGamma, MF:167-173 BetaBinomial, MF:246-251) in one
+ * launch each way: from the five sums of lbbnn_mf_sample_fwd, the Gamma draws tau_w (1) / tau_b (out) and the hyper-
+ * parameters to  bias = bias_mu + sigma_b eps_b  (sample_bias; bias_mu otherwise), logprobs2 = [log_prior, log_q]; see
+ * csrc/mf.cu for the expressions (the reference's own, term for term).  eps_out keeps the bias draw for the backward.
+ * bwd: d_scalars10 = [d s0..s4, d a, d b, d tau_w, d pa, d pb]; g_bias (out) = gradient arriving at `bias` from the
+ * linear layer (NULL = none); every output is written. */
+LBBNN_API int lbbnn_mf_prior_fwd(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                 const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                 const float* bias_mu, const float* bias_rho, const lbbnn_noise* eps_b, int sample_bias,
+                                 int64_t out_features, double n_weights, float* bias, float* eps_out, float* logprobs2,
+                                 lbbnn_stream s);
+LBBNN_API int lbbnn_mf_prior_bwd(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                 const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                 const float* bias_mu, const float* bias_rho, const float* bias, const float* eps,
+                                 int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
+                                 const float* g_log_q, const float* g_bias, float* d_scalars10, float* d_bias_a,
+                                 float* d_bias_b, float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s);
+
 /* ---- normalizing flows of flows2.py: PropagateFlow (flows2:14-46) over RNVP (flows2:188-219) or the
  * IAF-style MNF transform (flows2:225-241), as fused small-MLP kernels (one CTA per row of z runs the
  * whole stack; see csrc/flows.cu).  Weights are nn.Linear layout (out,in).
