@@ -274,7 +274,7 @@ class BayesianLinear(nn.Module):
         w, s = _MFSample.apply(self.weight_mu, self.weight_rho, self.lambdal, cgamma, self.pb, alpha_stale,
                                noise.get("eps_w"), mode, flags, self.last_noise_key)
         if want_lp:
-            self.alpha = 1 / (1 + torch.exp(-self.lambdal))                                   # MF:246
+            self.alpha = torch.sigmoid(self.lambdal)                                          # MF:246: 1 / (1 + exp(-lambda)), one kernel
             n = float(self.weight_mu.numel())
             tau_w = self._tau(self.weight_a, self.weight_b, noise.get("g0_w"))
             tau_b = self._tau(self.bias_a, self.bias_b, noise.get("g0_b"))
@@ -328,7 +328,7 @@ class BayesianNetwork(nn.Module):
         for i in range(samples):
             gs = []
             for li, l in enumerate(self.layers):
-                l.alpha = 1 / (1 + torch.exp(-l.lambdal))
+                l.alpha = torch.sigmoid(l.lambdal)            # 1 / (1 + exp(-lambda)) (MF:290) as one kernel each way
                 l.gamma.alpha = l.alpha
                 gs.append(l.gamma.rsample(None if us is None else us[i][li]))
             out = self.forward(input, *gs, sample=True, medimean=False, noises=None if noises is None else noises[i])
@@ -372,7 +372,7 @@ class SimStudyNetwork(nn.Module):
         outs, lps, lqs, nlls = [], [], [], []
         tgt = target.unsqueeze(1).float()
         for i in range(samples):
-            self.l1.alpha = 1 / (1 + torch.exp(-self.l1.lambdal))
+            self.l1.alpha = torch.sigmoid(self.l1.lambdal)
             self.l1.gamma.alpha = self.l1.alpha
             g1 = self.l1.gamma.rsample(None if us is None else us[i])
             out = self.forward(input, g1, sample=True, medimean=False, noise=None if noises is None else noises[i])
