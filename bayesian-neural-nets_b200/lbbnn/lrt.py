@@ -41,7 +41,11 @@ class _LRTFunction(torch.autograd.Function):
     """activations, kl = f(x, mu, rho, lambda, b_mu, b_rho[, z]); forward LRT:166-196, backward SURVEY §3.5."""
 
     @staticmethod
-    def forward(ctx, x, weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z, eps, cfg, sample, want_kl, noise_key):
+    def forward(ctx, x, weight_mu, weight_rho, lambdal, bias_mu, bias_rho, z, eps, cfg, sample, want_kl, noise_key,
+                relu=False, mask_dx=False):
+        """relu: the activations leave the kernel through F.relu (the layer's gradient input is then d loss / d PRE-relu
+        activation: whoever consumes them must mask it -- the next layer's backward with mask_dx does).
+        mask_dx: this layer's input x is such a relu output; its input gradient goes through [x > 0]."""
         K.require_device()
         x = x.contiguous()
         B, in_f = x.shape
@@ -56,7 +60,7 @@ class _LRTFunction(torch.autograd.Function):
             if tuple(eps.shape) != (B, out_f):
                 raise K.LbbnnError(f"eps must be {(B, out_f)}, got {tuple(eps.shape)}")
         noise = K.make_noise(eps, noise_key[0], noise_key[1])
-        flags = (K.FLAG_SAMPLE if sample else 0) | (K.FLAG_KL if want_kl else 0)
+        flags = (K.FLAG_SAMPLE if sample else 0) | (K.FLAG_KL if want_kl else 0) | (K.FLAG_RELU if relu else 0)
         act = torch.empty(B, out_f, dtype=torch.float32, device=x.device)
         dsf = torch.empty(B, out_f, dtype=torch.float32, device=x.device) if sample else None
         kl = torch.zeros((), dtype=torch.float32, device=x.device)
@@ -68,7 +72,7 @@ class _LRTFunction(torch.autograd.Function):
                                         K.ptr(dsf, allow_none=True), K.ptr(kl), K.ptr(mv, allow_none=True),
                                         ws.data_ptr(), ws.numel(), K.current_stream()))
         ctx.save_for_backward(x, *params, zc, dsf, mv)
-        ctx.cfg, ctx.sample, ctx.want_kl = cfg, sample, want_kl
+        ctx.cfg, ctx.sample, ctx.want_kl, ctx.mask_dx = cfg, sample, want_kl, bool(mask_dx)
         return act, kl
 
     @staticmethod
@@ -95,9 +99,10 @@ class _LRTFunction(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             K.check(K.lib.lbbnn_lrt_f32_bwd_input(layer, K.ptr(x), B, K.ptr(g_act), K.ptr(dsf, allow_none=True),
-                                                  cfg.priors, cfg.var_mode, flags, K.ptr(mv, allow_none=True),
-                                                  K.ptr(dx), ws.data_ptr(), ws.numel(), K.current_stream()))
-        return (dx, *grads, dz, None, None, None, None, None)
+                                                  cfg.priors, cfg.var_mode, flags | (K.FLAG_MASK_DX if ctx.mask_dx else 0),
+                                                  K.ptr(mv, allow_none=True), K.ptr(dx), ws.data_ptr(), ws.numel(),
+                                                  K.current_stream()))
+        return (dx, *grads, dz, None, None, None, None, None, None, None)
 
 
 def lrt_linear(x, weight_mu, weight_rho, lambdal, bias_mu, bias_rho, *, z=None, eps=None, cfg=None, sample=True,
@@ -198,12 +203,14 @@ class BayesianLinear(nn.Module):
         self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
         return self.last_noise_key
 
-    def forward(self, input, sample=False, calculate_log_probs=False, eps=None):
+    def forward(self, input, sample=False, calculate_log_probs=False, eps=None, _relu=False, _mask_dx=False):
+        """_relu / _mask_dx (internal, set by BayesianNetwork.forward): F.relu fused into this layer's kernel, and the relu
+        backward of the layer BELOW fused into this layer's input gradient (see _LRTFunction)."""
         sample_branch = self.training or sample
         want_kl = self.training or calculate_log_probs
         key = self._next_noise_key() if (sample_branch and eps is None) else (0, 0)
         act, kl = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho,
-                                     None, eps, self.cfg, sample_branch, want_kl, key)
+                                     None, eps, self.cfg, sample_branch, want_kl, key, _relu, _mask_dx)
         self.kl = kl if want_kl else 0
         return act
 
@@ -226,10 +233,9 @@ class BayesianNetwork(nn.Module):
     def forward(self, x, sample=False, eps=None):
         x = x.view(-1, self.sizes[0])
         ls = self.layers
-        for i, l in enumerate(ls):
-            x = l.forward(x, sample, eps=None if eps is None else eps[i])
-            x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
-        return x
+        for i, l in enumerate(ls):     # F.relu (LRT:208-209) rides in the layer kernels: forward flag here, backward mask in the next layer
+            x = l.forward(x, sample, eps=None if eps is None else eps[i], _relu=i < len(ls) - 1, _mask_dx=i > 0)
+        return F.log_softmax(x, dim=1)
 
     def kl(self):
         return sum(l.kl for l in self.layers)

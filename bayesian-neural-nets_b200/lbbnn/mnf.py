@@ -364,11 +364,11 @@ class BayesianLinear(nn.Module):
         drawn = self._draw(want_kl, nz)
         return drawn[0], (self._kl_branch(drawn, nz) if want_kl else 0)
 
-    def _activation(self, input, z_k, sample_branch, nz):
+    def _activation(self, input, z_k, sample_branch, nz, relu=False, mask_dx=False):
         self._calls += 1
         self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
         act, _ = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z_k,
-                                    nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key)
+                                    nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key, relu, mask_dx)
         return act
 
     def forward(self, input, sample=False, calculate_log_probs=False, noise=None):
@@ -427,8 +427,8 @@ class BayesianNetwork(nn.Module):
             cur.wait_event(drawn[i][1])
             z_k = drawn[i][0][0]
             z_k.record_stream(cur)
-            x = l._activation(x, z_k, l.training or sample, nz)
-            x = F.relu(x) if i < len(ls) - 1 else x
+            # F.relu (MNF:252-253) rides in the layer kernels: forward flag here, its backward as the next layer's dx mask
+            x = l._activation(x, z_k, l.training or sample, nz, relu=i < len(ls) - 1, mask_dx=i > 0)
             if interleave:
                 with torch.cuda.stream(s):
                     l.kl = l._kl_branch(drawn[i][0], nz) if (l.training or calculate_log_probs) else 0
