@@ -1295,17 +1295,22 @@ __device__ void last_bwd(const DevStep& a, float* __restrict__ sm) {
       p.dS[e] = dx * fv;
     }
   }
-  // dM = dE^T x, dV = dS^T x^2 (+ the bias column sums): CTAs from the BACK of the grid take 32-wide chunks of k.  dE, dS
-  // and the chunk's columns of x are staged in shared memory (compact loops: this code runs once per launch on a few
-  // CTAs, so its instruction footprint matters more than its issue rate); one (class, k) output per thread, the batch
-  // summed in order.
+  // dM = dE^T x, dV = dS^T x^2 (+ the bias column sums): CTAs from the BACK of the grid take (32-wide chunk of k) x (quarter
+  // of the 2 N output rows) tasks -- with whole chunks, 19 CTAs worked ~8.7 us at MNIST shape while 277 waited at the grid
+  // barrier.  dE, dS and the chunk's columns of x are staged in shared memory (compact loops: this code runs once per
+  // launch on a few CTAs, so its instruction footprint matters more than its issue rate); one (class, k) output per thread,
+  // the batch summed in order.
   constexpr int NW = NT / 32;
   const int nchunk = (K + 31) / 32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* gE = sm;                    // [B][N]
   float* gS = gE + B * N;            // [B][N]
   float* xs = gS + B * N;            // [B][32]
-  for (int chunk = G - 1 - (int)blockIdx.x; chunk < nchunk; chunk += G) {
+  constexpr int kJSplit = 4;
+  const int jper = (2 * N + kJSplit - 1) / kJSplit;
+  for (int task = G - 1 - (int)blockIdx.x; task < nchunk * kJSplit; task += G) {
+    const int chunk = task / kJSplit, js = task - chunk * kJSplit;
+    const int j_lo = js * jper, j_hi = min(2 * N, j_lo + jper);
     __syncthreads();
     for (int i0 = threadIdx.x; i0 < B * N; i0 += NT * 4) {
       float te[4], ts[4];
@@ -1336,8 +1341,8 @@ __device__ void last_bwd(const DevStep& a, float* __restrict__ sm) {
       }
     }
     __syncthreads();
-    for (int o = threadIdx.x; o < 2 * N * 32; o += NT) {
-      const int ln = o & 31, j = o >> 5;      // j in [0, 2N): dM rows then dV rows
+    for (int o = threadIdx.x; o < (j_hi - j_lo) * 32; o += NT) {
+      const int ln = o & 31, j = j_lo + (o >> 5);      // j in [0, 2N): dM rows then dV rows
       const bool sq = j >= N;
       const float* src = (sq ? gS : gE) + (sq ? j - N : j);
       float a0 = 0.f, a1 = 0.f;
@@ -1352,7 +1357,7 @@ __device__ void last_bwd(const DevStep& a, float* __restrict__ sm) {
       const int kk = chunk * 32 + ln;
       if (kk < K) (sq ? y.dV : y.dM)[(int64_t)(sq ? j - N : j) * K + kk] = a0 + a1;
     }
-    if (chunk == nchunk - 1) {   // bias column sums over the batch: a warp per column, lanes over b, fixed shuffle tree
+    if (chunk == nchunk - 1 && js == 0) {   // bias column sums over the batch: a warp per column, lanes over b, fixed shuffle tree
       for (int n = warp; n < 2 * N; n += NW) {
         const float* src = n < N ? gE : gS;
         const int c = n < N ? n : n - N;
