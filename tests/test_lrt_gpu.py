@@ -208,7 +208,9 @@ def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph, fused):
     tr = lb.LRTTrainer(net, batch_size=100, num_batches=C.NUM_BATCHES, lr=1e-3, use_graph=use_graph, inject_noise=True,
                        fused=fused)
     assert tr.fused == fused
-    layers = [{k: v.clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
+    # the oracle runs in float64 (the fp32 CPU oracle carries its own ~1e-5 rounding through three layers; against fp64 the
+    # fp32 kernels meet the stated 1e-5 on the loss, the KL and every gradient)
+    layers = [{k: v.double().clone().requires_grad_(True) for k, v in p.items()} for p in case["layers"]]
     opt = torch.optim.Adam([v for p in layers for v in p.values()], lr=1e-3)
     rng = np.random.default_rng(99)
     for step in range(3):
@@ -217,20 +219,22 @@ def test_trainer_step_matches_oracle_plus_torch_adam(lb, use_graph, fused):
             buf.copy_(e)
         out = tr.step(case["x"], case["y"])
         opt.zero_grad()
-        loss, nll, kl, _ = O.lrt_net_loss(case["x"], case["y"], layers, eps, C.NUM_BATCHES)
+        loss, nll, kl, _ = O.lrt_net_loss(case["x"].double(), case["y"], layers, [e.double() for e in eps], C.NUM_BATCHES)
         loss.backward()
-        assert abs(out["nll"] - nll.item()) / abs(nll.item()) < 1e-4, step
+        assert abs(out["nll"] - nll.item()) / abs(nll.item()) < TOL, step
         assert abs(out["kl"] - kl.item()) / abs(kl.item()) < TOL, step
         for li, (l, p) in enumerate(zip(net.layers, layers)):
             for k in NAMES:
-                assert C.rel_err(getattr(l, k).grad, p[k].grad) < 5e-5, (step, li, k, "grad")
+                assert C.rel_err(getattr(l, k).grad, p[k].grad.float()) < TOL, (step, li, k, "grad")
                 # Adam's first steps are ~lr*sign(g): drive torch's Adam with the trainer's own gradient so
                 # the optimizer kernel is compared exactly instead of amplifying 1e-6 gradient differences
-                p[k].grad = getattr(l, k).grad.detach().cpu().clone()
+                p[k].grad = getattr(l, k).grad.detach().cpu().double().clone()
         opt.step()
         for li, (l, p) in enumerate(zip(net.layers, layers)):
             for k in NAMES:
-                assert C.rel_err(getattr(l, k).data, p[k].data) < 2e-6, (step, li, k, "param")
+                assert C.rel_err(getattr(l, k).data, p[k].data.float()) < 2e-6, (step, li, k, "param")
+                with torch.no_grad():          # the next step starts from the trainer's fp32 parameters on both sides
+                    p[k].copy_(getattr(l, k).data.detach().cpu().double())
 
 
 @pytest.mark.parametrize("fused", [False, True])
