@@ -95,6 +95,51 @@ __global__ void logsoftmax_nll_kernel(const float* __restrict__ logits, const in
   }
 }
 
+// The whole objective of a minibatch (LRT:221-224, MNF:267-270) in one block: the kernel above plus
+//   loss = nll + kl_scale * sum_i kl_i        out = [loss, nll]
+// so that a module-level training step (GraphedTrainer) goes from the logits straight to d loss / d logits: the torch
+// formulation (log_softmax, nll_loss, the sum over the layers' kl, / NUM_BATCHES, + and their backward nodes) was ~20
+// launches of 1-6 us each on the critical path between the forward and the backward.
+constexpr int kMaxKlTerms = 16;
+struct ObjectiveArgs {
+  const float* logits;
+  const int64_t* target;
+  int64_t B, C;
+  const float* kl[kMaxKlTerms];
+  int n_kl;
+  float kl_scale;
+  float *out, *dlogits;
+};
+__global__ void __launch_bounds__(1024) objective_kernel(const ObjectiveArgs a) {
+  __shared__ float red[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float local = 0.f;
+  for (int64_t b = warp; b < a.B; b += nw) {
+    const float* row = a.logits + b * a.C;
+    float mx = -INFINITY;
+    for (int64_t c = lane; c < a.C; c += 32) mx = fmaxf(mx, row[c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float se = 0.f;
+    for (int64_t c = lane; c < a.C; c += 32) se += expf(row[c] - mx);
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    const int64_t t = a.target[b];
+    for (int64_t c = lane; c < a.C; c += 32) {
+      const float lp = row[c] - lse;
+      if (a.dlogits) a.dlogits[b * a.C + c] = expf(lp) - (c == t ? 1.0f : 0.0f);
+      if (c == t) local -= lp;
+    }
+  }
+  const float nll = block_sum(local, red);
+  if (threadIdx.x == 0) {
+    float kl = 0.f;
+    for (int i = 0; i < a.n_kl; ++i) kl += *a.kl[i];                     // in the order of sum(l.kl for l in layers)
+    a.out[0] = nll + kl * a.kl_scale;
+    a.out[1] = nll;
+  }
+}
+
 // large batches: one warp per row over many blocks, per-block partial sums, then a fixed-order final sum
 __global__ void __launch_bounds__(256) logsoftmax_nll_rows(const float* __restrict__ logits, const int64_t* __restrict__ target,
                                                            int64_t B, int64_t C, float* __restrict__ logp,
@@ -188,15 +233,32 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   }
 }
 
+constexpr int kAdamSmemEntries = 512;
+// adam_prepare for an optimizer that owns its step counter: t += 1, then the bias corrections of update t
+__global__ void adam_prepare_inc(int64_t* __restrict__ step_dev, float lr, float b1, float b2, float* __restrict__ coef) {
+  const int64_t ti = *step_dev + 1;
+  *step_dev = ti;
+  const double t = (double)ti;
+  coef[0] = lr / (float)(1.0 - pow((double)b1, t));
+  coef[1] = (float)sqrt(1.0 - pow((double)b2, t));
+}
+
 // The same update over a TABLE of tensors in one launch: block b works on 1024 consecutive elements of the tensor whose
 // [first_block, next first_block) range holds b (binary search over the table, read through L2 by every block).
 __global__ void __launch_bounds__(256) adam_multi_kernel(const lbbnn_adam_entry* __restrict__ table, int n_entries, float b1,
                                                          float b2, float eps, const float* __restrict__ coef) {
+  // the table's block ranges go through shared memory first: ONE L2 round trip for all of them, then the search -- eight
+  // dependent global loads per block (~4 us before the first useful load was issued) were half of this launch's 26 us
+  __shared__ int64_t s_first[kAdamSmemEntries];
+  const int ns = n_entries < kAdamSmemEntries ? n_entries : kAdamSmemEntries;
+  for (int i = threadIdx.x; i < ns; i += blockDim.x) s_first[i] = table[i].first_block;
+  __syncthreads();
   int lo = 0, hi = n_entries - 1;
   const int64_t blk = blockIdx.x;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
-    if (table[mid].first_block <= blk) lo = mid; else hi = mid - 1;
+    const int64_t fb = mid < ns ? s_first[mid] : table[mid].first_block;
+    if (fb <= blk) lo = mid; else hi = mid - 1;
   }
   const lbbnn_adam_entry e = table[lo];
   const float step_size = __ldg(coef) * e.lr_scale, bc2_sqrt = __ldg(coef + 1);
@@ -284,6 +346,21 @@ extern "C" int lbbnn_philox_normal_ex(float* out, int64_t n, const lbbnn_noise* 
   return check_launch("philox_noise");
 }
 
+extern "C" int lbbnn_nll_kl_objective_f32(const float* logits, const int64_t* target, int64_t B, int64_t C,
+                                          const float* const* kl_terms, int n_kl, float kl_scale, float* out2, float* dlogits,
+                                          lbbnn_stream s) {
+  LBBNN_REQUIRE(logits && target && out2 && B > 0 && C > 0, "bad logits/target/output");
+  LBBNN_REQUIRE(B <= 4096, "one-block objective: batch <= 4096 (got %lld)", (long long)B);
+  LBBNN_REQUIRE(n_kl >= 0 && n_kl <= kMaxKlTerms && (n_kl == 0 || kl_terms), "0 <= n_kl <= %d", kMaxKlTerms);
+  ObjectiveArgs a;
+  a.logits = logits; a.target = target; a.B = B; a.C = C; a.n_kl = n_kl; a.kl_scale = kl_scale; a.out = out2; a.dlogits = dlogits;
+  for (int i = 0; i < kMaxKlTerms; ++i) a.kl[i] = i < n_kl ? kl_terms[i] : nullptr;
+  for (int i = 0; i < n_kl; ++i) LBBNN_REQUIRE(a.kl[i], "NULL kl term %d", i);
+  const int threads = B >= 32 ? 1024 : (int)(32 * B);
+  objective_kernel<<<1, threads, 0, (cudaStream_t)s>>>(a);
+  return check_launch("nll_kl_objective");
+}
+
 extern "C" int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t B, int64_t C, float* logp,
                                         float* nll_sum, float* dlogits, float grad_scale, int64_t* step_inc,
                                         void* ws, size_t ws_bytes, lbbnn_stream s) {
@@ -342,6 +419,17 @@ extern "C" int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_ent
                 "bad argument");
   adam_prepare<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef_scratch);
   if (int rc = check_launch("adam_prepare")) return rc;
+  adam_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)s>>>(table_dev, n_entries, beta1, beta2, eps, coef_scratch);
+  return check_launch("adam_multi");
+}
+
+extern "C" int lbbnn_adam_multi_step_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
+                                         float beta1, float beta2, float eps, int64_t* step_dev, float* coef_scratch,
+                                         lbbnn_stream s) {
+  LBBNN_REQUIRE(table_dev && step_dev && coef_scratch && n_entries > 0 && total_blocks > 0 && total_blocks < (1LL << 31),
+                "bad argument");
+  adam_prepare_inc<<<1, 1, 0, (cudaStream_t)s>>>(step_dev, lr, beta1, beta2, coef_scratch);
+  if (int rc = check_launch("adam_prepare_inc")) return rc;
   adam_multi_kernel<<<(unsigned)total_blocks, 256, 0, (cudaStream_t)s>>>(table_dev, n_entries, beta1, beta2, eps, coef_scratch);
   return check_launch("adam_multi");
 }

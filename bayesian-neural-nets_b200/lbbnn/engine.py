@@ -9,6 +9,7 @@ sequence is captured once and replayed.  Parameters, gradients and Adam state li
 module keeps working (state_dict, eager forward) while the trainer owns the storage.
 """
 from ctypes import create_string_buffer as C_create_string_buffer
+from ctypes import c_void_p as C_void_p
 
 import os
 
@@ -630,7 +631,21 @@ class LRTTensorCoreTrainer:
             if self.fused_update:
                 self.dM = self.dV = None
         self.kl_next = torch.zeros(L, **f32)     # KL of the layers whose operands are carried from the previous update
-        self.carry_any = self.in_place and any(d["carry"] for d in self.tc)
+        # Layer 0's operands for the NEXT step from a prologue pass at the END of this one: the backward issues layer 1's
+        # input gradient and layer 0's dW (+ update) BEFORE layer 1's dW, so that the prologue of the freshly updated layer 0
+        # (and its KL term) runs on the side stream under layer 1's dW GEMM, and the next step's first forward GEMM no longer
+        # waits ~130 us for it.  M, V of layer 0 become derived state like the carried operands: refresh_operands().
+        # Opt-in (LBBNN_WIDE_CARRY0=1): on the power-capped B200s of this pool it measured 3.372 against 3.365 ms per step --
+        # the first GEMM does start ~100 us earlier, but the step is bound by its energy under the cap (sw_power_cap, SM
+        # clocks 1.69-1.72 of 1.965 GHz), not by that idle stretch.
+        self.side_carry0 = bool(self.in_place and self.side_prologue and self.fused_update and L >= 3 and
+                                not self.tc[0]["carry"] and not self.tc[1]["head"] and
+                                os.environ.get("LBBNN_WIDE_CARRY0", "0") == "1")
+        for li, d in enumerate(self.tc):
+            d["carry_side"] = self.side_carry0 and li == 0
+        self.carry_any = self.in_place and any(d["carry"] or d["carry_side"] for d in self.tc)
+        if self.carry_any:       # parameters loaded from outside after construction: re-derive the carried operands
+            net.register_load_state_dict_post_hook(lambda module, incompatible: self.refresh_operands())
         self.inject = inject_noise
         self.stats = torch.zeros(1 + L, **f32)
         nbytes = max([1 << 20, B // 8 * 4 + 1024] +
@@ -656,7 +671,7 @@ class LRTTensorCoreTrainer:
             return
         st, bf = K.current_stream(), torch.bfloat16
         for i, (l, d) in enumerate(zip(self.layers, self.tc)):
-            if not d["carry"]:
+            if not (d["carry"] or d["carry_side"]):
                 continue
             desc = K.make_layer(l.weight_mu.data, l.weight_rho.data, l.lambdal.data, l.bias_mu.data, l.bias_rho.data)
             K.check(K.lib.lbbnn_lrt_bf16_prologue(desc, l.cfg.priors, l.cfg.var_mode, K.ptr(d["M"], bf), K.ptr(d["V"], bf), None, None,
@@ -755,26 +770,29 @@ class LRTTensorCoreTrainer:
                                                           P(M32, True), P(V32, True), d["klws"].data_ptr(), d["klws"].numel(),
                                                           stream))
 
-        def kl_finalize(i, stream):
+        def kl_finalize(i, stream, out=None):
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
+            out = self.stats[1 + i:] if out is None else out
             K.check(lib.lbbnn_lrt_kl_finalize(d["klws"].data_ptr(), int(lib.lbbnn_lrt_bf16_prologue_kl_parts(fi, fo)), descs[i],
-                                              l.cfg.priors, self.stats[1 + i:].data_ptr(), stream))
+                                              l.cfg.priors, out.data_ptr(), stream))
 
-        if self.carry_any:                 # KL of the carried layers: computed by the previous step's update epilogues
-            self.stats[1:].copy_(self.kl_next); n += 1
+        carried = [d["carry"] or d["carry_side"] for d in self.tc]
+        for i in range(L):                 # KL of the carried layers: computed at the end of the previous step
+            if carried[i]:
+                self.stats[1 + i:2 + i].copy_(self.kl_next[i:i + 1]); n += 1
         ready = [None] * L
         kl_done = None
         if self.side_prologue:             # prologues up front on the side stream; each forward GEMM waits for its own M, V
             with torch.cuda.stream(side):  # only; the scalar KL reductions follow once every layer's operands are out
                 for i in range(L):
-                    if self.tc[i]["carry"]:
+                    if carried[i]:
                         continue
                     prologue(i, K.current_stream(), finalize=False); n += 1
                     ready[i] = torch.cuda.Event()
                     ready[i].record(side)
                 for i in range(L):
-                    if not self.tc[i]["carry"]:
+                    if not carried[i]:
                         kl_finalize(i, K.current_stream()); n += 1
                 kl_done = torch.cuda.Event()     # they read the biases: before the first bias update of the backward
                 kl_done.record(side)
@@ -783,8 +801,8 @@ class LRTTensorCoreTrainer:
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
             last = i == L - 1
-            if d["carry"]:
-                pass                        # M, V were written by the previous step's dW epilogue (or refresh_operands)
+            if carried[i]:
+                pass                        # M, V were written at the end of the previous step (or by refresh_operands)
             elif self.side_prologue:
                 main.wait_event(ready[i])
             else:
@@ -810,9 +828,26 @@ class LRTTensorCoreTrainer:
             return K.LayerGrads(*[t.data_ptr() for t in (l.weight_mu.grad, l.weight_rho.grad, l.lambdal.grad,
                                                          l.bias_mu.grad, l.bias_rho.grad)], None)
 
-        for i in reversed(range(L)):
+        def dx(i):
+            # ---- dx = dE M + 2 x (dS V) -> the layer below's dE, dS (+ bias partial sums) ----
+            l, d, p = self.layers[i], self.tc[i], self.tc[i - 1]
+            fi, fo = self.sizes[i]
+            if d["head"]:
+                M32, V32 = d["mv32"], d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
+                K.check(lib.lbbnn_tc_lrt_bwd_input_small(P(d["g32"]), P(d["dsf"]), P(M32), P(V32), B, fi, fo, P(p["act"], bf),
+                                                         P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf),
+                                                         P(p["dS"], bf), None, None, P(p["colsum"]), ws, wsn, st))
+                return 2
+            K.check(lib.lbbnn_tc_lrt_bwd_input_mn(P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
+                                                  P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
+                                                  P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"]), st))
+            return 1
+
+        def dw(i, dx_first=False):
+            """Layer i's bias sums, dM = dE^T x, dV = dS^T x^2 and the update.  Returns (launches, whether dx(i) was issued)."""
             l, d = self.layers[i], self.tc[i]
             fi, fo = self.sizes[i]
+            n, did_dx = 0, False
             xin, xin2 = (self.x_bf, self.x2_bf) if i == 0 else (self.tc[i - 1]["act"], self.tc[i - 1]["act2"])
             if i == L - 1:                 # fp32 upstream gradient of the loss head: stage dE, dS (+ K-major transposes for a
                 # <= 12-output head, whose (batch, out) rows are too short for a TMA pitch) and the bias sums
@@ -821,18 +856,10 @@ class LRTTensorCoreTrainer:
                 K.check(lib.lbbnn_colsum2(P(d["g32"]), P(d["dsf"]), 0, B, fo, P(d["colsum"]), ws, wsn, st)); n += 2
             elif d["colpart"] is not None:  # bias sums of this layer: partials written by the dX epilogue of the layer above
                 K.check(lib.lbbnn_tc_colsum_reduce(P(d["colpart"]), B, fo, P(d["colsum"]), st)); n += 1
-            def dx():
-                # ---- dx = dE M + 2 x (dS V) -> the layer below's dE, dS (+ bias partial sums) ----
-                p = self.tc[i - 1]
-                K.check(lib.lbbnn_tc_lrt_bwd_input_mn(P(d["dE"], bf), P(d["dS"], bf), P(d["M"], bf), P(d["V"], bf), B, fi, fo,
-                                                      P(p["act"], bf), P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX,
-                                                      P(p["dE"], bf), P(p["dS"], bf), P(p["colpart"]), st))
-
-            # ---- dM = dE^T x, dV = dS^T x^2 (+ update) ----
             if d["epi_update"]:            # chain rule + KL + Adam in the GEMM's epilogue; biases in a one-block kernel
                 if d["carry"]:
                     if i > 0:              # the epilogue below overwrites M, V with the next step's: their last reader goes first
-                        dx(); n += 1
+                        n += dx(i); did_dx = True
                     K.check(lib.lbbnn_tc_lrt_dw_adam_next(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), descs[i], B,
                                                           l.cfg.priors, l.cfg.var_mode, klg_post, self._adam_state(l),
                                                           P(d["M"], bf), P(d["V"], bf), d["klpart"].data_ptr(), st)); n += 2
@@ -844,45 +871,51 @@ class LRTTensorCoreTrainer:
                 if d["carry"]:             # next step's KL of this layer: weight partials + the (updated) bias term
                     K.check(lib.lbbnn_lrt_kl_finalize(d["klpart"].data_ptr(), d["klpart"].numel(), descs[i], l.cfg.priors,
                                                       self.kl_next[i:].data_ptr(), st)); n += 1
-                    continue
+                return n, did_dx
+            if self.fused_update:
+                dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
             else:
-                if self.fused_update:
-                    dM, dV = d["raw"][:fo * fi], d["raw"][fo * fi:2 * fo * fi]
-                else:
-                    dM, dV = self.dM, self.dV
+                dM, dV = self.dM, self.dV
 
-                def dw(stream):
-                    if d["head"]:          # A = dE^T, dS^T (out, batch) K-major; B = x, x^2 (batch, in) in place
-                        K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dET"], bf), P(d["dST"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
-                                                              0, 1, P(dM), P(dV), stream))
-                    else:
-                        K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
-                                                              1, 1, P(dM), P(dV), stream))
-                if self.fused_update and side is not None and self.overlap and d["head"] and i > 0:
-                    # the head's dW GEMM occupies 32 of 148 SMs: on the side stream, under the head's input-gradient kernel
-                    side.wait_stream(main)
-                    with torch.cuda.stream(side):
-                        dw(K.current_stream()); n += 1
+            def gemm(stream):
+                if d["head"]:          # A = dE^T, dS^T (out, batch) K-major; B = x, x^2 (batch, in) in place
+                    K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dET"], bf), P(d["dST"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
+                                                          0, 1, P(dM), P(dV), stream))
                 else:
-                    dw(st); n += 1
-                if self.fused_update and self.dp_sharded:
-                    self._sharded_layer_update(i, descs[i], main); n += 1
-                elif self.fused_update:
-                    self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
-                else:
-                    K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(dM), P(dV), P(d["colsum"]), l.cfg.priors, l.cfg.var_mode,
-                                                       K.FLAG_SAMPLE, None, klg_pre, grads_of(l), st)); n += 1
-            if i == 0:
-                continue
-            # ---- dx = dE M + 2 x (dS V) -> the layer below's dE, dS (+ bias partial sums) ----
-            p = self.tc[i - 1]
-            if d["head"]:
-                M32, V32 = d["mv32"], d["mv32"][K.lrt_mv_bytes(fi, fo) // 8:]
-                K.check(lib.lbbnn_tc_lrt_bwd_input_small(P(d["g32"]), P(d["dsf"]), P(M32), P(V32), B, fi, fo, P(p["act"], bf),
-                                                         P(p["dsf"]), K.FLAG_SAMPLE | K.FLAG_MASK_DX, P(p["dE"], bf),
-                                                         P(p["dS"], bf), None, None, P(p["colsum"]), ws, wsn, st)); n += 2
+                    K.check(lib.lbbnn_tc_dual_gemm_raw_ex(P(d["dE"], bf), P(d["dS"], bf), P(xin, bf), P(xin2, bf), fo, fi, B,
+                                                          1, 1, P(dM), P(dV), stream))
+            if self.fused_update and side is not None and self.overlap and d["head"] and i > 0:
+                # the head's dW GEMM occupies 32 of 148 SMs: on the side stream, under the head's input-gradient kernel
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    gemm(K.current_stream()); n += 1
             else:
-                dx(); n += 1
+                gemm(st); n += 1
+            if self.fused_update and self.dp_sharded:
+                self._sharded_layer_update(i, descs[i], main); n += 1
+            elif self.fused_update:
+                self._fused_layer_update(i, descs[i], dM, dV, main); n += 1
+            else:
+                K.check(lib.lbbnn_lrt_f32_finalize(descs[i], P(dM), P(dV), P(d["colsum"]), l.cfg.priors, l.cfg.var_mode,
+                                                   K.FLAG_SAMPLE, None, klg_pre, grads_of(l), st)); n += 1
+            return n, did_dx
+
+        for i in reversed(range(L)):
+            if self.side_carry0 and i == 1:
+                # layer 1's input gradient and layer 0's dW + update first; the freshly updated layer 0's operands and KL for
+                # the NEXT step on the side stream, under layer 1's dW GEMM (the step's last)
+                n += dx(1)
+                n += dw(0)[0]
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    prologue(0, K.current_stream(), finalize=False); n += 1
+                    kl_finalize(0, K.current_stream(), out=self.kl_next); n += 1
+                n += dw(1)[0]
+                break
+            k, did_dx = dw(i)
+            n += k
+            if i > 0 and not did_dx:
+                n += dx(i)
         if self.fused_update:
             if side is not None:
                 main.wait_stream(side)
@@ -1143,10 +1176,9 @@ class MultiTensorAdam:
             self._pending = rows
         else:
             self.table[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))
-        st = K.current_stream()
-        K.check(K.lib.lbbnn_counter_inc(K.ptr(self.t_dev, torch.int64), st))
-        K.check(K.lib.lbbnn_adam_multi_f32(self.table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0], self.betas[1],
-                                           self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
+        st = K.current_stream()        # t_dev += 1 and the bias corrections of update t in the first of the two launches
+        K.check(K.lib.lbbnn_adam_multi_step_f32(self.table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0],
+                                                self.betas[1], self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
 
     def finish_capture(self):
         if self._pending is not None:
@@ -1165,11 +1197,12 @@ class GraphedTrainer:
     optimizer is MultiTensorAdam by default: one launch instead of torch's ~40 multi_tensor_apply launches per step."""
 
     def __init__(self, net, batch_size, num_batches, objective="kl", lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
-                 in_features=None, optimizer=None, param_groups=None):
+                 in_features=None, optimizer=None, param_groups=None, fuse_objective=True):
         """optimizer: None = MultiTensorAdam (one launch for all parameters); "torch" = torch.optim.Adam(capturable=True);
         or any capturable torch optimizer instance over net.parameters().
         param_groups: torch.optim-style parameter groups with their own learning rates (the MF script's 33 groups,
-        MF:520-553: `lbbnn.mf.reference_param_groups(net)`), for the first two optimizer choices."""
+        MF:520-553: `lbbnn.mf.reference_param_groups(net)`), for the first two optimizer choices.
+        fuse_objective: objective="kl" through the one-launch loss head (_fused_objective) where the network allows it."""
         K.require_device()
         self.net, self.B, self.num_batches, self.objective = net, int(batch_size), num_batches, objective
         params = list(net.parameters())
@@ -1189,6 +1222,8 @@ class GraphedTrainer:
         else:
             self.opt = optimizer
         self.stats = torch.zeros(2, dtype=torch.float32, device=dev)      # [loss, nll]
+        self.fuse_objective = bool(fuse_objective)
+        self._dlogits = self._kl_grads = None
         self.stats_host = torch.zeros(2, dtype=torch.float32).pin_memory()
         self.x_host = torch.zeros(self.B, in_features, dtype=torch.float32).pin_memory()
         self.y_host = torch.zeros(self.B, dtype=torch.int64).pin_memory()
@@ -1208,18 +1243,44 @@ class GraphedTrainer:
             self.opt.finish_capture()
         self.warmup_steps = 3
 
+    def _fused_objective(self):
+        """objective="kl" on a network that exposes its logits and per-layer kl terms: ONE launch computes
+        loss = nll_loss(log_softmax(logits), y, 'sum') + sum(l.kl) / num_batches into self.stats and d loss / d logits
+        (lbbnn_nll_kl_objective_f32), and the backward starts at the logits and the kl terms with those gradients -- no
+        autograd nodes for log_softmax / nll_loss / the sum / the division.  Returns False when the network does not fit."""
+        net = self.net
+        if not (self.fuse_objective and hasattr(net, "_logits") and hasattr(net, "layers") and self.B <= 4096):
+            return False
+        logits = net._logits(self.x, sample=True)
+        kls = [l.kl for l in net.layers]
+        if not all(torch.is_tensor(k) and k.numel() == 1 and k.dtype == torch.float32 and k.requires_grad for k in kls) or \
+                len(kls) > 16 or logits.dtype != torch.float32 or not logits.is_contiguous():
+            raise K.LbbnnError("fused objective: the network's logits / kl terms are not what the kernel takes")
+        if self._dlogits is None or self._dlogits.shape != logits.shape:
+            self._dlogits = torch.empty_like(logits)
+            self._kl_grads = [torch.full_like(k, 1.0 / self.num_batches) for k in kls]      # d loss / d kl_i
+        ptrs = (C_void_p * len(kls))(*[k.data_ptr() for k in kls])
+        K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(self.y, torch.int64), logits.shape[0], logits.shape[1],
+                                                 ptrs, len(kls), 1.0 / self.num_batches, K.ptr(self.stats), K.ptr(self._dlogits),
+                                                 K.current_stream()))
+        torch.autograd.backward([logits] + kls, [self._dlogits] + self._kl_grads)
+        return True
+
     def _one_step(self):
         self.opt.zero_grad(set_to_none=True)
-        if self.objective == "elbo":
-            out = self.net.sample_elbo(self.x, self.y)
-            loss, nll = out[0], out[3]
+        if self.objective == "kl" and self._fused_objective():
+            self.opt.step()
         else:
-            logp = self.net(self.x, sample=True)
-            nll = torch.nn.functional.nll_loss(logp, self.y, reduction="sum")
-            loss = nll + self.net.kl() / self.num_batches
-        loss.backward()
-        self.opt.step()
-        self.stats.copy_(torch.stack([loss.detach(), nll.detach()]))
+            if self.objective == "elbo":
+                out = self.net.sample_elbo(self.x, self.y)
+                loss, nll = out[0], out[3]
+            else:
+                logp = self.net(self.x, sample=True)
+                nll = torch.nn.functional.nll_loss(logp, self.y, reduction="sum")
+                loss = nll + self.net.kl() / self.num_batches
+            loss.backward()
+            self.opt.step()
+            self.stats.copy_(torch.stack([loss.detach(), nll.detach()]))
         K.check(K.lib.lbbnn_counter_inc(K.ptr(self.step_dev, torch.int64), K.current_stream()))
 
     def step_device(self):

@@ -513,6 +513,13 @@ LBBNN_API int lbbnn_lrt_step_describe(const lbbnn_step* step, char* buf, size_t 
 LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
                                        float* logp, float* nll_sum, float* dlogits, float grad_scale,
                                        int64_t* step_inc, void* workspace, size_t workspace_bytes, lbbnn_stream s);
+/* The whole training objective of one minibatch in ONE launch (LRT:221-224, MNF:267-270):
+ *   nll = F.nll_loss(F.log_softmax(logits, 1), target, reduction='sum');  loss = nll + kl_scale * sum_i *kl_terms[i]
+ * out2 = [loss, nll]; dlogits (batch,classes; may be NULL) = softmax - onehot = d loss / d logits, and d loss / d kl_i is
+ * kl_scale.  kl_terms: HOST array of n_kl (<= 16) device pointers to the layers' scalar kl terms.  batch <= 4096. */
+LBBNN_API int lbbnn_nll_kl_objective_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
+                                         const float* const* kl_terms, int n_kl, float kl_scale, float* out2, float* dlogits,
+                                         lbbnn_stream s);
 
 /* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
  * step_dev: device int64 holding t, the 1-based index of THIS update; coef_scratch: 2 device floats
@@ -620,6 +627,11 @@ typedef struct lbbnn_adam_entry {
 LBBNN_API int lbbnn_adam_multi_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
                                    float beta1, float beta2, float eps, const int64_t* step_dev, float* coef_scratch,
                                    lbbnn_stream s);
+/* The same with the optimizer's step counter advanced by the call: *step_dev += 1 first (the 1-based index of this update),
+ * then the update -- one launch fewer than lbbnn_counter_inc + lbbnn_adam_multi_f32. */
+LBBNN_API int lbbnn_adam_multi_step_f32(const lbbnn_adam_entry* table_dev, int n_entries, int64_t total_blocks, float lr,
+                                        float beta1, float beta2, float eps, int64_t* step_dev, float* coef_scratch,
+                                        lbbnn_stream s);
 LBBNN_API int lbbnn_counter_inc(int64_t* counter, lbbnn_stream s);
 /* torch.optim.AdamW (variational_dropout.py:110): the update above preceded by param *= 1 - lr * weight_decay */
 LBBNN_API int lbbnn_adamw_f32(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

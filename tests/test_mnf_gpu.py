@@ -260,6 +260,52 @@ def test_graphed_trainer_replays_the_eager_step_with_fresh_noise(lb, kind):
     assert np.mean(nll[-10:]) < np.mean(nll[:10])                  # it trains
 
 
+def test_fused_objective_matches_the_torch_formulation(lb):
+    """lbbnn_nll_kl_objective_f32 (GraphedTrainer's loss head: nll_loss(log_softmax) + sum(kl) / NUM_BATCHES and
+    d loss / d logits in one launch, backward started at the logits and kl terms) against F.log_softmax / F.nll_loss /
+    net.kl() and loss.backward() on the SAME forward graph of the MNF network: loss, nll, and every parameter gradient
+    (MNF:267-272)."""
+    import ctypes
+    import torch.nn.functional as F
+    from lbbnn import _capi as K
+    torch.manual_seed(4)
+    rng = np.random.default_rng(9)
+    net = lb.mnf.BayesianNetwork((72, 40, 24, 10)).cuda().train()
+    x = C.t(rng.uniform(0, 1, size=(37, 72))).cuda()
+    y = torch.from_numpy(rng.integers(0, 10, size=(37,))).long().cuda()
+    logits = net._logits(x, sample=True)
+    kls = [l.kl for l in net.layers]
+    params = list(net.parameters())
+    nll = F.nll_loss(F.log_softmax(logits, dim=1), y, reduction="sum")
+    loss = nll + sum(kls) / C.NUM_BATCHES
+    ref = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
+    out, dlogits = torch.zeros(2, device="cuda"), torch.empty_like(logits)
+    ptrs = (ctypes.c_void_p * len(kls))(*[k.data_ptr() for k in kls])
+    K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(y, torch.int64), 37, 10, ptrs, len(kls),
+                                             1.0 / C.NUM_BATCHES, K.ptr(out), K.ptr(dlogits), K.current_stream()))
+    assert abs(out[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
+    assert abs(out[1].item() - nll.item()) <= 1e-6 * abs(nll.item())
+    for p in params:
+        p.grad = None
+    torch.autograd.backward([logits] + kls, [dlogits] + [torch.full_like(k, 1.0 / C.NUM_BATCHES) for k in kls])
+    n_checked = 0
+    for (name, p), r in zip(net.named_parameters(), ref):
+        if r is None:
+            assert p.grad is None, name
+            continue
+        assert C.rel_err(p.grad, r) < 2e-6, name
+        n_checked += 1
+    assert n_checked > 100                                          # weights, biases, q0 / r0 terms and both flows of 3 layers
+    # the trainer takes this path for the MNF network, and the torch formulation when asked to
+    tr = lb.GraphedTrainer(net, batch_size=37, num_batches=C.NUM_BATCHES, lr=0.0, objective="kl", in_features=72)
+    assert tr._dlogits is not None
+    tr_t = lb.GraphedTrainer(lb.mnf.BayesianNetwork((72, 40, 24, 10)).cuda(), batch_size=37, num_batches=C.NUM_BATCHES, lr=0.0,
+                             objective="kl", in_features=72, fuse_objective=False)
+    assert tr_t._dlogits is None
+    a, b = tr.step(x.cpu(), y.cpu()), tr_t.step(x.cpu(), y.cpu())
+    assert np.isfinite(a["loss"]) and np.isfinite(b["loss"]) and a["loss"] > a["nll"] > 0
+
+
 @pytest.mark.parametrize("D,O", [(784, 400), (50, 10), (33, 7)])
 def test_aux_kl_kernels_match_the_eager_formulation(lb, D, O):
     """log_q0 - log_rb (MNF:212-227) from the fused kernels (csrc/mnf_aux.cu) against the same terms written with torch

@@ -436,7 +436,7 @@ def test_wide_trainer_fused_update_matches_separate_passes(use_graph, carry):
                     getattr(l, k).copy_(v)
         tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-2, use_graph=use_graph,
                                         inject_noise=True, fused_update=fused, carry_operands=carry and fused)
-        assert tr.in_place and (not fused or tr.tc[0]["epi_update"]) and tr.carry_any == (carry and fused)
+        assert tr.in_place and (not fused or tr.tc[0]["epi_update"]) and tr.carry_any == ((carry or tr.side_carry0) and fused)
         for d, e in zip(tr.tc, case["eps"]):
             d["eps"].copy_(e)
         nets.append(net)
@@ -449,6 +449,46 @@ def test_wide_trainer_fused_update_matches_separate_passes(use_graph, carry):
         for k in case["layers"][0]:
             assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 5e-6, k
     assert C.rel_err(trs[1].exp_avg, trs[0].exp_avg) < 5e-6 and C.rel_err(trs[1].exp_avg_sq, trs[0].exp_avg_sq) < 5e-6
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_wide_trainer_side_carried_layer0_matches_the_default_order(use_graph, monkeypatch):
+    """LBBNN_WIDE_CARRY0=1: layer 1's input gradient and layer 0's dW + update are issued before layer 1's dW, and layer 0's
+    bf16 operands + KL for the NEXT step come from a prologue pass at the end of this one (side stream).  Same trajectory,
+    same per-step statistics as the default order over four steps; load_state_dict() re-derives the carried operands."""
+    import lbbnn
+    sizes = [(136, 264), (264, 72), (72, 10)]
+    B = 64
+    case = C.lrt_net_case(seed=93, batch=B, sizes=sizes)
+    nets, trs = [], []
+    for side in ("0", "1"):
+        monkeypatch.setenv("LBBNN_WIDE_CARRY0", side)
+        net = lbbnn.BayesianNetwork((136, 264, 72, 10)).cuda()
+        with torch.no_grad():
+            for l, p in zip(net.layers, case["layers"]):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-2, use_graph=use_graph,
+                                        inject_noise=True)
+        assert tr.side_carry0 == (side == "1") and tr.tc[0]["carry_side"] == (side == "1") and not tr.tc[1]["carry_side"]
+        for d, e in zip(tr.tc, case["eps"]):
+            d["eps"].copy_(e)
+        nets.append(net)
+        trs.append(tr)
+    for step in range(4):
+        if step == 2:            # parameters replaced from outside between two steps
+            sd = {k: v.clone() for k, v in nets[0].state_dict().items()}
+            for k in sd:
+                if k.endswith("weight_mu"):
+                    sd[k] = sd[k] * 1.01
+            for net in nets:
+                net.load_state_dict(sd)
+        outs = [tr.step(case["x"], case["y"]) for tr in trs]
+        assert abs(outs[0]["nll"] - outs[1]["nll"]) <= 1e-6 * abs(outs[0]["nll"]), step
+        assert abs(outs[0]["kl"] - outs[1]["kl"]) <= 1e-6 * abs(outs[0]["kl"]), step
+    for la, lb_ in zip(nets[0].layers, nets[1].layers):
+        for k in case["layers"][0]:
+            assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 1e-6, k
 
 
 # ---- 3xTF32 linear layer (csrc/tc_gemm_tf32.cu): fp32 accuracy on tcgen05 --------------------------------------------
