@@ -1142,6 +1142,51 @@ class MultiTensorAdam:
         self.coef = torch.zeros(2, dtype=torch.float32, device=dev)
         self.t_dev = torch.zeros(1, dtype=torch.int64, device=dev)      # 1-based index of the update being applied
         self._pending = None
+        # early / late split (set_late_params): see there
+        self._late_ids, self._early_n = None, 0
+        self._early_table = self._early_stream = self._early_pending = None
+        self._armed, self._early_seen, self._early_events, self._early_done = False, 0, [], False
+
+    def set_late_params(self, late_params):
+        """Update everything BUT `late_params` as soon as its gradients are final, in the middle of the backward: every
+        other parameter gets a post-accumulate-grad hook that records an event on the stream its gradient was accumulated
+        on; when the last of them has fired, the update of that whole group is launched on a private stream that waits for
+        exactly those events, and step() only has the late group left.  For the MNF network the late group is the first
+        layer's z flow and q0 parameters, whose gradients come out of the LAST node of the backward (a 34 us cluster launch
+        at the end of the critical path): the 23 us update of the other 3.3 M parameters runs under it instead of after it.
+        The group is the same on every step; a step in which some early parameter gets no gradient falls back to the one
+        launch in step()."""
+        late = {id(p) for p in late_params}
+        unknown = late - {id(p) for p in self.params}
+        if unknown:
+            raise ValueError("late parameters must belong to the optimizer")
+        early = [p for p in self.params if id(p) not in late]
+        if not early or not late:
+            return
+        self._late_ids, self._early_n = late, len(early)
+        dev = self.params[0].device
+        self._early_table = torch.zeros(len(early), 7, dtype=torch.int64, device=dev)
+        self._early_stream = torch.cuda.Stream(device=dev)
+        for p in early:
+            p.register_post_accumulate_grad_hook(self._on_grad)
+
+    def _on_grad(self, p):
+        if not self._armed or self._early_done:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._early_events.append(ev)
+        self._early_seen += 1
+        if self._early_seen < self._early_n:
+            return
+        rows, blocks = self._rows(lambda q: id(q) not in self._late_ids)
+        if len(rows) != self._early_n:
+            return
+        for ev in self._early_events:
+            self._early_stream.wait_event(ev)
+        with torch.cuda.stream(self._early_stream):
+            self._launch(rows, blocks, self._early_table, "_early_pending", advance=True)
+        self._early_done = True
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -1149,13 +1194,17 @@ class MultiTensorAdam:
                 p.grad = None
             elif p.grad is not None:
                 p.grad.zero_()
+        # the early group's hooks count from here; gradients that are zeroed in place accumulate in several pieces, so only
+        # the set_to_none form (one accumulation per parameter and backward) arms them
+        self._armed = self._late_ids is not None and bool(set_to_none)
+        self._early_seen, self._early_events, self._early_done = 0, [], False
 
-    def _rows(self):
+    def _rows(self, keep=None):
         import struct
         rows, blocks = [], 0
         for p, off, sc in zip(self.params, self.offs, self.lr_scale):
             g = p.grad
-            if g is None:
+            if g is None or (keep is not None and not keep(p)):
                 continue
             if g.dtype != torch.float32 or not g.is_contiguous() or not p.is_contiguous():
                 raise K.LbbnnError("MultiTensorAdam needs contiguous fp32 parameters and gradients")
@@ -1166,24 +1215,41 @@ class MultiTensorAdam:
             blocks += (n + 1023) // 1024
         return rows, blocks
 
+    def _launch(self, rows, blocks, table, pending_attr, advance):
+        if torch.cuda.is_current_stream_capturing():
+            prev = getattr(self, pending_attr)
+            if prev is not None and len(prev) != len(rows):
+                raise K.LbbnnError("the set of parameters with gradients changed during capture")
+            setattr(self, pending_attr, rows)
+        else:
+            table[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))
+        st = K.current_stream()
+        if advance:                    # t_dev += 1 and the bias corrections of update t in the first of the two launches
+            K.check(K.lib.lbbnn_adam_multi_step_f32(table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0],
+                                                    self.betas[1], self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
+        else:                          # same update index: the early group's launch has advanced it
+            K.check(K.lib.lbbnn_adam_multi_f32(table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0], self.betas[1],
+                                               self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
+
     def step(self):
-        rows, blocks = self._rows()
+        early_done, self._armed = self._early_done, False
+        self._early_done = False
+        if early_done:                 # the early group is being updated on its own stream: the late group after it
+            torch.cuda.current_stream().wait_stream(self._early_stream)
+            rows, blocks = self._rows(lambda q: id(q) in self._late_ids)
+        else:
+            rows, blocks = self._rows()
         if not rows:
             return
-        if torch.cuda.is_current_stream_capturing():
-            if self._pending is not None and len(self._pending) != len(rows):
-                raise K.LbbnnError("the set of parameters with gradients changed during capture")
-            self._pending = rows
-        else:
-            self.table[:len(rows)].copy_(torch.tensor(rows, dtype=torch.int64))
-        st = K.current_stream()        # t_dev += 1 and the bias corrections of update t in the first of the two launches
-        K.check(K.lib.lbbnn_adam_multi_step_f32(self.table.data_ptr(), len(rows), blocks, self.base_lr, self.betas[0],
-                                                self.betas[1], self.eps, K.ptr(self.t_dev, torch.int64), K.ptr(self.coef), st))
+        self._launch(rows, blocks, self.table, "_pending", advance=not early_done)
 
     def finish_capture(self):
         if self._pending is not None:
             self.table[:len(self._pending)].copy_(torch.tensor(self._pending, dtype=torch.int64))
             self._pending = None
+        if self._early_pending is not None:
+            self._early_table[:len(self._early_pending)].copy_(torch.tensor(self._early_pending, dtype=torch.int64))
+            self._early_pending = None
 
 
 class GraphedTrainer:
@@ -1216,6 +1282,8 @@ class GraphedTrainer:
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         if optimizer is None:
             self.opt = MultiTensorAdam(param_groups if param_groups is not None else params, lr=lr, betas=betas, eps=eps)
+            if hasattr(net, "late_grad_params") and os.environ.get("LBBNN_ADAM_SPLIT", "1") == "1":
+                self.opt.set_late_params(net.late_grad_params())
         elif isinstance(optimizer, str) and optimizer == "torch":
             self.opt = torch.optim.Adam(param_groups if param_groups is not None else params, lr=lr, betas=betas, eps=eps,
                                         capturable=True)

@@ -134,8 +134,8 @@ def _flow_grad_table(flow, params, gbuf):
 class _ZDraw(torch.autograd.Function):
     """The z0 draw (MNF:183-185) and the z flow (MNF:186-189) of one layer call, both rows in ONE launch each: row 0 is the
     activation's z (the last batch row's draw), row 1 -- training / calculate_log_probs -- the KL branch's
-    own sample_z() (MNF:210).  Returns (z_k, z2, log_det_q of row 1, z0 row 1 = what the reference leaves in self.z)
-    or, without the KL row, (z_k, z0 row 0)."""
+    own sample_z() (MNF:210).  Returns (z_k, z2, log_det_q of row 1, z0 row 1 = what the reference leaves in self.z,
+    aliases of q0_mean and q0_log_var for the KL branch) or, without the KL row, (z_k, z0 row 0)."""
 
     @staticmethod
     def forward(ctx, meta, q0m, q0lv, *zp):
@@ -174,7 +174,9 @@ class _ZDraw(torch.autograd.Function):
             z_row = z0[:1]
             ctx.mark_non_differentiable(z_row)
             return zs[0], z_row
-        return zs[0], zs[1], ld[1:], z0[1:2]
+        # q0_mean / q0_log_var for the KL branch pass through this node: their gradients from there arrive HERE and are
+        # added inside mnf_draw_bwd (aux_d_q0_*), instead of as two accumulation kernels at the very end of the backward
+        return zs[0], zs[1], ld[1:], z0[1:2], q0m.view_as(q0m), q0lv.view_as(q0lv)
 
     @staticmethod
     def backward(ctx, d_zk, *rest):
@@ -194,9 +196,9 @@ class _ZDraw(torch.autograd.Function):
         d_zk = cz(d_zk)
         if not want_kl:
             rows = d_zk.reshape(1, D) if d_zk is not None else torch.zeros(1, D, **f32)
-            dld, d_z0row = None, None
+            dld, d_z0row, d_q0m_kl, d_q0lv_kl = None, None, None, None
         else:
-            d_z2, d_ld, d_z0row = (cz(t) for t in rest)
+            d_z2, d_ld, d_z0row, d_q0m_kl, d_q0lv_kl = (cz(t) for t in rest)
             rows, dld = torch.empty(2, D, **f32), torch.empty(2, **f32)
             if d_ld is None:
                 dld.zero_()
@@ -204,7 +206,8 @@ class _ZDraw(torch.autograd.Function):
                                              K.ptr(d_zk, allow_none=True), K.ptr(d_z2, allow_none=True), None, D, K.ptr(rows), st))
         K.check(K.lib.lbbnn_flow_bwd(flow, gt, R, K.ptr(masks, allow_none=True), K.make_noise(None, *key), K.ptr(rows),
                                      K.ptr(dld, allow_none=True), K.ptr(save), K.ptr(dz0), st))
-        K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), R, D, 1 if want_kl else -1, None, None,
+        K.check(K.lib.lbbnn_mnf_draw_bwd(K.ptr(q0lv), K.ptr(eps), K.ptr(dz0), R, D, 1 if want_kl else -1,
+                                         K.ptr(d_q0m_kl, allow_none=True), K.ptr(d_q0lv_kl, allow_none=True),
                                          K.ptr(d_z0row, allow_none=True), K.ptr(d_mean), K.ptr(d_lv), st))
         gzs = gz[0] + gz[1] if R == 2 else gz[0]
         return (None, d_mean, d_lv, *[gzs[offs[j]:offs[j + 1]].view_as(zp[j]) for j in range(len(zp))])
@@ -348,15 +351,22 @@ class BayesianLinear(nn.Module):
     def _draw(self, want_kl, nz):
         """z0 draw + z flow of this call (one autograd node); returns the handle _kl_branch() continues from."""
         out = _ZDraw.apply((self, bool(want_kl), nz), self.q0_mean, self.q0_log_var, *self.z_flow._params())
-        self.z = out[-1]                                                # sample_z() leaves its last draw in self.z
+        self.z = out[3] if want_kl else out[-1]                         # sample_z() leaves its last draw in self.z
         return out
 
     def _kl_branch(self, drawn, nz):
         """The layer's kl from the KL row of _draw() (one autograd node)."""
-        _, z2, ld_q, z0row = drawn
-        return _KLBranch.apply((self, nz), self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho,
-                               self.q0_mean, self.q0_log_var, self.r0_c, self.r0_b1, self.r0_b2, z2, ld_q, z0row,
-                               *self.r_flow._params())
+        _, z2, ld_q, z0row, q0_mean, q0_log_var = drawn
+        return _KLBranch.apply((self, nz), *self._lrt_params(), q0_mean, q0_log_var, self.r0_c, self.r0_b1, self.r0_b2,
+                               z2, ld_q, z0row, *self.r_flow._params())
+
+    def _lrt_params(self):
+        """weight_mu, weight_rho, lambdal, bias_mu, bias_rho as the KL branch and the activation kernels take them: the
+        parameters themselves, or the aliases BayesianNetwork._logits made on the layer's accumulation stream -- the two
+        gradient contributions of each (KL branch, activation path) are then summed THERE, not on the streams that carry the
+        flows' backward."""
+        shared = getattr(self, "_shared", None)
+        return shared if shared is not None else (self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho)
 
     def _prepare(self, want_kl, nz):
         """Everything of forward() that does not depend on the input batch: the z flow on the live rows, and (training /
@@ -367,7 +377,7 @@ class BayesianLinear(nn.Module):
     def _activation(self, input, z_k, sample_branch, nz, relu=False, mask_dx=False):
         self._calls += 1
         self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
-        act, _ = _LRTFunction.apply(input, self.weight_mu, self.weight_rho, self.lambdal, self.bias_mu, self.bias_rho, z_k,
+        act, _ = _LRTFunction.apply(input, *self._lrt_params(), z_k,
                                     nz.get("eps"), self.cfg, sample_branch, False, self.last_noise_key, relu, mask_dx)
         return act
 
@@ -387,6 +397,7 @@ class BayesianNetwork(nn.Module):
             setattr(self, f"l{n}", BayesianLinear(i, o, num_transforms=num_transforms, **layer_kwargs))
         self._names = [f"l{n}" for n in range(1, len(sizes))]
         self._streams = None
+        self._acc_streams = None
 
     @property
     def layers(self):
@@ -408,8 +419,20 @@ class BayesianNetwork(nn.Module):
         cur = torch.cuda.current_stream()
         if self._streams is None or self._streams[0].device != x.device:
             self._streams = [torch.cuda.Stream(device=x.device) for _ in ls]
+            self._acc_streams = [torch.cuda.Stream(device=x.device) for _ in ls]
         for s in self._streams:
             s.wait_stream(cur)
+        # One alias per shared parameter and layer, made on that layer's ACCUMULATION stream: autograd sums the KL branch's
+        # and the activation path's gradients at the alias node, i.e. on that stream.  Summed at the leaf they ran on the
+        # layer's flow stream between the activation path's finalize and the z flow's backward -- five dependent ~3 us
+        # launches on the step's critical tail (profiles/r02_timeline_mnf.txt).  LBBNN_MNF_SHARE=0 keeps the leaf accumulation.
+        share = torch.is_grad_enabled() and os.environ.get("LBBNN_MNF_SHARE", "1") == "1"
+        for l, sa in zip(ls, self._acc_streams):
+            l._shared = None
+            if share and (l.training or calculate_log_probs):
+                sa.wait_stream(cur)
+                with torch.cuda.stream(sa):
+                    l._shared = tuple(p.view_as(p) for p in (l.weight_mu, l.weight_rho, l.lambdal, l.bias_mu, l.bias_rho))
         # issue order (same dependency graph either way; same-box A/B of the captured step, ms: 0.32-0.335 against 0.366-0.368
         # when each layer's KL branch is issued after that layer's activation kernels): every layer's draw + KL branch first
         interleave = os.environ.get("LBBNN_MNF_ORDER") == "layer"
@@ -432,11 +455,21 @@ class BayesianNetwork(nn.Module):
             if interleave:
                 with torch.cuda.stream(s):
                     l.kl = l._kl_branch(drawn[i][0], nz) if (l.training or calculate_log_probs) else 0
-        for l, s in zip(ls, self._streams):
+        for l, s, sa in zip(ls, self._streams, self._acc_streams):
             cur.wait_stream(s)
+            if l._shared is not None:
+                cur.wait_stream(sa)
+            l._shared = None
             if torch.is_tensor(l.kl):
                 l.kl.record_stream(cur)
         return x
 
     def kl(self):
         return sum(l.kl for l in self.layers)
+
+    def late_grad_params(self):
+        """The parameters whose gradients are produced by the LAST node of a backward pass -- the first layer's z draw + z
+        flow (it waits for that layer's dz from the activation path, which finishes last): MultiTensorAdam.set_late_params
+        updates everything else while that node runs."""
+        l = self.layers[0]
+        return [l.q0_mean, l.q0_log_var, *l.z_flow.parameters()]

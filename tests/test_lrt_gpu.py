@@ -337,6 +337,68 @@ def test_multi_tensor_adam_matches_torch_adam(lb):
     assert torch.equal(unused.detach(), u0) and int(ours.t_dev) == 5
 
 
+def test_multi_tensor_adam_early_group_updates_during_the_backward(lb):
+    """set_late_params: every parameter outside the late group is updated from inside loss.backward() (post-accumulate hooks
+    -> one launch on a private stream once the last early gradient is final), the late group by step(); the trajectory is
+    torch.optim.Adam's, eagerly and as a captured CUDA graph, and a backward that skips an early parameter falls back to the
+    single launch."""
+    torch.manual_seed(7)
+    shapes = [(300, 70), (70,), (1025,), (64, 70), (3,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device="cuda")) for s in shapes]
+    qs = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    x = torch.randn(5, 300, device="cuda")
+
+    def loss_of(t, scale):                       # t[2] and t[4] are used twice / last: several accumulation patterns
+        h = torch.tanh(x @ t[0] + t[1])
+        return scale * ((h @ t[3].T).sum() + (t[2] ** 2).sum() + t[2].sum() * t[4].sum() + (t[4] ** 3).sum())
+
+    ours = lb.MultiTensorAdam(ps, lr=1e-2)
+    ours.set_late_params([ps[2], ps[4]])
+    ref = torch.optim.Adam(qs, lr=1e-2)
+    for step in range(4):
+        ours.zero_grad()
+        ref.zero_grad()
+        loss_of(ps, 10.0 ** (step - 1)).backward()
+        assert ours._early_done                                      # launched from the hooks, before step()
+        loss_of(qs, 10.0 ** (step - 1)).backward()
+        ours.step()
+        ref.step()
+        torch.cuda.synchronize()
+        for p, q in zip(ps, qs):
+            assert C.rel_err(p.detach(), q.detach()) < 1e-6, step
+    assert int(ours.t_dev) == 4
+    # captured: the hooks' events and the private stream become graph branches
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    ours.zero_grad()
+    with torch.cuda.graph(g, stream=s):
+        ours.zero_grad()
+        loss_of(ps, 1.0).backward()
+        ours.step()
+    ours.finish_capture()
+    for _ in range(3):
+        g.replay()
+        ref.zero_grad()
+        loss_of(qs, 1.0).backward()
+        ref.step()
+    torch.cuda.synchronize()
+    for p, q in zip(ps, qs):
+        assert C.rel_err(p.detach(), q.detach()) < 2e-6
+    assert int(ours.t_dev) == 7
+    # an early parameter without gradient: no early launch, step() updates what has one
+    ours.zero_grad()
+    ref.zero_grad()
+    ((ps[0] ** 2).sum() + ps[2].sum()).backward()
+    ((qs[0] ** 2).sum() + qs[2].sum()).backward()
+    assert not ours._early_done
+    ours.step()
+    ref.step()
+    for i in (0, 2):             # (the optimizer counts updates globally, torch per parameter: compare the updated ones)
+        assert C.rel_err(ps[i].detach(), qs[i].detach()) < 2e-6
+    assert int(ours.t_dev) == 8
+
+
 def test_multi_tensor_adam_parameter_groups_match_torch_adam(lb):
     """f1: per-group learning rates.  The MF script's 33 parameter groups (MF:520-553: 1e-4 weights / biases, 1e-3 pa / pb,
     1e-5 Gamma hyper-parameters, 0.1 lambdal) through MultiTensorAdam (per-row lr in the device table) against
