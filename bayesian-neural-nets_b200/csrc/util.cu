@@ -113,19 +113,25 @@ struct ObjectiveArgs {
 __global__ void __launch_bounds__(1024) objective_kernel(const ObjectiveArgs a) {
   __shared__ float red[32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  // G lanes per row: 4 / 2 / 1 rows per warp pass for <= 8 / <= 16 / more classes (a 100 x 10 batch is one pass of the block,
+  // not four dependent load -> max -> exp -> sum -> log chains per warp)
+  const int G = a.C <= 8 ? 8 : (a.C <= 16 ? 16 : 32);
+  const int gl = lane & (G - 1), rows_per_pass = nw * (32 / G);
   float local = 0.f;
-  for (int64_t b = warp; b < a.B; b += nw) {
-    const float* row = a.logits + b * a.C;
+  for (int64_t b0 = 0; b0 < a.B; b0 += rows_per_pass) {             // uniform trip count: the shuffles below are warp-wide
+    const int64_t b = b0 + warp * (32 / G) + lane / G;
+    const bool ok = b < a.B;
+    const float* row = a.logits + (ok ? b : 0) * a.C;
     float mx = -INFINITY;
-    for (int64_t c = lane; c < a.C; c += 32) mx = fmaxf(mx, row[c]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int64_t c = gl; c < a.C; c += G) mx = fmaxf(mx, row[c]);
+    for (int o = G >> 1; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float se = 0.f;
-    for (int64_t c = lane; c < a.C; c += 32) se += expf(row[c] - mx);
-    se = warp_sum(se);
+    for (int64_t c = gl; c < a.C; c += G) se += expf(row[c] - mx);
+    for (int o = G >> 1; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
     const float lse = mx + logf(se);
+    if (!ok) continue;
     const int64_t t = a.target[b];
-    for (int64_t c = lane; c < a.C; c += 32) {
+    for (int64_t c = gl; c < a.C; c += G) {
       const float lp = row[c] - lse;
       if (a.dlogits) a.dlogits[b * a.C + c] = expf(lp) - (c == t ? 1.0f : 0.0f);
       if (c == t) local -= lp;

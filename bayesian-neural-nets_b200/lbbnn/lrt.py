@@ -37,6 +37,20 @@ class LayerConfig:
         self.var_mode = {"reference": K.VAR_REFERENCE, "exact": K.VAR_EXACT}[var_mode]
 
 
+_zero_scalars = {}
+
+
+def _zero_scalar(dev):
+    """A never-written 0-dim zero (the kl output of a call that was not asked for it) -- no fill launch per call."""
+    t = _zero_scalars.get(dev.index)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise K.LbbnnError("constant buffer would be created during CUDA-graph capture; run one eager step first")
+        t = torch.zeros((), dtype=torch.float32, device=dev)
+        _zero_scalars[dev.index] = t
+    return t
+
+
 class _LRTFunction(torch.autograd.Function):
     """activations, kl = f(x, mu, rho, lambda, b_mu, b_rho[, z]); forward LRT:166-196, backward SURVEY §3.5."""
 
@@ -63,7 +77,12 @@ class _LRTFunction(torch.autograd.Function):
         flags = (K.FLAG_SAMPLE if sample else 0) | (K.FLAG_KL if want_kl else 0) | (K.FLAG_RELU if relu else 0)
         act = torch.empty(B, out_f, dtype=torch.float32, device=x.device)
         dsf = torch.empty(B, out_f, dtype=torch.float32, device=x.device) if sample else None
-        kl = torch.zeros((), dtype=torch.float32, device=x.device)
+        ctx.set_materialize_grads(False)           # an unused output's gradient arrives as None, not as a zero-fill launch
+        if want_kl:
+            kl = torch.zeros((), dtype=torch.float32, device=x.device)
+        else:                                      # not computed (MNF layers: the KL branch is its own node): a shared constant
+            kl = _zero_scalar(x.device)
+            ctx.mark_non_differentiable(kl)
         # keep M,V for the input-gradient GEMM of the backward (else it recomputes them)
         mv = (torch.empty(K.lrt_mv_bytes(in_f, out_f) // 4, dtype=torch.float32, device=x.device)
               if ctx.needs_input_grad[0] else None)
