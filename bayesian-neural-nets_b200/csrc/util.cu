@@ -96,7 +96,9 @@ __global__ void logsoftmax_nll_kernel(const float* __restrict__ logits, const in
 }
 
 // The whole objective of a minibatch (LRT:221-224, MNF:267-270) in one block: the kernel above plus
-//   loss = nll + kl_scale * sum_i kl_i        out = [loss, nll]
+//   loss = nll + sum_i scale_i term_i         out = [loss, nll]
+// (scale_i = 1 / NUM_BATCHES for the layers' kl; the MF script's ELBO, MF:316-318, is the same with its log q terms at
+// + 1 / NUM_BATCHES and its log prior terms at - 1 / NUM_BATCHES)
 // so that a module-level training step (GraphedTrainer) goes from the logits straight to d loss / d logits: the torch
 // formulation (log_softmax, nll_loss, the sum over the layers' kl, / NUM_BATCHES, + and their backward nodes) was ~20
 // launches of 1-6 us each on the critical path between the forward and the backward.
@@ -106,8 +108,8 @@ struct ObjectiveArgs {
   const int64_t* target;
   int64_t B, C;
   const float* kl[kMaxKlTerms];
+  float scale[kMaxKlTerms];
   int n_kl;
-  float kl_scale;
   float *out, *dlogits;
 };
 __global__ void __launch_bounds__(1024) objective_kernel(const ObjectiveArgs a) {
@@ -140,8 +142,8 @@ __global__ void __launch_bounds__(1024) objective_kernel(const ObjectiveArgs a) 
   const float nll = block_sum(local, red);
   if (threadIdx.x == 0) {
     float kl = 0.f;
-    for (int i = 0; i < a.n_kl; ++i) kl += *a.kl[i];                     // in the order of sum(l.kl for l in layers)
-    a.out[0] = nll + kl * a.kl_scale;
+    for (int i = 0; i < a.n_kl; ++i) kl = fmaf(a.scale[i], *a.kl[i], kl);   // in the order of sum(l.kl for l in layers)
+    a.out[0] = nll + kl;
     a.out[1] = nll;
   }
 }
@@ -353,14 +355,17 @@ extern "C" int lbbnn_philox_normal_ex(float* out, int64_t n, const lbbnn_noise* 
 }
 
 extern "C" int lbbnn_nll_kl_objective_f32(const float* logits, const int64_t* target, int64_t B, int64_t C,
-                                          const float* const* kl_terms, int n_kl, float kl_scale, float* out2, float* dlogits,
-                                          lbbnn_stream s) {
+                                          const float* const* kl_terms, const float* term_scales, int n_kl, float kl_scale,
+                                          float* out2, float* dlogits, lbbnn_stream s) {
   LBBNN_REQUIRE(logits && target && out2 && B > 0 && C > 0, "bad logits/target/output");
   LBBNN_REQUIRE(B <= 4096, "one-block objective: batch <= 4096 (got %lld)", (long long)B);
   LBBNN_REQUIRE(n_kl >= 0 && n_kl <= kMaxKlTerms && (n_kl == 0 || kl_terms), "0 <= n_kl <= %d", kMaxKlTerms);
   ObjectiveArgs a;
-  a.logits = logits; a.target = target; a.B = B; a.C = C; a.n_kl = n_kl; a.kl_scale = kl_scale; a.out = out2; a.dlogits = dlogits;
-  for (int i = 0; i < kMaxKlTerms; ++i) a.kl[i] = i < n_kl ? kl_terms[i] : nullptr;
+  a.logits = logits; a.target = target; a.B = B; a.C = C; a.n_kl = n_kl; a.out = out2; a.dlogits = dlogits;
+  for (int i = 0; i < kMaxKlTerms; ++i) {
+    a.kl[i] = i < n_kl ? kl_terms[i] : nullptr;
+    a.scale[i] = i < n_kl ? kl_scale * (term_scales ? term_scales[i] : 1.0f) : 0.f;
+  }
   for (int i = 0; i < n_kl; ++i) LBBNN_REQUIRE(a.kl[i], "NULL kl term %d", i);
   const int threads = B >= 32 ? 1024 : (int)(32 * B);
   objective_kernel<<<1, threads, 0, (cudaStream_t)s>>>(a);

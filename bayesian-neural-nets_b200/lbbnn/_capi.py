@@ -216,7 +216,7 @@ SIGNATURES = {
     "lbbnn_adam_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_adam_multi_f32": (_INT, [_P, _INT, _I64, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_adam_multi_step_f32": (_INT, [_P, _INT, _I64, _F, _F, _F, _F, _P, _P, _P]),
-    "lbbnn_nll_kl_objective_f32": (_INT, [_P, _P, _I64, _I64, _P, _INT, _F, _P, _P, _P]),
+    "lbbnn_nll_kl_objective_f32": (_INT, [_P, _P, _I64, _I64, _P, _P, _INT, _F, _P, _P, _P]),
     "lbbnn_counter_inc": (_INT, [_P, _P]),
     "lbbnn_adamw_f32": (_INT, [_P, _P, _P, _P, _I64, _F, _F, _F, _F, _F, _P, _P, _P]),
     "lbbnn_vd_workspace_bytes": (_SZ, [_I64, _I64, _I64]),

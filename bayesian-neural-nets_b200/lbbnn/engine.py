@@ -10,6 +10,7 @@ module keeps working (state_dict, eager forward) while the trainer owns the stor
 """
 from ctypes import create_string_buffer as C_create_string_buffer
 from ctypes import c_void_p as C_void_p
+from ctypes import c_float as C_float
 
 import os
 
@@ -1312,31 +1313,41 @@ class GraphedTrainer:
         self.warmup_steps = 3
 
     def _fused_objective(self):
-        """objective="kl" on a network that exposes its logits and per-layer kl terms: ONE launch computes
-        loss = nll_loss(log_softmax(logits), y, 'sum') + sum(l.kl) / num_batches into self.stats and d loss / d logits
-        (lbbnn_nll_kl_objective_f32), and the backward starts at the logits and the kl terms with those gradients -- no
-        autograd nodes for log_softmax / nll_loss / the sum / the division.  Returns False when the network does not fit."""
+        """The objective through ONE launch (lbbnn_nll_kl_objective_f32) where the network exposes its logits and its
+        per-layer scalar terms: loss = nll_loss(log_softmax(logits), y, 'sum') + sum_i scale_i term_i into self.stats together
+        with d loss / d logits, and the backward started at the logits and the terms with those (constant) gradients -- no
+        autograd nodes for log_softmax / nll_loss / the sums / the division (~20 launches of 1-6 us on the critical path).
+        objective="kl" (MNF:267-270): terms = the layers' kl at 1 / num_batches.  objective="elbo" (MF:285-319 with
+        samples = 1): terms = the layers' log q at + 1 / num_batches and log prior at - 1 / num_batches.
+        Returns False when the network does not fit (the torch formulation runs instead)."""
         net = self.net
         if not (self.fuse_objective and hasattr(net, "_logits") and hasattr(net, "layers") and self.B <= 4096):
             return False
-        logits = net._logits(self.x, sample=True)
-        kls = [l.kl for l in net.layers]
-        if not all(torch.is_tensor(k) and k.numel() == 1 and k.dtype == torch.float32 and k.requires_grad for k in kls) or \
-                len(kls) > 16 or logits.dtype != torch.float32 or not logits.is_contiguous():
-            raise K.LbbnnError("fused objective: the network's logits / kl terms are not what the kernel takes")
+        if self.objective == "elbo":
+            if not hasattr(net, "_elbo_terms"):
+                return False
+            logits, terms, signs = net._elbo_terms(self.x)
+        else:
+            logits = net._logits(self.x, sample=True)
+            terms = [l.kl for l in net.layers]
+            signs = [1.0] * len(terms)
+        if not all(torch.is_tensor(k) and k.numel() == 1 and k.dtype == torch.float32 and k.requires_grad for k in terms) or \
+                len(terms) > 16 or logits.dtype != torch.float32 or not logits.is_contiguous():
+            raise K.LbbnnError("fused objective: the network's logits / scalar terms are not what the kernel takes")
         if self._dlogits is None or self._dlogits.shape != logits.shape:
             self._dlogits = torch.empty_like(logits)
-            self._kl_grads = [torch.full_like(k, 1.0 / self.num_batches) for k in kls]      # d loss / d kl_i
-        ptrs = (C_void_p * len(kls))(*[k.data_ptr() for k in kls])
+            self._kl_grads = [torch.full_like(k, sg / self.num_batches) for k, sg in zip(terms, signs)]    # d loss / d term_i
+        ptrs = (C_void_p * len(terms))(*[k.data_ptr() for k in terms])
+        scales = (C_float * len(terms))(*signs)
         K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(self.y, torch.int64), logits.shape[0], logits.shape[1],
-                                                 ptrs, len(kls), 1.0 / self.num_batches, K.ptr(self.stats), K.ptr(self._dlogits),
-                                                 K.current_stream()))
-        torch.autograd.backward([logits] + kls, [self._dlogits] + self._kl_grads)
+                                                 ptrs, scales, len(terms), 1.0 / self.num_batches, K.ptr(self.stats),
+                                                 K.ptr(self._dlogits), K.current_stream()))
+        torch.autograd.backward([logits] + terms, [self._dlogits] + self._kl_grads)
         return True
 
     def _one_step(self):
         self.opt.zero_grad(set_to_none=True)
-        if self.objective == "kl" and self._fused_objective():
+        if self._fused_objective():
             self.opt.step()
         else:
             if self.objective == "elbo":

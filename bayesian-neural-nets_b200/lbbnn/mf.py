@@ -308,13 +308,31 @@ class BayesianNetwork(nn.Module):
         return [getattr(self, n) for n in self._names]
 
     def forward(self, x, *gammas, sample=False, medimean=False, noises=None, **named):
+        return F.log_softmax(self._logits(x, *gammas, sample=sample, medimean=medimean, noises=noises, **named), dim=1)
+
+    def _logits(self, x, *gammas, sample=False, medimean=False, noises=None, **named):
+        """forward() without the closing log_softmax (GraphedTrainer fuses it with the loss)."""
         gs = list(gammas) + [named[f"g{i}"] for i in range(len(gammas) + 1, len(self._names) + 1) if f"g{i}" in named]
         x = x.view(-1, self.sizes[0])
         ls = self.layers
         for i, l in enumerate(ls):
             x = l.forward(x, gs[i], sample, medimean, noise=None if noises is None else noises[i])
-            x = F.relu(x) if i < len(ls) - 1 else F.log_softmax(x, dim=1)
+            if i < len(ls) - 1:
+                x = F.relu(x)
         return x
+
+    def _elbo_terms(self, input):
+        """One sample of sample_elbo (MF:285-319, samples = 1) up to the logits: (logits, the layers' log q and log prior
+        terms, their signs in loss = nll + (log q - log prior) / num_batches)."""
+        gs = []
+        for l in self.layers:
+            l.alpha = torch.sigmoid(l.lambdal)
+            l.gamma.alpha = l.alpha
+            gs.append(l.gamma.rsample(None))
+        logits = self._logits(input, *gs, sample=True, medimean=False)
+        lq = [l.log_variational_posterior for l in self.layers]
+        lp = [l.log_prior for l in self.layers]
+        return logits, lq + lp, [1.0] * len(lq) + [-1.0] * len(lp)
 
     def log_prior(self):
         return sum(l.log_prior for l in self.layers)

@@ -513,13 +513,15 @@ LBBNN_API int lbbnn_lrt_step_describe(const lbbnn_step* step, char* buf, size_t 
 LBBNN_API int lbbnn_logsoftmax_nll_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
                                        float* logp, float* nll_sum, float* dlogits, float grad_scale,
                                        int64_t* step_inc, void* workspace, size_t workspace_bytes, lbbnn_stream s);
-/* The whole training objective of one minibatch in ONE launch (LRT:221-224, MNF:267-270):
- *   nll = F.nll_loss(F.log_softmax(logits, 1), target, reduction='sum');  loss = nll + kl_scale * sum_i *kl_terms[i]
- * out2 = [loss, nll]; dlogits (batch,classes; may be NULL) = softmax - onehot = d loss / d logits, and d loss / d kl_i is
- * kl_scale.  kl_terms: HOST array of n_kl (<= 16) device pointers to the layers' scalar kl terms.  batch <= 4096. */
+/* The whole training objective of one minibatch in ONE launch (LRT:221-224, MNF:267-270; MF:316-318):
+ *   nll = F.nll_loss(F.log_softmax(logits, 1), target, reduction='sum')
+ *   loss = nll + kl_scale * sum_i term_scales[i] * *kl_terms[i]
+ * out2 = [loss, nll]; dlogits (batch,classes; may be NULL) = softmax - onehot = d loss / d logits, and d loss / d term_i is
+ * kl_scale * term_scales[i].  kl_terms: HOST array of n_kl (<= 16) device pointers to scalar terms -- the layers' kl, or the
+ * MF layers' log q (scale +1) and log prior (scale -1); term_scales: HOST array or NULL (all 1).  batch <= 4096. */
 LBBNN_API int lbbnn_nll_kl_objective_f32(const float* logits, const int64_t* target, int64_t batch, int64_t classes,
-                                         const float* const* kl_terms, int n_kl, float kl_scale, float* out2, float* dlogits,
-                                         lbbnn_stream s);
+                                         const float* const* kl_terms, const float* term_scales, int n_kl, float kl_scale,
+                                         float* out2, float* dlogits, lbbnn_stream s);
 
 /* ---- optimizer: torch.optim.Adam semantics (LRT:358), one flat buffer ----------------------------
  * step_dev: device int64 holding t, the 1-based index of THIS update; coef_scratch: 2 device floats

@@ -163,6 +163,52 @@ def _oracle_mc(net_params, x, seed, samples, lb, first=0, device="cpu", dtype=to
     return sum_logp, sum_prob
 
 
+def test_fused_elbo_objective_matches_sample_elbo_formulation(lb):
+    """GraphedTrainer's loss head for objective="elbo" (lbbnn_nll_kl_objective_f32 with the layers' log q at +1 / NUM_BATCHES
+    and log prior at -1 / NUM_BATCHES, backward started at the logits and those terms) against
+    loss = nll + (log q - log prior) / NUM_BATCHES of sample_elbo (MF:316-318) on the SAME forward graph: loss, nll and every
+    parameter gradient."""
+    import ctypes
+    import torch.nn.functional as F
+    from lbbnn import _capi as K
+    torch.manual_seed(5)
+    rng = np.random.default_rng(10)
+    net = lb.mf.BayesianNetwork((72, 40, 24, 10)).cuda().train()
+    x = C.t(rng.uniform(0, 1, size=(37, 72))).cuda()
+    y = torch.from_numpy(rng.integers(0, 10, size=(37,))).long().cuda()
+    logits, terms, signs = net._elbo_terms(x)
+    assert len(terms) == 6 and signs == [1.0] * 3 + [-1.0] * 3
+    params = list(net.parameters())
+    nll = F.nll_loss(F.log_softmax(logits, dim=1), y, reduction="sum")
+    loss = nll + (sum(terms[:3]) - sum(terms[3:])) / net.num_batches
+    ref = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
+    out, dlogits = torch.zeros(2, device="cuda"), torch.empty_like(logits)
+    ptrs = (ctypes.c_void_p * 6)(*[k.data_ptr() for k in terms])
+    scales = (ctypes.c_float * 6)(*signs)
+    K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(y, torch.int64), 37, 10, ptrs, scales, 6,
+                                             1.0 / net.num_batches, K.ptr(out), K.ptr(dlogits), K.current_stream()))
+    assert abs(out[0].item() - loss.item()) <= 2e-6 * abs(loss.item())
+    assert abs(out[1].item() - nll.item()) <= 1e-6 * abs(nll.item())
+    for p in params:
+        p.grad = None
+    torch.autograd.backward([logits] + terms, [dlogits] + [torch.full_like(k, sg / net.num_batches) for k, sg in zip(terms, signs)])
+    n_checked = 0
+    for (name, p), r in zip(net.named_parameters(), ref):
+        if r is None:
+            assert p.grad is None, name
+            continue
+        assert C.rel_err(p.grad, r) < 2e-6, name
+        n_checked += 1
+    assert n_checked >= 30
+    # (a fresh network: the graph above keeps this one's AccumulateGrad nodes on the default stream, which a capture on
+    # the trainer's stream must not touch)
+    net2 = lb.mf.BayesianNetwork((72, 40, 24, 10)).cuda()
+    tr = lb.GraphedTrainer(net2, batch_size=37, num_batches=net2.num_batches, lr=0.0, objective="elbo", in_features=72)
+    assert tr._dlogits is not None
+    o = tr.step(x.cpu(), y.cpu())
+    assert np.isfinite(o["loss"]) and o["nll"] > 0
+
+
 @pytest.mark.parametrize("use_graph,spl,gemm", [(False, 1, "simt"), (True, 1, "simt"), (False, 5, "simt"), (True, 8, "simt"),
                                                 (True, 16, "auto"), (False, 5, "tc"), (True, 8, "tc")])
 def test_mc_predictor_matches_oracle_and_is_split_invariant(lb, use_graph, spl, gemm):

@@ -281,7 +281,7 @@ def test_fused_objective_matches_the_torch_formulation(lb):
     ref = torch.autograd.grad(loss, params, retain_graph=True, allow_unused=True)
     out, dlogits = torch.zeros(2, device="cuda"), torch.empty_like(logits)
     ptrs = (ctypes.c_void_p * len(kls))(*[k.data_ptr() for k in kls])
-    K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(y, torch.int64), 37, 10, ptrs, len(kls),
+    K.check(K.lib.lbbnn_nll_kl_objective_f32(K.ptr(logits), K.ptr(y, torch.int64), 37, 10, ptrs, None, len(kls),
                                              1.0 / C.NUM_BATCHES, K.ptr(out), K.ptr(dlogits), K.current_stream()))
     assert abs(out[0].item() - loss.item()) <= 1e-6 * abs(loss.item())
     assert abs(out[1].item() - nll.item()) <= 1e-6 * abs(nll.item())
@@ -297,7 +297,8 @@ def test_fused_objective_matches_the_torch_formulation(lb):
         n_checked += 1
     assert n_checked > 100                                          # weights, biases, q0 / r0 terms and both flows of 3 layers
     # the trainer takes this path for the MNF network, and the torch formulation when asked to
-    tr = lb.GraphedTrainer(net, batch_size=37, num_batches=C.NUM_BATCHES, lr=0.0, objective="kl", in_features=72)
+    tr = lb.GraphedTrainer(lb.mnf.BayesianNetwork((72, 40, 24, 10)).cuda(), batch_size=37, num_batches=C.NUM_BATCHES, lr=0.0,
+                           objective="kl", in_features=72)
     assert tr._dlogits is not None
     tr_t = lb.GraphedTrainer(lb.mnf.BayesianNetwork((72, 40, 24, 10)).cuda(), batch_size=37, num_batches=C.NUM_BATCHES, lr=0.0,
                              objective="kl", in_features=72, fuse_objective=False)
