@@ -1380,4 +1380,12 @@ class GraphedTrainer:
             return None
         self.stats_host.copy_(self.stats, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return {"loss": float(self.stats_host[0]), "nll": float(self.stats_host[1])}
+        return self._stats_dict(self.stats_host)
+
+    def _stats_dict(self, st):
+        return {"loss": float(st[0]), "nll": float(st[1])}
+
+    # the pipelined host-buffer step of the LRT trainers: upload of batch i+1 on a copy stream under step i, the [loss, nll]
+    # of step i read at call i+1 (flush() delivers the last)
+    step_async = LRTTrainer.step_async
+    flush = LRTTrainer.flush

@@ -1096,8 +1096,17 @@ def bench_module(kind, steps, warmup, eager=False, cpu_budget_s=15.0):
             tr.y.copy_(y, non_blocking=True)
             tr.step_device()
 
-        def host_step(xh, yh):
-            return tr.step(xh, yh)["loss"]
+        if hasattr(tr, "step_async"):          # pipelined: upload of batch i+1 under step i, statistics read one call late
+            last = {}
+
+            def host_step(xh, yh):
+                out = tr.step_async(xh, yh)
+                if out is not None:
+                    last.update(out)
+                return last.get("loss")
+        else:
+            def host_step(xh, yh):
+                return tr.step(xh, yh)["loss"]
 
     for i in range(args.warmup):
         dev_step(px[i % POOL], py[i % POOL])
@@ -1115,6 +1124,8 @@ def bench_module(kind, steps, warmup, eager=False, cpu_budget_s=15.0):
     te0 = time.perf_counter()
     for i in range(args.steps):
         lv = host_step(px_h[(i + 7) % POOL], py_h[(i + 7) % POOL])
+    if tr is not None and hasattr(tr, "flush"):
+        lv = tr.flush()["loss"]               # the last step's statistics (inside the timed region)
     torch.cuda.synchronize()
     te1 = time.perf_counter()
     sampler.stop()
@@ -1128,7 +1139,10 @@ def bench_module(kind, steps, warmup, eager=False, cpu_budget_s=15.0):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": module_config(kind),
             "e2e": {"value": B * args.steps / (te1 - te0), "unit": "samples/s", "h2d_bytes_per_step": B * 784 * 4 + B * 8,
-                    "d2h_bytes_per_step": 4, "ms_per_step": (te1 - te0) / args.steps * 1e3},
+                    "d2h_bytes_per_step": 8 if (tr is not None and hasattr(tr, "step_async")) else 4,
+                    "ms_per_step": (te1 - te0) / args.steps * 1e3,
+                    "api": ("GraphedTrainer.step_async (pipelined: [loss, nll] of step i read at call i+1)"
+                            if (tr is not None and hasattr(tr, "step_async")) else "step(x_host, y_host)")},
             "gpu_launches": (tr.kernels_per_step * args.steps if kind == "vd_mnist" and tr is not None else None),
             "mode": "eager" if args.eager else "cuda-graph replay of the whole step",
             "roofline": {"bound": "hbm", "kernel": "whole step (all kernels of one replay)", "achieved": nbytes / (us * 1e-6) / 1e9,

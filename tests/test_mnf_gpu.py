@@ -254,6 +254,11 @@ def test_graphed_trainer_replays_the_eager_step_with_fresh_noise(lb, kind):
     assert len({o["nll"] for o in outs}) == 4                      # fresh noise on every replay
     assert all(torch.equal(a, b.detach()) for a, b in zip(p0, net.parameters()))
     assert tr.step_dev.item() == 3 + 4                             # warm-up steps + replays (the capture pass does not run)
+    # pipelined host-buffer steps: statistics arrive one call late, flush() delivers the last
+    outs = [tr.step_async(x, y) for _ in range(3)]
+    last = tr.flush()
+    assert outs[0] is None and all(np.isfinite(o["loss"]) and o["nll"] > 0 for o in outs[1:] + [last])
+    assert len({o["nll"] for o in outs[1:] + [last]}) == 3 and tr.step_dev.item() == 3 + 4 + 3
     net2 = make().cuda()
     tr2 = lb.GraphedTrainer(net2, batch_size=64, num_batches=C.NUM_BATCHES, lr=1e-3, objective=objective)
     nll = [tr2.step(x, y)["nll"] for _ in range(60)]
