@@ -377,6 +377,7 @@ struct FwdEpiArgs {
 
 constexpr int kEpiThreads = 128;
 
+constexpr int kEpiBatch = 8;      // splits whose partial tiles are in flight together (forward: E and S of each)
 __global__ void __launch_bounds__(kEpiThreads) lrt_f32_fwd_epilogue(const FwdEpiArgs a) {
   __shared__ double dred[32];
   Noise nz = a.noise;
@@ -389,18 +390,19 @@ __global__ void __launch_bounds__(kEpiThreads) lrt_f32_fwd_epilogue(const FwdEpi
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nquads; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
     float E[4] = {0.f, 0.f, 0.f, 0.f}, S[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f};
-    // fixed summation order over the splits; loads issued four splits at a time for memory parallelism
-    for (int s0 = 0; s0 < a.splits; s0 += 4) {
-      float pe[4][4], ps[4][4];
+    // fixed summation order over the splits; loads issued kEpiBatch splits at a time for memory parallelism: the kernel is
+    // a chain of (splits / batch) L2 round trips -- 49 splits at the 784-wide layer were 13 of them (6-8 us) four at a time
+    for (int s0 = 0; s0 < a.splits; s0 += kEpiBatch) {
+      float pe[kEpiBatch][4], ps[kEpiBatch][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kEpiBatch; ++u) {
         if (s0 + u < a.splits) {
           loadq(a.part + ((int64_t)(s0 + u) * 2 + 0) * total, e0, total, vec, pe[u]);
           if (sample) loadq(a.part + ((int64_t)(s0 + u) * 2 + 1) * total, e0, total, vec, ps[u]);
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kEpiBatch; ++u) {
         if (s0 + u < a.splits) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -965,13 +967,13 @@ __global__ void __launch_bounds__(kEpiThreads) lrt_f32_bwd_x_epilogue(const floa
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
     const int64_t e0 = q * 4;
     float s[4] = {0.f, 0.f, 0.f, 0.f}, xv[4];
-    for (int s0 = 0; s0 < splits; s0 += 4) {
-      float p[4][4];
+    for (int s0 = 0; s0 < splits; s0 += 2 * kEpiBatch) {
+      float p[2 * kEpiBatch][4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2 * kEpiBatch; ++u)
         if (s0 + u < splits) loadq(part + (int64_t)(s0 + u) * total, e0, total, vec, p[u]);
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2 * kEpiBatch; ++u)
         if (s0 + u < splits) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) s[j] += p[u][j];
