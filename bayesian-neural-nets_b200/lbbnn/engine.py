@@ -347,6 +347,30 @@ class LRTTrainer:
         with (torch.cuda.graph(self.graph, stream=cap) if cap is not None else torch.cuda.graph(self.graph)):
             self._enqueue()
 
+    def _retarget_inputs(self, x, y):
+        """Point the step at another (x, y) pair of device buffers (the next capture / enqueue reads them)."""
+        self.x, self.y = x, y
+        st = getattr(self, "_step_desc", None)
+        if st is not None:
+            st.x, st.y = K.ptr(x), K.ptr(y, torch.int64)
+
+    def _slot_graph(self, slot_x, slot_y):
+        """The captured step once more, reading its batch from (slot_x, slot_y) instead of self.x / self.y: step_async
+        replays the graph of the upload slot it has just filled, so the batch is not copied device-to-device first (134 MB
+        per step at the wide shape, two launches on the critical stream at the MNIST shape).  Same private pool as the main
+        graph; nothing in _enqueue allocates."""
+        x0, y0 = self.x, self.y
+        self._retarget_inputs(slot_x, slot_y)
+        try:
+            g = torch.cuda.CUDAGraph()
+            cap = getattr(self, "capture_stream", None)
+            kw = dict(pool=self.graph.pool())
+            with (torch.cuda.graph(g, stream=cap, **kw) if cap is not None else torch.cuda.graph(g, **kw)):
+                self._enqueue()
+        finally:
+            self._retarget_inputs(x0, y0)
+        return g
+
     # ---- public API -----------------------------------------------------------------------------------
     def step_device(self):
         """One training step on the data already in self.x / self.y (device resident)."""
@@ -392,7 +416,9 @@ class LRTTrainer:
                 xh=[None, None], yh=[None, None],        # pinned staging, only allocated for pageable inputs
                 sh=[torch.empty_like(self.stats_host).pin_memory() for _ in range(2)],
                 up=[torch.cuda.Event() for _ in range(2)], used=[torch.cuda.Event() for _ in range(2)],
-                done=[None, None])
+                done=[None, None],
+                slot_graphs=([None, None] if (getattr(self, "graph", None) is not None and hasattr(self, "_slot_graph") and
+                                              os.environ.get("LBBNN_SLOT_GRAPHS", "1") == "1") else None))
         P = self._pipe
         i = P["n"] & 1
         cur = torch.cuda.current_stream()
@@ -413,10 +439,16 @@ class LRTTrainer:
             P["ys"][i].copy_(src_y, non_blocking=True)
             P["up"][i].record(P["copy_stream"])
         cur.wait_event(P["up"][i])
-        self.x.copy_(P["xs"][i], non_blocking=True)
-        self.y.copy_(P["ys"][i], non_blocking=True)
-        P["used"][i].record(cur)
-        self.step_device()
+        if P["slot_graphs"] is not None:                 # the step captured against THIS slot's buffers: no device copy
+            if P["slot_graphs"][i] is None:
+                P["slot_graphs"][i] = self._slot_graph(P["xs"][i], P["ys"][i])
+            P["slot_graphs"][i].replay()
+            P["used"][i].record(cur)                     # the slot is free again once this step has run
+        else:
+            self.x.copy_(P["xs"][i], non_blocking=True)
+            self.y.copy_(P["ys"][i], non_blocking=True)
+            P["used"][i].record(cur)
+            self.step_device()
         P["sh"][i].copy_(self.stats, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(cur)
@@ -1092,6 +1124,8 @@ class LRTTensorCoreTrainer:
                                                       K.current_stream()))
 
     _capture = LRTTrainer._capture
+    _retarget_inputs = LRTTrainer._retarget_inputs
+    _slot_graph = LRTTrainer._slot_graph
     step_device = LRTTrainer.step_device
     step = LRTTrainer.step
     _stats_dict = LRTTrainer._stats_dict

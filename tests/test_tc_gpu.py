@@ -491,6 +491,38 @@ def test_wide_trainer_side_carried_layer0_matches_the_default_order(use_graph, m
             assert C.rel_err(getattr(lb_, k).detach(), getattr(la, k).detach()) < 1e-6, k
 
 
+def test_wide_trainer_step_async_matches_step(monkeypatch):
+    """The pipelined host-buffer API of the wide trainer (per-slot graphs: the step reads its batch from the upload slot, no
+    device-to-device copy) runs the same steps as step(): identical statistics one call late, identical parameters -- with
+    the slot graphs and with the copying fallback (LBBNN_SLOT_GRAPHS=0)."""
+    import lbbnn
+    sizes = [(136, 264), (264, 72), (72, 10)]
+    B = 64
+    case = C.lrt_net_case(seed=94, batch=B, sizes=sizes)
+    rng = np.random.default_rng(5)
+    xs = [C.t(rng.uniform(0, 1, size=(B, 136))) for _ in range(5)]
+    seqs = []
+    for mode in ("sync", "slots", "copies"):
+        monkeypatch.setenv("LBBNN_SLOT_GRAPHS", "0" if mode == "copies" else "1")
+        net = lbbnn.BayesianNetwork((136, 264, 72, 10)).cuda()
+        with torch.no_grad():
+            for l, p in zip(net.layers, case["layers"]):
+                for k, v in p.items():
+                    getattr(l, k).copy_(v)
+        tr = lbbnn.LRTTensorCoreTrainer(net, batch_size=B, num_batches=C.NUM_BATCHES, lr=1e-2, inject_noise=True)
+        for d, e in zip(tr.tc, case["eps"]):
+            d["eps"].copy_(e)
+        if mode == "sync":
+            out = [tr.step(x, case["y"]) for x in xs]
+        else:
+            out = [tr.step_async(x.pin_memory(), case["y"].pin_memory()) for x in xs]
+            assert out[0] is None and (tr._pipe["slot_graphs"] is not None) == (mode == "slots")
+            out = out[1:] + [tr.flush()]
+        seqs.append((out, tr.flat.clone()))
+    for other in seqs[1:]:
+        assert other[0] == seqs[0][0] and torch.equal(other[1], seqs[0][1])
+
+
 # ---- 3xTF32 linear layer (csrc/tc_gemm_tf32.cu): fp32 accuracy on tcgen05 --------------------------------------------
 # Tolerance: the same 1e-5 (max|a-b|/max|b| against an fp64 reference rounded to fp32) the CUDA-core fp32 GEMM is held
 # to -- north_star's fp32 bound.  A plain 1xTF32 product would sit near 1e-3.
