@@ -47,6 +47,11 @@ class _GammaSample(torch.autograd.Function):
         return dalpha, None, None, None, None
 
 
+# The two Gamma precisions of a layer call drawn outside autograd with their partial derivatives (BayesianLinear._tau_draw)
+# instead of torch.distributions.Gamma(...).rsample() + its autograd nodes; False keeps the torch formulation (tests compare).
+FUSED_TAU = True
+
+
 class _MFSample(torch.autograd.Function):
     """(w, sums[5]) = f(mu, rho, lambda, gamma, pb): weight sampling + log-prob element sums (csrc/mf.cu)."""
 
@@ -132,7 +137,8 @@ class _MFLogProbs(torch.autograd.Function):
     @staticmethod
     def forward(ctx, s, a, b, tau_w, ba, bb, tau_b, bias_mu, bias_rho, pa, pb, eps_b, meta):
         K.require_device()
-        sample_bias, n, key = meta
+        sample_bias, n, key = meta[:3]
+        ctx.tau_grads = meta[3] if len(meta) > 3 else None
         ts = [t.contiguous() for t in (s, a, b, tau_w, pa, pb, ba, bb, tau_b, bias_mu, bias_rho)]
         out_f = bias_mu.numel()
         dev = bias_mu.device
@@ -159,8 +165,16 @@ class _MFLogProbs(torch.autograd.Function):
                                          K.ptr(g_lp, allow_none=True), K.ptr(g_lq, allow_none=True), K.ptr(g_bias, allow_none=True),
                                          K.ptr(d10), K.ptr(d_ba), K.ptr(d_bb), K.ptr(d_tb), K.ptr(d_mu), K.ptr(d_rho),
                                          K.current_stream()))
-        #       s        a         b         tau_w     ba    bb    tau_b bias_mu bias_rho pa        pb        eps_b meta
-        return (d10[:5], d10[5:6], d10[6:7], d10[7:8], d_ba, d_bb, d_tb, d_mu, d_rho, d10[8:9], d10[9:10], None, None)
+        d_a, d_b, d_tw = d10[5:6], d10[6:7], d10[7:8]
+        if ctx.tau_grads is not None:
+            # the two precisions were drawn outside autograd (BayesianLinear._tau_draw) together with d tau / d a and
+            # d tau / d b: their chain rule is four fused multiply-adds here instead of ~18 torch nodes per layer
+            (ta_w, tb_w), (ta_b, tb_b) = ctx.tau_grads
+            d_a, d_b = torch.addcmul(d_a, d_tw, ta_w), torch.addcmul(d_b, d_tw, tb_w)
+            d_ba, d_bb = torch.addcmul(d_ba, d_tb, ta_b), torch.addcmul(d_bb, d_tb, tb_b)
+            d_tw = d_tb = None
+        #       s        a    b    tau_w ba    bb    tau_b bias_mu bias_rho pa        pb        eps_b meta
+        return (d10[:5], d_a, d_b, d_tw, d_ba, d_bb, d_tb, d_mu, d_rho, d10[8:9], d10[9:10], None, None)
 
 
 class _StdGammaReparam(torch.autograd.Function):
@@ -252,6 +266,22 @@ class BayesianLinear(nn.Module):
             return torch.distributions.Gamma(a, b, validate_args=False).rsample()   # no host sync: graph-capturable
         return _StdGammaReparam.apply(a, g0) / b
 
+    @staticmethod
+    def _tau_draw(a, b, g0=None):
+        """Gamma(a, b).rsample() (MF:167-173: the precisions of the GaussGamma priors) OUTSIDE autograd, with its two partial
+        derivatives: tau = g / b, g ~ standard Gamma(a) (or the injected draw g0); d tau / d a = standard_gamma_grad(a, g) / b
+        (torch's implicit reparameterisation, gamma.py:79-87), d tau / d b = -g / b^2.  _MFLogProbs applies them to the
+        gradient that reaches tau.  Depends on the hyper-parameters only: the network issues it for every layer on a side
+        stream at the start of the step."""
+        with torch.no_grad():
+            g = torch._standard_gamma(a) if g0 is None else g0
+            rb = 1.0 / b
+            tau = g * rb
+            d_a = torch._standard_gamma_grad(a, g) * rb
+            d_b = -tau * rb
+            tau.clamp_(min=torch.finfo(tau.dtype).tiny)            # Gamma.rsample's clamp (value only)
+        return tau, (d_a, d_b)
+
     def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):
         noise = noise or {}
         sample_branch = self.training or sample
@@ -274,15 +304,27 @@ class BayesianLinear(nn.Module):
         w, s = _MFSample.apply(self.weight_mu, self.weight_rho, self.lambdal, cgamma, self.pb, alpha_stale,
                                noise.get("eps_w"), mode, flags, self.last_noise_key)
         if want_lp:
-            self.alpha = torch.sigmoid(self.lambdal)                                          # MF:246: 1 / (1 + exp(-lambda)), one kernel
+            if not self.__dict__.pop("_alpha_fresh", False):
+                self.alpha = torch.sigmoid(self.lambdal)                                      # MF:246: 1 / (1 + exp(-lambda)), one kernel
             n = float(self.weight_mu.numel())
-            tau_w = self._tau(self.weight_a, self.weight_b, noise.get("g0_w"))
-            tau_b = self._tau(self.bias_a, self.bias_b, noise.get("g0_b"))
             # bias draw (stream + 2 of the call's noise key), GaussGamma / BetaBinomial / Gaussian log-probabilities: one launch
             bias_key = (self.last_noise_key[0], self.last_noise_key[1] + (2 << 32))
+            if FUSED_TAU:
+                pre = self.__dict__.pop("_tau_pre", None)
+                if pre is not None:
+                    torch.cuda.current_stream().wait_event(pre[2])
+                if pre is None or "g0_w" in noise or "g0_b" in noise:
+                    pre = (self._tau_draw(self.weight_a, self.weight_b, noise.get("g0_w")),
+                           self._tau_draw(self.bias_a, self.bias_b, noise.get("g0_b")))
+                (tau_w, tgw), (tau_b, tgb) = pre[:2]
+                meta = (sample_branch, n, bias_key, (tgw, tgb))
+            else:
+                tau_w = self._tau(self.weight_a, self.weight_b, noise.get("g0_w"))
+                tau_b = self._tau(self.bias_a, self.bias_b, noise.get("g0_b"))
+                meta = (sample_branch, n, bias_key)
             bias, self.log_prior, self.log_variational_posterior = _MFLogProbs.apply(
                 s, self.weight_a, self.weight_b, tau_w, self.bias_a, self.bias_b, tau_b, self.bias_mu, self.bias_rho, self.pa,
-                self.pb, eb, (sample_branch, n, bias_key))
+                self.pb, eb, meta)
         else:
             self.log_prior, self.log_variational_posterior = 0, 0
             if sample_branch:
@@ -324,12 +366,40 @@ class BayesianNetwork(nn.Module):
     def _elbo_terms(self, input):
         """One sample of sample_elbo (MF:285-319, samples = 1) up to the logits: (logits, the layers' log q and log prior
         terms, their signs in loss = nll + (log q - log prior) / num_batches)."""
+        if FUSED_TAU and input.is_cuda:      # the layers' precisions depend on hyper-parameters only: side stream, up front
+            cur = torch.cuda.current_stream()
+            if getattr(self, "_tau_stream", None) is None or self._tau_stream.device != input.device:
+                self._tau_stream = torch.cuda.Stream(device=input.device)
+            self._tau_stream.wait_stream(cur)
+            with torch.cuda.stream(self._tau_stream), torch.no_grad():
+                # ALL layers' weight and bias precisions as one batch: one standard-gamma draw, one standard_gamma_grad and a
+                # handful of elementwise launches over ~10^3 elements instead of nine launches per precision and layer
+                hp = [(l.weight_a, l.weight_b) for l in self.layers] + [(l.bias_a, l.bias_b) for l in self.layers]
+                a_all = torch.cat([a.reshape(-1) for a, _ in hp])
+                b_all = torch.cat([b.reshape(-1) for _, b in hp])
+                tau, (d_a, d_b) = BayesianLinear._tau_draw(a_all, b_all)
+                for u in (tau, d_a, d_b):
+                    u.record_stream(cur)
+                ev = torch.cuda.Event()
+                ev.record(self._tau_stream)
+                parts, off = [], 0
+                for a, _ in hp:
+                    n = a.numel()
+                    parts.append((tau[off:off + n].view_as(a), (d_a[off:off + n].view_as(a), d_b[off:off + n].view_as(a))))
+                    off += n
+                L = len(self.layers)
+                for i, l in enumerate(self.layers):
+                    l._tau_pre = (parts[i], parts[L + i], ev)
         gs = []
         for l in self.layers:
             l.alpha = torch.sigmoid(l.lambdal)
             l.gamma.alpha = l.alpha
+            l._alpha_fresh = True             # the layer call's own alpha (MF:246) is this very value: no second launch
             gs.append(l.gamma.rsample(None))
         logits = self._logits(input, *gs, sample=True, medimean=False)
+        for l in self.layers:
+            l.__dict__.pop("_tau_pre", None)
+            l.__dict__.pop("_alpha_fresh", None)
         lq = [l.log_variational_posterior for l in self.layers]
         lp = [l.log_prior for l in self.layers]
         return logits, lq + lp, [1.0] * len(lq) + [-1.0] * len(lp)

@@ -163,6 +163,16 @@ def _oracle_mc(net_params, x, seed, samples, lb, first=0, device="cpu", dtype=to
     return sum_logp, sum_prob
 
 
+def test_torch_gamma_rsample_path_still_matches_reference(lb, monkeypatch):
+    """lbbnn.mf.FUSED_TAU = False: the precisions through torch.distributions.Gamma(...).rsample() / _StdGammaReparam and
+    autograd instead of BayesianLinear._tau_draw's explicit derivative factors (the default, which every other test here
+    runs): same layer and network parity against the oracle and the reference goldens."""
+    monkeypatch.setattr(lb.mf, "FUSED_TAU", False)
+    test_mf_mnist_sample_elbo_matches_reference(lb)
+    for key in ("ma_rel", "mb_ex", "sa_rel"):
+        test_mf_layer_matches_oracle_and_reference(lb, key)
+
+
 def test_fused_elbo_objective_matches_sample_elbo_formulation(lb):
     """GraphedTrainer's loss head for objective="elbo" (lbbnn_nll_kl_objective_f32 with the layers' log q at +1 / NUM_BATCHES
     and log prior at -1 / NUM_BATCHES, backward started at the logits and those terms) against
