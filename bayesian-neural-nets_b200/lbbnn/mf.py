@@ -169,7 +169,9 @@ class _MFLogProbs(torch.autograd.Function):
         if ctx.tau_grads is not None:
             # the two precisions were drawn outside autograd (BayesianLinear._tau_draw) together with d tau / d a and
             # d tau / d b: their chain rule is four fused multiply-adds here instead of ~18 torch nodes per layer
-            (ta_w, tb_w), (ta_b, tb_b) = ctx.tau_grads
+            (ta_w, tb_w), (ta_b, tb_b), factors_ready = ctx.tau_grads
+            if factors_ready is not None:
+                torch.cuda.current_stream().wait_event(factors_ready)
             d_a, d_b = torch.addcmul(d_a, d_tw, ta_w), torch.addcmul(d_b, d_tw, tb_w)
             d_ba, d_bb = torch.addcmul(d_ba, d_tb, ta_b), torch.addcmul(d_bb, d_tb, tb_b)
             d_tw = d_tb = None
@@ -267,7 +269,7 @@ class BayesianLinear(nn.Module):
         return _StdGammaReparam.apply(a, g0) / b
 
     @staticmethod
-    def _tau_draw(a, b, g0=None):
+    def _tau_draw(a, b, g0=None, value_ready=None):
         """Gamma(a, b).rsample() (MF:167-173: the precisions of the GaussGamma priors) OUTSIDE autograd, with its two partial
         derivatives: tau = g / b, g ~ standard Gamma(a) (or the injected draw g0); d tau / d a = standard_gamma_grad(a, g) / b
         (torch's implicit reparameterisation, gamma.py:79-87), d tau / d b = -g / b^2.  _MFLogProbs applies them to the
@@ -276,10 +278,12 @@ class BayesianLinear(nn.Module):
         with torch.no_grad():
             g = torch._standard_gamma(a) if g0 is None else g0
             rb = 1.0 / b
-            tau = g * rb
+            raw = g * rb
+            tau = raw.clamp(min=torch.finfo(raw.dtype).tiny)       # Gamma.rsample's clamp (value only)
+            if value_ready is not None:                            # the forward needs tau only: the derivative factors
+                value_ready.record(torch.cuda.current_stream())    # (standard_gamma_grad: ~20 us) are the backward's
             d_a = torch._standard_gamma_grad(a, g) * rb
-            d_b = -tau * rb
-            tau.clamp_(min=torch.finfo(tau.dtype).tiny)            # Gamma.rsample's clamp (value only)
+            d_b = -raw * rb
         return tau, (d_a, d_b)
 
     def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):
@@ -312,12 +316,12 @@ class BayesianLinear(nn.Module):
             if FUSED_TAU:
                 pre = self.__dict__.pop("_tau_pre", None)
                 if pre is not None:
-                    torch.cuda.current_stream().wait_event(pre[2])
+                    torch.cuda.current_stream().wait_event(pre[2])       # the values; the backward waits for the factors
                 if pre is None or "g0_w" in noise or "g0_b" in noise:
                     pre = (self._tau_draw(self.weight_a, self.weight_b, noise.get("g0_w")),
-                           self._tau_draw(self.bias_a, self.bias_b, noise.get("g0_b")))
+                           self._tau_draw(self.bias_a, self.bias_b, noise.get("g0_b")), None, None)
                 (tau_w, tgw), (tau_b, tgb) = pre[:2]
-                meta = (sample_branch, n, bias_key, (tgw, tgb))
+                meta = (sample_branch, n, bias_key, (tgw, tgb, pre[3]))
             else:
                 tau_w = self._tau(self.weight_a, self.weight_b, noise.get("g0_w"))
                 tau_b = self._tau(self.bias_a, self.bias_b, noise.get("g0_b"))
@@ -366,22 +370,34 @@ class BayesianNetwork(nn.Module):
     def _elbo_terms(self, input):
         """One sample of sample_elbo (MF:285-319, samples = 1) up to the logits: (logits, the layers' log q and log prior
         terms, their signs in loss = nll + (log q - log prior) / num_batches)."""
-        if FUSED_TAU and input.is_cuda:      # the layers' precisions depend on hyper-parameters only: side stream, up front
+        fork = None
+        if FUSED_TAU and input.is_cuda:
             cur = torch.cuda.current_stream()
             if getattr(self, "_tau_stream", None) is None or self._tau_stream.device != input.device:
                 self._tau_stream = torch.cuda.Stream(device=input.device)
-            self._tau_stream.wait_stream(cur)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+        gs = []
+        for l in self.layers:
+            l.alpha = torch.sigmoid(l.lambdal)
+            l.gamma.alpha = l.alpha
+            l._alpha_fresh = True             # the layer call's own alpha (MF:246) is this very value: no second launch
+            gs.append(l.gamma.rsample(None))
+        if fork is not None:                  # the layers' precisions depend on hyper-parameters only: side stream
+            # (issued here, after the gamma launches, but forked from the start of the step: a captured graph issues its
+            # nodes in capture order, and ten side-stream launches in front of the main path delayed it by ~12 us)
+            self._tau_stream.wait_event(fork)
             with torch.cuda.stream(self._tau_stream), torch.no_grad():
                 # ALL layers' weight and bias precisions as one batch: one standard-gamma draw, one standard_gamma_grad and a
                 # handful of elementwise launches over ~10^3 elements instead of nine launches per precision and layer
                 hp = [(l.weight_a, l.weight_b) for l in self.layers] + [(l.bias_a, l.bias_b) for l in self.layers]
                 a_all = torch.cat([a.reshape(-1) for a, _ in hp])
                 b_all = torch.cat([b.reshape(-1) for _, b in hp])
-                tau, (d_a, d_b) = BayesianLinear._tau_draw(a_all, b_all)
+                ev, ev_grads = torch.cuda.Event(), torch.cuda.Event()
+                tau, (d_a, d_b) = BayesianLinear._tau_draw(a_all, b_all, value_ready=ev)
+                ev_grads.record(self._tau_stream)
                 for u in (tau, d_a, d_b):
                     u.record_stream(cur)
-                ev = torch.cuda.Event()
-                ev.record(self._tau_stream)
                 parts, off = [], 0
                 for a, _ in hp:
                     n = a.numel()
@@ -389,13 +405,7 @@ class BayesianNetwork(nn.Module):
                     off += n
                 L = len(self.layers)
                 for i, l in enumerate(self.layers):
-                    l._tau_pre = (parts[i], parts[L + i], ev)
-        gs = []
-        for l in self.layers:
-            l.alpha = torch.sigmoid(l.lambdal)
-            l.gamma.alpha = l.alpha
-            l._alpha_fresh = True             # the layer call's own alpha (MF:246) is this very value: no second launch
-            gs.append(l.gamma.rsample(None))
+                    l._tau_pre = (parts[i], parts[L + i], ev, ev_grads)
         logits = self._logits(input, *gs, sample=True, medimean=False)
         for l in self.layers:
             l.__dict__.pop("_tau_pre", None)
