@@ -377,6 +377,9 @@ struct PriorBwdArgs {
   float n;
   float* d_scalar;                                          // [ds0..ds4, da, db, dtau_w, dpa, dpb]
   float *d_ba, *d_bb, *d_tau_b, *d_bias_mu, *d_bias_rho;    // (out) each
+  // optional: the precisions were drawn outside autograd as tau = g / b; their partial derivatives wrt (a, b) -- (1,) for the
+  // weights' tau, (out) for the biases' -- fold the gradient that reaches tau into da, db here
+  const float *tw_da, *tw_db, *tb_da, *tb_db;
 };
 
 __global__ void __launch_bounds__(kThreads) mf_prior_bwd_kernel(const PriorBwdArgs a) {
@@ -385,9 +388,15 @@ __global__ void __launch_bounds__(kThreads) mf_prior_bwd_kernel(const PriorBwdAr
     const float mu = __ldg(a.bias_mu + i), rho = __ldg(a.bias_rho + i), sb = sigma_of(rho);
     const float bias = __ldg(a.bias + i), e = __ldg(a.eps + i), d = bias - mu;
     const float ba = __ldg(a.ba + i), bb = __ldg(a.bb + i), tb = __ldg(a.tau_b + i);
-    a.d_ba[i] = gp * (logf(bb) + tb - digammaf(ba));
-    a.d_bb[i] = gp * (ba / bb - tb);
-    a.d_tau_b[i] = gp * ((ba - 0.5f) - bb - bias * bias);
+    const float dtb = gp * ((ba - 0.5f) - bb - bias * bias);
+    float dba = gp * (logf(bb) + tb - digammaf(ba)), dbb = gp * (ba / bb - tb);
+    if (a.tb_da) {
+      dba = fmaf(dtb, __ldg(a.tb_da + i), dba);
+      dbb = fmaf(dtb, __ldg(a.tb_db + i), dbb);
+    }
+    a.d_ba[i] = dba;
+    a.d_bb[i] = dbb;
+    a.d_tau_b[i] = dtb;
     const float inv2 = 1.0f / (sb * sb);
     const float G = (a.g_bias ? __ldg(a.g_bias + i) : 0.f) + gp * (-2.0f * tb * bias) + gq * (-d * inv2);   // d loss / d bias
     a.d_bias_mu[i] = G + gq * (d * inv2);
@@ -403,9 +412,15 @@ __global__ void __launch_bounds__(kThreads) mf_prior_bwd_kernel(const PriorBwdAr
     a.d_scalar[2] = gp;
     a.d_scalar[3] = gq;
     a.d_scalar[4] = gq;
-    a.d_scalar[5] = gp * s0 * (logf(bv) + tw - digammaf(av));
-    a.d_scalar[6] = gp * s0 * (av / bv - tw);
-    a.d_scalar[7] = gp * (s0 * ((av - 0.5f) - bv) - s1);
+    const float dtw = gp * (s0 * ((av - 0.5f) - bv) - s1);
+    float da = gp * s0 * (logf(bv) + tw - digammaf(av)), db = gp * s0 * (av / bv - tw);
+    if (a.tw_da) {
+      da = fmaf(dtw, a.tw_da[0], da);
+      db = fmaf(dtw, a.tw_db[0], db);
+    }
+    a.d_scalar[5] = da;
+    a.d_scalar[6] = db;
+    a.d_scalar[7] = dtw;
     const float psi_s = digammaf(pa + pb) - digammaf(1.0f + pa + pb);
     a.d_scalar[8] = gp * a.n * (psi_s - digammaf(pa));
     a.d_scalar[9] = gp * a.n * (psi_s - digammaf(pb));
@@ -541,6 +556,20 @@ extern "C" int lbbnn_mf_prior_bwd(const float* sums5, const float* a, const floa
                                   int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
                                   const float* g_log_q, const float* g_bias, float* d_scalars10, float* d_bias_a, float* d_bias_b,
                                   float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s) {
+  return lbbnn_mf_prior_bwd_tau(sums5, a, b, tau_w, pa, pb, bias_a, bias_b, tau_b, bias_mu, bias_rho, bias, eps, sample_bias,
+                                out_features, n_weights, g_log_prior, g_log_q, g_bias, nullptr, nullptr, nullptr, nullptr,
+                                d_scalars10, d_bias_a, d_bias_b, d_tau_b, d_bias_mu, d_bias_rho, s);
+}
+
+extern "C" int lbbnn_mf_prior_bwd_tau(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                      const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                      const float* bias_mu, const float* bias_rho, const float* bias, const float* eps,
+                                      int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
+                                      const float* g_log_q, const float* g_bias, const float* dtau_w_da, const float* dtau_w_db,
+                                      const float* dtau_b_da, const float* dtau_b_db, float* d_scalars10, float* d_bias_a,
+                                      float* d_bias_b, float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s) {
+  LBBNN_REQUIRE((dtau_w_da == nullptr) == (dtau_w_db == nullptr) && (dtau_b_da == nullptr) == (dtau_b_db == nullptr),
+                "the derivative factors of a precision come in pairs");
   LBBNN_REQUIRE(sums5 && a && b && tau_w && pa && pb && bias_a && bias_b && tau_b && bias_mu && bias_rho && bias && eps,
                 "NULL argument");
   LBBNN_REQUIRE(d_scalars10 && d_bias_a && d_bias_b && d_tau_b && d_bias_mu && d_bias_rho, "NULL output");
@@ -550,6 +579,7 @@ extern "C" int lbbnn_mf_prior_bwd(const float* sums5, const float* a, const floa
   p.bias_mu = bias_mu; p.bias_rho = bias_rho; p.bias = bias; p.eps = eps; p.g_lp = g_log_prior; p.g_lq = g_log_q; p.g_bias = g_bias;
   p.out = (int)out_features; p.sample = sample_bias ? 1 : 0; p.n = (float)n_weights;
   p.d_scalar = d_scalars10; p.d_ba = d_bias_a; p.d_bb = d_bias_b; p.d_tau_b = d_tau_b; p.d_bias_mu = d_bias_mu; p.d_bias_rho = d_bias_rho;
+  p.tw_da = dtau_w_da; p.tw_db = dtau_w_db; p.tb_da = dtau_b_da; p.tb_db = dtau_b_db;
   mf_prior_bwd_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>(p);
   return check_launch("mf_prior_bwd");
 }

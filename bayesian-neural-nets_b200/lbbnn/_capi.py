@@ -197,6 +197,7 @@ SIGNATURES = {
                                    _P, _SZ, _P]),
     "lbbnn_mf_prior_fwd": (_INT, [_P] * 11 + [C.POINTER(Noise), _INT, _I64, C.c_double, _P, _P, _P, _P]),
     "lbbnn_mf_prior_bwd": (_INT, [_P] * 13 + [_INT, _I64, C.c_double] + [_P] * 9 + [_P]),
+    "lbbnn_mf_prior_bwd_tau": (_INT, [_P] * 13 + [_INT, _I64, C.c_double] + [_P] * 13 + [_P]),
     "lbbnn_flow_save_floats": (_SZ, [C.POINTER(Flow), _I64]),
     "lbbnn_flow_fwd": (_INT, [C.POINTER(Flow), _P, _I64, _P, C.POINTER(Noise), _P, _P, _P, _P]),
     "lbbnn_flow_bwd": (_INT, [C.POINTER(Flow), C.POINTER(FlowGrads), _I64, _P, C.POINTER(Noise), _P, _P, _P, _P, _P]),

@@ -161,19 +161,21 @@ class _MFLogProbs(torch.autograd.Function):
         d_ba, d_bb, d_tb, d_mu, d_rho = (torch.empty(out_f, **f32) for _ in range(5))
         cz = lambda t: None if t is None else t.contiguous().float()   # noqa: E731
         g_bias, g_lp, g_lq = cz(g_bias), cz(g_lp), cz(g_lq)
-        K.check(K.lib.lbbnn_mf_prior_bwd(*[K.ptr(t) for t in ts], K.ptr(bias), K.ptr(eps), int(sample_bias), out_f, float(n),
-                                         K.ptr(g_lp, allow_none=True), K.ptr(g_lq, allow_none=True), K.ptr(g_bias, allow_none=True),
-                                         K.ptr(d10), K.ptr(d_ba), K.ptr(d_bb), K.ptr(d_tb), K.ptr(d_mu), K.ptr(d_rho),
-                                         K.current_stream()))
-        d_a, d_b, d_tw = d10[5:6], d10[6:7], d10[7:8]
+        factors = [None] * 4
         if ctx.tau_grads is not None:
             # the two precisions were drawn outside autograd (BayesianLinear._tau_draw) together with d tau / d a and
-            # d tau / d b: their chain rule is four fused multiply-adds here instead of ~18 torch nodes per layer
+            # d tau / d b: their chain rule is four fused multiply-adds inside the kernel instead of ~18 torch nodes per layer
             (ta_w, tb_w), (ta_b, tb_b), factors_ready = ctx.tau_grads
             if factors_ready is not None:
                 torch.cuda.current_stream().wait_event(factors_ready)
-            d_a, d_b = torch.addcmul(d_a, d_tw, ta_w), torch.addcmul(d_b, d_tw, tb_w)
-            d_ba, d_bb = torch.addcmul(d_ba, d_tb, ta_b), torch.addcmul(d_bb, d_tb, tb_b)
+            factors = [t.contiguous() for t in (ta_w, tb_w, ta_b, tb_b)]
+        K.check(K.lib.lbbnn_mf_prior_bwd_tau(*[K.ptr(t) for t in ts], K.ptr(bias), K.ptr(eps), int(sample_bias), out_f, float(n),
+                                             K.ptr(g_lp, allow_none=True), K.ptr(g_lq, allow_none=True),
+                                             K.ptr(g_bias, allow_none=True), *[K.ptr(t, allow_none=True) for t in factors],
+                                             K.ptr(d10), K.ptr(d_ba), K.ptr(d_bb), K.ptr(d_tb), K.ptr(d_mu), K.ptr(d_rho),
+                                             K.current_stream()))
+        d_a, d_b, d_tw = d10[5:6], d10[6:7], d10[7:8]
+        if ctx.tau_grads is not None:
             d_tw = d_tb = None
         #       s        a    b    tau_w ba    bb    tau_b bias_mu bias_rho pa        pb        eps_b meta
         return (d10[:5], d_a, d_b, d_tw, d_ba, d_bb, d_tb, d_mu, d_rho, d10[8:9], d10[9:10], None, None)

@@ -352,6 +352,16 @@ LBBNN_API int lbbnn_mf_prior_bwd(const float* sums5, const float* a, const float
                                  int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
                                  const float* g_log_q, const float* g_bias, float* d_scalars10, float* d_bias_a,
                                  float* d_bias_b, float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s);
+/* The same with the two Gamma precisions drawn OUTSIDE autograd (tau = g / b, g ~ standard Gamma(a)): dtau_*_da / dtau_*_db are
+ * their partial derivatives (standard_gamma_grad(a, g) / b and -g / b^2; (1,) for the weights' precision, (out) for the
+ * biases'; NULL pairs = none) and the gradient that reaches each tau is folded into d a, d b here (d tau is still written). */
+LBBNN_API int lbbnn_mf_prior_bwd_tau(const float* sums5, const float* a, const float* b, const float* tau_w, const float* pa,
+                                     const float* pb, const float* bias_a, const float* bias_b, const float* tau_b,
+                                     const float* bias_mu, const float* bias_rho, const float* bias, const float* eps,
+                                     int sample_bias, int64_t out_features, double n_weights, const float* g_log_prior,
+                                     const float* g_log_q, const float* g_bias, const float* dtau_w_da, const float* dtau_w_db,
+                                     const float* dtau_b_da, const float* dtau_b_db, float* d_scalars10, float* d_bias_a,
+                                     float* d_bias_b, float* d_tau_b, float* d_bias_mu, float* d_bias_rho, lbbnn_stream s);
 
 /* ---- normalizing flows of flows2.py: PropagateFlow (flows2:14-46) over RNVP (flows2:188-219) or the
  * IAF-style MNF transform (flows2:225-241), as fused small-MLP kernels (one CTA per row of z runs the
