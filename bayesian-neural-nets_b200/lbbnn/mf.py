@@ -99,16 +99,20 @@ class _Linear(torch.autograd.Function):
     """F.linear(x, W, b) on the fp32 SIMT GEMM kernels (MF:255)."""
 
     @staticmethod
-    def forward(ctx, x, W, b):
+    def forward(ctx, x, W, b, relu=False, mask_dx=False):
+        """relu: the output leaves the kernel through F.relu (MF:268-269); the gradient that comes back is then the one wrt the
+        PRE-relu output, which the consumer must have masked -- the next layer's backward with mask_dx does (its input x is this
+        relu output, and [x > 0] is the relu's derivative)."""
         K.require_device()
         x, W, b = x.contiguous(), W.contiguous(), b.contiguous()
         B, kf = x.shape
         nf = W.shape[0]
         out = torch.empty(B, nf, dtype=torch.float32, device=x.device)
         ws = K.workspace(K.lrt_workspace_bytes(B, kf, nf), x.device)
-        K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(x), K.ptr(W), K.ptr(b), B, kf, nf, 0, K.ptr(out), ws.data_ptr(), ws.numel(),
-                                           K.current_stream()))
+        K.check(K.lib.lbbnn_linear_f32_fwd(K.ptr(x), K.ptr(W), K.ptr(b), B, kf, nf, K.FLAG_RELU if relu else 0, K.ptr(out),
+                                           ws.data_ptr(), ws.numel(), K.current_stream()))
         ctx.save_for_backward(x, W)
+        ctx.mask_dx = bool(mask_dx)
         return out
 
     @staticmethod
@@ -124,9 +128,10 @@ class _Linear(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
-            K.check(K.lib.lbbnn_linear_f32_bwd_input(K.ptr(x), K.ptr(W), K.ptr(g), B, kf, nf, 0, K.ptr(dx), ws.data_ptr(),
+            K.check(K.lib.lbbnn_linear_f32_bwd_input(K.ptr(x), K.ptr(W), K.ptr(g), B, kf, nf,
+                                                     K.FLAG_MASK_DX if ctx.mask_dx else 0, K.ptr(dx), ws.data_ptr(),
                                                      ws.numel(), K.current_stream()))
-        return dx, dW, db
+        return dx, dW, db, None, None
 
 
 class _MFLogProbs(torch.autograd.Function):
@@ -288,7 +293,8 @@ class BayesianLinear(nn.Module):
             d_b = -raw * rb
         return tau, (d_a, d_b)
 
-    def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):
+    def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None, _relu=False,
+                _mask_dx=False):
         noise = noise or {}
         sample_branch = self.training or sample
         want_lp = self.training or calculate_log_probs
@@ -338,7 +344,7 @@ class BayesianLinear(nn.Module):
                 bias = self.bias_mu + sb * (eb if eb is not None else torch.randn_like(sb))
             else:
                 bias = self.bias_mu
-        return _Linear.apply(input, w, bias)
+        return _Linear.apply(input, w, bias, _relu, _mask_dx)
 
 
 class BayesianNetwork(nn.Module):
@@ -363,10 +369,9 @@ class BayesianNetwork(nn.Module):
         gs = list(gammas) + [named[f"g{i}"] for i in range(len(gammas) + 1, len(self._names) + 1) if f"g{i}" in named]
         x = x.view(-1, self.sizes[0])
         ls = self.layers
-        for i, l in enumerate(ls):
-            x = l.forward(x, gs[i], sample, medimean, noise=None if noises is None else noises[i])
-            if i < len(ls) - 1:
-                x = F.relu(x)
+        for i, l in enumerate(ls):          # F.relu (MF:268-269) rides in the layer kernels: forward flag, next layer's dx mask
+            x = l.forward(x, gs[i], sample, medimean, noise=None if noises is None else noises[i], _relu=i < len(ls) - 1,
+                          _mask_dx=i > 0)
         return x
 
     def _elbo_terms(self, input):
