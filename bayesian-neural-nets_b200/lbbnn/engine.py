@@ -1190,7 +1190,8 @@ class MultiTensorAdam:
         layer's z flow and q0 parameters, whose gradients come out of the LAST node of the backward (a 34 us cluster launch
         at the end of the critical path): the 23 us update of the other 3.3 M parameters runs under it instead of after it.
         The group is the same on every step; a step in which some early parameter gets no gradient falls back to the one
-        launch in step()."""
+        launch in step().  Contract: zero_grad(set_to_none=True), ONE backward pass, step() -- gradients accumulated over
+        several backward passes would be consumed after the first (do not call this for such a loop)."""
         late = {id(p) for p in late_params}
         unknown = late - {id(p) for p in self.params}
         if unknown:
