@@ -106,6 +106,28 @@ __global__ void __launch_bounds__(kThreads) mf_gamma_bwd_kernel(const float* __r
 }
 
 // ---- weight sampling + log-prob sums ------------------------------------------------------------------
+// The last block to arrive sums the per-block partials [gridDim.x][width] in sum_partials_kernel's order (thread-strided, then
+// block_sum) and returns true to thread 0 with the totals in out[]; every other block returns false.  The ticket is reset.
+template <int WIDTH>
+__device__ __forceinline__ bool last_block_totals(const double* __restrict__ part, unsigned int* ticket, double* red,
+                                                  double (&out)[WIDTH]) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+#pragma unroll
+  for (int k = 0; k < WIDTH; ++k) {
+    double acc = 0.0;
+    for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) acc += __ldcg(part + (int64_t)i * WIDTH + k);
+    out[k] = block_sum(acc, red);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+  return threadIdx.x == 0;
+}
+
 struct SampleArgs {
   const float *mu, *rho, *lam, *gamma, *alpha_stale, *pb;
   Noise eps;
@@ -116,6 +138,10 @@ struct SampleArgs {
   int exact_b, exact_wp, exact_gp;   // round(gamma.detach()) inside Bernoulli / GaussGamma / BetaBinomial log_prob
   float* w;
   double* part;    // [gridDim.x][5]
+  // optional: the last block to arrive (ticket) closes the five sums itself -- same order as sum_partials_kernel -- instead of
+  // a second launch; the ticket is zero on entry and is left zero
+  unsigned int* ticket;
+  float* sums;
   // optional, for the Monte-Carlo predictive loop: draw the hard mask inside ([u < alpha], no gamma tensor)
   int native_gamma;
   Noise gu;
@@ -198,6 +224,13 @@ __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a)
       const double t = block_sum((double)s[k], red);
       if (threadIdx.x == 0) a.part[(int64_t)blockIdx.x * 5 + k] = t;
     }
+    if (a.ticket) {
+      double tot[5];
+      if (last_block_totals<5>(a.part, a.ticket, red, tot)) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) a.sums[k] = (float)tot[k];
+      }
+    }
   }
 }
 
@@ -219,7 +252,10 @@ struct SampleBwdArgs {
   int lp_on_ws, exact_b, exact_wp, exact_gp, want_dgamma;
   float *dmu, *drho, *dlam, *dgamma;
   double* part;   // [gridDim.x][1]: sum psi(1+pb-g) (for dpb)
+  unsigned int* ticket;   // optional, as in SampleArgs: the last block writes dpb = c[2] * sum of the partials
+  float* dpb;
 };
+
 
 __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwdArgs a) {
   __shared__ double red[32];
@@ -281,6 +317,10 @@ __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwd
   }
   const double t = block_sum((double)psisum, red);
   if (threadIdx.x == 0) a.part[blockIdx.x] = t;
+  if (a.ticket) {
+    double tot[1];
+    if (last_block_totals<1>(a.part, a.ticket, red, tot)) *a.dpb = (float)tot[0] * (a.c ? a.c[2] : 0.f);   // = sum_partials + scale_scalar
+  }
 }
 
 // Monte-Carlo predictive accumulators (test_ensemble, MF:367-406): per input row add log_softmax(logits) and
@@ -458,7 +498,7 @@ static int mf_sample_launch(const float* mu, const float* rho, const float* lamb
                             const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode, int flags,
                             float* w, float* sums, void* ws, size_t ws_bytes, const lbbnn_noise* gamma_u,
                             const float* bias_mu, const float* bias_rho, const lbbnn_noise* eps_b, int64_t n_bias,
-                            float* bias_out, lbbnn_stream s) {
+                            float* bias_out, lbbnn_stream s, unsigned int* ticket = nullptr) {
   LBBNN_REQUIRE(mu && rho && lambdal && w && n > 0, "NULL argument");
   LBBNN_REQUIRE(mode == LBBNN_MF_JOINTMEAN || gamma || gamma_u, "gamma (tensor or native draw) required");
   LBBNN_REQUIRE(!bias_out || (bias_mu && bias_rho && n_bias > 0), "bias sampling needs bias_mu/bias_rho");
@@ -475,10 +515,11 @@ static int mf_sample_launch(const float* mu, const float* rho, const float* lamb
   a.native_gamma = (gamma == nullptr && gamma_u != nullptr && mode != LBBNN_MF_JOINTMEAN) ? 1 : 0;
   a.gu = make_noise(gamma_u);
   a.bias_mu = bias_mu; a.bias_rho = bias_rho; a.eb = make_noise(eps_b); a.n_bias = n_bias; a.bias_out = bias_out;
+  a.ticket = lp ? ticket : nullptr; a.sums = sums;
   const unsigned blocks = (unsigned)ew_blocks(n);
   mf_sample_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
   if (int rc = check_launch("mf_sample")) return rc;
-  if (lp) {
+  if (lp && !ticket) {
     sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 5, sums);
     return check_launch("mf_sum_partials");
   }
@@ -490,6 +531,15 @@ extern "C" int lbbnn_mf_sample_fwd(const float* mu, const float* rho, const floa
                                    int flags, float* w, float* sums, void* ws, size_t ws_bytes, lbbnn_stream s) {
   return mf_sample_launch(mu, rho, lambdal, gamma, alpha_stale, pb, n, eps, mode, flags, w, sums, ws, ws_bytes, nullptr,
                           nullptr, nullptr, nullptr, 0, nullptr, s);
+}
+
+extern "C" int lbbnn_mf_sample_fwd_ticket(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                          const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode,
+                                          int flags, float* w, float* sums, void* ws, size_t ws_bytes, unsigned int* ticket,
+                                          lbbnn_stream s) {
+  LBBNN_REQUIRE(ticket, "NULL ticket");
+  return mf_sample_launch(mu, rho, lambdal, gamma, alpha_stale, pb, n, eps, mode, flags, w, sums, ws, ws_bytes, nullptr,
+                          nullptr, nullptr, nullptr, 0, nullptr, s, ticket);
 }
 
 // one launch per layer of the Monte-Carlo predictive loop: hard mask drawn natively, weights and bias sampled
@@ -513,6 +563,14 @@ extern "C" int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const floa
                                    int64_t n, const lbbnn_noise* eps, int flags, const float* dw, const float* dsums,
                                    float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb, void* ws,
                                    size_t ws_bytes, lbbnn_stream s) {
+  return lbbnn_mf_sample_bwd_ticket(mu, rho, lambdal, gamma, pb, n, eps, flags, dw, dsums, dmu, drho, dlambdal, dgamma, dpb, ws,
+                                    ws_bytes, nullptr, s);
+}
+
+extern "C" int lbbnn_mf_sample_bwd_ticket(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                          const float* pb, int64_t n, const lbbnn_noise* eps, int flags, const float* dw,
+                                          const float* dsums, float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
+                                          void* ws, size_t ws_bytes, unsigned int* ticket, lbbnn_stream s) {
   LBBNN_REQUIRE(mu && rho && lambdal && gamma && pb && dmu && drho && dlambdal && dpb && n > 0, "NULL argument");
   LBBNN_REQUIRE(ws && ws_bytes >= lbbnn_mf_workspace_bytes(n), "workspace too small");
   SampleBwdArgs a;
@@ -524,9 +582,11 @@ extern "C" int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const floa
   a.exact_gp = (flags & LBBNN_MF_FLAG_EXACT_GPRIOR) ? 1 : 0;
   a.want_dgamma = dgamma ? 1 : 0;
   a.dmu = dmu; a.drho = drho; a.dlam = dlambdal; a.dgamma = dgamma; a.part = (double*)ws;
+  a.ticket = ticket; a.dpb = dpb;
   const unsigned blocks = (unsigned)ew_blocks(n);
   mf_sample_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
   if (int rc = check_launch("mf_sample_bwd")) return rc;
+  if (ticket) return LBBNN_OK;          // the last block has written dpb = dL/ds2 * sum psi(1+pb-g)
   sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 1, dpb);
   if (int rc = check_launch("mf_sum_partials")) return rc;
   scale_scalar_kernel<<<1, 1, 0, (cudaStream_t)s>>>(dpb, dsums, 2);   // dpb = dL/ds2 * sum psi(1+pb-g)

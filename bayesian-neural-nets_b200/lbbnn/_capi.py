@@ -182,6 +182,9 @@ SIGNATURES = {
     "lbbnn_mf_gamma_sample": (_INT, [_P, _P, _I64, C.POINTER(Noise), _INT, _F, _P, _P]),
     "lbbnn_mf_gamma_sample_bwd": (_INT, [_P, _P, _P, _P, _I64, _F, _P, _P]),
     "lbbnn_mf_sample_fwd": (_INT, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _INT, _P, _P, _P, _SZ, _P]),
+    "lbbnn_mf_sample_fwd_ticket": (_INT, [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _INT, _P, _P, _P, _SZ, _P, _P]),
+    "lbbnn_mf_sample_bwd_ticket": (_INT, [_P, _P, _P, _P, _P, _I64, C.POINTER(Noise), _INT, _P, _P, _P, _P, _P, _P, _P, _P, _SZ,
+                                          _P, _P]),
     "lbbnn_mf_sample_predict": (_INT, [C.POINTER(Layer), C.POINTER(Noise), C.POINTER(Noise), C.POINTER(Noise), _P, _P, _P]),
     "lbbnn_mc_accumulate": (_INT, [_P, _I64, _I64, _P, _P, _P, _P]),
     "lbbnn_mc_sample": (_INT, [C.POINTER(Layer), _INT, _P, _U64, _U64, _U64, _P, _P, _P]),

@@ -52,6 +52,22 @@ class _GammaSample(torch.autograd.Function):
 FUSED_TAU = True
 
 
+_ticket_bufs = {}
+
+
+def _tickets(dev):
+    """Two device counters (forward, backward) for the last-block reductions of the sampler kernels on the CURRENT stream:
+    zero when a launch starts, zero again when it ends; one pair per (device, stream) like the kernel workspace."""
+    key = (dev.index, K.current_stream())
+    t = _ticket_bufs.get(key)
+    if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise K.LbbnnError("ticket buffer would be created during CUDA-graph capture; run one eager step first")
+        t = torch.zeros(2, dtype=torch.int32, device=dev)
+        _ticket_bufs[key] = t
+    return t
+
+
 class _MFSample(torch.autograd.Function):
     """(w, sums[5]) = f(mu, rho, lambda, gamma, pb): weight sampling + log-prob element sums (csrc/mf.cu)."""
 
@@ -62,13 +78,22 @@ class _MFSample(torch.autograd.Function):
         gamma = gamma.contiguous() if gamma is not None else None
         n = mu.numel()
         w = torch.empty_like(mu)
-        sums = torch.zeros(5, dtype=torch.float32, device=mu.device)
+        want_lp = bool(flags & K.MF_FLAG_LOGPROBS)
+        # with log-probs every sum is written by the launch's last block (ticket): no zero-fill, no second launch
+        sums = (torch.empty if want_lp else torch.zeros)(5, dtype=torch.float32, device=mu.device)
         ws = K.workspace(K.lib.lbbnn_mf_workspace_bytes(n), mu.device)
         eps = eps.contiguous() if eps is not None else None
         noise = K.make_noise(eps, key[0], key[1])
-        K.check(K.lib.lbbnn_mf_sample_fwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma, allow_none=True),
-                                          K.ptr(alpha_stale, allow_none=True), K.ptr(pb), n, noise, mode, flags,
-                                          K.ptr(w), K.ptr(sums), ws.data_ptr(), ws.numel(), K.current_stream()))
+        ctx.tickets = tickets = _tickets(mu.device) if want_lp else None
+        if want_lp:
+            K.check(K.lib.lbbnn_mf_sample_fwd_ticket(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma, allow_none=True),
+                                                     K.ptr(alpha_stale, allow_none=True), K.ptr(pb), n, noise, mode, flags,
+                                                     K.ptr(w), K.ptr(sums), ws.data_ptr(), ws.numel(), tickets.data_ptr(),
+                                                     K.current_stream()))
+        else:
+            K.check(K.lib.lbbnn_mf_sample_fwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma, allow_none=True),
+                                              K.ptr(alpha_stale, allow_none=True), K.ptr(pb), n, noise, mode, flags,
+                                              K.ptr(w), K.ptr(sums), ws.data_ptr(), ws.numel(), K.current_stream()))
         ctx.save_for_backward(mu, rho, lam, gamma, pb, eps)
         ctx.mode, ctx.flags, ctx.key = mode, flags, key
         return w, sums
@@ -83,15 +108,23 @@ class _MFSample(torch.autograd.Function):
         dmu, drho, dlam = torch.empty_like(mu), torch.empty_like(mu), torch.empty_like(mu)
         want_dg = ctx.needs_input_grad[3]
         dgamma = torch.empty_like(mu) if want_dg else None
-        dpb = torch.zeros_like(pb)
         ws = K.workspace(K.lib.lbbnn_mf_workspace_bytes(n), mu.device)
         noise = K.make_noise(eps, ctx.key[0], ctx.key[1])
         dw_c = dw.contiguous() if dw is not None else None
         ds_c = dsums.contiguous() if dsums is not None else None
-        K.check(K.lib.lbbnn_mf_sample_bwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma), K.ptr(pb), n, noise, ctx.flags,
-                                          K.ptr(dw_c, allow_none=True), K.ptr(ds_c, allow_none=True), K.ptr(dmu),
-                                          K.ptr(drho), K.ptr(dlam), K.ptr(dgamma, allow_none=True), K.ptr(dpb),
-                                          ws.data_ptr(), ws.numel(), K.current_stream()))
+        if ctx.tickets is not None:        # dpb written by the launch's last block: no fill, no reduction / scaling launches
+            dpb = torch.empty_like(pb)
+            K.check(K.lib.lbbnn_mf_sample_bwd_ticket(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma), K.ptr(pb), n, noise,
+                                                     ctx.flags, K.ptr(dw_c, allow_none=True), K.ptr(ds_c, allow_none=True),
+                                                     K.ptr(dmu), K.ptr(drho), K.ptr(dlam), K.ptr(dgamma, allow_none=True),
+                                                     K.ptr(dpb), ws.data_ptr(), ws.numel(), ctx.tickets.data_ptr() + 4,
+                                                     K.current_stream()))
+        else:
+            dpb = torch.zeros_like(pb)
+            K.check(K.lib.lbbnn_mf_sample_bwd(K.ptr(mu), K.ptr(rho), K.ptr(lam), K.ptr(gamma), K.ptr(pb), n, noise, ctx.flags,
+                                              K.ptr(dw_c, allow_none=True), K.ptr(ds_c, allow_none=True), K.ptr(dmu),
+                                              K.ptr(drho), K.ptr(dlam), K.ptr(dgamma, allow_none=True), K.ptr(dpb),
+                                              ws.data_ptr(), ws.numel(), K.current_stream()))
         return dmu, drho, dlam, dgamma, dpb, None, None, None, None, None
 
 

@@ -334,6 +334,17 @@ LBBNN_API int lbbnn_mf_sample_bwd(const float* mu, const float* rho, const float
                                   const float* dw, const float* dsums,
                                   float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
                                   void* workspace, size_t workspace_bytes, lbbnn_stream s);
+/* lbbnn_mf_sample_fwd / _bwd with the closing reductions (the five sums; dpb) done by the LAST block of the launch instead of one
+ * / two further launches: `ticket` is a device counter that is zero on entry and is left zero (one per concurrent call site);
+ * same summation order, bit-identical results. */
+LBBNN_API int lbbnn_mf_sample_fwd_ticket(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                         const float* alpha_stale, const float* pb, int64_t n, const lbbnn_noise* eps, int mode,
+                                         int flags, float* w, float* sums, void* ws, size_t ws_bytes, unsigned int* ticket,
+                                         lbbnn_stream s);
+LBBNN_API int lbbnn_mf_sample_bwd_ticket(const float* mu, const float* rho, const float* lambdal, const float* gamma,
+                                         const float* pb, int64_t n, const lbbnn_noise* eps, int flags, const float* dw,
+                                         const float* dsums, float* dmu, float* drho, float* dlambdal, float* dgamma, float* dpb,
+                                         void* ws, size_t ws_bytes, unsigned int* ticket, lbbnn_stream s);
 
 /* The scalar tail of the MF layer's log-probabilities (MF:148-150 GaussGamma, MF:167-173 BetaBinomial, MF:246-251) in one
  * launch each way: from the five sums of lbbnn_mf_sample_fwd, the Gamma draws tau_w (1) / tau_b (out) and the hyper-
