@@ -20,18 +20,20 @@ _LOG_SQRT_2PI = math.log(math.sqrt(2 * math.pi))
 
 
 class _GammaSample(torch.autograd.Function):
-    """gamma.rsample() for a given alpha tensor (MF:110-117)."""
+    """gamma.rsample() for a given alpha tensor (MF:110-117) -- or, from_lambda, for alpha = sigmoid(lambdal) formed inside
+    the kernel (forward and backward: no torch.sigmoid node on either side)."""
 
     @staticmethod
-    def forward(ctx, alpha, u, exact, temperature, key):
+    def forward(ctx, alpha, u, exact, temperature, key, from_lambda=False):
         K.require_device()
         alpha_c = alpha.contiguous()
         gamma = torch.empty_like(alpha_c)
         noise = K.make_noise(u.contiguous() if u is not None else None, key[0], key[1])
-        K.check(K.lib.lbbnn_mf_gamma_sample(None, K.ptr(alpha_c), alpha_c.numel(), noise, int(exact), temperature,
-                                            K.ptr(gamma), K.current_stream()))
+        src = (K.ptr(alpha_c), None) if from_lambda else (None, K.ptr(alpha_c))
+        K.check(K.lib.lbbnn_mf_gamma_sample(*src, alpha_c.numel(), noise, int(exact), temperature, K.ptr(gamma),
+                                            K.current_stream()))
         ctx.save_for_backward(alpha_c, gamma)
-        ctx.exact, ctx.t = exact, temperature
+        ctx.exact, ctx.t, ctx.from_lambda = exact, temperature, bool(from_lambda)
         if exact:
             ctx.mark_non_differentiable(gamma)
         return gamma
@@ -39,12 +41,13 @@ class _GammaSample(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dgamma):
         if ctx.exact:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         alpha, gamma = ctx.saved_tensors
         dalpha = torch.empty_like(alpha)
-        K.check(K.lib.lbbnn_mf_gamma_sample_bwd(None, K.ptr(alpha), K.ptr(gamma), K.ptr(dgamma.contiguous()),
-                                                alpha.numel(), ctx.t, K.ptr(dalpha), K.current_stream()))
-        return dalpha, None, None, None, None
+        src = (K.ptr(alpha), None) if ctx.from_lambda else (None, K.ptr(alpha))
+        K.check(K.lib.lbbnn_mf_gamma_sample_bwd(*src, K.ptr(gamma), K.ptr(dgamma.contiguous()), alpha.numel(), ctx.t,
+                                                K.ptr(dalpha), K.current_stream()))
+        return dalpha, None, None, None, None, None
 
 
 # The two Gamma precisions of a layer call drawn outside autograd with their partial derivatives (BayesianLinear._tau_draw)
@@ -245,9 +248,12 @@ class MFBernoulliView:
         self._calls = 0
         self.last_noise_key = None
 
-    def rsample(self, u=None):
+    def rsample(self, u=None, lambdal=None):
+        """lambdal: draw for alpha = sigmoid(lambdal) without materialising alpha (the gradient then goes to lambdal)."""
         self._calls += 1
         self.last_noise_key = (current_seed(), (self._uid << 40) | self._calls)
+        if lambdal is not None:
+            return _GammaSample.apply(lambdal, u, bool(self.exact), float(self.temperature), self.last_noise_key, True)
         return _GammaSample.apply(self.alpha, u, bool(self.exact), float(self.temperature), self.last_noise_key)
 
 
@@ -419,15 +425,22 @@ class BayesianNetwork(nn.Module):
             fork.record(cur)
         gs = []
         for l in self.layers:
-            l.alpha = torch.sigmoid(l.lambdal)
-            l.gamma.alpha = l.alpha
+            if fork is not None:              # alpha = sigmoid(lambda) inside the mask kernels; the attribute on the side stream
+                gs.append(l.gamma.rsample(None, lambdal=l.lambdal))
+            else:
+                l.alpha = torch.sigmoid(l.lambdal)
+                l.gamma.alpha = l.alpha
+                gs.append(l.gamma.rsample(None))
             l._alpha_fresh = True             # the layer call's own alpha (MF:246) is this very value: no second launch
-            gs.append(l.gamma.rsample(None))
         if fork is not None:                  # the layers' precisions depend on hyper-parameters only: side stream
             # (issued here, after the gamma launches, but forked from the start of the step: a captured graph issues its
             # nodes in capture order, and ten side-stream launches in front of the main path delayed it by ~12 us)
             self._tau_stream.wait_event(fork)
             with torch.cuda.stream(self._tau_stream), torch.no_grad():
+                for l in self.layers:         # the reference's alpha attributes (MF:290-297): values only, nobody waits for them
+                    l.alpha = torch.sigmoid(l.lambdal)
+                    l.alpha.record_stream(cur)
+                    l.gamma.alpha = l.alpha
                 # ALL layers' weight and bias precisions as one batch: one standard-gamma draw, one standard_gamma_grad and a
                 # handful of elementwise launches over ~10^3 elements instead of nine launches per precision and layer
                 hp = [(l.weight_a, l.weight_b) for l in self.layers] + [(l.bias_a, l.bias_b) for l in self.layers]
