@@ -15,10 +15,13 @@
 // All vectorised (float4) and coalesced; reductions are two-stage with a fixed order (deterministic).
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace lbbnn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kLpWidthDefault = 2;   // see lp_width(): same-box A/B 0.2734 (4) / 0.2641 (2) / 0.2644 (1) ms per MF step
 constexpr float kLogSqrt2Pi = 0.91893853320467274178f;
 
 __device__ __forceinline__ void ldq(const float* __restrict__ p, int64_t e0, int64_t n, bool vec, float out[4]) {
@@ -37,6 +40,53 @@ __device__ __forceinline__ void stq(float* __restrict__ p, int64_t e0, int64_t n
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       if (e0 + j < n) p[e0 + j] = v[j];
+  }
+}
+
+// W consecutive elements per thread (W = 4: one Philox group per thread; 2 / 1: two / four threads share a group and each
+// recomputes it -- more warps in flight for the latency-bound log-probability kernels, ncu: 24 % warps active at W = 4)
+template <int W>
+__device__ __forceinline__ void ldw(const float* __restrict__ p, int64_t e0, int64_t n, bool vec, float (&out)[W]) {
+  if constexpr (W == 4) {
+    ldq(p, e0, n, vec, out);
+  } else if constexpr (W == 2) {
+    if (vec && e0 + 1 < n) {
+      const float2 v = __ldg(reinterpret_cast<const float2*>(p + e0));
+      out[0] = v.x; out[1] = v.y;
+    } else {
+      out[0] = e0 < n ? __ldg(p + e0) : 0.f;
+      out[1] = e0 + 1 < n ? __ldg(p + e0 + 1) : 0.f;
+    }
+  } else {
+    out[0] = e0 < n ? __ldg(p + e0) : 0.f;
+  }
+}
+template <int W>
+__device__ __forceinline__ void stw(float* __restrict__ p, int64_t e0, int64_t n, bool vec, const float (&v)[W]) {
+  if constexpr (W == 4) {
+    stq(p, e0, n, vec, v);
+  } else if constexpr (W == 2) {
+    if (vec && e0 + 1 < n) {
+      *reinterpret_cast<float2*>(p + e0) = make_float2(v[0], v[1]);
+    } else {
+      if (e0 < n) p[e0] = v[0];
+      if (e0 + 1 < n) p[e0 + 1] = v[1];
+    }
+  } else {
+    if (e0 < n) p[e0] = v[0];
+  }
+}
+// this thread's W values of a Philox group of four (sub = first element's position in the group)
+template <int W>
+__device__ __forceinline__ void pickw(const float (&g4)[4], int sub, float (&out)[W]) {
+  if constexpr (W == 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) out[j] = g4[j];
+  } else if constexpr (W == 2) {
+    out[0] = sub ? g4[2] : g4[0];
+    out[1] = sub ? g4[3] : g4[1];
+  } else {
+    out[0] = sub == 0 ? g4[0] : (sub == 1 ? g4[1] : (sub == 2 ? g4[2] : g4[3]));
   }
 }
 
@@ -152,6 +202,7 @@ struct SampleArgs {
   float* bias_out;
 };
 
+template <int W>
 __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a) {
   __shared__ double red[32];
   Noise nz = a.eps, gu = a.gu;
@@ -169,30 +220,40 @@ __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a)
                    (a.gamma == nullptr || aligned16(a.gamma)) && (a.alpha_stale == nullptr || aligned16(a.alpha_stale)) &&
                    (nz.ptr == nullptr || aligned16(nz.ptr));
   const float pb = a.want_lp ? __ldg(a.pb) : 1.0f;
-  const int64_t nq = ceil_div(a.n, 4);
+  const int64_t nth = ceil_div(a.n, (int64_t)W);
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = q * 4;
-    float mu[4], rho[4], lam[4], ga[4] = {0.f, 0.f, 0.f, 0.f}, ep[4] = {0.f, 0.f, 0.f, 0.f}, w[4];
-    ldq(a.mu, e0, a.n, vec, mu);
-    if (a.mode == LBBNN_MF_SAMPLE || a.want_lp) ldq(a.rho, e0, a.n, vec, rho);
-    if (a.want_lp || a.native_gamma || (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr)) ldq(a.lam, e0, a.n, vec, lam);
-    if (a.mode == LBBNN_MF_JOINTMEAN) {
-      if (a.alpha_stale) ldq(a.alpha_stale, e0, a.n, vec, ga);
-    } else if (a.native_gamma) {
-      float u[4];
-      philox_uniform4(gu.seed, gu.stream, (uint64_t)q, u);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nth; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = t * W;
+    const uint64_t q = (uint64_t)(e0 >> 2);      // Philox group of the elements, as in the one-group-per-thread form
+    const int sub = (int)(e0 & 3);
+    float mu[W], rho[W], lam[W], ga[W], ep[W], w[W];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) ga[j] = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;
+    for (int j = 0; j < W; ++j) ga[j] = ep[j] = rho[j] = lam[j] = 0.f;
+    ldw<W>(a.mu, e0, a.n, vec, mu);
+    if (a.mode == LBBNN_MF_SAMPLE || a.want_lp) ldw<W>(a.rho, e0, a.n, vec, rho);
+    if (a.want_lp || a.native_gamma || (a.mode == LBBNN_MF_JOINTMEAN && a.alpha_stale == nullptr)) ldw<W>(a.lam, e0, a.n, vec, lam);
+    if (a.mode == LBBNN_MF_JOINTMEAN) {
+      if (a.alpha_stale) ldw<W>(a.alpha_stale, e0, a.n, vec, ga);
+    } else if (a.native_gamma) {
+      float u4[4], u[W];
+      philox_uniform4(gu.seed, gu.stream, q, u4);
+      pickw<W>(u4, sub, u);
+#pragma unroll
+      for (int j = 0; j < W; ++j) ga[j] = u[j] < alpha_of(lam[j]) ? 1.0f : 0.0f;
     } else {
-      ldq(a.gamma, e0, a.n, vec, ga);
+      ldw<W>(a.gamma, e0, a.n, vec, ga);
     }
     if (a.mode == LBBNN_MF_SAMPLE) {
-      if (nz.ptr) ldq(nz.ptr, e0, a.n, vec, ep);
-      else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+      if (nz.ptr) {
+        ldw<W>(nz.ptr, e0, a.n, vec, ep);
+      } else {
+        float n4[4];
+        philox_normal4(nz.seed, nz.stream, q, n4);
+        pickw<W>(n4, sub, ep);
+      }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W; ++j) {
       w[j] = 0.f;
       if (e0 + j >= a.n) continue;
       float ws = mu[j];
@@ -216,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) mf_sample_kernel(const SampleArgs a)
         s[4] += g_b * logf(al + 1e-8f) + (1.0f - g_b) * logf(1.0f - al + 1e-8f);
       }
     }
-    stq(a.w, e0, a.n, vec, w);
+    stw<W>(a.w, e0, a.n, vec, w);
   }
   if (a.want_lp) {
 #pragma unroll
@@ -257,6 +318,7 @@ struct SampleBwdArgs {
 };
 
 
+template <int W>
 __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwdArgs a) {
   __shared__ double red[32];
   Noise nz = a.eps;
@@ -270,20 +332,29 @@ __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwd
     for (int k = 0; k < 5; ++k) c[k] = __ldg(a.c + k);
   }
   const float pb = __ldg(a.pb);
-  const int64_t nq = ceil_div(a.n, 4);
+  const int64_t nth = ceil_div(a.n, (int64_t)W);
   float psisum = 0.f;
-  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t e0 = q * 4;
-    float mu[4], rho[4], lam[4], ga[4], ep[4], dw[4] = {0.f, 0.f, 0.f, 0.f}, gm[4], gr[4], gl[4], gg[4];
-    ldq(a.mu, e0, a.n, vec, mu);
-    ldq(a.rho, e0, a.n, vec, rho);
-    ldq(a.lam, e0, a.n, vec, lam);
-    ldq(a.gamma, e0, a.n, vec, ga);
-    if (a.dw) ldq(a.dw, e0, a.n, vec, dw);
-    if (nz.ptr) ldq(nz.ptr, e0, a.n, vec, ep);
-    else philox_normal4(nz.seed, nz.stream, (uint64_t)q, ep);
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < nth; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t e0 = t * W;
+    const uint64_t q = (uint64_t)(e0 >> 2);
+    const int sub = (int)(e0 & 3);
+    float mu[W], rho[W], lam[W], ga[W], ep[W], dw[W], gm[W], gr[W], gl[W], gg[W];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W; ++j) dw[j] = 0.f;
+    ldw<W>(a.mu, e0, a.n, vec, mu);
+    ldw<W>(a.rho, e0, a.n, vec, rho);
+    ldw<W>(a.lam, e0, a.n, vec, lam);
+    ldw<W>(a.gamma, e0, a.n, vec, ga);
+    if (a.dw) ldw<W>(a.dw, e0, a.n, vec, dw);
+    if (nz.ptr) {
+      ldw<W>(nz.ptr, e0, a.n, vec, ep);
+    } else {
+      float n4[4];
+      philox_normal4(nz.seed, nz.stream, q, n4);
+      pickw<W>(n4, sub, ep);
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
       gm[j] = gr[j] = gl[j] = gg[j] = 0.f;
       if (e0 + j >= a.n) continue;
       const float sg = sigma_of(rho[j]), al = alpha_of(lam[j]), g = ga[j];
@@ -310,10 +381,10 @@ __global__ void __launch_bounds__(kThreads) mf_sample_bwd_kernel(const SampleBwd
       gl[j] = dal * al * (1.0f - al);
       gg[j] = ws * dw_tot + dg_dir;
     }
-    stq(a.dmu, e0, a.n, vec, gm);
-    stq(a.drho, e0, a.n, vec, gr);
-    stq(a.dlam, e0, a.n, vec, gl);
-    if (a.want_dgamma) stq(a.dgamma, e0, a.n, vec, gg);
+    stw<W>(a.dmu, e0, a.n, vec, gm);
+    stw<W>(a.drho, e0, a.n, vec, gr);
+    stw<W>(a.dlam, e0, a.n, vec, gl);
+    if (a.want_dgamma) stw<W>(a.dgamma, e0, a.n, vec, gg);
   }
   const double t = block_sum((double)psisum, red);
   if (threadIdx.x == 0) a.part[blockIdx.x] = t;
@@ -357,6 +428,21 @@ __global__ void scale_scalar_kernel(float* v, const float* c, int k) { *v *= c ?
 
 int64_t ew_blocks(int64_t n) {
   int64_t b = ceil_div(ceil_div(n, 4), kThreads);
+  const int64_t cap = 8LL * sm_count();
+  return b < 1 ? 1 : (b > cap ? cap : b);
+}
+// weights per thread of the log-probability kernels (mf_sample with log-probs, mf_sample_bwd): LBBNN_MF_SPLIT = 4 | 2 | 1
+int lp_width() {
+  static int w = 0;
+  if (!w) {
+    const char* e = getenv("LBBNN_MF_SPLIT");
+    const int v = e ? atoi(e) : kLpWidthDefault;
+    w = (v == 1 || v == 2 || v == 4) ? v : kLpWidthDefault;
+  }
+  return w;
+}
+int64_t lp_blocks(int64_t n, int width) {
+  int64_t b = ceil_div(ceil_div(n, (int64_t)width), kThreads);
   const int64_t cap = 8LL * sm_count();
   return b < 1 ? 1 : (b > cap ? cap : b);
 }
@@ -472,7 +558,7 @@ __global__ void __launch_bounds__(kThreads) mf_prior_bwd_kernel(const PriorBwdAr
 
 using namespace lbbnn;
 
-extern "C" size_t lbbnn_mf_workspace_bytes(int64_t n) { return n > 0 ? (size_t)ew_blocks(n) * 5 * sizeof(double) + 256 : 0; }
+extern "C" size_t lbbnn_mf_workspace_bytes(int64_t n) { return n > 0 ? (size_t)lp_blocks(n, 1) * 5 * sizeof(double) + 256 : 0; }
 
 extern "C" int lbbnn_mf_gamma_sample(const float* lambdal, const float* alpha, int64_t n, const lbbnn_noise* u, int exact,
                                      float temperature, float* gamma, lbbnn_stream s) {
@@ -516,8 +602,11 @@ static int mf_sample_launch(const float* mu, const float* rho, const float* lamb
   a.gu = make_noise(gamma_u);
   a.bias_mu = bias_mu; a.bias_rho = bias_rho; a.eb = make_noise(eps_b); a.n_bias = n_bias; a.bias_out = bias_out;
   a.ticket = lp ? ticket : nullptr; a.sums = sums;
-  const unsigned blocks = (unsigned)ew_blocks(n);
-  mf_sample_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  const int width = lp ? lp_width() : 4;        // without log-probs the kernel is a light elementwise pass: one group per thread
+  const unsigned blocks = (unsigned)lp_blocks(n, width);
+  if (width == 1) mf_sample_kernel<1><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  else if (width == 2) mf_sample_kernel<2><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  else mf_sample_kernel<4><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
   if (int rc = check_launch("mf_sample")) return rc;
   if (lp && !ticket) {
     sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 5, sums);
@@ -583,8 +672,11 @@ extern "C" int lbbnn_mf_sample_bwd_ticket(const float* mu, const float* rho, con
   a.want_dgamma = dgamma ? 1 : 0;
   a.dmu = dmu; a.drho = drho; a.dlam = dlambdal; a.dgamma = dgamma; a.part = (double*)ws;
   a.ticket = ticket; a.dpb = dpb;
-  const unsigned blocks = (unsigned)ew_blocks(n);
-  mf_sample_bwd_kernel<<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  const int width = lp_width();
+  const unsigned blocks = (unsigned)lp_blocks(n, width);
+  if (width == 1) mf_sample_bwd_kernel<1><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  else if (width == 2) mf_sample_bwd_kernel<2><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
+  else mf_sample_bwd_kernel<4><<<blocks, kThreads, 0, (cudaStream_t)s>>>(a);
   if (int rc = check_launch("mf_sample_bwd")) return rc;
   if (ticket) return LBBNN_OK;          // the last block has written dpb = dL/ds2 * sum psi(1+pb-g)
   sum_partials_kernel<<<1, kThreads, 0, (cudaStream_t)s>>>((const double*)ws, (int)blocks, 1, dpb);
