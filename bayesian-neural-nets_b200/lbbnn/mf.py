@@ -8,6 +8,7 @@ terms) stays in torch on the device, exactly where the reference has it, so auto
 weight_a/weight_b/bias_a/bias_b/pa/pb unchanged.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -334,6 +335,12 @@ class BayesianLinear(nn.Module):
 
     def forward(self, input, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None, _relu=False,
                 _mask_dx=False):
+        w, bias = self._draw_weights(cgamma, sample, medimean, calculate_log_probs, noise)
+        return _Linear.apply(input, w, bias, _relu, _mask_dx)
+
+    def _draw_weights(self, cgamma, sample=False, medimean=False, calculate_log_probs=False, noise=None):
+        """Everything of forward() that does not depend on the input batch: the weights and bias of this call (MF:228-245)
+        and, training / calculate_log_probs, log_prior and log_variational_posterior (MF:246-251).  Returns (w, bias)."""
         noise = noise or {}
         sample_branch = self.training or sample
         want_lp = self.training or calculate_log_probs
@@ -383,7 +390,7 @@ class BayesianLinear(nn.Module):
                 bias = self.bias_mu + sb * (eb if eb is not None else torch.randn_like(sb))
             else:
                 bias = self.bias_mu
-        return _Linear.apply(input, w, bias, _relu, _mask_dx)
+        return w, bias
 
 
 class BayesianNetwork(nn.Module):
@@ -423,10 +430,16 @@ class BayesianNetwork(nn.Module):
                 self._tau_stream = torch.cuda.Stream(device=input.device)
             fork = torch.cuda.Event()
             fork.record(cur)
+        ls = self.layers
+        if fork is not None and (getattr(self, "_layer_streams", None) is None or
+                                 self._layer_streams[0].device != input.device):
+            self._layer_streams = [torch.cuda.Stream(device=input.device) for _ in ls]
         gs = []
-        for l in self.layers:
+        for i, l in enumerate(ls):
             if fork is not None:              # alpha = sigmoid(lambda) inside the mask kernels; the attribute on the side stream
-                gs.append(l.gamma.rsample(None, lambdal=l.lambdal))
+                self._layer_streams[i].wait_event(fork)
+                with torch.cuda.stream(self._layer_streams[i]):
+                    gs.append(l.gamma.rsample(None, lambdal=l.lambdal))
             else:
                 l.alpha = torch.sigmoid(l.lambdal)
                 l.gamma.alpha = l.alpha
@@ -451,6 +464,8 @@ class BayesianNetwork(nn.Module):
                 ev_grads.record(self._tau_stream)
                 for u in (tau, d_a, d_b):
                     u.record_stream(cur)
+                    for st in self._layer_streams:
+                        u.record_stream(st)
                 parts, off = [], 0
                 for a, _ in hp:
                     n = a.numel()
@@ -459,7 +474,30 @@ class BayesianNetwork(nn.Module):
                 L = len(self.layers)
                 for i, l in enumerate(self.layers):
                     l._tau_pre = (parts[i], parts[L + i], ev, ev_grads)
-        logits = self._logits(input, *gs, sample=True, medimean=False)
+        if fork is not None and os.environ.get("LBBNN_MF_STREAMS", "1") == "1":
+            # Mask, weights, bias and log-probabilities of a layer depend on parameters and noise only: each layer's on ITS
+            # stream, all three at once from the start of the step; the caller's stream carries just the linear layers and
+            # waits for one event per layer.  Autograd replays every node on its forward stream, so the log-probability
+            # backward of layer l (sampler + scalar tail: 14-23 us) runs beside the linear backward of layer l - 1 as well.
+            drawn = []
+            for i, l in enumerate(ls):
+                with torch.cuda.stream(self._layer_streams[i]):
+                    w, bias = l._draw_weights(gs[i], True, False, False, None)
+                    ev = torch.cuda.Event()
+                    ev.record(self._layer_streams[i])
+                for t in (w, bias, l.log_prior, l.log_variational_posterior):
+                    t.record_stream(cur)
+                drawn.append((w, bias, ev))
+            x = input.view(-1, self.sizes[0])
+            for i, (w, bias, ev) in enumerate(drawn):
+                cur.wait_event(ev)
+                x = _Linear.apply(x, w, bias, i < len(ls) - 1, i > 0)
+            logits = x
+        else:
+            if fork is not None:
+                for i, st in enumerate(self._layer_streams):
+                    cur.wait_stream(st)
+            logits = self._logits(input, *gs, sample=True, medimean=False)
         for l in self.layers:
             l.__dict__.pop("_tau_pre", None)
             l.__dict__.pop("_alpha_fresh", None)
